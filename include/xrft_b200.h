@@ -1,0 +1,141 @@
+/*
+ * xrft_b200 -- C-ABI of the B200-native spectral engine behind the xrft API.
+ *
+ * The reference (xgcm/xrft @ efc1c30) is pure Python and has no FFI.  Its numeric seam --
+ * the only place raw buffers are handed to third-party code -- is:
+ *
+ *   (S1) the module object returned by `_fft_module`            xrft/xrft.py:32-36
+ *        used as  fftm.fftn / rfftn / ifftn / irfftn / fftshift / ifftshift
+ *                                                              xrft/xrft.py:398-404, 439-447, 586-591, 612-621
+ *   (S2) the detrend ufuncs   `da.mean`, `scipy.signal.detrend`,
+ *        `_detrend_2d_ufunc(arr)`, `_detrend_3d_ufunc(arr)`     xrft/detrend.py:55, 65-71, 100-113, 116-138
+ *   (S3) the window product   `scipy_win_func(n, sym=False)` outer product multiply
+ *                                                              xrft/xrft.py:83-103
+ *   (S4) spectrum algebra     |F|^2, F conj(G), angle, scalings xrft/xrft.py:740-748, 825-833, 865-869
+ *   (S5) `_binned_agg(array, indices, num_bins, func=sum)`      xrft/xrft.py:877-907
+ *
+ * Every entry point below replaces one of those seams (cited per function) or fuses several
+ * of them into one pass.  Conventions: plain pointers and sizes only; all data pointers are
+ * DEVICE pointers owned by the caller (torch.Tensor.data_ptr() in the Python binding); inputs
+ * are never modified; no hidden device allocations except cached twiddle tables; `stream` is a
+ * cudaStream_t passed as void* (NULL = default stream); every function returns 0 on success or
+ * a negative XRFTB_E* code with a message retrievable by xrftb_last_error() (thread-local).
+ * Arrays are C-contiguous (row-major).  dtype: 0 = float32 / complex64, 1 = float64 / complex128.
+ * There is NO CPU fallback: without a CUDA device the compute entry points return XRFTB_ECUDA.
+ */
+#ifndef XRFT_B200_H
+#define XRFT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XRFTB_VERSION 100 /* 0.1.0 */
+
+enum { XRFTB_OK = 0, XRFTB_EINVAL = -1, XRFTB_EUNSUPPORTED = -2, XRFTB_ECUDA = -3, XRFTB_EWORKSPACE = -4 };
+enum { XRFTB_F32 = 0, XRFTB_F64 = 1 };
+/* transform kinds, numpy semantics (forward unnormalised, inverse 1/N) */
+enum { XRFTB_C2C_FWD = 0, XRFTB_C2C_INV = 1, XRFTB_R2C = 2, XRFTB_C2R = 3 };
+/* epilogue modes */
+enum {
+    XRFTB_EPI_COMPLEX = 0,    /* F * scale * ramps                         (xrft.fft,            xrft.py:446-472) */
+    XRFTB_EPI_POWER = 1,      /* |F|^2 * scale * weight                    (power_spectrum,      xrft.py:740-748) */
+    XRFTB_EPI_CROSS = 2,      /* F1 conj(F2) * scale * ramps * weight      (cross_spectrum,      xrft.py:825-833) */
+    XRFTB_EPI_PHASE = 3,      /* angle(F1 conj(F2) * ramps)                (cross_phase,         xrft.py:865-869) */
+    XRFTB_EPI_BINS_POWER = 4, /* radial-bin sum of POWER, no spectrum out  (isotropize,          xrft.py:895-906) */
+    XRFTB_EPI_BINS_CROSS = 5  /* radial-bin sum of CROSS (re,im), no spectrum out */
+};
+
+int xrftb_version(void);
+const char* xrftb_last_error(void);
+/* sm_count, compute capability and opt-in shared memory per block of the current device */
+int xrftb_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* smem_optin);
+
+/* ---- (S1) np.fft.fftn / ifftn / rfftn / irfftn --------------------------------------------------
+ * N-D transform over `axes` of a C-contiguous array.  `shape[ndim]` is the REAL-SPACE shape.
+ *   C2C_FWD/INV : in, out complex, same shape; any distinct axes.
+ *   R2C         : in real `shape`; out complex with last dim shape[ndim-1]/2+1; the last listed axis
+ *                 must be ndim-1 (the reference always moves real_dim last: xrft.py:386,396).
+ *   C2R         : in complex (last dim N/2+1), out real `shape`; same axis rule; needs a workspace of
+ *                 the input's size when naxes > 1 (input is never modified).
+ * Lengths: every power of two up to 2^14 (f32) / 2^13 (f64) on the contiguous axis (R2C/C2R: twice
+ * that), up to 8192 on strided axes; other lengths return XRFTB_EUNSUPPORTED.
+ * in == out is allowed for C2C. */
+size_t xrftb_fftn_workspace(int dtype, int kind, int ndim, const int64_t* shape, int naxes, const int* axes);
+int xrftb_fftn(const void* in, void* out, void* work, size_t work_bytes, int dtype, int kind, int ndim,
+               const int64_t* shape, int naxes, const int* axes, void* stream);
+
+/* ---- (S2) detrend -------------------------------------------------------------------------------
+ * Real input viewed as [batch][n0][n1][n2] (use 1 for unused leading dims).  `moments` receives
+ * per item {S, S0, S1, S2}: the sum and the centred first moments sum((i_d - (n_d-1)/2) * x).
+ * On a full regular grid the least-squares (hyper)plane of xrft/detrend.py:100-138 and
+ * scipy.signal.detrend (detrend.py:65-71) is   mean + sum_d S_d / V_d * (i_d - (n_d-1)/2),
+ * V_d = npts * (n_d^2 - 1) / 12  (orthogonal regressors), which detrend_apply evaluates in fp64. */
+int xrftb_moments(const void* in, double* moments, int dtype, int64_t batch, int64_t n0, int64_t n1, int64_t n2,
+                  void* stream);
+/* out = (in - trend) * w0[i0] * w1[i1] * w2[i2];  detrend: 0 none, 1 constant (da.mean, detrend.py:55),
+ * 2 linear; windows nullable (S3, xrft.py:96-103).  in == out allowed. */
+int xrftb_detrend_window(const void* in, void* out, const double* moments, int detrend, const void* w0, const void* w1,
+                         const void* w2, int dtype, int64_t batch, int64_t n0, int64_t n1, int64_t n2, void* stream);
+
+/* ---- (S4) generic spectral epilogue over up to 3 trailing transform axes --------------------------
+ * in1 (and in2 for CROSS/PHASE): complex [batch][k0][k1][k2in]; hermitian != 0 means the inputs are
+ * rfftn half spectra (k2in = k2/2+1) of REAL fields, expanded to the full k2 width on output unless
+ * keep_half.  shift[d]: fftshift on axis d (xrft.py:446-447).  ramp[d]: complex vectors indexed by the
+ * UNSHIFTED frequency index of axis d (phase ramp xrft.py:462-469; for CROSS the caller passes
+ * ramp1*conj(ramp2)), nullable.  weight: real vector on axis 2 (one-sided x2, xrft.py:673-682), nullable.
+ * out: complex (COMPLEX, CROSS) or real (POWER, PHASE), [batch][k0][k1][W], W = keep_half ? k2/2+1 : k2. */
+int xrftb_spectral_post(const void* in1, const void* in2, void* out, int dtype, int mode, int64_t batch, int64_t k0,
+                        int64_t k1, int64_t k2, int hermitian, int keep_half, const int* shift, const void* const* ramp,
+                        const void* weight, double scale, void* stream);
+
+/* ---- (S5) _binned_agg(func="sum") ---------------------------------------------------------------
+ * array: real (is_complex = 0) or complex [batch][ncell]; lut: int32 [ncell], negative = masked
+ * (the NaN mask of xrft.py:895-896); bins: float64 [batch][nbins] or [batch][nbins][2], ACCUMULATED
+ * into (caller zeroes). */
+int xrftb_binned_sum(const void* array, const int32_t* lut, double* bins, int dtype, int is_complex, int64_t batch,
+                     int64_t ncell, int nbins, void* stream);
+
+/* ---- fused hot path: detrend + window + 2-D real FFT + spectrum epilogue ---------------------------
+ * One call == power_spectrum / cross_spectrum / cross_phase / isotropic_* / fft of REAL fields over the
+ * two trailing axes (xrft.py:685-750 and callees): S2+S3 fused into the row-pass loads, S1 as an
+ * R2C row pass + strided column pass through a blocked half-spectrum intermediate, S4 (+S5) fused
+ * into the column-pass stores.  in1/in2: real [batch][ny][nx]; ny, nx powers of two,
+ * 2 <= ny <= 8192 (4096 for two-field modes), 4 <= nx <= 32768 (f32) / 16384 (f64).
+ * Output position/shape as xrftb_spectral_post with (k1, k2) = (ny, nx).
+ * BINS modes: lut int32 [ny][W] (bin of each OUTPUT cell, negative = skip), bins accumulated. */
+typedef struct {
+    int dtype;
+    int64_t batch;
+    int ny, nx;
+    const void* in1;
+    const void* in2;
+    int detrend;          /* 0 none, 1 constant, 2 linear */
+    const void* win_y;    /* T[ny] or NULL */
+    const void* win_x;    /* T[nx] or NULL */
+    int mode;             /* XRFTB_EPI_* */
+    int keep_half;        /* 1: real_dim semantics, output width nx/2+1, no x shift */
+    int shift_y, shift_x;
+    double scale;
+    const void* ramp_y;   /* complex T[ny], unshifted index, or NULL */
+    const void* ramp_x;   /* complex T[W], unshifted index, or NULL */
+    const void* weight_x; /* T[nx/2+1] or NULL (keep_half only) */
+    void* out;
+    const int32_t* lut;
+    double* bins;
+    int nbins;
+    void* work;
+    size_t work_bytes;
+} xrftb_spectrum2d_desc;
+
+/* minimum workspace (one batch item in flight) and the size that keeps `batch` items in flight */
+size_t xrftb_spectrum2d_workspace(int dtype, int ny, int nx, int two_fields, int64_t batch_in_flight);
+int xrftb_spectrum2d(const xrftb_spectrum2d_desc* desc, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XRFT_B200_H */

@@ -1,0 +1,322 @@
+"""Device backend: torch.Tensor containers in, C-ABI calls out.
+
+This is the object the host bookkeeping uses where the reference uses ``_fft_module(da)``
+(xrft/xrft.py:32-36): it exposes numpy.fft-shaped ``fftn / rfftn / ifftn / irfftn`` plus the
+detrend / window / spectrum / binning seams.  torch is plumbing only (device memory, streams);
+all arithmetic happens in xrft_b200/csrc kernels.  No CPU fallback: every function raises if
+CUDA or the library is unavailable.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib as L
+
+_REAL = {torch.float32: L.F32, torch.float64: L.F64}
+_CPLX = {torch.complex64: L.F32, torch.complex128: L.F64}
+_TO_CPLX = {torch.float32: torch.complex64, torch.float64: torch.complex128}
+_TO_REAL = {torch.complex64: torch.float32, torch.complex128: torch.float64}
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise L.XrftbError("xrft_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return L.load()
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _dev(t: torch.Tensor):
+    if not t.is_cuda:
+        raise L.XrftbError("backend expects CUDA tensors")
+    return t.contiguous()
+
+
+def _i64(vals):
+    return (C.c_int64 * len(vals))(*[int(v) for v in vals])
+
+
+def _ints(vals):
+    return (C.c_int * len(vals))(*[int(v) for v in vals])
+
+
+# ---------------------------------------------------------------------------------------------
+# (S1) numpy.fft-shaped transforms
+# ---------------------------------------------------------------------------------------------
+def _norm_axes(ndim, axes):
+    if axes is None:
+        axes = list(range(ndim))
+    axes = [a % ndim for a in axes]
+    return axes
+
+
+def fftn(x: torch.Tensor, axes=None, inverse=False) -> torch.Tensor:
+    lib = require_cuda()
+    if x.dtype in _REAL:
+        x = x.to(_TO_CPLX[x.dtype])
+    x = _dev(x)
+    axes = _norm_axes(x.ndim, axes)
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        rc = lib.xrftb_fftn(_ptr(x), _ptr(out), None, 0, _CPLX[x.dtype], L.C2C_INV if inverse else L.C2C_FWD, x.ndim,
+                            _i64(x.shape), len(axes), _ints(axes), _stream())
+    L.check(rc, "xrftb_fftn")
+    return out
+
+
+def ifftn(x, axes=None):
+    return fftn(x, axes, inverse=True)
+
+
+def rfftn(x: torch.Tensor, axes=None) -> torch.Tensor:
+    lib = require_cuda()
+    x = _dev(x)
+    if x.dtype not in _REAL:
+        raise TypeError("rfftn expects a real tensor")
+    axes = _norm_axes(x.ndim, axes)
+    if axes[-1] != x.ndim - 1:
+        raise ValueError("rfftn: the last transform axis must be the last array axis")
+    oshape = list(x.shape)
+    oshape[-1] = x.shape[-1] // 2 + 1
+    out = torch.empty(oshape, dtype=_TO_CPLX[x.dtype], device=x.device)
+    with torch.cuda.device(x.device):
+        rc = lib.xrftb_fftn(_ptr(x), _ptr(out), None, 0, _REAL[x.dtype], L.R2C, x.ndim, _i64(x.shape), len(axes),
+                            _ints(axes), _stream())
+    L.check(rc, "xrftb_fftn(R2C)")
+    return out
+
+
+def irfftn(x: torch.Tensor, axes=None) -> torch.Tensor:
+    """numpy.fft.irfftn without ``s``: output length 2*(m-1) on the last axis."""
+    lib = require_cuda()
+    x = _dev(x)
+    if x.dtype not in _CPLX:
+        x = x.to(_TO_CPLX[x.dtype])
+    axes = _norm_axes(x.ndim, axes)
+    if axes[-1] != x.ndim - 1:
+        raise ValueError("irfftn: the last transform axis must be the last array axis")
+    rshape = list(x.shape)
+    rshape[-1] = 2 * (x.shape[-1] - 1)
+    out = torch.empty(rshape, dtype=_TO_REAL[x.dtype], device=x.device)
+    dt = _CPLX[x.dtype]
+    with torch.cuda.device(x.device):
+        wb = lib.xrftb_fftn_workspace(dt, L.C2R, x.ndim, _i64(rshape), len(axes), _ints(axes))
+        work = torch.empty(max(wb, 1), dtype=torch.uint8, device=x.device) if wb else None
+        rc = lib.xrftb_fftn(_ptr(x), _ptr(out), _ptr(work), wb, dt, L.C2R, x.ndim, _i64(rshape), len(axes), _ints(axes),
+                            _stream())
+    L.check(rc, "xrftb_fftn(C2R)")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# (S2/S3) detrend + window
+# ---------------------------------------------------------------------------------------------
+def _view4(x: torch.Tensor, ntrail: int):
+    """[batch][n0][n1][n2] extents of a tensor whose last `ntrail` (<=3) axes are the core axes."""
+    core = list(x.shape[x.ndim - ntrail:])
+    while len(core) < 3:
+        core = [1] + core
+    batch = 1
+    for s in x.shape[: x.ndim - ntrail]:
+        batch *= s
+    return batch, core
+
+
+def moments(x: torch.Tensor, ntrail: int) -> torch.Tensor:
+    lib = require_cuda()
+    x = _dev(x)
+    batch, core = _view4(x, ntrail)
+    mom = torch.empty((batch, 4), dtype=torch.float64, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = lib.xrftb_moments(_ptr(x), _ptr(mom), _REAL[x.dtype], batch, core[0], core[1], core[2], _stream())
+    L.check(rc, "xrftb_moments")
+    return mom
+
+
+def detrend_window(x: torch.Tensor, ntrail: int, detrend: int, windows: Sequence[Optional[torch.Tensor]] = ()) -> torch.Tensor:
+    """(x - trend) * prod_d w_d over the last `ntrail` axes; detrend 0 none / 1 constant / 2 linear."""
+    lib = require_cuda()
+    x = _dev(x)
+    batch, core = _view4(x, ntrail)
+    mom = moments(x, ntrail) if detrend else None
+    w = [None, None, None]
+    for i, wi in enumerate(windows):
+        if wi is not None:
+            w[3 - len(windows) + i] = wi.to(device=x.device, dtype=x.dtype).contiguous()
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        rc = lib.xrftb_detrend_window(_ptr(x), _ptr(out), _ptr(mom), detrend, _ptr(w[0]), _ptr(w[1]), _ptr(w[2]),
+                                      _REAL[x.dtype], batch, core[0], core[1], core[2], _stream())
+    L.check(rc, "xrftb_detrend_window")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# (S4) generic spectral epilogue
+# ---------------------------------------------------------------------------------------------
+def spectral_post(f1: torch.Tensor, f2: Optional[torch.Tensor], mode: int, ntrail: int, full_last: int, hermitian: bool,
+                  keep_half: bool, shift: Sequence[bool], ramps: Sequence[Optional[torch.Tensor]], weight, scale: float):
+    """f1/f2: complex spectra whose last `ntrail` axes are transform axes; full_last = real-space
+    length of the last axis (needed when hermitian)."""
+    lib = require_cuda()
+    f1 = _dev(f1)
+    if f2 is not None:
+        f2 = _dev(f2)
+    kin = list(f1.shape[f1.ndim - ntrail:])
+    k = list(kin)
+    if hermitian:
+        k[-1] = full_last
+    while len(k) < 3:
+        k = [1] + k
+    batch = 1
+    for s in f1.shape[: f1.ndim - ntrail]:
+        batch *= s
+    W = (k[2] // 2 + 1) if keep_half else k[2]
+    rdt = _TO_REAL[f1.dtype]
+    odt = f1.dtype if mode in (L.EPI_COMPLEX, L.EPI_CROSS) else rdt
+    oshape = list(f1.shape[: f1.ndim - 1]) + [W]
+    out = torch.empty(oshape, dtype=odt, device=f1.device)
+    sh = [0, 0, 0]
+    rp = [None, None, None]
+    for i in range(ntrail):
+        sh[3 - ntrail + i] = 1 if shift[i] else 0
+        if ramps and ramps[i] is not None:
+            rp[3 - ntrail + i] = ramps[i].to(device=f1.device, dtype=f1.dtype).contiguous()
+    rarr = (C.c_void_p * 3)(*[r.data_ptr() if r is not None else None for r in rp])
+    wt = weight.to(device=f1.device, dtype=rdt).contiguous() if weight is not None else None
+    with torch.cuda.device(f1.device):
+        rc = lib.xrftb_spectral_post(_ptr(f1), _ptr(f2), _ptr(out), _CPLX[f1.dtype], mode, batch, k[0], k[1], k[2],
+                                     1 if hermitian else 0, 1 if keep_half else 0, _ints(sh), rarr, _ptr(wt), float(scale),
+                                     _stream())
+    L.check(rc, "xrftb_spectral_post")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# (S5) radial-bin sum
+# ---------------------------------------------------------------------------------------------
+def binned_sum(arr: torch.Tensor, lut: torch.Tensor, nbins: int, ncore: int) -> torch.Tensor:
+    """sum of `arr` over its last `ncore` axes grouped by lut (int32, same core shape, <0 = masked).
+    Returns float64 [..., nbins] (complex128 for complex input)."""
+    lib = require_cuda()
+    arr = _dev(arr)
+    lut = lut.to(device=arr.device, dtype=torch.int32).contiguous()
+    lead = list(arr.shape[: arr.ndim - ncore])
+    ncell = 1
+    for s in arr.shape[arr.ndim - ncore:]:
+        ncell *= s
+    batch = 1
+    for s in lead:
+        batch *= s
+    is_c = arr.dtype in _CPLX
+    dt = _CPLX[arr.dtype] if is_c else _REAL[arr.dtype]
+    bins = torch.zeros(lead + [nbins] + ([2] if is_c else []), dtype=torch.float64, device=arr.device)
+    with torch.cuda.device(arr.device):
+        rc = lib.xrftb_binned_sum(_ptr(arr), _ptr(lut), _ptr(bins), dt, 1 if is_c else 0, batch, ncell, nbins, _stream())
+    L.check(rc, "xrftb_binned_sum")
+    return torch.view_as_complex(bins) if is_c else bins
+
+
+# ---------------------------------------------------------------------------------------------
+# fused hot path
+# ---------------------------------------------------------------------------------------------
+_WORK = {}
+
+
+def _workspace(device, nbytes):
+    key = (device.type, device.index)
+    w = _WORK.get(key)
+    if w is None or w.numel() < nbytes:
+        _WORK[key] = w = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    return w
+
+
+def spectrum2d_supported(ny: int, nx: int, dtype, two_fields: bool) -> bool:
+    def p2(n):
+        return n >= 1 and (n & (n - 1)) == 0
+    if not (p2(ny) and p2(nx)) or ny < 2 or nx < 4:
+        return False
+    f32 = dtype in (torch.float32,)
+    max_nx = 32768 if f32 else 16384
+    max_ny = (4096 if two_fields else 8192) if f32 else (4096 if two_fields else 8192)
+    return nx <= max_nx and ny <= max_ny
+
+
+def spectrum2d(x1: torch.Tensor, x2: Optional[torch.Tensor], mode: int, detrend: int = 0, win_y=None, win_x=None,
+               keep_half=False, shift_y=False, shift_x=False, scale=1.0, ramp_y=None, ramp_x=None, weight_x=None,
+               lut=None, nbins=0, max_work_bytes: int = 2 << 30) -> torch.Tensor:
+    """Fused detrend + window + 2-D real FFT + epilogue over the last two axes of x1 (and x2)."""
+    lib = require_cuda()
+    x1 = _dev(x1)
+    rdt = x1.dtype
+    cdt = _TO_CPLX[rdt]
+    if x2 is not None:
+        x2 = _dev(x2)
+        if x2.shape != x1.shape or x2.dtype != rdt:
+            raise ValueError("spectrum2d: x1/x2 shape or dtype mismatch")
+    ny, nx = x1.shape[-2], x1.shape[-1]
+    lead = list(x1.shape[:-2])
+    batch = 1
+    for s in lead:
+        batch *= s
+    two = mode in (L.EPI_CROSS, L.EPI_PHASE, L.EPI_BINS_CROSS)
+    dev = x1.device
+    W = nx // 2 + 1 if keep_half else nx
+
+    def prep(v, dt):
+        return v.to(device=dev, dtype=dt).contiguous() if v is not None else None
+
+    win_y, win_x, weight_x = prep(win_y, rdt), prep(win_x, rdt), prep(weight_x, rdt)
+    ramp_y, ramp_x = prep(ramp_y, cdt), prep(ramp_x, cdt)
+    bins_mode = mode in (L.EPI_BINS_POWER, L.EPI_BINS_CROSS)
+    if bins_mode:
+        lut = lut.to(device=dev, dtype=torch.int32).contiguous()
+        out = torch.zeros(lead + [nbins] + ([2] if mode == L.EPI_BINS_CROSS else []), dtype=torch.float64, device=dev)
+    else:
+        odt = cdt if mode in (L.EPI_COMPLEX, L.EPI_CROSS) else rdt
+        out = torch.empty(lead + [ny, W], dtype=odt, device=dev)
+    dt = _REAL[rdt]
+    with torch.cuda.device(dev):
+        need1 = lib.xrftb_spectrum2d_workspace(dt, ny, nx, 1 if two else 0, 1)
+        if need1 == 0:
+            raise NotImplementedError(f"spectrum2d: unsupported size {ny}x{nx}")
+        needall = lib.xrftb_spectrum2d_workspace(dt, ny, nx, 1 if two else 0, batch)
+        wbytes = max(need1, min(needall, max_work_bytes))
+        work = _workspace(dev, wbytes)
+        # batch is limited to 65535 items per call by the C-ABI
+        flat1 = x1.reshape(batch, ny, nx)
+        flat2 = x2.reshape(batch, ny, nx) if x2 is not None else None
+        oflat = out.reshape(batch, -1)
+        step = 65535
+        for b0 in range(0, batch, step):
+            nb = min(step, batch - b0)
+            d = L.Spectrum2dDesc()
+            d.dtype, d.batch, d.ny, d.nx = dt, nb, ny, nx
+            d.in1 = flat1[b0:].data_ptr()
+            d.in2 = flat2[b0:].data_ptr() if flat2 is not None else None
+            d.detrend = detrend
+            d.win_y = win_y.data_ptr() if win_y is not None else None
+            d.win_x = win_x.data_ptr() if win_x is not None else None
+            d.mode, d.keep_half, d.shift_y, d.shift_x, d.scale = mode, int(keep_half), int(shift_y), int(shift_x), float(scale)
+            d.ramp_y = ramp_y.data_ptr() if ramp_y is not None else None
+            d.ramp_x = ramp_x.data_ptr() if ramp_x is not None else None
+            d.weight_x = weight_x.data_ptr() if weight_x is not None else None
+            if bins_mode:
+                d.out, d.lut, d.bins, d.nbins = None, lut.data_ptr(), oflat[b0:].data_ptr(), nbins
+            else:
+                d.out, d.lut, d.bins, d.nbins = oflat[b0:].data_ptr(), None, None, 0
+            d.work, d.work_bytes = work.data_ptr(), work.numel()
+            rc = lib.xrftb_spectrum2d(C.byref(d), _stream())
+            L.check(rc, "xrftb_spectrum2d")
+    if mode == L.EPI_BINS_CROSS:
+        return torch.view_as_complex(out)
+    return out

@@ -1,0 +1,555 @@
+// xrft_b200 -- C-ABI entry points, twiddle cache, and the bandwidth-bound elementwise kernels
+// (moments reduce, detrend+window, generic spectral epilogue, radial-bin sum).
+// See include/xrft_b200.h for the reference seams each entry point replaces.
+#include <cstdarg>
+#include <cstdio>
+#include <cmath>
+#include <map>
+#include <mutex>
+#include <vector>
+#include "../../include/xrft_b200.h"
+#include "internal.h"
+
+namespace xrftb {
+
+// ------------------------------------------------------------------------------------------------
+// errors / device
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("%s launch failed: %s", what, cudaGetErrorString(e)); return XRFTB_ECUDA; }
+    return 0;
+}
+int sm_count() {
+    static thread_local int cached_dev = -1, cached = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 1;
+    if (dev != cached_dev) {
+        cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
+        cached_dev = dev;
+    }
+    return cached > 0 ? cached : 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// twiddle cache
+// ------------------------------------------------------------------------------------------------
+static std::mutex g_tw_mu;
+static std::map<std::tuple<int, int, int, int>, void*> g_tw;  // (device, kind, dtype, log2) -> device ptr
+
+template <typename T> static const cplx<T>* get_table(int kind, int log2n) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { set_error("no CUDA device"); return nullptr; }
+    const int dt = sizeof(T) == 4 ? 0 : 1;
+    std::lock_guard<std::mutex> lk(g_tw_mu);
+    auto key = std::make_tuple(dev, kind, dt, log2n);
+    auto it = g_tw.find(key);
+    if (it != g_tw.end()) return reinterpret_cast<const cplx<T>*>(it->second);
+    const long n = 1L << log2n;
+    const long count = kind == 0 ? n : n / 2 + 1;
+    std::vector<cplx<T>> h(count);
+    for (long m = 0; m < count; ++m) {
+        // exact octant symmetries are not needed at 1e-6 / 1e-3 tolerances; double sincos is exact enough
+        double a = -2.0 * M_PI * (double)m / (double)n;
+        h[m].x = (T)cos(a);
+        h[m].y = (T)sin(a);
+    }
+    void* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, count * sizeof(cplx<T>));
+    if (e == cudaSuccess) e = cudaMemcpy(d, h.data(), count * sizeof(cplx<T>), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { set_error("twiddle table upload failed: %s", cudaGetErrorString(e)); return nullptr; }
+    g_tw[key] = d;
+    return reinterpret_cast<const cplx<T>*>(d);
+}
+template <> const cplx<float>* twiddle_fft<float>(int l) { return get_table<float>(0, l); }
+template <> const cplx<double>* twiddle_fft<double>(int l) { return get_table<double>(0, l); }
+template <> const cplx<float>* twiddle_r2c<float>(int l) { return get_table<float>(1, l); }
+template <> const cplx<double>* twiddle_r2c<double>(int l) { return get_table<double>(1, l); }
+
+// ------------------------------------------------------------------------------------------------
+// K1: moments.  item = [n0][n1][n2]; rows = n0*n1 of length n2.  fp64 accumulation.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) moments_kernel(const T* __restrict__ in, double* __restrict__ mom, long n0, long n1,
+                                                      long n2, int chunks) {
+    const long b = blockIdx.y;
+    const long rows = n0 * n1;
+    const long r0 = rows * blockIdx.x / chunks, r1 = rows * (blockIdx.x + 1) / chunks;
+    const T* base = in + b * rows * n2;
+    const double c0m = 0.5 * (double)(n0 - 1), c1m = 0.5 * (double)(n1 - 1), c2m = 0.5 * (double)(n2 - 1);
+    double S = 0, S0 = 0, S1 = 0, S2 = 0;
+    const bool vec = (sizeof(T) == 4) && (n2 % 4 == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0);
+    for (long r = r0; r < r1; ++r) {
+        const T* p = base + r * n2;
+        double s = 0, sx = 0;
+        if (vec) {
+            const float4* p4 = reinterpret_cast<const float4*>(p);
+            for (long i = threadIdx.x; i < n2 / 4; i += blockDim.x) {
+                float4 x = p4[i];
+                const float c = (float)((double)(4 * i) - c2m);  // half-integers: exact in fp32
+                float s4 = (x.x + x.y) + (x.z + x.w);
+                float w4 = (c * x.x + (c + 1.f) * x.y) + ((c + 2.f) * x.z + (c + 3.f) * x.w);
+                s += (double)s4;
+                sx += (double)w4;
+            }
+        } else {
+            for (long i = threadIdx.x; i < n2; i += blockDim.x) {
+                double x = (double)p[i];
+                s += x;
+                sx += ((double)i - c2m) * x;
+            }
+        }
+        const long i0 = r / n1, i1 = r - i0 * n1;
+        S += s;
+        S0 += ((double)i0 - c0m) * s;
+        S1 += ((double)i1 - c1m) * s;
+        S2 += sx;
+    }
+    __shared__ double red[4][8];
+    double vals[4] = {S, S0, S1, S2};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        double x = vals[k];
+        for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+        if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double x = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) x += red[threadIdx.x][w];
+        atomicAdd(mom + b * 4 + threadIdx.x, x);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// detrend + window (non-fused path and the public xrft.detrend)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) detrend_window_kernel(const T* __restrict__ in, T* __restrict__ out,
+                                                             const double* __restrict__ mom, int detrend, const T* w0,
+                                                             const T* w1, const T* w2, long n0, long n1, long n2, long total) {
+    const double npts = (double)n0 * (double)n1 * (double)n2;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long i2 = i % n2;
+        long r = i / n2;
+        const long i1 = r % n1;
+        r /= n1;
+        const long i0 = r % n0;
+        const long b = r / n0;
+        double x = (double)in[i];
+        if (detrend) {
+            const double* m = mom + b * 4;
+            double p = m[0] / npts;
+            if (detrend == 2) {
+                if (n0 > 1) p += m[1] / (npts * ((double)n0 * n0 - 1.0) / 12.0) * ((double)i0 - 0.5 * (n0 - 1));
+                if (n1 > 1) p += m[2] / (npts * ((double)n1 * n1 - 1.0) / 12.0) * ((double)i1 - 0.5 * (n1 - 1));
+                if (n2 > 1) p += m[3] / (npts * ((double)n2 * n2 - 1.0) / 12.0) * ((double)i2 - 0.5 * (n2 - 1));
+            }
+            x -= p;
+        }
+        T y = (T)x;  // the reference rounds the detrended field to the input dtype (output_dtypes=[da.dtype])
+        if (w0) y *= w0[i0];
+        if (w1) y *= w1[i1];
+        if (w2) y *= w2[i2];
+        out[i] = y;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic spectral epilogue (non-fused path)
+// ------------------------------------------------------------------------------------------------
+struct PostDesc {
+    int mode;
+    long k0, k1, k2, k2in, W;
+    int hermitian;
+    int shift[3];
+    const void* ramp[3];
+    const void* weight;
+    double scale;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) spectral_post_kernel(const cplx<T>* __restrict__ in1, const cplx<T>* __restrict__ in2,
+                                                            void* __restrict__ out, PostDesc d, long total) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long o2 = i % d.W;
+        long r = i / d.W;
+        const long o1 = r % d.k1;
+        r /= d.k1;
+        const long o0 = r % d.k0;
+        const long b = r / d.k0;
+        // o = (k + N/2) % N  <=>  k = (o + N - N/2) % N
+        const long f0 = d.shift[0] ? (o0 + d.k0 - d.k0 / 2) % d.k0 : o0;
+        const long f1 = d.shift[1] ? (o1 + d.k1 - d.k1 / 2) % d.k1 : o1;
+        const long f2 = d.shift[2] ? (o2 + d.k2 - d.k2 / 2) % d.k2 : o2;
+        long s0 = f0, s1 = f1, s2 = f2;
+        bool cj = false;
+        if (d.hermitian && f2 > d.k2 / 2) {
+            s0 = (d.k0 - f0) % d.k0; s1 = (d.k1 - f1) % d.k1; s2 = d.k2 - f2; cj = true;
+        }
+        const long src = ((b * d.k0 + s0) * d.k1 + s1) * d.k2in + s2;
+        cplx<T> a = in1[src];
+        if (cj) a.y = -a.y;
+        cplx<T> val;
+        if (d.mode == EPI_COMPLEX) val = a;
+        else if (d.mode == EPI_POWER) val = mk<T>(a.x * a.x + a.y * a.y, 0);
+        else {
+            cplx<T> g = in2[src];
+            if (cj) g.y = -g.y;
+            val = cmulc(a, g);
+        }
+        if (d.ramp[0]) val = cmul(val, reinterpret_cast<const cplx<T>*>(d.ramp[0])[f0]);
+        if (d.ramp[1]) val = cmul(val, reinterpret_cast<const cplx<T>*>(d.ramp[1])[f1]);
+        if (d.ramp[2]) val = cmul(val, reinterpret_cast<const cplx<T>*>(d.ramp[2])[f2]);
+        T sc = (T)d.scale;
+        if (d.weight) sc *= reinterpret_cast<const T*>(d.weight)[f2];
+        val = cscale(val, sc);
+        if (d.mode == EPI_COMPLEX || d.mode == EPI_CROSS) reinterpret_cast<cplx<T>*>(out)[i] = val;
+        else if (d.mode == EPI_POWER) reinterpret_cast<T*>(out)[i] = val.x;
+        else reinterpret_cast<T*>(out)[i] = xatan2(val.y, val.x);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// radial-bin sum: per-CTA fp64 histogram in shared memory, flushed with one global atomic per bin
+// ------------------------------------------------------------------------------------------------
+template <typename T, bool CPLX>
+__global__ void __launch_bounds__(256) binned_sum_kernel(const T* __restrict__ arr, const int* __restrict__ lut,
+                                                         double* __restrict__ bins, long ncell, int nbins, int chunks) {
+    extern __shared__ double hist[];
+    const long b = blockIdx.y;
+    const int width = CPLX ? 2 : 1;
+    for (int i = threadIdx.x; i < nbins * width; i += blockDim.x) hist[i] = 0.0;
+    __syncthreads();
+    const long c0 = ncell * blockIdx.x / chunks, c1 = ncell * (blockIdx.x + 1) / chunks;
+    const T* p = arr + b * ncell * width;
+    for (long i = c0 + threadIdx.x; i < c1; i += blockDim.x) {
+        const int bin = lut[i];
+        if (bin < 0) continue;
+        if (CPLX) {
+            atomicAdd(&hist[2 * bin], (double)p[2 * i]);
+            atomicAdd(&hist[2 * bin + 1], (double)p[2 * i + 1]);
+        } else {
+            atomicAdd(&hist[bin], (double)p[i]);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nbins * width; i += blockDim.x)
+        if (hist[i] != 0.0) atomicAdd(bins + b * nbins * width + i, hist[i]);
+}
+
+static inline int ilog2_exact(int64_t n) {
+    if (n < 1 || (n & (n - 1))) return -1;
+    int l = 0;
+    while ((1LL << l) < n) ++l;
+    return l;
+}
+
+static inline unsigned ew_grid(long total) {
+    long g = (total + 255) / 256;
+    long cap = (long)sm_count() * 16;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (unsigned)g;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fftn composition
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+static int fftn_impl(const void* in, void* out, void* work, size_t work_bytes, int kind, int ndim, const int64_t* shape,
+                     int naxes, const int* axes, cudaStream_t st) {
+    using C = cplx<T>;
+    // complex-array shape
+    std::vector<int64_t> cshape(shape, shape + ndim);
+    const bool real_kind = (kind == XRFTB_R2C || kind == XRFTB_C2R);
+    if (real_kind) {
+        if (axes[naxes - 1] != ndim - 1) { set_error("R2C/C2R: the last listed axis must be the last array axis"); return XRFTB_EINVAL; }
+        cshape[ndim - 1] = shape[ndim - 1] / 2 + 1;
+    }
+    double norm = 1.0;
+    for (int i = 0; i < naxes; ++i) norm *= (double)shape[axes[i]];
+    const bool inverse = (kind == XRFTB_C2C_INV || kind == XRFTB_C2R);
+    const T inv_scale = inverse ? (T)(1.0 / norm) : (T)1;
+
+    auto strided_pass = [&](const C* src, C* dst, int axis, int inv, T scale) -> int {
+        const int l2 = ilog2_exact(cshape[axis]);
+        if (l2 < 1) { set_error("fftn: axis %d length %lld is not a supported power of two", axis, (long long)cshape[axis]); return XRFTB_EUNSUPPORTED; }
+        long A = 1, B = 1;
+        for (int d = 0; d < axis; ++d) A *= cshape[d];
+        for (int d = axis + 1; d < ndim; ++d) B *= cshape[d];
+        if (B == 1) return rows_c2c<T>(src, dst, l2, A, cshape[axis], cshape[axis], inv, scale, st);
+        return cols_c2c<T>(src, dst, l2, A, B, inv, scale, st);
+    };
+
+    if (kind == XRFTB_C2C_FWD || kind == XRFTB_C2C_INV) {
+        const C* src = reinterpret_cast<const C*>(in);
+        C* dst = reinterpret_cast<C*>(out);
+        for (int i = 0; i < naxes; ++i) {
+            const bool last = (i == naxes - 1);
+            int rc = strided_pass(src, dst, axes[i], inverse ? 1 : 0, last ? inv_scale : (T)1);
+            if (rc) return rc;
+            src = dst;
+        }
+        return 0;
+    }
+    if (kind == XRFTB_R2C) {
+        const int64_t N = shape[ndim - 1];
+        const int l2 = ilog2_exact(N);
+        if (l2 < 2) { set_error("rfftn: real axis length %lld unsupported", (long long)N); return XRFTB_EUNSUPPORTED; }
+        long nseq = 1;
+        for (int d = 0; d < ndim - 1; ++d) nseq *= shape[d];
+        RowsR2CFused<T> io{};
+        io.in = reinterpret_cast<const T*>(in); io.in_row_stride = N; io.Ny = 1; io.detrend = 0; io.moments = nullptr;
+        io.wy = nullptr; io.wx = nullptr; io.out = reinterpret_cast<C*>(out); io.tileC = 0; io.out_seq_stride = N / 2 + 1;
+        int rc = rows_r2c<T>(io, l2 - 1, nseq, st);
+        if (rc) return rc;
+        C* dst = reinterpret_cast<C*>(out);
+        for (int i = 0; i < naxes - 1; ++i) {
+            rc = strided_pass(dst, dst, axes[i], 0, (T)1);
+            if (rc) return rc;
+        }
+        return 0;
+    }
+    // C2R
+    {
+        const int64_t N = shape[ndim - 1];
+        const int l2 = ilog2_exact(N);
+        if (l2 < 2) { set_error("irfftn: real axis length %lld unsupported", (long long)N); return XRFTB_EUNSUPPORTED; }
+        long nseq = 1, ctotal = 1;
+        for (int d = 0; d < ndim - 1; ++d) nseq *= shape[d];
+        for (int d = 0; d < ndim; ++d) ctotal *= cshape[d];
+        const C* src = reinterpret_cast<const C*>(in);
+        if (naxes > 1) {
+            if (work == nullptr || work_bytes < (size_t)ctotal * sizeof(C)) { set_error("irfftn: workspace too small"); return XRFTB_EWORKSPACE; }
+            C* w = reinterpret_cast<C*>(work);
+            for (int i = 0; i < naxes - 1; ++i) {
+                int rc = strided_pass(src, w, axes[i], 1, (T)1);
+                if (rc) return rc;
+                src = w;
+            }
+        }
+        return rows_c2r<T>(src, N / 2 + 1, reinterpret_cast<T*>(out), N, l2 - 1, nseq, inv_scale, st);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused 2-D real spectrum
+// ------------------------------------------------------------------------------------------------
+template <typename T> static size_t interm_bytes_per_item(int ny, int nx, int C) {
+    const long ntile = (nx / 2) / C + 1;
+    return (size_t)ntile * ny * C * sizeof(cplx<T>);
+}
+
+template <typename T>
+static int spectrum2d_impl(const xrftb_spectrum2d_desc& q, cudaStream_t st) {
+    using C_ = cplx<T>;
+    const int ly = ilog2_exact(q.ny), lx = ilog2_exact(q.nx);
+    if (ly < 1 || lx < 2) { set_error("spectrum2d: ny, nx must be powers of two (ny>=2, nx>=4), got %d x %d", q.ny, q.nx); return XRFTB_EUNSUPPORTED; }
+    const bool two = (q.mode == XRFTB_EPI_CROSS || q.mode == XRFTB_EPI_PHASE || q.mode == XRFTB_EPI_BINS_CROSS);
+    if (two && !q.in2) { set_error("spectrum2d: mode %d needs in2", q.mode); return XRFTB_EINVAL; }
+    const int C = cols_tile_width<T>(ly, two);
+    if (C < 1 || ly > TypeCfg<T>::MAX_COLS_LOG2 || lx - 1 > TypeCfg<T>::MAX_ROWS_LOG2) { set_error("spectrum2d: size %d x %d unsupported", q.ny, q.nx); return XRFTB_EUNSUPPORTED; }
+    if (q.shift_x && q.keep_half) { set_error("spectrum2d: shift_x is incompatible with keep_half"); return XRFTB_EINVAL; }
+    const int fields = two ? 2 : 1;
+    const long ntile = (q.nx / 2) / C + 1;
+    const size_t per_item = interm_bytes_per_item<T>(q.ny, q.nx, C);
+    const size_t mom_bytes = (size_t)q.batch * fields * 4 * sizeof(double);
+    const size_t mom_region = (mom_bytes + 255) & ~(size_t)255;
+    if (!q.work || q.work_bytes < mom_region + per_item * fields) { set_error("spectrum2d: workspace too small (%zu < %zu)", q.work_bytes, mom_region + per_item * fields); return XRFTB_EWORKSPACE; }
+    long bchunk = (long)((q.work_bytes - mom_region) / (per_item * fields));
+    if (bchunk > q.batch) bchunk = q.batch;
+    double* mom = reinterpret_cast<double*>(q.work);
+    C_* interm = reinterpret_cast<C_*>(reinterpret_cast<char*>(q.work) + mom_region);
+    const long item = (long)q.ny * q.nx;
+    const T* ins[2] = {reinterpret_cast<const T*>(q.in1), reinterpret_cast<const T*>(q.in2)};
+
+    if (q.detrend) {
+        cudaError_t e = cudaMemsetAsync(mom, 0, mom_bytes, st);
+        if (e != cudaSuccess) { set_error("memset: %s", cudaGetErrorString(e)); return XRFTB_ECUDA; }
+        for (int f = 0; f < fields; ++f) {
+            int chunks = (int)((2L * sm_count() + q.batch - 1) / q.batch);
+            if (chunks < 1) chunks = 1;
+            if (chunks > q.ny) chunks = q.ny;
+            dim3 grid(chunks, (unsigned)q.batch);
+            moments_kernel<T><<<grid, 256, 0, st>>>(ins[f], mom + (size_t)f * q.batch * 4, 1, q.ny, q.nx, chunks);
+            if (int rc = check_launch("moments_kernel")) return rc;
+        }
+    }
+    EpilogueDesc d{};
+    d.mode = q.mode; d.Ny = q.ny; d.Nx = q.nx; d.full = q.keep_half ? 0 : 1; d.shift_y = q.shift_y; d.shift_x = q.shift_x;
+    d.scale = q.scale; d.ramp_y = q.ramp_y; d.ramp_x = q.ramp_x; d.weight_x = q.weight_x; d.lut = q.lut; d.nbins = q.nbins;
+    const long W = q.keep_half ? q.nx / 2 + 1 : q.nx;
+    const bool bins_mode = (q.mode == XRFTB_EPI_BINS_POWER || q.mode == XRFTB_EPI_BINS_CROSS);
+    const size_t out_elem = (q.mode == XRFTB_EPI_COMPLEX || q.mode == XRFTB_EPI_CROSS) ? sizeof(C_) : sizeof(T);
+    for (long b0 = 0; b0 < q.batch; b0 += bchunk) {
+        const long nb = (q.batch - b0 < bchunk) ? q.batch - b0 : bchunk;
+        for (int f = 0; f < fields; ++f) {
+            RowsR2CFused<T> io{};
+            io.in = ins[f] + b0 * item; io.in_row_stride = q.nx; io.Ny = q.ny; io.detrend = q.detrend;
+            io.moments = mom + ((size_t)f * q.batch + b0) * 4;
+            io.wy = reinterpret_cast<const T*>(q.win_y); io.wx = reinterpret_cast<const T*>(q.win_x);
+            io.out = interm + (size_t)f * bchunk * (per_item / sizeof(C_)); io.tileC = C; io.out_seq_stride = 0;
+            if (int rc = rows_r2c<T>(io, lx - 1, nb * q.ny, st)) return rc;
+        }
+        d.out = bins_mode ? nullptr : reinterpret_cast<char*>(q.out) + (size_t)b0 * q.ny * W * out_elem;
+        d.bins = bins_mode ? q.bins + (size_t)b0 * q.nbins * (q.mode == XRFTB_EPI_BINS_CROSS ? 2 : 1) : nullptr;
+        const C_* i1 = interm;
+        const C_* i2 = two ? interm + (size_t)bchunk * (per_item / sizeof(C_)) : nullptr;
+        if (int rc = cols_fused<T>(i1, i2, ly, nb * ntile, (int)ntile, d, st)) return rc;
+    }
+    return 0;
+}
+
+}  // namespace xrftb
+
+using namespace xrftb;
+
+extern "C" {
+
+int xrftb_version(void) { return XRFTB_VERSION; }
+const char* xrftb_last_error(void) { return g_err; }
+
+int xrftb_device_info(int* sms, int* major, int* minor, size_t* smem_optin) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) { set_error("cudaGetDevice: %s", cudaGetErrorString(e)); return XRFTB_ECUDA; }
+    cudaDeviceProp p;
+    e = cudaGetDeviceProperties(&p, dev);
+    if (e != cudaSuccess) { set_error("cudaGetDeviceProperties: %s", cudaGetErrorString(e)); return XRFTB_ECUDA; }
+    if (sms) *sms = p.multiProcessorCount;
+    if (major) *major = p.major;
+    if (minor) *minor = p.minor;
+    if (smem_optin) *smem_optin = p.sharedMemPerBlockOptin;
+    return 0;
+}
+
+size_t xrftb_fftn_workspace(int dtype, int kind, int ndim, const int64_t* shape, int naxes, const int*) {
+    if (kind != XRFTB_C2R || naxes <= 1) return 0;
+    size_t n = 1;
+    for (int d = 0; d < ndim - 1; ++d) n *= (size_t)shape[d];
+    n *= (size_t)(shape[ndim - 1] / 2 + 1);
+    return n * (dtype == XRFTB_F32 ? 8 : 16);
+}
+
+int xrftb_fftn(const void* in, void* out, void* work, size_t work_bytes, int dtype, int kind, int ndim, const int64_t* shape,
+               int naxes, const int* axes, void* stream) {
+    if (!in || !out || ndim < 1 || ndim > 8 || naxes < 1 || naxes > ndim) { set_error("fftn: bad arguments"); return XRFTB_EINVAL; }
+    for (int i = 0; i < naxes; ++i) {
+        if (axes[i] < 0 || axes[i] >= ndim) { set_error("fftn: axis out of range"); return XRFTB_EINVAL; }
+        for (int j = 0; j < i; ++j)
+            if (axes[j] == axes[i]) { set_error("fftn: repeated axis"); return XRFTB_EINVAL; }
+    }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (dtype == XRFTB_F32) return fftn_impl<float>(in, out, work, work_bytes, kind, ndim, shape, naxes, axes, st);
+    if (dtype == XRFTB_F64) return fftn_impl<double>(in, out, work, work_bytes, kind, ndim, shape, naxes, axes, st);
+    set_error("fftn: bad dtype %d", dtype);
+    return XRFTB_EINVAL;
+}
+
+int xrftb_moments(const void* in, double* moments, int dtype, int64_t batch, int64_t n0, int64_t n1, int64_t n2, void* stream) {
+    if (!in || !moments || batch < 1 || n0 < 1 || n1 < 1 || n2 < 1) { set_error("moments: bad arguments"); return XRFTB_EINVAL; }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemsetAsync(moments, 0, (size_t)batch * 4 * sizeof(double), st);
+    if (e != cudaSuccess) { set_error("memset: %s", cudaGetErrorString(e)); return XRFTB_ECUDA; }
+    long rows = n0 * n1;
+    int chunks = (int)((2L * sm_count() + batch - 1) / batch);
+    if (chunks < 1) chunks = 1;
+    if (chunks > rows) chunks = (int)rows;
+    if (batch > 65535) { set_error("moments: batch > 65535 unsupported"); return XRFTB_EUNSUPPORTED; }
+    dim3 grid(chunks, (unsigned)batch);
+    if (dtype == XRFTB_F32) moments_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(in), moments, n0, n1, n2, chunks);
+    else if (dtype == XRFTB_F64) moments_kernel<double><<<grid, 256, 0, st>>>(reinterpret_cast<const double*>(in), moments, n0, n1, n2, chunks);
+    else { set_error("moments: bad dtype"); return XRFTB_EINVAL; }
+    return check_launch("moments_kernel");
+}
+
+int xrftb_detrend_window(const void* in, void* out, const double* moments, int detrend, const void* w0, const void* w1,
+                         const void* w2, int dtype, int64_t batch, int64_t n0, int64_t n1, int64_t n2, void* stream) {
+    if (!in || !out || (detrend && !moments)) { set_error("detrend_window: bad arguments"); return XRFTB_EINVAL; }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const long total = batch * n0 * n1 * n2;
+    if (dtype == XRFTB_F32)
+        detrend_window_kernel<float><<<ew_grid(total), 256, 0, st>>>(reinterpret_cast<const float*>(in), reinterpret_cast<float*>(out), moments, detrend,
+            reinterpret_cast<const float*>(w0), reinterpret_cast<const float*>(w1), reinterpret_cast<const float*>(w2), n0, n1, n2, total);
+    else if (dtype == XRFTB_F64)
+        detrend_window_kernel<double><<<ew_grid(total), 256, 0, st>>>(reinterpret_cast<const double*>(in), reinterpret_cast<double*>(out), moments, detrend,
+            reinterpret_cast<const double*>(w0), reinterpret_cast<const double*>(w1), reinterpret_cast<const double*>(w2), n0, n1, n2, total);
+    else { set_error("detrend_window: bad dtype"); return XRFTB_EINVAL; }
+    return check_launch("detrend_window_kernel");
+}
+
+int xrftb_spectral_post(const void* in1, const void* in2, void* out, int dtype, int mode, int64_t batch, int64_t k0, int64_t k1,
+                        int64_t k2, int hermitian, int keep_half, const int* shift, const void* const* ramp, const void* weight,
+                        double scale, void* stream) {
+    if (!in1 || !out || mode < 0 || mode > XRFTB_EPI_PHASE) { set_error("spectral_post: bad arguments"); return XRFTB_EINVAL; }
+    if ((mode == XRFTB_EPI_CROSS || mode == XRFTB_EPI_PHASE) && !in2) { set_error("spectral_post: in2 required"); return XRFTB_EINVAL; }
+    if (keep_half && !hermitian) { set_error("spectral_post: keep_half requires hermitian input"); return XRFTB_EINVAL; }
+    PostDesc d{};
+    d.mode = mode; d.k0 = k0; d.k1 = k1; d.k2 = k2; d.k2in = hermitian ? k2 / 2 + 1 : k2; d.W = keep_half ? k2 / 2 + 1 : k2;
+    d.hermitian = (hermitian && !keep_half) ? 1 : 0;
+    for (int i = 0; i < 3; ++i) { d.shift[i] = shift ? shift[i] : 0; d.ramp[i] = ramp ? ramp[i] : nullptr; }
+    if (keep_half && d.shift[2]) { set_error("spectral_post: cannot shift the half axis"); return XRFTB_EINVAL; }
+    d.weight = weight; d.scale = scale;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const long total = batch * k0 * k1 * d.W;
+    if (dtype == XRFTB_F32)
+        spectral_post_kernel<float><<<ew_grid(total), 256, 0, st>>>(reinterpret_cast<const float2*>(in1), reinterpret_cast<const float2*>(in2), out, d, total);
+    else if (dtype == XRFTB_F64)
+        spectral_post_kernel<double><<<ew_grid(total), 256, 0, st>>>(reinterpret_cast<const double2*>(in1), reinterpret_cast<const double2*>(in2), out, d, total);
+    else { set_error("spectral_post: bad dtype"); return XRFTB_EINVAL; }
+    return check_launch("spectral_post_kernel");
+}
+
+int xrftb_binned_sum(const void* array, const int32_t* lut, double* bins, int dtype, int is_complex, int64_t batch, int64_t ncell,
+                     int nbins, void* stream) {
+    if (!array || !lut || !bins || nbins < 1 || nbins > 2048 || batch < 1 || batch > 65535) { set_error("binned_sum: bad arguments (nbins<=2048, batch<=65535)"); return XRFTB_EINVAL; }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    int chunks = (int)((4L * sm_count() + batch - 1) / batch);
+    if (chunks < 1) chunks = 1;
+    if ((long)chunks * 1024 > ncell) chunks = (int)((ncell + 1023) / 1024);
+    dim3 grid(chunks, (unsigned)batch);
+    const size_t smem = (size_t)nbins * (is_complex ? 2 : 1) * sizeof(double);
+    if (dtype == XRFTB_F32) {
+        if (is_complex) binned_sum_kernel<float, true><<<grid, 256, smem, st>>>(reinterpret_cast<const float*>(array), lut, bins, ncell, nbins, chunks);
+        else binned_sum_kernel<float, false><<<grid, 256, smem, st>>>(reinterpret_cast<const float*>(array), lut, bins, ncell, nbins, chunks);
+    } else if (dtype == XRFTB_F64) {
+        if (is_complex) binned_sum_kernel<double, true><<<grid, 256, smem, st>>>(reinterpret_cast<const double*>(array), lut, bins, ncell, nbins, chunks);
+        else binned_sum_kernel<double, false><<<grid, 256, smem, st>>>(reinterpret_cast<const double*>(array), lut, bins, ncell, nbins, chunks);
+    } else { set_error("binned_sum: bad dtype"); return XRFTB_EINVAL; }
+    return check_launch("binned_sum_kernel");
+}
+
+size_t xrftb_spectrum2d_workspace(int dtype, int ny, int nx, int two_fields, int64_t batch_in_flight) {
+    const int ly = ilog2_exact(ny);
+    if (ly < 1 || nx < 4) return 0;
+    const int C = dtype == XRFTB_F32 ? cols_tile_width<float>(ly, two_fields != 0) : cols_tile_width<double>(ly, two_fields != 0);
+    if (C < 1) return 0;
+    const size_t per_item = dtype == XRFTB_F32 ? interm_bytes_per_item<float>(ny, nx, C) : interm_bytes_per_item<double>(ny, nx, C);
+    const int fields = two_fields ? 2 : 1;
+    if (batch_in_flight < 1) batch_in_flight = 1;
+    // moments region is sized for up to 65536 items x 2 fields
+    return ((size_t)65536 * 2 * 4 * sizeof(double)) + per_item * fields * (size_t)batch_in_flight + 256;
+}
+
+int xrftb_spectrum2d(const xrftb_spectrum2d_desc* q, void* stream) {
+    if (!q || !q->in1 || q->batch < 1) { set_error("spectrum2d: bad descriptor"); return XRFTB_EINVAL; }
+    if (q->batch > 65535) { set_error("spectrum2d: batch > 65535 per call unsupported (split the call)"); return XRFTB_EUNSUPPORTED; }
+    const bool bins_mode = (q->mode == XRFTB_EPI_BINS_POWER || q->mode == XRFTB_EPI_BINS_CROSS);
+    if (bins_mode && (!q->lut || !q->bins || q->nbins < 1)) { set_error("spectrum2d: bins mode needs lut/bins/nbins"); return XRFTB_EINVAL; }
+    if (!bins_mode && !q->out) { set_error("spectrum2d: out is NULL"); return XRFTB_EINVAL; }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (q->dtype == XRFTB_F32) return spectrum2d_impl<float>(*q, st);
+    if (q->dtype == XRFTB_F64) return spectrum2d_impl<double>(*q, st);
+    set_error("spectrum2d: bad dtype %d", q->dtype);
+    return XRFTB_EINVAL;
+}
+
+}  // extern "C"

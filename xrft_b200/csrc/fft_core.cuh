@@ -1,0 +1,229 @@
+// xrft_b200 -- in-CTA Stockham auto-sort FFT engine for sm_100a.
+//
+// Replaces the arithmetic that the reference delegates to numpy's pocketfft
+// (np.fft.fftn / rfftn / ifftn / irfftn, call sites xrft/xrft.py:398-404,
+// 439-447, 586-591, 612-621).  No cuFFT, no Triton.
+//
+// Model: a sequence of L = 2^k complex points is owned by NT = L/E threads, each
+// holding E points in registers: v[q] = x[u + q*NT].  One stage = (twiddle,
+// radix-R butterflies in registers, R <= E) -> scatter to shared memory at the
+// Stockham auto-sort position -> gather v[q] = y[u + q*NT].  The register
+// residency makes the exchange in-place (one smem buffer, two barriers/stage).
+// Radices: E, E, ..., 2^rem (first stage has Ns = 1, i.e. no twiddles).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <type_traits>
+
+namespace xrftb {
+
+template <typename T> struct cplx_of;
+template <> struct cplx_of<float> { using type = float2; };
+template <> struct cplx_of<double> { using type = double2; };
+template <typename T> using cplx = typename cplx_of<T>::type;
+
+template <typename T> __host__ __device__ __forceinline__ cplx<T> mk(T x, T y) { cplx<T> r; r.x = x; r.y = y; return r; }
+
+template <typename C> __device__ __forceinline__ C cadd(C a, C b) { C r; r.x = a.x + b.x; r.y = a.y + b.y; return r; }
+template <typename C> __device__ __forceinline__ C csub(C a, C b) { C r; r.x = a.x - b.x; r.y = a.y - b.y; return r; }
+template <typename C> __device__ __forceinline__ C cmul(C a, C b) {
+    C r; r.x = a.x * b.x - a.y * b.y; r.y = a.x * b.y + a.y * b.x; return r;
+}
+// a * conj(b)
+template <typename C> __device__ __forceinline__ C cmulc(C a, C b) {
+    C r; r.x = a.x * b.x + a.y * b.y; r.y = a.y * b.x - a.x * b.y; return r;
+}
+template <typename C> __device__ __forceinline__ C cconj(C a) { a.y = -a.y; return a; }
+template <typename C> __device__ __forceinline__ C mul_mi(C a) { C r; r.x = a.y; r.y = -a.x; return r; }  // * (-i)
+template <typename C> __device__ __forceinline__ C mul_pi(C a) { C r; r.x = -a.y; r.y = a.x; return r; }  // * (+i)
+template <typename C, typename T> __device__ __forceinline__ C cscale(C a, T s) { a.x *= s; a.y *= s; return a; }
+
+// ---------------------------------------------------------------------------------------------
+// register radix kernels, forward sign (exp(-i..)), natural-order output, in place
+// ---------------------------------------------------------------------------------------------
+template <typename C> __device__ __forceinline__ void fft2(C& a, C& b) { C t = a; a = cadd(t, b); b = csub(t, b); }
+
+template <typename C> __device__ __forceinline__ void fft4(C& v0, C& v1, C& v2, C& v3) {
+    C a0 = cadd(v0, v2), a1 = csub(v0, v2), a2 = cadd(v1, v3), a3 = mul_mi(csub(v1, v3));
+    v0 = cadd(a0, a2); v1 = cadd(a1, a3); v2 = csub(a0, a2); v3 = csub(a1, a3);
+}
+
+template <typename T, typename C> __device__ __forceinline__ void fft8(C* a) {
+    const T s = (T)0.70710678118654752440;
+    C e0 = a[0], e1 = a[2], e2 = a[4], e3 = a[6];
+    C o0 = a[1], o1 = a[3], o2 = a[5], o3 = a[7];
+    fft4(e0, e1, e2, e3);
+    fft4(o0, o1, o2, o3);
+    C t1; t1.x = (o1.x + o1.y) * s; t1.y = (o1.y - o1.x) * s;      // * w8^1
+    C t2 = mul_mi(o2);                                              // * w8^2
+    C t3; t3.x = (o3.y - o3.x) * s; t3.y = -(o3.x + o3.y) * s;     // * w8^3
+    a[0] = cadd(e0, o0); a[4] = csub(e0, o0);
+    a[1] = cadd(e1, t1); a[5] = csub(e1, t1);
+    a[2] = cadd(e2, t2); a[6] = csub(e2, t2);
+    a[3] = cadd(e3, t3); a[7] = csub(e3, t3);
+}
+
+template <typename T, typename C> __device__ __forceinline__ void fft16(C* a) {
+    const T c1 = (T)0.92387953251128675613, s1 = (T)0.38268343236508977173, s = (T)0.70710678118654752440;
+    C e[8], o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { e[i] = a[2 * i]; o[i] = a[2 * i + 1]; }
+    fft8<T>(e);
+    fft8<T>(o);
+    C t;
+    // w16^k = (cos(pi k/8), -sin(pi k/8))
+    t = o[1]; o[1].x = t.x * c1 + t.y * s1; o[1].y = t.y * c1 - t.x * s1;
+    t = o[2]; o[2].x = (t.x + t.y) * s;     o[2].y = (t.y - t.x) * s;
+    t = o[3]; o[3].x = t.x * s1 + t.y * c1; o[3].y = t.y * s1 - t.x * c1;
+    o[4] = mul_mi(o[4]);
+    t = o[5]; o[5].x = -t.x * s1 + t.y * c1; o[5].y = -t.y * s1 - t.x * c1;
+    t = o[6]; o[6].x = (t.y - t.x) * s;      o[6].y = -(t.x + t.y) * s;
+    t = o[7]; o[7].x = -t.x * c1 + t.y * s1; o[7].y = -t.y * c1 - t.x * s1;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a[i] = cadd(e[i], o[i]); a[i + 8] = csub(e[i], o[i]); }
+}
+
+template <typename T, int R> struct Radix;
+template <typename T> struct Radix<T, 1> { static __device__ __forceinline__ void run(cplx<T>*) {} };
+template <typename T> struct Radix<T, 2> { static __device__ __forceinline__ void run(cplx<T>* a) { fft2(a[0], a[1]); } };
+template <typename T> struct Radix<T, 4> { static __device__ __forceinline__ void run(cplx<T>* a) { fft4(a[0], a[1], a[2], a[3]); } };
+template <typename T> struct Radix<T, 8> { static __device__ __forceinline__ void run(cplx<T>* a) { fft8<T>(a); } };
+template <typename T> struct Radix<T, 16> { static __device__ __forceinline__ void run(cplx<T>* a) { fft16<T>(a); } };
+
+// ---------------------------------------------------------------------------------------------
+// twiddles: table tw[m] = exp(-2 pi i m / L), m in [0, L), host-computed in double.
+// Loads w^1, w^2, w^4, w^8 (exact table entries) and derives the rest by <= 2 products.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int R>
+__device__ __forceinline__ void apply_twiddles(cplx<T>* a, const cplx<T>* __restrict__ tw, int idx) {
+    using C = cplx<T>;
+    if constexpr (R >= 2) {
+        C w1 = __ldg(tw + idx);
+        a[1] = cmul(a[1], w1);
+        if constexpr (R >= 4) {
+            C w2 = __ldg(tw + 2 * idx);
+            C w3 = cmul(w1, w2);
+            a[2] = cmul(a[2], w2);
+            a[3] = cmul(a[3], w3);
+            if constexpr (R >= 8) {
+                C w4 = __ldg(tw + 4 * idx);
+                a[4] = cmul(a[4], w4);
+                a[5] = cmul(a[5], cmul(w1, w4));
+                a[6] = cmul(a[6], cmul(w2, w4));
+                C w7 = cmul(w3, w4);
+                a[7] = cmul(a[7], w7);
+                if constexpr (R >= 16) {
+                    C w8 = __ldg(tw + 8 * idx);
+                    a[8] = cmul(a[8], w8);
+                    a[9] = cmul(a[9], cmul(w1, w8));
+                    a[10] = cmul(a[10], cmul(w2, w8));
+                    a[11] = cmul(a[11], cmul(w3, w8));
+                    C w12 = cmul(w4, w8);
+                    a[12] = cmul(a[12], w12);
+                    a[13] = cmul(a[13], cmul(w1, w12));
+                    a[14] = cmul(a[14], cmul(w2, w12));
+                    a[15] = cmul(a[15], cmul(w3, w12));
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// shared-memory view.  Logical point o of sequence-slot `s` lives at
+//     base + (pad(o) * SI + s_off)          pad(o) = o + (o >> LOGPAD)
+// rows (kernel A):   SI = 1, s_off = seq * seq_stride
+// columns (kernel B): SI = C (tile width), s_off = column within the tile
+// The pad (one point per first-stage radix) removes the stride-R bank conflicts of the
+// Ns = 1 scatter.
+// ---------------------------------------------------------------------------------------------
+template <int LOGPAD> __host__ __device__ __forceinline__ int padded(int o) { return o + (o >> LOGPAD); }
+
+template <int LOG2L, int LOGE> struct Geometry {
+    static constexpr int L = 1 << LOG2L;
+    static constexpr int E = 1 << LOGE;
+    static constexpr int NT = L / E;
+    static constexpr int LOGPAD = LOGE;              // first radix == E
+    static constexpr int LPAD = L + (L >> LOGPAD);   // padded length in points
+    static constexpr int NSTAGES = (LOG2L + LOGE - 1) / LOGE;
+    static constexpr int LOGR_LAST = LOG2L - (NSTAGES - 1) * LOGE;  // in (0, LOGE]
+    static constexpr int LOGNS_LAST = (NSTAGES - 1) * LOGE;
+};
+
+// v[g + t*G] after the LAST stage is output point final_index(u, g, t)
+template <int LOG2L, int LOGE>
+__device__ __forceinline__ int final_index(int u, int g, int t) {
+    using G_ = Geometry<LOG2L, LOGE>;
+    constexpr int R = 1 << G_::LOGR_LAST;
+    constexpr int Ns = 1 << G_::LOGNS_LAST;
+    int j = u + g * G_::NT;
+    int jm = j & (Ns - 1);
+    return (j - jm) * R + jm + t * Ns;
+}
+
+template <typename T, int LOG2L, int LOGE, int LOGNS>
+struct Stages {
+    using G_ = Geometry<LOG2L, LOGE>;
+    static constexpr int E = G_::E;
+    static constexpr int REM = LOG2L - LOGNS;
+    static constexpr int LOGR = REM >= LOGE ? LOGE : REM;
+    static constexpr int R = 1 << LOGR;
+    static constexpr int G = E / R;
+    static constexpr int Ns = 1 << LOGNS;
+    static constexpr bool LAST = (LOGNS + LOGR == LOG2L);
+
+    // sm: smem base of this thread's sequence slot (already offset by s_off); SI: point stride.
+    template <int NSEQV>
+    static __device__ __forceinline__ void run(cplx<T> (&v)[NSEQV][E], int u, cplx<T>* sm, int SI, int vstride,
+                                               const cplx<T>* __restrict__ tw) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            int j = u + g * G_::NT;
+            int jm = j & (Ns - 1);
+#pragma unroll
+            for (int s = 0; s < NSEQV; ++s) {
+                cplx<T> a[R];
+#pragma unroll
+                for (int t = 0; t < R; ++t) a[t] = v[s][g + t * G];
+                if constexpr (LOGNS > 0) apply_twiddles<T, R>(a, tw, jm * (G_::L / (Ns * R)));
+                Radix<T, R>::run(a);
+#pragma unroll
+                for (int t = 0; t < R; ++t) v[s][g + t * G] = a[t];
+            }
+        }
+        if constexpr (!LAST) {
+            // scatter (auto-sort position), barrier, gather
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                int j = u + g * G_::NT;
+                int jm = j & (Ns - 1);
+                int o0 = (j - jm) * R + jm;
+#pragma unroll
+                for (int t = 0; t < R; ++t) {
+                    int p = padded<G_::LOGPAD>(o0 + t * Ns) * SI;
+#pragma unroll
+                    for (int s = 0; s < NSEQV; ++s) sm[p + s * vstride] = v[s][g + t * G];
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < E; ++q) {
+                int p = padded<G_::LOGPAD>(u + q * G_::NT) * SI;
+#pragma unroll
+                for (int s = 0; s < NSEQV; ++s) v[s][q] = sm[p + s * vstride];
+            }
+            __syncthreads();
+            Stages<T, LOG2L, LOGE, LOGNS + LOGR>::template run<NSEQV>(v, u, sm, SI, vstride, tw);
+        }
+    }
+};
+
+// whole forward FFT of the register-resident sequence(s); results stay in registers, mapped by
+// final_index<LOG2L, LOGE>(u, g, t) with g in [0, E/R_last), t in [0, R_last).
+template <typename T, int LOG2L, int LOGE, int NSEQV>
+__device__ __forceinline__ void block_fft(cplx<T> (&v)[NSEQV][1 << LOGE], int u, cplx<T>* sm, int SI, int vstride,
+                                          const cplx<T>* __restrict__ tw) {
+    Stages<T, LOG2L, LOGE, 0>::template run<NSEQV>(v, u, sm, SI, vstride, tw);
+}
+
+}  // namespace xrftb

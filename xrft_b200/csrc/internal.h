@@ -1,0 +1,40 @@
+// xrft_b200 -- internal C++ interface between the C-ABI (api.cu) and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "fft_kernels.cuh"
+
+namespace xrftb {
+
+void set_error(const char* fmt, ...);
+int sm_count();
+int check_launch(const char* what);
+
+// device-resident twiddle tables, computed in double on the host, cached per (device, length)
+template <typename T> const cplx<T>* twiddle_fft(int log2L);  // exp(-2 pi i m / L), m in [0, L)
+template <typename T> const cplx<T>* twiddle_r2c(int log2N);  // exp(-2 pi i k / N), k in [0, N/2]
+
+template <typename T> struct TypeCfg;
+template <> struct TypeCfg<float> { static constexpr int LOGE = 4; static constexpr int V = 2; static constexpr int TILE_POINTS = 16384; static constexpr int CMAX = 16; static constexpr int MAX_ROWS_LOG2 = 14; static constexpr int MAX_COLS_LOG2 = 13; };
+template <> struct TypeCfg<double> { static constexpr int LOGE = 3; static constexpr int V = 1; static constexpr int TILE_POINTS = 8192; static constexpr int CMAX = 8; static constexpr int MAX_ROWS_LOG2 = 13; static constexpr int MAX_COLS_LOG2 = 13; };
+
+// tile width (columns per CTA) of the strided pass for a given length
+template <typename T> inline int cols_tile_width(int log2L, bool two_fields) {
+    int c = TypeCfg<T>::TILE_POINTS >> log2L;
+    if (c > TypeCfg<T>::CMAX) c = TypeCfg<T>::CMAX;
+    if (two_fields) c >>= 1;
+    return c;  // 0 => unsupported
+}
+
+template <typename T> int rows_c2c(const cplx<T>* in, cplx<T>* out, int log2L, long nseq, long in_stride, long out_stride,
+                                   int inverse, T scale, cudaStream_t st);
+template <typename T> int rows_r2c(RowsR2CFused<T> io, int log2M, long nseq, cudaStream_t st);
+template <typename T> int rows_c2r(const cplx<T>* in, long in_stride, T* out, long out_stride, int log2M, long nseq, T scale,
+                                   cudaStream_t st);
+template <typename T> int cols_c2c(const cplx<T>* in, cplx<T>* out, int log2L, long A, long B, int inverse, T scale,
+                                   cudaStream_t st);
+template <typename T> int cols_fused(const cplx<T>* in1, const cplx<T>* in2, int log2L, long ntiles_total, int ntile,
+                                     const EpilogueDesc& d, cudaStream_t st);
+
+}  // namespace xrftb

@@ -1,0 +1,65 @@
+// xrft_b200 -- templated launchers (included by the per-dtype instantiation units).
+#pragma once
+#include "internal.h"
+
+namespace xrftb {
+
+template <class Kern>
+static inline int prepare_kernel(Kern kern, int threads, size_t smem, int* occ_cache) {
+    if (*occ_cache < 0) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(e)); return -3; }
+        int occ = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem);
+        if (e != cudaSuccess || occ < 1) { set_error("occupancy query failed (threads=%d smem=%zu): %s", threads, smem, cudaGetErrorString(e)); return -3; }
+        *occ_cache = occ;
+    }
+    return 0;
+}
+
+constexpr int cmin(int a, int b) { return a < b ? a : b; }
+constexpr int cmax(int a, int b) { return a > b ? a : b; }
+
+// sequences per CTA on the contiguous-axis pass
+template <int LOG2L, int LOGE> constexpr int rows_seq_generic() { return cmax(1, cmin(128, 256 >> (LOG2L - LOGE))); }
+template <int LOG2L, int LOGE> constexpr int rows_seq_fused() { return cmax(rows_seq_generic<LOG2L, LOGE>(), cmax(1, cmin(4, 512 >> (LOG2L - LOGE)))); }
+
+template <typename T, int LOG2L, int SEQ, class IO>
+static int launch_rows(const IO& io, long nseq, cudaStream_t st) {
+    constexpr int LOGE = cmin(TypeCfg<T>::LOGE, LOG2L);
+    using G_ = Geometry<LOG2L, LOGE>;
+    auto kern = rows_kernel<T, LOG2L, LOGE, SEQ, IO>;
+    constexpr int threads = G_::NT * SEQ;
+    constexpr size_t smem = (size_t)SEQ * (G_::LPAD + IO::kSeqSkew) * sizeof(cplx<T>);
+    static int occ = -1;
+    if (int rc = prepare_kernel(kern, threads, smem, &occ)) return rc;
+    const cplx<T>* tw = twiddle_fft<T>(LOG2L);
+    if (!tw) return -3;
+    long ngroups = (nseq + SEQ - 1) / SEQ;
+    long grid = (long)sm_count() * occ;
+    if (grid > ngroups) grid = ngroups;
+    if (grid < 1) return 0;
+    kern<<<(unsigned)grid, threads, smem, st>>>(io, tw, nseq);
+    return check_launch("rows_kernel");
+}
+
+template <typename T, int LOG2L, int C, class IO>
+static int launch_cols(const IO& io, long ntiles, cudaStream_t st) {
+    constexpr int LOGE = cmin(TypeCfg<T>::LOGE, LOG2L);
+    constexpr int V = cmin(TypeCfg<T>::V, C);
+    using G_ = Geometry<LOG2L, LOGE>;
+    auto kern = cols_kernel<T, LOG2L, LOGE, C, V, IO>;
+    constexpr int threads = G_::NT * (C / V);
+    constexpr size_t smem = (size_t)G_::LPAD * C * sizeof(cplx<T>) + (IO::kTwoFields ? (size_t)G_::L * C * sizeof(cplx<T>) : 0);
+    static int occ = -1;
+    if (int rc = prepare_kernel(kern, threads, smem, &occ)) return rc;
+    const cplx<T>* tw = twiddle_fft<T>(LOG2L);
+    if (!tw) return -3;
+    long grid = (long)sm_count() * occ;
+    if (grid > ntiles) grid = ntiles;
+    if (grid < 1) return 0;
+    kern<<<(unsigned)grid, threads, smem, st>>>(io, tw, ntiles);
+    return check_launch("cols_kernel");
+}
+
+}  // namespace xrftb

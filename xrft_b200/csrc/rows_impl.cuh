@@ -1,0 +1,58 @@
+// xrft_b200 -- contiguous-axis pass dispatch (length -> template instantiation).
+#pragma once
+#include "launch.cuh"
+
+namespace xrftb {
+
+#define XRFTB_ROWS_CASES(X) \
+    X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13)
+
+template <typename T>
+int rows_c2c(const cplx<T>* in, cplx<T>* out, int log2L, long nseq, long in_stride, long out_stride, int inverse, T scale,
+             cudaStream_t st) {
+    RowsC2C<T> io{in, out, in_stride, out_stride, inverse, scale};
+    switch (log2L) {
+#define X(K) case K: return launch_rows<T, K, rows_seq_generic<K, cmin(TypeCfg<T>::LOGE, K)>()>(io, nseq, st);
+        XRFTB_ROWS_CASES(X)
+#undef X
+        case 14:
+            if constexpr (TypeCfg<T>::MAX_ROWS_LOG2 >= 14) return launch_rows<T, 14, 1>(io, nseq, st);
+        default: break;
+    }
+    set_error("rows_c2c: unsupported length 2^%d", log2L);
+    return -2;
+}
+
+template <typename T>
+int rows_r2c(RowsR2CFused<T> io, int log2M, long nseq, cudaStream_t st) {
+    io.tw_r2c = twiddle_r2c<T>(log2M + 1);
+    if (!io.tw_r2c) return -3;
+    switch (log2M) {
+#define X(K) case K: return launch_rows<T, K, rows_seq_fused<K, cmin(TypeCfg<T>::LOGE, K)>()>(io, nseq, st);
+        XRFTB_ROWS_CASES(X)
+#undef X
+        case 14:
+            if constexpr (TypeCfg<T>::MAX_ROWS_LOG2 >= 14) return launch_rows<T, 14, 1>(io, nseq, st);
+        default: break;
+    }
+    set_error("rows_r2c: unsupported half length 2^%d", log2M);
+    return -2;
+}
+
+template <typename T>
+int rows_c2r(const cplx<T>* in, long in_stride, T* out, long out_stride, int log2M, long nseq, T scale, cudaStream_t st) {
+    RowsC2R<T> io{in, in_stride, out, out_stride, scale, twiddle_r2c<T>(log2M + 1)};
+    if (!io.tw_r2c) return -3;
+    switch (log2M) {
+#define X(K) case K: return launch_rows<T, K, rows_seq_generic<K, cmin(TypeCfg<T>::LOGE, K)>()>(io, nseq, st);
+        XRFTB_ROWS_CASES(X)
+#undef X
+        case 14:
+            if constexpr (TypeCfg<T>::MAX_ROWS_LOG2 >= 14) return launch_rows<T, 14, 1>(io, nseq, st);
+        default: break;
+    }
+    set_error("rows_c2r: unsupported half length 2^%d", log2M);
+    return -2;
+}
+
+}  // namespace xrftb
