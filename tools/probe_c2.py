@@ -1,0 +1,29 @@
+"""Quick perf probe of the fused config-2 path (not the bench contract)."""
+import sys, time
+import numpy as np, torch, scipy.signal as sps
+sys.path.insert(0, ".")
+from xrft_b200 import backend as B, _lib as L
+
+ny = nx = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+T = int(sys.argv[2]) if len(sys.argv) > 2 else 32
+reps = int(sys.argv[3]) if len(sys.argv) > 3 else 5
+dt = torch.float32 if (len(sys.argv) <= 4 or sys.argv[4] == "f32") else torch.float64
+g = torch.Generator(device="cuda").manual_seed(1234)
+x = torch.randn((T, ny, nx), generator=g, device="cuda", dtype=dt)
+x += 0.3 * torch.arange(nx, device="cuda", dtype=dt) - 0.7 * torch.arange(ny, device="cuda", dtype=dt)[:, None] + 5
+wy = torch.from_numpy(sps.windows.hann(ny, sym=False)); wx = torch.from_numpy(sps.windows.hann(nx, sym=False))
+chunks = [int(c) for c in sys.argv[5].split(",")] if len(sys.argv) > 5 else [0]
+lib = L.load()
+for ch in chunks:
+    mw = (2 << 30) if ch == 0 else lib.xrftb_spectrum2d_workspace(0 if dt == torch.float32 else 1, ny, nx, 0, ch)
+    def run():
+        return B.spectrum2d(x, None, L.EPI_POWER, detrend=2, win_y=wy, win_x=wx, shift_y=True, shift_x=True, scale=1.0 / (ny * nx), max_work_bytes=mw)
+    for _ in range(2): out = run()
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps): out = run()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    pts = T * ny * nx
+    print(f"{ny}x{nx}x{T} {dt} chunk={ch}: {ms:.3f} ms/step  {pts / ms / 1e6:.1f} GPts/s  (8 B/pt -> {pts * 8 / ms / 1e6:.0f} GB/s algorithmic)")

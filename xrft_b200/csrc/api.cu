@@ -77,7 +77,7 @@ template <> const cplx<double>* twiddle_r2c<double>(int l) { return get_table<do
 // K1: moments.  item = [n0][n1][n2]; rows = n0*n1 of length n2.  fp64 accumulation.
 // ------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(256) moments_kernel(const T* __restrict__ in, double* __restrict__ mom, long n0, long n1,
+__global__ void __launch_bounds__(512) moments_kernel(const T* __restrict__ in, double* __restrict__ mom, long n0, long n1,
                                                       long n2, int chunks) {
     const long b = blockIdx.y;
     const long rows = n0 * n1;
@@ -86,33 +86,54 @@ __global__ void __launch_bounds__(256) moments_kernel(const T* __restrict__ in, 
     const double c0m = 0.5 * (double)(n0 - 1), c1m = 0.5 * (double)(n1 - 1), c2m = 0.5 * (double)(n2 - 1);
     double S = 0, S0 = 0, S1 = 0, S2 = 0;
     const bool vec = (sizeof(T) == 4) && (n2 % 4 == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0);
-    for (long r = r0; r < r1; ++r) {
-        const T* p = base + r * n2;
-        double s = 0, sx = 0;
-        if (vec) {
-            const float4* p4 = reinterpret_cast<const float4*>(p);
-            for (long i = threadIdx.x; i < n2 / 4; i += blockDim.x) {
-                float4 x = p4[i];
-                const float c = (float)((double)(4 * i) - c2m);  // half-integers: exact in fp32
-                float s4 = (x.x + x.y) + (x.z + x.w);
-                float w4 = (c * x.x + (c + 1.f) * x.y) + ((c + 2.f) * x.z + (c + 3.f) * x.w);
+    if (vec) {
+        // thread-private column position is fixed when blockDim divides the row: weights hoisted
+        const long n4 = n2 / 4;
+        for (long r = r0; r < r1; ++r) {
+            const float4* p4 = reinterpret_cast<const float4*>(base + r * n2);
+            float s4 = 0.f, w4 = 0.f;  // fp32 partials over <= 4*ceil(n4/blockDim) values, folded into fp64 per row
+            double s = 0, sx = 0;
+            long i = threadIdx.x;
+            for (; i + 3 * blockDim.x < n4; i += 4 * blockDim.x) {
+                float4 x0 = __ldg(p4 + i), x1 = __ldg(p4 + i + blockDim.x), x2 = __ldg(p4 + i + 2 * blockDim.x), x3 = __ldg(p4 + i + 3 * blockDim.x);
+                const float c = (float)((double)(4 * i) - c2m), dc = (float)(4 * blockDim.x);
+                s4 = ((x0.x + x0.y) + (x0.z + x0.w)) + ((x1.x + x1.y) + (x1.z + x1.w)) + ((x2.x + x2.y) + (x2.z + x2.w)) + ((x3.x + x3.y) + (x3.z + x3.w));
+                w4 = (c * x0.x + (c + 1.f) * x0.y) + ((c + 2.f) * x0.z + (c + 3.f) * x0.w);
+                w4 += ((c + dc) * x1.x + (c + dc + 1.f) * x1.y) + ((c + dc + 2.f) * x1.z + (c + dc + 3.f) * x1.w);
+                w4 += ((c + 2 * dc) * x2.x + (c + 2 * dc + 1.f) * x2.y) + ((c + 2 * dc + 2.f) * x2.z + (c + 2 * dc + 3.f) * x2.w);
+                w4 += ((c + 3 * dc) * x3.x + (c + 3 * dc + 1.f) * x3.y) + ((c + 3 * dc + 2.f) * x3.z + (c + 3 * dc + 3.f) * x3.w);
                 s += (double)s4;
                 sx += (double)w4;
             }
-        } else {
+            for (; i < n4; i += blockDim.x) {
+                float4 x = __ldg(p4 + i);
+                const float c = (float)((double)(4 * i) - c2m);
+                s += (double)((x.x + x.y) + (x.z + x.w));
+                sx += (double)((c * x.x + (c + 1.f) * x.y) + ((c + 2.f) * x.z + (c + 3.f) * x.w));
+            }
+            const long i0 = r / n1, i1 = r - i0 * n1;
+            S += s;
+            S0 += ((double)i0 - c0m) * s;
+            S1 += ((double)i1 - c1m) * s;
+            S2 += sx;
+        }
+    } else {
+        for (long r = r0; r < r1; ++r) {
+            const T* p = base + r * n2;
+            double s = 0, sx = 0;
             for (long i = threadIdx.x; i < n2; i += blockDim.x) {
                 double x = (double)p[i];
                 s += x;
                 sx += ((double)i - c2m) * x;
             }
+            const long i0 = r / n1, i1 = r - i0 * n1;
+            S += s;
+            S0 += ((double)i0 - c0m) * s;
+            S1 += ((double)i1 - c1m) * s;
+            S2 += sx;
         }
-        const long i0 = r / n1, i1 = r - i0 * n1;
-        S += s;
-        S0 += ((double)i0 - c0m) * s;
-        S1 += ((double)i1 - c1m) * s;
-        S2 += sx;
     }
-    __shared__ double red[4][8];
+    __shared__ double red[4][16];
     double vals[4] = {S, S0, S1, S2};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -218,6 +239,45 @@ __global__ void __launch_bounds__(256) spectral_post_kernel(const cplx<T>* __res
 }
 
 // ------------------------------------------------------------------------------------------------
+// Hermitian completion of a full-width spectrum whose direct half (unshifted kx <= Nx/2) is written:
+//   out[-ky][-kx] = conj(out[ky][kx]) (* ramp correction for unit-modulus ramps), rows fully coalesced.
+// ------------------------------------------------------------------------------------------------
+template <typename T, bool CPLX>
+__global__ void __launch_bounds__(256) mirror_fill_kernel(void* __restrict__ out_, int logNy, int logNx, int shift_y, int shift_x,
+                                                          const cplx<T>* __restrict__ ramp_y, const cplx<T>* __restrict__ ramp_x,
+                                                          long nrows_total) {
+    using E = typename std::conditional<CPLX, cplx<T>, T>::type;
+    E* out = reinterpret_cast<E*>(out_);
+    const int Ny = 1 << logNy, Nx = 1 << logNx, M = Nx >> 1;
+    const int sy = shift_y ? Ny / 2 : 0, sx = shift_x ? M : 0;
+    // target cells: unshifted kx' in (M, Nx)  <=>  ox' = (kx' + sx) & (Nx-1); there are M-1 of them per row
+    const int per_row = M - 1;
+    for (long row = blockIdx.x; row < nrows_total; row += gridDim.x) {
+        const long b = row >> logNy;
+        const int oy = (int)(row & (Ny - 1));
+        const int kyt = (oy - sy) & (Ny - 1);             // target unshifted row index
+        const int kys = (Ny - kyt) & (Ny - 1);            // source (direct) row
+        const int oys = (kys + sy) & (Ny - 1);
+        const E* src = out + ((b << logNy) | oys) * (long)Nx;
+        E* dst = out + ((b << logNy) | oy) * (long)Nx;
+        cplx<T> ry = mk<T>(1, 0);
+        if constexpr (CPLX) { if (ramp_y) ry = cmul(__ldg(ramp_y + kys), __ldg(ramp_y + kyt)); }
+#pragma unroll 4
+        for (int j = threadIdx.x; j < per_row; j += blockDim.x) {
+            const int kxt = M + 1 + j;                    // target unshifted column index
+            const int kxs = Nx - kxt;
+            E v = src[(kxs + sx) & (Nx - 1)];
+            if constexpr (CPLX) {
+                v.y = -v.y;
+                if (ramp_y) v = cmul(v, ry);
+                if (ramp_x) v = cmul(v, cmul(__ldg(ramp_x + kxs), __ldg(ramp_x + kxt)));
+            }
+            dst[(kxt + sx) & (Nx - 1)] = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // radial-bin sum: per-CTA fp64 histogram in shared memory, flushed with one global atomic per bin
 // ------------------------------------------------------------------------------------------------
 template <typename T, bool CPLX>
@@ -250,6 +310,11 @@ static inline int ilog2_exact(int64_t n) {
     int l = 0;
     while ((1LL << l) < n) ++l;
     return l;
+}
+
+static inline unsigned mirror_grid(long nrows) {
+    long cap = (long)sm_count() * 16;
+    return (unsigned)(nrows < cap ? nrows : cap);
 }
 
 static inline unsigned ew_grid(long total) {
@@ -307,8 +372,8 @@ static int fftn_impl(const void* in, void* out, void* work, size_t work_bytes, i
         long nseq = 1;
         for (int d = 0; d < ndim - 1; ++d) nseq *= shape[d];
         RowsR2CFused<T> io{};
-        io.in = reinterpret_cast<const T*>(in); io.in_row_stride = N; io.Ny = 1; io.detrend = 0; io.moments = nullptr;
-        io.wy = nullptr; io.wx = nullptr; io.out = reinterpret_cast<C*>(out); io.tileC = 0; io.out_seq_stride = N / 2 + 1;
+        io.in = reinterpret_cast<const T*>(in); io.in_row_stride = N; io.logNy = 0; io.detrend = 0; io.moments = nullptr;
+        io.wy = nullptr; io.wx = nullptr; io.out = reinterpret_cast<C*>(out); io.logC = -1; io.out_seq_stride = N / 2 + 1;
         int rc = rows_r2c<T>(io, l2 - 1, nseq, st);
         if (rc) return rc;
         C* dst = reinterpret_cast<C*>(out);
@@ -336,7 +401,7 @@ static int fftn_impl(const void* in, void* out, void* work, size_t work_bytes, i
                 src = w;
             }
         }
-        return rows_c2r<T>(src, N / 2 + 1, reinterpret_cast<T*>(out), N, l2 - 1, nseq, inv_scale, st);
+        return rows_c2r<T>(src, N / 2 + 1, reinterpret_cast<T*>(out), N, l2 - 1, nseq, inv_scale * (T)2, st);  // half-length inverse: 1/M = 2/N
     }
 }
 
@@ -366,6 +431,7 @@ static int spectrum2d_impl(const xrftb_spectrum2d_desc& q, cudaStream_t st) {
     if (!q.work || q.work_bytes < mom_region + per_item * fields) { set_error("spectrum2d: workspace too small (%zu < %zu)", q.work_bytes, mom_region + per_item * fields); return XRFTB_EWORKSPACE; }
     long bchunk = (long)((q.work_bytes - mom_region) / (per_item * fields));
     if (bchunk > q.batch) bchunk = q.batch;
+    { const long nch = (q.batch + bchunk - 1) / bchunk; bchunk = (q.batch + nch - 1) / nch; }  // balanced chunks
     double* mom = reinterpret_cast<double*>(q.work);
     C_* interm = reinterpret_cast<C_*>(reinterpret_cast<char*>(q.work) + mom_region);
     const long item = (long)q.ny * q.nx;
@@ -375,7 +441,7 @@ static int spectrum2d_impl(const xrftb_spectrum2d_desc& q, cudaStream_t st) {
         cudaError_t e = cudaMemsetAsync(mom, 0, mom_bytes, st);
         if (e != cudaSuccess) { set_error("memset: %s", cudaGetErrorString(e)); return XRFTB_ECUDA; }
         for (int f = 0; f < fields; ++f) {
-            int chunks = (int)((2L * sm_count() + q.batch - 1) / q.batch);
+            int chunks = (int)((8L * sm_count() + q.batch - 1) / q.batch);
             if (chunks < 1) chunks = 1;
             if (chunks > q.ny) chunks = q.ny;
             dim3 grid(chunks, (unsigned)q.batch);
@@ -384,7 +450,8 @@ static int spectrum2d_impl(const xrftb_spectrum2d_desc& q, cudaStream_t st) {
         }
     }
     EpilogueDesc d{};
-    d.mode = q.mode; d.Ny = q.ny; d.Nx = q.nx; d.full = q.keep_half ? 0 : 1; d.shift_y = q.shift_y; d.shift_x = q.shift_x;
+    const bool mirror_pass = !q.keep_half && (q.mode == XRFTB_EPI_POWER || q.mode == XRFTB_EPI_COMPLEX || q.mode == XRFTB_EPI_CROSS) && q.nx >= 8;
+    d.logNx = lx; d.full = q.keep_half ? 0 : (mirror_pass ? 2 : 1); d.shift_y = q.shift_y; d.shift_x = q.shift_x;
     d.scale = q.scale; d.ramp_y = q.ramp_y; d.ramp_x = q.ramp_x; d.weight_x = q.weight_x; d.lut = q.lut; d.nbins = q.nbins;
     const long W = q.keep_half ? q.nx / 2 + 1 : q.nx;
     const bool bins_mode = (q.mode == XRFTB_EPI_BINS_POWER || q.mode == XRFTB_EPI_BINS_CROSS);
@@ -393,17 +460,26 @@ static int spectrum2d_impl(const xrftb_spectrum2d_desc& q, cudaStream_t st) {
         const long nb = (q.batch - b0 < bchunk) ? q.batch - b0 : bchunk;
         for (int f = 0; f < fields; ++f) {
             RowsR2CFused<T> io{};
-            io.in = ins[f] + b0 * item; io.in_row_stride = q.nx; io.Ny = q.ny; io.detrend = q.detrend;
+            io.in = ins[f] + b0 * item; io.in_row_stride = q.nx; io.logNy = ly; io.detrend = q.detrend;
             io.moments = mom + ((size_t)f * q.batch + b0) * 4;
             io.wy = reinterpret_cast<const T*>(q.win_y); io.wx = reinterpret_cast<const T*>(q.win_x);
-            io.out = interm + (size_t)f * bchunk * (per_item / sizeof(C_)); io.tileC = C; io.out_seq_stride = 0;
+            io.out = interm + (size_t)f * bchunk * (per_item / sizeof(C_)); io.logC = ilog2_exact(C); io.out_seq_stride = 0;
             if (int rc = rows_r2c<T>(io, lx - 1, nb * q.ny, st)) return rc;
         }
         d.out = bins_mode ? nullptr : reinterpret_cast<char*>(q.out) + (size_t)b0 * q.ny * W * out_elem;
         d.bins = bins_mode ? q.bins + (size_t)b0 * q.nbins * (q.mode == XRFTB_EPI_BINS_CROSS ? 2 : 1) : nullptr;
         const C_* i1 = interm;
         const C_* i2 = two ? interm + (size_t)bchunk * (per_item / sizeof(C_)) : nullptr;
-        if (int rc = cols_fused<T>(i1, i2, ly, nb * ntile, (int)ntile, d, st)) return rc;
+        if (int rc = cols_fused<T>(q.mode, i1, i2, ly, nb * ntile, (int)ntile, d, st)) return rc;
+        if (mirror_pass) {
+            const long nrows = nb * q.ny;
+            if (q.mode == XRFTB_EPI_POWER)
+                mirror_fill_kernel<T, false><<<mirror_grid(nrows), 256, 0, st>>>(d.out, ly, lx, q.shift_y, q.shift_x, nullptr, nullptr, nrows);
+            else
+                mirror_fill_kernel<T, true><<<mirror_grid(nrows), 256, 0, st>>>(d.out, ly, lx, q.shift_y, q.shift_x,
+                    reinterpret_cast<const C_*>(q.ramp_y), reinterpret_cast<const C_*>(q.ramp_x), nrows);
+            if (int rc = check_launch("mirror_fill_kernel")) return rc;
+        }
     }
     return 0;
 }
@@ -460,7 +536,7 @@ int xrftb_moments(const void* in, double* moments, int dtype, int64_t batch, int
     cudaError_t e = cudaMemsetAsync(moments, 0, (size_t)batch * 4 * sizeof(double), st);
     if (e != cudaSuccess) { set_error("memset: %s", cudaGetErrorString(e)); return XRFTB_ECUDA; }
     long rows = n0 * n1;
-    int chunks = (int)((2L * sm_count() + batch - 1) / batch);
+    int chunks = (int)((8L * sm_count() + batch - 1) / batch);
     if (chunks < 1) chunks = 1;
     if (chunks > rows) chunks = (int)rows;
     if (batch > 65535) { set_error("moments: batch > 65535 unsupported"); return XRFTB_EUNSUPPORTED; }

@@ -1,5 +1,4 @@
 #include "cols_impl.cuh"
 namespace xrftb {
 template int cols_c2c<float>(const float2*, float2*, int, long, long, int, float, cudaStream_t);
-template int cols_fused<float>(const float2*, const float2*, int, long, int, const EpilogueDesc&, cudaStream_t);
 }

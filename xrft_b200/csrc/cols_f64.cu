@@ -1,5 +1,4 @@
 #include "cols_impl.cuh"
 namespace xrftb {
 template int cols_c2c<double>(const double2*, double2*, int, long, long, int, double, cudaStream_t);
-template int cols_fused<double>(const double2*, const double2*, int, long, int, const EpilogueDesc&, cudaStream_t);
 }

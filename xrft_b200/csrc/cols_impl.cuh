@@ -29,25 +29,25 @@ int cols_c2c(const cplx<T>* in, cplx<T>* out, int log2L, long A, long B, int inv
     return -2;
 }
 
-template <typename T, int K, bool TWO>
+template <typename T, int K, int MODE>
 static int cols_fused_k(const cplx<T>* in1, const cplx<T>* in2, long ntiles_total, int ntile, const EpilogueDesc& d, cudaStream_t st) {
-    constexpr int C = TileC<T, K, TWO>::value;
+    using IO = ColsFused<T, MODE>;
+    constexpr int C = TileC<T, K, IO::kTwoFields>::value;
     if constexpr (C < 1) {
-        set_error("cols_fused: length 2^%d too long for %d field(s)", K, TWO ? 2 : 1);
+        set_error("cols_fused: length 2^%d too long for %d field(s)", K, IO::kTwoFields ? 2 : 1);
         return -2;
     } else {
-        ColsFused<T, TWO> io{in1, in2, ntile, d};
-        return launch_cols<T, K, C>(io, ntiles_total, st);
+        IO io{in1, in2, ntile, d};
+        const size_t extra = IO::kBins ? (size_t)d.nbins * (IO::kCplxStage ? 2 : 1) * sizeof(double) : 0;
+        return launch_cols<T, K, C>(io, ntiles_total, st, extra);
     }
 }
 
-template <typename T>
-int cols_fused(const cplx<T>* in1, const cplx<T>* in2, int log2L, long ntiles_total, int ntile, const EpilogueDesc& d,
-               cudaStream_t st) {
-    const bool two = in2 != nullptr;
+template <typename T, int MODE>
+int cols_fused_mode(const cplx<T>* in1, const cplx<T>* in2, int log2L, long ntiles_total, int ntile, const EpilogueDesc& d,
+                    cudaStream_t st) {
     switch (log2L) {
-#define X(K) case K: return two ? cols_fused_k<T, K, true>(in1, in2, ntiles_total, ntile, d, st) \
-                                : cols_fused_k<T, K, false>(in1, in2, ntiles_total, ntile, d, st);
+#define X(K) case K: return cols_fused_k<T, K, MODE>(in1, in2, ntiles_total, ntile, d, st);
         XRFTB_COLS_CASES(X)
 #undef X
         default: break;

@@ -161,7 +161,11 @@ __device__ __forceinline__ int final_index(int u, int g, int t) {
     return (j - jm) * R + jm + t * Ns;
 }
 
-template <typename T, int LOG2L, int LOGE, int LOGNS>
+// Shared-memory addressing is affine in the unrolled indices so every access is [base + immediate]:
+//   gather  point u + q*NT          -> pad(u) + q*(NT + NT/PADW)            (NT multiple of PADW)
+//   scatter point o0 + t*Ns, Ns>=PADW -> pad(o0) + t*(Ns + Ns/PADW)
+//   scatter point j*R + t,   Ns==1   -> j*(R+1) + t                          (R == PADW)
+template <typename T, int LOG2L, int LOGE, int LOGNS, int SI>
 struct Stages {
     using G_ = Geometry<LOG2L, LOGE>;
     static constexpr int E = G_::E;
@@ -171,10 +175,12 @@ struct Stages {
     static constexpr int G = E / R;
     static constexpr int Ns = 1 << LOGNS;
     static constexpr bool LAST = (LOGNS + LOGR == LOG2L);
+    static constexpr int PADW = 1 << G_::LOGPAD;
 
-    // sm: smem base of this thread's sequence slot (already offset by s_off); SI: point stride.
+    // sm: smem base of this thread's slot (already offset by the column / sequence); vstride: distance
+    // between the NSEQV register-resident sequences of one thread.
     template <int NSEQV>
-    static __device__ __forceinline__ void run(cplx<T> (&v)[NSEQV][E], int u, cplx<T>* sm, int SI, int vstride,
+    static __device__ __forceinline__ void run(cplx<T> (&v)[NSEQV][E], int u, cplx<T>* sm, int vstride,
                                                const cplx<T>* __restrict__ tw) {
 #pragma unroll
         for (int g = 0; g < G; ++g) {
@@ -192,38 +198,54 @@ struct Stages {
             }
         }
         if constexpr (!LAST) {
-            // scatter (auto-sort position), barrier, gather
 #pragma unroll
             for (int g = 0; g < G; ++g) {
                 int j = u + g * G_::NT;
                 int jm = j & (Ns - 1);
                 int o0 = (j - jm) * R + jm;
+                cplx<T>* base;
+                int tstep;
+                if constexpr (Ns == 1 && R == PADW) { base = sm + (j * (R + 1)) * SI; tstep = SI; }
+                else if constexpr (Ns >= PADW) { base = sm + padded<G_::LOGPAD>(o0) * SI; tstep = (Ns + Ns / PADW) * SI; }
+                else { base = nullptr; tstep = 0; }
 #pragma unroll
                 for (int t = 0; t < R; ++t) {
-                    int p = padded<G_::LOGPAD>(o0 + t * Ns) * SI;
+                    cplx<T>* p;
+                    if constexpr ((Ns == 1 && R == PADW) || Ns >= PADW) p = base + t * tstep;
+                    else p = sm + padded<G_::LOGPAD>(o0 + t * Ns) * SI;
 #pragma unroll
-                    for (int s = 0; s < NSEQV; ++s) sm[p + s * vstride] = v[s][g + t * G];
+                    for (int s = 0; s < NSEQV; ++s) p[s * vstride] = v[s][g + t * G];
                 }
             }
             __syncthreads();
+            {
+                cplx<T>* base = sm + padded<G_::LOGPAD>(u) * SI;
 #pragma unroll
-            for (int q = 0; q < E; ++q) {
-                int p = padded<G_::LOGPAD>(u + q * G_::NT) * SI;
+                for (int q = 0; q < E; ++q) {
+                    cplx<T>* p;
+                    if constexpr (G_::NT % PADW == 0) p = base + q * ((G_::NT + G_::NT / PADW) * SI);
+                    else p = sm + padded<G_::LOGPAD>(u + q * G_::NT) * SI;
 #pragma unroll
-                for (int s = 0; s < NSEQV; ++s) v[s][q] = sm[p + s * vstride];
+                    for (int s = 0; s < NSEQV; ++s) v[s][q] = p[s * vstride];
+                }
             }
             __syncthreads();
-            Stages<T, LOG2L, LOGE, LOGNS + LOGR>::template run<NSEQV>(v, u, sm, SI, vstride, tw);
+            Stages<T, LOG2L, LOGE, LOGNS + LOGR, SI>::template run<NSEQV>(v, u, sm, vstride, tw);
         }
     }
 };
 
 // whole forward FFT of the register-resident sequence(s); results stay in registers, mapped by
 // final_index<LOG2L, LOGE>(u, g, t) with g in [0, E/R_last), t in [0, R_last).
-template <typename T, int LOG2L, int LOGE, int NSEQV>
-__device__ __forceinline__ void block_fft(cplx<T> (&v)[NSEQV][1 << LOGE], int u, cplx<T>* sm, int SI, int vstride,
+template <typename T, int LOG2L, int LOGE, int NSEQV, int SI>
+__device__ __forceinline__ void block_fft(cplx<T> (&v)[NSEQV][1 << LOGE], int u, cplx<T>* sm, int vstride,
                                           const cplx<T>* __restrict__ tw) {
-    Stages<T, LOG2L, LOGE, 0>::template run<NSEQV>(v, u, sm, SI, vstride, tw);
+    Stages<T, LOG2L, LOGE, 0, SI>::template run<NSEQV>(v, u, sm, vstride, tw);
+}
+
+// hint the L2 to fetch a contiguous chunk (next tile / next rows) while the current one is transformed
+__device__ __forceinline__ void prefetch_l2_bulk(const void* gptr, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
 }
 
 }  // namespace xrftb

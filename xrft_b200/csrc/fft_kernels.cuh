@@ -18,8 +18,12 @@ namespace xrftb {
 
 // register budget: keep >= 512 threads resident per SM (<= 128 registers/thread)
 constexpr int min_blocks_for(int threads) { return threads >= 512 ? 1 : (512 / threads > 8 ? 8 : 512 / threads); }
+constexpr int ilog2c(int n) { return n <= 1 ? 0 : 1 + ilog2c(n / 2); }
 
 enum : int { EPI_COMPLEX = 0, EPI_POWER = 1, EPI_CROSS = 2, EPI_PHASE = 3, EPI_BINS_POWER = 4, EPI_BINS_CROSS = 5 };
+
+__device__ __forceinline__ float xatan2(float y, float x) { return atan2f(y, x); }
+__device__ __forceinline__ double xatan2(double y, double x) { return atan2(y, x); }
 
 // =============================================================================================
 // K-A : rows
@@ -38,9 +42,10 @@ rows_kernel(IO io, const cplx<T>* __restrict__ tw, long nseq) {
     for (long grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
         const long seq = grp * SEQ + s;
         const bool active = seq < nseq;
+        if (threadIdx.x == 0 && grp + gridDim.x < ngroups) io.template prefetch<LOG2L, SEQ>((grp + gridDim.x) * SEQ, nseq);
         cplx<T> v[1][E];
         io.template load<LOG2L, LOGE>(seq, active, u, v[0]);
-        block_fft<T, LOG2L, LOGE, 1>(v, u, sm, 1, 0, tw);
+        block_fft<T, LOG2L, LOGE, 1, 1>(v, u, sm, 0, tw);
         io.template store<LOG2L, LOGE, SEQ>(grp, seq, active, u, s, v[0], smem, SEQ_STRIDE, nseq);
     }
 }
@@ -50,14 +55,16 @@ template <typename T> struct RowsC2C {
     static constexpr int kSeqSkew = 0;
     const cplx<T>* in; cplx<T>* out; long in_stride, out_stride; int inverse; T scale;
 
+    template <int LOG2L, int SEQ> __device__ __forceinline__ void prefetch(long, long) const {}
+
     template <int LOG2L, int LOGE>
     __device__ __forceinline__ void load(long seq, bool active, int u, cplx<T> (&v)[1 << LOGE]) const {
         constexpr int NT = Geometry<LOG2L, LOGE>::NT;
-        const cplx<T>* p = in + seq * in_stride;
+        const cplx<T>* p = in + seq * in_stride + u;
 #pragma unroll
         for (int q = 0; q < (1 << LOGE); ++q) {
             cplx<T> x = mk<T>(0, 0);
-            if (active) x = p[u + q * NT];
+            if (active) x = p[q * NT];
             if (inverse) x.y = -x.y;
             v[q] = x;
         }
@@ -91,114 +98,151 @@ __device__ __forceinline__ cplx<T> r2c_split(cplx<T> zk, cplx<T> zm, cplx<T> w) 
 
 // ---- fused real-input row pass -----------------------------------------------------------------
 // prologue : (x - plane) * wy[iy] * wx[ix]       (detrend in fp64 -- SURVEY F6 -- window in T)
-// epilogue : R2C split, then either the natural half-spectrum [seq][M+1]   (tileC == 0)
-//            or the BLOCKED intermediate [batch][tile][Ny][C] consumed by cols_kernel (tileC > 0):
+// epilogue : R2C split, then either the natural half-spectrum [seq][M+1]   (logC < 0)
+//            or the BLOCKED intermediate [batch][tile][Ny][C] consumed by cols_kernel (logC >= 0):
 //            each CTA writes SEQ*C*sizeof(cplx) contiguous bytes per tile, each column tile is
 //            one contiguous Ny*C*sizeof(cplx) chunk for the column pass.
+//            Ny and C are powers of two: all index math is shifts and masks.
 template <typename T> struct RowsR2CFused {
     static constexpr int kSeqSkew = 4;  // rows skewed by 4 points: conflict-free cross-row gathers
     const T* in; long in_row_stride;    // real input, element stride between consecutive rows
-    int Ny;                              // rows per batch item (1 for 1-D)
+    int logNy;                           // log2(rows per batch item) (0 for 1-D)
     int detrend;                         // 0 none | 1 constant | 2 linear
     const double* moments;               // [batch][4] : S, S0(unused), Sy, Sx -- sum and centred first moments
     const T* wy; const T* wx;            // window vectors (nullable)
-    cplx<T>* out; int tileC; long out_seq_stride;  // natural: stride per seq ; blocked: unused
+    cplx<T>* out; int logC; long out_seq_stride;  // natural: stride per seq ; blocked: unused
     const cplx<T>* tw_r2c;               // exp(-2 pi i k / N), k in [0, M]
+
+    template <int LOG2L, int SEQ> __device__ __forceinline__ void prefetch(long seq0, long nseq) const {
+        constexpr unsigned row_bytes = (unsigned)(2u << LOG2L) * sizeof(T);
+        if (in_row_stride == (2 << LOG2L) && seq0 + SEQ <= nseq && (row_bytes * SEQ) % 16 == 0)
+            prefetch_l2_bulk(in + seq0 * in_row_stride, row_bytes * SEQ);
+    }
 
     template <int LOG2L, int LOGE>
     __device__ __forceinline__ void load(long seq, bool active, int u, cplx<T> (&v)[1 << LOGE]) const {
         constexpr int NT = Geometry<LOG2L, LOGE>::NT;
         constexpr int Nx = 2 << LOG2L;
-        const long b = seq / Ny;
-        const int iy = (int)(seq - b * Ny);
-        double rowc = 0.0, cx = 0.0;
+        const int Ny = 1 << logNy;
+        const long b = seq >> logNy;
+        const int iy = (int)(seq & (Ny - 1));
+        double p0 = 0.0, cx = 0.0;
         if (detrend && active) {
             const double* m = moments + b * 4;
             const double npts = (double)Ny * (double)Nx;
-            rowc = m[0] / npts;
+            p0 = m[0] / npts;
             if (detrend == 2) {
                 // least-squares plane on a full regular grid == centred first moments (orthogonal regressors)
                 const double vy = (double)Nx * ((double)Ny * ((double)Ny * Ny - 1.0) / 12.0);
                 const double vx = (double)Ny * ((double)Nx * ((double)Nx * Nx - 1.0) / 12.0);
                 const double cy = Ny > 1 ? m[2] / vy : 0.0;
                 cx = m[3] / vx;
-                rowc += cy * ((double)iy - 0.5 * (Ny - 1)) - cx * (0.5 * (Nx - 1));
+                p0 += cy * ((double)iy - 0.5 * (Ny - 1)) + cx * ((double)(2 * u) - 0.5 * (Nx - 1));
             }
         }
+        const double pstep = cx * (double)(2 * NT);
         const T wrow = (wy != nullptr && active) ? wy[iy] : (T)1;
-        const T* p = in + seq * in_row_stride;
+        const cplx<T>* p = reinterpret_cast<const cplx<T>*>(in + seq * in_row_stride) + u;
+        const cplx<T>* pw = reinterpret_cast<const cplx<T>*>(wx) + u;
+        cplx<T> x[1 << LOGE];
 #pragma unroll
         for (int q = 0; q < (1 << LOGE); ++q) {
-            const int n = u + q * NT;
-            cplx<T> x = mk<T>(0, 0);
-            if (active) x = *reinterpret_cast<const cplx<T>*>(p + 2 * n);
+            x[q] = mk<T>(0, 0);
+            if (active) x[q] = p[q * NT];
+        }
+#pragma unroll
+        for (int q = 0; q < (1 << LOGE); ++q) {
+            cplx<T> y = x[q];
             if (detrend) {
-                x.x = (T)((double)x.x - (rowc + cx * (double)(2 * n)));
-                x.y = (T)((double)x.y - (rowc + cx * (double)(2 * n + 1)));
+                y.x = (T)((double)y.x - p0);
+                y.y = (T)((double)y.y - (p0 + cx));
+                p0 += pstep;
             }
             if (wx != nullptr) {
-                cplx<T> w = *reinterpret_cast<const cplx<T>*>(wx + 2 * n);
-                x.x *= w.x * wrow; x.y *= w.y * wrow;
+                cplx<T> w = __ldg(pw + q * NT);
+                y.x *= w.x * wrow; y.y *= w.y * wrow;
             } else {
-                x.x *= wrow; x.y *= wrow;
+                y.x *= wrow; y.y *= wrow;
             }
-            v[q] = x;
+            v[q] = y;
         }
+    }
+
+    template <int LOG2L, int LOGE>
+    __device__ __forceinline__ cplx<T> split_at(const cplx<T>* smr, int k) const {
+        using G_ = Geometry<LOG2L, LOGE>;
+        constexpr int M = G_::L;
+        cplx<T> zk = smr[padded<G_::LOGPAD>(k & (M - 1))];
+        cplx<T> zm = smr[padded<G_::LOGPAD>((M - k) & (M - 1))];
+        return r2c_split<T>(zk, zm, __ldg(tw_r2c + k));
     }
 
     template <int LOG2L, int LOGE, int SEQ>
     __device__ __forceinline__ void store(long grp, long seq, bool active, int u, int s, cplx<T> (&v)[1 << LOGE],
                                           cplx<T>* smem, int seq_stride, long nseq) const {
         using G_ = Geometry<LOG2L, LOGE>;
-        constexpr int R = 1 << G_::LOGR_LAST, G = G_::E / R, M = G_::L, NT = G_::NT;
+        constexpr int R = 1 << G_::LOGR_LAST, G = G_::E / R, M = G_::L, NT = G_::NT, NTHR = NT * SEQ;
+        constexpr int LOGSEQ = ilog2c(SEQ);
         cplx<T>* sm = smem + s * seq_stride;
 #pragma unroll
         for (int g = 0; g < G; ++g)
 #pragma unroll
             for (int t = 0; t < R; ++t) sm[padded<G_::LOGPAD>(final_index<LOG2L, LOGE>(u, g, t))] = v[g + t * G];
         __syncthreads();
-        if (tileC == 0) {
+        if (logC < 0) {
             if (active) {
                 cplx<T>* p = out + seq * out_seq_stride;
-                for (int k = u; k <= M; k += NT) {
-                    cplx<T> zk = sm[padded<G_::LOGPAD>(k & (M - 1))];
-                    cplx<T> zm = sm[padded<G_::LOGPAD>((M - k) & (M - 1))];
-                    p[k] = r2c_split<T>(zk, zm, __ldg(tw_r2c + k));
-                }
+                for (int k = u; k <= M; k += NT) p[k] = split_at<LOG2L, LOGE>(sm, k);
             }
         } else {
-            const int C = tileC;
-            const int ntile = M / C + 1;
-            const int total = ntile * SEQ * C;
-            for (int w = threadIdx.x; w < total; w += NT * SEQ) {
-                const int c = w % C;
-                const int s2 = (w / C) % SEQ;
-                const int t = w / (C * SEQ);
-                const int k = t * C + c;
+            // thread -> (tile t, row s2, column c), c fastest: SEQ*C consecutive threads write one contiguous run
+            const int C = 1 << logC;
+            const int Ny = 1 << logNy;
+            const int ntile = (M >> logC) + 1;
+            if ((NTHR >> (logC + LOGSEQ)) >= 1) {
+                const int c = threadIdx.x & (C - 1);
+                const int s2 = (threadIdx.x >> logC) & (SEQ - 1);
                 const long seq2 = grp * SEQ + s2;
-                if (seq2 >= nseq) continue;
-                const long b = seq2 / Ny;
-                const int iy = (int)(seq2 - b * Ny);
-                cplx<T> r = mk<T>(0, 0);
-                if (k <= M) {
+                if (seq2 < nseq) {
+                    const long b = seq2 >> logNy;
+                    const int iy = (int)(seq2 & (Ny - 1));
                     const cplx<T>* smr = smem + s2 * seq_stride;
-                    cplx<T> zk = smr[padded<G_::LOGPAD>(k & (M - 1))];
-                    cplx<T> zm = smr[padded<G_::LOGPAD>((M - k) & (M - 1))];
-                    r = r2c_split<T>(zk, zm, __ldg(tw_r2c + k));
+                    const int tstep = NTHR >> (logC + LOGSEQ);
+                    const long ostep = ((long)Ny << logC) * tstep;
+                    int t = threadIdx.x >> (logC + LOGSEQ);
+                    cplx<T>* po = out + (((b * ntile + t) << logNy) + iy) * C + c;
+                    for (; t < ntile; t += tstep, po += ostep) {
+                        const int k = (t << logC) + c;
+                        *po = (k <= M) ? split_at<LOG2L, LOGE>(smr, k) : mk<T>(0, 0);
+                    }
                 }
-                out[((b * ntile + t) * (long)Ny + iy) * C + c] = r;
+            } else {
+                for (int w = threadIdx.x; w < ntile * SEQ * C; w += NTHR) {
+                    const int c = w & (C - 1);
+                    const int s2 = (w >> logC) & (SEQ - 1);
+                    const int t = w >> (logC + LOGSEQ);
+                    const long seq2 = grp * SEQ + s2;
+                    if (seq2 >= nseq) continue;
+                    const long b = seq2 >> logNy;
+                    const int iy = (int)(seq2 & (Ny - 1));
+                    const int k = (t << logC) + c;
+                    out[(((b * ntile + t) << logNy) + iy) * C + c] =
+                        (k <= M) ? split_at<LOG2L, LOGE>(smem + s2 * seq_stride, k) : mk<T>(0, 0);
+                }
             }
         }
         __syncthreads();
     }
 };
 
-// ---- C2R: half spectrum [seq][M+1] -> real [seq][N], numpy irfft semantics (scale = 1/N folded in) --
+// ---- C2R: half spectrum [seq][M+1] -> real [seq][N], numpy irfft semantics (scale = 2/N folded in) --
 //   Z[k] = E + i O,  E = (X[k] + conj X[M-k]) / 2,  O = w_N^{-k} (X[k] - conj X[M-k]) / 2
 //   z = IFFT_M(Z) = conj(FFT(conj Z)) ;  x[2n] = Re z[n], x[2n+1] = Im z[n]
 template <typename T> struct RowsC2R {
     static constexpr int kSeqSkew = 0;
     const cplx<T>* in; long in_stride; T* out; long out_stride; T scale; const cplx<T>* tw_r2c;
+
+    template <int LOG2L, int SEQ> __device__ __forceinline__ void prefetch(long, long) const {}
 
     template <int LOG2L, int LOGE>
     __device__ __forceinline__ void load(long seq, bool active, int u, cplx<T> (&v)[1 << LOGE]) const {
@@ -249,10 +293,12 @@ cols_kernel(IO io, const cplx<T>* __restrict__ tw, long ntiles) {
     cplx<T>* smem = reinterpret_cast<cplx<T>*>(smem_raw);
     const int cg = threadIdx.x % CG, u = threadIdx.x / CG;
     cplx<T>* sm = smem + cg * V;
+    io.template init<LOG2L, LOGE, C, V>(smem);
     for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        if (threadIdx.x == 0 && tile + gridDim.x < ntiles) io.template prefetch<LOG2L, C>(tile + gridDim.x);
         cplx<T> v[V][E];
         io.template load<LOG2L, LOGE, C, V>(tile, u, cg, v, 0);
-        block_fft<T, LOG2L, LOGE, V>(v, u, sm, C, 1, tw);
+        block_fft<T, LOG2L, LOGE, V, C>(v, u, sm, 1, tw);
         if constexpr (IO::kTwoFields) {
             // park field-1 spectrum in thread-private smem slots, transform field 2, then combine
             cplx<T>* park = smem + G_::LPAD * C;
@@ -262,10 +308,10 @@ cols_kernel(IO io, const cplx<T>* __restrict__ tw, long ntiles) {
 #pragma unroll
                 for (int q = 0; q < E; ++q) park[(vv * E + q) * NTHR + threadIdx.x] = v[vv][q];
             io.template load<LOG2L, LOGE, C, V>(tile, u, cg, v, 1);
-            block_fft<T, LOG2L, LOGE, V>(v, u, sm, C, 1, tw);
-            io.template store2<LOG2L, LOGE, C, V>(tile, u, cg, v, park, NTHR);
+            block_fft<T, LOG2L, LOGE, V, C>(v, u, sm, 1, tw);
+            io.template store<LOG2L, LOGE, C, V>(tile, u, cg, v, smem, park, NTHR);
         } else {
-            io.template store<LOG2L, LOGE, C, V>(tile, u, cg, v);
+            io.template store<LOG2L, LOGE, C, V>(tile, u, cg, v, smem, nullptr, 0);
         }
     }
 }
@@ -273,28 +319,32 @@ cols_kernel(IO io, const cplx<T>* __restrict__ tw, long ntiles) {
 // ---- plain strided C2C on a [A][L][B] row-major view (in-place safe) ---------------------------
 template <typename T> struct ColsC2C {
     static constexpr bool kTwoFields = false;
+    static constexpr bool kBins = false;
     const cplx<T>* in; cplx<T>* out; long B; long tiles_per_row; int inverse; T scale;
+
+    template <int LOG2L, int C> __device__ __forceinline__ void prefetch(long) const {}
+    template <int LOG2L, int LOGE, int C, int V> __device__ __forceinline__ void init(cplx<T>*) const {}
 
     template <int LOG2L, int LOGE, int C, int V>
     __device__ __forceinline__ void load(long tile, int u, int cg, cplx<T> (&v)[V][1 << LOGE], int) const {
         constexpr int NT = Geometry<LOG2L, LOGE>::NT, L = 1 << LOG2L;
         const long a = tile / tiles_per_row;
         const long b0 = (tile - a * tiles_per_row) * C + cg * V;
-        const cplx<T>* p = in + a * L * B + b0;
+        const cplx<T>* p = in + a * L * B + b0 + (long)u * B;
+        const long qstep = (long)NT * B;
 #pragma unroll
         for (int q = 0; q < (1 << LOGE); ++q) {
-            const long l = u + q * NT;
 #pragma unroll
             for (int vv = 0; vv < V; ++vv) {
                 cplx<T> x = mk<T>(0, 0);
-                if (b0 + vv < B) x = p[l * B + vv];
+                if (b0 + vv < B) x = p[q * qstep + vv];
                 if (inverse) x.y = -x.y;
                 v[vv][q] = x;
             }
         }
     }
     template <int LOG2L, int LOGE, int C, int V>
-    __device__ __forceinline__ void store(long tile, int u, int cg, cplx<T> (&v)[V][1 << LOGE]) const {
+    __device__ __forceinline__ void store(long tile, int u, int cg, cplx<T> (&v)[V][1 << LOGE], cplx<T>*, cplx<T>*, int) const {
         using G_ = Geometry<LOG2L, LOGE>;
         constexpr int R = 1 << G_::LOGR_LAST, G = G_::E / R, L = 1 << LOG2L;
         const long a = tile / tiles_per_row;
@@ -315,101 +365,90 @@ template <typename T> struct ColsC2C {
                 }
             }
     }
-    template <int LOG2L, int LOGE, int C, int V>
-    __device__ __forceinline__ void store2(long, int, int, cplx<T> (&)[V][1 << LOGE], cplx<T>*, int) const {}
 };
 
 // ---- fused column pass of the 2-D real transform -------------------------------------------------
 // input  : blocked half-spectrum intermediate(s) [batch][ntile][Ny][C] written by RowsR2CFused
-// output : by `mode`, at fftshift-ed positions, Hermitian-mirrored to the full Nx width when full != 0
+// output : by MODE, at fftshift-ed positions, Hermitian-mirrored to the full Nx width when full != 0.
+// The epilogue value of every (ky, c) of the tile is staged in shared memory (the exchange buffer is
+// free after the last gather), then rows of the tile are written cooperatively: one thread owns one
+// output row segment (C direct cells + C mirrored cells), so index math is per row, not per cell.
 struct EpilogueDesc {
-    int mode;              // EPI_*
-    int Ny, Nx;            // transform sizes (Nx real axis)
-    int full;              // 1: write full Nx-wide spectrum (mirror), 0: half spectrum Nx/2+1 (real_dim semantics)
+    int logNx;             // log2 of the real-axis length
+    int full;              // 0: half spectrum, width Nx/2+1 (real_dim semantics); 1: full width, mirror cells written here;
+                           // 2: full width, only the direct cells (kx <= Nx/2) written here, mirror_fill_kernel completes the rest
     int shift_y, shift_x;  // fftshift on output (shift_x requires full)
     double scale;
     const void* ramp_y;    // complex<T>[Ny]  (unshifted index), nullable
-    const void* ramp_x;    // complex<T>[Nx or Nx/2+1] (unshifted index), nullable
+    const void* ramp_x;    // complex<T>[W]   (unshifted index), nullable
     const void* weight_x;  // T[Nx/2+1] real one-sided weights (half mode), nullable
-    void* out;             // complex<T> or T, [batch][Ny][Wout]
-    const int* lut;        // bins: int32 [Ny][Wout] bin of each OUTPUT cell (negative = skip)
+    void* out;             // complex<T> or T, [batch][Ny][W]
+    const int* lut;        // bins: int32 [Ny][W] bin of each OUTPUT cell (negative = skip)
     double* bins;          // [batch][nbins] (power) or [batch][nbins][2] (cross)
     int nbins;
 };
 
-__device__ __forceinline__ float xatan2(float y, float x) { return atan2f(y, x); }
-__device__ __forceinline__ double xatan2(double y, double x) { return atan2(y, x); }
+template <typename T> __device__ __forceinline__ T conj_of(T v) { return v; }
+__device__ __forceinline__ float2 conj_of(float2 v) { v.y = -v.y; return v; }
+__device__ __forceinline__ double2 conj_of(double2 v) { v.y = -v.y; return v; }
+template <typename T> __device__ __forceinline__ T wscale(T v, T w) { return v * w; }
+__device__ __forceinline__ float2 wscale(float2 v, float w) { v.x *= w; v.y *= w; return v; }
+__device__ __forceinline__ double2 wscale(double2 v, double w) { v.x *= w; v.y *= w; return v; }
 
-template <typename T>
-__device__ __forceinline__ void emit_cell(const EpilogueDesc& d, long b, int ky, int kx, bool mirrored, cplx<T> f, cplx<T> f2) {
-    // (ky, kx): unshifted output frequency indices in the FULL (or half) grid; f already conj'd if mirrored
-    const int W = d.full ? d.Nx : d.Nx / 2 + 1;
-    cplx<T> val;
-    if (d.mode == EPI_COMPLEX) val = f;
-    else if (d.mode == EPI_POWER || d.mode == EPI_BINS_POWER) val = mk<T>(f.x * f.x + f.y * f.y, 0);
-    else val = cmulc(f, f2);
-    if (d.ramp_y) val = cmul(val, __ldg(reinterpret_cast<const cplx<T>*>(d.ramp_y) + ky));
-    if (d.ramp_x) val = cmul(val, __ldg(reinterpret_cast<const cplx<T>*>(d.ramp_x) + kx));
-    T sc = (T)d.scale;
-    if (d.weight_x) sc *= __ldg(reinterpret_cast<const T*>(d.weight_x) + kx);
-    val = cscale(val, sc);
-    const int oy = d.shift_y ? ((ky + d.Ny / 2) & (d.Ny - 1)) : ky;
-    const int ox = d.shift_x ? ((kx + d.Nx / 2) & (d.Nx - 1)) : kx;
-    const long cell = (long)oy * W + ox;
-    switch (d.mode) {
-        case EPI_COMPLEX:
-        case EPI_CROSS:
-            reinterpret_cast<cplx<T>*>(d.out)[(b * d.Ny) * (long)W + cell] = val;
-            break;
-        case EPI_POWER:
-            reinterpret_cast<T*>(d.out)[(b * d.Ny) * (long)W + cell] = val.x;
-            break;
-        case EPI_PHASE:
-            reinterpret_cast<T*>(d.out)[(b * d.Ny) * (long)W + cell] = xatan2(val.y, val.x);
-            break;
-        case EPI_BINS_POWER: {
-            const int bin = d.lut[cell];
-            if (bin >= 0) atomicAdd(d.bins + b * d.nbins + bin, (double)val.x);
-        } break;
-        case EPI_BINS_CROSS: {
-            const int bin = d.lut[cell];
-            if (bin >= 0) {
-                atomicAdd(d.bins + (b * d.nbins + bin) * 2, (double)val.x);
-                atomicAdd(d.bins + (b * d.nbins + bin) * 2 + 1, (double)val.y);
-            }
-        } break;
-    }
-}
-
-template <typename T, bool TWO> struct ColsFused {
-    static constexpr bool kTwoFields = TWO;
+template <typename T, int MODE> struct ColsFused {
+    static constexpr bool kTwoFields = (MODE == EPI_CROSS || MODE == EPI_PHASE || MODE == EPI_BINS_CROSS);
+    static constexpr bool kBins = (MODE == EPI_BINS_POWER || MODE == EPI_BINS_CROSS);
+    static constexpr bool kCplxStage = (MODE == EPI_COMPLEX || MODE == EPI_CROSS || MODE == EPI_PHASE || MODE == EPI_BINS_CROSS);
+    static constexpr bool kCplxOut = (MODE == EPI_COMPLEX || MODE == EPI_CROSS);
+    using StageT = typename std::conditional<kCplxStage, cplx<T>, T>::type;
+    using OutT = typename std::conditional<kCplxOut, cplx<T>, T>::type;
     const cplx<T>* in1; const cplx<T>* in2; int ntile; EpilogueDesc d;
+
+    template <int LOG2L, int LOGE, int C, int V> static constexpr int hist_offset_bytes() {
+        using G_ = Geometry<LOG2L, LOGE>;
+        return (G_::LPAD * C + (kTwoFields ? G_::L * C : 0)) * (int)sizeof(cplx<T>);
+    }
+    template <int LOG2L, int LOGE, int C, int V> __device__ __forceinline__ void init(cplx<T>* smem) const {
+        if constexpr (kBins) {
+            double* hist = reinterpret_cast<double*>(reinterpret_cast<char*>(smem) + hist_offset_bytes<LOG2L, LOGE, C, V>());
+            for (int i = threadIdx.x; i < d.nbins * (kCplxStage ? 2 : 1); i += blockDim.x) hist[i] = 0.0;
+            __syncthreads();
+        }
+    }
+
+    template <int LOG2L, int C> __device__ __forceinline__ void prefetch(long tile) const {
+        constexpr unsigned bytes = (unsigned)((1u << LOG2L) * C * sizeof(cplx<T>));
+        if constexpr (bytes % 16 == 0) {
+            prefetch_l2_bulk(in1 + tile * (long)(1 << LOG2L) * C, bytes);
+            if (kTwoFields) prefetch_l2_bulk(in2 + tile * (long)(1 << LOG2L) * C, bytes);
+        }
+    }
 
     template <int LOG2L, int LOGE, int C, int V>
     __device__ __forceinline__ void load(long tile, int u, int cg, cplx<T> (&v)[V][1 << LOGE], int field) const {
         constexpr int NT = Geometry<LOG2L, LOGE>::NT, L = 1 << LOG2L;
-        const cplx<T>* p = (field ? in2 : in1) + tile * (long)L * C + cg * V;
+        const cplx<T>* p = (field ? in2 : in1) + tile * (long)L * C + cg * V + u * C;
 #pragma unroll
         for (int q = 0; q < (1 << LOGE); ++q) {
-            const int l = u + q * NT;
             if constexpr (V == 2 && sizeof(T) == 4) {
-                float4 x = *reinterpret_cast<const float4*>(p + (long)l * C);
+                float4 x = *reinterpret_cast<const float4*>(p + q * (NT * C));
                 v[0][q] = mk<T>(x.x, x.y);
                 v[V - 1][q] = mk<T>(x.z, x.w);
             } else {
 #pragma unroll
-                for (int vv = 0; vv < V; ++vv) v[vv][q] = p[(long)l * C + vv];
+                for (int vv = 0; vv < V; ++vv) v[vv][q] = p[q * (NT * C) + vv];
             }
         }
     }
 
     template <int LOG2L, int LOGE, int C, int V>
-    __device__ __forceinline__ void emit_all(long tile, int u, int cg, cplx<T> (&v)[V][1 << LOGE], const cplx<T>* park, int nthr) const {
+    __device__ __forceinline__ void store(long tile, int u, int cg, cplx<T> (&v)[V][1 << LOGE], cplx<T>* smem, const cplx<T>* park,
+                                          int nthr) const {
         using G_ = Geometry<LOG2L, LOGE>;
-        constexpr int R = 1 << G_::LOGR_LAST, G = G_::E / R, E = G_::E;
-        const long b = tile / ntile;
-        const int t0 = (int)(tile - b * ntile);
-        const int M = d.Nx / 2;
+        constexpr int R = 1 << G_::LOGR_LAST, G = G_::E / R, E = G_::E, Ny = 1 << LOG2L, NTHR = G_::NT * (C / V);
+        StageT* stage = reinterpret_cast<StageT*>(smem);
+        const T sc = (T)d.scale;
+        // ---- 1. epilogue value of each owned (ky, c) -> staging [ky][C]
 #pragma unroll
         for (int g = 0; g < G; ++g)
 #pragma unroll
@@ -417,26 +456,135 @@ template <typename T, bool TWO> struct ColsFused {
                 const int ky = final_index<LOG2L, LOGE>(u, g, t);
 #pragma unroll
                 for (int vv = 0; vv < V; ++vv) {
-                    const int kx = t0 * C + cg * V + vv;
-                    if (kx > M) continue;
                     cplx<T> f = v[vv][g + t * G];
-                    cplx<T> f1 = f, f2 = f;
-                    if (TWO) { f1 = park[(vv * E + (g + t * G)) * nthr + threadIdx.x]; f2 = f; }
-                    emit_cell<T>(d, b, ky, kx, false, f1, f2);
+                    StageT val;
+                    if constexpr (MODE == EPI_COMPLEX) val = cscale(f, sc);
+                    else if constexpr (MODE == EPI_POWER || MODE == EPI_BINS_POWER) val = (f.x * f.x + f.y * f.y) * sc;
+                    else {
+                        cplx<T> f1 = park[(vv * E + (g + t * G)) * nthr + threadIdx.x];
+                        val = cscale(cmulc(f1, f), sc);
+                    }
+                    stage[ky * C + cg * V + vv] = val;
+                }
+            }
+        __syncthreads();
+        // ---- 2. cooperative row-segment stores
+        const int Nx = 1 << d.logNx, M = Nx >> 1;
+        const int W = d.full ? Nx : M + 1;
+        const long b = tile / ntile;
+        const int kx0 = (int)(tile - b * ntile) * C;
+        const int sy = d.shift_y ? Ny / 2 : 0, sx = d.shift_x ? Nx / 2 : 0;
+        // per-column invariants
+        cplx<T> rx_d[C], rx_m[C];
+        bool use_rx = false;
+        if constexpr (kCplxStage && !kBins) {
+            use_rx = d.ramp_x != nullptr;
+            if (use_rx) {
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const int kx = kx0 + c;
+                    rx_d[c] = kx <= M ? __ldg(reinterpret_cast<const cplx<T>*>(d.ramp_x) + kx) : mk<T>(1, 0);
+                    rx_m[c] = (d.full && kx > 0 && kx < M) ? __ldg(reinterpret_cast<const cplx<T>*>(d.ramp_x) + (Nx - kx)) : mk<T>(1, 0);
+                }
+            }
+        }
+        T wgt[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) wgt[c] = (T)1;
+        const bool use_w = d.weight_x != nullptr;
+        if (use_w) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) if (kx0 + c <= M) wgt[c] = __ldg(reinterpret_cast<const T*>(d.weight_x) + kx0 + c);
+        }
+        const int ox0 = (kx0 + sx) & (Nx - 1);  // direct cells: ox0 + c (no wrap inside an aligned tile)
+        OutT* outb = kBins ? nullptr : reinterpret_cast<OutT*>(d.out) + b * (long)Ny * W;
+        const bool whole = (kx0 + C - 1 <= M);
+        double* hist = reinterpret_cast<double*>(reinterpret_cast<char*>(smem) + hist_offset_bytes<LOG2L, LOGE, C, V>());
+        for (int ky = threadIdx.x; ky < Ny; ky += NTHR) {
+            StageT p[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) p[c] = stage[ky * C + c];
+            const int kym = (Ny - ky) & (Ny - 1);
+            const int oy = (ky + sy) & (Ny - 1);
+            const int oym = (kym + sy) & (Ny - 1);
+            cplx<T> ry_d = mk<T>(1, 0), ry_m = mk<T>(1, 0);
+            bool use_ry = false;
+            if constexpr (kCplxStage && !kBins) {
+                use_ry = d.ramp_y != nullptr;
+                if (use_ry) {
+                    ry_d = __ldg(reinterpret_cast<const cplx<T>*>(d.ramp_y) + ky);
+                    ry_m = __ldg(reinterpret_cast<const cplx<T>*>(d.ramp_y) + kym);
+                }
+            }
+            if constexpr (!kBins) {
+                OutT* rowd = outb + (long)oy * W + ox0;
+                OutT q[C];
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    StageT x = p[c];
+                    if constexpr (kCplxStage) { if (use_ry) x = cmul(x, ry_d); if (use_rx) x = cmul(x, rx_d[c]); }
+                    if (use_w) x = wscale(x, wgt[c]);
+                    if constexpr (MODE == EPI_PHASE) q[c] = xatan2(x.y, x.x); else q[c] = x;
+                }
+                if (d.full && whole && (C * sizeof(OutT)) % 16 == 0) {
+                    struct alignas(16) Vec { OutT e[C]; };
+                    Vec vv_;
+#pragma unroll
+                    for (int c = 0; c < C; ++c) vv_.e[c] = q[c];
+                    *reinterpret_cast<Vec*>(rowd) = vv_;
+                } else {
+#pragma unroll
+                    for (int c = 0; c < C; ++c) if (kx0 + c <= M) outb[(long)oy * W + ((kx0 + c + sx) & (Nx - 1))] = q[c];
+                }
+                if (d.full == 1) {
+                    OutT* rowm = outb + (long)oym * W;
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        const int kx = kx0 + c;
+                        if (kx > 0 && kx < M) {
+                            StageT x = conj_of(p[c]);
+                            if constexpr (kCplxStage) { if (use_ry) x = cmul(x, ry_m); if (use_rx) x = cmul(x, rx_m[c]); }
+                            OutT o;
+                            if constexpr (MODE == EPI_PHASE) o = xatan2(x.y, x.x); else o = x;
+                            rowm[(Nx - kx + sx) & (Nx - 1)] = o;
+                        }
+                    }
+                }
+            } else {
+                // radial-bin accumulate into the CTA histogram (fp64, shared memory); LUT addressed by OUTPUT cell
+                const int* lutm = d.lut + (long)oym * W;
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const int kx = kx0 + c;
+                    if (kx > M) continue;
+                    StageT x = p[c];
+                    if (use_w) x = wscale(x, wgt[c]);
+                    int bin = __ldg(d.lut + (long)oy * W + ((kx + sx) & (Nx - 1)));
+                    if (bin >= 0) {
+                        if constexpr (kCplxStage) { atomicAdd(hist + 2 * bin, (double)x.x); atomicAdd(hist + 2 * bin + 1, (double)x.y); }
+                        else atomicAdd(hist + bin, (double)x);
+                    }
                     if (d.full && kx > 0 && kx < M) {
-                        const int kym = (d.Ny - ky) & (d.Ny - 1);
-                        emit_cell<T>(d, b, kym, d.Nx - kx, true, cconj(f1), cconj(f2));
+                        bin = __ldg(lutm + ((Nx - kx + sx) & (Nx - 1)));
+                        if (bin >= 0) {
+                            if constexpr (kCplxStage) { atomicAdd(hist + 2 * bin, (double)x.x); atomicAdd(hist + 2 * bin + 1, -(double)x.y); }
+                            else atomicAdd(hist + bin, (double)x);
+                        }
                     }
                 }
             }
-    }
-    template <int LOG2L, int LOGE, int C, int V>
-    __device__ __forceinline__ void store(long tile, int u, int cg, cplx<T> (&v)[V][1 << LOGE]) const {
-        emit_all<LOG2L, LOGE, C, V>(tile, u, cg, v, nullptr, 0);
-    }
-    template <int LOG2L, int LOGE, int C, int V>
-    __device__ __forceinline__ void store2(long tile, int u, int cg, cplx<T> (&v)[V][1 << LOGE], cplx<T>* park, int nthr) const {
-        emit_all<LOG2L, LOGE, C, V>(tile, u, cg, v, park, nthr);
+        }
+        __syncthreads();
+        if constexpr (kBins) {
+            // flush the CTA histogram of this tile to the item's global bins
+            const int nb = d.nbins * (kCplxStage ? 2 : 1);
+            double* bb = d.bins + b * (long)nb;
+            for (int i = threadIdx.x; i < nb; i += NTHR) {
+                double h = hist[i];
+                if (h != 0.0) { atomicAdd(bb + i, h); hist[i] = 0.0; }
+            }
+            __syncthreads();
+        }
     }
 };
 

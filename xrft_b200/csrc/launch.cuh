@@ -17,6 +17,7 @@ static inline int prepare_kernel(Kern kern, int threads, size_t smem, int* occ_c
     return 0;
 }
 
+constexpr int kMaxFusedBins = 1024;
 constexpr int cmin(int a, int b) { return a < b ? a : b; }
 constexpr int cmax(int a, int b) { return a > b ? a : b; }
 
@@ -44,15 +45,19 @@ static int launch_rows(const IO& io, long nseq, cudaStream_t st) {
 }
 
 template <typename T, int LOG2L, int C, class IO>
-static int launch_cols(const IO& io, long ntiles, cudaStream_t st) {
+static int launch_cols(const IO& io, long ntiles, cudaStream_t st, size_t extra_smem = 0) {
     constexpr int LOGE = cmin(TypeCfg<T>::LOGE, LOG2L);
     constexpr int V = cmin(TypeCfg<T>::V, C);
     using G_ = Geometry<LOG2L, LOGE>;
     auto kern = cols_kernel<T, LOG2L, LOGE, C, V, IO>;
     constexpr int threads = G_::NT * (C / V);
-    constexpr size_t smem = (size_t)G_::LPAD * C * sizeof(cplx<T>) + (IO::kTwoFields ? (size_t)G_::L * C * sizeof(cplx<T>) : 0);
+    constexpr size_t smem_fixed = (size_t)G_::LPAD * C * sizeof(cplx<T>) + (IO::kTwoFields ? (size_t)G_::L * C * sizeof(cplx<T>) : 0);
+    // bins modes append a histogram of up to kMaxFusedBins (x2 for complex) doubles
+    constexpr size_t smem_cap = smem_fixed + (IO::kBins ? (size_t)kMaxFusedBins * 2 * sizeof(double) : 0);
+    const size_t smem = smem_fixed + extra_smem;
+    if (smem > smem_cap) { set_error("launch_cols: too many bins for the fused path"); return -2; }
     static int occ = -1;
-    if (int rc = prepare_kernel(kern, threads, smem, &occ)) return rc;
+    if (int rc = prepare_kernel(kern, threads, smem_cap, &occ)) return rc;
     const cplx<T>* tw = twiddle_fft<T>(LOG2L);
     if (!tw) return -3;
     long grid = (long)sm_count() * occ;
