@@ -84,13 +84,19 @@ int xrftb_detrend_window(const void* in, void* out, const double* moments, int d
 /* ---- (S4) generic spectral epilogue over up to 3 trailing transform axes --------------------------
  * in1 (and in2 for CROSS/PHASE): complex [batch][k0][k1][k2in]; hermitian != 0 means the inputs are
  * rfftn half spectra (k2in = k2/2+1) of REAL fields, expanded to the full k2 width on output unless
- * keep_half.  shift[d]: fftshift on axis d (xrft.py:446-447).  ramp[d]: complex vectors indexed by the
+ * keep_half.  shift[d]: 0 none, 1 fftshift (xrft.py:446-447), 2 ifftshift (xrft.py:612-614) on axis d.  ramp[d]: complex vectors indexed by the
  * UNSHIFTED frequency index of axis d (phase ramp xrft.py:462-469; for CROSS the caller passes
  * ramp1*conj(ramp2)), nullable.  weight: real vector on axis 2 (one-sided x2, xrft.py:673-682), nullable.
  * out: complex (COMPLEX, CROSS) or real (POWER, PHASE), [batch][k0][k1][W], W = keep_half ? k2/2+1 : k2. */
 int xrftb_spectral_post(const void* in1, const void* in2, void* out, int dtype, int mode, int64_t batch, int64_t k0,
                         int64_t k1, int64_t k2, int hermitian, int keep_half, const int* shift, const void* const* ramp,
                         const void* weight, double scale, void* stream);
+
+/* circular roll + scale over up to 3 trailing axes, real or complex: out[(i + s) % n] = in[i] * scale.
+ * Replaces the output-side fftm.ifftshift / fftm.fftshift and the `/ prod(spacing)` of xrft.ifft
+ * (xrft.py:617-621, 641-642).  Out of place only. */
+int xrftb_roll_scale(const void* in, void* out, int dtype, int is_complex, int64_t batch, int64_t n0, int64_t n1, int64_t n2,
+                     int64_t s0, int64_t s1, int64_t s2, double scale, void* stream);
 
 /* ---- (S5) _binned_agg(func="sum") ---------------------------------------------------------------
  * array: real (is_complex = 0) or complex [batch][ncell]; lut: int32 [ncell], negative = masked

@@ -1,0 +1,403 @@
+"""GPU parity of the xrft-facing API against the oracle (numpy restatement of the reference).
+
+Ported from the reference's own tests (xrft/tests/test_xrft.py, test_detrend.py, test_padding.py):
+same compositions, same known answers, compared on the same seeded inputs.  Tolerances:
+float64 1e-6 relative (north_star; in practice ~1e-12), float32 1e-3 relative (normwise).
+"""
+import warnings
+
+import numpy as np
+import pytest
+import scipy.signal as sps
+
+pytestmark = pytest.mark.gpu
+
+import xrft_b200 as xrft  # noqa: E402
+from xrft_b200 import DataArray  # noqa: E402
+from oracle import xrft_oracle as O  # noqa: E402
+
+warnings.simplefilter("ignore", FutureWarning)
+
+
+def lab(da: DataArray) -> O.Labelled:
+    coords = {d: da[d].values for d in da.dims if d in da.coords}
+    cattrs = {d: dict(da[d].attrs) for d in da.dims if d in da.coords}
+    chunks = None
+    if da.chunks:
+        chunks = {d: c[0] for d, c in zip(da.dims, da.chunks)}
+    return O.Labelled(da.values, da.dims, coords, cattrs, chunks)
+
+
+def relerr(a, b):
+    a = np.asarray(a); b = np.asarray(b)
+    den = np.linalg.norm(b.ravel())
+    return np.linalg.norm((a - b).ravel()) / (den if den > 0 else 1.0)
+
+
+def same(out: DataArray, ref: O.Labelled, tol=1e-9, check_attrs=True):
+    assert tuple(out.dims) == tuple(ref.dims), (out.dims, ref.dims)
+    assert out.shape == ref.data.shape
+    for d in ref.dims:
+        if d in ref.coords:
+            np.testing.assert_allclose(out[d].values.astype(float) if out[d].values.dtype.kind != "M" else out[d].values.astype("i8"),
+                                       ref.coords[d].astype(float) if ref.coords[d].dtype.kind != "M" else ref.coords[d].astype("i8"),
+                                       rtol=1e-12, atol=1e-12, equal_nan=True)
+        if check_attrs and d in ref.coord_attrs:
+            for k, v in ref.coord_attrs[d].items():
+                assert k in out[d].attrs, (d, k)
+                np.testing.assert_allclose(out[d].attrs[k], v, rtol=1e-12)
+    assert relerr(out.values, ref.data) < tol, relerr(out.values, ref.data)
+
+
+def mk(shape, dims, rng, dt=np.float64, spacing=None, offset=None, cplx=False):
+    data = rng.standard_normal(shape)
+    if cplx:
+        data = data + 1j * rng.standard_normal(shape)
+    data = data.astype(np.complex128 if cplx and dt == np.float64 else np.complex64 if cplx else dt)
+    coords = {}
+    for i, (d, n) in enumerate(zip(dims, shape)):
+        dx = (spacing or {}).get(d, 0.5 + 0.25 * i)
+        x0 = (offset or {}).get(d, 1.0 * i)
+        coords[d] = x0 + dx * np.arange(n)
+    return DataArray(data, dims=dims, coords=coords)
+
+
+# ------------------------------------------------------------------------------------------- fft
+@pytest.mark.parametrize("kw", [
+    dict(), dict(detrend="constant"), dict(detrend="linear"), dict(window="hann"), dict(shift=False),
+    dict(true_phase=False, true_amplitude=False), dict(detrend="linear", window="tukey", true_phase=False),
+])
+@pytest.mark.parametrize("n", [16, 64, 4096])
+def test_fft_1d(kw, n):
+    rng = np.random.default_rng(n)
+    da = mk((n,), ("x",), rng)
+    same(xrft.fft(da, **kw), O.fft(lab(da), **kw))
+
+
+def test_fft_1d_nocoords_and_dft_warning():
+    rng = np.random.default_rng(0)
+    da = DataArray(rng.random(32), dims=["x"])
+    with pytest.warns(FutureWarning):
+        ft = xrft.dft(da, detrend="constant")
+    assert ft.dims == ("freq_x",)
+    np.testing.assert_allclose(ft["freq_x"].values, np.fft.fftshift(np.fft.fftfreq(32, 1)))
+    data = da.values - da.values.mean()
+    np.testing.assert_allclose(ft.values, np.fft.fftshift(np.fft.fft(data)), atol=1e-12)
+    ft = xrft.fft(da, detrend="linear", true_phase=False, true_amplitude=False)
+    np.testing.assert_allclose(ft.values, np.fft.fftshift(np.fft.fft(sps.detrend(da.values))), atol=1e-12)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(), dict(dim=["y"]), dict(dim=["x"]), dict(dim=["y", "x"], detrend="linear", window="hann"),
+    dict(dim=["y", "x"], detrend="constant", window="hamming", shift=False), dict(dim=["x", "y"]),
+    dict(dim=["time"]), dict(real_dim="x", dim=["y", "x"]), dict(real_dim="y", dim=["y", "x"]),
+    dict(real_dim="x", dim=["x"], detrend="linear"), dict(dim=["time", "y", "x"], detrend="linear", window="hann"),
+    dict(dim=["y", "x"], true_phase=False, true_amplitude=False),
+])
+def test_fft_nd(kw):
+    rng = np.random.default_rng(5)
+    da = mk((4, 16, 32), ("time", "y", "x"), rng)
+    same(xrft.fft(da, **kw), O.fft(lab(da), **kw))
+
+
+def test_fft_complex_input_and_decreasing_coords():
+    rng = np.random.default_rng(6)
+    da = mk((8, 16), ("y", "x"), rng, cplx=True)
+    same(xrft.fft(da), O.fft(lab(da)))
+    same(xrft.fft(da, dim=["x"], detrend="constant"), O.fft(lab(da), dim=["x"], detrend="constant"))
+    dd = DataArray(rng.standard_normal((8, 16)), dims=["y", "x"], coords={"y": np.arange(8, 0, -1) * 1.0, "x": np.arange(16, 0, -1) * 0.5})
+    same(xrft.fft(dd), O.fft(lab(dd)))
+    ps = xrft.power_spectrum(dd, shift=False, density=True)
+    assert (ps.values >= 0.0).all()
+
+
+def test_fft_keeps_other_coords_and_name_order():
+    rng = np.random.default_rng(7)
+    da = mk((4, 16, 8), ("time", "y", "x"), rng)
+    ft = xrft.fft(da, dim=["y"])
+    assert ft.dims == ("time", "freq_y", "x")
+    assert "time" in ft.coords and "x" in ft.coords and "y" not in ft.coords
+    np.testing.assert_array_equal(xrft.fft(da, dim="y", shift=False).values, xrft.fft(da, dim=["y"], shift=False).values)
+
+
+def test_fft_float32_mixed_precision_tolerance():
+    rng = np.random.default_rng(8)
+    da = mk((3, 64, 128), ("t", "y", "x"), rng, dt=np.float32)
+    out = xrft.fft(da, dim=["y", "x"], detrend="linear", window="hann")
+    ref = O.fft(lab(da), dim=["y", "x"], detrend="linear", window="hann")
+    same(out, ref, tol=1e-3, check_attrs=False)
+
+
+def test_chunks_to_segments():
+    rng = np.random.default_rng(9)
+    da = mk((64,), ("x",), rng).chunk({"x": 16})
+    out = xrft.fft(da, dim=["x"], chunks_to_segments=True)
+    same(out, O.fft(lab(da), dim=["x"], chunks_to_segments=True))
+    assert out.dims == ("x_segment", "freq_x")
+    da2 = mk((32, 64), ("y", "x"), rng).chunk({"y": 16, "x": 32})
+    same(xrft.power_spectrum(da2, chunks_to_segments=True, window="hann", window_correction=True),
+         O.power_spectrum(lab(da2), chunks_to_segments=True, window="hann", window_correction=True))
+
+
+# ------------------------------------------------------------------------------------- spectra
+@pytest.mark.parametrize("kw", [
+    dict(dim=["y", "x"]), dict(dim=["y", "x"], detrend="constant", window="hann"),
+    dict(dim=["y", "x"], detrend="linear", window="hann", window_correction=True),
+    dict(dim=["y", "x"], scaling="spectrum", window="flattop", window_correction=True),
+    dict(dim=["y", "x"], density=False, window="hann", detrend="constant"),
+    dict(dim=["y"], real_dim="x", window="hann", density=False, detrend="constant"),
+    dict(dim=["x"], real_dim="x", detrend="constant"), dict(dim=["time"], shift=False),
+    dict(dim=["y", "x"], real_dim="x", detrend="linear", window="bartlett"),
+])
+def test_power_spectrum(kw):
+    rng = np.random.default_rng(10)
+    da = mk((2, 16, 32), ("time", "y", "x"), rng)
+    same(xrft.power_spectrum(da, **kw), O.power_spectrum(lab(da), **kw))
+
+
+def test_power_spectrum_periodogram_known_answer():
+    """xrft/tests/test_xrft.py:389-404"""
+    rng = np.random.default_rng(11)
+    da = DataArray(rng.random(16), dims=["x"], coords={"x": np.arange(16)})
+    f, p = sps.periodogram(da.values, window="rectangular", return_onesided=True)
+    ps = xrft.power_spectrum(da, dim="x", real_dim="x", detrend="constant")
+    np.testing.assert_almost_equal(ps.values, p)
+
+
+def test_power_spectrum_sine_amplitude_known_answer():
+    """xrft/tests/test_xrft.py:406-442 (segment length 1024 instead of 1000: power-of-two path)"""
+    A, fs, fsig, nseg = 20, 16384.0, 512.0, 1024
+    tt = np.arange(int(fs)) / fs
+    x = A * np.sin(2 * np.pi * fsig * tt)
+    for window_type in ["hann", "bartlett", "tukey", "flattop"]:
+        x_da = DataArray(x, coords=[tt], dims=["t"]).chunk({"t": nseg})
+        ps = xrft.power_spectrum(x_da, dim="t", window=window_type, chunks_to_segments=True, window_correction=True).mean("t_segment")
+        np.testing.assert_allclose(np.sqrt(np.trapezoid(ps.values, ps["freq_t"].values)), A * np.sqrt(2) / 2, rtol=1e-3)
+        ps = xrft.power_spectrum(x_da, dim="t", window=window_type, chunks_to_segments=True, scaling="spectrum",
+                                 window_correction=True).mean("t_segment")
+        np.testing.assert_allclose(ps.sel(freq_t=fsig).values, 0.5 * A ** 2 / 2.0)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(dim=["y", "x"]), dict(dim=["y", "x"], detrend="constant", window="hann", window_correction=True),
+    dict(dim=["y", "x"], true_phase=False, scaling="spectrum"), dict(dim=["x"], real_dim="x", detrend="linear"),
+    dict(dim=["y", "x"], density=False, window="hann"),
+])
+def test_cross_spectrum_and_phase(kw):
+    rng = np.random.default_rng(12)
+    a = mk((2, 16, 32), ("time", "y", "x"), rng)
+    b = mk((2, 16, 32), ("time", "y", "x"), rng)
+    cs_ref = O.cross_spectrum(lab(a), lab(b), **kw)
+    same(xrft.cross_spectrum(a, b, **kw), cs_ref)
+    ref = O.cross_phase(lab(a), lab(b), **kw)
+    out = xrft.cross_phase(a, b, **kw)
+    assert out.dims == ref.dims
+    d = np.angle(np.exp(1j * (out.values - ref.data)))  # compare modulo 2 pi (branch cut at +-pi)
+    sig = np.abs(cs_ref.data) > 1e-9 * np.abs(cs_ref.data).max()  # the angle of a ~0 bin (DC after detrend) is noise
+    assert np.abs(d[sig]).max() < 1e-7
+
+
+def test_cross_phase_true_phase_lagged_coords():
+    """xrft/tests/test_xrft.py:661-690: different coordinate origins leave a phase ramp in the cross spectrum."""
+    rng = np.random.default_rng(13)
+    a = mk((16, 32), ("y", "x"), rng, offset={"y": 0.0, "x": 0.0})
+    b = mk((16, 32), ("y", "x"), rng, offset={"y": 0.5, "x": 2.0})
+    same(xrft.cross_spectrum(a, b), O.cross_spectrum(lab(a), lab(b)))
+    out, ref = xrft.cross_phase(a, b), O.cross_phase(lab(a), lab(b))
+    d = np.angle(np.exp(1j * (out.values - ref.data)))
+    assert np.abs(d).max() < 1e-7
+
+
+def test_cross_phase_1d_known_answer():
+    """xrft/tests/test_xrft.py:608-633: two sines in quadrature have cross phase pi/2 at the signal frequency."""
+    N = 32
+    x = np.linspace(0, 1, num=N, endpoint=False)
+    f = 6
+    p1, p2 = 0, np.pi / 2
+    da1 = DataArray(np.cos(2 * np.pi * f * x + p1), dims=["x"], coords={"x": x}, name="a")
+    da2 = DataArray(np.cos(2 * np.pi * f * x + p2), dims=["x"], coords={"x": x}, name="b")
+    cp = xrft.cross_phase(da1, da2)
+    assert cp.name == "a_b_phase"
+    actual = cp.sel(freq_x=f).values
+    np.testing.assert_almost_equal(actual, p1 - p2)
+    with pytest.raises(ValueError):
+        xrft.cross_phase(da1, DataArray(da2.values[:, None].repeat(4, 1), dims=["x", "z"], coords={"x": x, "z": np.arange(4.)}))
+
+
+def test_parseval():
+    """xrft/tests/test_xrft.py:693-842 (power-of-two sizes)"""
+    rng = np.random.default_rng(14)
+    N = 16
+    dx, dy = 1.0, 0.5
+    da = DataArray(rng.random((N, N)), dims=["x", "y"], coords={"x": dx * np.arange(N), "y": dy * np.arange(N)})
+    # (1/dxdy) * mean(ps) == mean(da^2)   (xrft/tests/test_xrft.py:727-731)
+    ps = xrft.power_spectrum(da, window=None)
+    np.testing.assert_almost_equal(ps.values.mean() / (dx * dy), (np.asarray(da.values) ** 2).mean(), decimal=5)
+    ps = xrft.power_spectrum(da, window="hann", detrend="constant")
+    w = sps.windows.hann(N, sym=False)
+    win = w[:, None] * w[None, :]
+    dprime = da.values - da.values.mean()
+    np.testing.assert_almost_equal(ps.values.mean() / (dx * dy), ((dprime * win) ** 2).mean(), decimal=5)
+    # one-sided (real_dim) spectrum integrates to the same variance: sum(ps) dk dl == mean(da^2)
+    ps = xrft.power_spectrum(da, real_dim="y")
+    np.testing.assert_almost_equal(ps.values.sum() * np.prod([ps[d].attrs["spacing"] for d in ps.dims]),
+                                   (da.values ** 2).mean(), decimal=5)
+
+
+# ------------------------------------------------------------------------------------- inverse
+@pytest.mark.parametrize("real_dim", [None, "x"])
+def test_ifft_fft_round_trip(real_dim):
+    rng = np.random.default_rng(15)
+    da = mk((8, 16, 32), ("t", "y", "x"), rng, offset={"y": -3.0, "x": 7.0})
+    ft = xrft.fft(da, dim=["y", "x"], real_dim=real_dim)
+    ref_ft = O.fft(lab(da), dim=["y", "x"], real_dim=real_dim)
+    kw = dict(dim=["freq_y", "freq_x"], real_dim="freq_x" if real_dim else None)
+    back = xrft.ifft(ft, **kw)
+    ref = O.ifft(ref_ft, **kw)
+    same(back, ref, check_attrs=True)
+    np.testing.assert_allclose(back.values.real, da.values, atol=1e-10)
+    np.testing.assert_allclose(back["x"].values, da["x"].values, atol=1e-12)
+    # explicit lag, shift False, true_phase False
+    for kw2 in [dict(lag=[0.0, 0.0]), dict(shift=False), dict(true_phase=False, lag=[0.0, 0.0])]:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            same(xrft.ifft(ft, **kw, **kw2), O.ifft(ref_ft, **kw, **kw2))
+
+
+def test_idft_dft_1d():
+    rng = np.random.default_rng(16)
+    da = mk((64,), ("x",), rng)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        back = xrft.idft(xrft.dft(da, true_phase=True, true_amplitude=True), true_phase=True, true_amplitude=True)
+    np.testing.assert_allclose(back.values.real, da.values, atol=1e-12)
+
+
+# ------------------------------------------------------------------------------------ isotropic
+@pytest.mark.parametrize("truncate", [False, True])
+@pytest.mark.parametrize("n", [32, 128])
+def test_isotropize_and_isotropic_spectra(truncate, n):
+    rng = np.random.default_rng(17)
+    da = mk((3, n, n), ("t", "y", "x"), rng, spacing={"y": 1.0, "x": 1.0})
+    kw = dict(dim=["y", "x"], detrend="constant", window="hann", truncate=truncate)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out = xrft.isotropic_power_spectrum(da, **kw)
+        ref = O.isotropic_power_spectrum(lab(da), **kw)
+    assert out.dims == ref.dims == ("t", "freq_r")
+    np.testing.assert_allclose(out["freq_r"].values, ref.coords["freq_r"], rtol=1e-12, equal_nan=True)
+    assert relerr(out.values, ref.data) < 1e-10
+    # sum conservation (xrft/tests/test_xrft.py:963)
+    ps = xrft.power_spectrum(da, dim=["y", "x"], detrend="constant", window="hann")
+    np.testing.assert_allclose(out.values.sum(axis=-1), ps.values.sum(axis=(-2, -1)), rtol=1e-10)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        iso2 = xrft.isotropize(ps, ["freq_y", "freq_x"], truncate=truncate)
+    assert relerr(iso2.values, ref.data) < 1e-10
+    b = mk((3, n, n), ("t", "y", "x"), rng, spacing={"y": 1.0, "x": 1.0})
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        outc = xrft.isotropic_cross_spectrum(da, b, **kw)
+        refc = O.isotropic_cross_spectrum(lab(da), lab(b), **kw)
+    assert relerr(outc.values, refc.data) < 1e-10
+    with pytest.raises(ValueError):
+        xrft.isotropic_power_spectrum(da, dim=["t", "y", "x"])
+
+
+def test_isotropic_slope():
+    """xrft/tests/test_xrft.py:995-1031: a k^-3 synthetic field isotropizes to slope -3 (N = 512)."""
+    N, dL, amp, s = 512, 1.0, 1e1, -3.0
+    rng = np.random.default_rng(18)
+    k = np.fft.fftshift(np.fft.fftfreq(N, dL))
+    kk, ll = np.meshgrid(k, k)
+    K = np.sqrt(kk ** 2 + ll ** 2)
+    with np.errstate(divide="ignore"):
+        spec = np.where(K > 0, amp * K ** (s - 1.0), 0.0)
+    phase = rng.uniform(-np.pi, np.pi, (N, N))
+    F = np.sqrt(spec) * np.exp(1j * phase)
+    field = np.real(np.fft.ifft2(np.fft.ifftshift(F))) * N
+    da = DataArray(field, dims=["y", "x"], coords={"y": np.arange(N) * dL, "x": np.arange(N) * dL})
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        iso = xrft.isotropic_power_spectrum(da, dim=["y", "x"], window="hann", detrend="constant", truncate=True)
+    kr = iso["freq_r"].values
+    good = np.isfinite(kr) & (kr > 0)
+    sel = good & (np.arange(kr.size) >= 4) & (np.arange(kr.size) < kr.size // 2)
+    _, slope, _ = xrft.fit_loglog(kr[sel], iso.values[sel])
+    assert abs(slope - s) < 0.25
+
+
+# ---------------------------------------------------------------------------------- detrend/pad
+@pytest.mark.parametrize("dims,detrend_dims", [(("x",), ["x"]), (("y", "x"), ["y", "x"]), (("t", "y", "x"), ["y", "x"]),
+                                               (("z", "y", "x"), ["z", "y", "x"]), (("t", "y", "x"), ["t"]), (("t", "y", "x"), ["y"])])
+@pytest.mark.parametrize("kind", ["constant", "linear"])
+def test_detrend(dims, detrend_dims, kind):
+    rng = np.random.default_rng(19)
+    shape = (8, 16, 32)[3 - len(dims):]
+    da = mk(shape, dims, rng)
+    trend = sum((i + 1) * 0.37 * np.arange(n).reshape([-1 if j == i else 1 for j in range(len(shape))]) for i, n in enumerate(shape))
+    da = da + trend
+    same(xrft.detrend(da, detrend_dims, kind), O.detrend(lab(da), detrend_dims, kind), tol=1e-10)
+
+
+def test_pad_fft_ifft_unpad_round_trip():
+    """xrft/tests/test_padding.py:207-234"""
+    rng = np.random.default_rng(20)
+    da = mk((24, 48), ("y", "x"), rng, spacing={"y": 0.5, "x": 0.25}, offset={"y": -1.0, "x": 3.0})
+    padded = xrft.pad(da, x=8, y=4)
+    assert padded.shape == (32, 64)
+    ref_p = O.pad(lab(da), {"x": 8, "y": 4})
+    np.testing.assert_allclose(padded["x"].values, ref_p.coords["x"])
+    assert padded["x"].attrs["pad_width"] == 8
+    ft = xrft.fft(padded, real_dim="x", true_phase=True)
+    back = xrft.ifft(ft, real_dim="freq_x", true_phase=True)
+    back = back.assign_coords({"x": DataArray(back["x"].values, dims=("x",), attrs={"pad_width": 8}),
+                               "y": DataArray(back["y"].values, dims=("y",), attrs={"pad_width": 4})})
+    un = xrft.unpad(back)
+    np.testing.assert_allclose(un.values, da.values, atol=1e-10)
+    np.testing.assert_allclose(un["x"].values, da["x"].values, atol=1e-10)
+
+
+# ------------------------------------------------------------------ large sizes, property checks
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_large_power_spectrum_properties(dt):
+    """BASELINE config-2 slice size (4096^2): Parseval + oracle parity on one slice."""
+    import torch
+    n = 4096 if dt == np.float32 else 2048
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    x = torch.randn((2, n, n), generator=g, device="cuda", dtype=torch.float32 if dt == np.float32 else torch.float64)
+    x += 0.3 * torch.arange(n, device="cuda") - 0.7 * torch.arange(n, device="cuda")[:, None] + 5
+    da = DataArray(x, dims=["time", "y", "x"], coords={"time": np.arange(2.), "y": np.arange(n) * 1.0, "x": np.arange(n) * 1.0})
+    ps = xrft.power_spectrum(da, dim=["y", "x"], detrend="linear", window="hann")
+    assert ps.dims == ("time", "freq_y", "freq_x")
+    # Parseval: sum(ps) * dk*dl == sum((w * detrended)^2) * dx*dy
+    xd = xrft.detrend(da, ["y", "x"], "linear").values.astype(np.float64)
+    w = sps.windows.hann(n, sym=False)
+    e_space = ((xd * (w[:, None] * w[None, :])) ** 2).mean(axis=(1, 2))
+    e_spec = ps.values.astype(np.float64).mean(axis=(1, 2))  # dx = dy = 1
+    np.testing.assert_allclose(e_spec, e_space, rtol=2e-4 if dt == np.float32 else 1e-10)
+    # Hermitian symmetry of the full spectrum of a real field
+    p = ps.values[0]
+    np.testing.assert_allclose(p[1:, 1:], p[1:, 1:][::-1, ::-1], rtol=1e-5)
+    # oracle parity on the first slice (the oracle's dense least-squares detrend takes a few seconds)
+    ref = O.power_spectrum(O.Labelled(da.values[:1].astype(np.float64), da.dims, {"y": np.arange(n) * 1.0, "x": np.arange(n) * 1.0}),
+                           dim=["y", "x"], detrend="linear", window="hann").data
+    assert relerr(ps.values[:1], ref) < (1e-3 if dt == np.float32 else 1e-6)
+
+
+def test_rfft_irfft_round_trip_padded_f64():
+    """BASELINE config 5 at a reduced size: pad -> rfft -> irfft -> unpad + Parseval."""
+    import torch
+    n, p = 1024, 512
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn((n, n), generator=g, device="cuda", dtype=torch.float64)
+    da = DataArray(x, dims=["y", "x"], coords={"y": np.arange(n) * 0.5, "x": np.arange(n) * 0.5})
+    padded = xrft.pad(da, x=p, y=p)
+    ft = xrft.fft(padded, real_dim="x")
+    back = xrft.ifft(ft, real_dim="freq_x")
+    un = xrft.unpad(back, {"x": p, "y": p})
+    err = np.abs(un.values - da.values).max() / np.abs(da.values).max()
+    assert err < 1e-6
+    ps = xrft.power_spectrum(padded, real_dim="x")
+    np.testing.assert_allclose(ps.values.sum() * ps["freq_x"].attrs["spacing"] * ps["freq_y"].attrs["spacing"],
+                               (padded.values ** 2).mean(), rtol=1e-10)

@@ -21,6 +21,7 @@ EXPORTS = [
     "xrftb_moments",
     "xrftb_detrend_window",
     "xrftb_spectral_post",
+    "xrftb_roll_scale",
     "xrftb_binned_sum",
     "xrftb_spectrum2d_workspace",
     "xrftb_spectrum2d",
@@ -89,12 +90,13 @@ def load():
     lib.xrftb_detrend_window.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64, vp]
     lib.xrftb_spectral_post.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int,
                                         C.c_int, ip, C.POINTER(vp), vp, C.c_double, vp]
+    lib.xrftb_roll_scale.argtypes = [vp, vp, C.c_int, C.c_int] + [C.c_int64] * 7 + [C.c_double, vp]
     lib.xrftb_binned_sum.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int, vp]
     lib.xrftb_spectrum2d_workspace.restype = C.c_size_t
     lib.xrftb_spectrum2d_workspace.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64]
     lib.xrftb_spectrum2d.argtypes = [C.POINTER(Spectrum2dDesc), vp]
     for name in ["xrftb_device_info", "xrftb_fftn", "xrftb_moments", "xrftb_detrend_window", "xrftb_spectral_post",
-                 "xrftb_binned_sum", "xrftb_spectrum2d"]:
+                 "xrftb_binned_sum", "xrftb_spectrum2d", "xrftb_roll_scale"]:
         getattr(lib, name).restype = C.c_int
     _lib = lib
     return lib

@@ -188,7 +188,7 @@ def spectral_post(f1: torch.Tensor, f2: Optional[torch.Tensor], mode: int, ntrai
     sh = [0, 0, 0]
     rp = [None, None, None]
     for i in range(ntrail):
-        sh[3 - ntrail + i] = 1 if shift[i] else 0
+        sh[3 - ntrail + i] = int(shift[i]) if shift[i] else 0
         if ramps and ramps[i] is not None:
             rp[3 - ntrail + i] = ramps[i].to(device=f1.device, dtype=f1.dtype).contiguous()
     rarr = (C.c_void_p * 3)(*[r.data_ptr() if r is not None else None for r in rp])
@@ -198,6 +198,26 @@ def spectral_post(f1: torch.Tensor, f2: Optional[torch.Tensor], mode: int, ntrai
                                      1 if hermitian else 0, 1 if keep_half else 0, _ints(sh), rarr, _ptr(wt), float(scale),
                                      _stream())
     L.check(rc, "xrftb_spectral_post")
+    return out
+
+
+def roll_scale(x: torch.Tensor, ntrail: int, shifts: Sequence[int], scale: float) -> torch.Tensor:
+    """out[(i + s) % n] = x[i] * scale over the last `ntrail` axes (real or complex)."""
+    lib = require_cuda()
+    x = _dev(x)
+    if all(int(s) == 0 for s in shifts) and scale == 1.0:
+        return x
+    is_c = x.dtype in _CPLX
+    dt = _CPLX[x.dtype] if is_c else _REAL[x.dtype]
+    batch, core = _view4(x, ntrail)
+    sh = [0, 0, 0]
+    for i, s in enumerate(shifts):
+        sh[3 - ntrail + i] = int(s)
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        rc = lib.xrftb_roll_scale(_ptr(x), _ptr(out), dt, 1 if is_c else 0, batch, core[0], core[1], core[2], sh[0], sh[1], sh[2],
+                                  float(scale), _stream())
+    L.check(rc, "xrftb_roll_scale")
     return out
 
 

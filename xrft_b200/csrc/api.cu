@@ -207,9 +207,10 @@ __global__ void __launch_bounds__(256) spectral_post_kernel(const cplx<T>* __res
         const long o0 = r % d.k0;
         const long b = r / d.k0;
         // o = (k + N/2) % N  <=>  k = (o + N - N/2) % N
-        const long f0 = d.shift[0] ? (o0 + d.k0 - d.k0 / 2) % d.k0 : o0;
-        const long f1 = d.shift[1] ? (o1 + d.k1 - d.k1 / 2) % d.k1 : o1;
-        const long f2 = d.shift[2] ? (o2 + d.k2 - d.k2 / 2) % d.k2 : o2;
+        // shift 1 (fftshift): o = (f + N/2) % N ; shift 2 (ifftshift): o = (f + N - N/2) % N
+        const long f0 = d.shift[0] == 1 ? (o0 + d.k0 - d.k0 / 2) % d.k0 : d.shift[0] == 2 ? (o0 + d.k0 / 2) % d.k0 : o0;
+        const long f1 = d.shift[1] == 1 ? (o1 + d.k1 - d.k1 / 2) % d.k1 : d.shift[1] == 2 ? (o1 + d.k1 / 2) % d.k1 : o1;
+        const long f2 = d.shift[2] == 1 ? (o2 + d.k2 - d.k2 / 2) % d.k2 : d.shift[2] == 2 ? (o2 + d.k2 / 2) % d.k2 : o2;
         long s0 = f0, s1 = f1, s2 = f2;
         bool cj = false;
         if (d.hermitian && f2 > d.k2 / 2) {
@@ -235,6 +236,25 @@ __global__ void __launch_bounds__(256) spectral_post_kernel(const cplx<T>* __res
         if (d.mode == EPI_COMPLEX || d.mode == EPI_CROSS) reinterpret_cast<cplx<T>*>(out)[i] = val;
         else if (d.mode == EPI_POWER) reinterpret_cast<T*>(out)[i] = val.x;
         else reinterpret_cast<T*>(out)[i] = xatan2(val.y, val.x);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// circular roll + scale over up to 3 trailing axes: out[(i + s) % n] = in[i] * scale (np.fft.fftshift /
+// ifftshift of xrft.py:617-621 and the 1/prod(spacing) of xrft.py:641-642 on the inverse path)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) roll_scale_kernel(const T* __restrict__ in, T* __restrict__ out, long n0, long n1, long n2,
+                                                         long s0, long s1, long s2, int width, T scale, long total) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long i2 = i % n2;
+        long r = i / n2;
+        const long i1 = r % n1;
+        r /= n1;
+        const long i0 = r % n0;
+        const long b = r / n0;
+        const long o = ((b * n0 + (i0 + s0) % n0) * n1 + (i1 + s1) % n1) * n2 + (i2 + s2) % n2;
+        for (int w = 0; w < width; ++w) out[o * width + w] = in[i * width + w] * scale;
     }
 }
 
@@ -601,6 +621,22 @@ int xrftb_binned_sum(const void* array, const int32_t* lut, double* bins, int dt
         else binned_sum_kernel<double, false><<<grid, 256, smem, st>>>(reinterpret_cast<const double*>(array), lut, bins, ncell, nbins, chunks);
     } else { set_error("binned_sum: bad dtype"); return XRFTB_EINVAL; }
     return check_launch("binned_sum_kernel");
+}
+
+int xrftb_roll_scale(const void* in, void* out, int dtype, int is_complex, int64_t batch, int64_t n0, int64_t n1, int64_t n2,
+                     int64_t s0, int64_t s1, int64_t s2, double scale, void* stream) {
+    if (!in || !out || in == out) { set_error("roll_scale: bad arguments (in-place is not supported)"); return XRFTB_EINVAL; }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const long total = batch * n0 * n1 * n2;
+    const int width = is_complex ? 2 : 1;
+    if (dtype == XRFTB_F32)
+        roll_scale_kernel<float><<<ew_grid(total), 256, 0, st>>>(reinterpret_cast<const float*>(in), reinterpret_cast<float*>(out), n0, n1, n2,
+            ((s0 % n0) + n0) % n0, ((s1 % n1) + n1) % n1, ((s2 % n2) + n2) % n2, width, (float)scale, total);
+    else if (dtype == XRFTB_F64)
+        roll_scale_kernel<double><<<ew_grid(total), 256, 0, st>>>(reinterpret_cast<const double*>(in), reinterpret_cast<double*>(out), n0, n1, n2,
+            ((s0 % n0) + n0) % n0, ((s1 % n1) + n1) % n1, ((s2 % n2) + n2) % n2, width, scale, total);
+    else { set_error("roll_scale: bad dtype"); return XRFTB_EINVAL; }
+    return check_launch("roll_scale_kernel");
 }
 
 size_t xrftb_spectrum2d_workspace(int dtype, int ny, int nx, int two_fields, int64_t batch_in_flight) {

@@ -1,0 +1,751 @@
+"""A minimal, duck-typed stand-in for ``xarray.DataArray``.
+
+``xarray`` (like dask, numpy_groupies and cftime) is not installable in this image
+(SURVEY.md F2), so the xrft-facing API of xrft_b200 works on this class; real
+``xarray.DataArray`` objects are accepted and returned when xarray is importable
+(see ``from_any`` / ``to_xarray``).  Only the surface the reference uses is covered
+(SURVEY.md Appendix B): named dims, 1-D dimension coordinates with attrs, name-based
+broadcasting arithmetic, numpy ufunc dispatch, and the handful of reshaping methods
+xrft calls.  ``data`` may be a numpy array or a torch tensor (CPU or CUDA); ``values``
+is always numpy.  ``chunks`` is plain metadata ({dim: chunk length}) standing in for
+dask chunking (used by ``chunks_to_segments`` and the multi-GPU sharder).
+"""
+from __future__ import annotations
+
+import numbers
+from collections import OrderedDict
+from typing import Any, Dict, Hashable, Iterable, Mapping, Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+try:  # torch is plumbing for device memory; the shim itself works without it
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+
+def _is_torch(x) -> bool:
+    return torch is not None and isinstance(x, torch.Tensor)
+
+
+def _to_numpy(x) -> np.ndarray:
+    if _is_torch(x):
+        return x.detach().cpu().numpy()
+    return np.asarray(x)
+
+
+class _KeepAttrs:
+    value = False
+
+
+class set_options:
+    """``xr.set_options(keep_attrs=True)`` context manager (xrft/xrft.py:634-639)."""
+
+    def __init__(self, keep_attrs=None, **_):
+        self.keep_attrs = keep_attrs
+
+    def __enter__(self):
+        self._old = _KeepAttrs.value
+        if self.keep_attrs is not None:
+            _KeepAttrs.value = bool(self.keep_attrs)
+        return self
+
+    def __exit__(self, *exc):
+        _KeepAttrs.value = self._old
+        return False
+
+
+class Coordinates(OrderedDict):
+    """name -> DataArray (1-D for dimension coordinates)."""
+
+    def __init__(self, owner=None):
+        super().__init__()
+        self._owner = owner
+
+    def __setitem__(self, key, value):
+        if not isinstance(value, DataArray):
+            arr = np.asarray(value)
+            dims = (key,) if arr.ndim == 1 else ()
+            value = DataArray(arr, dims=dims, name=key, _coord=True)
+        elif not value._is_coord:
+            value = DataArray(value.data, dims=value.dims, name=key, attrs=value.attrs, _coord=True)
+        OrderedDict.__setitem__(self, key, value)
+
+    def to_index(self):  # pragma: no cover - convenience
+        return {k: v.values for k, v in self.items()}
+
+
+def _normalize_coords(coords, dims, shape) -> "Coordinates":
+    out = Coordinates()
+    if coords is None:
+        return out
+    if isinstance(coords, Mapping):
+        items = list(coords.items())
+    else:  # list aligned with dims (xarray allows coords=[x, y])
+        items = list(zip(dims, coords))
+    for name, val in items:
+        if isinstance(val, DataArray):
+            c = DataArray(val.data, dims=val.dims if val.dims else (), name=name, attrs=dict(val.attrs), _coord=True)
+        elif isinstance(val, tuple) and len(val) in (2, 3) and isinstance(val[0], (str, list, tuple)):
+            cd = (val[0],) if isinstance(val[0], str) else tuple(val[0])
+            c = DataArray(np.asarray(val[1]), dims=cd, name=name, attrs=dict(val[2]) if len(val) == 3 else None, _coord=True)
+        else:
+            arr = np.asarray(val) if not _is_torch(val) else _to_numpy(val)
+            if isinstance(val, range):
+                arr = np.arange(val.start, val.stop, val.step)
+            c = DataArray(arr, dims=(name,) if arr.ndim == 1 else (), name=name, _coord=True)
+        for d, n in zip(c.dims, c.shape):
+            if d in dims and shape[dims.index(d)] != n:
+                raise ValueError(f"conflicting sizes for dimension {d!r}: length {n} on coordinate {name!r} and {shape[dims.index(d)]} on the data")
+        OrderedDict.__setitem__(out, name, c)
+    return out
+
+
+class DataArray:
+    __array_priority__ = 60
+
+    def __init__(self, data, coords=None, dims=None, name=None, attrs=None, _coord=False, chunks=None):
+        if isinstance(data, DataArray):
+            coords = coords if coords is not None else data.coords
+            dims = dims if dims is not None else data.dims
+            name = name if name is not None else data.name
+            attrs = attrs if attrs is not None else data.attrs
+            data = data.data
+        if not _is_torch(data):
+            data = np.asarray(data)
+        self._data = data
+        ndim = data.ndim
+        if dims is None:
+            if coords is not None and not isinstance(coords, Mapping):
+                dims = tuple(getattr(c, "name", None) or f"dim_{i}" for i, c in enumerate(coords))
+            elif isinstance(coords, Mapping) and len(coords) == ndim and ndim > 0:
+                dims = tuple(coords.keys())
+            else:
+                dims = tuple(f"dim_{i}" for i in range(ndim))
+        if isinstance(dims, str):
+            dims = (dims,)
+        dims = tuple(dims)
+        if len(dims) != ndim:
+            raise ValueError(f"different number of dimensions on data ({ndim}) and dims ({len(dims)})")
+        self._dims = dims
+        self.name = name
+        self.attrs = dict(attrs) if attrs else {}
+        self._is_coord = _coord
+        self._chunks = dict(chunks) if chunks else None
+        if _coord:
+            self._coords = Coordinates()
+        else:
+            self._coords = _normalize_coords(coords, dims, tuple(data.shape))
+
+    # ------------------------------------------------------------------ basic properties
+    @property
+    def data(self):
+        return self._data
+
+    @data.setter
+    def data(self, v):
+        self._data = v
+
+    @property
+    def values(self) -> np.ndarray:
+        return _to_numpy(self._data)
+
+    @property
+    def dims(self) -> Tuple[str, ...]:
+        return self._dims
+
+    @property
+    def shape(self):
+        return tuple(self._data.shape)
+
+    @property
+    def ndim(self):
+        return self._data.ndim
+
+    @property
+    def size(self):
+        return int(np.prod(self.shape)) if self.ndim else 1
+
+    @property
+    def sizes(self):
+        return OrderedDict(zip(self._dims, self.shape))
+
+    @property
+    def dtype(self):
+        return self.values.dtype if not _is_torch(self._data) else _to_numpy(self._data[..., :0] if self.ndim else self._data).dtype
+
+    @property
+    def coords(self):
+        if self._is_coord and self.name is not None and len(self._dims) == 1 and self.name == self._dims[0] and not self._coords:
+            c = Coordinates()
+            OrderedDict.__setitem__(c, self.name, self)
+            return c
+        return self._coords
+
+    @property
+    def chunks(self):
+        """None, or a tuple of per-dim chunk-length tuples (dask-like), from the {dim: length} metadata."""
+        if not self._chunks:
+            return None
+        out = []
+        for d, n in zip(self._dims, self.shape):
+            c = self._chunks.get(d, n)
+            c = n if c in (-1, None) else int(c)
+            full, rem = divmod(n, c)
+            out.append(tuple([c] * full + ([rem] if rem else [])))
+        return tuple(out)
+
+    def chunk(self, chunks=None, **kw):
+        ch = dict(chunks or {})
+        ch.update(kw)
+        if not ch:
+            ch = {d: n for d, n in zip(self._dims, self.shape)}
+        return self._replace(chunks=ch)
+
+    def compute(self):
+        return self
+
+    load = compute
+
+    @property
+    def real(self):
+        return self._replace(data=self._data.real)
+
+    @property
+    def imag(self):
+        return self._replace(data=self._data.imag)
+
+    @property
+    def T(self):
+        return self.transpose(*self._dims[::-1])
+
+    def conj(self):
+        return self._replace(data=self._data.conj())
+
+    def item(self):
+        return self.values.item()
+
+    def astype(self, dt):
+        return self._replace(data=self.values.astype(dt))
+
+    def __len__(self):
+        return self.shape[0]
+
+    def __iter__(self):
+        for i in range(len(self)):
+            yield self[i]
+
+    def __float__(self):
+        return float(self.values)
+
+    def __int__(self):
+        return int(self.values)
+
+    def __complex__(self):
+        return complex(self.values)
+
+    def __bool__(self):
+        return bool(self.values)
+
+    def __array__(self, dtype=None, copy=None):
+        v = self.values
+        return v.astype(dtype) if dtype is not None else v
+
+    def __repr__(self):
+        return f"<xrft_b200.DataArray {self.name!r} {dict(self.sizes)} dtype={self.dtype}>\n{self.values!r}\nCoordinates: {list(self.coords)}"
+
+    def __getattr__(self, name):
+        # attribute-style access to coords and attrs (da.x, coord.spacing)
+        if name.startswith("_"):
+            raise AttributeError(name)
+        coords = self.__dict__.get("_coords")
+        if coords is not None and name in coords:
+            return coords[name]
+        dims = self.__dict__.get("_dims", ())
+        if name in dims:
+            return self[name]
+        attrs = self.__dict__.get("attrs", {})
+        if name in attrs:
+            return attrs[name]
+        raise AttributeError(f"{type(self).__name__!s} has no attribute {name!r}")
+
+    # ------------------------------------------------------------------ construction helpers
+    def _replace(self, data=None, dims=None, coords=None, name="__keep__", attrs="__keep__", chunks="__keep__"):
+        out = DataArray.__new__(DataArray)
+        out._data = self._data if data is None else data
+        out._dims = self._dims if dims is None else tuple(dims)
+        out.name = self.name if name == "__keep__" else name
+        out.attrs = dict(self.attrs) if attrs == "__keep__" else dict(attrs or {})
+        out._is_coord = self._is_coord
+        out._chunks = (dict(self._chunks) if self._chunks else None) if chunks == "__keep__" else (dict(chunks) if chunks else None)
+        if coords is None:
+            c = Coordinates()
+            for k, v in self._coords.items():
+                OrderedDict.__setitem__(c, k, v)
+            out._coords = c
+        else:
+            out._coords = coords
+        return out
+
+    def copy(self, deep=True, data=None):
+        if data is None:
+            data = self._data.clone() if _is_torch(self._data) else np.array(self._data, copy=True)
+        elif not _is_torch(data):
+            data = np.asarray(data)
+            if data.shape != self.shape:
+                raise ValueError("copy(data=...) must keep the shape")
+        out = self._replace(data=data)
+        c = Coordinates()
+        for k, v in self.coords.items():
+            OrderedDict.__setitem__(c, k, v._replace() if v is not self else v)
+        if not self._is_coord:
+            out._coords = c
+        return out
+
+    def get_axis_num(self, dim):
+        if isinstance(dim, (list, tuple)):
+            return tuple(self._dims.index(d) for d in dim)
+        try:
+            return self._dims.index(dim)
+        except ValueError:
+            raise ValueError(f"{dim!r} not found in array dimensions {self._dims!r}")
+
+    # ------------------------------------------------------------------ indexing
+    def _coord_for_dim(self, d) -> "DataArray":
+        if d in self._coords:
+            return self._coords[d]
+        n = self.shape[self._dims.index(d)]
+        return DataArray(np.arange(n), dims=(d,), name=d, _coord=True)
+
+    def __getitem__(self, key):
+        if isinstance(key, str):
+            if key in self.coords:
+                return self.coords[key]
+            if key in self._dims:
+                return self._coord_for_dim(key)
+            raise KeyError(key)
+        if isinstance(key, Mapping):
+            return self.isel(key)
+        if not isinstance(key, tuple):
+            key = (key,)
+        if any(k is Ellipsis for k in key):
+            i = [j for j, k in enumerate(key) if k is Ellipsis][0]
+            key = key[:i] + (slice(None),) * (self.ndim - len(key) + 1) + key[i + 1:]
+        key = key + (slice(None),) * (self.ndim - len(key))
+        return self.isel({d: k for d, k in zip(self._dims, key)})
+
+    def __setitem__(self, key, value):
+        if isinstance(key, str):
+            self._coords[key] = value
+            return
+        v = value.data if isinstance(value, DataArray) else value
+        self._data[key] = v
+
+    def isel(self, indexers=None, drop=False, **kw):
+        idx = dict(indexers or {})
+        idx.update(kw)
+        key = []
+        newdims = []
+        for d in self._dims:
+            k = idx.get(d, slice(None))
+            if isinstance(k, DataArray):
+                k = k.values
+            if isinstance(k, (list, np.ndarray)):
+                k = np.asarray(k)
+            key.append(k)
+            if not isinstance(k, numbers.Integral):
+                newdims.append(d)
+        # apply one axis at a time (avoids numpy fancy-index broadcasting between axes)
+        data = self._data
+        ax = 0
+        for d, k in zip(self._dims, key):
+            sl = [slice(None)] * data.ndim
+            sl[ax] = k if not (isinstance(k, np.ndarray) and _is_torch(data)) else torch.as_tensor(k, device=data.device)
+            data = data[tuple(sl)]
+            if not isinstance(k, numbers.Integral):
+                ax += 1
+        coords = Coordinates()
+        for name, c in self._coords.items():
+            cidx = {d: idx[d] for d in c.dims if d in idx}
+            cc = c.isel(cidx) if cidx else c
+            if cc.ndim == 0 and drop:
+                continue
+            OrderedDict.__setitem__(coords, name, cc)
+        if self._is_coord:
+            coords = Coordinates()
+        return self._replace(data=data, dims=newdims, coords=coords)
+
+    def sel(self, indexers=None, method=None, **kw):
+        idx = dict(indexers or {})
+        idx.update(kw)
+        pos = {}
+        for d, val in idx.items():
+            c = self[d].values
+            if isinstance(val, slice):
+                lo = -np.inf if val.start is None else val.start
+                hi = np.inf if val.stop is None else val.stop
+                pos[d] = np.nonzero((c >= lo) & (c <= hi))[0]
+            else:
+                if method == "nearest":
+                    pos[d] = int(np.argmin(np.abs(c - val)))
+                else:
+                    hit = np.nonzero(c == val)[0]
+                    if hit.size == 0:
+                        hit = np.nonzero(np.isclose(c, val, rtol=1e-12, atol=0))[0]
+                    if hit.size == 0:
+                        raise KeyError(val)
+                    pos[d] = int(hit[0])
+        return self.isel(pos)
+
+    # ------------------------------------------------------------------ reshaping
+    def transpose(self, *dims):
+        if not dims:
+            dims = self._dims[::-1]
+        if Ellipsis in dims:
+            rest = [d for d in self._dims if d not in dims]
+            i = dims.index(Ellipsis)
+            dims = tuple(dims[:i]) + tuple(rest) + tuple(dims[i + 1:])
+        if set(dims) != set(self._dims) or len(dims) != len(self._dims):
+            raise ValueError(f"{dims} must be a permutation of {self._dims}")
+        if tuple(dims) == self._dims:
+            return self._replace()
+        perm = [self._dims.index(d) for d in dims]
+        data = self._data.permute(*perm) if _is_torch(self._data) else np.transpose(self._data, perm)
+        return self._replace(data=data, dims=dims)
+
+    def swap_dims(self, mapping):
+        newdims = tuple(mapping.get(d, d) for d in self._dims)
+        coords = Coordinates()
+        for name, c in self._coords.items():
+            cd = tuple(mapping.get(d, d) for d in c.dims)
+            OrderedDict.__setitem__(coords, name, c._replace(dims=cd))
+        return self._replace(dims=newdims, coords=coords)
+
+    def assign_coords(self, coords=None, **kw):
+        new = dict(coords or {})
+        new.update(kw)
+        out = self._replace()
+        for name, val in new.items():
+            if isinstance(val, DataArray):
+                c = DataArray(val.data, dims=val.dims, name=name, attrs=dict(val.attrs), _coord=True)
+            else:
+                arr = np.asarray(val)
+                c = DataArray(arr, dims=(name,) if arr.ndim == 1 else (), name=name, _coord=True)
+            for d, n in zip(c.dims, c.shape):
+                if d in out._dims and out.shape[out._dims.index(d)] != n:
+                    raise ValueError(f"conflicting sizes for dimension {d!r}")
+            OrderedDict.__setitem__(out._coords, name, c)
+        return out
+
+    def drop_vars(self, names, errors="raise"):
+        if isinstance(names, str):
+            names = [names]
+        out = self._replace()
+        for n in names:
+            if n in out._coords:
+                OrderedDict.__delitem__(out._coords, n)
+        return out
+
+    drop = drop_vars
+
+    def reset_coords(self, names=None, drop=False):
+        return self.drop_vars(names or [n for n in self._coords if n not in self._dims])
+
+    def rename(self, new_name_or_name_dict=None, **names):
+        if isinstance(new_name_or_name_dict, Mapping) or names:
+            m = dict(new_name_or_name_dict or {})
+            m.update(names)
+            dims = tuple(m.get(d, d) for d in self._dims)
+            coords = Coordinates()
+            for k, c in self._coords.items():
+                OrderedDict.__setitem__(coords, m.get(k, k), c._replace(dims=tuple(m.get(d, d) for d in c.dims), name=m.get(k, k)))
+            return self._replace(dims=dims, coords=coords)
+        return self._replace(name=new_name_or_name_dict)
+
+    def sortby(self, variables, ascending=True):
+        if isinstance(variables, (str, DataArray)):
+            variables = [variables]
+        out = self
+        for v in variables:
+            d = v if isinstance(v, str) else v.dims[0]
+            order = np.argsort(out[d].values, kind="stable")
+            if not ascending:
+                order = order[::-1]
+            if np.array_equal(order, np.arange(order.size)):
+                continue
+            out = out.isel({d: order})
+        return out
+
+    def expand_dims(self, dim, axis=0):
+        data = self._data.unsqueeze(axis) if _is_torch(self._data) else np.expand_dims(self._data, axis)
+        dims = list(self._dims)
+        dims.insert(axis, dim)
+        return self._replace(data=data, dims=dims)
+
+    def squeeze(self):
+        keep = [d for d, n in zip(self._dims, self.shape) if n != 1]
+        return self.isel({d: 0 for d in self._dims if d not in keep})
+
+    def pad(self, pad_width=None, mode="constant", stat_length=None, constant_values=None, end_values=None, reflect_type=None, **kw):
+        pw = dict(pad_width or {})
+        pw.update(kw)
+        widths = []
+        for d in self._dims:
+            w = pw.get(d, 0)
+            widths.append((w, w) if isinstance(w, numbers.Integral) else tuple(w))
+        kwargs = {}
+        if mode == "constant":
+            kwargs["constant_values"] = 0 if constant_values is None else constant_values
+        if stat_length is not None:
+            kwargs["stat_length"] = stat_length
+        if end_values is not None:
+            kwargs["end_values"] = end_values
+        if reflect_type is not None:
+            kwargs["reflect_type"] = reflect_type
+        vals = self.values
+        if mode == "constant" and kwargs["constant_values"] is not None and np.issubdtype(vals.dtype, np.integer) and isinstance(kwargs["constant_values"], float) and np.isnan(kwargs["constant_values"]):
+            vals = vals.astype(float)
+        data = np.pad(vals, widths, mode=mode, **kwargs)
+        coords = Coordinates()
+        for name, c in self._coords.items():
+            if any(d in pw for d in c.dims):
+                # xarray pads dimension coordinates with NaN; xrft.pad overwrites them right after
+                cw = [((pw[d], pw[d]) if isinstance(pw[d], numbers.Integral) else tuple(pw[d])) if d in pw else (0, 0) for d in c.dims]
+                cv = c.values
+                cdata = np.pad(cv.astype(float) if np.issubdtype(cv.dtype, np.number) else cv, cw, mode="constant", constant_values=np.nan)
+                OrderedDict.__setitem__(coords, name, c._replace(data=cdata))
+            else:
+                OrderedDict.__setitem__(coords, name, c)
+        return self._replace(data=data, coords=coords)
+
+    # ------------------------------------------------------------------ reductions
+    def _reduce(self, fn_np, fn_t, dim=None, **kw):
+        if dim is None:
+            dims = list(self._dims)
+        elif isinstance(dim, str):
+            dims = [dim]
+        else:
+            dims = list(dim)
+        axes = tuple(self._dims.index(d) for d in dims)
+        if _is_torch(self._data) and fn_t is not None:
+            data = fn_t(self._data, axes) if axes else self._data
+        else:
+            data = fn_np(self.values, axis=axes, **kw) if axes else self.values
+        newdims = [d for d in self._dims if d not in dims]
+        coords = Coordinates()
+        for name, c in self._coords.items():
+            if not any(d in dims for d in c.dims):
+                OrderedDict.__setitem__(coords, name, c)
+        return self._replace(data=data, dims=newdims, coords=coords, attrs=self.attrs if _KeepAttrs.value else None)
+
+    def mean(self, dim=None, **kw):
+        return self._reduce(np.mean, (lambda t, ax: t.mean(dim=ax)) if torch is not None else None, dim)
+
+    def sum(self, dim=None, **kw):
+        return self._reduce(np.sum, (lambda t, ax: t.sum(dim=ax)) if torch is not None else None, dim)
+
+    def max(self, dim=None, **kw):
+        return self._reduce(np.max, None, dim)
+
+    def min(self, dim=None, **kw):
+        return self._reduce(np.min, None, dim)
+
+    def std(self, dim=None, **kw):
+        return self._reduce(np.std, None, dim)
+
+    def var(self, dim=None, **kw):
+        return self._reduce(np.var, None, dim)
+
+    def all(self, dim=None):
+        return self._reduce(np.all, None, dim)
+
+    def any(self, dim=None):
+        return self._reduce(np.any, None, dim)
+
+    def isnull(self):
+        return self._replace(data=np.isnan(self.values))
+
+    def where(self, cond, other=np.nan):
+        c = cond.values if isinstance(cond, DataArray) else np.asarray(cond)
+        v = self.values
+        if np.issubdtype(v.dtype, np.integer):
+            v = v.astype(float)
+        return self._replace(data=np.where(c, v, other))
+
+    def dropna(self, dim, how="any"):
+        ax = self._dims.index(dim)
+        v = self.values
+        other = tuple(i for i in range(v.ndim) if i != ax)
+        bad = np.isnan(v).any(axis=other) if how == "any" else np.isnan(v).all(axis=other)
+        # NB: xarray's dropna looks at the DATA only, not at NaN coordinates
+        return self.isel({dim: np.nonzero(~bad)[0]})
+
+    # ------------------------------------------------------------------ arithmetic
+    @staticmethod
+    def _broadcast(a: "DataArray", b: "DataArray"):
+        dims = list(a._dims) + [d for d in b._dims if d not in a._dims]
+
+        def expand(x):
+            data = x._data
+            have = list(x._dims)
+            perm = [have.index(d) for d in dims if d in have]
+            if _is_torch(data):
+                data = data.permute(*perm) if perm else data
+            else:
+                data = np.transpose(data, perm) if perm else data
+            shape = []
+            it = iter(range(len(perm)))
+            k = 0
+            for d in dims:
+                if d in have:
+                    shape.append(data.shape[k])
+                    k += 1
+                else:
+                    shape.append(1)
+            return data.reshape(shape)
+
+        return dims, expand(a), expand(b)
+
+    def _binary(self, other, op, reflexive=False):
+        if isinstance(other, DataArray):
+            dims, x, y = DataArray._broadcast(self, other)
+            if _is_torch(x) != _is_torch(y):
+                if _is_torch(x):
+                    y = torch.as_tensor(np.ascontiguousarray(y), device=x.device)
+                else:
+                    x = torch.as_tensor(np.ascontiguousarray(x), device=y.device)
+            data = op(y, x) if reflexive else op(x, y)
+            coords = Coordinates()
+            for src in (self, other):
+                for name, c in src.coords.items():
+                    if name not in coords:
+                        OrderedDict.__setitem__(coords, name, c)
+            name = self.name if self.name == other.name else None
+            out = DataArray.__new__(DataArray)
+            out._data, out._dims, out.name = data, tuple(dims), name
+            out.attrs = dict(self.attrs) if _KeepAttrs.value else {}
+            out._is_coord = False
+            out._chunks = self._chunks or other._chunks
+            out._coords = coords
+            if self._is_coord and _KeepAttrs.value:
+                out.attrs = dict(self.attrs)
+            return out
+        y = other
+        x = self._data
+        if _is_torch(x) and isinstance(y, np.ndarray):
+            y = torch.as_tensor(y, device=x.device)
+        if _is_torch(x) and isinstance(y, (np.floating, np.integer, np.complexfloating)):
+            y = y.item()
+        data = op(y, x) if reflexive else op(x, y)
+        if not _is_torch(data):
+            data = np.asarray(data)
+        out = self._replace(data=data, attrs=self.attrs if (_KeepAttrs.value) else None)
+        if self._is_coord:
+            out._is_coord = False
+            c = Coordinates()
+            if self.name is not None and self._dims == (self.name,):
+                OrderedDict.__setitem__(c, self.name, self)
+            out._coords = c
+            if _KeepAttrs.value:
+                out.attrs = dict(self.attrs)
+        return out
+
+    def __add__(self, o): return self._binary(o, lambda a, b: a + b)
+    def __radd__(self, o): return self._binary(o, lambda a, b: a + b, True)
+    def __sub__(self, o): return self._binary(o, lambda a, b: a - b)
+    def __rsub__(self, o): return self._binary(o, lambda a, b: a - b, True)
+    def __mul__(self, o): return self._binary(o, lambda a, b: a * b)
+    def __rmul__(self, o): return self._binary(o, lambda a, b: a * b, True)
+    def __truediv__(self, o): return self._binary(o, lambda a, b: a / b)
+    def __rtruediv__(self, o): return self._binary(o, lambda a, b: a / b, True)
+    def __pow__(self, o): return self._binary(o, lambda a, b: a ** b)
+    def __rpow__(self, o): return self._binary(o, lambda a, b: a ** b, True)
+    def __mod__(self, o): return self._binary(o, lambda a, b: a % b)
+    def __lt__(self, o): return self._binary(o, lambda a, b: a < b)
+    def __le__(self, o): return self._binary(o, lambda a, b: a <= b)
+    def __gt__(self, o): return self._binary(o, lambda a, b: a > b)
+    def __ge__(self, o): return self._binary(o, lambda a, b: a >= b)
+    def __eq__(self, o): return self._binary(o, lambda a, b: a == b)  # noqa: E711
+    def __ne__(self, o): return self._binary(o, lambda a, b: a != b)
+    __hash__ = None
+
+    def __neg__(self): return self._replace(data=-self._data)
+    def __pos__(self): return self._replace()
+    def __abs__(self): return self._replace(data=abs(self._data))
+
+    _TORCH_UFUNC = {"absolute": "abs", "fabs": "abs", "conjugate": "conj", "exp": "exp", "sqrt": "sqrt", "log": "log", "log2": "log2",
+                    "log10": "log10", "sin": "sin", "cos": "cos", "negative": "neg", "real": "real", "imag": "imag", "square": "square",
+                    "isnan": "isnan"}
+
+    def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
+        if method != "__call__" or kwargs.get("out") is not None:
+            return NotImplemented
+        das = [x for x in inputs if isinstance(x, DataArray)]
+        if len(inputs) == 1:
+            x = inputs[0]
+            d = x._data
+            if _is_torch(d) and ufunc.__name__ in self._TORCH_UFUNC:
+                t = getattr(torch, self._TORCH_UFUNC[ufunc.__name__])(d)
+                if ufunc.__name__ == "conjugate":
+                    t = t.resolve_conj()
+                return x._replace(data=t)
+            if _is_torch(d) and ufunc.__name__ == "angle":  # pragma: no cover (np.angle is not a ufunc)
+                return x._replace(data=torch.angle(d))
+            return x._replace(data=ufunc(x.values, **kwargs))
+        if len(inputs) == 2:
+            a, b = inputs
+            if isinstance(a, DataArray):
+                return a._binary(b, lambda p, q: ufunc(_to_numpy(p), _to_numpy(q), **kwargs))
+            return b._binary(a, lambda p, q: ufunc(_to_numpy(p), _to_numpy(q), **kwargs), True)
+        return NotImplemented
+
+    def __array_function__(self, func, types, args, kwargs):
+        # np.flip / np.angle / np.real ... on a DataArray keep the labels when shape is preserved
+        def unwrap(x):
+            return x.values if isinstance(x, DataArray) else x
+        first = next((a for a in args if isinstance(a, DataArray)), None)
+        res = func(*[unwrap(a) for a in args], **{k: unwrap(v) for k, v in kwargs.items()})
+        if first is not None and isinstance(res, np.ndarray) and res.shape == first.shape and func.__name__ in (
+                "flip", "angle", "real", "imag", "abs", "absolute", "conj", "nan_to_num", "round", "around", "where", "copy"):
+            return first._replace(data=res)
+        return res
+
+
+# ---------------------------------------------------------------------------------------------
+# xarray interop + helpers mirroring the few xarray free functions the reference uses
+# ---------------------------------------------------------------------------------------------
+def from_any(obj) -> DataArray:
+    """Accept our DataArray, a real xarray.DataArray, or a bare array."""
+    if isinstance(obj, DataArray):
+        return obj
+    mod = type(obj).__module__
+    if mod.startswith("xarray"):
+        coords = {}
+        for k, v in obj.coords.items():
+            coords[k] = DataArray(np.asarray(v.values), dims=tuple(v.dims), name=k, attrs=dict(v.attrs), _coord=True)
+        chunks = None
+        if getattr(obj, "chunks", None):
+            chunks = {d: c[0] for d, c in zip(obj.dims, obj.chunks)}
+        out = DataArray(np.asarray(obj.values), dims=tuple(obj.dims), name=obj.name, attrs=dict(obj.attrs), chunks=chunks)
+        for k, c in coords.items():
+            OrderedDict.__setitem__(out._coords, k, c)
+        return out
+    return DataArray(obj)
+
+
+def to_xarray(da: DataArray):
+    import xarray as xr  # only called when xarray exists
+
+    coords = {k: (c.dims, c.values, dict(c.attrs)) for k, c in da.coords.items()}
+    return xr.DataArray(da.values, dims=da.dims, coords=coords, name=da.name, attrs=dict(da.attrs))
+
+
+def either_dict_or_kwargs(pos_kwargs, kw_kwargs, func_name):
+    """xarray.core.utils.either_dict_or_kwargs (used by xrft/padding.py:158, 411)."""
+    if pos_kwargs is None or pos_kwargs == {}:
+        return kw_kwargs
+    if not isinstance(pos_kwargs, Mapping):
+        raise ValueError(f"the first argument to .{func_name} must be a dictionary")
+    if kw_kwargs:
+        raise ValueError(f"cannot specify both keyword and positional arguments to .{func_name}")
+    return pos_kwargs
