@@ -61,9 +61,11 @@ int xrftb_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* smem_
  *                 must be ndim-1 (the reference always moves real_dim last: xrft.py:386,396).
  *   C2R         : in complex (last dim N/2+1), out real `shape`; same axis rule; needs a workspace of
  *                 the input's size when naxes > 1 (input is never modified).
- * Lengths: every power of two up to 2^14 (f32) / 2^13 (f64) on the contiguous axis (R2C/C2R: twice
- * that), up to 8192 on strided axes; other lengths return XRFTB_EUNSUPPORTED.
- * in == out is allowed for C2C. */
+ * Lengths: powers of two up to 2^14 (f32) / 2^13 (f64) on the contiguous axis (R2C/C2R: twice that) and
+ * up to 8192 on strided axes run on the Stockham kernels; any length <= 64 runs a direct DFT; any other
+ * length n runs Bluestein's chirp-z on the same kernels as long as nextpow2(2n-1) fits those limits
+ * (n <= 8192 f32 / 4096 f64 contiguous, n <= 4096 strided); beyond that XRFTB_EUNSUPPORTED.
+ * `work` must hold xrftb_fftn_workspace(...) bytes (0 for power-of-two C2C/R2C).  in == out is allowed for C2C. */
 size_t xrftb_fftn_workspace(int dtype, int kind, int ndim, const int64_t* shape, int naxes, const int* axes);
 int xrftb_fftn(const void* in, void* out, void* work, size_t work_bytes, int dtype, int kind, int ndim,
                const int64_t* shape, int naxes, const int* axes, void* stream);

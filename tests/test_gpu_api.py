@@ -401,3 +401,34 @@ def test_rfft_irfft_round_trip_padded_f64():
     ps = xrft.power_spectrum(padded, real_dim="x")
     np.testing.assert_allclose(ps.values.sum() * ps["freq_x"].attrs["spacing"] * ps["freq_y"].attrs["spacing"],
                                (padded.values ** 2).mean(), rtol=1e-10)
+
+
+# ------------------------------------------------------ the reference's own (non power-of-two) sizes
+@pytest.mark.parametrize("shape,dims,kw", [
+    ((16,), ("x",), dict(detrend="linear")), ((10,), ("x",), dict(detrend="constant", window="hann")),
+    ((15, 19), ("y", "x"), dict(detrend="linear", window="hann")), ((20, 30), ("y", "x"), dict(real_dim="x")),
+    ((2, 10, 21), ("t", "y", "x"), dict(dim=["y", "x"], detrend="constant")), ((5, 40, 60), ("t", "y", "x"), dict(dim=["y", "x"], window="tukey")),
+    ((6, 8, 10), ("z", "y", "x"), dict(detrend="linear", window="hann")), ((100,), ("x",), dict()),
+    ((1000,), ("x",), dict(detrend="linear")), ((3, 258), ("t", "x"), dict(dim=["x"], real_dim="x")), ((366, 4), ("t", "x"), dict(dim=["t"])),
+])
+def test_reference_sizes_fft_and_power(shape, dims, kw):
+    rng = np.random.default_rng(sum(shape))
+    da = mk(shape, dims, rng)
+    same(xrft.fft(da, **kw), O.fft(lab(da), **kw), tol=1e-8)
+    same(xrft.power_spectrum(da, **kw), O.power_spectrum(lab(da), **kw), tol=1e-8)
+
+
+def test_reference_sizes_round_trip_and_iso():
+    rng = np.random.default_rng(77)
+    da = mk((20, 30), ("y", "x"), rng)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        back = xrft.ifft(xrft.fft(da))
+        np.testing.assert_allclose(back.values.real, da.values, atol=1e-10)
+        back = xrft.ifft(xrft.fft(da, real_dim="x"), real_dim="freq_x")
+        np.testing.assert_allclose(back.values, da.values, atol=1e-10)
+        da2 = mk((3, 40, 60), ("t", "y", "x"), rng, spacing={"y": 1.0, "x": 1.0})
+        out = xrft.isotropic_power_spectrum(da2, dim=["y", "x"], detrend="linear", window="hann")
+        ref = O.isotropic_power_spectrum(lab(da2), dim=["y", "x"], detrend="linear", window="hann")
+    assert relerr(out.values, ref.data) < 1e-8
+    np.testing.assert_allclose(out["freq_r"].values, ref.coords["freq_r"], rtol=1e-12)

@@ -86,3 +86,57 @@ def test_spectrum2d_power(dt, shape, detrend):
                        shift_y=True, shift_x=True, scale=scale).cpu().numpy()
     tol = 5e-4 if dt == np.float32 else 1e-10
     assert relerr(out, ref) < tol
+
+
+# ---------------------------------------------------------------- arbitrary lengths
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("n", [1, 3, 5, 10, 15, 19, 20, 30, 60, 100, 258, 366, 1000, 2601, 3650])
+def test_c2c_any_length(dt, n):
+    from xrft_b200 import backend as B
+    rng = np.random.default_rng(n)
+    x = cplx(rng, (3, n), dt)
+    tol = TOL[dt] * (10 if n > 64 else 1)
+    y = B.fftn(torch.from_numpy(x).cuda(), axes=[1]).cpu().numpy()
+    assert relerr(y, np.fft.fft(x.astype(np.complex128), axis=1)) < tol
+    yi = B.ifftn(torch.from_numpy(x).cuda(), axes=[1]).cpu().numpy()
+    assert relerr(yi, np.fft.ifft(x.astype(np.complex128), axis=1)) < tol
+    if n <= 1000:  # strided axis
+        xs = cplx(rng, (2, n, 7), dt)
+        ys = B.fftn(torch.from_numpy(xs).cuda(), axes=[1]).cpu().numpy()
+        assert relerr(ys, np.fft.fft(xs.astype(np.complex128), axis=1)) < tol
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("shape", [(4, 10), (3, 15, 20), (2, 30, 40), (2, 6, 100), (1, 12, 1000), (5, 2), (3, 3), (2, 8, 2)])
+def test_r2c_c2r_any_length(dt, shape):
+    from xrft_b200 import backend as B
+    rng = np.random.default_rng(sum(shape))
+    x = rng.standard_normal(shape).astype(dt)
+    axes = list(range(1, len(shape)))
+    y = B.rfftn(torch.from_numpy(x).cuda(), axes=axes).cpu().numpy()
+    ref = np.fft.rfftn(x.astype(np.float64), axes=axes)
+    tol = TOL[dt] * 10
+    assert relerr(y, ref) < tol
+    if shape[-1] % 2 == 0:
+        back = B.irfftn(torch.from_numpy(ref.astype(y.dtype)).cuda(), axes=axes).cpu().numpy()
+        assert relerr(back, x) < tol
+
+
+def test_binned_sum_and_moments():
+    from xrft_b200 import backend as B
+    rng = np.random.default_rng(3)
+    a = rng.standard_normal((4, 50, 60))
+    lut = rng.integers(-1, 17, size=(50, 60)).astype(np.int32)
+    out = B.binned_sum(torch.from_numpy(a).cuda(), torch.from_numpy(lut), 17, 2).cpu().numpy()
+    ref = np.stack([np.bincount(lut.ravel()[lut.ravel() >= 0], a[i].ravel()[lut.ravel() >= 0], 17) for i in range(4)])
+    np.testing.assert_allclose(out, ref, rtol=1e-12, atol=1e-12)
+    ac = (a + 1j * rng.standard_normal(a.shape)).astype(np.complex64)
+    outc = B.binned_sum(torch.from_numpy(ac).cuda(), torch.from_numpy(lut), 17, 2).cpu().numpy()
+    refc = np.stack([np.bincount(lut.ravel()[lut.ravel() >= 0], ac[i].real.ravel()[lut.ravel() >= 0], 17)
+                     + 1j * np.bincount(lut.ravel()[lut.ravel() >= 0], ac[i].imag.ravel()[lut.ravel() >= 0], 17) for i in range(4)])
+    np.testing.assert_allclose(outc, refc, rtol=1e-5, atol=1e-5)
+    m = B.moments(torch.from_numpy(a).cuda(), 2).cpu().numpy()
+    iy = np.arange(50) - 24.5; ix = np.arange(60) - 29.5
+    np.testing.assert_allclose(m[:, 0], a.sum(axis=(1, 2)), rtol=1e-12)
+    np.testing.assert_allclose(m[:, 2], (a * iy[None, :, None]).sum(axis=(1, 2)), rtol=1e-10, atol=1e-9)
+    np.testing.assert_allclose(m[:, 3], (a * ix[None, None, :]).sum(axis=(1, 2)), rtol=1e-10, atol=1e-9)

@@ -66,8 +66,11 @@ def fftn(x: torch.Tensor, axes=None, inverse=False) -> torch.Tensor:
     x = _dev(x)
     axes = _norm_axes(x.ndim, axes)
     out = torch.empty_like(x)
+    kind = L.C2C_INV if inverse else L.C2C_FWD
     with torch.cuda.device(x.device):
-        rc = lib.xrftb_fftn(_ptr(x), _ptr(out), None, 0, _CPLX[x.dtype], L.C2C_INV if inverse else L.C2C_FWD, x.ndim,
+        wb = lib.xrftb_fftn_workspace(_CPLX[x.dtype], kind, x.ndim, _i64(x.shape), len(axes), _ints(axes))
+        work = torch.empty(wb, dtype=torch.uint8, device=x.device)
+        rc = lib.xrftb_fftn(_ptr(x), _ptr(out), _ptr(work), wb, _CPLX[x.dtype], kind, x.ndim,
                             _i64(x.shape), len(axes), _ints(axes), _stream())
     L.check(rc, "xrftb_fftn")
     return out
@@ -89,7 +92,9 @@ def rfftn(x: torch.Tensor, axes=None) -> torch.Tensor:
     oshape[-1] = x.shape[-1] // 2 + 1
     out = torch.empty(oshape, dtype=_TO_CPLX[x.dtype], device=x.device)
     with torch.cuda.device(x.device):
-        rc = lib.xrftb_fftn(_ptr(x), _ptr(out), None, 0, _REAL[x.dtype], L.R2C, x.ndim, _i64(x.shape), len(axes),
+        wb = lib.xrftb_fftn_workspace(_REAL[x.dtype], L.R2C, x.ndim, _i64(x.shape), len(axes), _ints(axes))
+        work = torch.empty(wb, dtype=torch.uint8, device=x.device)
+        rc = lib.xrftb_fftn(_ptr(x), _ptr(out), _ptr(work), wb, _REAL[x.dtype], L.R2C, x.ndim, _i64(x.shape), len(axes),
                             _ints(axes), _stream())
     L.check(rc, "xrftb_fftn(R2C)")
     return out

@@ -325,6 +325,124 @@ __global__ void __launch_bounds__(256) binned_sum_kernel(const T* __restrict__ a
         if (hist[i] != 0.0) atomicAdd(bins + b * nbins * width + i, hist[i]);
 }
 
+// ------------------------------------------------------------------------------------------------
+// arbitrary lengths (the reference's tests use 10, 15, 19, 20, 30, 40, 100, 1000 ...)
+//   N <= kSmallDft : direct O(N^2) DFT, one thread per sequence, twiddles in shared memory
+//   otherwise      : Bluestein chirp-z on top of the power-of-two passes (no cuFFT, no CPU fallback)
+// All operate on a [A][N][B] row-major view (FFT along the middle axis), in-place safe.
+// ------------------------------------------------------------------------------------------------
+constexpr int kSmallDft = 64;
+
+// mode: 0 C2C forward, 1 C2C inverse (x scale), 2 R2C (real in, k <= N/2 out), 3 C2R (half in, real out, x scale)
+template <typename T>
+__global__ void __launch_bounds__(128) dft_small_kernel(const void* __restrict__ in_, void* __restrict__ out_, int N, long A, long B,
+                                                        int mode, T scale) {
+    __shared__ double2 tw[kSmallDft];
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        double s, c;
+        sincospi(-2.0 * (double)i / (double)N, &s, &c);
+        tw[i] = make_double2(c, s);
+    }
+    __syncthreads();
+    const long nseq = A * B;
+    const int H = N / 2 + 1;
+    for (long q = blockIdx.x * (long)blockDim.x + threadIdx.x; q < nseq; q += (long)gridDim.x * blockDim.x) {
+        const long a = q / B, b = q - a * B;
+        double2 x[kSmallDft];
+        if (mode == 2) {
+            const T* p = reinterpret_cast<const T*>(in_) + a * N * B + b;
+            for (int n = 0; n < N; ++n) x[n] = make_double2((double)p[n * B], 0.0);
+        } else if (mode == 3) {
+            const cplx<T>* p = reinterpret_cast<const cplx<T>*>(in_) + a * H * B + b;
+            for (int k = 0; k < H; ++k) { cplx<T> v = p[k * B]; x[k] = make_double2((double)v.x, (double)v.y); }
+            x[0].y = 0.0;
+            if (N % 2 == 0) x[N / 2].y = 0.0;
+            for (int k = H; k < N; ++k) x[k] = make_double2(x[N - k].x, -x[N - k].y);
+        } else {
+            const cplx<T>* p = reinterpret_cast<const cplx<T>*>(in_) + a * N * B + b;
+            for (int n = 0; n < N; ++n) { cplx<T> v = p[n * B]; x[n] = make_double2((double)v.x, (double)v.y); }
+        }
+        const bool inv = (mode == 1 || mode == 3);
+        const int K = (mode == 2) ? H : N;
+        for (int k = 0; k < K; ++k) {
+            double re = 0.0, im = 0.0;
+            int idx = 0;
+            for (int n = 0; n < N; ++n) {
+                double2 w = tw[idx];
+                if (inv) w.y = -w.y;
+                re += x[n].x * w.x - x[n].y * w.y;
+                im += x[n].x * w.y + x[n].y * w.x;
+                idx += k;
+                if (idx >= N) idx -= N;
+            }
+            if (mode == 3) reinterpret_cast<T*>(out_)[(a * N + k) * B + b] = (T)(re * (double)scale);
+            else if (mode == 2) reinterpret_cast<cplx<T>*>(out_)[(a * H + k) * B + b] = mk<T>((T)re, (T)im);
+            else reinterpret_cast<cplx<T>*>(out_)[(a * N + k) * B + b] = mk<T>((T)(re * (double)scale), (T)(im * (double)scale));
+        }
+    }
+}
+
+// Bluestein: X[k] = b[k] * sum_n (x[n] b[n]) conj(b[k-n]),  b[n] = exp(-i pi n^2 / N)
+// pre : work[a][m][b] = (conj? x)[a][m][b] * chirp[m]   (m < N), 0 (N <= m < M);  real or complex x
+// mul : work[a][m][b] *= filt[m]                        (filt = FFT_M of the wrapped conj chirp)
+// post: out[a][k][b]  = (conj?)(work[a][k][b] * chirp[k]) * scale, k < N
+template <typename T, bool REAL_IN>
+__global__ void __launch_bounds__(256) bluestein_pre_kernel(const void* __restrict__ in_, cplx<T>* __restrict__ work, const cplx<T>* __restrict__ chirp,
+                                                            long A, long N, long M, long B, int conj_in, long total) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long b = i % B;
+        long r = i / B;
+        const long m = r % M;
+        const long a = r / M;
+        cplx<T> v = mk<T>(0, 0);
+        if (m < N) {
+            if (REAL_IN) v = mk<T>(reinterpret_cast<const T*>(in_)[(a * N + m) * B + b], 0);
+            else v = reinterpret_cast<const cplx<T>*>(in_)[(a * N + m) * B + b];
+            if (conj_in) v.y = -v.y;
+            v = cmul(v, chirp[m]);
+        }
+        work[i] = v;
+    }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) bluestein_mul_kernel(cplx<T>* __restrict__ work, const cplx<T>* __restrict__ filt, long M, long B, long total) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long m = (i / B) % M;
+        work[i] = cmul(work[i], filt[m]);
+    }
+}
+template <typename T, bool REAL_OUT>
+__global__ void __launch_bounds__(256) bluestein_post_kernel(const cplx<T>* __restrict__ work, void* __restrict__ out_, const cplx<T>* __restrict__ chirp,
+                                                             long A, long N, long Nout, long M, long B, int conj_out, T scale, long total) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long b = i % B;
+        long r = i / B;
+        const long k = r % Nout;
+        const long a = r / Nout;
+        cplx<T> v = cmul(work[(a * M + k) * B + b], chirp[k]);
+        if (conj_out) v.y = -v.y;
+        if (REAL_OUT) reinterpret_cast<T*>(out_)[i] = v.x * scale;
+        else reinterpret_cast<cplx<T>*>(out_)[i] = cscale(v, scale);
+    }
+}
+// Hermitian extension of a half spectrum along the last-but-B axis: [A][H][B] -> [A][N][B] (for the non-pow2 C2R path)
+template <typename T>
+__global__ void __launch_bounds__(256) herm_extend_kernel(const cplx<T>* __restrict__ in, cplx<T>* __restrict__ out, long N, long B, long total) {
+    const long H = N / 2 + 1;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long b = i % B;
+        long r = i / B;
+        const long k = r % N;
+        const long a = r / N;
+        cplx<T> v;
+        if (k < H) { v = in[(a * H + k) * B + b]; if (k == 0 || (N % 2 == 0 && k == N / 2)) v.y = 0; }
+        else { v = in[(a * H + (N - k)) * B + b]; v.y = -v.y; }
+        out[i] = v;
+    }
+}
+
+static inline int next_pow2_log(long n) { int l = 0; while ((1L << l) < n) ++l; return l; }
+
 static inline int ilog2_exact(int64_t n) {
     if (n < 1 || (n & (n - 1))) return -1;
     int l = 0;
@@ -348,11 +466,136 @@ static inline unsigned ew_grid(long total) {
 // ------------------------------------------------------------------------------------------------
 // fftn composition
 // ------------------------------------------------------------------------------------------------
+static std::map<std::tuple<int, int, long, int>, std::pair<void*, void*>> g_chirp;  // (device, dtype, N, log2M) -> (chirp, filter)
+
+template <typename T> static int get_chirp(long N, int log2M, const cplx<T>** chirp, const cplx<T>** filt, cudaStream_t st) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int dt = sizeof(T) == 4 ? 0 : 1;
+    auto key = std::make_tuple(dev, dt, N, log2M);
+    {
+        std::lock_guard<std::mutex> lk(g_tw_mu);
+        auto it = g_chirp.find(key);
+        if (it != g_chirp.end()) { *chirp = (const cplx<T>*)it->second.first; *filt = (const cplx<T>*)it->second.second; return 0; }
+    }
+    const long M = 1L << log2M;
+    std::vector<cplx<T>> hb(N), hc(M);
+    for (long m = 0; m < M; ++m) hc[m] = mk<T>(0, 0);
+    for (long n = 0; n < N; ++n) {
+        const long r = (n * n) % (2 * N);  // exp(-i pi n^2 / N) has period 2N in n^2
+        const double ang = -M_PI * (double)r / (double)N;
+        hb[n] = mk<T>((T)cos(ang), (T)sin(ang));
+        cplx<T> cj = mk<T>(hb[n].x, -hb[n].y);
+        hc[n] = cj;
+        if (n > 0) hc[M - n] = cj;
+    }
+    cplx<T>*db = nullptr, *dc = nullptr, *df = nullptr;
+    cudaError_t e = cudaMalloc(&db, N * sizeof(cplx<T>));
+    if (e == cudaSuccess) e = cudaMalloc(&dc, M * sizeof(cplx<T>));
+    if (e == cudaSuccess) e = cudaMalloc(&df, M * sizeof(cplx<T>));
+    if (e == cudaSuccess) e = cudaMemcpy(db, hb.data(), N * sizeof(cplx<T>), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(dc, hc.data(), M * sizeof(cplx<T>), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { set_error("chirp table: %s", cudaGetErrorString(e)); return XRFTB_ECUDA; }
+    int rc = rows_c2c<T>(dc, df, log2M, 1, M, M, 0, (T)1, st);
+    if (rc) return rc;
+    cudaStreamSynchronize(st);
+    cudaFree(dc);
+    std::lock_guard<std::mutex> lk(g_tw_mu);
+    g_chirp[key] = std::make_pair((void*)db, (void*)df);
+    *chirp = db; *filt = df;
+    return 0;
+}
+
+template <typename T> static bool fast_len(long n, bool contiguous) {
+    const int l2 = ilog2_exact(n);
+    if (l2 < 1) return false;
+    return l2 <= (contiguous ? TypeCfg<T>::MAX_ROWS_LOG2 : TypeCfg<T>::MAX_COLS_LOG2);
+}
+// workspace (bytes) one C2C pass of length n over an [A][n][B] view needs
+template <typename T> static size_t pass_workspace(long A, long n, long B) {
+    if (fast_len<T>(n, B == 1) || n <= kSmallDft) return 0;
+    const int lm = next_pow2_log(2 * n - 1);
+    return (size_t)A * (1UL << lm) * B * sizeof(cplx<T>);
+}
+
+// one C2C pass along the middle axis of [A][n][B]; src may equal dst
+template <typename T>
+static int c2c_pass(const cplx<T>* src, cplx<T>* dst, long A, long n, long B, int inverse, T scale, void* work, size_t work_bytes,
+                    cudaStream_t st) {
+    if (n == 1) {
+        if (src != dst || scale != (T)1) {
+            const long total = A * B;
+            roll_scale_kernel<T><<<ew_grid(total), 256, 0, st>>>(reinterpret_cast<const T*>(src), reinterpret_cast<T*>(dst), 1, 1, total, 0, 0, 0, 2, scale, total);
+            return check_launch("roll_scale_kernel");
+        }
+        return 0;
+    }
+    if (fast_len<T>(n, B == 1)) {
+        const int l2 = ilog2_exact(n);
+        if (B == 1) return rows_c2c<T>(src, dst, l2, A, n, n, inverse, scale, st);
+        return cols_c2c<T>(src, dst, l2, A, B, inverse, scale, st);
+    }
+    if (n <= kSmallDft) {
+        const long nseq = A * B;
+        dft_small_kernel<T><<<(unsigned)((nseq + 127) / 128 > 4096 ? 4096 : (nseq + 127) / 128), 128, 0, st>>>(src, dst, (int)n, A, B, inverse ? 1 : 0, scale);
+        return check_launch("dft_small_kernel");
+    }
+    const int lm = next_pow2_log(2 * n - 1);
+    const long M = 1L << lm;
+    if (lm > (B == 1 ? TypeCfg<T>::MAX_ROWS_LOG2 : TypeCfg<T>::MAX_COLS_LOG2)) {
+        set_error("fftn: length %ld needs a %ld-point Bluestein convolution, beyond the single-pass limit (see DESIGN.md)", n, M);
+        return XRFTB_EUNSUPPORTED;
+    }
+    const size_t need = (size_t)A * M * B * sizeof(cplx<T>);
+    if (!work || work_bytes < need) { set_error("fftn: workspace too small for Bluestein (%zu < %zu)", work_bytes, need); return XRFTB_EWORKSPACE; }
+    const cplx<T>*chirp, *filt;
+    if (int rc = get_chirp<T>(n, lm, &chirp, &filt, st)) return rc;
+    cplx<T>* w = reinterpret_cast<cplx<T>*>(work);
+    const long tw_ = A * M * B;
+    bluestein_pre_kernel<T, false><<<ew_grid(tw_), 256, 0, st>>>(src, w, chirp, A, n, M, B, inverse, tw_);
+    if (int rc = check_launch("bluestein_pre")) return rc;
+    if (int rc = (B == 1 ? rows_c2c<T>(w, w, lm, A, M, M, 0, (T)1, st) : cols_c2c<T>(w, w, lm, A, B, 0, (T)1, st))) return rc;
+    bluestein_mul_kernel<T><<<ew_grid(tw_), 256, 0, st>>>(w, filt, M, B, tw_);
+    if (int rc = check_launch("bluestein_mul")) return rc;
+    if (int rc = (B == 1 ? rows_c2c<T>(w, w, lm, A, M, M, 1, (T)(1.0 / M), st) : cols_c2c<T>(w, w, lm, A, B, 1, (T)(1.0 / M), st))) return rc;
+    const long to = A * n * B;
+    bluestein_post_kernel<T, false><<<ew_grid(to), 256, 0, st>>>(w, dst, chirp, A, n, n, M, B, inverse, scale, to);
+    return check_launch("bluestein_post");
+}
+
+template <typename T>
+static size_t fftn_workspace_impl(int kind, int ndim, const int64_t* shape, int naxes, const int* axes) {
+    std::vector<int64_t> cshape(shape, shape + ndim);
+    const bool real_kind = (kind == XRFTB_R2C || kind == XRFTB_C2R);
+    const long N = shape[ndim - 1];
+    if (real_kind) cshape[ndim - 1] = N / 2 + 1;
+    size_t need = 0;
+    auto view = [&](int axis, long& A, long& B) { A = 1; B = 1; for (int d = 0; d < axis; ++d) A *= cshape[d]; for (int d = axis + 1; d < ndim; ++d) B *= cshape[d]; };
+    for (int i = 0; i < naxes - (real_kind ? 1 : 0); ++i) {
+        long A, B; view(axes[i], A, B);
+        size_t w = pass_workspace<T>(A, cshape[axes[i]], B);
+        if (w > need) need = w;
+    }
+    size_t base = 0;
+    if (real_kind) {
+        long nseq = 1; for (int d = 0; d < ndim - 1; ++d) nseq *= shape[d];
+        const bool fast_real = ilog2_exact(N) >= 2 && ilog2_exact(N) - 1 <= TypeCfg<T>::MAX_ROWS_LOG2;
+        size_t last = 0;
+        if (!fast_real && N > kSmallDft) {
+            const int lm = next_pow2_log(2 * N - 1);
+            last = (size_t)nseq * (1UL << lm) * sizeof(cplx<T>);
+            if (kind == XRFTB_C2R) last += (size_t)nseq * N * sizeof(cplx<T>);  // Hermitian-extended copy
+        }
+        if (kind == XRFTB_C2R && naxes > 1) base = (size_t)nseq * (N / 2 + 1) * sizeof(cplx<T>);  // private copy of the input
+        if (last > need) need = last;
+    }
+    return base + need + 512;
+}
+
 template <typename T>
 static int fftn_impl(const void* in, void* out, void* work, size_t work_bytes, int kind, int ndim, const int64_t* shape,
                      int naxes, const int* axes, cudaStream_t st) {
     using C = cplx<T>;
-    // complex-array shape
     std::vector<int64_t> cshape(shape, shape + ndim);
     const bool real_kind = (kind == XRFTB_R2C || kind == XRFTB_C2R);
     if (real_kind) {
@@ -363,65 +606,97 @@ static int fftn_impl(const void* in, void* out, void* work, size_t work_bytes, i
     for (int i = 0; i < naxes; ++i) norm *= (double)shape[axes[i]];
     const bool inverse = (kind == XRFTB_C2C_INV || kind == XRFTB_C2R);
     const T inv_scale = inverse ? (T)(1.0 / norm) : (T)1;
+    char* wbase = reinterpret_cast<char*>(work);
+    size_t wleft = work ? work_bytes : 0;
+    auto view = [&](int axis, long& A, long& B) { A = 1; B = 1; for (int d = 0; d < axis; ++d) A *= cshape[d]; for (int d = axis + 1; d < ndim; ++d) B *= cshape[d]; };
 
-    auto strided_pass = [&](const C* src, C* dst, int axis, int inv, T scale) -> int {
-        const int l2 = ilog2_exact(cshape[axis]);
-        if (l2 < 1) { set_error("fftn: axis %d length %lld is not a supported power of two", axis, (long long)cshape[axis]); return XRFTB_EUNSUPPORTED; }
-        long A = 1, B = 1;
-        for (int d = 0; d < axis; ++d) A *= cshape[d];
-        for (int d = axis + 1; d < ndim; ++d) B *= cshape[d];
-        if (B == 1) return rows_c2c<T>(src, dst, l2, A, cshape[axis], cshape[axis], inv, scale, st);
-        return cols_c2c<T>(src, dst, l2, A, B, inv, scale, st);
-    };
-
-    if (kind == XRFTB_C2C_FWD || kind == XRFTB_C2C_INV) {
+    if (!real_kind) {
         const C* src = reinterpret_cast<const C*>(in);
         C* dst = reinterpret_cast<C*>(out);
         for (int i = 0; i < naxes; ++i) {
-            const bool last = (i == naxes - 1);
-            int rc = strided_pass(src, dst, axes[i], inverse ? 1 : 0, last ? inv_scale : (T)1);
+            long A, B; view(axes[i], A, B);
+            int rc = c2c_pass<T>(src, dst, A, cshape[axes[i]], B, inverse ? 1 : 0, (i == naxes - 1) ? inv_scale : (T)1, wbase, wleft, st);
             if (rc) return rc;
             src = dst;
         }
         return 0;
     }
+    const long N = shape[ndim - 1], H = N / 2 + 1;
+    long nseq = 1;
+    for (int d = 0; d < ndim - 1; ++d) nseq *= shape[d];
+    const int l2 = ilog2_exact(N);
+    const bool fast_real = l2 >= 2 && l2 - 1 <= TypeCfg<T>::MAX_ROWS_LOG2;
     if (kind == XRFTB_R2C) {
-        const int64_t N = shape[ndim - 1];
-        const int l2 = ilog2_exact(N);
-        if (l2 < 2) { set_error("rfftn: real axis length %lld unsupported", (long long)N); return XRFTB_EUNSUPPORTED; }
-        long nseq = 1;
-        for (int d = 0; d < ndim - 1; ++d) nseq *= shape[d];
-        RowsR2CFused<T> io{};
-        io.in = reinterpret_cast<const T*>(in); io.in_row_stride = N; io.logNy = 0; io.detrend = 0; io.moments = nullptr;
-        io.wy = nullptr; io.wx = nullptr; io.out = reinterpret_cast<C*>(out); io.logC = -1; io.out_seq_stride = N / 2 + 1;
-        int rc = rows_r2c<T>(io, l2 - 1, nseq, st);
-        if (rc) return rc;
         C* dst = reinterpret_cast<C*>(out);
+        if (fast_real) {
+            RowsR2CFused<T> io{};
+            io.in = reinterpret_cast<const T*>(in); io.in_row_stride = N; io.logNy = 0; io.detrend = 0; io.moments = nullptr;
+            io.wy = nullptr; io.wx = nullptr; io.out = dst; io.logC = -1; io.out_seq_stride = H;
+            if (int rc = rows_r2c<T>(io, l2 - 1, nseq, st)) return rc;
+        } else if (N <= kSmallDft) {
+            if (N < 2) { set_error("rfftn: real axis must have at least 2 points"); return XRFTB_EINVAL; }
+            dft_small_kernel<T><<<(unsigned)((nseq + 127) / 128 > 4096 ? 4096 : (nseq + 127) / 128), 128, 0, st>>>(in, dst, (int)N, nseq, 1, 2, (T)1);
+            if (int rc = check_launch("dft_small_kernel")) return rc;
+        } else {
+            const int lm = next_pow2_log(2 * N - 1);
+            const long M = 1L << lm;
+            if (lm > TypeCfg<T>::MAX_ROWS_LOG2) { set_error("rfftn: length %ld beyond the single-pass Bluestein limit", N); return XRFTB_EUNSUPPORTED; }
+            const size_t need = (size_t)nseq * M * sizeof(C);
+            if (wleft < need) { set_error("rfftn: workspace too small (%zu < %zu)", wleft, need); return XRFTB_EWORKSPACE; }
+            const C*chirp, *filt;
+            if (int rc = get_chirp<T>(N, lm, &chirp, &filt, st)) return rc;
+            C* w = reinterpret_cast<C*>(wbase);
+            const long tw_ = nseq * M;
+            bluestein_pre_kernel<T, true><<<ew_grid(tw_), 256, 0, st>>>(in, w, chirp, nseq, N, M, 1, 0, tw_);
+            if (int rc = rows_c2c<T>(w, w, lm, nseq, M, M, 0, (T)1, st)) return rc;
+            bluestein_mul_kernel<T><<<ew_grid(tw_), 256, 0, st>>>(w, filt, M, 1, tw_);
+            if (int rc = rows_c2c<T>(w, w, lm, nseq, M, M, 1, (T)(1.0 / M), st)) return rc;
+            bluestein_post_kernel<T, false><<<ew_grid(nseq * H), 256, 0, st>>>(w, dst, chirp, nseq, N, H, M, 1, 0, (T)1, nseq * H);
+            if (int rc = check_launch("bluestein r2c")) return rc;
+        }
         for (int i = 0; i < naxes - 1; ++i) {
-            rc = strided_pass(dst, dst, axes[i], 0, (T)1);
-            if (rc) return rc;
+            long A, B; view(axes[i], A, B);
+            if (int rc = c2c_pass<T>(dst, dst, A, cshape[axes[i]], B, 0, (T)1, wbase, wleft, st)) return rc;
         }
         return 0;
     }
-    // C2R
-    {
-        const int64_t N = shape[ndim - 1];
-        const int l2 = ilog2_exact(N);
-        if (l2 < 2) { set_error("irfftn: real axis length %lld unsupported", (long long)N); return XRFTB_EUNSUPPORTED; }
-        long nseq = 1, ctotal = 1;
-        for (int d = 0; d < ndim - 1; ++d) nseq *= shape[d];
-        for (int d = 0; d < ndim; ++d) ctotal *= cshape[d];
-        const C* src = reinterpret_cast<const C*>(in);
-        if (naxes > 1) {
-            if (work == nullptr || work_bytes < (size_t)ctotal * sizeof(C)) { set_error("irfftn: workspace too small"); return XRFTB_EWORKSPACE; }
-            C* w = reinterpret_cast<C*>(work);
-            for (int i = 0; i < naxes - 1; ++i) {
-                int rc = strided_pass(src, w, axes[i], 1, (T)1);
-                if (rc) return rc;
-                src = w;
-            }
+    // ---- C2R
+    const C* src = reinterpret_cast<const C*>(in);
+    if (naxes > 1) {
+        const size_t copy_bytes = (size_t)nseq * H * sizeof(C);
+        if (wleft < copy_bytes) { set_error("irfftn: workspace too small"); return XRFTB_EWORKSPACE; }
+        C* w = reinterpret_cast<C*>(wbase);
+        wbase += (copy_bytes + 255) & ~(size_t)255;
+        wleft = wleft > ((copy_bytes + 255) & ~(size_t)255) ? wleft - ((copy_bytes + 255) & ~(size_t)255) : 0;
+        for (int i = 0; i < naxes - 1; ++i) {
+            long A, B; view(axes[i], A, B);
+            if (int rc = c2c_pass<T>(src, w, A, cshape[axes[i]], B, 1, (T)1, wbase, wleft, st)) return rc;
+            src = w;
         }
-        return rows_c2r<T>(src, N / 2 + 1, reinterpret_cast<T*>(out), N, l2 - 1, nseq, inv_scale * (T)2, st);  // half-length inverse: 1/M = 2/N
+    }
+    if (fast_real) return rows_c2r<T>(src, H, reinterpret_cast<T*>(out), N, l2 - 1, nseq, inv_scale * (T)2, st);  // half-length inverse: 1/M = 2/N
+    if (N <= kSmallDft) {
+        dft_small_kernel<T><<<(unsigned)((nseq + 127) / 128 > 4096 ? 4096 : (nseq + 127) / 128), 128, 0, st>>>(src, out, (int)N, nseq, 1, 3, inv_scale);
+        return check_launch("dft_small_kernel");
+    }
+    {
+        const int lm = next_pow2_log(2 * N - 1);
+        const long M = 1L << lm;
+        if (lm > TypeCfg<T>::MAX_ROWS_LOG2) { set_error("irfftn: length %ld beyond the single-pass Bluestein limit", N); return XRFTB_EUNSUPPORTED; }
+        const size_t need = (size_t)nseq * (M + N) * sizeof(C);
+        if (wleft < need) { set_error("irfftn: workspace too small (%zu < %zu)", wleft, need); return XRFTB_EWORKSPACE; }
+        const C*chirp, *filt;
+        if (int rc = get_chirp<T>(N, lm, &chirp, &filt, st)) return rc;
+        C* ext = reinterpret_cast<C*>(wbase);
+        C* w = ext + nseq * N;
+        herm_extend_kernel<T><<<ew_grid(nseq * N), 256, 0, st>>>(src, ext, N, 1, nseq * N);
+        const long tw_ = nseq * M;
+        bluestein_pre_kernel<T, false><<<ew_grid(tw_), 256, 0, st>>>(ext, w, chirp, nseq, N, M, 1, 1, tw_);
+        if (int rc = rows_c2c<T>(w, w, lm, nseq, M, M, 0, (T)1, st)) return rc;
+        bluestein_mul_kernel<T><<<ew_grid(tw_), 256, 0, st>>>(w, filt, M, 1, tw_);
+        if (int rc = rows_c2c<T>(w, w, lm, nseq, M, M, 1, (T)(1.0 / M), st)) return rc;
+        bluestein_post_kernel<T, true><<<ew_grid(nseq * N), 256, 0, st>>>(w, out, chirp, nseq, N, N, M, 1, 1, inv_scale, nseq * N);
+        return check_launch("bluestein c2r");
     }
 }
 
@@ -527,12 +802,9 @@ int xrftb_device_info(int* sms, int* major, int* minor, size_t* smem_optin) {
     return 0;
 }
 
-size_t xrftb_fftn_workspace(int dtype, int kind, int ndim, const int64_t* shape, int naxes, const int*) {
-    if (kind != XRFTB_C2R || naxes <= 1) return 0;
-    size_t n = 1;
-    for (int d = 0; d < ndim - 1; ++d) n *= (size_t)shape[d];
-    n *= (size_t)(shape[ndim - 1] / 2 + 1);
-    return n * (dtype == XRFTB_F32 ? 8 : 16);
+size_t xrftb_fftn_workspace(int dtype, int kind, int ndim, const int64_t* shape, int naxes, const int* axes) {
+    if (ndim < 1 || ndim > 8 || naxes < 1 || naxes > ndim || !shape || !axes) return 0;
+    return dtype == XRFTB_F32 ? fftn_workspace_impl<float>(kind, ndim, shape, naxes, axes) : fftn_workspace_impl<double>(kind, ndim, shape, naxes, axes);
 }
 
 int xrftb_fftn(const void* in, void* out, void* work, size_t work_bytes, int dtype, int kind, int ndim, const int64_t* shape,
