@@ -53,6 +53,12 @@ int xrftb_version(void);
 const char* xrftb_last_error(void);
 /* sm_count, compute capability and opt-in shared memory per block of the current device */
 int xrftb_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* smem_optin);
+/* number of kernels this library has launched since the last reset (bench.py's gpu_launches) */
+long xrftb_launch_count(int reset);
+/* per-kernel-class CUDA-event timing of xrftb_spectrum2d: begin() arms it, end() synchronises and returns
+ * summed milliseconds and launch counts for {moments, row pass, column pass, mirror fill}. */
+int xrftb_profile_begin(void);
+int xrftb_profile_end(double ms[4], long counts[4]);
 
 /* ---- (S1) np.fft.fftn / ifftn / rfftn / irfftn --------------------------------------------------
  * N-D transform over `axes` of a C-contiguous array.  `shape[ndim]` is the REAL-SPACE shape.

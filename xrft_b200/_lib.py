@@ -16,6 +16,9 @@ EXPORTS = [
     "xrftb_version",
     "xrftb_last_error",
     "xrftb_device_info",
+    "xrftb_launch_count",
+    "xrftb_profile_begin",
+    "xrftb_profile_end",
     "xrftb_fftn_workspace",
     "xrftb_fftn",
     "xrftb_moments",
@@ -83,6 +86,9 @@ def load():
     lib.xrftb_version.restype = C.c_int
     lib.xrftb_last_error.restype = C.c_char_p
     lib.xrftb_device_info.argtypes = [ip, ip, ip, C.POINTER(C.c_size_t)]
+    lib.xrftb_launch_count.restype = C.c_long
+    lib.xrftb_launch_count.argtypes = [C.c_int]
+    lib.xrftb_profile_end.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_long)]
     lib.xrftb_fftn_workspace.restype = C.c_size_t
     lib.xrftb_fftn_workspace.argtypes = [C.c_int, C.c_int, C.c_int, i64p, C.c_int, ip]
     lib.xrftb_fftn.argtypes = [vp, vp, vp, C.c_size_t, C.c_int, C.c_int, C.c_int, i64p, C.c_int, ip, vp]

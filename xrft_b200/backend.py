@@ -255,6 +255,14 @@ def binned_sum(arr: torch.Tensor, lut: torch.Tensor, nbins: int, ncore: int) -> 
 # fused hot path
 # ---------------------------------------------------------------------------------------------
 _WORK = {}
+_FUSED_CHUNK = 16  # batch items (dask-style chunks along the outer axis) per fused kernel chain
+
+
+def set_fused_chunk(n: int):
+    """Batch items processed per moments -> rows -> cols -> mirror kernel chain (bounds the workspace)."""
+    global _FUSED_CHUNK
+    _FUSED_CHUNK = max(1, int(n))
+
 
 
 def _workspace(device, nbytes):
@@ -278,7 +286,7 @@ def spectrum2d_supported(ny: int, nx: int, dtype, two_fields: bool) -> bool:
 
 def spectrum2d(x1: torch.Tensor, x2: Optional[torch.Tensor], mode: int, detrend: int = 0, win_y=None, win_x=None,
                keep_half=False, shift_y=False, shift_x=False, scale=1.0, ramp_y=None, ramp_x=None, weight_x=None,
-               lut=None, nbins=0, max_work_bytes: int = 2 << 30) -> torch.Tensor:
+               lut=None, nbins=0, max_work_bytes: Optional[int] = None) -> torch.Tensor:
     """Fused detrend + window + 2-D real FFT + epilogue over the last two axes of x1 (and x2)."""
     lib = require_cuda()
     x1 = _dev(x1)
@@ -315,6 +323,10 @@ def spectrum2d(x1: torch.Tensor, x2: Optional[torch.Tensor], mode: int, detrend:
         if need1 == 0:
             raise NotImplementedError(f"spectrum2d: unsupported size {ny}x{nx}")
         needall = lib.xrftb_spectrum2d_workspace(dt, ny, nx, 1 if two else 0, batch)
+        if max_work_bytes is None:
+            # default: _FUSED_CHUNK items of >= 4096^2 points; smaller grids keep ~the same bytes in flight
+            items = max(_FUSED_CHUNK, (_FUSED_CHUNK * 4096 * 4096) // (ny * nx))
+            max_work_bytes = lib.xrftb_spectrum2d_workspace(dt, ny, nx, 1 if two else 0, items)
         wbytes = max(need1, min(needall, max_work_bytes))
         work = _workspace(dev, wbytes)
         # batch is limited to 65535 items per call by the C-ABI

@@ -1,6 +1,7 @@
 // xrft_b200 -- C-ABI entry points, twiddle cache, and the bandwidth-bound elementwise kernels
 // (moments reduce, detrend+window, generic spectral epilogue, radial-bin sum).
 // See include/xrft_b200.h for the reference seams each entry point replaces.
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cmath>
@@ -22,7 +23,9 @@ void set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+static std::atomic<long> g_launches{0};
 int check_launch(const char* what) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("%s launch failed: %s", what, cudaGetErrorString(e)); return XRFTB_ECUDA; }
     return 0;
@@ -37,6 +40,22 @@ int sm_count() {
     }
     return cached > 0 ? cached : 1;
 }
+
+// ------------------------------------------------------------------------------------------------
+// optional per-kernel-class timing of the fused path (CUDA events on the launching stream); used by
+// bench.py to report the dominant kernel's achieved bandwidth.  Off by default (zero overhead).
+// ------------------------------------------------------------------------------------------------
+enum { PROF_MOMENTS = 0, PROF_ROWS = 1, PROF_COLS = 2, PROF_MIRROR = 3, PROF_NKIND = 4 };
+struct ProfRec { cudaEvent_t a, b; int kind; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+struct ProfScope {
+    ProfRec r{}; bool on; cudaStream_t st;
+    ProfScope(int kind, cudaStream_t s) : on(g_prof_on), st(s) {
+        if (on) { r.kind = kind; cudaEventCreate(&r.a); cudaEventCreate(&r.b); cudaEventRecord(r.a, st); }
+    }
+    ~ProfScope() { if (on) { cudaEventRecord(r.b, st); g_prof.push_back(r); } }
+};
 
 // ------------------------------------------------------------------------------------------------
 // twiddle cache
@@ -740,6 +759,7 @@ static int spectrum2d_impl(const xrftb_spectrum2d_desc& q, cudaStream_t st) {
             if (chunks < 1) chunks = 1;
             if (chunks > q.ny) chunks = q.ny;
             dim3 grid(chunks, (unsigned)q.batch);
+            ProfScope ps_(PROF_MOMENTS, st);
             moments_kernel<T><<<grid, 256, 0, st>>>(ins[f], mom + (size_t)f * q.batch * 4, 1, q.ny, q.nx, chunks);
             if (int rc = check_launch("moments_kernel")) return rc;
         }
@@ -759,14 +779,17 @@ static int spectrum2d_impl(const xrftb_spectrum2d_desc& q, cudaStream_t st) {
             io.moments = mom + ((size_t)f * q.batch + b0) * 4;
             io.wy = reinterpret_cast<const T*>(q.win_y); io.wx = reinterpret_cast<const T*>(q.win_x);
             io.out = interm + (size_t)f * bchunk * (per_item / sizeof(C_)); io.logC = ilog2_exact(C); io.out_seq_stride = 0;
+            ProfScope ps_(PROF_ROWS, st);
             if (int rc = rows_r2c<T>(io, lx - 1, nb * q.ny, st)) return rc;
         }
         d.out = bins_mode ? nullptr : reinterpret_cast<char*>(q.out) + (size_t)b0 * q.ny * W * out_elem;
         d.bins = bins_mode ? q.bins + (size_t)b0 * q.nbins * (q.mode == XRFTB_EPI_BINS_CROSS ? 2 : 1) : nullptr;
         const C_* i1 = interm;
         const C_* i2 = two ? interm + (size_t)bchunk * (per_item / sizeof(C_)) : nullptr;
-        if (int rc = cols_fused<T>(q.mode, i1, i2, ly, nb * ntile, (int)ntile, d, st)) return rc;
+        { ProfScope ps_(PROF_COLS, st);
+        if (int rc = cols_fused<T>(q.mode, i1, i2, ly, nb * ntile, (int)ntile, d, st)) return rc; }
         if (mirror_pass) {
+            ProfScope ps_(PROF_MIRROR, st);
             const long nrows = nb * q.ny;
             if (q.mode == XRFTB_EPI_POWER)
                 mirror_fill_kernel<T, false><<<mirror_grid(nrows), 256, 0, st>>>(d.out, ly, lx, q.shift_y, q.shift_x, nullptr, nullptr, nrows);
@@ -786,6 +809,29 @@ using namespace xrftb;
 extern "C" {
 
 int xrftb_version(void) { return XRFTB_VERSION; }
+long xrftb_launch_count(int reset) {
+    long v = g_launches.load();
+    if (reset) g_launches.store(0);
+    return v;
+}
+int xrftb_profile_begin(void) {
+    for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    g_prof.clear();
+    g_prof_on = true;
+    return 0;
+}
+int xrftb_profile_end(double* ms, long* counts) {
+    g_prof_on = false;
+    for (int k = 0; k < PROF_NKIND; ++k) { ms[k] = 0.0; counts[k] = 0; }
+    for (auto& r : g_prof) {
+        cudaEventSynchronize(r.b);
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) { ms[r.kind] += t; counts[r.kind] += 1; }
+        cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    }
+    g_prof.clear();
+    return 0;
+}
 const char* xrftb_last_error(void) { return g_err; }
 
 int xrftb_device_info(int* sms, int* major, int* minor, size_t* smem_optin) {
