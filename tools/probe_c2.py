@@ -26,4 +26,6 @@ for ch in chunks:
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     pts = T * ny * nx
-    print(f"{ny}x{nx}x{T} {dt} chunk={ch}: {ms:.3f} ms/step  {pts / ms / 1e6:.1f} GPts/s  (8 B/pt -> {pts * 8 / ms / 1e6:.0f} GB/s algorithmic)")
+    import ctypes
+    lib.xrftb_profile_begin(); out = run(); pm = (ctypes.c_double * 4)(); pc = (ctypes.c_long * 4)(); lib.xrftb_profile_end(pm, pc)
+    print(f"{ny}x{nx}x{T} {dt} chunk={ch}: {ms:.3f} ms/step  {pts / ms / 1e6:.1f} GPts/s | us/16slices-equiv: " + " ".join(f"{n}={pm[i] * 1e3 * 16 / T:.0f}" for i, n in enumerate(["mom", "rows", "cols", "mirror"])))

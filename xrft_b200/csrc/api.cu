@@ -299,6 +299,38 @@ __global__ void __launch_bounds__(256) mirror_fill_kernel(void* __restrict__ out
         const int oys = (kys + sy) & (Ny - 1);
         const E* src = out + ((b << logNy) | oys) * (long)Nx;
         E* dst = out + ((b << logNy) | oy) * (long)Nx;
+        if constexpr (!CPLX && sizeof(T) == 4) {
+            if (Nx >= 64) {
+                // target column c (in the half being filled) takes source column Nx - c of the other half (both in the
+                // SHIFTED or both in the unshifted frame: (kxs + sx) + (kxt + sx) == Nx (mod Nx)).
+                // Aligned 16 B stores of targets [4g, 4g+3] need sources [Nx-4g-3, Nx-4g]: one aligned float4
+                // [Nx-4g-4, Nx-4g-1] plus the first element of the previous (higher) float4 -> one warp shuffle.
+                const int t0 = shift_x ? 0 : M;            // first column of the target half (column t0 itself is direct)
+                const float* srcf = reinterpret_cast<const float*>(src);
+                float* dstf = reinterpret_cast<float*>(dst);
+                const int ngroups = M / 4;
+                for (int g0 = 0; g0 < ngroups; g0 += blockDim.x) {
+                    const int g = g0 + threadIdx.x;
+                    const bool act = g < ngroups;
+                    const int c = t0 + 4 * g;              // target columns c .. c+3
+                    const int s_hi = (Nx - c) & (Nx - 1);  // source of target c (wraps to 0 when c == 0)
+                    float4 lo = make_float4(0, 0, 0, 0);
+                    if (act) lo = *reinterpret_cast<const float4*>(srcf + ((Nx - c - 4) & (Nx - 1)));  // sources of c+4 .. c+1 (reversed)
+                    // source of target c is element x of the float4 held by the thread handling group g-1
+                    float prev = __shfl_up_sync(0xffffffffu, lo.x, 1);
+                    if ((threadIdx.x & 31) == 0 && act) prev = srcf[s_hi];
+                    if (act) {
+                        float4 o = make_float4(prev, lo.w, lo.z, lo.y);
+                        if (g == 0) {  // column t0 is a direct cell (kx = 0 or Nyquist): keep it
+                            dstf[c + 1] = o.y; dstf[c + 2] = o.z; dstf[c + 3] = o.w;
+                        } else {
+                            *reinterpret_cast<float4*>(dstf + c) = o;
+                        }
+                    }
+                }
+                continue;
+            }
+        }
         cplx<T> ry = mk<T>(1, 0);
         if constexpr (CPLX) { if (ramp_y) ry = cmul(__ldg(ramp_y + kys), __ldg(ramp_y + kyt)); }
 #pragma unroll 4

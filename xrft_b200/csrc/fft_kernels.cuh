@@ -17,7 +17,10 @@
 namespace xrftb {
 
 // register budget: keep >= 512 threads resident per SM (<= 128 registers/thread)
-constexpr int min_blocks_for(int threads) { return threads >= 512 ? 1 : (512 / threads > 8 ? 8 : 512 / threads); }
+#ifndef XRFTB_TARGET_THREADS
+#define XRFTB_TARGET_THREADS 512
+#endif
+constexpr int min_blocks_for(int threads) { return threads >= XRFTB_TARGET_THREADS ? 1 : (XRFTB_TARGET_THREADS / threads > 8 ? 8 : XRFTB_TARGET_THREADS / threads); }
 constexpr int ilog2c(int n) { return n <= 1 ? 0 : 1 + ilog2c(n / 2); }
 
 enum : int { EPI_COMPLEX = 0, EPI_POWER = 1, EPI_CROSS = 2, EPI_PHASE = 3, EPI_BINS_POWER = 4, EPI_BINS_CROSS = 5 };
@@ -39,14 +42,20 @@ rows_kernel(IO io, const cplx<T>* __restrict__ tw, long nseq) {
     const int s = threadIdx.x / NT, u = threadIdx.x % NT;
     cplx<T>* sm = smem + s * SEQ_STRIDE;
     const long ngroups = (nseq + SEQ - 1) / SEQ;
+    // software pipeline: the global loads of the NEXT group are issued before the store phase of the current one
+    cplx<T> raw[E];
+    if ((long)blockIdx.x < ngroups) io.template fetch<LOG2L, LOGE>((long)blockIdx.x * SEQ + s, (long)blockIdx.x * SEQ + s < nseq, u, raw);
     for (long grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
         const long seq = grp * SEQ + s;
         const bool active = seq < nseq;
-        if (threadIdx.x == 0 && grp + gridDim.x < ngroups) io.template prefetch<LOG2L, SEQ>((grp + gridDim.x) * SEQ, nseq);
+        const long nxt = grp + gridDim.x;
+        if (threadIdx.x == 0 && nxt + gridDim.x < ngroups) io.template prefetch<LOG2L, SEQ>((nxt + gridDim.x) * SEQ, nseq);
         cplx<T> v[1][E];
-        io.template load<LOG2L, LOGE>(seq, active, u, v[0]);
+        io.template prologue<LOG2L, LOGE>(seq, active, u, raw, v[0]);
         block_fft<T, LOG2L, LOGE, 1, 1>(v, u, sm, 0, tw);
-        io.template store<LOG2L, LOGE, SEQ>(grp, seq, active, u, s, v[0], smem, SEQ_STRIDE, nseq);
+        io.template store_a<LOG2L, LOGE, SEQ>(grp, seq, active, u, s, v[0], smem, SEQ_STRIDE, nseq);
+        if (nxt < ngroups) io.template fetch<LOG2L, LOGE>(nxt * SEQ + s, nxt * SEQ + s < nseq, u, raw);
+        io.template store_b<LOG2L, LOGE, SEQ>(grp, seq, active, u, s, v[0], smem, SEQ_STRIDE, nseq);
     }
 }
 
@@ -58,19 +67,26 @@ template <typename T> struct RowsC2C {
     template <int LOG2L, int SEQ> __device__ __forceinline__ void prefetch(long, long) const {}
 
     template <int LOG2L, int LOGE>
-    __device__ __forceinline__ void load(long seq, bool active, int u, cplx<T> (&v)[1 << LOGE]) const {
+    __device__ __forceinline__ void fetch(long seq, bool active, int u, cplx<T> (&raw)[1 << LOGE]) const {
         constexpr int NT = Geometry<LOG2L, LOGE>::NT;
         const cplx<T>* p = in + seq * in_stride + u;
 #pragma unroll
         for (int q = 0; q < (1 << LOGE); ++q) {
-            cplx<T> x = mk<T>(0, 0);
-            if (active) x = p[q * NT];
+            raw[q] = mk<T>(0, 0);
+            if (active) raw[q] = p[q * NT];
+        }
+    }
+    template <int LOG2L, int LOGE>
+    __device__ __forceinline__ void prologue(long, bool, int, cplx<T> (&raw)[1 << LOGE], cplx<T> (&v)[1 << LOGE]) const {
+#pragma unroll
+        for (int q = 0; q < (1 << LOGE); ++q) {
+            cplx<T> x = raw[q];
             if (inverse) x.y = -x.y;
             v[q] = x;
         }
     }
     template <int LOG2L, int LOGE, int SEQ>
-    __device__ __forceinline__ void store(long, long seq, bool active, int u, int, cplx<T> (&v)[1 << LOGE], cplx<T>*, int, long) const {
+    __device__ __forceinline__ void store_a(long, long seq, bool active, int u, int, cplx<T> (&v)[1 << LOGE], cplx<T>*, int, long) const {
         using G_ = Geometry<LOG2L, LOGE>;
         constexpr int R = 1 << G_::LOGR_LAST, G = G_::E / R;
         if (!active) return;
@@ -84,6 +100,8 @@ template <typename T> struct RowsC2C {
                 p[final_index<LOG2L, LOGE>(u, g, t)] = cscale(x, scale);
             }
     }
+    template <int LOG2L, int LOGE, int SEQ>
+    __device__ __forceinline__ void store_b(long, long, bool, int, int, cplx<T> (&)[1 << LOGE], cplx<T>*, int, long) const {}
 };
 
 // R2C split of the packed half-length transform: Z = FFT_M(x[2n] + i x[2n+1]), N = 2M:
@@ -120,7 +138,18 @@ template <typename T> struct RowsR2CFused {
     }
 
     template <int LOG2L, int LOGE>
-    __device__ __forceinline__ void load(long seq, bool active, int u, cplx<T> (&v)[1 << LOGE]) const {
+    __device__ __forceinline__ void fetch(long seq, bool active, int u, cplx<T> (&raw)[1 << LOGE]) const {
+        constexpr int NT = Geometry<LOG2L, LOGE>::NT;
+        const cplx<T>* p = reinterpret_cast<const cplx<T>*>(in + seq * in_row_stride) + u;
+#pragma unroll
+        for (int q = 0; q < (1 << LOGE); ++q) {
+            raw[q] = mk<T>(0, 0);
+            if (active) raw[q] = p[q * NT];
+        }
+    }
+
+    template <int LOG2L, int LOGE>
+    __device__ __forceinline__ void prologue(long seq, bool active, int u, cplx<T> (&raw)[1 << LOGE], cplx<T> (&v)[1 << LOGE]) const {
         constexpr int NT = Geometry<LOG2L, LOGE>::NT;
         constexpr int Nx = 2 << LOG2L;
         const int Ny = 1 << logNy;
@@ -142,21 +171,14 @@ template <typename T> struct RowsR2CFused {
         }
         const double pstep = cx * (double)(2 * NT);
         const T wrow = (wy != nullptr && active) ? wy[iy] : (T)1;
-        const cplx<T>* p = reinterpret_cast<const cplx<T>*>(in + seq * in_row_stride) + u;
         const cplx<T>* pw = reinterpret_cast<const cplx<T>*>(wx) + u;
-        cplx<T> x[1 << LOGE];
 #pragma unroll
         for (int q = 0; q < (1 << LOGE); ++q) {
-            x[q] = mk<T>(0, 0);
-            if (active) x[q] = p[q * NT];
-        }
-#pragma unroll
-        for (int q = 0; q < (1 << LOGE); ++q) {
-            cplx<T> y = x[q];
+            cplx<T> y = raw[q];
             if (detrend) {
-                y.x = (T)((double)y.x - p0);
-                y.y = (T)((double)y.y - (p0 + cx));
-                p0 += pstep;
+                const double pq = p0 + (double)q * pstep;  // independent per q: no serial fp64 dependency chain
+                y.x = (T)((double)y.x - pq);
+                y.y = (T)((double)y.y - (pq + cx));
             }
             if (wx != nullptr) {
                 cplx<T> w = __ldg(pw + q * NT);
@@ -178,17 +200,24 @@ template <typename T> struct RowsR2CFused {
     }
 
     template <int LOG2L, int LOGE, int SEQ>
-    __device__ __forceinline__ void store(long grp, long seq, bool active, int u, int s, cplx<T> (&v)[1 << LOGE],
-                                          cplx<T>* smem, int seq_stride, long nseq) const {
+    __device__ __forceinline__ void store_a(long, long, bool, int u, int s, cplx<T> (&v)[1 << LOGE], cplx<T>* smem, int seq_stride, long) const {
         using G_ = Geometry<LOG2L, LOGE>;
-        constexpr int R = 1 << G_::LOGR_LAST, G = G_::E / R, M = G_::L, NT = G_::NT, NTHR = NT * SEQ;
-        constexpr int LOGSEQ = ilog2c(SEQ);
+        constexpr int R = 1 << G_::LOGR_LAST, G = G_::E / R;
         cplx<T>* sm = smem + s * seq_stride;
 #pragma unroll
         for (int g = 0; g < G; ++g)
 #pragma unroll
             for (int t = 0; t < R; ++t) sm[padded<G_::LOGPAD>(final_index<LOG2L, LOGE>(u, g, t))] = v[g + t * G];
         __syncthreads();
+    }
+
+    template <int LOG2L, int LOGE, int SEQ>
+    __device__ __forceinline__ void store_b(long grp, long seq, bool active, int u, int s, cplx<T> (&)[1 << LOGE],
+                                            cplx<T>* smem, int seq_stride, long nseq) const {
+        using G_ = Geometry<LOG2L, LOGE>;
+        constexpr int M = G_::L, NT = G_::NT, NTHR = NT * SEQ, PADW = 1 << G_::LOGPAD;
+        constexpr int LOGSEQ = ilog2c(SEQ);
+        cplx<T>* sm = smem + s * seq_stride;
         if (logC < 0) {
             if (active) {
                 cplx<T>* p = out + seq * out_seq_stride;
@@ -199,7 +228,9 @@ template <typename T> struct RowsR2CFused {
             const int C = 1 << logC;
             const int Ny = 1 << logNy;
             const int ntile = (M >> logC) + 1;
-            if ((NTHR >> (logC + LOGSEQ)) >= 1) {
+            const int tstep = NTHR >> (logC + LOGSEQ);                // tiles covered per sweep of the CTA
+            if (tstep >= 1 && ((tstep << logC) % PADW) == 0 && M % (tstep << logC) == 0) {
+                // k advances by KS = tstep*C (a multiple of the pad width) per sweep: every index below is affine
                 const int c = threadIdx.x & (C - 1);
                 const int s2 = (threadIdx.x >> logC) & (SEQ - 1);
                 const long seq2 = grp * SEQ + s2;
@@ -207,13 +238,30 @@ template <typename T> struct RowsR2CFused {
                     const long b = seq2 >> logNy;
                     const int iy = (int)(seq2 & (Ny - 1));
                     const cplx<T>* smr = smem + s2 * seq_stride;
-                    const int tstep = NTHR >> (logC + LOGSEQ);
+                    const int KS = tstep << logC, KSP = KS + KS / PADW;
+                    const int t0 = threadIdx.x >> (logC + LOGSEQ);
+                    const int k0 = (t0 << logC) + c;                  // 0 <= k0 < KS
                     const long ostep = ((long)Ny << logC) * tstep;
-                    int t = threadIdx.x >> (logC + LOGSEQ);
-                    cplx<T>* po = out + (((b * ntile + t) << logNy) + iy) * C + c;
-                    for (; t < ntile; t += tstep, po += ostep) {
-                        const int k = (t << logC) + c;
-                        *po = (k <= M) ? split_at<LOG2L, LOGE>(smr, k) : mk<T>(0, 0);
+                    cplx<T>* po = out + (((b * ntile + t0) << logNy) + iy) * C + c;
+                    const cplx<T>* pk = smr + padded<G_::LOGPAD>(k0);
+                    const cplx<T>* pm = smr + padded<G_::LOGPAD>((M - k0) & (M - 1));   // k0 == 0 -> Z[0]
+                    const cplx<T>* ptw = tw_r2c + k0;
+                    const int nsweep = M / KS;                         // tiles [0, M/C) : all k < M
+                    {   // first sweep: k0 may be 0 (its mirror index wraps), handled by the pm above
+                        *po = r2c_split<T>(*pk, *pm, __ldg(ptw));
+                        pm = smr + padded<G_::LOGPAD>(M - k0 - KS > 0 ? M - k0 - KS : 0);
+                        pk += KSP; ptw += KS; po += ostep;
+                    }
+#pragma unroll 4
+                    for (int i = 1; i < nsweep; ++i) {
+                        *po = r2c_split<T>(*pk, *pm, __ldg(ptw));
+                        pk += KSP; pm -= KSP; ptw += KS; po += ostep;
+                    }
+                    // last tile (t = M/C): column M (Nyquist) then zero padding
+                    if (t0 == 0) {
+                        cplx<T> z0 = smr[0];
+                        cplx<T>* pl = out + (((b * ntile + (M >> logC)) << logNy) + iy) * C + c;
+                        *pl = (c == 0) ? mk<T>(z0.x - z0.y, 0) : mk<T>(0, 0);
                     }
                 }
             } else {
@@ -245,7 +293,9 @@ template <typename T> struct RowsC2R {
     template <int LOG2L, int SEQ> __device__ __forceinline__ void prefetch(long, long) const {}
 
     template <int LOG2L, int LOGE>
-    __device__ __forceinline__ void load(long seq, bool active, int u, cplx<T> (&v)[1 << LOGE]) const {
+    __device__ __forceinline__ void fetch(long, bool, int, cplx<T> (&)[1 << LOGE]) const {}
+    template <int LOG2L, int LOGE>
+    __device__ __forceinline__ void prologue(long seq, bool active, int u, cplx<T> (&)[1 << LOGE], cplx<T> (&v)[1 << LOGE]) const {
         constexpr int NT = Geometry<LOG2L, LOGE>::NT, M = 1 << LOG2L;
         const cplx<T>* p = in + seq * in_stride;
 #pragma unroll
@@ -265,7 +315,9 @@ template <typename T> struct RowsC2R {
         }
     }
     template <int LOG2L, int LOGE, int SEQ>
-    __device__ __forceinline__ void store(long, long seq, bool active, int u, int, cplx<T> (&v)[1 << LOGE], cplx<T>*, int, long) const {
+    __device__ __forceinline__ void store_b(long, long, bool, int, int, cplx<T> (&)[1 << LOGE], cplx<T>*, int, long) const {}
+    template <int LOG2L, int LOGE, int SEQ>
+    __device__ __forceinline__ void store_a(long, long seq, bool active, int u, int, cplx<T> (&v)[1 << LOGE], cplx<T>*, int, long) const {
         using G_ = Geometry<LOG2L, LOGE>;
         constexpr int R = 1 << G_::LOGR_LAST, G = G_::E / R;
         if (!active) return;
@@ -294,10 +346,13 @@ cols_kernel(IO io, const cplx<T>* __restrict__ tw, long ntiles) {
     const int cg = threadIdx.x % CG, u = threadIdx.x / CG;
     cplx<T>* sm = smem + cg * V;
     io.template init<LOG2L, LOGE, C, V>(smem);
+    // software pipeline: the loads of the NEXT tile are issued between staging the epilogue values in shared memory
+    // (after which the registers are dead) and the cooperative store loop, so their latency hides behind the stores
+    cplx<T> v[V][E];
+    if ((long)blockIdx.x < ntiles) io.template load<LOG2L, LOGE, C, V>((long)blockIdx.x, u, cg, v, 0);
     for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        if (threadIdx.x == 0 && tile + gridDim.x < ntiles) io.template prefetch<LOG2L, C>(tile + gridDim.x);
-        cplx<T> v[V][E];
-        io.template load<LOG2L, LOGE, C, V>(tile, u, cg, v, 0);
+        const long nxt = tile + gridDim.x;
+        if (threadIdx.x == 0 && nxt + gridDim.x < ntiles) io.template prefetch<LOG2L, C>(nxt + gridDim.x);
         block_fft<T, LOG2L, LOGE, V, C>(v, u, sm, 1, tw);
         if constexpr (IO::kTwoFields) {
             // park field-1 spectrum in thread-private smem slots, transform field 2, then combine
@@ -309,10 +364,12 @@ cols_kernel(IO io, const cplx<T>* __restrict__ tw, long ntiles) {
                 for (int q = 0; q < E; ++q) park[(vv * E + q) * NTHR + threadIdx.x] = v[vv][q];
             io.template load<LOG2L, LOGE, C, V>(tile, u, cg, v, 1);
             block_fft<T, LOG2L, LOGE, V, C>(v, u, sm, 1, tw);
-            io.template store<LOG2L, LOGE, C, V>(tile, u, cg, v, smem, park, NTHR);
+            io.template store_a<LOG2L, LOGE, C, V>(tile, u, cg, v, smem, park, NTHR);
         } else {
-            io.template store<LOG2L, LOGE, C, V>(tile, u, cg, v, smem, nullptr, 0);
+            io.template store_a<LOG2L, LOGE, C, V>(tile, u, cg, v, smem, nullptr, 0);
         }
+        if (nxt < ntiles) io.template load<LOG2L, LOGE, C, V>(nxt, u, cg, v, 0);
+        io.template store_b<LOG2L, LOGE, C, V>(tile, smem);
     }
 }
 
@@ -343,8 +400,9 @@ template <typename T> struct ColsC2C {
             }
         }
     }
+    template <int LOG2L, int LOGE, int C, int V> __device__ __forceinline__ void store_b(long, cplx<T>*) const {}
     template <int LOG2L, int LOGE, int C, int V>
-    __device__ __forceinline__ void store(long tile, int u, int cg, cplx<T> (&v)[V][1 << LOGE], cplx<T>*, cplx<T>*, int) const {
+    __device__ __forceinline__ void store_a(long tile, int u, int cg, cplx<T> (&v)[V][1 << LOGE], cplx<T>*, cplx<T>*, int) const {
         using G_ = Geometry<LOG2L, LOGE>;
         constexpr int R = 1 << G_::LOGR_LAST, G = G_::E / R, L = 1 << LOG2L;
         const long a = tile / tiles_per_row;
@@ -442,10 +500,10 @@ template <typename T, int MODE> struct ColsFused {
     }
 
     template <int LOG2L, int LOGE, int C, int V>
-    __device__ __forceinline__ void store(long tile, int u, int cg, cplx<T> (&v)[V][1 << LOGE], cplx<T>* smem, const cplx<T>* park,
-                                          int nthr) const {
+    __device__ __forceinline__ void store_a(long tile, int u, int cg, cplx<T> (&v)[V][1 << LOGE], cplx<T>* smem, const cplx<T>* park,
+                                            int nthr) const {
         using G_ = Geometry<LOG2L, LOGE>;
-        constexpr int R = 1 << G_::LOGR_LAST, G = G_::E / R, E = G_::E, Ny = 1 << LOG2L, NTHR = G_::NT * (C / V);
+        constexpr int R = 1 << G_::LOGR_LAST, G = G_::E / R, E = G_::E;
         StageT* stage = reinterpret_cast<StageT*>(smem);
         const T sc = (T)d.scale;
         // ---- 1. epilogue value of each owned (ky, c) -> staging [ky][C]
@@ -468,6 +526,13 @@ template <typename T, int MODE> struct ColsFused {
                 }
             }
         __syncthreads();
+    }
+
+    template <int LOG2L, int LOGE, int C, int V>
+    __device__ __forceinline__ void store_b(long tile, cplx<T>* smem) const {
+        using G_ = Geometry<LOG2L, LOGE>;
+        constexpr int Ny = 1 << LOG2L, NTHR = G_::NT * (C / V);
+        StageT* stage = reinterpret_cast<StageT*>(smem);
         // ---- 2. cooperative row-segment stores
         const int Nx = 1 << d.logNx, M = Nx >> 1;
         const int W = d.full ? Nx : M + 1;

@@ -16,7 +16,10 @@ template <typename T> const cplx<T>* twiddle_fft(int log2L);  // exp(-2 pi i m /
 template <typename T> const cplx<T>* twiddle_r2c(int log2N);  // exp(-2 pi i k / N), k in [0, N/2]
 
 template <typename T> struct TypeCfg;
-template <> struct TypeCfg<float> { static constexpr int LOGE = 4; static constexpr int V = 2; static constexpr int TILE_POINTS = 16384; static constexpr int CMAX = 16; static constexpr int MAX_ROWS_LOG2 = 14; static constexpr int MAX_COLS_LOG2 = 13; };
+#ifndef XRFTB_F32_LOGE
+#define XRFTB_F32_LOGE 4
+#endif
+template <> struct TypeCfg<float> { static constexpr int LOGE = XRFTB_F32_LOGE; static constexpr int V = 2; static constexpr int TILE_POINTS = 16384; static constexpr int CMAX = 16; static constexpr int MAX_ROWS_LOG2 = 14; static constexpr int MAX_COLS_LOG2 = 13; };
 template <> struct TypeCfg<double> { static constexpr int LOGE = 3; static constexpr int V = 1; static constexpr int TILE_POINTS = 8192; static constexpr int CMAX = 8; static constexpr int MAX_ROWS_LOG2 = 13; static constexpr int MAX_COLS_LOG2 = 13; };
 
 // tile width (columns per CTA) of the strided pass for a given length

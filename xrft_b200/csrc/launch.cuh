@@ -23,7 +23,10 @@ constexpr int cmax(int a, int b) { return a > b ? a : b; }
 
 // sequences per CTA on the contiguous-axis pass
 template <int LOG2L, int LOGE> constexpr int rows_seq_generic() { return cmax(1, cmin(128, 256 >> (LOG2L - LOGE))); }
-template <int LOG2L, int LOGE> constexpr int rows_seq_fused() { return cmax(rows_seq_generic<LOG2L, LOGE>(), cmax(1, cmin(4, 512 >> (LOG2L - LOGE)))); }
+#ifndef XRFTB_FUSED_CTA_THREADS
+#define XRFTB_FUSED_CTA_THREADS 512
+#endif
+template <int LOG2L, int LOGE> constexpr int rows_seq_fused() { return cmax(rows_seq_generic<LOG2L, LOGE>(), cmax(1, cmin(4, XRFTB_FUSED_CTA_THREADS >> (LOG2L - LOGE)))); }
 
 template <typename T, int LOG2L, int SEQ, class IO>
 static int launch_rows(const IO& io, long nseq, cudaStream_t st) {

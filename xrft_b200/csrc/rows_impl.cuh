@@ -1,5 +1,6 @@
 // xrft_b200 -- contiguous-axis pass dispatch (length -> template instantiation).
 #pragma once
+#include <cstdlib>
 #include "launch.cuh"
 
 namespace xrftb {
@@ -27,6 +28,17 @@ template <typename T>
 int rows_r2c(RowsR2CFused<T> io, int log2M, long nseq, cudaStream_t st) {
     io.tw_r2c = twiddle_r2c<T>(log2M + 1);
     if (!io.tw_r2c) return -3;
+    // tuning knob (experiments): rows per CTA of the fused pass for the large sizes
+    static int seq_override = -1;
+    if (seq_override < 0) { const char* e = getenv("XRFTB_ROWS_SEQ"); seq_override = e ? atoi(e) : 0; }
+    if (seq_override > 0 && log2M >= 9 && log2M <= 12) {
+        switch (log2M * 10 + seq_override) {
+#define Y(K, S) case K * 10 + S: return launch_rows<T, K, S>(io, nseq, st);
+            Y(9, 1) Y(9, 2) Y(9, 4) Y(10, 1) Y(10, 2) Y(10, 4) Y(11, 1) Y(11, 2) Y(11, 4) Y(12, 1) Y(12, 2)
+#undef Y
+            default: break;
+        }
+    }
     switch (log2M) {
 #define X(K) case K: return launch_rows<T, K, rows_seq_fused<K, cmin(TypeCfg<T>::LOGE, K)>()>(io, nseq, st);
         XRFTB_ROWS_CASES(X)
