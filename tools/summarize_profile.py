@@ -8,7 +8,7 @@ for row in csv.DictReader(lines):
     n = row["Kernel Name"]
     short = re.sub(r"\(.*", "", n)
     short = re.sub(r"xrftb::", "", short)
-    if "xrftb" not in n: short = "[torch] " + short[:60]
+    if "at::" in n or "at_cuda" in n or "elementwise" in n: short = "[torch] " + short[:60]
     tot[short] = tot.get(short, 0.0) + float(row["Metric Value"].replace(",", "")); cnt[short] += 1
 total = sum(tot.values())
 md = ["# ncu launch list (gpu__time_duration.sum, --clock-control none; cold-cache, serialised: compare SHARES)", "",
