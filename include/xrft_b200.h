@@ -141,6 +141,7 @@ typedef struct {
     const int32_t* lut;
     double* bins;
     int nbins;
+    int lut_symmetric;    /* 1 if lut[-ky][-kx] == lut[ky][kx] for all cells (radial bins): lets mirrored cells reuse the bin */
     void* work;
     size_t work_bytes;
 } xrftb_spectrum2d_desc;

@@ -58,6 +58,7 @@ class Spectrum2dDesc(C.Structure):
         ("lut", C.c_void_p),
         ("bins", C.c_void_p),
         ("nbins", C.c_int),
+        ("lut_symmetric", C.c_int),
         ("work", C.c_void_p),
         ("work_bytes", C.c_size_t),
     ]

@@ -311,7 +311,13 @@ def spectrum2d(x1: torch.Tensor, x2: Optional[torch.Tensor], mode: int, detrend:
     win_y, win_x, weight_x = prep(win_y, rdt), prep(win_x, rdt), prep(weight_x, rdt)
     ramp_y, ramp_x = prep(ramp_y, cdt), prep(ramp_x, cdt)
     bins_mode = mode in (L.EPI_BINS_POWER, L.EPI_BINS_CROSS)
+    lut_sym = 0
     if bins_mode:
+        lc = lut.to(dtype=torch.int32)
+        if lc.ndim == 2 and lc.shape == (ny, W) and not keep_half:
+            # symmetric under (ky, kx) -> (-ky, -kx) in the unshifted frame == same test in the shifted frame (even sizes)
+            us = torch.roll(lc, shifts=(-(ny // 2) if shift_y else 0, -(nx // 2) if shift_x else 0), dims=(0, 1))
+            lut_sym = int(torch.equal(us, torch.roll(torch.flip(us, dims=(0, 1)), shifts=(1, 1), dims=(0, 1))))
         lut = lut.to(device=dev, dtype=torch.int32).contiguous()
         out = torch.zeros(lead + [nbins] + ([2] if mode == L.EPI_BINS_CROSS else []), dtype=torch.float64, device=dev)
     else:
@@ -349,6 +355,7 @@ def spectrum2d(x1: torch.Tensor, x2: Optional[torch.Tensor], mode: int, detrend:
             d.weight_x = weight_x.data_ptr() if weight_x is not None else None
             if bins_mode:
                 d.out, d.lut, d.bins, d.nbins = None, lut.data_ptr(), oflat[b0:].data_ptr(), nbins
+                d.lut_symmetric = lut_sym
             else:
                 d.out, d.lut, d.bins, d.nbins = oflat[b0:].data_ptr(), None, None, 0
             d.work, d.work_bytes = work.data_ptr(), work.numel()

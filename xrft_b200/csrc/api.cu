@@ -105,7 +105,30 @@ __global__ void __launch_bounds__(512) moments_kernel(const T* __restrict__ in, 
     const double c0m = 0.5 * (double)(n0 - 1), c1m = 0.5 * (double)(n1 - 1), c2m = 0.5 * (double)(n2 - 1);
     double S = 0, S0 = 0, S1 = 0, S2 = 0;
     const bool vec = (sizeof(T) == 4) && (n2 % 4 == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0);
-    if (vec) {
+    if (vec && n2 / 4 < 2 * (long)blockDim.x) {
+        // short rows: flat float4 index over the CTA's row range so every thread has work
+        const long n4 = n2 / 4;
+        const float4* p4 = reinterpret_cast<const float4*>(base + r0 * n2);
+        const long tot4 = (r1 - r0) * n4;
+        const bool p2 = (n4 & (n4 - 1)) == 0;
+        int sh = 0;
+        while ((1L << sh) < n4) ++sh;
+        double s = 0, sx = 0, sy0 = 0, sy1 = 0;
+        for (long i = threadIdx.x; i < tot4; i += blockDim.x) {
+            float4 x = __ldg(p4 + i);
+            const long rr = p2 ? (i >> sh) : (i / n4);
+            const long c4 = i - rr * n4;
+            const float c = (float)((double)(4 * c4) - c2m);
+            const double s4 = (double)((x.x + x.y) + (x.z + x.w));
+            const long r = r0 + rr;
+            const long i0 = r / n1, i1 = r - i0 * n1;
+            s += s4;
+            sx += (double)((c * x.x + (c + 1.f) * x.y) + ((c + 2.f) * x.z + (c + 3.f) * x.w));
+            sy0 += ((double)i0 - c0m) * s4;
+            sy1 += ((double)i1 - c1m) * s4;
+        }
+        S = s; S0 = sy0; S1 = sy1; S2 = sx;
+    } else if (vec) {
         // thread-private column position is fixed when blockDim divides the row: weights hoisted
         const long n4 = n2 / 4;
         for (long r = r0; r < r1; ++r) {
@@ -799,7 +822,7 @@ static int spectrum2d_impl(const xrftb_spectrum2d_desc& q, cudaStream_t st) {
     EpilogueDesc d{};
     const bool mirror_pass = !q.keep_half && (q.mode == XRFTB_EPI_POWER || q.mode == XRFTB_EPI_COMPLEX || q.mode == XRFTB_EPI_CROSS) && q.nx >= 8;
     d.logNx = lx; d.full = q.keep_half ? 0 : (mirror_pass ? 2 : 1); d.shift_y = q.shift_y; d.shift_x = q.shift_x;
-    d.scale = q.scale; d.ramp_y = q.ramp_y; d.ramp_x = q.ramp_x; d.weight_x = q.weight_x; d.lut = q.lut; d.nbins = q.nbins;
+    d.scale = q.scale; d.ramp_y = q.ramp_y; d.ramp_x = q.ramp_x; d.weight_x = q.weight_x; d.lut = q.lut; d.nbins = q.nbins; d.lut_symmetric = q.lut_symmetric;
     const long W = q.keep_half ? q.nx / 2 + 1 : q.nx;
     const bool bins_mode = (q.mode == XRFTB_EPI_BINS_POWER || q.mode == XRFTB_EPI_BINS_CROSS);
     const size_t out_elem = (q.mode == XRFTB_EPI_COMPLEX || q.mode == XRFTB_EPI_CROSS) ? sizeof(C_) : sizeof(T);
