@@ -432,3 +432,28 @@ def test_reference_sizes_round_trip_and_iso():
         ref = O.isotropic_power_spectrum(lab(da2), dim=["y", "x"], detrend="linear", window="hann")
     assert relerr(out.values, ref.data) < 1e-8
     np.testing.assert_allclose(out["freq_r"].values, ref.coords["freq_r"], rtol=1e-12)
+
+
+def test_host_streaming_matches_device_path():
+    """numpy in -> numpy out through the chunk-streamed (H2D | kernels | D2H) path equals the device-resident path."""
+    import torch
+    from xrft_b200 import api as A
+    rng = np.random.default_rng(21)
+    x = (rng.standard_normal((24, 128, 256)) + 0.1 * np.arange(256)).astype(np.float32)
+    c = {"t": np.arange(24.0), "y": np.arange(128) * 1.0, "x": np.arange(256) * 1.0}
+    old = (A._STREAM_MIN_BYTES, A._STREAM_CHUNK_BYTES)
+    A._STREAM_MIN_BYTES, A._STREAM_CHUNK_BYTES = 1, 5 * 128 * 256 * 4  # 5 items per chunk -> ragged last chunk
+    try:
+        host = xrft.power_spectrum(DataArray(x, dims=["t", "y", "x"], coords=c), dim=["y", "x"], detrend="linear", window="hann")
+        assert isinstance(host.data, np.ndarray)
+        outbuf = torch.empty((24, 128, 256), dtype=torch.float32).pin_memory()
+        host2 = xrft.power_spectrum(DataArray(x, dims=["t", "y", "x"], coords=c), dim=["y", "x"], detrend="linear", window="hann", out=outbuf)
+        cs = xrft.cross_spectrum(DataArray(x, dims=["t", "y", "x"], coords=c), DataArray(x[::-1].copy(), dims=["t", "y", "x"], coords=c), dim=["y", "x"])
+    finally:
+        A._STREAM_MIN_BYTES, A._STREAM_CHUNK_BYTES = old
+    devres = xrft.power_spectrum(DataArray(torch.from_numpy(x).cuda(), dims=["t", "y", "x"], coords=c), dim=["y", "x"], detrend="linear", window="hann")
+    np.testing.assert_array_equal(host.values, devres.values)
+    np.testing.assert_array_equal(host2.values, devres.values)
+    np.testing.assert_array_equal(outbuf.numpy(), devres.values)
+    ref = O.cross_spectrum(lab(DataArray(x, dims=["t", "y", "x"], coords=c)), lab(DataArray(x[::-1].copy(), dims=["t", "y", "x"], coords=c)), dim=["y", "x"])
+    assert relerr(cs.values, ref.data) < 1e-3

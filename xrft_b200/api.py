@@ -349,7 +349,66 @@ def _label_output(P, data, new_last_sizes=None, extra_attrs=True):
     return out.transpose(*[swap.get(d, d) for d in P["rawdims"]])
 
 
-def _run_forward(P, das, mode, detrend, window, scale, ramps=None, weight=None, lut=None, nbins=0):
+_STREAM_MIN_BYTES = 256 << 20    # host inputs at least this large are streamed chunk-wise (H2D | compute | D2H overlap)
+_STREAM_CHUNK_BYTES = 256 << 20  # target input bytes per streamed chunk
+
+
+def _stream_host_chunks(arrs, ntrans, out_host, core):
+    """Out-of-core style execution for HOST (numpy) inputs whose transform axes are trailing: the leading (batch)
+    axis is cut into chunks that flow through three CUDA streams -- host->device copy of chunk i+1, kernels of
+    chunk i and device->host copy of chunk i-1 overlap (the role dask's chunk iteration plays in the reference).
+    `core(x1, x2)` runs the device numerics for one chunk; the result lands in `out_host` (pinned if possible)."""
+    torch = _torch()
+    host = [torch.from_numpy(np.ascontiguousarray(a)) for a in arrs]
+    lead = host[0].shape[0]
+    per_item = host[0][0].numel() * host[0].element_size()
+    step = max(1, min(lead, _STREAM_CHUNK_BYTES // max(per_item, 1)))
+    dev = torch.device("cuda", torch.cuda.current_device())
+    s_in, s_cmp, s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
+    cur = torch.cuda.current_stream()
+    for st in (s_in, s_cmp, s_out):
+        st.wait_stream(cur)
+    bufs = [[torch.empty((step,) + tuple(h.shape[1:]), dtype=h.dtype, device=dev) for h in host] for _ in range(2)]
+    ev_in = [torch.cuda.Event() for _ in range(2)]
+    ev_free = [torch.cuda.Event() for _ in range(2)]   # input buffer b consumed by the kernels
+    result = None
+    keep = []
+    for i, lo in enumerate(range(0, lead, step)):
+        hi = min(lead, lo + step)
+        b = i % 2
+        with torch.cuda.stream(s_in):
+            if i >= 2:
+                s_in.wait_event(ev_free[b])
+            for h, d in zip(host, bufs[b]):
+                d[: hi - lo].copy_(h[lo:hi], non_blocking=True)
+            ev_in[b].record(s_in)
+        with torch.cuda.stream(s_cmp):
+            s_cmp.wait_event(ev_in[b])
+            xs = [d[: hi - lo] for d in bufs[b]]
+            o = core(xs[0], xs[1] if len(xs) == 2 else None)
+            ev_free[b].record(s_cmp)
+            done = torch.cuda.Event()
+            done.record(s_cmp)
+        if out_host is None:
+            full = (lead,) + tuple(o.shape[1:])
+            try:
+                out_host = torch.empty(full, dtype=o.dtype, pin_memory=True)
+            except Exception:  # pragma: no cover - pinned allocation can fail on small hosts
+                out_host = torch.empty(full, dtype=o.dtype)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(done)
+            o.record_stream(s_out)
+            out_host[lo:hi].copy_(o, non_blocking=True)
+        keep.append(o)
+        if len(keep) > 3:
+            keep.pop(0)
+    for st in (s_in, s_cmp, s_out):
+        cur.wait_stream(st)
+    torch.cuda.current_stream().synchronize()
+    return out_host
+
+
+def _run_forward(P, das, mode, detrend, window, scale, ramps=None, weight=None, lut=None, nbins=0, out=None):
     """Numerics of fft/power/cross for the prepared plan P on one or two DataArrays (already stacked/transposed)."""
     torch = _torch()
     dim, real_dim = P["dim"], P["real_dim"]
@@ -359,6 +418,27 @@ def _run_forward(P, das, mode, detrend, window, scale, ramps=None, weight=None, 
     if detrend not in (None, "constant", "linear"):
         raise NotImplementedError("%s is not a valid detrending option. Valid options are: 'constant','linear', or None." % detrend)
     wins = _window_vectors(P["N"], window) if window is not None else None
+    # ---- host inputs: stream chunks of the leading axis (numpy in -> numpy out, like the reference)
+    nd = P["da"].ndim
+    host_in = all(not _is_torch(d.data) for d in das)
+    trailing = list(P["axis_num"]) == list(range(nd - ntrans, nd))
+    if (host_in and trailing and nd > ntrans and not P["reversed_dims"] and mode not in (L.EPI_BINS_POWER, L.EPI_BINS_CROSS)
+            and das[0].data.dtype in (np.float32, np.float64) and all(d.data.dtype == das[0].data.dtype for d in das)
+            and das[0].data.nbytes >= _STREAM_MIN_BYTES and das[0].shape[0] >= 2):
+        from . import backend as B
+        B.require_cuda()
+        keep_half = real_dim is not None
+        shifts = [P["shift"]] * ntrans if real_dim is None else [False] * ntrans
+
+        def core(x1, x2):
+            return _spectral_core(x1, x2, ntrans, mode, detrend=detrend, windows=wins, keep_half=keep_half, shift=shifts,
+                                  ramps=ramps, weight=weight, scale=scale)
+
+        oh = None
+        if out is not None:
+            oh = out if _is_torch(out) else torch.from_numpy(out)
+        res = _stream_host_chunks([d.data for d in das], ntrans, oh, core)
+        return res.numpy() if out is None or not _is_torch(out) else res
     xs = []
     inv = None
     for da in das:
@@ -592,6 +672,7 @@ def power_spectrum(da, dim=None, real_dim=None, scaling="density", window_correc
 
 def _spectrum(da1, da2, mode, dim, real_dim, scaling, window_correction, kwargs, bins=None):
     kw = dict(kwargs)
+    out_buf = kw.pop("out", None)  # extension: preallocated (pinned) host result buffer for streamed host inputs
     detrend_t = kw.pop("detrend", None)
     window = kw.pop("window", None)
     true_phase = kw.pop("true_phase", True)
@@ -627,7 +708,7 @@ def _spectrum(da1, da2, mode, dim, real_dim, scaling, window_correction, kwargs,
         n_real = da1.sizes[P["real_dim"]] if not c2s else P["da"].sizes[P["real_dim"]]
         weight = _real_dim_weights(n_real, P["N"][-1] // 2 + 1)
     lut, nbins = (None, 0) if bins is None else bins(P)
-    out = _run_forward(P, das, mode, detrend_t, window, scale, ramps=ramps, weight=weight, lut=lut, nbins=nbins)
+    out = _run_forward(P, das, mode, detrend_t, window, scale, ramps=ramps, weight=weight, lut=lut, nbins=nbins, out=out_buf)
     return P, out
 
 
