@@ -68,10 +68,10 @@ int xrftb_profile_end(double ms[4], long counts[4]);
  *   C2R         : in complex (last dim N/2+1), out real `shape`; same axis rule; needs a workspace of
  *                 the input's size when naxes > 1 (input is never modified).
  * Lengths: powers of two up to 2^14 (f32) / 2^13 (f64) on the contiguous axis (R2C/C2R: twice that) and
- * up to 8192 on strided axes run on the Stockham kernels; any length <= 64 runs a direct DFT; any other
- * length n runs Bluestein's chirp-z on the same kernels as long as nextpow2(2n-1) fits those limits
- * (n <= 8192 f32 / 4096 f64 contiguous, n <= 4096 strided); beyond that XRFTB_EUNSUPPORTED.
- * `work` must hold xrftb_fftn_workspace(...) bytes (0 for power-of-two C2C/R2C).  in == out is allowed for C2C. */
+ * up to 8192 on strided axes run in one Stockham pass; longer powers of two (to 2^26) run the four-step
+ * decomposition n = n1*n2 on the same kernels; any length <= 64 runs a direct DFT; every other length runs
+ * Bluestein's chirp-z on top of the power-of-two machinery.  `work` must hold xrftb_fftn_workspace(...) bytes
+ * (0 for single-pass power-of-two C2C/R2C).  in == out is allowed for C2C. */
 size_t xrftb_fftn_workspace(int dtype, int kind, int ndim, const int64_t* shape, int naxes, const int* axes);
 int xrftb_fftn(const void* in, void* out, void* work, size_t work_bytes, int dtype, int kind, int ndim,
                const int64_t* shape, int naxes, const int* axes, void* stream);

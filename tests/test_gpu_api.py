@@ -457,3 +457,19 @@ def test_host_streaming_matches_device_path():
     np.testing.assert_array_equal(outbuf.numpy(), devres.values)
     ref = O.cross_spectrum(lab(DataArray(x, dims=["t", "y", "x"], coords=c)), lab(DataArray(x[::-1].copy(), dims=["t", "y", "x"], coords=c)), dim=["y", "x"])
     assert relerr(cs.values, ref.data) < 1e-3
+
+
+def test_theoretical_matching_440000_points():
+    """xrft/tests/test_xrft.py:1210-1228: FT of a gate function is a sinc (440 000-point transform, atol 1e-3)."""
+    dx = 0.0001
+    x = np.arange(-22.0, 22.0, dx)[:440000]
+    T = 1.0
+    y = np.where(np.abs(x) <= T / 2, 1.0, 0.0)
+    da = DataArray(y, dims=["x"], coords={"x": x})
+    ft = xrft.fft(da, true_phase=True, true_amplitude=True)
+    k = ft["freq_x"].values
+    sel = np.abs(k) < 30
+    np.testing.assert_allclose(ft.values.real[sel], T * np.sinc(k[sel] * T), atol=1e-3)
+    np.testing.assert_allclose(ft.values.imag[sel], 0, atol=1e-3)
+    ref = O.fft(lab(da), true_phase=True, true_amplitude=True)
+    assert relerr(ft.values, ref.data) < 1e-9

@@ -140,3 +140,37 @@ def test_binned_sum_and_moments():
     np.testing.assert_allclose(m[:, 0], a.sum(axis=(1, 2)), rtol=1e-12)
     np.testing.assert_allclose(m[:, 2], (a * iy[None, :, None]).sum(axis=(1, 2)), rtol=1e-10, atol=1e-9)
     np.testing.assert_allclose(m[:, 3], (a * ix[None, None, :]).sum(axis=(1, 2)), rtol=1e-10, atol=1e-9)
+
+
+# ------------------------------------------------- lengths beyond one CTA: four-step (+ Bluestein on top of it)
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("n", [1 << 15, 1 << 16, 1 << 18, 20000, 440000])
+def test_long_contiguous(dt, n):
+    from xrft_b200 import backend as B
+    rng = np.random.default_rng(n % 1000)
+    x = cplx(rng, (2, n), dt)
+    tol = 5e-5 if dt == np.float32 else 1e-11
+    y = B.fftn(torch.from_numpy(x).cuda(), axes=[1]).cpu().numpy()
+    assert relerr(y, np.fft.fft(x.astype(np.complex128), axis=1)) < tol
+    yi = B.ifftn(torch.from_numpy(x).cuda(), axes=[1]).cpu().numpy()
+    assert relerr(yi, np.fft.ifft(x.astype(np.complex128), axis=1)) < tol
+    xr = rng.standard_normal((2, n)).astype(dt)
+    yr = B.rfftn(torch.from_numpy(xr).cuda(), axes=[1]).cpu().numpy()
+    ref = np.fft.rfft(xr.astype(np.float64), axis=1)
+    assert relerr(yr, ref) < tol
+    if n % 2 == 0:
+        back = B.irfftn(torch.from_numpy(ref.astype(yr.dtype)).cuda(), axes=[1]).cpu().numpy()
+        assert relerr(back, xr) < tol
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_long_strided_16384(dt):
+    """the strided axis of BASELINE config 5 at full size (8192^2 padded to 16384^2): four-step 128 x 128"""
+    from xrft_b200 import backend as B
+    rng = np.random.default_rng(5)
+    x = cplx(rng, (16384, 9), dt)
+    y = B.fftn(torch.from_numpy(x).cuda(), axes=[0]).cpu().numpy()
+    assert relerr(y, np.fft.fft(x.astype(np.complex128), axis=0)) < (5e-5 if dt == np.float32 else 1e-11)
+    xr = rng.standard_normal((16384, 64)).astype(dt)
+    yr = B.rfftn(torch.from_numpy(xr).cuda(), axes=[0, 1]).cpu().numpy()
+    assert relerr(yr, np.fft.rfftn(xr.astype(np.float64))) < (5e-5 if dt == np.float32 else 1e-11)

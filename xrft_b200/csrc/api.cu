@@ -515,6 +515,51 @@ __global__ void __launch_bounds__(256) herm_extend_kernel(const cplx<T>* __restr
     }
 }
 
+// four-step helpers for power-of-two lengths beyond one CTA's shared memory: n = n1 * n2,
+//   x[i1*n2 + i2] --FFT over i1--> Y[k1][i2] --* w_n^(k1 i2)--> --FFT over i2--> Z[k1][k2] --transpose--> X[k1 + n1 k2]
+template <typename T>
+__global__ void __launch_bounds__(256) fourstep_twiddle_kernel(cplx<T>* __restrict__ y, long n1, long n2, long B, int conj_tw, long total) {
+    const double inv_n = 1.0 / (double)(n1 * n2);
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long i2 = (i / B) % n2;
+        const long k1 = (i / (B * n2)) % n1;
+        const long r = (k1 * i2) % (n1 * n2);
+        double sn, cs;
+        sincospi(-2.0 * (double)r * inv_n, &sn, &cs);
+        if (conj_tw) sn = -sn;
+        cplx<T> v = y[i];
+        y[i] = mk<T>((T)((double)v.x * cs - (double)v.y * sn), (T)((double)v.x * sn + (double)v.y * cs));
+    }
+}
+// out[a][k2][k1][b] = in[a][k1][k2][b] * scale
+template <typename T>
+__global__ void __launch_bounds__(256) fourstep_transpose_kernel(const cplx<T>* __restrict__ in, cplx<T>* __restrict__ out, long n1, long n2, long B,
+                                                                 T scale, long total) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long b = i % B;
+        long r = i / B;
+        const long k1 = r % n1;
+        r /= n1;
+        const long k2 = r % n2;
+        const long a = r / n2;
+        out[i] = cscale(in[((a * n1 + k1) * n2 + k2) * B + b], scale);
+    }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) real_to_cplx_kernel(const T* __restrict__ in, cplx<T>* __restrict__ out, long total) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) out[i] = mk<T>(in[i], 0);
+}
+// out[s][k] = in[s][k] for k < H (complex crop) or out[s][n] = Re in[s][n] (REAL_OUT, H == N)
+template <typename T, bool REAL_OUT>
+__global__ void __launch_bounds__(256) crop_kernel(const cplx<T>* __restrict__ in, void* __restrict__ out, long N, long H, long total) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long k = i % H, sq = i / H;
+        cplx<T> v = in[sq * N + k];
+        if (REAL_OUT) reinterpret_cast<T*>(out)[i] = v.x;
+        else reinterpret_cast<cplx<T>*>(out)[i] = v;
+    }
+}
+
 static inline int next_pow2_log(long n) { int l = 0; while ((1L << l) < n) ++l; return l; }
 
 static inline int ilog2_exact(int64_t n) {
@@ -542,6 +587,25 @@ static inline unsigned ew_grid(long total) {
 // ------------------------------------------------------------------------------------------------
 static std::map<std::tuple<int, int, long, int>, std::pair<void*, void*>> g_chirp;  // (device, dtype, N, log2M) -> (chirp, filter)
 
+template <typename T> static bool fast_len(long n, bool contiguous) {
+    const int l2 = ilog2_exact(n);
+    if (l2 < 1) return false;
+    return l2 <= (contiguous ? TypeCfg<T>::MAX_ROWS_LOG2 : TypeCfg<T>::MAX_COLS_LOG2);
+}
+// workspace (bytes) one C2C pass of length n over an [A][n][B] view needs
+template <typename T> static size_t pass_workspace(long A, long n, long B) {
+    if (n <= 1 || fast_len<T>(n, B == 1) || n <= kSmallDft) return 0;
+    const size_t al = 256;
+    if (ilog2_exact(n) > 0) return (((size_t)A * n * B * sizeof(cplx<T>)) + al) & ~(al - 1);   // four-step scratch
+    const int lm = next_pow2_log(2 * n - 1);
+    const long M = 1L << lm;
+    return ((((size_t)A * M * B * sizeof(cplx<T>)) + al) & ~(al - 1)) + pass_workspace<T>(A, M, B);
+}
+
+template <typename T>
+static int c2c_pass(const cplx<T>* src, cplx<T>* dst, long A, long n, long B, int inverse, T scale, void* work, size_t work_bytes,
+                    cudaStream_t st);
+
 template <typename T> static int get_chirp(long N, int log2M, const cplx<T>** chirp, const cplx<T>** filt, cudaStream_t st) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -556,7 +620,7 @@ template <typename T> static int get_chirp(long N, int log2M, const cplx<T>** ch
     std::vector<cplx<T>> hb(N), hc(M);
     for (long m = 0; m < M; ++m) hc[m] = mk<T>(0, 0);
     for (long n = 0; n < N; ++n) {
-        const long r = (n * n) % (2 * N);  // exp(-i pi n^2 / N) has period 2N in n^2
+        const long r = (long)(((__int128)n * n) % (2 * N));  // exp(-i pi n^2 / N) has period 2N in n^2
         const double ang = -M_PI * (double)r / (double)N;
         hb[n] = mk<T>((T)cos(ang), (T)sin(ang));
         cplx<T> cj = mk<T>(hb[n].x, -hb[n].y);
@@ -564,32 +628,24 @@ template <typename T> static int get_chirp(long N, int log2M, const cplx<T>** ch
         if (n > 0) hc[M - n] = cj;
     }
     cplx<T>*db = nullptr, *dc = nullptr, *df = nullptr;
+    void* tmp = nullptr;
+    const size_t ws = pass_workspace<T>(1, M, 1);
     cudaError_t e = cudaMalloc(&db, N * sizeof(cplx<T>));
     if (e == cudaSuccess) e = cudaMalloc(&dc, M * sizeof(cplx<T>));
     if (e == cudaSuccess) e = cudaMalloc(&df, M * sizeof(cplx<T>));
+    if (e == cudaSuccess && ws) e = cudaMalloc(&tmp, ws);
     if (e == cudaSuccess) e = cudaMemcpy(db, hb.data(), N * sizeof(cplx<T>), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(dc, hc.data(), M * sizeof(cplx<T>), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { set_error("chirp table: %s", cudaGetErrorString(e)); return XRFTB_ECUDA; }
-    int rc = rows_c2c<T>(dc, df, log2M, 1, M, M, 0, (T)1, st);
+    int rc = c2c_pass<T>(dc, df, 1, M, 1, 0, (T)1, tmp, ws, st);
     if (rc) return rc;
     cudaStreamSynchronize(st);
     cudaFree(dc);
+    if (tmp) cudaFree(tmp);
     std::lock_guard<std::mutex> lk(g_tw_mu);
     g_chirp[key] = std::make_pair((void*)db, (void*)df);
     *chirp = db; *filt = df;
     return 0;
-}
-
-template <typename T> static bool fast_len(long n, bool contiguous) {
-    const int l2 = ilog2_exact(n);
-    if (l2 < 1) return false;
-    return l2 <= (contiguous ? TypeCfg<T>::MAX_ROWS_LOG2 : TypeCfg<T>::MAX_COLS_LOG2);
-}
-// workspace (bytes) one C2C pass of length n over an [A][n][B] view needs
-template <typename T> static size_t pass_workspace(long A, long n, long B) {
-    if (fast_len<T>(n, B == 1) || n <= kSmallDft) return 0;
-    const int lm = next_pow2_log(2 * n - 1);
-    return (size_t)A * (1UL << lm) * B * sizeof(cplx<T>);
 }
 
 // one C2C pass along the middle axis of [A][n][B]; src may equal dst
@@ -614,27 +670,47 @@ static int c2c_pass(const cplx<T>* src, cplx<T>* dst, long A, long n, long B, in
         dft_small_kernel<T><<<(unsigned)((nseq + 127) / 128 > 4096 ? 4096 : (nseq + 127) / 128), 128, 0, st>>>(src, dst, (int)n, A, B, inverse ? 1 : 0, scale);
         return check_launch("dft_small_kernel");
     }
+    const size_t need = pass_workspace<T>(A, n, B);
+    if (!work || work_bytes < need) { set_error("fftn: workspace too small for length %ld (%zu < %zu)", n, work_bytes, need); return XRFTB_EWORKSPACE; }
+    cplx<T>* w = reinterpret_cast<cplx<T>*>(work);
+    const int l2 = ilog2_exact(n);
+    if (l2 > 0) {
+        // ---- four-step: n = n1 * n2, both within the single-pass limits
+        const long n1 = 1L << (l2 / 2), n2 = n / n1;
+        if (ilog2_exact(n2) > TypeCfg<T>::MAX_COLS_LOG2) { set_error("fftn: length %ld too long", n); return XRFTB_EUNSUPPORTED; }
+        const long total = A * n * B;
+        if (int rc = cols_c2c<T>(src, w, ilog2_exact(n1), A, n2 * B, inverse, (T)1, st)) return rc;              // FFT over i1
+        fourstep_twiddle_kernel<T><<<ew_grid(total), 256, 0, st>>>(w, n1, n2, B, inverse, total);
+        if (int rc = check_launch("fourstep_twiddle")) return rc;
+        if (int rc = (B == 1 ? rows_c2c<T>(w, w, ilog2_exact(n2), A * n1, n2, n2, inverse, (T)1, st)
+                             : cols_c2c<T>(w, w, ilog2_exact(n2), A * n1, B, inverse, (T)1, st))) return rc;       // FFT over i2
+        fourstep_transpose_kernel<T><<<ew_grid(total), 256, 0, st>>>(w, dst, n1, n2, B, scale, total);
+        return check_launch("fourstep_transpose");
+    }
+    // ---- Bluestein on top of the power-of-two machinery (recursive: M may itself need the four-step)
     const int lm = next_pow2_log(2 * n - 1);
     const long M = 1L << lm;
-    if (lm > (B == 1 ? TypeCfg<T>::MAX_ROWS_LOG2 : TypeCfg<T>::MAX_COLS_LOG2)) {
-        set_error("fftn: length %ld needs a %ld-point Bluestein convolution, beyond the single-pass limit (see DESIGN.md)", n, M);
-        return XRFTB_EUNSUPPORTED;
-    }
-    const size_t need = (size_t)A * M * B * sizeof(cplx<T>);
-    if (!work || work_bytes < need) { set_error("fftn: workspace too small for Bluestein (%zu < %zu)", work_bytes, need); return XRFTB_EWORKSPACE; }
+    if (lm > 26) { set_error("fftn: length %ld too long", n); return XRFTB_EUNSUPPORTED; }
+    const size_t mine = (((size_t)A * M * B * sizeof(cplx<T>)) + 256) & ~(size_t)255;
+    char* sub = reinterpret_cast<char*>(work) + mine;
+    const size_t sub_bytes = work_bytes - mine;
     const cplx<T>*chirp, *filt;
     if (int rc = get_chirp<T>(n, lm, &chirp, &filt, st)) return rc;
-    cplx<T>* w = reinterpret_cast<cplx<T>*>(work);
     const long tw_ = A * M * B;
     bluestein_pre_kernel<T, false><<<ew_grid(tw_), 256, 0, st>>>(src, w, chirp, A, n, M, B, inverse, tw_);
     if (int rc = check_launch("bluestein_pre")) return rc;
-    if (int rc = (B == 1 ? rows_c2c<T>(w, w, lm, A, M, M, 0, (T)1, st) : cols_c2c<T>(w, w, lm, A, B, 0, (T)1, st))) return rc;
+    if (int rc = c2c_pass<T>(w, w, A, M, B, 0, (T)1, sub, sub_bytes, st)) return rc;
     bluestein_mul_kernel<T><<<ew_grid(tw_), 256, 0, st>>>(w, filt, M, B, tw_);
     if (int rc = check_launch("bluestein_mul")) return rc;
-    if (int rc = (B == 1 ? rows_c2c<T>(w, w, lm, A, M, M, 1, (T)(1.0 / M), st) : cols_c2c<T>(w, w, lm, A, B, 1, (T)(1.0 / M), st))) return rc;
+    if (int rc = c2c_pass<T>(w, w, A, M, B, 1, (T)(1.0 / M), sub, sub_bytes, st)) return rc;
     const long to = A * n * B;
     bluestein_post_kernel<T, false><<<ew_grid(to), 256, 0, st>>>(w, dst, chirp, A, n, n, M, B, inverse, scale, to);
     return check_launch("bluestein_post");
+}
+
+template <typename T> static bool fast_real_len(long N) {
+    const int l2 = ilog2_exact(N);
+    return l2 >= 2 && l2 - 1 <= TypeCfg<T>::MAX_ROWS_LOG2;
 }
 
 template <typename T>
@@ -653,15 +729,13 @@ static size_t fftn_workspace_impl(int kind, int ndim, const int64_t* shape, int 
     size_t base = 0;
     if (real_kind) {
         long nseq = 1; for (int d = 0; d < ndim - 1; ++d) nseq *= shape[d];
-        const bool fast_real = ilog2_exact(N) >= 2 && ilog2_exact(N) - 1 <= TypeCfg<T>::MAX_ROWS_LOG2;
-        size_t last = 0;
-        if (!fast_real && N > kSmallDft) {
-            const int lm = next_pow2_log(2 * N - 1);
-            last = (size_t)nseq * (1UL << lm) * sizeof(cplx<T>);
-            if (kind == XRFTB_C2R) last += (size_t)nseq * N * sizeof(cplx<T>);  // Hermitian-extended copy
+        if (!fast_real_len<T>(N) && N > kSmallDft) {
+            // generic real path: full-length complex copy + whatever the complex pass needs
+            size_t last = (((size_t)nseq * N * sizeof(cplx<T>)) + 256) & ~(size_t)255;
+            last += pass_workspace<T>(nseq, N, 1);
+            if (last > need) need = last;
         }
-        if (kind == XRFTB_C2R && naxes > 1) base = (size_t)nseq * (N / 2 + 1) * sizeof(cplx<T>);  // private copy of the input
-        if (last > need) need = last;
+        if (kind == XRFTB_C2R && naxes > 1) base = (((size_t)nseq * (N / 2 + 1) * sizeof(cplx<T>)) + 256) & ~(size_t)255;  // private copy of the input
     }
     return base + need + 512;
 }
@@ -699,7 +773,9 @@ static int fftn_impl(const void* in, void* out, void* work, size_t work_bytes, i
     long nseq = 1;
     for (int d = 0; d < ndim - 1; ++d) nseq *= shape[d];
     const int l2 = ilog2_exact(N);
-    const bool fast_real = l2 >= 2 && l2 - 1 <= TypeCfg<T>::MAX_ROWS_LOG2;
+    const bool fast_real = fast_real_len<T>(N);
+    const unsigned small_grid = (unsigned)((nseq + 127) / 128 > 4096 ? 4096 : (nseq + 127) / 128);
+    if (N < 2) { set_error("real transforms need at least 2 points on the real axis"); return XRFTB_EINVAL; }
     if (kind == XRFTB_R2C) {
         C* dst = reinterpret_cast<C*>(out);
         if (fast_real) {
@@ -708,25 +784,17 @@ static int fftn_impl(const void* in, void* out, void* work, size_t work_bytes, i
             io.wy = nullptr; io.wx = nullptr; io.out = dst; io.logC = -1; io.out_seq_stride = H;
             if (int rc = rows_r2c<T>(io, l2 - 1, nseq, st)) return rc;
         } else if (N <= kSmallDft) {
-            if (N < 2) { set_error("rfftn: real axis must have at least 2 points"); return XRFTB_EINVAL; }
-            dft_small_kernel<T><<<(unsigned)((nseq + 127) / 128 > 4096 ? 4096 : (nseq + 127) / 128), 128, 0, st>>>(in, dst, (int)N, nseq, 1, 2, (T)1);
+            dft_small_kernel<T><<<small_grid, 128, 0, st>>>(in, dst, (int)N, nseq, 1, 2, (T)1);
             if (int rc = check_launch("dft_small_kernel")) return rc;
         } else {
-            const int lm = next_pow2_log(2 * N - 1);
-            const long M = 1L << lm;
-            if (lm > TypeCfg<T>::MAX_ROWS_LOG2) { set_error("rfftn: length %ld beyond the single-pass Bluestein limit", N); return XRFTB_EUNSUPPORTED; }
-            const size_t need = (size_t)nseq * M * sizeof(C);
-            if (wleft < need) { set_error("rfftn: workspace too small (%zu < %zu)", wleft, need); return XRFTB_EWORKSPACE; }
-            const C*chirp, *filt;
-            if (int rc = get_chirp<T>(N, lm, &chirp, &filt, st)) return rc;
-            C* w = reinterpret_cast<C*>(wbase);
-            const long tw_ = nseq * M;
-            bluestein_pre_kernel<T, true><<<ew_grid(tw_), 256, 0, st>>>(in, w, chirp, nseq, N, M, 1, 0, tw_);
-            if (int rc = rows_c2c<T>(w, w, lm, nseq, M, M, 0, (T)1, st)) return rc;
-            bluestein_mul_kernel<T><<<ew_grid(tw_), 256, 0, st>>>(w, filt, M, 1, tw_);
-            if (int rc = rows_c2c<T>(w, w, lm, nseq, M, M, 1, (T)(1.0 / M), st)) return rc;
-            bluestein_post_kernel<T, false><<<ew_grid(nseq * H), 256, 0, st>>>(w, dst, chirp, nseq, N, H, M, 1, 0, (T)1, nseq * H);
-            if (int rc = check_launch("bluestein r2c")) return rc;
+            // promote to complex, full-length complex pass (four-step / Bluestein), keep k <= N/2
+            const size_t cb = (((size_t)nseq * N * sizeof(C)) + 256) & ~(size_t)255;
+            if (wleft < cb) { set_error("rfftn: workspace too small (%zu < %zu)", wleft, cb); return XRFTB_EWORKSPACE; }
+            C* full = reinterpret_cast<C*>(wbase);
+            real_to_cplx_kernel<T><<<ew_grid(nseq * N), 256, 0, st>>>(reinterpret_cast<const T*>(in), full, nseq * N);
+            if (int rc = c2c_pass<T>(full, full, nseq, N, 1, 0, (T)1, wbase + cb, wleft - cb, st)) return rc;
+            crop_kernel<T, false><<<ew_grid(nseq * H), 256, 0, st>>>(full, dst, N, H, nseq * H);
+            if (int rc = check_launch("crop_kernel")) return rc;
         }
         for (int i = 0; i < naxes - 1; ++i) {
             long A, B; view(axes[i], A, B);
@@ -737,11 +805,11 @@ static int fftn_impl(const void* in, void* out, void* work, size_t work_bytes, i
     // ---- C2R
     const C* src = reinterpret_cast<const C*>(in);
     if (naxes > 1) {
-        const size_t copy_bytes = (size_t)nseq * H * sizeof(C);
+        const size_t copy_bytes = (((size_t)nseq * H * sizeof(C)) + 256) & ~(size_t)255;
         if (wleft < copy_bytes) { set_error("irfftn: workspace too small"); return XRFTB_EWORKSPACE; }
         C* w = reinterpret_cast<C*>(wbase);
-        wbase += (copy_bytes + 255) & ~(size_t)255;
-        wleft = wleft > ((copy_bytes + 255) & ~(size_t)255) ? wleft - ((copy_bytes + 255) & ~(size_t)255) : 0;
+        wbase += copy_bytes;
+        wleft -= copy_bytes;
         for (int i = 0; i < naxes - 1; ++i) {
             long A, B; view(axes[i], A, B);
             if (int rc = c2c_pass<T>(src, w, A, cshape[axes[i]], B, 1, (T)1, wbase, wleft, st)) return rc;
@@ -750,27 +818,17 @@ static int fftn_impl(const void* in, void* out, void* work, size_t work_bytes, i
     }
     if (fast_real) return rows_c2r<T>(src, H, reinterpret_cast<T*>(out), N, l2 - 1, nseq, inv_scale * (T)2, st);  // half-length inverse: 1/M = 2/N
     if (N <= kSmallDft) {
-        dft_small_kernel<T><<<(unsigned)((nseq + 127) / 128 > 4096 ? 4096 : (nseq + 127) / 128), 128, 0, st>>>(src, out, (int)N, nseq, 1, 3, inv_scale);
+        dft_small_kernel<T><<<small_grid, 128, 0, st>>>(src, out, (int)N, nseq, 1, 3, inv_scale);
         return check_launch("dft_small_kernel");
     }
     {
-        const int lm = next_pow2_log(2 * N - 1);
-        const long M = 1L << lm;
-        if (lm > TypeCfg<T>::MAX_ROWS_LOG2) { set_error("irfftn: length %ld beyond the single-pass Bluestein limit", N); return XRFTB_EUNSUPPORTED; }
-        const size_t need = (size_t)nseq * (M + N) * sizeof(C);
-        if (wleft < need) { set_error("irfftn: workspace too small (%zu < %zu)", wleft, need); return XRFTB_EWORKSPACE; }
-        const C*chirp, *filt;
-        if (int rc = get_chirp<T>(N, lm, &chirp, &filt, st)) return rc;
+        const size_t cb = (((size_t)nseq * N * sizeof(C)) + 256) & ~(size_t)255;
+        if (wleft < cb) { set_error("irfftn: workspace too small (%zu < %zu)", wleft, cb); return XRFTB_EWORKSPACE; }
         C* ext = reinterpret_cast<C*>(wbase);
-        C* w = ext + nseq * N;
         herm_extend_kernel<T><<<ew_grid(nseq * N), 256, 0, st>>>(src, ext, N, 1, nseq * N);
-        const long tw_ = nseq * M;
-        bluestein_pre_kernel<T, false><<<ew_grid(tw_), 256, 0, st>>>(ext, w, chirp, nseq, N, M, 1, 1, tw_);
-        if (int rc = rows_c2c<T>(w, w, lm, nseq, M, M, 0, (T)1, st)) return rc;
-        bluestein_mul_kernel<T><<<ew_grid(tw_), 256, 0, st>>>(w, filt, M, 1, tw_);
-        if (int rc = rows_c2c<T>(w, w, lm, nseq, M, M, 1, (T)(1.0 / M), st)) return rc;
-        bluestein_post_kernel<T, true><<<ew_grid(nseq * N), 256, 0, st>>>(w, out, chirp, nseq, N, N, M, 1, 1, inv_scale, nseq * N);
-        return check_launch("bluestein c2r");
+        if (int rc = c2c_pass<T>(ext, ext, nseq, N, 1, 1, inv_scale, wbase + cb, wleft - cb, st)) return rc;
+        crop_kernel<T, true><<<ew_grid(nseq * N), 256, 0, st>>>(ext, out, N, N, nseq * N);
+        return check_launch("crop_kernel");
     }
 }
 
