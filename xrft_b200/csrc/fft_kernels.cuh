@@ -283,6 +283,142 @@ template <typename T> struct RowsR2CFused {
     }
 };
 
+// ---- fused real-input row pass, TWO rows per thread (the hot 2-D path) ------------------------------------
+// Same math as rows_kernel<RowsR2CFused> in blocked mode; each thread owns the same 16 points of two adjacent
+// rows, interleaved in shared memory ([pad(o)][2]) so every exchange access is one 128-bit LDS/STS for both
+// rows and the stage twiddles are generated once per pair.  Needs Ny % (2*PAIRS) == 0 (rows of a CTA group are
+// consecutive rows of one item).
+template <typename T, int LOG2L, int LOGE, int PAIRS>
+__global__ void __launch_bounds__((1 << (LOG2L - LOGE)) * PAIRS, min_blocks_for((1 << (LOG2L - LOGE)) * PAIRS))
+rows2_kernel(RowsR2CFused<T> io, const cplx<T>* __restrict__ tw, long nseq) {
+    using G_ = Geometry<LOG2L, LOGE>;
+    constexpr int E = G_::E, NT = G_::NT, SEQ = 2 * PAIRS, NTHR = NT * PAIRS, M = G_::L, Nx = 2 * M;
+    constexpr int PAIR_STRIDE = 2 * G_::LPAD + 8;
+    constexpr int R = 1 << G_::LOGR_LAST, G = E / R, PADW = 1 << G_::LOGPAD, LOGSEQ = ilog2c(SEQ);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx<T>* smem = reinterpret_cast<cplx<T>*>(smem_raw);
+    const int pr = threadIdx.x / NT, u = threadIdx.x % NT;
+    cplx<T>* sm = smem + pr * PAIR_STRIDE;
+    const long ngroups = nseq / SEQ;
+    const int Ny = 1 << io.logNy;
+    const int logC = io.logC, C = 1 << logC;
+    const int ntile = (M >> logC) + 1;
+    // two CTAs per SM interleave their load / transform / store phases; the next group is L2-prefetched
+    for (long grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+        const long nxt = grp + gridDim.x;
+        if (threadIdx.x == 0 && nxt < ngroups) io.template prefetch<LOG2L, SEQ>(nxt * SEQ, nseq);
+        cplx<T> v[2][E];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const cplx<T>* p = reinterpret_cast<const cplx<T>*>(io.in + (grp * SEQ + 2 * pr + r) * io.in_row_stride) + u;
+#pragma unroll
+            for (int q = 0; q < E; ++q) v[r][q] = p[q * NT];
+        }
+        // ---- prologue: fp64 plane subtract, window
+        {
+            const long seq0 = grp * SEQ + 2 * pr;
+            const long b = seq0 >> io.logNy;
+            const int iy0 = (int)(seq0 & (Ny - 1));
+            double pm = 0.0, cx = 0.0, cy = 0.0;
+            if (io.detrend) {
+                const double* m = io.moments + b * 4;
+                const double npts = (double)Ny * (double)Nx;
+                pm = m[0] / npts;
+                if (io.detrend == 2) {
+                    const double vy = (double)Nx * ((double)Ny * ((double)Ny * Ny - 1.0) / 12.0);
+                    const double vx = (double)Ny * ((double)Nx * ((double)Nx * Nx - 1.0) / 12.0);
+                    cy = Ny > 1 ? m[2] / vy : 0.0;
+                    cx = m[3] / vx;
+                    pm += cx * ((double)(2 * u) - 0.5 * (Nx - 1));
+                }
+            }
+            const double pstep = cx * (double)(2 * NT);
+            const cplx<T>* pw = reinterpret_cast<const cplx<T>*>(io.wx) + u;
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const double p0 = pm + cy * ((double)(iy0 + r) - 0.5 * (Ny - 1));
+                const T wrow = io.wy != nullptr ? io.wy[iy0 + r] : (T)1;
+#pragma unroll
+                for (int q = 0; q < E; ++q) {
+                    cplx<T> y = v[r][q];
+                    if (io.detrend) {
+                        const double pq = p0 + (double)q * pstep;
+                        y.x = (T)((double)y.x - pq);
+                        y.y = (T)((double)y.y - (pq + cx));
+                    }
+                    if (io.wx != nullptr) {
+                        cplx<T> w = __ldg(pw + q * NT);
+                        y.x *= w.x * wrow; y.y *= w.y * wrow;
+                    } else {
+                        y.x *= wrow; y.y *= wrow;
+                    }
+                    v[r][q] = y;
+                }
+            }
+        }
+        block_fft<T, LOG2L, LOGE, 2, 2>(v, u, sm, 1, tw);
+        // ---- store_a: both rows' packed spectra Z -> smem (natural order, interleaved)
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+#pragma unroll
+            for (int t = 0; t < R; ++t) {
+                cplx<T>* p = sm + padded<G_::LOGPAD>(final_index<LOG2L, LOGE>(u, g, t)) * 2;
+                p[0] = v[0][g + t * G];
+                p[1] = v[1][g + t * G];
+            }
+        __syncthreads();
+        // ---- store_b: R2C split + blocked store; thread -> (tile t, row s2, column c), c fastest
+        {
+            const int tstep = NTHR >> (logC + LOGSEQ);
+            const int c = threadIdx.x & (C - 1);
+            const int s2 = (threadIdx.x >> logC) & (SEQ - 1);
+            const long seq2 = grp * SEQ + s2;
+            const long b = seq2 >> io.logNy;
+            const int iy = (int)(seq2 & (Ny - 1));
+            const cplx<T>* smr = smem + (s2 >> 1) * PAIR_STRIDE + (s2 & 1);
+            if (tstep >= 1 && ((tstep << logC) % PADW) == 0 && M % (tstep << logC) == 0) {
+                const int KS = tstep << logC, KSP2 = 2 * (KS + KS / PADW);
+                const int t0 = threadIdx.x >> (logC + LOGSEQ);
+                const int k0 = (t0 << logC) + c;
+                const long ostep = ((long)Ny << logC) * tstep;
+                cplx<T>* po = io.out + (((b * ntile + t0) << io.logNy) + iy) * C + c;
+                const cplx<T>* pk = smr + 2 * padded<G_::LOGPAD>(k0);
+                const cplx<T>* pmr = smr + 2 * padded<G_::LOGPAD>((M - k0) & (M - 1));
+                const cplx<T>* ptw = io.tw_r2c + k0;
+                const int nsweep = M / KS;
+                *po = r2c_split<T>(*pk, *pmr, __ldg(ptw));
+                pmr = smr + 2 * padded<G_::LOGPAD>(M - k0 - KS > 0 ? M - k0 - KS : 0);
+                pk += KSP2; ptw += KS; po += ostep;
+#pragma unroll 4
+                for (int i = 1; i < nsweep; ++i) {
+                    *po = r2c_split<T>(*pk, *pmr, __ldg(ptw));
+                    pk += KSP2; pmr -= KSP2; ptw += KS; po += ostep;
+                }
+                if (t0 == 0) {
+                    cplx<T> z0 = smr[0];
+                    cplx<T>* pl = io.out + (((b * ntile + (M >> logC)) << io.logNy) + iy) * C + c;
+                    *pl = (c == 0) ? mk<T>(z0.x - z0.y, 0) : mk<T>(0, 0);
+                }
+            } else {
+                for (int w = threadIdx.x; w < ntile * SEQ * C; w += NTHR) {
+                    const int c2 = w & (C - 1);
+                    const int s3 = (w >> logC) & (SEQ - 1);
+                    const int t = w >> (logC + LOGSEQ);
+                    const long seq3 = grp * SEQ + s3;
+                    const long b3 = seq3 >> io.logNy;
+                    const int iy3 = (int)(seq3 & (Ny - 1));
+                    const int k = (t << logC) + c2;
+                    const cplx<T>* sr = smem + (s3 >> 1) * PAIR_STRIDE + (s3 & 1);
+                    cplx<T> r = mk<T>(0, 0);
+                    if (k <= M) r = r2c_split<T>(sr[2 * padded<G_::LOGPAD>(k & (M - 1))], sr[2 * padded<G_::LOGPAD>((M - k) & (M - 1))], __ldg(io.tw_r2c + k));
+                    io.out[(((b3 * ntile + t) << io.logNy) + iy3) * C + c2] = r;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // ---- C2R: half spectrum [seq][M+1] -> real [seq][N], numpy irfft semantics (scale = 2/N folded in) --
 //   Z[k] = E + i O,  E = (X[k] + conj X[M-k]) / 2,  O = w_N^{-k} (X[k] - conj X[M-k]) / 2
 //   z = IFFT_M(Z) = conj(FFT(conj Z)) ;  x[2n] = Re z[n], x[2n+1] = Im z[n]

@@ -28,6 +28,21 @@ template <typename T>
 int rows_r2c(RowsR2CFused<T> io, int log2M, long nseq, cudaStream_t st) {
     io.tw_r2c = twiddle_r2c<T>(log2M + 1);
     if (!io.tw_r2c) return -3;
+    // hot 2-D path: two rows per thread (float32, blocked output, enough rows per item)
+    static int v2 = -1;
+    if (v2 < 0) { const char* e = getenv("XRFTB_ROWS_V2"); v2 = e ? atoi(e) : 1; }
+    if constexpr (sizeof(T) == 4) {
+        if (v2 > 0 && io.logC >= 0 && io.logNy >= 2 && io.in_row_stride == (2L << log2M) && nseq % 4 == 0) {
+            switch (log2M) {
+                case 8: return launch_rows2<T, 8, 2>(io, nseq, st);
+                case 9: return launch_rows2<T, 9, 2>(io, nseq, st);
+                case 10: return launch_rows2<T, 10, 2>(io, nseq, st);
+                case 11: return launch_rows2<T, 11, 2>(io, nseq, st);
+                case 12: return launch_rows2<T, 12, 2>(io, nseq, st);
+                default: break;
+            }
+        }
+    }
     // tuning knob (experiments): rows per CTA of the fused pass for the large sizes
     static int seq_override = -1;
     if (seq_override < 0) { const char* e = getenv("XRFTB_ROWS_SEQ"); seq_override = e ? atoi(e) : 0; }
