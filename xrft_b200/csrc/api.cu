@@ -3,6 +3,7 @@
 // See include/xrft_b200.h for the reference seams each entry point replaces.
 #include <atomic>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdio>
 #include <cmath>
 #include <map>
@@ -10,6 +11,7 @@
 #include <vector>
 #include "../../include/xrft_b200.h"
 #include "internal.h"
+#include <cudaTypedefs.h>
 
 namespace xrftb {
 
@@ -188,6 +190,45 @@ __global__ void __launch_bounds__(512) moments_kernel(const T* __restrict__ in, 
         double x = 0;
         for (int w = 0; w < (int)(blockDim.x >> 5); ++w) x += red[threadIdx.x][w];
         atomicAdd(mom + b * 4 + threadIdx.x, x);
+    }
+}
+
+// light variant for the side stream: one 128-thread CTA per SM at <= 32 registers so it fits beside the hot FFT
+// kernels (which leave 4 K registers per SM free); float32 rows whose length is a power of two >= 4
+__global__ void __maxnreg__(32) moments_side_kernel(const float* __restrict__ in, double* __restrict__ mom, int log_n4, int log_ny, long nitems) {
+    const long per_item4 = 1L << (log_n4 + log_ny);
+    const long n4 = 1L << log_n4, ny = 1L << log_ny;
+    const double c1m = 0.5 * (double)(ny - 1), c2m = 0.5 * (double)(4 * n4 - 1);
+    const float4* p4 = reinterpret_cast<const float4*>(in);
+    // CTA -> (item, slab of the item); slabs = gridDim.x / nitems rounded down to >= 1
+    const long slabs = gridDim.x >= nitems ? gridDim.x / nitems : 1;
+    for (long w = blockIdx.x; w < nitems * slabs; w += gridDim.x) {
+        const long b = w / slabs, sl = w - b * slabs;
+        const long lo = per_item4 * sl / slabs, hi = per_item4 * (sl + 1) / slabs;
+        double S = 0, Sy = 0, Sx = 0;
+        for (long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+            const float4 x = __ldg(p4 + b * per_item4 + i);
+            const long r = i >> log_n4, c4 = i & (n4 - 1);
+            const float c = (float)((double)(4 * c4) - c2m);
+            const double s4 = (double)((x.x + x.y) + (x.z + x.w));
+            S += s4;
+            Sy += ((double)r - c1m) * s4;
+            Sx += (double)((c * x.x + (c + 1.f) * x.y) + ((c + 2.f) * x.z + (c + 3.f) * x.w));
+        }
+        __shared__ double red[3][4];
+        double vals[3] = {S, Sy, Sx};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            double x = vals[k];
+            for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+            if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = x;
+        }
+        __syncthreads();
+        if (threadIdx.x < 3) {
+            double x = red[threadIdx.x][0] + red[threadIdx.x][1] + red[threadIdx.x][2] + red[threadIdx.x][3];
+            atomicAdd(mom + b * 4 + (threadIdx.x == 0 ? 0 : threadIdx.x + 1), x);   // {S, -, Sy, Sx}
+        }
+        __syncthreads();
     }
 }
 
@@ -835,6 +876,26 @@ static int fftn_impl(const void* in, void* out, void* work, size_t work_bytes, i
 // ------------------------------------------------------------------------------------------------
 // fused 2-D real spectrum
 // ------------------------------------------------------------------------------------------------
+// TMA descriptor of the POWER output viewed as [rows][W] float32, box = [box_rows][box_cols]
+static bool encode_out_tmap(CUtensorMap* tm, void* base, long rows, long W, int box_cols, int box_rows) {
+    static PFN_cuTensorMapEncodeTiled_v12000 enc = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+            enc = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+    }
+    if (!enc) return false;
+    cuuint64_t gdim[2] = {(cuuint64_t)W, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)W * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <typename T> static size_t interm_bytes_per_item(int ny, int nx, int C) {
     const long ntile = (nx / 2) / C + 1;
     return (size_t)ntile * ny * C * sizeof(cplx<T>);
@@ -864,17 +925,43 @@ static int spectrum2d_impl(const xrftb_spectrum2d_desc& q, cudaStream_t st) {
     const long item = (long)q.ny * q.nx;
     const T* ins[2] = {reinterpret_cast<const T*>(q.in1), reinterpret_cast<const T*>(q.in2)};
 
+    // Moments of chunk c+1 run on a side stream while the row/column passes of chunk c run on the caller's stream:
+    // the reduce is bandwidth-bound, the FFT passes are issue-bound, and the hot kernels leave room for one light CTA/SM.
+    static int side_on = -1;
+    if (side_on < 0) { const char* e = getenv("XRFTB_SIDE_MOMENTS"); side_on = e ? atoi(e) : 0; }  // measured slower: off by default
+    const long nchunks = (q.batch + bchunk - 1) / bchunk;
+    const bool side = side_on && q.detrend && std::is_same<T, float>::value && nchunks > 1 && lx >= 2 && fields == 1;
+    static thread_local cudaStream_t s_side = nullptr;
+    std::vector<cudaEvent_t> ev_mom;
+    auto launch_moments = [&](const T* base, double* m, long nitems, cudaStream_t stream, bool light) -> int {
+        ProfScope ps_(PROF_MOMENTS, stream);
+        if (light) {
+            if constexpr (std::is_same<T, float>::value)
+                moments_side_kernel<<<sm_count(), 128, 0, stream>>>(base, m, lx - 2, ly, nitems);
+        } else {
+            int chunks = (int)((8L * sm_count() + nitems - 1) / nitems);
+            if (chunks < 1) chunks = 1;
+            if (chunks > q.ny) chunks = q.ny;
+            dim3 grid(chunks, (unsigned)nitems);
+            moments_kernel<T><<<grid, 256, 0, st>>>(base, m, 1, q.ny, q.nx, chunks);
+        }
+        return check_launch("moments_kernel");
+    };
     if (q.detrend) {
         cudaError_t e = cudaMemsetAsync(mom, 0, mom_bytes, st);
         if (e != cudaSuccess) { set_error("memset: %s", cudaGetErrorString(e)); return XRFTB_ECUDA; }
-        for (int f = 0; f < fields; ++f) {
-            int chunks = (int)((8L * sm_count() + q.batch - 1) / q.batch);
-            if (chunks < 1) chunks = 1;
-            if (chunks > q.ny) chunks = q.ny;
-            dim3 grid(chunks, (unsigned)q.batch);
-            ProfScope ps_(PROF_MOMENTS, st);
-            moments_kernel<T><<<grid, 256, 0, st>>>(ins[f], mom + (size_t)f * q.batch * 4, 1, q.ny, q.nx, chunks);
-            if (int rc = check_launch("moments_kernel")) return rc;
+        if (!side) {
+            for (int f = 0; f < fields; ++f)
+                if (int rc = launch_moments(ins[f], mom + (size_t)f * q.batch * 4, q.batch, st, false)) return rc;
+        } else {
+            if (!s_side) cudaStreamCreateWithFlags(&s_side, cudaStreamNonBlocking);
+            ev_mom.resize(nchunks);
+            for (auto& ev : ev_mom) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+            // chunk 0 on the caller's stream (nothing to overlap with yet); the side stream starts after the memset
+            const long nb0 = q.batch < bchunk ? q.batch : bchunk;
+            if (int rc = launch_moments(ins[0], mom, nb0, st, false)) return rc;
+            cudaEventRecord(ev_mom[0], st);
+            cudaStreamWaitEvent(s_side, ev_mom[0], 0);
         }
     }
     EpilogueDesc d{};
@@ -886,6 +973,8 @@ static int spectrum2d_impl(const xrftb_spectrum2d_desc& q, cudaStream_t st) {
     const size_t out_elem = (q.mode == XRFTB_EPI_COMPLEX || q.mode == XRFTB_EPI_CROSS) ? sizeof(C_) : sizeof(T);
     for (long b0 = 0; b0 < q.batch; b0 += bchunk) {
         const long nb = (q.batch - b0 < bchunk) ? q.batch - b0 : bchunk;
+        const long ci = b0 / bchunk;
+        if (side && ci > 0) cudaStreamWaitEvent(st, ev_mom[ci], 0);
         for (int f = 0; f < fields; ++f) {
             RowsR2CFused<T> io{};
             io.in = ins[f] + b0 * item; io.in_row_stride = q.nx; io.logNy = ly; io.detrend = q.detrend;
@@ -895,12 +984,28 @@ static int spectrum2d_impl(const xrftb_spectrum2d_desc& q, cudaStream_t st) {
             ProfScope ps_(PROF_ROWS, st);
             if (int rc = rows_r2c<T>(io, lx - 1, nb * q.ny, st)) return rc;
         }
+        if (side && ci + 1 < nchunks) {
+            const long b1 = b0 + bchunk;
+            const long nb1 = (q.batch - b1 < bchunk) ? q.batch - b1 : bchunk;
+            if (int rc = launch_moments(ins[0] + b1 * item, mom + b1 * 4, nb1, s_side, true)) return rc;
+            cudaEventRecord(ev_mom[ci + 1], s_side);
+        }
         d.out = bins_mode ? nullptr : reinterpret_cast<char*>(q.out) + (size_t)b0 * q.ny * W * out_elem;
         d.bins = bins_mode ? q.bins + (size_t)b0 * q.nbins * (q.mode == XRFTB_EPI_BINS_CROSS ? 2 : 1) : nullptr;
         const C_* i1 = interm;
         const C_* i2 = two ? interm + (size_t)bchunk * (per_item / sizeof(C_)) : nullptr;
+        CUtensorMap tmap;
+        const CUtensorMap* ptm = nullptr;
+        d.use_tma = 0;
+        static int tma_on = -1;
+        if (tma_on < 0) { const char* e = getenv("XRFTB_TMA_STORE"); tma_on = e ? atoi(e) : 1; }
+        if (tma_on && q.mode == XRFTB_EPI_POWER && std::is_same<T, float>::value && C >= 8 /* >= 32-byte rows: 16-byte boxes measured slower than LSU stores */ && (mirror_pass || q.keep_half) && !q.weight_x
+            && (W * sizeof(float)) % 16 == 0 && q.ny >= 4) {
+            const int box_rows = q.ny / 2 < 256 ? q.ny / 2 : 256;
+            if (encode_out_tmap(&tmap, d.out, nb * q.ny, W, C, box_rows)) { d.use_tma = 1; d.tma_box_rows = box_rows; ptm = &tmap; }
+        }
         { ProfScope ps_(PROF_COLS, st);
-        if (int rc = cols_fused<T>(q.mode, i1, i2, ly, nb * ntile, (int)ntile, d, st)) return rc; }
+        if (int rc = cols_fused<T>(q.mode, i1, i2, ly, nb * ntile, (int)ntile, d, ptm, st)) return rc; }
         if (mirror_pass) {
             ProfScope ps_(PROF_MIRROR, st);
             const long nrows = nb * q.ny;
@@ -912,6 +1017,7 @@ static int spectrum2d_impl(const xrftb_spectrum2d_desc& q, cudaStream_t st) {
             if (int rc = check_launch("mirror_fill_kernel")) return rc;
         }
     }
+    for (auto& ev : ev_mom) cudaEventDestroy(ev);
     return 0;
 }
 

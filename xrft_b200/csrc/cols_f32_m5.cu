@@ -1,4 +1,4 @@
 #include "cols_impl.cuh"
 namespace xrftb {
-template int cols_fused_mode<float, EPI_BINS_CROSS>(const float2*, const float2*, int, long, int, const EpilogueDesc&, cudaStream_t);
+template int cols_fused_mode<float, EPI_BINS_CROSS>(const float2*, const float2*, int, long, int, const EpilogueDesc&, const CUtensorMap*, cudaStream_t);
 }

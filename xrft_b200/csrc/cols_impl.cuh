@@ -30,14 +30,15 @@ int cols_c2c(const cplx<T>* in, cplx<T>* out, int log2L, long A, long B, int inv
 }
 
 template <typename T, int K, int MODE>
-static int cols_fused_k(const cplx<T>* in1, const cplx<T>* in2, long ntiles_total, int ntile, const EpilogueDesc& d, cudaStream_t st) {
+static int cols_fused_k(const cplx<T>* in1, const cplx<T>* in2, long ntiles_total, int ntile, const EpilogueDesc& d, const CUtensorMap* tmap, cudaStream_t st) {
     using IO = ColsFused<T, MODE>;
     constexpr int C = TileC<T, K, IO::kTwoFields>::value;
     if constexpr (C < 1) {
         set_error("cols_fused: length 2^%d too long for %d field(s)", K, IO::kTwoFields ? 2 : 1);
         return -2;
     } else {
-        IO io{in1, in2, ntile, d};
+        IO io{in1, in2, ntile, d, {}};
+        if (tmap) io.tmap = *tmap;
         const size_t extra = IO::kBins ? (size_t)d.nbins * (IO::kCplxStage ? 2 : 1) * sizeof(double) : 0;
         return launch_cols<T, K, C>(io, ntiles_total, st, extra);
     }
@@ -45,9 +46,9 @@ static int cols_fused_k(const cplx<T>* in1, const cplx<T>* in2, long ntiles_tota
 
 template <typename T, int MODE>
 int cols_fused_mode(const cplx<T>* in1, const cplx<T>* in2, int log2L, long ntiles_total, int ntile, const EpilogueDesc& d,
-                    cudaStream_t st) {
+                    const CUtensorMap* tmap, cudaStream_t st) {
     switch (log2L) {
-#define X(K) case K: return cols_fused_k<T, K, MODE>(in1, in2, ntiles_total, ntile, d, st);
+#define X(K) case K: return cols_fused_k<T, K, MODE>(in1, in2, ntiles_total, ntile, d, tmap, st);
         XRFTB_COLS_CASES(X)
 #undef X
         default: break;

@@ -12,6 +12,7 @@
 //   |F|^2, F conj(G), angle, psd scalings     xrft/xrft.py:740-748, 825-833, 865-869
 //   radial-bin sum                            xrft/xrft.py:895-906
 #pragma once
+#include <cuda.h>
 #include "fft_core.cuh"
 
 namespace xrftb {
@@ -474,7 +475,7 @@ template <typename T> struct RowsC2R {
 // =============================================================================================
 template <typename T, int LOG2L, int LOGE, int C, int V, class IO>
 __global__ void __launch_bounds__((1 << (LOG2L - LOGE)) * (C / V), min_blocks_for((1 << (LOG2L - LOGE)) * (C / V)))
-cols_kernel(IO io, const cplx<T>* __restrict__ tw, long ntiles) {
+cols_kernel(const __grid_constant__ IO io, const cplx<T>* __restrict__ tw, long ntiles) {
     using G_ = Geometry<LOG2L, LOGE>;
     constexpr int E = G_::E, CG = C / V;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -489,6 +490,7 @@ cols_kernel(IO io, const cplx<T>* __restrict__ tw, long ntiles) {
     for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long nxt = tile + gridDim.x;
         if (threadIdx.x == 0 && nxt + gridDim.x < ntiles) io.template prefetch<LOG2L, C>(nxt + gridDim.x);
+        io.tma_reads_done();  // staging buffer (aliases the exchange buffer) may be overwritten from here on
         block_fft<T, LOG2L, LOGE, V, C>(v, u, sm, 1, tw);
         if constexpr (IO::kTwoFields) {
             // park field-1 spectrum in thread-private smem slots, transform field 2, then combine
@@ -507,6 +509,7 @@ cols_kernel(IO io, const cplx<T>* __restrict__ tw, long ntiles) {
         if (nxt < ntiles) io.template load<LOG2L, LOGE, C, V>(nxt, u, cg, v, 0);
         io.template store_b<LOG2L, LOGE, C, V>(tile, smem);
     }
+    io.tma_drain();
 }
 
 // ---- plain strided C2C on a [A][L][B] row-major view (in-place safe) ---------------------------
@@ -517,6 +520,8 @@ template <typename T> struct ColsC2C {
 
     template <int LOG2L, int C> __device__ __forceinline__ void prefetch(long) const {}
     template <int LOG2L, int LOGE, int C, int V> __device__ __forceinline__ void init(cplx<T>*) const {}
+    __device__ __forceinline__ void tma_reads_done() const {}
+    __device__ __forceinline__ void tma_drain() const {}
 
     template <int LOG2L, int LOGE, int C, int V>
     __device__ __forceinline__ void load(long tile, int u, int cg, cplx<T> (&v)[V][1 << LOGE], int) const {
@@ -580,6 +585,8 @@ struct EpilogueDesc {
     const int* lut;        // bins: int32 [Ny][W] bin of each OUTPUT cell (negative = skip)
     double* bins;          // [batch][nbins] (power) or [batch][nbins][2] (cross)
     int nbins;
+    int use_tma;           // POWER: write the direct cells with TMA tensor stores (tmap describes out as [rows][W] float)
+    int tma_box_rows;      // rows per TMA box (<= 256, divides Ny/2 so a box never straddles the fftshift wrap)
     int lut_symmetric;     // bins: lut[-ky][-kx] == lut[ky][kx] for every cell (true for radial bins): mirror cells reuse the bin
 };
 
@@ -601,6 +608,7 @@ template <typename T, int MODE> struct ColsFused {
     // inside the fp32 tolerance); the cross-tile / cross-item accumulation in global memory is fp64
     using HistT = T;
     const cplx<T>* in1; const cplx<T>* in2; int ntile; EpilogueDesc d;
+    alignas(64) CUtensorMap tmap;  // only read when d.use_tma
 
     template <int LOG2L, int LOGE, int C, int V> static constexpr int hist_offset_bytes() {
         using G_ = Geometry<LOG2L, LOGE>;
@@ -611,6 +619,20 @@ template <typename T, int MODE> struct ColsFused {
             HistT* hist = reinterpret_cast<HistT*>(reinterpret_cast<char*>(smem) + hist_offset_bytes<LOG2L, LOGE, C, V>());
             for (int i = threadIdx.x; i < d.nbins * (kCplxStage ? 2 : 1); i += blockDim.x) hist[i] = 0;
             __syncthreads();
+        }
+    }
+
+    __device__ __forceinline__ void tma_reads_done() const {
+        if constexpr (MODE == EPI_POWER) {
+            if (d.use_tma) {
+                if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncthreads();
+            }
+        }
+    }
+    __device__ __forceinline__ void tma_drain() const {
+        if constexpr (MODE == EPI_POWER) {
+            if (d.use_tma && threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         }
     }
 
@@ -665,6 +687,9 @@ template <typename T, int MODE> struct ColsFused {
                     stage[ky * C + cg * V + vv] = val;
                 }
             }
+        if constexpr (MODE == EPI_POWER) {
+            if (d.use_tma) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy (TMA) reads
+        }
         __syncthreads();
     }
 
@@ -673,6 +698,29 @@ template <typename T, int MODE> struct ColsFused {
         using G_ = Geometry<LOG2L, LOGE>;
         constexpr int Ny = 1 << LOG2L, NTHR = G_::NT * (C / V);
         StageT* stage = reinterpret_cast<StageT*>(smem);
+        if constexpr (MODE == EPI_POWER && sizeof(T) == 4) {
+            if (d.use_tma) {
+                // ---- 2'. TMA tensor stores: box = [box_rows][C] floats (16 B rows), one elected thread, asynchronous;
+                //          the LSU never sees the 16-byte scattered row segments
+                if (threadIdx.x == 0) {
+                    const int Nx_ = 1 << d.logNx;
+                    const long b_ = tile / ntile;
+                    const int kx0_ = (int)(tile - b_ * ntile) * C;
+                    const int sy_ = d.shift_y ? Ny / 2 : 0, sx_ = d.shift_x ? Nx_ / 2 : 0;
+                    const int ox0_ = (kx0_ + sx_) & (Nx_ - 1);
+                    const int br = d.tma_box_rows;
+                    const unsigned sbase = (unsigned)__cvta_generic_to_shared(stage);
+                    for (int ky0 = 0; ky0 < Ny; ky0 += br) {
+                        const int oy0 = (ky0 + sy_) & (Ny - 1);
+                        const int row = (int)(b_ * Ny) + oy0;
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                                     :: "l"(&tmap), "r"(ox0_), "r"(row), "r"(sbase + (unsigned)(ky0 * C * sizeof(float))) : "memory");
+                    }
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                return;  // no trailing barrier: tma_reads_done() guards the buffer before it is reused
+            }
+        }
         // ---- 2. cooperative row-segment stores
         const int Nx = 1 << d.logNx, M = Nx >> 1;
         const int W = d.full ? Nx : M + 1;
@@ -705,7 +753,11 @@ template <typename T, int MODE> struct ColsFused {
         OutT* outb = kBins ? nullptr : reinterpret_cast<OutT*>(d.out) + b * (long)Ny * W;
         const bool whole = (kx0 + C - 1 <= M);
         HistT* hist = reinterpret_cast<HistT*>(reinterpret_cast<char*>(smem) + hist_offset_bytes<LOG2L, LOGE, C, V>());
-        for (int ky = threadIdx.x; ky < Ny; ky += NTHR) {
+        constexpr int ROW_ITERS = (Ny + NTHR - 1) / NTHR;
+#pragma unroll 4
+        for (int it = 0; it < ROW_ITERS; ++it) {
+            const int ky = threadIdx.x + it * NTHR;
+            if (ky >= Ny) break;
             StageT p[C];
 #pragma unroll
             for (int c = 0; c < C; ++c) p[c] = stage[ky * C + c];

@@ -39,16 +39,16 @@ template <typename T> int cols_c2c(const cplx<T>* in, cplx<T>* out, int log2L, l
                                    cudaStream_t st);
 // one explicit instantiation per (T, MODE), spread over several translation units
 template <typename T, int MODE> int cols_fused_mode(const cplx<T>* in1, const cplx<T>* in2, int log2L, long ntiles_total, int ntile,
-                                                    const EpilogueDesc& d, cudaStream_t st);
+                                                    const EpilogueDesc& d, const CUtensorMap* tmap, cudaStream_t st);
 template <typename T> inline int cols_fused(int mode, const cplx<T>* in1, const cplx<T>* in2, int log2L, long ntiles_total, int ntile,
-                                            const EpilogueDesc& d, cudaStream_t st) {
+                                            const EpilogueDesc& d, const CUtensorMap* tmap, cudaStream_t st) {
     switch (mode) {
-        case EPI_COMPLEX: return cols_fused_mode<T, EPI_COMPLEX>(in1, in2, log2L, ntiles_total, ntile, d, st);
-        case EPI_POWER: return cols_fused_mode<T, EPI_POWER>(in1, in2, log2L, ntiles_total, ntile, d, st);
-        case EPI_CROSS: return cols_fused_mode<T, EPI_CROSS>(in1, in2, log2L, ntiles_total, ntile, d, st);
-        case EPI_PHASE: return cols_fused_mode<T, EPI_PHASE>(in1, in2, log2L, ntiles_total, ntile, d, st);
-        case EPI_BINS_POWER: return cols_fused_mode<T, EPI_BINS_POWER>(in1, in2, log2L, ntiles_total, ntile, d, st);
-        case EPI_BINS_CROSS: return cols_fused_mode<T, EPI_BINS_CROSS>(in1, in2, log2L, ntiles_total, ntile, d, st);
+        case EPI_COMPLEX: return cols_fused_mode<T, EPI_COMPLEX>(in1, in2, log2L, ntiles_total, ntile, d, tmap, st);
+        case EPI_POWER: return cols_fused_mode<T, EPI_POWER>(in1, in2, log2L, ntiles_total, ntile, d, tmap, st);
+        case EPI_CROSS: return cols_fused_mode<T, EPI_CROSS>(in1, in2, log2L, ntiles_total, ntile, d, tmap, st);
+        case EPI_PHASE: return cols_fused_mode<T, EPI_PHASE>(in1, in2, log2L, ntiles_total, ntile, d, tmap, st);
+        case EPI_BINS_POWER: return cols_fused_mode<T, EPI_BINS_POWER>(in1, in2, log2L, ntiles_total, ntile, d, tmap, st);
+        case EPI_BINS_CROSS: return cols_fused_mode<T, EPI_BINS_CROSS>(in1, in2, log2L, ntiles_total, ntile, d, tmap, st);
     }
     set_error("cols_fused: bad mode %d", mode);
     return -1;

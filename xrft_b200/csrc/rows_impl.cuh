@@ -32,13 +32,12 @@ int rows_r2c(RowsR2CFused<T> io, int log2M, long nseq, cudaStream_t st) {
     static int v2 = -1;
     if (v2 < 0) { const char* e = getenv("XRFTB_ROWS_V2"); v2 = e ? atoi(e) : 1; }
     if constexpr (sizeof(T) == 4) {
-        if (v2 > 0 && io.logC >= 0 && io.logNy >= 2 && io.in_row_stride == (2L << log2M) && nseq % 4 == 0) {
+        // PAIRS row pairs per CTA so that a CTA has 256 threads; its 2*PAIRS rows must be consecutive rows of one item
+        if (v2 > 0 && io.logC >= 0 && io.in_row_stride == (2L << log2M)) {
             switch (log2M) {
-                case 8: return launch_rows2<T, 8, 2>(io, nseq, st);
-                case 9: return launch_rows2<T, 9, 2>(io, nseq, st);
-                case 10: return launch_rows2<T, 10, 2>(io, nseq, st);
-                case 11: return launch_rows2<T, 11, 2>(io, nseq, st);
-                case 12: return launch_rows2<T, 12, 2>(io, nseq, st);
+#define Z(K, P) case K: if (io.logNy >= ilog2c(2 * P) && nseq % (2 * P) == 0) return launch_rows2<T, K, P>(io, nseq, st); break;
+                Z(7, 32) Z(8, 16) Z(9, 8) Z(10, 4) Z(11, 2) Z(12, 1)
+#undef Z
                 default: break;
             }
         }
