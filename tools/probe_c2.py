@@ -13,11 +13,14 @@ x = torch.randn((T, ny, nx), generator=g, device="cuda", dtype=dt)
 x += 0.3 * torch.arange(nx, device="cuda", dtype=dt) - 0.7 * torch.arange(ny, device="cuda", dtype=dt)[:, None] + 5
 wy = torch.from_numpy(sps.windows.hann(ny, sym=False)); wx = torch.from_numpy(sps.windows.hann(nx, sym=False))
 chunks = [int(c) for c in sys.argv[5].split(",")] if len(sys.argv) > 5 else [0]
+mode = sys.argv[6] if len(sys.argv) > 6 else "power"
+x2 = torch.roll(x, shifts=(3, 5), dims=(1, 2)) + 0.5 if mode != "power" else None
+MODE = {"power": L.EPI_POWER, "cross": L.EPI_CROSS, "phase": L.EPI_PHASE}[mode]
 lib = L.load()
 for ch in chunks:
-    mw = (2 << 30) if ch == 0 else lib.xrftb_spectrum2d_workspace(0 if dt == torch.float32 else 1, ny, nx, 0, ch)
+    mw = (2 << 30) if ch == 0 else lib.xrftb_spectrum2d_workspace(0 if dt == torch.float32 else 1, ny, nx, 0 if mode == "power" else 1, ch)
     def run():
-        return B.spectrum2d(x, None, L.EPI_POWER, detrend=2, win_y=wy, win_x=wx, shift_y=True, shift_x=True, scale=1.0 / (ny * nx), max_work_bytes=mw)
+        return B.spectrum2d(x, x2, MODE, detrend=2, win_y=wy, win_x=wx, shift_y=True, shift_x=True, scale=1.0 / (ny * nx), max_work_bytes=mw)
     for _ in range(2): out = run()
     torch.cuda.synchronize()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)

@@ -348,8 +348,9 @@ __global__ void __launch_bounds__(256) roll_scale_kernel(const T* __restrict__ i
 template <typename T, bool CPLX>
 __global__ void __launch_bounds__(256) mirror_fill_kernel(void* __restrict__ out_, int logNy, int logNx, int shift_y, int shift_x,
                                                           const cplx<T>* __restrict__ ramp_y, const cplx<T>* __restrict__ ramp_x,
-                                                          long nrows_total) {
+                                                          long nrows_total, int negate) {
     using E = typename std::conditional<CPLX, cplx<T>, T>::type;
+    const T sgn = negate ? (T)-1 : (T)1;   // cross-phase: angle(conj z) = -angle(z)
     E* out = reinterpret_cast<E*>(out_);
     const int Ny = 1 << logNy, Nx = 1 << logNx, M = Nx >> 1;
     const int sy = shift_y ? Ny / 2 : 0, sx = shift_x ? M : 0;
@@ -384,12 +385,35 @@ __global__ void __launch_bounds__(256) mirror_fill_kernel(void* __restrict__ out
                     float prev = __shfl_up_sync(0xffffffffu, lo.x, 1);
                     if ((threadIdx.x & 31) == 0 && act) prev = srcf[s_hi];
                     if (act) {
-                        float4 o = make_float4(prev, lo.w, lo.z, lo.y);
+                        float4 o = make_float4(sgn * prev, sgn * lo.w, sgn * lo.z, sgn * lo.y);
                         if (g == 0) {  // column t0 is a direct cell (kx = 0 or Nyquist): keep it
                             dstf[c + 1] = o.y; dstf[c + 2] = o.z; dstf[c + 3] = o.w;
                         } else {
                             *reinterpret_cast<float4*>(dstf + c) = o;
                         }
+                    }
+                }
+                continue;
+            }
+        }
+        if constexpr (CPLX && sizeof(T) == 4) {
+            if (Nx >= 64 && !ramp_y && !ramp_x) {
+                // complex64, no ramps: out[-k] = conj(out[k]); two cells (16 B) per thread, same shuffle realignment
+                const int t0 = shift_x ? 0 : M;
+                const float2* srcz = reinterpret_cast<const float2*>(src);
+                float2* dstz = reinterpret_cast<float2*>(dst);
+                const int ngroups = M / 2;
+                for (int g0 = 0; g0 < ngroups; g0 += blockDim.x) {
+                    const int g = g0 + threadIdx.x;
+                    const bool act = g < ngroups;
+                    const int c = t0 + 2 * g;              // target columns c, c+1
+                    float4 lo = make_float4(0, 0, 0, 0);
+                    if (act) lo = *reinterpret_cast<const float4*>(srcz + ((Nx - c - 2) & (Nx - 1)));  // sources of c+2 (x,y), c+1 (z,w)
+                    float px = __shfl_up_sync(0xffffffffu, lo.x, 1), py = __shfl_up_sync(0xffffffffu, lo.y, 1);
+                    if ((threadIdx.x & 31) == 0 && act) { float2 z = srcz[(Nx - c) & (Nx - 1)]; px = z.x; py = z.y; }
+                    if (act) {
+                        if (g == 0) dstz[c + 1] = make_float2(lo.z, -lo.w);   // column t0 is a direct cell
+                        else *reinterpret_cast<float4*>(dstz + c) = make_float4(px, -py, lo.z, -lo.w);
                     }
                 }
                 continue;
@@ -406,6 +430,8 @@ __global__ void __launch_bounds__(256) mirror_fill_kernel(void* __restrict__ out
                 v.y = -v.y;
                 if (ramp_y) v = cmul(v, ry);
                 if (ramp_x) v = cmul(v, cmul(__ldg(ramp_x + kxs), __ldg(ramp_x + kxt)));
+            } else {
+                v = v * sgn;
             }
             dst[(kxt + sx) & (Nx - 1)] = v;
         }
@@ -965,7 +991,8 @@ static int spectrum2d_impl(const xrftb_spectrum2d_desc& q, cudaStream_t st) {
         }
     }
     EpilogueDesc d{};
-    const bool mirror_pass = !q.keep_half && (q.mode == XRFTB_EPI_POWER || q.mode == XRFTB_EPI_COMPLEX || q.mode == XRFTB_EPI_CROSS) && q.nx >= 8;
+    const bool phase_plain = (q.mode == XRFTB_EPI_PHASE && !q.ramp_y && !q.ramp_x);  // angle(conj z) = -angle(z)
+    const bool mirror_pass = !q.keep_half && (q.mode == XRFTB_EPI_POWER || q.mode == XRFTB_EPI_COMPLEX || q.mode == XRFTB_EPI_CROSS || phase_plain) && q.nx >= 8;
     d.logNx = lx; d.full = q.keep_half ? 0 : (mirror_pass ? 2 : 1); d.shift_y = q.shift_y; d.shift_x = q.shift_x;
     d.scale = q.scale; d.ramp_y = q.ramp_y; d.ramp_x = q.ramp_x; d.weight_x = q.weight_x; d.lut = q.lut; d.nbins = q.nbins; d.lut_symmetric = q.lut_symmetric;
     const long W = q.keep_half ? q.nx / 2 + 1 : q.nx;
@@ -1009,11 +1036,12 @@ static int spectrum2d_impl(const xrftb_spectrum2d_desc& q, cudaStream_t st) {
         if (mirror_pass) {
             ProfScope ps_(PROF_MIRROR, st);
             const long nrows = nb * q.ny;
-            if (q.mode == XRFTB_EPI_POWER)
-                mirror_fill_kernel<T, false><<<mirror_grid(nrows), 256, 0, st>>>(d.out, ly, lx, q.shift_y, q.shift_x, nullptr, nullptr, nrows);
+            if (q.mode == XRFTB_EPI_POWER || q.mode == XRFTB_EPI_PHASE)
+                mirror_fill_kernel<T, false><<<mirror_grid(nrows), 256, 0, st>>>(d.out, ly, lx, q.shift_y, q.shift_x, nullptr, nullptr, nrows,
+                                                                                 q.mode == XRFTB_EPI_PHASE ? 1 : 0);
             else
                 mirror_fill_kernel<T, true><<<mirror_grid(nrows), 256, 0, st>>>(d.out, ly, lx, q.shift_y, q.shift_x,
-                    reinterpret_cast<const C_*>(q.ramp_y), reinterpret_cast<const C_*>(q.ramp_x), nrows);
+                    reinterpret_cast<const C_*>(q.ramp_y), reinterpret_cast<const C_*>(q.ramp_x), nrows, 0);
             if (int rc = check_launch("mirror_fill_kernel")) return rc;
         }
     }

@@ -492,24 +492,36 @@ cols_kernel(const __grid_constant__ IO io, const cplx<T>* __restrict__ tw, long 
         if (threadIdx.x == 0 && nxt + gridDim.x < ntiles) io.template prefetch<LOG2L, C>(nxt + gridDim.x);
         io.tma_reads_done();  // staging buffer (aliases the exchange buffer) may be overwritten from here on
         block_fft<T, LOG2L, LOGE, V, C>(v, u, sm, 1, tw);
-        if constexpr (IO::kTwoFields) {
-            // park field-1 spectrum in thread-private smem slots, transform field 2, then combine
-            cplx<T>* park = smem + G_::LPAD * C;
-            constexpr int NTHR = G_::NT * CG;
-#pragma unroll
-            for (int vv = 0; vv < V; ++vv)
-#pragma unroll
-                for (int q = 0; q < E; ++q) park[(vv * E + q) * NTHR + threadIdx.x] = v[vv][q];
-            io.template load<LOG2L, LOGE, C, V>(tile, u, cg, v, 1);
-            block_fft<T, LOG2L, LOGE, V, C>(v, u, sm, 1, tw);
-            io.template store_a<LOG2L, LOGE, C, V>(tile, u, cg, v, smem, park, NTHR);
-        } else {
-            io.template store_a<LOG2L, LOGE, C, V>(tile, u, cg, v, smem, nullptr, 0);
-        }
+        io.template store_a<LOG2L, LOGE, C, V>(tile, u, cg, v, smem);
         if (nxt < ntiles) io.template load<LOG2L, LOGE, C, V>(nxt, u, cg, v, 0);
-        io.template store_b<LOG2L, LOGE, C, V>(tile, smem);
+        io.template store_b<LOG2L, LOGE, C, (1 << (LOG2L - LOGE)) * (C / V)>(tile, smem);
     }
     io.tma_drain();
+}
+
+// Two-field variant (cross spectrum / phase / complex bins): each thread owns the SAME column of both fields, the two
+// fields are interleaved in shared memory ([pad(l)][C][2]) and transformed by one block_fft call (shared twiddles,
+// 128-bit exchanges); F1 and F2 of a cell end up in the same thread, so F1 conj(F2) needs no extra exchange.
+template <typename T, int LOG2L, int LOGE, int C, class IO>
+__global__ void __launch_bounds__((1 << (LOG2L - LOGE)) * C, min_blocks_for((1 << (LOG2L - LOGE)) * C))
+cols2f_kernel(const __grid_constant__ IO io, const cplx<T>* __restrict__ tw, long ntiles) {
+    using G_ = Geometry<LOG2L, LOGE>;
+    constexpr int E = G_::E;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx<T>* smem = reinterpret_cast<cplx<T>*>(smem_raw);
+    const int c = threadIdx.x % C, u = threadIdx.x / C;
+    cplx<T>* sm = smem + 2 * c;
+    io.template init<LOG2L, LOGE, C, 1>(smem);
+    cplx<T> v[2][E];
+    if ((long)blockIdx.x < ntiles) io.template load2f<LOG2L, LOGE, C>((long)blockIdx.x, u, c, v);
+    for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long nxt = tile + gridDim.x;
+        if (threadIdx.x == 0 && nxt + gridDim.x < ntiles) io.template prefetch<LOG2L, C>(nxt + gridDim.x);
+        block_fft<T, LOG2L, LOGE, 2, 2 * C>(v, u, sm, 1, tw);
+        io.template store_a2f<LOG2L, LOGE, C>(tile, u, c, v, smem);
+        if (nxt < ntiles) io.template load2f<LOG2L, LOGE, C>(nxt, u, c, v);
+        io.template store_b<LOG2L, LOGE, C, (1 << (LOG2L - LOGE)) * C>(tile, smem);
+    }
 }
 
 // ---- plain strided C2C on a [A][L][B] row-major view (in-place safe) ---------------------------
@@ -541,9 +553,9 @@ template <typename T> struct ColsC2C {
             }
         }
     }
-    template <int LOG2L, int LOGE, int C, int V> __device__ __forceinline__ void store_b(long, cplx<T>*) const {}
+    template <int LOG2L, int LOGE, int C, int NTHR> __device__ __forceinline__ void store_b(long, cplx<T>*) const {}
     template <int LOG2L, int LOGE, int C, int V>
-    __device__ __forceinline__ void store_a(long tile, int u, int cg, cplx<T> (&v)[V][1 << LOGE], cplx<T>*, cplx<T>*, int) const {
+    __device__ __forceinline__ void store_a(long tile, int u, int cg, cplx<T> (&v)[V][1 << LOGE], cplx<T>*) const {
         using G_ = Geometry<LOG2L, LOGE>;
         constexpr int R = 1 << G_::LOGR_LAST, G = G_::E / R, L = 1 << LOG2L;
         const long a = tile / tiles_per_row;
@@ -612,11 +624,11 @@ template <typename T, int MODE> struct ColsFused {
 
     template <int LOG2L, int LOGE, int C, int V> static constexpr int hist_offset_bytes() {
         using G_ = Geometry<LOG2L, LOGE>;
-        return (G_::LPAD * C + (kTwoFields ? G_::L * C : 0)) * (int)sizeof(cplx<T>);
+        return (G_::LPAD * C * (kTwoFields ? 2 : 1)) * (int)sizeof(cplx<T>);
     }
     template <int LOG2L, int LOGE, int C, int V> __device__ __forceinline__ void init(cplx<T>* smem) const {
         if constexpr (kBins) {
-            HistT* hist = reinterpret_cast<HistT*>(reinterpret_cast<char*>(smem) + hist_offset_bytes<LOG2L, LOGE, C, V>());
+            HistT* hist = reinterpret_cast<HistT*>(reinterpret_cast<char*>(smem) + hist_offset_bytes<LOG2L, LOGE, C, 1>());
             for (int i = threadIdx.x; i < d.nbins * (kCplxStage ? 2 : 1); i += blockDim.x) hist[i] = 0;
             __syncthreads();
         }
@@ -661,11 +673,41 @@ template <typename T, int MODE> struct ColsFused {
         }
     }
 
-    template <int LOG2L, int LOGE, int C, int V>
-    __device__ __forceinline__ void store_a(long tile, int u, int cg, cplx<T> (&v)[V][1 << LOGE], cplx<T>* smem, const cplx<T>* park,
-                                            int nthr) const {
+    // two-field modes: thread (u, c) loads column c of both fields
+    template <int LOG2L, int LOGE, int C>
+    __device__ __forceinline__ void load2f(long tile, int u, int c, cplx<T> (&v)[2][1 << LOGE]) const {
+        constexpr int NT = Geometry<LOG2L, LOGE>::NT, L = 1 << LOG2L;
+        const long off = tile * (long)L * C + c + u * C;
+#pragma unroll
+        for (int q = 0; q < (1 << LOGE); ++q) {
+            v[0][q] = in1[off + q * (NT * C)];
+            v[1][q] = in2[off + q * (NT * C)];
+        }
+    }
+    template <int LOG2L, int LOGE, int C>
+    __device__ __forceinline__ void store_a2f(long, int u, int c, cplx<T> (&v)[2][1 << LOGE], cplx<T>* smem) const {
         using G_ = Geometry<LOG2L, LOGE>;
-        constexpr int R = 1 << G_::LOGR_LAST, G = G_::E / R, E = G_::E;
+        constexpr int R = 1 << G_::LOGR_LAST, G = G_::E / R;
+        StageT* stage = reinterpret_cast<StageT*>(smem);
+        const T sc = (T)d.scale;
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+#pragma unroll
+            for (int t = 0; t < R; ++t) {
+                const int ky = final_index<LOG2L, LOGE>(u, g, t);
+                if constexpr (kCplxStage) stage[ky * C + c] = cscale(cmulc(v[0][g + t * G], v[1][g + t * G]), sc);
+            }
+        __syncthreads();
+    }
+
+    template <int LOG2L, int LOGE, int C, int V>
+    __device__ __forceinline__ void store_a(long tile, int u, int cg, cplx<T> (&v)[V][1 << LOGE], cplx<T>* smem) const {
+        using G_ = Geometry<LOG2L, LOGE>;
+        constexpr int R = 1 << G_::LOGR_LAST, G = G_::E / R;
+        constexpr int nthr = 0;
+        const cplx<T>* park = nullptr;
+        (void)nthr; (void)park;
+        constexpr int E = G_::E;
         StageT* stage = reinterpret_cast<StageT*>(smem);
         const T sc = (T)d.scale;
         // ---- 1. epilogue value of each owned (ky, c) -> staging [ky][C]
@@ -693,10 +735,10 @@ template <typename T, int MODE> struct ColsFused {
         __syncthreads();
     }
 
-    template <int LOG2L, int LOGE, int C, int V>
+    template <int LOG2L, int LOGE, int C, int NTHR>
     __device__ __forceinline__ void store_b(long tile, cplx<T>* smem) const {
         using G_ = Geometry<LOG2L, LOGE>;
-        constexpr int Ny = 1 << LOG2L, NTHR = G_::NT * (C / V);
+        constexpr int Ny = 1 << LOG2L;
         StageT* stage = reinterpret_cast<StageT*>(smem);
         if constexpr (MODE == EPI_POWER && sizeof(T) == 4) {
             if (d.use_tma) {
@@ -752,7 +794,7 @@ template <typename T, int MODE> struct ColsFused {
         const int ox0 = (kx0 + sx) & (Nx - 1);  // direct cells: ox0 + c (no wrap inside an aligned tile)
         OutT* outb = kBins ? nullptr : reinterpret_cast<OutT*>(d.out) + b * (long)Ny * W;
         const bool whole = (kx0 + C - 1 <= M);
-        HistT* hist = reinterpret_cast<HistT*>(reinterpret_cast<char*>(smem) + hist_offset_bytes<LOG2L, LOGE, C, V>());
+        HistT* hist = reinterpret_cast<HistT*>(reinterpret_cast<char*>(smem) + hist_offset_bytes<LOG2L, LOGE, C, 1>());
         constexpr int ROW_ITERS = (Ny + NTHR - 1) / NTHR;
 #pragma unroll 4
         for (int it = 0; it < ROW_ITERS; ++it) {

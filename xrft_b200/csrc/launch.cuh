@@ -71,9 +71,9 @@ static int launch_cols(const IO& io, long ntiles, cudaStream_t st, size_t extra_
     constexpr int LOGE = cmin(TypeCfg<T>::LOGE, LOG2L);
     constexpr int V = cmin(TypeCfg<T>::V, C);
     using G_ = Geometry<LOG2L, LOGE>;
-    auto kern = cols_kernel<T, LOG2L, LOGE, C, V, IO>;
-    constexpr int threads = G_::NT * (C / V);
-    constexpr size_t smem_fixed = (size_t)G_::LPAD * C * sizeof(cplx<T>) + (IO::kTwoFields ? (size_t)G_::L * C * sizeof(cplx<T>) : 0);
+    auto kern = [] { if constexpr (IO::kTwoFields) return cols2f_kernel<T, LOG2L, LOGE, C, IO>; else return cols_kernel<T, LOG2L, LOGE, C, V, IO>; }();
+    constexpr int threads = IO::kTwoFields ? G_::NT * C : G_::NT * (C / V);
+    constexpr size_t smem_fixed = (size_t)G_::LPAD * C * sizeof(cplx<T>) * (IO::kTwoFields ? 2 : 1);
     // bins modes append a histogram of up to kMaxFusedBins (x2 for complex) doubles
     constexpr size_t smem_cap = smem_fixed + (IO::kBins ? (size_t)kMaxFusedBins * 2 * sizeof(double) : 0);
     const size_t smem = smem_fixed + extra_smem;
