@@ -266,7 +266,7 @@ def run_b200(args):
     del out
 
     # ---- roofline of the dominant kernel (achieved algorithmic bytes / CUDA-event duration)
-    names = ["moments_kernel", "rows_kernel<RowsR2CFused>", "cols_kernel<ColsFused POWER>", "mirror_fill_kernel"]
+    names = ["moments_kernel", "rows2_kernel<RowsR2CFused>", "cols_kernel<ColsFused POWER>", "mirror_fill_kernel"]
     # algorithmic bytes per real-space point each kernel must move: read f32 | read f32 + write c64 half spectrum |
     # read half spectrum + write the direct half of the f32 output | read + write the mirrored half
     half = (nx // 2 + 1) / nx

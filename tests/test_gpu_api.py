@@ -473,3 +473,22 @@ def test_theoretical_matching_440000_points():
     np.testing.assert_allclose(ft.values.imag[sel], 0, atol=1e-3)
     ref = O.fft(lab(da), true_phase=True, true_amplitude=True)
     assert relerr(ft.values, ref.data) < 1e-9
+
+
+@pytest.mark.parametrize("dt,shape", [(np.float32, (2, 512, 1024)), (np.float64, (1, 256, 512)), (np.float32, (1, 2048, 2048))])
+def test_cross_spectrum_phase_large(dt, shape):
+    """two-field fused kernels at multi-stage FFT sizes (both fields interleaved per thread; mirror pass)"""
+    rng = np.random.default_rng(31)
+    a = mk(shape, ("t", "y", "x"), rng, dt=dt, spacing={"t": 1.0, "y": 1.0, "x": 1.0})
+    b = mk(shape, ("t", "y", "x"), rng, dt=dt, spacing={"t": 1.0, "y": 1.0, "x": 1.0})
+    kw = dict(dim=["y", "x"], detrend="constant", window="hann")
+    tol = 1e-3 if dt == np.float32 else 1e-9
+    ref = O.cross_spectrum(lab(a), lab(b), **kw)
+    same(xrft.cross_spectrum(a, b, **kw), ref, tol=tol, check_attrs=False)
+    out = xrft.cross_phase(a, b, **kw)
+    d = np.abs(np.angle(np.exp(1j * (out.values - np.angle(ref.data)))))
+    sig = np.abs(ref.data) > 1e-3 * np.abs(ref.data).max()
+    assert d[sig].max() < (2e-2 if dt == np.float32 else 1e-6)
+    # Hermitian structure of the cross spectrum of real fields: C(-k) = conj(C(k))
+    c = xrft.cross_spectrum(a, b, **kw).values[0]
+    np.testing.assert_allclose(c[1:, 1:], np.conj(c[1:, 1:][::-1, ::-1]), rtol=1e-4, atol=1e-6 * np.abs(c).max())

@@ -44,7 +44,7 @@ for d in data:
         b = tobytes("dram__bytes_read.sum") + tobytes("dram__bytes_write.sum")
         t = tosec("gpu__time_duration.sum")
         md.append(f"- **dram traffic per launch: {b/1e6:.1f} MB = {b/pts_per_launch:.2f} B/point; {b/t/1e9:.0f} GB/s while running**")
-        cls = "moments_kernel" if "moments" in name else "rows_kernel<RowsR2CFused>" if "rows_kernel" in name else "cols_kernel<ColsFused POWER>" if "cols_kernel" in name else "mirror_fill_kernel"
+        cls = "moments_kernel" if "moments" in name else "rows2_kernel<RowsR2CFused>" if "rows" in name else "cols_kernel<ColsFused POWER>" if "cols_kernel" in name else "mirror_fill_kernel"
         traffic[cls] = {"dram_bytes_per_point": b / pts_per_launch, "launch_us": t * 1e6}
     except Exception as e:
         md.append(f"- (traffic parse failed: {e})")
