@@ -195,6 +195,8 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # keep stdout to the single JSON line: NCCL's banner / debug output goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -338,6 +340,7 @@ def run_b200(args):
                "sample": f"{ns} slices of {ny}x{nx} float32 ({dt:.1f} s), oracle power_spectrum(detrend='linear', window='hann'), {workers} threads"}
 
     if rank == 0:
+        sys.stdout.flush()
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
