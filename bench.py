@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--ny", type=int, default=4096)
     ap.add_argument("--nx", type=int, default=4096)
     ap.add_argument("--e2e-time", type=int, default=64, help="time slices per end-to-end step (host buffers)")
-    ap.add_argument("--chunk", type=int, default=16, help="time slices per fused kernel chain (dask chunk {'time':16})")
+    ap.add_argument("--chunk", type=int, default=8, help="time slices per fused kernel chain (dask chunk {'time':16})")
     ap.add_argument("--cpu-slices", type=int, default=0, help="slices in the CPU sample (0 = one per worker)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

@@ -255,7 +255,7 @@ def binned_sum(arr: torch.Tensor, lut: torch.Tensor, nbins: int, ncore: int) -> 
 # fused hot path
 # ---------------------------------------------------------------------------------------------
 _WORK = {}
-_FUSED_CHUNK = 16  # batch items (dask-style chunks along the outer axis) per fused kernel chain
+_FUSED_CHUNK = 8  # batch items (dask-style chunks along the outer axis) per fused kernel chain
 
 
 def set_fused_chunk(n: int):
@@ -331,7 +331,7 @@ def spectrum2d(x1: torch.Tensor, x2: Optional[torch.Tensor], mode: int, detrend:
         needall = lib.xrftb_spectrum2d_workspace(dt, ny, nx, 1 if two else 0, batch)
         if max_work_bytes is None:
             # default: _FUSED_CHUNK items of >= 4096^2 points; smaller grids keep ~the same bytes in flight
-            items = max(_FUSED_CHUNK, (_FUSED_CHUNK * 4096 * 4096) // (ny * nx))
+            items = max(_FUSED_CHUNK, (_FUSED_CHUNK * 4096 * 4096) // (ny * nx))  # ~512 MiB of f32 input per kernel chain
             max_work_bytes = lib.xrftb_spectrum2d_workspace(dt, ny, nx, 1 if two else 0, items)
         wbytes = max(need1, min(needall, max_work_bytes))
         work = _workspace(dev, wbytes)

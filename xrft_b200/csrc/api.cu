@@ -1021,6 +1021,9 @@ static int spectrum2d_impl(const xrftb_spectrum2d_desc& q, cudaStream_t st) {
         d.bins = bins_mode ? q.bins + (size_t)b0 * q.nbins * (q.mode == XRFTB_EPI_BINS_CROSS ? 2 : 1) : nullptr;
         const C_* i1 = interm;
         const C_* i2 = two ? interm + (size_t)bchunk * (per_item / sizeof(C_)) : nullptr;
+        static int hints_on = -1;
+        if (hints_on < 0) { const char* e = getenv("XRFTB_L2_HINTS"); hints_on = e ? atoi(e) : 0; }
+        d.l2_hints = hints_on;
         CUtensorMap tmap;
         const CUtensorMap* ptm = nullptr;
         d.use_tma = 0;

@@ -26,6 +26,22 @@ constexpr int ilog2c(int n) { return n <= 1 ? 0 : 1 + ilog2c(n / 2); }
 
 enum : int { EPI_COMPLEX = 0, EPI_POWER = 1, EPI_CROSS = 2, EPI_PHASE = 3, EPI_BINS_POWER = 4, EPI_BINS_CROSS = 5 };
 
+// L2 cache-policy hinted 16-byte accesses (experiment knob XRFTB_L2_HINTS): the intermediate is read exactly once
+// (evict-first), the 16-byte output row segments should stay in L2 until the neighbouring tile completes the sector
+// (evict-last), so that partial sectors are merged instead of written back early
+__device__ __forceinline__ float4 ld16_evict_first(const void* p) {
+    float4 r;
+    asm volatile("{\n\t.reg .b64 pol;\n\tcreatepolicy.fractional.L2::evict_first.b64 pol, 1.0;\n\t"
+                 "ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], pol;\n\t}"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st16_evict_last(void* p, float4 v) {
+    asm volatile("{\n\t.reg .b64 pol;\n\tcreatepolicy.fractional.L2::evict_last.b64 pol, 1.0;\n\t"
+                 "st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, pol;\n\t}"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 __device__ __forceinline__ float xatan2(float y, float x) { return atan2f(y, x); }
 __device__ __forceinline__ double xatan2(double y, double x) { return atan2(y, x); }
 
@@ -599,6 +615,7 @@ struct EpilogueDesc {
     int nbins;
     int use_tma;           // POWER: write the direct cells with TMA tensor stores (tmap describes out as [rows][W] float)
     int tma_box_rows;      // rows per TMA box (<= 256, divides Ny/2 so a box never straddles the fftshift wrap)
+    int l2_hints;          // 1: evict-first tile loads / evict-last row-segment stores
     int lut_symmetric;     // bins: lut[-ky][-kx] == lut[ky][kx] for every cell (true for radial bins): mirror cells reuse the bin
 };
 
@@ -663,7 +680,7 @@ template <typename T, int MODE> struct ColsFused {
 #pragma unroll
         for (int q = 0; q < (1 << LOGE); ++q) {
             if constexpr (V == 2 && sizeof(T) == 4) {
-                float4 x = *reinterpret_cast<const float4*>(p + q * (NT * C));
+                float4 x = d.l2_hints ? ld16_evict_first(p + q * (NT * C)) : *reinterpret_cast<const float4*>(p + q * (NT * C));
                 v[0][q] = mk<T>(x.x, x.y);
                 v[V - 1][q] = mk<T>(x.z, x.w);
             } else {
@@ -830,7 +847,12 @@ template <typename T, int MODE> struct ColsFused {
                     Vec vv_;
 #pragma unroll
                     for (int c = 0; c < C; ++c) vv_.e[c] = q[c];
-                    *reinterpret_cast<Vec*>(rowd) = vv_;
+                    if constexpr (sizeof(Vec) == 16) {
+                        if (d.l2_hints) st16_evict_last(rowd, *reinterpret_cast<const float4*>(&vv_));
+                        else *reinterpret_cast<Vec*>(rowd) = vv_;
+                    } else {
+                        *reinterpret_cast<Vec*>(rowd) = vv_;
+                    }
                 } else {
 #pragma unroll
                     for (int c = 0; c < C; ++c) if (kx0 + c <= M) outb[(long)oy * W + ((kx0 + c + sx) & (Nx - 1))] = q[c];
