@@ -331,7 +331,8 @@ def spectrum2d(x1: torch.Tensor, x2: Optional[torch.Tensor], mode: int, detrend:
         needall = lib.xrftb_spectrum2d_workspace(dt, ny, nx, 1 if two else 0, batch)
         if max_work_bytes is None:
             # default: _FUSED_CHUNK items of >= 4096^2 points; smaller grids keep ~the same bytes in flight
-            items = max(_FUSED_CHUNK, (_FUSED_CHUNK * 4096 * 4096) // (ny * nx))  # ~512 MiB of f32 input per kernel chain
+            # measured: 4-12 items of 4096^2 per kernel chain are equivalent, smaller grids prefer ~2x more points in flight
+            items = _FUSED_CHUNK if ny * nx >= 4096 * 4096 else max(_FUSED_CHUNK, (2 * _FUSED_CHUNK * 4096 * 4096) // (ny * nx))
             max_work_bytes = lib.xrftb_spectrum2d_workspace(dt, ny, nx, 1 if two else 0, items)
         wbytes = max(need1, min(needall, max_work_bytes))
         work = _workspace(dev, wbytes)
