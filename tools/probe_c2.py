@@ -31,4 +31,14 @@ for ch in chunks:
     pts = T * ny * nx
     import ctypes
     lib.xrftb_profile_begin(); out = run(); pm = (ctypes.c_double * 4)(); pc = (ctypes.c_long * 4)(); lib.xrftb_profile_end(pm, pc)
-    print(f"{ny}x{nx}x{T} {dt} chunk={ch}: {ms:.3f} ms/step  {pts / ms / 1e6:.1f} GPts/s | us/16slices-equiv: " + " ".join(f"{n}={pm[i] * 1e3 * 16 / T:.0f}" for i, n in enumerate(["mom", "rows", "cols", "mirror"])))
+    err = ""
+    if mode == "power":
+        # accuracy of slice 0 against a float64 numpy evaluation of the reference formulas (closed-form plane, f32 round, window, fft2)
+        xd = x[0].double().cpu().numpy()
+        ii = np.arange(ny)[:, None] - 0.5 * (ny - 1); jj = np.arange(nx)[None, :] - 0.5 * (nx - 1)
+        pl = xd.mean() + ii * ((ii * xd).sum() / (nx * ny * (ny * ny - 1) / 12)) + jj * ((jj * xd).sum() / (ny * nx * (nx * nx - 1) / 12))
+        d = (xd - pl).astype(np.float32 if dt == torch.float32 else np.float64).astype(np.float64)
+        ref = np.fft.fftshift(np.abs(np.fft.fft2(d * wy.numpy()[:, None] * wx.numpy()[None, :])) ** 2) / (ny * nx)
+        got = out[0].double().cpu().numpy()
+        err = f" relL2={np.linalg.norm(got - ref) / np.linalg.norm(ref):.2e} maxrel={np.abs(got - ref).max() / ref.max():.2e}"
+    print(f"{ny}x{nx}x{T} {dt} chunk={ch}:{err} {ms:.3f} ms/step  {pts / ms / 1e6:.1f} GPts/s | us/16slices-equiv: " + " ".join(f"{n}={pm[i] * 1e3 * 16 / T:.0f}" for i, n in enumerate(["mom", "rows", "cols", "mirror"])))

@@ -233,6 +233,84 @@ __global__ void __maxnreg__(32) moments_side_kernel(const float* __restrict__ in
 }
 
 // ------------------------------------------------------------------------------------------------
+// row-line detrend completion (fused float32 path).  The row pass subtracted from row i of item b the exactly known
+// line ph_i(j) = A0 + B j and recorded (A0, B, sum_j r, sum_j (j - jc) r) of the residual r = x - ph.
+//   row sums of x        S_i = Nx A0 + B Nx (Nx-1)/2 + sum r ;   T_i = sum_j (j - jc) x = B vx + sum (j - jc) r
+//   least-squares plane  a = sum S_i / (Ny Nx), b = sum (i - ic) S_i / (Nx vy), c = sum T_i / (Ny vx)   (detrend=linear;
+//                        b = c = 0 for detrend=constant) -- the same centred-moment closed form as moments_kernel
+//   still to subtract    plane - ph_i = -(alpha_i + gamma_i (j - jc)),  alpha_i = A0 + B jc - a - b (i - ic), gamma_i = B - c
+// Output: ag[b][i] = w_y(i) (alpha_i, gamma_i); the column pass adds ag.x What(kx) + ag.y Jhat(kx) to row i of the
+// half-spectrum (What, Jhat = transforms of w_x(j) and w_x(j)(j - jc)).  One CTA per item, fp64 throughout.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) rowline_fix_kernel(const float4* __restrict__ rowstats, cplx<T>* __restrict__ ag, const T* __restrict__ wy,
+                                                          int ny, int nx, int detrend) {
+    const long b = blockIdx.x;
+    const float4* rs = rowstats + b * ny;
+    const double ic = 0.5 * (double)(ny - 1), jc = 0.5 * (double)(nx - 1);
+    const double vx = (double)nx * ((double)nx * nx - 1.0) / 12.0, vy = (double)ny * ((double)ny * ny - 1.0) / 12.0;
+    const double tri = 0.5 * (double)nx * (double)(nx - 1);
+    double S = 0, Sy = 0, Sx = 0;
+    for (int i = threadIdx.x; i < ny; i += blockDim.x) {
+        const float4 r = rs[i];
+        const double Si = (double)nx * (double)r.x + (double)r.y * tri + (double)r.z;
+        S += Si;
+        Sy += ((double)i - ic) * Si;
+        Sx += (double)r.y * vx + (double)r.w;
+    }
+    __shared__ double red[3][8];
+    __shared__ double plane[3];
+    double vals[3] = {S, Sy, Sx};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        double x = vals[k];
+        for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+        if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double x = 0;
+        for (int w = 0; w < 8; ++w) x += red[threadIdx.x][w];
+        plane[threadIdx.x] = x;
+    }
+    __syncthreads();
+    const double a = plane[0] / ((double)ny * (double)nx);
+    const double bb = (detrend == 2 && ny > 1) ? plane[1] / ((double)nx * vy) : 0.0;
+    const double c = (detrend == 2) ? plane[2] / ((double)ny * vx) : 0.0;
+    for (int i = threadIdx.x; i < ny; i += blockDim.x) {
+        const float4 r = rs[i];
+        const double w = wy ? (double)wy[i] : 1.0;
+        const double alpha = (double)r.x + (double)r.y * jc - a - bb * ((double)i - ic);
+        const double gamma = (double)r.y - c;
+        ag[b * ny + i] = mk<T>((T)(w * alpha), (T)(w * gamma));
+    }
+}
+// rows [w_x(j)] and [w_x(j) (j - jc)] in double, input of the one-off transform that yields What, Jhat
+template <typename T>
+__global__ void __launch_bounds__(256) rowline_wj_in_kernel(const T* __restrict__ wx, double* __restrict__ rows, int nx) {
+    const double jc = 0.5 * (double)(nx - 1);
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nx; j += gridDim.x * blockDim.x) {
+        const double w = wx ? (double)wx[j] : 1.0;
+        rows[j] = w;
+        rows[nx + j] = w * ((double)j - jc);
+    }
+}
+// wj[2 k] = What(k), wj[2 k + 1] = Jhat(k) for k <= M; zero for the padding columns of the last tile
+template <typename T>
+__global__ void __launch_bounds__(256) rowline_wj_out_kernel(const double2* __restrict__ spec, cplx<T>* __restrict__ wj, int M, int ncols) {
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < ncols; k += gridDim.x * blockDim.x) {
+        cplx<T> w = mk<T>(0, 0), j = mk<T>(0, 0);
+        if (k <= M) {
+            const double2 a = spec[k], b = spec[(M + 1) + k];
+            w = mk<T>((T)a.x, (T)a.y);
+            j = mk<T>((T)b.x, (T)b.y);
+        }
+        wj[2 * k] = w;
+        wj[2 * k + 1] = j;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // detrend + window (non-fused path and the public xrft.detrend)
 // ------------------------------------------------------------------------------------------------
 template <typename T>
@@ -927,6 +1005,19 @@ template <typename T> static size_t interm_bytes_per_item(int ny, int nx, int C)
     return (size_t)ntile * ny * C * sizeof(cplx<T>);
 }
 
+// row-line detrend: per-item rowstats (float4 / row) + ag (cplx<T> / row); fixed: wj table + its fp64 transform scratch
+static inline size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
+template <typename T> static size_t rowline_item_bytes(int ny) { return (size_t)ny * (sizeof(float4) + sizeof(cplx<T>)); }
+template <typename T> static size_t rowline_fixed_bytes(int nx, int C) {
+    const size_t ncols = (size_t)((nx / 2) / C + 1) * C;
+    return align256(ncols * 2 * sizeof(cplx<T>)) + align256((size_t)2 * nx * sizeof(double)) + align256((size_t)2 * (nx / 2 + 1) * sizeof(double2));
+}
+static bool rowline_enabled() {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("XRFTB_ROWLINE"); on = e ? atoi(e) : 0; }
+    return on != 0;
+}
+
 template <typename T>
 static int spectrum2d_impl(const xrftb_spectrum2d_desc& q, cudaStream_t st) {
     using C_ = cplx<T>;
@@ -941,13 +1032,38 @@ static int spectrum2d_impl(const xrftb_spectrum2d_desc& q, cudaStream_t st) {
     const long ntile = (q.nx / 2) / C + 1;
     const size_t per_item = interm_bytes_per_item<T>(q.ny, q.nx, C);
     const size_t mom_bytes = (size_t)q.batch * fields * 4 * sizeof(double);
-    const size_t mom_region = (mom_bytes + 255) & ~(size_t)255;
-    if (!q.work || q.work_bytes < mom_region + per_item * fields) { set_error("spectrum2d: workspace too small (%zu < %zu)", q.work_bytes, mom_region + per_item * fields); return XRFTB_EWORKSPACE; }
-    long bchunk = (long)((q.work_bytes - mom_region) / (per_item * fields));
+    // row-line detrend (no moments pass): float32, one field, and the two-rows-per-thread row kernel is the one that runs
+    const bool rowline = std::is_same<T, float>::value && q.detrend && !two && rowline_enabled() && rows2_eligible(lx - 1, ly);
+    const size_t mom_region = align256(mom_bytes) + (rowline ? rowline_fixed_bytes<T>(q.nx, C) : 0);
+    const size_t item_total = per_item * fields + (rowline ? rowline_item_bytes<T>(q.ny) : 0);
+    if (!q.work || q.work_bytes < mom_region + item_total) { set_error("spectrum2d: workspace too small (%zu < %zu)", q.work_bytes, mom_region + item_total); return XRFTB_EWORKSPACE; }
+    long bchunk = (long)((q.work_bytes - mom_region) / item_total);
     if (bchunk > q.batch) bchunk = q.batch;
     { const long nch = (q.batch + bchunk - 1) / bchunk; bchunk = (q.batch + nch - 1) / nch; }  // balanced chunks
     double* mom = reinterpret_cast<double*>(q.work);
     C_* interm = reinterpret_cast<C_*>(reinterpret_cast<char*>(q.work) + mom_region);
+    float4* rowstats = nullptr;
+    C_* ag = nullptr;
+    C_* wj = nullptr;
+    if (rowline) {
+        char* fx = reinterpret_cast<char*>(q.work) + align256(mom_bytes);
+        const int M = q.nx / 2;
+        const size_t ncols = (size_t)(M / C + 1) * C;
+        wj = reinterpret_cast<C_*>(fx);
+        double* wrows = reinterpret_cast<double*>(fx + align256(ncols * 2 * sizeof(C_)));
+        double2* wspec = reinterpret_cast<double2*>(reinterpret_cast<char*>(wrows) + align256((size_t)2 * q.nx * sizeof(double)));
+        rowstats = reinterpret_cast<float4*>(reinterpret_cast<char*>(interm) + (size_t)bchunk * per_item * fields);
+        ag = reinterpret_cast<C_*>(rowstats + (size_t)bchunk * q.ny);
+        // What, Jhat: one fp64 real transform of two rows of length nx, once per call
+        rowline_wj_in_kernel<T><<<(q.nx + 255) / 256, 256, 0, st>>>(reinterpret_cast<const T*>(q.win_x), wrows, q.nx);
+        if (int rc = check_launch("rowline_wj_in_kernel")) return rc;
+        RowsR2CFused<double> wio{};
+        wio.in = wrows; wio.in_row_stride = q.nx; wio.logNy = 0; wio.detrend = 0; wio.moments = nullptr; wio.wy = nullptr; wio.wx = nullptr;
+        wio.out = wspec; wio.logC = -1; wio.out_seq_stride = M + 1; wio.rowstats = nullptr;
+        if (int rc = rows_r2c<double>(wio, lx - 1, 2, st)) return rc;
+        rowline_wj_out_kernel<T><<<(unsigned)((ncols + 255) / 256), 256, 0, st>>>(wspec, wj, M, (int)ncols);
+        if (int rc = check_launch("rowline_wj_out_kernel")) return rc;
+    }
     const long item = (long)q.ny * q.nx;
     const T* ins[2] = {reinterpret_cast<const T*>(q.in1), reinterpret_cast<const T*>(q.in2)};
 
@@ -956,7 +1072,7 @@ static int spectrum2d_impl(const xrftb_spectrum2d_desc& q, cudaStream_t st) {
     static int side_on = -1;
     if (side_on < 0) { const char* e = getenv("XRFTB_SIDE_MOMENTS"); side_on = e ? atoi(e) : 0; }  // measured slower: off by default
     const long nchunks = (q.batch + bchunk - 1) / bchunk;
-    const bool side = side_on && q.detrend && std::is_same<T, float>::value && nchunks > 1 && lx >= 2 && fields == 1;
+    const bool side = side_on && q.detrend && !rowline && std::is_same<T, float>::value && nchunks > 1 && lx >= 2 && fields == 1;
     static thread_local cudaStream_t s_side = nullptr;
     std::vector<cudaEvent_t> ev_mom;
     auto launch_moments = [&](const T* base, double* m, long nitems, cudaStream_t stream, bool light) -> int {
@@ -973,7 +1089,7 @@ static int spectrum2d_impl(const xrftb_spectrum2d_desc& q, cudaStream_t st) {
         }
         return check_launch("moments_kernel");
     };
-    if (q.detrend) {
+    if (q.detrend && !rowline) {
         cudaError_t e = cudaMemsetAsync(mom, 0, mom_bytes, st);
         if (e != cudaSuccess) { set_error("memset: %s", cudaGetErrorString(e)); return XRFTB_ECUDA; }
         if (!side) {
@@ -1008,8 +1124,14 @@ static int spectrum2d_impl(const xrftb_spectrum2d_desc& q, cudaStream_t st) {
             io.moments = mom + ((size_t)f * q.batch + b0) * 4;
             io.wy = reinterpret_cast<const T*>(q.win_y); io.wx = reinterpret_cast<const T*>(q.win_x);
             io.out = interm + (size_t)f * bchunk * (per_item / sizeof(C_)); io.logC = ilog2_exact(C); io.out_seq_stride = 0;
+            io.rowstats = rowline ? rowstats : nullptr;
             ProfScope ps_(PROF_ROWS, st);
             if (int rc = rows_r2c<T>(io, lx - 1, nb * q.ny, st)) return rc;
+        }
+        if (rowline) {
+            ProfScope ps_(PROF_MOMENTS, st);
+            rowline_fix_kernel<T><<<(unsigned)nb, 256, 0, st>>>(rowstats, ag, reinterpret_cast<const T*>(q.win_y), q.ny, q.nx, q.detrend);
+            if (int rc = check_launch("rowline_fix_kernel")) return rc;
         }
         if (side && ci + 1 < nchunks) {
             const long b1 = b0 + bchunk;
@@ -1024,6 +1146,8 @@ static int spectrum2d_impl(const xrftb_spectrum2d_desc& q, cudaStream_t st) {
         static int hints_on = -1;
         if (hints_on < 0) { const char* e = getenv("XRFTB_L2_HINTS"); hints_on = e ? atoi(e) : 0; }
         d.l2_hints = hints_on;
+        d.fix_ag = rowline ? ag : nullptr;
+        d.fix_wj = rowline ? wj : nullptr;
         CUtensorMap tmap;
         const CUtensorMap* ptm = nullptr;
         d.use_tma = 0;
@@ -1215,8 +1339,10 @@ size_t xrftb_spectrum2d_workspace(int dtype, int ny, int nx, int two_fields, int
     const size_t per_item = dtype == XRFTB_F32 ? interm_bytes_per_item<float>(ny, nx, C) : interm_bytes_per_item<double>(ny, nx, C);
     const int fields = two_fields ? 2 : 1;
     if (batch_in_flight < 1) batch_in_flight = 1;
-    // moments region is sized for up to 65536 items x 2 fields
-    return ((size_t)65536 * 2 * 4 * sizeof(double)) + per_item * fields * (size_t)batch_in_flight + 256;
+    // moments region is sized for up to 65536 items x 2 fields; row-line detrend tables (float32, one field) ride along
+    const size_t rl_fixed = (dtype == XRFTB_F32 && !two_fields) ? rowline_fixed_bytes<float>(nx, C) : 0;
+    const size_t rl_item = (dtype == XRFTB_F32 && !two_fields) ? rowline_item_bytes<float>(ny) : 0;
+    return ((size_t)65536 * 2 * 4 * sizeof(double)) + rl_fixed + (per_item * fields + rl_item) * (size_t)batch_in_flight + 1024;
 }
 
 int xrftb_spectrum2d(const xrftb_spectrum2d_desc* q, void* stream) {

@@ -1,5 +1,6 @@
 // xrft_b200 -- strided-axis pass dispatch.
 #pragma once
+#include <cstdlib>
 #include "launch.cuh"
 
 namespace xrftb {
@@ -37,9 +38,17 @@ static int cols_fused_k(const cplx<T>* in1, const cplx<T>* in2, long ntiles_tota
         set_error("cols_fused: length 2^%d too long for %d field(s)", K, IO::kTwoFields ? 2 : 1);
         return -2;
     } else {
-        IO io{in1, in2, ntile, d, {}};
+        IO io{in1, in2, ntile, d, 0, reinterpret_cast<const cplx<T>*>(d.fix_ag), reinterpret_cast<const cplx<T>*>(d.fix_wj), {}};
+        io.hist_off = IO::template hist_offset_bytes<K, cmin(TypeCfg<T>::LOGE, K), C, 1>();
         if (tmap) io.tmap = *tmap;
         const size_t extra = IO::kBins ? (size_t)d.nbins * (IO::kCplxStage ? 2 : 1) * sizeof(double) : 0;
+        // real-valued single-field epilogues of the float32 path: bulk-copy fed variant (the staging buffer fits the
+        // half-size exchange buffer).  XRFTB_COLS_ASYNC=0 selects the register-prefetch kernel.
+        if constexpr (sizeof(T) == 4 && (MODE == EPI_POWER || MODE == EPI_BINS_POWER) && (K > TypeCfg<T>::LOGE) && C >= 2 && C % 2 == 0) {
+            static int async_on = -1;
+            if (async_on < 0) { const char* e = getenv("XRFTB_COLS_ASYNC"); async_on = e ? atoi(e) : 0; }
+            if (async_on) return launch_cols_async<T, K, C>(io, ntiles_total, st, extra);
+        }
         return launch_cols<T, K, C>(io, ntiles_total, st, extra);
     }
 }

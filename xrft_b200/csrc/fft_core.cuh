@@ -243,6 +243,134 @@ __device__ __forceinline__ void block_fft(cplx<T> (&v)[NSEQV][1 << LOGE], int u,
     Stages<T, LOG2L, LOGE, 0, SI>::template run<NSEQV>(v, u, sm, vstride, tw);
 }
 
+// ---------------------------------------------------------------------------------------------
+// asynchronous tile loads: 1-D bulk copies (TMA engine, SASS UBLKCP) completing on an mbarrier.
+// One elected thread arms the barrier with the byte count and issues the copies; every thread
+// waits on the phase parity before reading the landing buffer.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "XRFTB_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra XRFTB_DONE_%=;\n\t"
+        "bra XRFTB_WAIT_%=;\n\t"
+        "XRFTB_DONE_%=:\n\t}"
+        ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_load_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------
+// Stage driver of the asynchronous column kernel.  Two register-resident sequences per thread
+// (columns 2*cg, 2*cg+1 of a C-column tile, CG = C/2 column groups).  Exchange #0 goes through
+// the full-width landing buffer `smL` ([pad(o)][C], 128-bit accesses, both sequences at once);
+// after its gather the buffer is dead and `hook()` re-arms it with the NEXT tile's bulk load.
+// Every later exchange goes through the half-size buffer `smX` ([pad(o)][CG]), one sequence at a
+// time, so that the load stays in flight for the rest of the tile.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int LOG2L, int LOGE, int LOGNS, int C>
+struct StagesAsync {
+    using G_ = Geometry<LOG2L, LOGE>;
+    static constexpr int E = G_::E;
+    static constexpr int CG = C / 2;
+    static constexpr int REM = LOG2L - LOGNS;
+    static constexpr int LOGR = REM >= LOGE ? LOGE : REM;
+    static constexpr int R = 1 << LOGR;
+    static constexpr int G = E / R;
+    static constexpr int Ns = 1 << LOGNS;
+    static constexpr bool LAST = (LOGNS + LOGR == LOG2L);
+    static constexpr int PADW = 1 << G_::LOGPAD;
+
+    // scatter sequence(s) [s0, s0+ns) of v to `sm` (point stride SI, sequence stride 1)
+    template <int SI, int S0, int NS>
+    static __device__ __forceinline__ void scatter(cplx<T> (&v)[2][E], int u, cplx<T>* sm) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            int j = u + g * G_::NT;
+            int jm = j & (Ns - 1);
+            int o0 = (j - jm) * R + jm;
+            cplx<T>* base;
+            int tstep;
+            if constexpr (Ns == 1 && R == PADW) { base = sm + (j * (R + 1)) * SI; tstep = SI; }
+            else if constexpr (Ns >= PADW) { base = sm + padded<G_::LOGPAD>(o0) * SI; tstep = (Ns + Ns / PADW) * SI; }
+            else { base = nullptr; tstep = 0; }
+#pragma unroll
+            for (int t = 0; t < R; ++t) {
+                cplx<T>* p;
+                if constexpr ((Ns == 1 && R == PADW) || Ns >= PADW) p = base + t * tstep;
+                else p = sm + padded<G_::LOGPAD>(o0 + t * Ns) * SI;
+#pragma unroll
+                for (int s = 0; s < NS; ++s) p[s] = v[S0 + s][g + t * G];
+            }
+        }
+    }
+    template <int SI, int S0, int NS>
+    static __device__ __forceinline__ void gather(cplx<T> (&v)[2][E], int u, cplx<T>* sm) {
+        cplx<T>* base = sm + padded<G_::LOGPAD>(u) * SI;
+#pragma unroll
+        for (int q = 0; q < E; ++q) {
+            cplx<T>* p;
+            if constexpr (G_::NT % PADW == 0) p = base + q * ((G_::NT + G_::NT / PADW) * SI);
+            else p = sm + padded<G_::LOGPAD>(u + q * G_::NT) * SI;
+#pragma unroll
+            for (int s = 0; s < NS; ++s) v[S0 + s][q] = p[s];
+        }
+    }
+
+    template <class Hook>
+    static __device__ __forceinline__ void run(cplx<T> (&v)[2][E], int u, cplx<T>* smL, cplx<T>* smX,
+                                               const cplx<T>* __restrict__ tw, Hook&& hook) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            int j = u + g * G_::NT;
+            int jm = j & (Ns - 1);
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                cplx<T> a[R];
+#pragma unroll
+                for (int t = 0; t < R; ++t) a[t] = v[s][g + t * G];
+                if constexpr (LOGNS > 0) apply_twiddles<T, R>(a, tw, jm * (G_::L / (Ns * R)));
+                Radix<T, R>::run(a);
+#pragma unroll
+                for (int t = 0; t < R; ++t) v[s][g + t * G] = a[t];
+            }
+        }
+        if constexpr (!LAST) {
+            if constexpr (LOGNS == 0) {
+                __syncthreads();            // every thread has taken its points of the landed tile out of smL
+                scatter<C, 0, 2>(v, u, smL);
+                __syncthreads();
+                gather<C, 0, 2>(v, u, smL);
+                fence_proxy_async_smem();   // generic-proxy accesses of smL are ordered before the bulk copy that re-fills it
+                __syncthreads();
+                hook();
+            } else {
+                scatter<CG, 0, 1>(v, u, smX);
+                __syncthreads();
+                gather<CG, 0, 1>(v, u, smX);
+                __syncthreads();
+                scatter<CG, 1, 1>(v, u, smX);
+                __syncthreads();
+                gather<CG, 1, 1>(v, u, smX);
+                __syncthreads();
+            }
+            StagesAsync<T, LOG2L, LOGE, LOGNS + LOGR, C>::run(v, u, smL, smX, tw, hook);
+        }
+    }
+};
+
 // hint the L2 to fetch a contiguous chunk (next tile / next rows) while the current one is transformed
 __device__ __forceinline__ void prefetch_l2_bulk(const void* gptr, unsigned bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");

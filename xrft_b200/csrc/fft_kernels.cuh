@@ -124,9 +124,9 @@ template <typename T> struct RowsC2C {
 // R2C split of the packed half-length transform: Z = FFT_M(x[2n] + i x[2n+1]), N = 2M:
 //   X[k] = E + w_N^k O,  E = (Z[k] + conj Z[M-k]) / 2,  O = -i (Z[k] - conj Z[M-k]) / 2,  k in [0, M]
 template <typename T>
-__device__ __forceinline__ cplx<T> r2c_split(cplx<T> zk, cplx<T> zm, cplx<T> w) {
-    cplx<T> e = mk<T>((T)0.5 * (zk.x + zm.x), (T)0.5 * (zk.y - zm.y));
-    cplx<T> d = mk<T>((T)0.5 * (zk.x - zm.x), (T)0.5 * (zk.y + zm.y));  // (Z[k] - conj Z[M-k]) / 2
+__device__ __forceinline__ cplx<T> r2c_split(cplx<T> zk, cplx<T> zm, cplx<T> w, T h = (T)0.5) {   // h = 1/2 (x a real row factor)
+    cplx<T> e = mk<T>(h * (zk.x + zm.x), h * (zk.y - zm.y));
+    cplx<T> d = mk<T>(h * (zk.x - zm.x), h * (zk.y + zm.y));  // (Z[k] - conj Z[M-k]) / 2
     cplx<T> o = mul_mi(d);
     return cadd(e, cmul(w, o));
 }
@@ -147,6 +147,11 @@ template <typename T> struct RowsR2CFused {
     const T* wy; const T* wx;            // window vectors (nullable)
     cplx<T>* out; int logC; long out_seq_stride;  // natural: stride per seq ; blocked: unused
     const cplx<T>* tw_r2c;               // exp(-2 pi i k / N), k in [0, M]
+    // row-line detrend (rows2_kernel): instead of the global plane (which needs a separate moments pass over the input),
+    // each row subtracts ITS OWN exactly representable line ph(j) = A0 + B j and records (A0, B, sum r, sum (j-jc) r) of
+    // the residual r; the difference between the row lines and the least-squares plane is added back in the column pass
+    // (ColsFused::fix), where it is a rank-2 update of the half-spectrum.  rowstats == nullptr: global-plane prologue.
+    float4* rowstats;
 
     template <int LOG2L, int SEQ> __device__ __forceinline__ void prefetch(long seq0, long nseq) const {
         constexpr unsigned row_bytes = (unsigned)(2u << LOG2L) * sizeof(T);
@@ -305,7 +310,7 @@ template <typename T> struct RowsR2CFused {
 // rows, interleaved in shared memory ([pad(o)][2]) so every exchange access is one 128-bit LDS/STS for both
 // rows and the stage twiddles are generated once per pair.  Needs Ny % (2*PAIRS) == 0 (rows of a CTA group are
 // consecutive rows of one item).
-template <typename T, int LOG2L, int LOGE, int PAIRS>
+template <typename T, int LOG2L, int LOGE, int PAIRS, bool ROWLINE>
 __global__ void __launch_bounds__((1 << (LOG2L - LOGE)) * PAIRS, min_blocks_for((1 << (LOG2L - LOGE)) * PAIRS))
 rows2_kernel(RowsR2CFused<T> io, const cplx<T>* __restrict__ tw, long nseq) {
     using G_ = Geometry<LOG2L, LOGE>;
@@ -331,6 +336,70 @@ rows2_kernel(RowsR2CFused<T> io, const cplx<T>* __restrict__ tw, long nseq) {
 #pragma unroll
             for (int q = 0; q < E; ++q) v[r][q] = p[q * NT];
         }
+        // ---- prologue (row-line variant): fp32 line subtract with exact line values, residual sums, window
+        if constexpr (ROWLINE) {
+            if constexpr (sizeof(T) == 4) {
+            constexpr int RL = NT < 32 ? NT : 32, WPP = NT / RL;      // lanes per reduction segment, partial slots per pair
+            float* part = reinterpret_cast<float*>(smem + PAIRS * PAIR_STRIDE);   // [PAIRS][WPP][4] partial sums, then [PAIRS][4] lines
+            float* lines = part + PAIRS * WPP * 4;
+            const long seq0 = grp * SEQ + 2 * pr;
+            const float jf0 = (float)(2 * u);
+            const float jc = 0.5f * (float)(Nx - 1);
+            const cplx<T>* pw = reinterpret_cast<const cplx<T>*>(io.wx) + u;
+            // residual sums per row: sx, sy (even / odd columns) and the q-weighted tx, ty; column j = 2u + 2 NT q (+1), so
+            //   sum r = sx + sy ;  sum (j - jc) r = (2u - jc) sx + (2u + 1 - jc) sy + 2 NT (tx + ty)
+            // The row's window factor w_y(i) is NOT applied here: the R2C split folds it into its 1/2 (store phase).
+            float A0[2], B[2], sx[2] = {0.f, 0.f}, sy[2] = {0.f, 0.f}, tx[2] = {0.f, 0.f}, ty[2] = {0.f, 0.f};
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const float* rowp = io.in + (seq0 + r) * io.in_row_stride;
+                const float x0 = __ldg(rowp), x1 = __ldg(rowp + (Nx - 1));
+                const float m = fmaxf(fabsf(x0), fabsf(x1));
+                A0[r] = 0.f; B[r] = 0.f;
+                if (m > 1e-30f && m < 1e30f) {
+                    // quantum Q = 2^(floor(log2 m) - 21): A0, B are multiples of Q and |A0 + B j| < 2^(floor(log2 m) + 2),
+                    // so every line value is representable: fmaf(B, j, A0) and (that + B) return them exactly
+                    const float p2 = __int_as_float(__float_as_int(m) & 0x7f800000);
+                    const float Q = p2 * 4.76837158203125e-07f, iQ = 2097152.0f / p2;
+                    A0[r] = rintf(x0 * iQ) * Q;
+                    B[r] = rintf((x1 - x0) * (1.0f / (float)(Nx - 1)) * iQ) * Q;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < E; ++q) {
+                const float jf = jf0 + (float)(2 * NT * q);
+                cplx<T> w = mk<T>(1, 1);
+                if (io.wx != nullptr) w = __ldg(pw + q * NT);
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    cplx<T> y = v[r][q];
+                    const float ph = fmaf(B[r], jf, A0[r]);
+                    y.x -= ph;
+                    y.y -= ph + B[r];
+                    sx[r] += y.x; sy[r] += y.y;
+                    tx[r] = fmaf((float)q, y.x, tx[r]);
+                    ty[r] = fmaf((float)q, y.y, ty[r]);
+                    y.x *= w.x; y.y *= w.y;
+                    v[r][q] = y;
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                float s2 = sx[r] + sy[r];
+                float t2 = fmaf(jf0 - jc, sx[r], fmaf(jf0 + 1.f - jc, sy[r], (float)(2 * NT) * (tx[r] + ty[r])));
+#pragma unroll
+                for (int off = RL / 2; off > 0; off >>= 1) {
+                    s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+                    t2 += __shfl_xor_sync(0xffffffffu, t2, off);
+                }
+                if ((u & (RL - 1)) == 0) {
+                    part[(pr * WPP + u / RL) * 4 + 2 * r] = s2;
+                    part[(pr * WPP + u / RL) * 4 + 2 * r + 1] = t2;
+                }
+                if (u == 0) { lines[pr * 4 + 2 * r] = A0[r]; lines[pr * 4 + 2 * r + 1] = B[r]; }
+            }
+            }
+        } else
         // ---- prologue: fp64 plane subtract, window
         {
             const long seq0 = grp * SEQ + 2 * pr;
@@ -384,6 +453,21 @@ rows2_kernel(RowsR2CFused<T> io, const cplx<T>* __restrict__ tw, long nseq) {
                 p[1] = v[1][g + t * G];
             }
         __syncthreads();
+        if constexpr (ROWLINE) {
+            if constexpr (sizeof(T) == 4) {
+                // the partial sums became visible at the barrier above; one thread per row folds them
+                constexpr int RL = NT < 32 ? NT : 32, WPP = NT / RL;
+                const float* part = reinterpret_cast<const float*>(smem + PAIRS * PAIR_STRIDE);
+                const float* lines = part + PAIRS * WPP * 4;
+                if (threadIdx.x < SEQ) {
+                    const int p_ = threadIdx.x >> 1, r_ = threadIdx.x & 1;
+                    float a = 0.f, b_ = 0.f;
+#pragma unroll
+                    for (int w = 0; w < WPP; ++w) { a += part[(p_ * WPP + w) * 4 + 2 * r_]; b_ += part[(p_ * WPP + w) * 4 + 2 * r_ + 1]; }
+                    io.rowstats[grp * SEQ + threadIdx.x] = make_float4(lines[p_ * 4 + 2 * r_], lines[p_ * 4 + 2 * r_ + 1], a, b_);
+                }
+            }
+        }
         // ---- store_b: R2C split + blocked store; thread -> (tile t, row s2, column c), c fastest
         {
             const int tstep = NTHR >> (logC + LOGSEQ);
@@ -393,6 +477,9 @@ rows2_kernel(RowsR2CFused<T> io, const cplx<T>* __restrict__ tw, long nseq) {
             const long b = seq2 >> io.logNy;
             const int iy = (int)(seq2 & (Ny - 1));
             const cplx<T>* smr = smem + (s2 >> 1) * PAIR_STRIDE + (s2 & 1);
+            // row-line variant: the row's window factor w_y(iy) rides on the 1/2 of the split
+            T hrow = (T)0.5;
+            if constexpr (ROWLINE) { if (io.wy != nullptr) hrow *= io.wy[iy]; }
             if (tstep >= 1 && ((tstep << logC) % PADW) == 0 && M % (tstep << logC) == 0) {
                 const int KS = tstep << logC, KSP2 = 2 * (KS + KS / PADW);
                 const int t0 = threadIdx.x >> (logC + LOGSEQ);
@@ -403,18 +490,18 @@ rows2_kernel(RowsR2CFused<T> io, const cplx<T>* __restrict__ tw, long nseq) {
                 const cplx<T>* pmr = smr + 2 * padded<G_::LOGPAD>((M - k0) & (M - 1));
                 const cplx<T>* ptw = io.tw_r2c + k0;
                 const int nsweep = M / KS;
-                *po = r2c_split<T>(*pk, *pmr, __ldg(ptw));
+                *po = r2c_split<T>(*pk, *pmr, __ldg(ptw), hrow);
                 pmr = smr + 2 * padded<G_::LOGPAD>(M - k0 - KS > 0 ? M - k0 - KS : 0);
                 pk += KSP2; ptw += KS; po += ostep;
 #pragma unroll 4
                 for (int i = 1; i < nsweep; ++i) {
-                    *po = r2c_split<T>(*pk, *pmr, __ldg(ptw));
+                    *po = r2c_split<T>(*pk, *pmr, __ldg(ptw), hrow);
                     pk += KSP2; pmr -= KSP2; ptw += KS; po += ostep;
                 }
                 if (t0 == 0) {
                     cplx<T> z0 = smr[0];
                     cplx<T>* pl = io.out + (((b * ntile + (M >> logC)) << io.logNy) + iy) * C + c;
-                    *pl = (c == 0) ? mk<T>(z0.x - z0.y, 0) : mk<T>(0, 0);
+                    *pl = (c == 0) ? mk<T>(((T)2 * hrow) * (z0.x - z0.y), 0) : mk<T>(0, 0);
                 }
             } else {
                 for (int w = threadIdx.x; w < ntile * SEQ * C; w += NTHR) {
@@ -427,7 +514,9 @@ rows2_kernel(RowsR2CFused<T> io, const cplx<T>* __restrict__ tw, long nseq) {
                     const int k = (t << logC) + c2;
                     const cplx<T>* sr = smem + (s3 >> 1) * PAIR_STRIDE + (s3 & 1);
                     cplx<T> r = mk<T>(0, 0);
-                    if (k <= M) r = r2c_split<T>(sr[2 * padded<G_::LOGPAD>(k & (M - 1))], sr[2 * padded<G_::LOGPAD>((M - k) & (M - 1))], __ldg(io.tw_r2c + k));
+                    T h3 = (T)0.5;
+                    if constexpr (ROWLINE) { if (io.wy != nullptr) h3 *= io.wy[iy3]; }
+                    if (k <= M) r = r2c_split<T>(sr[2 * padded<G_::LOGPAD>(k & (M - 1))], sr[2 * padded<G_::LOGPAD>((M - k) & (M - 1))], __ldg(io.tw_r2c + k), h3);
                     io.out[(((b3 * ntile + t) << io.logNy) + iy3) * C + c2] = r;
                 }
             }
@@ -507,6 +596,11 @@ cols_kernel(const __grid_constant__ IO io, const cplx<T>* __restrict__ tw, long 
         const long nxt = tile + gridDim.x;
         if (threadIdx.x == 0 && nxt + gridDim.x < ntiles) io.template prefetch<LOG2L, C>(nxt + gridDim.x);
         io.tma_reads_done();  // staging buffer (aliases the exchange buffer) may be overwritten from here on
+        {
+            cplx<T> ag_[E];
+            io.template fix_fetch<LOG2L, LOGE>(tile, u, ag_);
+            io.template fix_apply<LOG2L, LOGE, C, V>(tile, cg, ag_, v);
+        }
         block_fft<T, LOG2L, LOGE, V, C>(v, u, sm, 1, tw);
         io.template store_a<LOG2L, LOGE, C, V>(tile, u, cg, v, smem);
         if (nxt < ntiles) io.template load<LOG2L, LOGE, C, V>(nxt, u, cg, v, 0);
@@ -540,6 +634,61 @@ cols2f_kernel(const __grid_constant__ IO io, const cplx<T>* __restrict__ tw, lon
     }
 }
 
+// Asynchronous variant of cols_kernel for tiles that are ONE contiguous chunk of global memory (the blocked
+// intermediate): the next tile is brought into shared memory by bulk copies (TMA engine) that stay in flight while
+// the current tile is transformed and stored, instead of by register loads issued just before the store phase.
+// Shared memory: landing buffer L [LPAD][C] (also exchange #0), half-size buffer X [LPAD][C/2] (later exchanges,
+// one register sequence at a time, and the epilogue staging), one mbarrier, then the IO's histogram.
+template <typename T, int LOG2L, int LOGE, int C, class IO>
+__global__ void __launch_bounds__((1 << (LOG2L - LOGE)) * (C / 2), min_blocks_for((1 << (LOG2L - LOGE)) * (C / 2)))
+cols_async_kernel(const __grid_constant__ IO io, const cplx<T>* __restrict__ tw, long ntiles) {
+    using G_ = Geometry<LOG2L, LOGE>;
+    constexpr int E = G_::E, CG = C / 2, NT = G_::NT, L = 1 << LOG2L, NTHR = NT * CG;
+    constexpr unsigned TILE_BYTES = (unsigned)(L * C * sizeof(cplx<T>));
+    constexpr unsigned PIECE = TILE_BYTES > 32768u ? 32768u : TILE_BYTES;
+    static_assert(LOG2L > LOGE, "needs at least one exchange");
+    static_assert(TILE_BYTES % PIECE == 0 && PIECE % 16 == 0, "bulk copies are multiples of 16 bytes");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    cplx<T>* smL = reinterpret_cast<cplx<T>*>(smem_raw);
+    cplx<T>* smX = smL + G_::LPAD * C;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smX + G_::LPAD * CG);
+    const int cg = threadIdx.x % CG, u = threadIdx.x / CG;
+    if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_init_fence(); }
+    io.template init<LOG2L, LOGE, C, 2>(smX);   // ends with a barrier when there is a histogram
+    __syncthreads();
+    auto issue = [&](long tile) {
+        const char* src = reinterpret_cast<const char*>(io.template tile_src<LOG2L, C>(tile));
+        mbar_expect_tx(bar, TILE_BYTES);
+#pragma unroll
+        for (unsigned off = 0; off < TILE_BYTES; off += PIECE) bulk_load_g2s(reinterpret_cast<char*>(smL) + off, src + off, PIECE, bar);
+    };
+    if (threadIdx.x == 0 && (long)blockIdx.x < ntiles) issue((long)blockIdx.x);
+    unsigned phase = 0;
+    for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long nxt = tile + gridDim.x;
+        cplx<T> ag_[E];
+        io.template fix_fetch<LOG2L, LOGE>(tile, u, ag_);   // issued before the wait: their latency hides behind it
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+        cplx<T> v[2][E];
+        {
+            const cplx<T>* pl = smL + u * C + cg * 2;
+#pragma unroll
+            for (int q = 0; q < E; ++q) {
+                v[0][q] = pl[q * (NT * C)];
+                v[1][q] = pl[q * (NT * C) + 1];
+            }
+        }
+        io.template fix_apply<LOG2L, LOGE, C, 2>(tile, cg, ag_, v);
+        io.tma_reads_done();  // asynchronous stores of the previous tile have finished reading the staging buffer X
+        StagesAsync<T, LOG2L, LOGE, 0, C>::run(v, u, smL + cg * 2, smX + cg, tw,
+                                               [&]() { if (threadIdx.x == 0 && nxt < ntiles) issue(nxt); });
+        io.template store_a<LOG2L, LOGE, C, 2>(tile, u, cg, v, smX);
+        io.template store_b<LOG2L, LOGE, C, NTHR>(tile, smX);
+    }
+    io.tma_drain();
+}
+
 // ---- plain strided C2C on a [A][L][B] row-major view (in-place safe) ---------------------------
 template <typename T> struct ColsC2C {
     static constexpr bool kTwoFields = false;
@@ -550,6 +699,9 @@ template <typename T> struct ColsC2C {
     template <int LOG2L, int LOGE, int C, int V> __device__ __forceinline__ void init(cplx<T>*) const {}
     __device__ __forceinline__ void tma_reads_done() const {}
     __device__ __forceinline__ void tma_drain() const {}
+    template <int LOG2L, int LOGE> __device__ __forceinline__ void fix_fetch(long, int, cplx<T> (&)[1 << LOGE]) const {}
+    template <int LOG2L, int LOGE, int C, int V>
+    __device__ __forceinline__ void fix_apply(long, int, const cplx<T> (&)[1 << LOGE], cplx<T> (&)[V][1 << LOGE]) const {}
 
     template <int LOG2L, int LOGE, int C, int V>
     __device__ __forceinline__ void load(long tile, int u, int cg, cplx<T> (&v)[V][1 << LOGE], int) const {
@@ -616,6 +768,8 @@ struct EpilogueDesc {
     int use_tma;           // POWER: write the direct cells with TMA tensor stores (tmap describes out as [rows][W] float)
     int tma_box_rows;      // rows per TMA box (<= 256, divides Ny/2 so a box never straddles the fftshift wrap)
     int l2_hints;          // 1: evict-first tile loads / evict-last row-segment stores
+    const void* fix_ag;    // row-line detrend completion (see ColsFused::ag / wj); nullptr = none
+    const void* fix_wj;
     int lut_symmetric;     // bins: lut[-ky][-kx] == lut[ky][kx] for every cell (true for radial bins): mirror cells reuse the bin
 };
 
@@ -637,15 +791,22 @@ template <typename T, int MODE> struct ColsFused {
     // inside the fp32 tolerance); the cross-tile / cross-item accumulation in global memory is fp64
     using HistT = T;
     const cplx<T>* in1; const cplx<T>* in2; int ntile; EpilogueDesc d;
+    int hist_off;                  // bins modes: byte offset of the CTA histogram from the staging-buffer base (set by the launcher)
+    // row-line detrend completion (single-field modes): the row pass subtracted per-row lines; the remaining
+    // w_y(i) * (alpha_i + gamma_i (j - jc)) transforms along x to  A_i * What(kx) + G_i * Jhat(kx):
+    //   ag[b][i] = (A_i, G_i)   (real pair per row, rowline_fix_kernel) ;  wj[2 kx], wj[2 kx + 1] = What(kx), Jhat(kx)
+    const cplx<T>* ag; const cplx<T>* wj;
     alignas(64) CUtensorMap tmap;  // only read when d.use_tma
 
     template <int LOG2L, int LOGE, int C, int V> static constexpr int hist_offset_bytes() {
         using G_ = Geometry<LOG2L, LOGE>;
         return (G_::LPAD * C * (kTwoFields ? 2 : 1)) * (int)sizeof(cplx<T>);
     }
+    // the tile as one contiguous chunk of global memory (single-field modes; cols_async_kernel)
+    template <int LOG2L, int C> __device__ __forceinline__ const cplx<T>* tile_src(long tile) const { return in1 + tile * (long)(1 << LOG2L) * C; }
     template <int LOG2L, int LOGE, int C, int V> __device__ __forceinline__ void init(cplx<T>* smem) const {
         if constexpr (kBins) {
-            HistT* hist = reinterpret_cast<HistT*>(reinterpret_cast<char*>(smem) + hist_offset_bytes<LOG2L, LOGE, C, 1>());
+            HistT* hist = reinterpret_cast<HistT*>(reinterpret_cast<char*>(smem) + hist_off);
             for (int i = threadIdx.x; i < d.nbins * (kCplxStage ? 2 : 1); i += blockDim.x) hist[i] = 0;
             __syncthreads();
         }
@@ -688,6 +849,33 @@ template <typename T, int MODE> struct ColsFused {
                 for (int vv = 0; vv < V; ++vv) v[vv][q] = p[q * (NT * C) + vv];
             }
         }
+    }
+
+    // add the row-line completion to the freshly loaded tile (rows u + q NT, columns cg V + vv); `a` holds ag of those rows
+    template <int LOG2L, int LOGE>
+    __device__ __forceinline__ void fix_fetch(long tile, int u, cplx<T> (&a)[1 << LOGE]) const {
+        constexpr int NT = Geometry<LOG2L, LOGE>::NT;
+        if (ag == nullptr) return;
+        const long b = tile / ntile;
+        const cplx<T>* pa = ag + (b << LOG2L) + u;
+#pragma unroll
+        for (int q = 0; q < (1 << LOGE); ++q) a[q] = __ldg(pa + q * NT);
+    }
+    template <int LOG2L, int LOGE, int C, int V>
+    __device__ __forceinline__ void fix_apply(long tile, int cg, const cplx<T> (&a)[1 << LOGE], cplx<T> (&v)[V][1 << LOGE]) const {
+        if (ag == nullptr) return;
+        const long b = tile / ntile;
+        const int kx0 = (int)(tile - b * ntile) * C + cg * V;
+        cplx<T> W[V], J[V];
+#pragma unroll
+        for (int vv = 0; vv < V; ++vv) { W[vv] = __ldg(wj + 2 * (kx0 + vv)); J[vv] = __ldg(wj + 2 * (kx0 + vv) + 1); }
+#pragma unroll
+        for (int q = 0; q < (1 << LOGE); ++q)
+#pragma unroll
+            for (int vv = 0; vv < V; ++vv) {
+                v[vv][q].x += a[q].x * W[vv].x + a[q].y * J[vv].x;
+                v[vv][q].y += a[q].x * W[vv].y + a[q].y * J[vv].y;
+            }
     }
 
     // two-field modes: thread (u, c) loads column c of both fields
@@ -811,7 +999,7 @@ template <typename T, int MODE> struct ColsFused {
         const int ox0 = (kx0 + sx) & (Nx - 1);  // direct cells: ox0 + c (no wrap inside an aligned tile)
         OutT* outb = kBins ? nullptr : reinterpret_cast<OutT*>(d.out) + b * (long)Ny * W;
         const bool whole = (kx0 + C - 1 <= M);
-        HistT* hist = reinterpret_cast<HistT*>(reinterpret_cast<char*>(smem) + hist_offset_bytes<LOG2L, LOGE, C, 1>());
+        HistT* hist = reinterpret_cast<HistT*>(reinterpret_cast<char*>(smem) + hist_off);
         constexpr int ROW_ITERS = (Ny + NTHR - 1) / NTHR;
 #pragma unroll 4
         for (int it = 0; it < ROW_ITERS; ++it) {

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stddef.h>
+#include <stdlib.h>
 #include "fft_kernels.cuh"
 
 namespace xrftb {
@@ -28,6 +29,14 @@ template <typename T> inline int cols_tile_width(int log2L, bool two_fields) {
     if (c > TypeCfg<T>::CMAX) c = TypeCfg<T>::CMAX;
     if (two_fields) c >>= 1;
     return c;  // 0 => unsupported
+}
+
+// the two-rows-per-thread row kernel (float32, blocked output) handles half lengths 2^7..2^12 with 2^(12 - log2M) row pairs
+// per CTA; the 2 * pairs rows of a CTA must be consecutive rows of one item
+inline bool rows2_eligible(int log2M, int logNy) {
+    static int v2 = -1;
+    if (v2 < 0) { const char* e = getenv("XRFTB_ROWS_V2"); v2 = e ? atoi(e) : 1; }
+    return v2 > 0 && log2M >= 7 && log2M <= 12 && logNy >= (12 - log2M) + 1;
 }
 
 template <typename T> int rows_c2c(const cplx<T>* in, cplx<T>* out, int log2L, long nseq, long in_stride, long out_stride,

@@ -47,13 +47,15 @@ static int launch_rows(const IO& io, long nseq, cudaStream_t st) {
     return check_launch("rows_kernel");
 }
 
-template <typename T, int LOG2L, int PAIRS>
+template <typename T, int LOG2L, int PAIRS, bool ROWLINE>
 static int launch_rows2(const RowsR2CFused<T>& io, long nseq, cudaStream_t st) {
     constexpr int LOGE = cmin(TypeCfg<T>::LOGE, LOG2L);
     using G_ = Geometry<LOG2L, LOGE>;
-    auto kern = rows2_kernel<T, LOG2L, LOGE, PAIRS>;
+    auto kern = rows2_kernel<T, LOG2L, LOGE, PAIRS, ROWLINE>;
     constexpr int threads = G_::NT * PAIRS;
-    constexpr size_t smem = (size_t)PAIRS * (2 * G_::LPAD + 8) * sizeof(cplx<T>);
+    // + row-line partial sums [PAIRS][WPP][4] and lines [PAIRS][4] (floats)
+    constexpr int WPP = G_::NT < 32 ? 1 : G_::NT / 32;
+    constexpr size_t smem = (size_t)PAIRS * (2 * G_::LPAD + 8) * sizeof(cplx<T>) + (size_t)PAIRS * (WPP + 1) * 4 * sizeof(float);
     static int occ = -1;
     if (int rc = prepare_kernel(kern, threads, smem, &occ)) return rc;
     const cplx<T>* tw = twiddle_fft<T>(LOG2L);
@@ -87,6 +89,29 @@ static int launch_cols(const IO& io, long ntiles, cudaStream_t st, size_t extra_
     if (grid < 1) return 0;
     kern<<<(unsigned)grid, threads, smem, st>>>(io, tw, ntiles);
     return check_launch("cols_kernel");
+}
+
+// asynchronous (bulk-copy fed) column pass: landing buffer + half-size exchange buffer + mbarrier (+ histogram)
+template <typename T, int LOG2L, int C, class IO>
+static int launch_cols_async(IO io, long ntiles, cudaStream_t st, size_t extra_smem = 0) {
+    constexpr int LOGE = cmin(TypeCfg<T>::LOGE, LOG2L);
+    using G_ = Geometry<LOG2L, LOGE>;
+    auto kern = cols_async_kernel<T, LOG2L, LOGE, C, IO>;
+    constexpr int threads = G_::NT * (C / 2);
+    constexpr size_t smem_fixed = (size_t)G_::LPAD * (C + C / 2) * sizeof(cplx<T>) + 16;
+    constexpr size_t smem_cap = smem_fixed + (IO::kBins ? (size_t)kMaxFusedBins * 2 * sizeof(double) : 0);
+    const size_t smem = smem_fixed + extra_smem;
+    if (smem > smem_cap) { set_error("launch_cols_async: too many bins for the fused path"); return -2; }
+    io.hist_off = (int)((size_t)G_::LPAD * (C / 2) * sizeof(cplx<T>) + 16);   // relative to the X buffer
+    static int occ = -1;
+    if (int rc = prepare_kernel(kern, threads, smem_cap, &occ)) return rc;
+    const cplx<T>* tw = twiddle_fft<T>(LOG2L);
+    if (!tw) return -3;
+    long grid = (long)sm_count() * occ;
+    if (grid > ntiles) grid = ntiles;
+    if (grid < 1) return 0;
+    kern<<<(unsigned)grid, threads, smem, st>>>(io, tw, ntiles);
+    return check_launch("cols_async_kernel");
 }
 
 }  // namespace xrftb

@@ -29,19 +29,19 @@ int rows_r2c(RowsR2CFused<T> io, int log2M, long nseq, cudaStream_t st) {
     io.tw_r2c = twiddle_r2c<T>(log2M + 1);
     if (!io.tw_r2c) return -3;
     // hot 2-D path: two rows per thread (float32, blocked output, enough rows per item)
-    static int v2 = -1;
-    if (v2 < 0) { const char* e = getenv("XRFTB_ROWS_V2"); v2 = e ? atoi(e) : 1; }
     if constexpr (sizeof(T) == 4) {
         // PAIRS row pairs per CTA so that a CTA has 256 threads; its 2*PAIRS rows must be consecutive rows of one item
-        if (v2 > 0 && io.logC >= 0 && io.in_row_stride == (2L << log2M)) {
+        if (rows2_eligible(log2M, io.logNy) && io.logC >= 0 && io.in_row_stride == (2L << log2M)) {
             switch (log2M) {
-#define Z(K, P) case K: if (io.logNy >= ilog2c(2 * P) && nseq % (2 * P) == 0) return launch_rows2<T, K, P>(io, nseq, st); break;
+#define Z(K, P) case K: if (io.logNy >= ilog2c(2 * P) && nseq % (2 * P) == 0) \
+                    return io.rowstats ? launch_rows2<T, K, P, true>(io, nseq, st) : launch_rows2<T, K, P, false>(io, nseq, st); break;
                 Z(7, 32) Z(8, 16) Z(9, 8) Z(10, 4) Z(11, 2) Z(12, 1)
 #undef Z
                 default: break;
             }
         }
     }
+    if (io.rowstats != nullptr) { set_error("rows_r2c: row-line detrend needs the two-rows-per-thread kernel"); return -2; }
     // tuning knob (experiments): rows per CTA of the fused pass for the large sizes
     static int seq_override = -1;
     if (seq_override < 0) { const char* e = getenv("XRFTB_ROWS_SEQ"); seq_override = e ? atoi(e) : 0; }
