@@ -7,6 +7,7 @@ ny = sys.argv[1] if len(sys.argv) > 1 else "4096"
 T = sys.argv[2] if len(sys.argv) > 2 else "64"
 reps = sys.argv[3] if len(sys.argv) > 3 else "3"
 VARIANTS = [
+    ("columns-first (moments + cols R2C + rows C2C|power, no mirror)", {"XRFTB_COLS_FIRST": "1"}),
     ("register-prefetch cols + moments pass", {"XRFTB_COLS_ASYNC": "0", "XRFTB_ROWLINE": "0"}),
     ("bulk-copy cols      + moments pass", {"XRFTB_COLS_ASYNC": "1", "XRFTB_ROWLINE": "0"}),
     ("register-prefetch cols + row-line detrend", {"XRFTB_COLS_ASYNC": "0", "XRFTB_ROWLINE": "1"}),

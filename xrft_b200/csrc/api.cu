@@ -1014,8 +1014,66 @@ template <typename T> static size_t rowline_fixed_bytes(int nx, int C) {
 }
 static bool rowline_enabled() {
     static int on = -1;
-    if (on < 0) { const char* e = getenv("XRFTB_ROWLINE"); on = e ? atoi(e) : 0; }
+    if (on < 0) { const char* e = getenv("XRFTB_ROWLINE"); on = e ? atoi(e) : 1; }
     return on != 0;
+}
+
+// "columns first" order (see ColsR2CPack / RowsC2CPower): eligible for the full-width power spectrum
+static bool colsfirst_enabled() {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("XRFTB_COLS_FIRST"); on = e ? atoi(e) : 0; }
+    return on != 0;
+}
+template <typename T> static bool colsfirst_eligible(int mode, int keep_half, const void* weight_x, int ly, int lx, int nx) {
+    if (mode != XRFTB_EPI_POWER || keep_half || weight_x) return false;
+    const int C = cols_tile_width<T>(ly, false);
+    return C >= 1 && ly >= 1 && ly <= TypeCfg<T>::MAX_COLS_LOG2 && lx >= 1 && lx <= TypeCfg<T>::MAX_ROWS_LOG2 && nx >= 2 * C;
+}
+template <typename T> static size_t colsfirst_item_bytes(int ny, int nx) { return (size_t)(ny / 2 + 1) * nx * sizeof(cplx<T>); }
+
+template <typename T>
+static int spectrum2d_colsfirst(const xrftb_spectrum2d_desc& q, int ly, int lx, cudaStream_t st) {
+    using C_ = cplx<T>;
+    const int C = cols_tile_width<T>(ly, false);
+    const int H = q.ny / 2 + 1;
+    const size_t per_item = colsfirst_item_bytes<T>(q.ny, q.nx);
+    const size_t mom_bytes = (size_t)q.batch * 4 * sizeof(double);
+    const size_t mom_region = align256(mom_bytes);
+    if (!q.work || q.work_bytes < mom_region + per_item) { set_error("spectrum2d: workspace too small (%zu < %zu)", q.work_bytes, mom_region + per_item); return XRFTB_EWORKSPACE; }
+    long bchunk = (long)((q.work_bytes - mom_region) / per_item);
+    if (bchunk > q.batch) bchunk = q.batch;
+    { const long nch = (q.batch + bchunk - 1) / bchunk; bchunk = (q.batch + nch - 1) / nch; }
+    double* mom = reinterpret_cast<double*>(q.work);
+    C_* interm = reinterpret_cast<C_*>(reinterpret_cast<char*>(q.work) + mom_region);
+    const long item = (long)q.ny * q.nx;
+    const T* in = reinterpret_cast<const T*>(q.in1);
+    if (q.detrend) {
+        cudaError_t e = cudaMemsetAsync(mom, 0, mom_bytes, st);
+        if (e != cudaSuccess) { set_error("memset: %s", cudaGetErrorString(e)); return XRFTB_ECUDA; }
+        ProfScope ps_(PROF_MOMENTS, st);
+        int chunks = (int)((8L * sm_count() + q.batch - 1) / q.batch);
+        if (chunks < 1) chunks = 1;
+        if (chunks > q.ny) chunks = q.ny;
+        dim3 grid(chunks, (unsigned)q.batch);
+        moments_kernel<T><<<grid, 256, 0, st>>>(in, mom, 1, q.ny, q.nx, chunks);
+        if (int rc = check_launch("moments_kernel")) return rc;
+    }
+    const int tiles_per_item = q.nx / (2 * C);
+    for (long b0 = 0; b0 < q.batch; b0 += bchunk) {
+        const long nb = (q.batch - b0 < bchunk) ? q.batch - b0 : bchunk;
+        {
+            ColsR2CPack<T> io{in + b0 * item, q.nx, tiles_per_item, q.detrend, mom + b0 * 4,
+                              reinterpret_cast<const T*>(q.win_y), reinterpret_cast<const T*>(q.win_x), interm};
+            ProfScope ps_(PROF_COLS, st);
+            if (int rc = cols_r2c_pack<T>(io, ly, nb * tiles_per_item, st)) return rc;
+        }
+        {
+            RowsC2CPower<T> io{interm, reinterpret_cast<T*>(q.out) + b0 * item, ly, H, q.shift_y, q.shift_x, (T)q.scale};
+            ProfScope ps_(PROF_ROWS, st);
+            if (int rc = rows_c2c_power<T>(io, lx, nb * H, st)) return rc;
+        }
+    }
+    return 0;
 }
 
 template <typename T>
@@ -1025,6 +1083,7 @@ static int spectrum2d_impl(const xrftb_spectrum2d_desc& q, cudaStream_t st) {
     if (ly < 1 || lx < 2) { set_error("spectrum2d: ny, nx must be powers of two (ny>=2, nx>=4), got %d x %d", q.ny, q.nx); return XRFTB_EUNSUPPORTED; }
     const bool two = (q.mode == XRFTB_EPI_CROSS || q.mode == XRFTB_EPI_PHASE || q.mode == XRFTB_EPI_BINS_CROSS);
     if (two && !q.in2) { set_error("spectrum2d: mode %d needs in2", q.mode); return XRFTB_EINVAL; }
+    if (colsfirst_enabled() && colsfirst_eligible<T>(q.mode, q.keep_half, q.weight_x, ly, lx, q.nx)) return spectrum2d_colsfirst<T>(q, ly, lx, st);
     const int C = cols_tile_width<T>(ly, two);
     if (C < 1 || ly > TypeCfg<T>::MAX_COLS_LOG2 || lx - 1 > TypeCfg<T>::MAX_ROWS_LOG2) { set_error("spectrum2d: size %d x %d unsupported", q.ny, q.nx); return XRFTB_EUNSUPPORTED; }
     if (q.shift_x && q.keep_half) { set_error("spectrum2d: shift_x is incompatible with keep_half"); return XRFTB_EINVAL; }
@@ -1342,7 +1401,12 @@ size_t xrftb_spectrum2d_workspace(int dtype, int ny, int nx, int two_fields, int
     // moments region is sized for up to 65536 items x 2 fields; row-line detrend tables (float32, one field) ride along
     const size_t rl_fixed = (dtype == XRFTB_F32 && !two_fields) ? rowline_fixed_bytes<float>(nx, C) : 0;
     const size_t rl_item = (dtype == XRFTB_F32 && !two_fields) ? rowline_item_bytes<float>(ny) : 0;
-    return ((size_t)65536 * 2 * 4 * sizeof(double)) + rl_fixed + (per_item * fields + rl_item) * (size_t)batch_in_flight + 1024;
+    size_t item_total = per_item * fields + rl_item;
+    if (!two_fields) {   // the columns-first order keeps [ny/2+1][nx] complex per item
+        const size_t cf = dtype == XRFTB_F32 ? colsfirst_item_bytes<float>(ny, nx) : colsfirst_item_bytes<double>(ny, nx);
+        if (cf > item_total) item_total = cf;
+    }
+    return ((size_t)65536 * 2 * 4 * sizeof(double)) + rl_fixed + item_total * (size_t)batch_in_flight + 1024;
 }
 
 int xrftb_spectrum2d(const xrftb_spectrum2d_desc* q, void* stream) {

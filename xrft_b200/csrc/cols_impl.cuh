@@ -30,6 +30,18 @@ int cols_c2c(const cplx<T>* in, cplx<T>* out, int log2L, long A, long B, int inv
     return -2;
 }
 
+template <typename T>
+int cols_r2c_pack(const ColsR2CPack<T>& io, int log2L, long ntiles, cudaStream_t st) {
+    switch (log2L) {
+#define X(K) case K: if constexpr (TileC<T, K, false>::value >= 1) return launch_cols<T, K, TileC<T, K, false>::value>(io, ntiles, st); break;
+        XRFTB_COLS_CASES(X)
+#undef X
+        default: break;
+    }
+    set_error("cols_r2c_pack: unsupported length 2^%d", log2L);
+    return -2;
+}
+
 template <typename T, int K, int MODE>
 static int cols_fused_k(const cplx<T>* in1, const cplx<T>* in2, long ntiles_total, int ntile, const EpilogueDesc& d, const CUtensorMap* tmap, cudaStream_t st) {
     using IO = ColsFused<T, MODE>;
@@ -45,9 +57,11 @@ static int cols_fused_k(const cplx<T>* in1, const cplx<T>* in2, long ntiles_tota
         // real-valued single-field epilogues of the float32 path: bulk-copy fed variant (the staging buffer fits the
         // half-size exchange buffer).  XRFTB_COLS_ASYNC=0 selects the register-prefetch kernel.
         if constexpr (sizeof(T) == 4 && (MODE == EPI_POWER || MODE == EPI_BINS_POWER) && (K > TypeCfg<T>::LOGE) && C >= 2 && C % 2 == 0) {
+            // measured (profiles/README.md): wins where the epilogue stores are asynchronous too (TMA tensor stores, C >= 8);
+            // at C = 4 the 16-byte row-segment stores dominate and the extra exchange barriers cost more than the loads hide
             static int async_on = -1;
-            if (async_on < 0) { const char* e = getenv("XRFTB_COLS_ASYNC"); async_on = e ? atoi(e) : 0; }
-            if (async_on) return launch_cols_async<T, K, C>(io, ntiles_total, st, extra);
+            if (async_on < 0) { const char* e = getenv("XRFTB_COLS_ASYNC"); async_on = e ? atoi(e) : 2; }
+            if (async_on == 1 || (async_on == 2 && C >= 8)) return launch_cols_async<T, K, C>(io, ntiles_total, st, extra);
         }
         return launch_cols<T, K, C>(io, ntiles_total, st, extra);
     }

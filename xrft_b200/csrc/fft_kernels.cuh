@@ -599,7 +599,7 @@ cols_kernel(const __grid_constant__ IO io, const cplx<T>* __restrict__ tw, long 
         {
             cplx<T> ag_[E];
             io.template fix_fetch<LOG2L, LOGE>(tile, u, ag_);
-            io.template fix_apply<LOG2L, LOGE, C, V>(tile, cg, ag_, v);
+            io.template fix_apply<LOG2L, LOGE, C, V>(tile, u, cg, ag_, v);
         }
         block_fft<T, LOG2L, LOGE, V, C>(v, u, sm, 1, tw);
         io.template store_a<LOG2L, LOGE, C, V>(tile, u, cg, v, smem);
@@ -679,7 +679,7 @@ cols_async_kernel(const __grid_constant__ IO io, const cplx<T>* __restrict__ tw,
                 v[1][q] = pl[q * (NT * C) + 1];
             }
         }
-        io.template fix_apply<LOG2L, LOGE, C, 2>(tile, cg, ag_, v);
+        io.template fix_apply<LOG2L, LOGE, C, 2>(tile, u, cg, ag_, v);
         io.tma_reads_done();  // asynchronous stores of the previous tile have finished reading the staging buffer X
         StagesAsync<T, LOG2L, LOGE, 0, C>::run(v, u, smL + cg * 2, smX + cg, tw,
                                                [&]() { if (threadIdx.x == 0 && nxt < ntiles) issue(nxt); });
@@ -701,7 +701,7 @@ template <typename T> struct ColsC2C {
     __device__ __forceinline__ void tma_drain() const {}
     template <int LOG2L, int LOGE> __device__ __forceinline__ void fix_fetch(long, int, cplx<T> (&)[1 << LOGE]) const {}
     template <int LOG2L, int LOGE, int C, int V>
-    __device__ __forceinline__ void fix_apply(long, int, const cplx<T> (&)[1 << LOGE], cplx<T> (&)[V][1 << LOGE]) const {}
+    __device__ __forceinline__ void fix_apply(long, int, int, const cplx<T> (&)[1 << LOGE], cplx<T> (&)[V][1 << LOGE]) const {}
 
     template <int LOG2L, int LOGE, int C, int V>
     __device__ __forceinline__ void load(long tile, int u, int cg, cplx<T> (&v)[V][1 << LOGE], int) const {
@@ -744,6 +744,183 @@ template <typename T> struct ColsC2C {
                 }
             }
     }
+};
+
+// =============================================================================================
+// "columns first" order of the fused 2-D real transform (full-width real-valued epilogues: power spectrum).
+//   pass 1  cols_kernel<ColsR2CPack>  : FFT along y of the REAL input, two adjacent real columns packed into one complex
+//           sequence (re = column 2c, im = column 2c+1); detrend + window fused into the load; the two spectra are
+//           separated after the transform and rows ky in [0, Ny/2] of the half-spectrum are written row-major,
+//           [batch][Ny/2+1][Nx] complex, in 2C*8-byte segments.
+//   pass 2  rows_kernel<RowsC2CPower> : complex FFT along x of every half-spectrum row (contiguous), |F|^2 * scale,
+//           then the row is written twice, fully coalesced: to output row ky, and reversed to row -ky
+//           (out[-ky][-kx] = out[ky][kx] for real input).  No separate Hermitian mirror pass, no 16-byte scatter.
+// =============================================================================================
+template <typename T> struct ColsR2CPack {
+    static constexpr bool kTwoFields = false;
+    static constexpr bool kBins = false;
+    const T* in;            // [batch][Ny][Nx] real
+    int Nx;                 // row length (elements)
+    int tiles_per_item;     // Nx / (2 C)
+    int detrend;            // 0 none | 1 constant | 2 linear (global plane from `moments`)
+    const double* moments;  // [batch][4] : S, -, Sy, Sx (moments_kernel)
+    const T* wy; const T* wx;
+    cplx<T>* out;           // [batch][Ny/2+1][Nx]
+
+    template <int LOG2L, int C> __device__ __forceinline__ void prefetch(long) const {}
+    template <int LOG2L, int LOGE, int C, int V> __device__ __forceinline__ void init(cplx<T>*) const {}
+    __device__ __forceinline__ void tma_reads_done() const {}
+    __device__ __forceinline__ void tma_drain() const {}
+    template <int LOG2L, int LOGE> __device__ __forceinline__ void fix_fetch(long, int, cplx<T> (&)[1 << LOGE]) const {}
+
+    template <int LOG2L, int LOGE, int C, int V>
+    __device__ __forceinline__ void load(long tile, int u, int cg, cplx<T> (&v)[V][1 << LOGE], int) const {
+        constexpr int NT = Geometry<LOG2L, LOGE>::NT;
+        const long b = tile / tiles_per_item;
+        const int x0 = (int)(tile - b * tiles_per_item) * (2 * C) + cg * (2 * V);
+        const T* p = in + ((b << LOG2L) + u) * (long)Nx + x0;
+        const long qstep = (long)NT * Nx;
+#pragma unroll
+        for (int q = 0; q < (1 << LOGE); ++q) {
+            if constexpr (V == 2 && sizeof(T) == 4) {
+                const float4 x = *reinterpret_cast<const float4*>(p + q * qstep);
+                v[0][q] = mk<T>(x.x, x.y);
+                v[1][q] = mk<T>(x.z, x.w);
+            } else {
+#pragma unroll
+                for (int vv = 0; vv < V; ++vv) v[vv][q] = *reinterpret_cast<const cplx<T>*>(p + q * qstep + 2 * vv);
+            }
+        }
+    }
+    // detrend (fp64 plane) + window on the freshly loaded tile: rows u + q NT, real columns x0 + 2 vv (+1)
+    template <int LOG2L, int LOGE, int C, int V>
+    __device__ __forceinline__ void fix_apply(long tile, int u, int cg, const cplx<T> (&)[1 << LOGE], cplx<T> (&v)[V][1 << LOGE]) const {
+        constexpr int NT = Geometry<LOG2L, LOGE>::NT, Ny = 1 << LOG2L;
+        const long b = tile / tiles_per_item;
+        const int x0 = (int)(tile - b * tiles_per_item) * (2 * C) + cg * (2 * V);
+        double p0 = 0.0, cx = 0.0, cy = 0.0;
+        if (detrend) {
+            const double* m = moments + b * 4;
+            const double npts = (double)Ny * (double)Nx;
+            p0 = m[0] / npts;
+            if (detrend == 2) {
+                const double vy = (double)Nx * ((double)Ny * ((double)Ny * Ny - 1.0) / 12.0);
+                const double vx = (double)Ny * ((double)Nx * ((double)Nx * Nx - 1.0) / 12.0);
+                cy = Ny > 1 ? m[2] / vy : 0.0;
+                cx = m[3] / vx;
+                p0 += cy * ((double)u - 0.5 * (Ny - 1)) + cx * ((double)x0 - 0.5 * (Nx - 1));
+            }
+        }
+        const double pstep = cy * (double)NT;
+        T wxv[2 * V];
+#pragma unroll
+        for (int k = 0; k < 2 * V; ++k) wxv[k] = wx != nullptr ? __ldg(wx + x0 + k) : (T)1;
+#pragma unroll
+        for (int q = 0; q < (1 << LOGE); ++q) {
+            const T wrow = wy != nullptr ? __ldg(wy + u + q * NT) : (T)1;
+            const double pq = p0 + (double)q * pstep;
+#pragma unroll
+            for (int vv = 0; vv < V; ++vv) {
+                cplx<T> y = v[vv][q];
+                if (detrend) {
+                    y.x = (T)((double)y.x - (pq + cx * (double)(2 * vv)));
+                    y.y = (T)((double)y.y - (pq + cx * (double)(2 * vv + 1)));
+                }
+                y.x *= wxv[2 * vv] * wrow;
+                y.y *= wxv[2 * vv + 1] * wrow;
+                v[vv][q] = y;
+            }
+        }
+    }
+    // packed spectra Z -> staging [ky][C] (natural order)
+    template <int LOG2L, int LOGE, int C, int V>
+    __device__ __forceinline__ void store_a(long, int u, int cg, cplx<T> (&v)[V][1 << LOGE], cplx<T>* smem) const {
+        using G_ = Geometry<LOG2L, LOGE>;
+        constexpr int R = 1 << G_::LOGR_LAST, G = G_::E / R;
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+#pragma unroll
+            for (int t = 0; t < R; ++t) {
+                const int ky = final_index<LOG2L, LOGE>(u, g, t);
+#pragma unroll
+                for (int vv = 0; vv < V; ++vv) smem[ky * C + cg * V + vv] = v[vv][g + t * G];
+            }
+        __syncthreads();
+    }
+    // separate the two real columns of every packed column: A[k] = (Z[k] + conj Z[N-k]) / 2, B[k] = -i (Z[k] - conj Z[N-k]) / 2,
+    // rows k in [0, Ny/2]; one thread writes both spectra of one (k, packed column): 2*sizeof(cplx) contiguous bytes
+    template <int LOG2L, int LOGE, int C, int NTHR>
+    __device__ __forceinline__ void store_b(long tile, cplx<T>* smem) const {
+        constexpr int Ny = 1 << LOG2L, H = Ny / 2 + 1;
+        const long b = tile / tiles_per_item;
+        const int x0 = (int)(tile - b * tiles_per_item) * (2 * C);
+        cplx<T>* ob = out + (b * H) * (long)Nx + x0;
+        for (int idx = threadIdx.x; idx < H * C; idx += NTHR) {
+            const int ky = idx / C, c = idx - ky * C;
+            const cplx<T> za = smem[ky * C + c];
+            const cplx<T> zb = smem[((Ny - ky) & (Ny - 1)) * C + c];
+            const cplx<T> A = mk<T>((T)0.5 * (za.x + zb.x), (T)0.5 * (za.y - zb.y));
+            const cplx<T> B = mk<T>((T)0.5 * (za.y + zb.y), (T)0.5 * (zb.x - za.x));
+            cplx<T>* po = ob + (long)ky * Nx + 2 * c;
+            if constexpr (sizeof(T) == 4) {
+                *reinterpret_cast<float4*>(po) = make_float4(A.x, A.y, B.x, B.y);
+            } else {
+                po[0] = A; po[1] = B;
+            }
+        }
+        __syncthreads();
+    }
+};
+
+// pass 2: rows of the half-spectrum [batch][H][Nx] complex -> power spectrum rows ky and -ky of out [batch][Ny][Nx] real
+template <typename T> struct RowsC2CPower {
+    static constexpr int kSeqSkew = 0;
+    const cplx<T>* in; T* out; int logNy; int H; int shift_y, shift_x; T scale;
+
+    template <int LOG2L, int SEQ> __device__ __forceinline__ void prefetch(long seq0, long nseq) const {
+        constexpr unsigned row_bytes = (unsigned)((1u << LOG2L) * sizeof(cplx<T>));
+        if (seq0 + SEQ <= nseq) prefetch_l2_bulk(in + seq0 * (long)(1 << LOG2L), row_bytes * SEQ);
+    }
+    template <int LOG2L, int LOGE>
+    __device__ __forceinline__ void fetch(long seq, bool active, int u, cplx<T> (&raw)[1 << LOGE]) const {
+        constexpr int NT = Geometry<LOG2L, LOGE>::NT;
+        const cplx<T>* p = in + seq * (long)(1 << LOG2L) + u;
+#pragma unroll
+        for (int q = 0; q < (1 << LOGE); ++q) {
+            raw[q] = mk<T>(0, 0);
+            if (active) raw[q] = p[q * NT];
+        }
+    }
+    template <int LOG2L, int LOGE>
+    __device__ __forceinline__ void prologue(long, bool, int, cplx<T> (&raw)[1 << LOGE], cplx<T> (&v)[1 << LOGE]) const {
+#pragma unroll
+        for (int q = 0; q < (1 << LOGE); ++q) v[q] = raw[q];
+    }
+    template <int LOG2L, int LOGE, int SEQ>
+    __device__ __forceinline__ void store_a(long, long seq, bool active, int u, int, cplx<T> (&v)[1 << LOGE], cplx<T>*, int, long) const {
+        using G_ = Geometry<LOG2L, LOGE>;
+        constexpr int R = 1 << G_::LOGR_LAST, G = G_::E / R, Nx = 1 << LOG2L;
+        if (!active) return;
+        const int Ny = 1 << logNy;
+        const long b = seq / H;
+        const int ky = (int)(seq - b * H);
+        const int sy = shift_y ? Ny / 2 : 0, sx = shift_x ? Nx / 2 : 0;
+        T* rowd = out + ((b << logNy) + ((ky + sy) & (Ny - 1))) * (long)Nx;
+        T* rowm = out + ((b << logNy) + ((Ny - ky + sy) & (Ny - 1))) * (long)Nx;
+        const bool mirror = (ky != 0) && (2 * ky != Ny);   // rows 0 and Ny/2 are their own mirror image
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+#pragma unroll
+            for (int t = 0; t < R; ++t) {
+                const cplx<T> f = v[g + t * G];
+                const T val = (f.x * f.x + f.y * f.y) * scale;
+                const int kx = final_index<LOG2L, LOGE>(u, g, t);
+                rowd[(kx + sx) & (Nx - 1)] = val;
+                if (mirror) rowm[(Nx - kx + sx) & (Nx - 1)] = val;
+            }
+    }
+    template <int LOG2L, int LOGE, int SEQ>
+    __device__ __forceinline__ void store_b(long, long, bool, int, int, cplx<T> (&)[1 << LOGE], cplx<T>*, int, long) const {}
 };
 
 // ---- fused column pass of the 2-D real transform -------------------------------------------------
@@ -862,7 +1039,7 @@ template <typename T, int MODE> struct ColsFused {
         for (int q = 0; q < (1 << LOGE); ++q) a[q] = __ldg(pa + q * NT);
     }
     template <int LOG2L, int LOGE, int C, int V>
-    __device__ __forceinline__ void fix_apply(long tile, int cg, const cplx<T> (&a)[1 << LOGE], cplx<T> (&v)[V][1 << LOGE]) const {
+    __device__ __forceinline__ void fix_apply(long tile, int, int cg, const cplx<T> (&a)[1 << LOGE], cplx<T> (&v)[V][1 << LOGE]) const {
         if (ag == nullptr) return;
         const long b = tile / ntile;
         const int kx0 = (int)(tile - b * ntile) * C + cg * V;

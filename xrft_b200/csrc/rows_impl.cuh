@@ -66,6 +66,20 @@ int rows_r2c(RowsR2CFused<T> io, int log2M, long nseq, cudaStream_t st) {
 }
 
 template <typename T>
+int rows_c2c_power(const RowsC2CPower<T>& io, int log2L, long nseq, cudaStream_t st) {
+    switch (log2L) {
+#define X(K) case K: return launch_rows<T, K, rows_seq_generic<K, cmin(TypeCfg<T>::LOGE, K)>()>(io, nseq, st);
+        XRFTB_ROWS_CASES(X)
+#undef X
+        case 14:
+            if constexpr (TypeCfg<T>::MAX_ROWS_LOG2 >= 14) return launch_rows<T, 14, 1>(io, nseq, st);
+        default: break;
+    }
+    set_error("rows_c2c_power: unsupported length 2^%d", log2L);
+    return -2;
+}
+
+template <typename T>
 int rows_c2r(const cplx<T>* in, long in_stride, T* out, long out_stride, int log2M, long nseq, T scale, cudaStream_t st) {
     RowsC2R<T> io{in, in_stride, out, out_stride, scale, twiddle_r2c<T>(log2M + 1)};
     if (!io.tw_r2c) return -3;
