@@ -7,11 +7,11 @@ ny = sys.argv[1] if len(sys.argv) > 1 else "4096"
 T = sys.argv[2] if len(sys.argv) > 2 else "64"
 reps = sys.argv[3] if len(sys.argv) > 3 else "3"
 VARIANTS = [
-    ("columns-first (moments + cols R2C + rows C2C|power, no mirror)", {"XRFTB_COLS_FIRST": "1"}),
-    ("register-prefetch cols + moments pass", {"XRFTB_COLS_ASYNC": "0", "XRFTB_ROWLINE": "0"}),
-    ("bulk-copy cols      + moments pass", {"XRFTB_COLS_ASYNC": "1", "XRFTB_ROWLINE": "0"}),
+    ("columns-first, moments pass, LDG pass 1", {"XRFTB_COLS_FIRST": "1", "XRFTB_ROWLINE": "0", "XRFTB_COLS_ASYNC": "0"}),
+    ("columns-first, column-line, LDG pass 1", {"XRFTB_COLS_FIRST": "1", "XRFTB_ROWLINE": "1", "XRFTB_COLS_ASYNC": "0"}),
+    ("columns-first, moments pass, TMA pass 1", {"XRFTB_COLS_FIRST": "1", "XRFTB_ROWLINE": "0"}),
+    ("columns-first, column-line, TMA pass 1", {"XRFTB_COLS_FIRST": "1", "XRFTB_ROWLINE": "1"}),
     ("register-prefetch cols + row-line detrend", {"XRFTB_COLS_ASYNC": "0", "XRFTB_ROWLINE": "1"}),
-    ("bulk-copy cols      + row-line detrend", {"XRFTB_COLS_ASYNC": "1", "XRFTB_ROWLINE": "1"}),
 ]
 for name, env in VARIANTS:
     e = dict(os.environ); e.update(env)

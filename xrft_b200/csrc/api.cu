@@ -1031,14 +1031,23 @@ template <typename T> static bool colsfirst_eligible(int mode, int keep_half, co
 }
 template <typename T> static size_t colsfirst_item_bytes(int ny, int nx) { return (size_t)(ny / 2 + 1) * nx * sizeof(cplx<T>); }
 
+// column-line detrend tables of the columns-first order: per item colstats (float4 / column) + ag (cplx<T> / column);
+// fixed: wj table (ny/2+1 pairs) + its fp64 transform scratch
+template <typename T> static size_t colline_item_bytes(int nx) { return (size_t)nx * (sizeof(float4) + sizeof(cplx<T>)); }
+template <typename T> static size_t colline_fixed_bytes(int ny) {
+    return align256((size_t)(ny / 2 + 1) * 2 * sizeof(cplx<T>)) + align256((size_t)2 * ny * sizeof(double)) + align256((size_t)2 * (ny / 2 + 1) * sizeof(double2));
+}
+
 template <typename T>
 static int spectrum2d_colsfirst(const xrftb_spectrum2d_desc& q, int ly, int lx, cudaStream_t st) {
     using C_ = cplx<T>;
     const int C = cols_tile_width<T>(ly, false);
     const int H = q.ny / 2 + 1;
-    const size_t per_item = colsfirst_item_bytes<T>(q.ny, q.nx);
+    // column-line detrend (no moments pass): float32 with two packed columns per thread, ny long enough for the fp64 table transform
+    const bool colline = std::is_same<T, float>::value && q.detrend && rowline_enabled() && C >= 2 && ly >= 3;
+    const size_t per_item = colsfirst_item_bytes<T>(q.ny, q.nx) + (colline ? colline_item_bytes<T>(q.nx) : 0);
     const size_t mom_bytes = (size_t)q.batch * 4 * sizeof(double);
-    const size_t mom_region = align256(mom_bytes);
+    const size_t mom_region = align256(mom_bytes) + (colline ? colline_fixed_bytes<T>(q.ny) : 0);
     if (!q.work || q.work_bytes < mom_region + per_item) { set_error("spectrum2d: workspace too small (%zu < %zu)", q.work_bytes, mom_region + per_item); return XRFTB_EWORKSPACE; }
     long bchunk = (long)((q.work_bytes - mom_region) / per_item);
     if (bchunk > q.batch) bchunk = q.batch;
@@ -1047,7 +1056,27 @@ static int spectrum2d_colsfirst(const xrftb_spectrum2d_desc& q, int ly, int lx, 
     C_* interm = reinterpret_cast<C_*>(reinterpret_cast<char*>(q.work) + mom_region);
     const long item = (long)q.ny * q.nx;
     const T* in = reinterpret_cast<const T*>(q.in1);
-    if (q.detrend) {
+    float4* colstats = nullptr;
+    C_* ag = nullptr;
+    C_* wj = nullptr;
+    if (colline) {
+        char* fx = reinterpret_cast<char*>(q.work) + align256(mom_bytes);
+        const int My = q.ny / 2;
+        wj = reinterpret_cast<C_*>(fx);
+        double* wrows = reinterpret_cast<double*>(fx + align256((size_t)H * 2 * sizeof(C_)));
+        double2* wspec = reinterpret_cast<double2*>(reinterpret_cast<char*>(wrows) + align256((size_t)2 * q.ny * sizeof(double)));
+        colstats = reinterpret_cast<float4*>(reinterpret_cast<char*>(interm) + (size_t)bchunk * colsfirst_item_bytes<T>(q.ny, q.nx));
+        ag = reinterpret_cast<C_*>(colstats + (size_t)bchunk * q.nx);
+        // transforms of w_y(i) and w_y(i)(i - ic), k <= ny/2: one fp64 real transform of two rows, once per call
+        rowline_wj_in_kernel<T><<<(q.ny + 255) / 256, 256, 0, st>>>(reinterpret_cast<const T*>(q.win_y), wrows, q.ny);
+        if (int rc = check_launch("rowline_wj_in_kernel")) return rc;
+        RowsR2CFused<double> wio{};
+        wio.in = wrows; wio.in_row_stride = q.ny; wio.logNy = 0; wio.detrend = 0; wio.moments = nullptr; wio.wy = nullptr; wio.wx = nullptr;
+        wio.out = wspec; wio.logC = -1; wio.out_seq_stride = H; wio.rowstats = nullptr;
+        if (int rc = rows_r2c<double>(wio, ly - 1, 2, st)) return rc;
+        rowline_wj_out_kernel<T><<<(unsigned)((H + 255) / 256), 256, 0, st>>>(wspec, wj, My, H);
+        if (int rc = check_launch("rowline_wj_out_kernel")) return rc;
+    } else if (q.detrend) {
         cudaError_t e = cudaMemsetAsync(mom, 0, mom_bytes, st);
         if (e != cudaSuccess) { set_error("memset: %s", cudaGetErrorString(e)); return XRFTB_ECUDA; }
         ProfScope ps_(PROF_MOMENTS, st);
@@ -1063,12 +1092,26 @@ static int spectrum2d_colsfirst(const xrftb_spectrum2d_desc& q, int ly, int lx, 
         const long nb = (q.batch - b0 < bchunk) ? q.batch - b0 : bchunk;
         {
             ColsR2CPack<T> io{in + b0 * item, q.nx, tiles_per_item, q.detrend, mom + b0 * 4,
-                              reinterpret_cast<const T*>(q.win_y), reinterpret_cast<const T*>(q.win_x), interm};
+                              reinterpret_cast<const T*>(q.win_y), reinterpret_cast<const T*>(q.win_x), interm, colstats, 0, {}};
+            // tensor-map fed (asynchronous) variant: float32, >= 2 exchange stages, 16-byte aligned rows
+            static int async_on = -1;
+            if (async_on < 0) { const char* e = getenv("XRFTB_COLS_ASYNC"); async_on = e ? atoi(e) : 2; }
+            bool use_async = false;
+            if (async_on && std::is_same<T, float>::value && ly > TypeCfg<T>::LOGE && C >= 2 && (q.nx * sizeof(T)) % 16 == 0) {
+                const int box_rows = q.ny < 256 ? q.ny : 256;
+                if (encode_out_tmap(&io.tmap, const_cast<T*>(in + b0 * item), nb * q.ny, q.nx, 2 * C, box_rows)) { io.box_rows = box_rows; use_async = true; }
+            }
             ProfScope ps_(PROF_COLS, st);
-            if (int rc = cols_r2c_pack<T>(io, ly, nb * tiles_per_item, st)) return rc;
+            if (int rc = cols_r2c_pack<T>(io, ly, nb * tiles_per_item, use_async, st)) return rc;
+        }
+        if (colline) {
+            // the row-line completion kernel with the roles of the axes swapped: nx lines (columns) of length ny
+            ProfScope ps_(PROF_MOMENTS, st);
+            rowline_fix_kernel<T><<<(unsigned)nb, 256, 0, st>>>(colstats, ag, reinterpret_cast<const T*>(q.win_x), q.nx, q.ny, q.detrend);
+            if (int rc = check_launch("rowline_fix_kernel")) return rc;
         }
         {
-            RowsC2CPower<T> io{interm, reinterpret_cast<T*>(q.out) + b0 * item, ly, H, q.shift_y, q.shift_x, (T)q.scale};
+            RowsC2CPower<T> io{interm, reinterpret_cast<T*>(q.out) + b0 * item, ly, H, q.shift_y, q.shift_x, (T)q.scale, colline ? ag : nullptr, wj};
             ProfScope ps_(PROF_ROWS, st);
             if (int rc = rows_c2c_power<T>(io, lx, nb * H, st)) return rc;
         }
@@ -1404,9 +1447,11 @@ size_t xrftb_spectrum2d_workspace(int dtype, int ny, int nx, int two_fields, int
     size_t item_total = per_item * fields + rl_item;
     if (!two_fields) {   // the columns-first order keeps [ny/2+1][nx] complex per item
         const size_t cf = dtype == XRFTB_F32 ? colsfirst_item_bytes<float>(ny, nx) : colsfirst_item_bytes<double>(ny, nx);
-        if (cf > item_total) item_total = cf;
+        const size_t cl = dtype == XRFTB_F32 ? cf + colline_item_bytes<float>(nx) : cf;
+        if (cl > item_total) item_total = cl;
     }
-    return ((size_t)65536 * 2 * 4 * sizeof(double)) + rl_fixed + item_total * (size_t)batch_in_flight + 1024;
+    const size_t cl_fixed = (dtype == XRFTB_F32 && !two_fields) ? colline_fixed_bytes<float>(ny) : 0;
+    return ((size_t)65536 * 2 * 4 * sizeof(double)) + (rl_fixed > cl_fixed ? rl_fixed : cl_fixed) + item_total * (size_t)batch_in_flight + 1024;
 }
 
 int xrftb_spectrum2d(const xrftb_spectrum2d_desc* q, void* stream) {

@@ -270,6 +270,11 @@ __device__ __forceinline__ void bulk_load_g2s(void* dst_smem, const void* src_gm
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// 2-D tensor-map tile load (TMA, SASS UTMALDG): box {c0 .. , c1 ..} of the tensor described by `tmap` -> dense smem box
+__device__ __forceinline__ void tensor_load_2d_g2s(void* dst_smem, const void* tmap, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst_smem)), "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------

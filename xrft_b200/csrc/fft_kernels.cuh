@@ -599,7 +599,7 @@ cols_kernel(const __grid_constant__ IO io, const cplx<T>* __restrict__ tw, long 
         {
             cplx<T> ag_[E];
             io.template fix_fetch<LOG2L, LOGE>(tile, u, ag_);
-            io.template fix_apply<LOG2L, LOGE, C, V>(tile, u, cg, ag_, v);
+            io.template fix_apply<LOG2L, LOGE, C, V>(tile, u, cg, ag_, v, reinterpret_cast<float*>(smem + G_::LPAD * C));
         }
         block_fft<T, LOG2L, LOGE, V, C>(v, u, sm, 1, tw);
         io.template store_a<LOG2L, LOGE, C, V>(tile, u, cg, v, smem);
@@ -644,24 +644,17 @@ __global__ void __launch_bounds__((1 << (LOG2L - LOGE)) * (C / 2), min_blocks_fo
 cols_async_kernel(const __grid_constant__ IO io, const cplx<T>* __restrict__ tw, long ntiles) {
     using G_ = Geometry<LOG2L, LOGE>;
     constexpr int E = G_::E, CG = C / 2, NT = G_::NT, L = 1 << LOG2L, NTHR = NT * CG;
-    constexpr unsigned TILE_BYTES = (unsigned)(L * C * sizeof(cplx<T>));
-    constexpr unsigned PIECE = TILE_BYTES > 32768u ? 32768u : TILE_BYTES;
     static_assert(LOG2L > LOGE, "needs at least one exchange");
-    static_assert(TILE_BYTES % PIECE == 0 && PIECE % 16 == 0, "bulk copies are multiples of 16 bytes");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     cplx<T>* smL = reinterpret_cast<cplx<T>*>(smem_raw);
     cplx<T>* smX = smL + G_::LPAD * C;
     uint64_t* bar = reinterpret_cast<uint64_t*>(smX + G_::LPAD * CG);
+    float* extra = reinterpret_cast<float*>(bar + 2);   // IO scratch (histogram / partial sums) behind the barrier
     const int cg = threadIdx.x % CG, u = threadIdx.x / CG;
     if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_init_fence(); }
     io.template init<LOG2L, LOGE, C, 2>(smX);   // ends with a barrier when there is a histogram
     __syncthreads();
-    auto issue = [&](long tile) {
-        const char* src = reinterpret_cast<const char*>(io.template tile_src<LOG2L, C>(tile));
-        mbar_expect_tx(bar, TILE_BYTES);
-#pragma unroll
-        for (unsigned off = 0; off < TILE_BYTES; off += PIECE) bulk_load_g2s(reinterpret_cast<char*>(smL) + off, src + off, PIECE, bar);
-    };
+    auto issue = [&](long tile) { io.template issue_load<LOG2L, C>(tile, smL, bar); };
     if (threadIdx.x == 0 && (long)blockIdx.x < ntiles) issue((long)blockIdx.x);
     unsigned phase = 0;
     for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -679,12 +672,16 @@ cols_async_kernel(const __grid_constant__ IO io, const cplx<T>* __restrict__ tw,
                 v[1][q] = pl[q * (NT * C) + 1];
             }
         }
-        io.template fix_apply<LOG2L, LOGE, C, 2>(tile, u, cg, ag_, v);
+        io.template fix_apply<LOG2L, LOGE, C, 2>(tile, u, cg, ag_, v, extra);
         io.tma_reads_done();  // asynchronous stores of the previous tile have finished reading the staging buffer X
         StagesAsync<T, LOG2L, LOGE, 0, C>::run(v, u, smL + cg * 2, smX + cg, tw,
                                                [&]() { if (threadIdx.x == 0 && nxt < ntiles) issue(nxt); });
-        io.template store_a<LOG2L, LOGE, C, 2>(tile, u, cg, v, smX);
-        io.template store_b<LOG2L, LOGE, C, NTHR>(tile, smX);
+        if constexpr (IO::kSplitEpilogue) {
+            io.template store_split<LOG2L, LOGE, C, NTHR>(tile, u, cg, v, smX, extra);
+        } else {
+            io.template store_a<LOG2L, LOGE, C, 2>(tile, u, cg, v, smX);
+            io.template store_b<LOG2L, LOGE, C, NTHR>(tile, smX);
+        }
     }
     io.tma_drain();
 }
@@ -693,6 +690,7 @@ cols_async_kernel(const __grid_constant__ IO io, const cplx<T>* __restrict__ tw,
 template <typename T> struct ColsC2C {
     static constexpr bool kTwoFields = false;
     static constexpr bool kBins = false;
+    static constexpr int kExtraSmemBytes = 0;
     const cplx<T>* in; cplx<T>* out; long B; long tiles_per_row; int inverse; T scale;
 
     template <int LOG2L, int C> __device__ __forceinline__ void prefetch(long) const {}
@@ -701,7 +699,7 @@ template <typename T> struct ColsC2C {
     __device__ __forceinline__ void tma_drain() const {}
     template <int LOG2L, int LOGE> __device__ __forceinline__ void fix_fetch(long, int, cplx<T> (&)[1 << LOGE]) const {}
     template <int LOG2L, int LOGE, int C, int V>
-    __device__ __forceinline__ void fix_apply(long, int, int, const cplx<T> (&)[1 << LOGE], cplx<T> (&)[V][1 << LOGE]) const {}
+    __device__ __forceinline__ void fix_apply(long, int, int, const cplx<T> (&)[1 << LOGE], cplx<T> (&)[V][1 << LOGE], float* = nullptr) const {}
 
     template <int LOG2L, int LOGE, int C, int V>
     __device__ __forceinline__ void load(long tile, int u, int cg, cplx<T> (&v)[V][1 << LOGE], int) const {
@@ -759,19 +757,42 @@ template <typename T> struct ColsC2C {
 template <typename T> struct ColsR2CPack {
     static constexpr bool kTwoFields = false;
     static constexpr bool kBins = false;
+    static constexpr int kExtraSmemBytes = 8192;   // column-line partial sums [warps][2C][2] + lines [2C][2] (floats)
     const T* in;            // [batch][Ny][Nx] real
     int Nx;                 // row length (elements)
     int tiles_per_item;     // Nx / (2 C)
-    int detrend;            // 0 none | 1 constant | 2 linear (global plane from `moments`)
-    const double* moments;  // [batch][4] : S, -, Sy, Sx (moments_kernel)
+    int detrend;            // 0 none | 1 constant | 2 linear
+    const double* moments;  // global-plane variant: [batch][4] : S, -, Sy, Sx (moments_kernel)
     const T* wy; const T* wx;
     cplx<T>* out;           // [batch][Ny/2+1][Nx]
+    // column-line variant (float32; no moments pass): every column subtracts its own exactly representable line
+    // ph_j(i) = A0 + B i and records (A0, B, sum_i r, sum_i (i - ic) r) of the residual in colstats[batch][Nx]; the
+    // difference to the least-squares plane is added to the half-spectrum rows in pass 2 (RowsC2CPower::prologue).
+    float4* colstats;
+    // cols_async_kernel: tile = Ny rows x 2C reals, fetched as boxes of box_rows rows through a 2-D tensor map of the
+    // input viewed as [batch * Ny][Nx]; a dense box row = 2C reals = C packed points, i.e. the [ky][C] layout the kernel reads
+    int box_rows;
+    alignas(64) CUtensorMap tmap;
+    static constexpr bool kSplitEpilogue = true;
+    template <int LOG2L, int C> __device__ __forceinline__ void issue_load(long tile, cplx<T>* smL, uint64_t* bar) const {
+        constexpr int Ny = 1 << LOG2L;
+        const long b = tile / tiles_per_item;
+        const int x0 = (int)(tile - b * tiles_per_item) * (2 * C);
+        const int row0 = (int)(b << LOG2L);
+        mbar_expect_tx(bar, (unsigned)(Ny * C * sizeof(cplx<T>)));
+        for (int r0 = 0; r0 < Ny; r0 += box_rows) tensor_load_2d_g2s(smL + r0 * C, &tmap, x0, row0 + r0, bar);
+    }
 
     template <int LOG2L, int C> __device__ __forceinline__ void prefetch(long) const {}
     template <int LOG2L, int LOGE, int C, int V> __device__ __forceinline__ void init(cplx<T>*) const {}
     __device__ __forceinline__ void tma_reads_done() const {}
     __device__ __forceinline__ void tma_drain() const {}
-    template <int LOG2L, int LOGE> __device__ __forceinline__ void fix_fetch(long, int, cplx<T> (&)[1 << LOGE]) const {}
+    // window factors of the rows this thread owns, fetched ahead of use
+    template <int LOG2L, int LOGE> __device__ __forceinline__ void fix_fetch(long, int u, cplx<T> (&a)[1 << LOGE]) const {
+        constexpr int NT = Geometry<LOG2L, LOGE>::NT;
+#pragma unroll
+        for (int q = 0; q < (1 << LOGE); ++q) a[q].x = wy != nullptr ? __ldg(wy + u + q * NT) : (T)1;
+    }
 
     template <int LOG2L, int LOGE, int C, int V>
     __device__ __forceinline__ void load(long tile, int u, int cg, cplx<T> (&v)[V][1 << LOGE], int) const {
@@ -792,12 +813,73 @@ template <typename T> struct ColsR2CPack {
             }
         }
     }
-    // detrend (fp64 plane) + window on the freshly loaded tile: rows u + q NT, real columns x0 + 2 vv (+1)
+    // detrend + w_y(i) on the freshly loaded tile: rows u + q NT, real columns x0 + 2 vv (+1).  w_x(j) is applied when the
+    // two spectra of a packed column are separated (store_b).  `extra` = the partial-sum area behind the exchange buffer.
     template <int LOG2L, int LOGE, int C, int V>
-    __device__ __forceinline__ void fix_apply(long tile, int u, int cg, const cplx<T> (&)[1 << LOGE], cplx<T> (&v)[V][1 << LOGE]) const {
-        constexpr int NT = Geometry<LOG2L, LOGE>::NT, Ny = 1 << LOG2L;
+    __device__ __forceinline__ void fix_apply(long tile, int u, int cg, const cplx<T> (&a)[1 << LOGE], cplx<T> (&v)[V][1 << LOGE], float* extra) const {
+        constexpr int NT = Geometry<LOG2L, LOGE>::NT, Ny = 1 << LOG2L, CG = C / V;
         const long b = tile / tiles_per_item;
         const int x0 = (int)(tile - b * tiles_per_item) * (2 * C) + cg * (2 * V);
+        if (colstats != nullptr) {
+            if constexpr (sizeof(T) == 4 && V == 2) {
+                if (detrend) {
+                    const float* top = in + (b << LOG2L) * (long)Nx + x0;
+                    const float4 e0 = *reinterpret_cast<const float4*>(top);
+                    const float4 e1 = *reinterpret_cast<const float4*>(top + (long)(Ny - 1) * Nx);
+                    const float x0v[4] = {e0.x, e0.y, e0.z, e0.w}, x1v[4] = {e1.x, e1.y, e1.z, e1.w};
+                    float A0[4], B[4], sx[4] = {0.f, 0.f, 0.f, 0.f}, tq[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float m = fmaxf(fabsf(x0v[k]), fabsf(x1v[k]));
+                        A0[k] = 0.f; B[k] = 0.f;
+                        if (m > 1e-30f && m < 1e30f) {   // same exact-line construction as the row-line prologue of rows2_kernel
+                            const float p2 = __int_as_float(__float_as_int(m) & 0x7f800000);
+                            const float Q = p2 * 4.76837158203125e-07f, iQ = 2097152.0f / p2;
+                            A0[k] = rintf(x0v[k] * iQ) * Q;
+                            B[k] = rintf((x1v[k] - x0v[k]) * (1.0f / (float)(Ny > 1 ? Ny - 1 : 1)) * iQ) * Q;
+                        }
+                    }
+                    const float if0 = (float)u;
+#pragma unroll
+                    for (int q = 0; q < (1 << LOGE); ++q) {
+                        const float fi = if0 + (float)(q * NT);
+                        const float wrow = a[q].x;
+                        float r[4] = {v[0][q].x, v[0][q].y, v[1][q].x, v[1][q].y};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            r[k] -= fmaf(B[k], fi, A0[k]);
+                            sx[k] += r[k];
+                            tq[k] = fmaf((float)q, r[k], tq[k]);
+                            r[k] *= wrow;
+                        }
+                        v[0][q] = mk<T>(r[0], r[1]);
+                        v[1][q] = mk<T>(r[2], r[3]);
+                    }
+                    // column sums over all rows: lanes that share cg (stride CG inside the warp), then across warps via `extra`
+                    const float ic = 0.5f * (float)(Ny - 1);
+                    constexpr int NTHR = NT * CG, NW = NTHR >= 32 ? NTHR / 32 : 1, LW = NTHR >= 32 ? 32 : NTHR;
+                    constexpr unsigned LMASK = NTHR >= 32 ? 0xffffffffu : ((1u << (NTHR & 31)) - 1u);
+                    float* part = extra;                       // [NW][CG][4][2]
+                    float* lines = extra + NW * CG * 8;        // [CG][4][2]
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        float s2 = sx[k];
+                        float t2 = fmaf(if0 - ic, sx[k], (float)NT * tq[k]);
+#pragma unroll
+                        for (int off = CG; off < LW; off <<= 1) {
+                            s2 += __shfl_xor_sync(LMASK, s2, off);
+                            t2 += __shfl_xor_sync(LMASK, t2, off);
+                        }
+                        if ((threadIdx.x & (LW - 1)) < CG) {
+                            float* pp = part + (((threadIdx.x / LW) * CG + cg) * 4 + k) * 2;
+                            pp[0] = s2; pp[1] = t2;
+                        }
+                        if (u == 0) { lines[(cg * 4 + k) * 2] = A0[k]; lines[(cg * 4 + k) * 2 + 1] = B[k]; }
+                    }
+                    return;
+                }
+            }
+        }
         double p0 = 0.0, cx = 0.0, cy = 0.0;
         if (detrend) {
             const double* m = moments + b * 4;
@@ -812,12 +894,9 @@ template <typename T> struct ColsR2CPack {
             }
         }
         const double pstep = cy * (double)NT;
-        T wxv[2 * V];
-#pragma unroll
-        for (int k = 0; k < 2 * V; ++k) wxv[k] = wx != nullptr ? __ldg(wx + x0 + k) : (T)1;
 #pragma unroll
         for (int q = 0; q < (1 << LOGE); ++q) {
-            const T wrow = wy != nullptr ? __ldg(wy + u + q * NT) : (T)1;
+            const T wrow = a[q].x;
             const double pq = p0 + (double)q * pstep;
 #pragma unroll
             for (int vv = 0; vv < V; ++vv) {
@@ -826,8 +905,8 @@ template <typename T> struct ColsR2CPack {
                     y.x = (T)((double)y.x - (pq + cx * (double)(2 * vv)));
                     y.y = (T)((double)y.y - (pq + cx * (double)(2 * vv + 1)));
                 }
-                y.x *= wxv[2 * vv] * wrow;
-                y.y *= wxv[2 * vv + 1] * wrow;
+                y.x *= wrow;
+                y.y *= wrow;
                 v[vv][q] = y;
             }
         }
@@ -847,20 +926,109 @@ template <typename T> struct ColsR2CPack {
             }
         __syncthreads();
     }
+    // Epilogue of cols_async_kernel: the staging buffer holds only half a tile, so the rows are unpacked in two rounds.
+    // With Q = Ny/4: round 1 stages ky in [0,Q) and [3Q,Ny) (slots ky, ky-2Q) and unpacks k in [0,Q) (partner Ny-k);
+    // round 2 stages ky in [Q,3Q] (slot ky-Q) and unpacks k in [Q,2Q].  Row segments stay 2C*sizeof(cplx) bytes wide.
+    template <int LOG2L, int LOGE, int C, int NTHR>
+    __device__ __forceinline__ void store_split(long tile, int u, int cg, cplx<T> (&v)[2][1 << LOGE], cplx<T>* smX, const float* extra) const {
+        using G_ = Geometry<LOG2L, LOGE>;
+        constexpr int R = 1 << G_::LOGR_LAST, G = G_::E / R, Ny = 1 << LOG2L, Q = Ny / 4, H = Ny / 2 + 1;
+        const long b = tile / tiles_per_item;
+        const int x0 = (int)(tile - b * tiles_per_item) * (2 * C);
+        write_colstats<C, NTHR>(b, x0, extra);
+        cplx<T>* ob = out + (b * H) * (long)Nx + x0;
+        constexpr bool FIXED_C = (NTHR % C == 0);
+        int c = threadIdx.x & (C - 1);
+        T ha = (T)0.5 * (wx != nullptr ? __ldg(wx + x0 + 2 * c) : (T)1);
+        T hb = (T)0.5 * (wx != nullptr ? __ldg(wx + x0 + 2 * c + 1) : (T)1);
+#pragma unroll
+        for (int round = 0; round < 2; ++round) {
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+#pragma unroll
+                for (int t = 0; t < R; ++t) {
+                    const int ky = final_index<LOG2L, LOGE>(u, g, t);
+                    const bool outer = (ky < Q) || (ky >= 3 * Q);
+                    const bool mine = round == 0 ? outer : (!outer || ky == 3 * Q);
+                    if (mine) {
+                        const int slot = round == 0 ? (ky < Q ? ky : ky - 2 * Q) : ky - Q;
+                        smX[slot * C + cg * 2] = v[0][g + t * G];
+                        smX[slot * C + cg * 2 + 1] = v[1][g + t * G];
+                    }
+                }
+            __syncthreads();
+            const int k0 = round == 0 ? 0 : Q;
+            const int nk = round == 0 ? Q : Q + 1;
+#pragma unroll 4
+            for (int idx = threadIdx.x; idx < nk * C; idx += NTHR) {
+                const int kr = idx / C;
+                if constexpr (!FIXED_C) {
+                    c = idx - kr * C;
+                    ha = (T)0.5 * (wx != nullptr ? __ldg(wx + x0 + 2 * c) : (T)1);
+                    hb = (T)0.5 * (wx != nullptr ? __ldg(wx + x0 + 2 * c + 1) : (T)1);
+                }
+                const int ky = k0 + kr;
+                const int sa = round == 0 ? ky : ky - Q;
+                const int sb = round == 0 ? (ky == 0 ? 0 : Ny - ky - 2 * Q) : Ny - ky - Q;
+                const cplx<T> za = smX[sa * C + c];
+                const cplx<T> zb = smX[sb * C + c];
+                const cplx<T> A = mk<T>(ha * (za.x + zb.x), ha * (za.y - zb.y));
+                const cplx<T> B = mk<T>(hb * (za.y + zb.y), hb * (zb.x - za.x));
+                cplx<T>* po = ob + (long)ky * Nx + 2 * c;
+                if constexpr (sizeof(T) == 4) {
+                    *reinterpret_cast<float4*>(po) = make_float4(A.x, A.y, B.x, B.y);
+                } else {
+                    po[0] = A; po[1] = B;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // fold the per-warp column sums (visible after any barrier behind fix_apply) and record the column lines
+    template <int C, int NTHR>
+    __device__ __forceinline__ void write_colstats(long b, int x0, const float* extra) const {
+        if (colstats != nullptr && detrend) {
+            if constexpr (sizeof(T) == 4) {
+                constexpr int CG = C / 2, NW = NTHR >= 32 ? NTHR / 32 : 1;
+                const float* part = extra;
+                const float* lines = part + NW * CG * 8;
+                for (int col = threadIdx.x; col < 2 * C; col += NTHR) {   // real column x0 + col, col = cg * 4 + k
+                    float s2 = 0.f, t2 = 0.f;
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) { s2 += part[(w * 2 * C + col) * 2]; t2 += part[(w * 2 * C + col) * 2 + 1]; }
+                    colstats[b * Nx + x0 + col] = make_float4(lines[col * 2], lines[col * 2 + 1], s2, t2);
+                }
+            }
+        }
+    }
     // separate the two real columns of every packed column: A[k] = (Z[k] + conj Z[N-k]) / 2, B[k] = -i (Z[k] - conj Z[N-k]) / 2,
-    // rows k in [0, Ny/2]; one thread writes both spectra of one (k, packed column): 2*sizeof(cplx) contiguous bytes
+    // rows k in [0, Ny/2], each scaled by its column's w_x; one thread writes both spectra of one (k, packed column):
+    // 2*sizeof(cplx) contiguous bytes, C threads cover one 2C*sizeof(cplx)-byte row segment
     template <int LOG2L, int LOGE, int C, int NTHR>
     __device__ __forceinline__ void store_b(long tile, cplx<T>* smem) const {
+        using G_ = Geometry<LOG2L, LOGE>;
         constexpr int Ny = 1 << LOG2L, H = Ny / 2 + 1;
         const long b = tile / tiles_per_item;
         const int x0 = (int)(tile - b * tiles_per_item) * (2 * C);
+        write_colstats<C, NTHR>(b, x0, reinterpret_cast<const float*>(smem + G_::LPAD * C));
         cplx<T>* ob = out + (b * H) * (long)Nx + x0;
-        for (int idx = threadIdx.x; idx < H * C; idx += NTHR) {
-            const int ky = idx / C, c = idx - ky * C;
+        constexpr int ITEMS = H * C;
+        constexpr bool FIXED_C = (NTHR % C == 0);       // then the packed column of a thread is the same in every sweep
+        int c = threadIdx.x & (C - 1);
+        T ha = (T)0.5 * (wx != nullptr ? __ldg(wx + x0 + 2 * c) : (T)1);
+        T hb = (T)0.5 * (wx != nullptr ? __ldg(wx + x0 + 2 * c + 1) : (T)1);
+#pragma unroll 4
+        for (int idx = threadIdx.x; idx < ITEMS; idx += NTHR) {
+            const int ky = idx / C;
+            if constexpr (!FIXED_C) {
+                c = idx - ky * C;
+                ha = (T)0.5 * (wx != nullptr ? __ldg(wx + x0 + 2 * c) : (T)1);
+                hb = (T)0.5 * (wx != nullptr ? __ldg(wx + x0 + 2 * c + 1) : (T)1);
+            }
             const cplx<T> za = smem[ky * C + c];
             const cplx<T> zb = smem[((Ny - ky) & (Ny - 1)) * C + c];
-            const cplx<T> A = mk<T>((T)0.5 * (za.x + zb.x), (T)0.5 * (za.y - zb.y));
-            const cplx<T> B = mk<T>((T)0.5 * (za.y + zb.y), (T)0.5 * (zb.x - za.x));
+            const cplx<T> A = mk<T>(ha * (za.x + zb.x), ha * (za.y - zb.y));
+            const cplx<T> B = mk<T>(hb * (za.y + zb.y), hb * (zb.x - za.x));
             cplx<T>* po = ob + (long)ky * Nx + 2 * c;
             if constexpr (sizeof(T) == 4) {
                 *reinterpret_cast<float4*>(po) = make_float4(A.x, A.y, B.x, B.y);
@@ -876,6 +1044,9 @@ template <typename T> struct ColsR2CPack {
 template <typename T> struct RowsC2CPower {
     static constexpr int kSeqSkew = 0;
     const cplx<T>* in; T* out; int logNy; int H; int shift_y, shift_x; T scale;
+    // column-line detrend completion: row ky of item b gets ag[b][j].x * wj[2 ky] + ag[b][j].y * wj[2 ky + 1] added at column j
+    // (ag = w_x(j) (alpha_j, gamma_j), wj = transforms of w_y(i) and w_y(i)(i - ic)); nullptr = none
+    const cplx<T>* ag; const cplx<T>* wj;
 
     template <int LOG2L, int SEQ> __device__ __forceinline__ void prefetch(long seq0, long nseq) const {
         constexpr unsigned row_bytes = (unsigned)((1u << LOG2L) * sizeof(cplx<T>));
@@ -892,9 +1063,22 @@ template <typename T> struct RowsC2CPower {
         }
     }
     template <int LOG2L, int LOGE>
-    __device__ __forceinline__ void prologue(long, bool, int, cplx<T> (&raw)[1 << LOGE], cplx<T> (&v)[1 << LOGE]) const {
+    __device__ __forceinline__ void prologue(long seq, bool active, int u, cplx<T> (&raw)[1 << LOGE], cplx<T> (&v)[1 << LOGE]) const {
+        constexpr int NT = Geometry<LOG2L, LOGE>::NT;
+        if (ag != nullptr && active) {
+            const long b = seq / H;
+            const int ky = (int)(seq - b * H);
+            const cplx<T> W = __ldg(wj + 2 * ky), J = __ldg(wj + 2 * ky + 1);
+            const cplx<T>* pa = ag + (b << LOG2L) + u;
 #pragma unroll
-        for (int q = 0; q < (1 << LOGE); ++q) v[q] = raw[q];
+            for (int q = 0; q < (1 << LOGE); ++q) {
+                const cplx<T> a = __ldg(pa + q * NT);
+                v[q] = mk<T>(raw[q].x + a.x * W.x + a.y * J.x, raw[q].y + a.x * W.y + a.y * J.y);
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < (1 << LOGE); ++q) v[q] = raw[q];
+        }
     }
     template <int LOG2L, int LOGE, int SEQ>
     __device__ __forceinline__ void store_a(long, long seq, bool active, int u, int, cplx<T> (&v)[1 << LOGE], cplx<T>*, int, long) const {
@@ -907,7 +1091,9 @@ template <typename T> struct RowsC2CPower {
         const int sy = shift_y ? Ny / 2 : 0, sx = shift_x ? Nx / 2 : 0;
         T* rowd = out + ((b << logNy) + ((ky + sy) & (Ny - 1))) * (long)Nx;
         T* rowm = out + ((b << logNy) + ((Ny - ky + sy) & (Ny - 1))) * (long)Nx;
-        const bool mirror = (ky != 0) && (2 * ky != Ny);   // rows 0 and Ny/2 are their own mirror image
+        // rows 0 and Ny/2 are their own mirror image (rowm == rowd): their kx <= Nx/2 half is written and mirrored inside
+        // the row, so the result is exactly symmetric like every other row pair
+        const bool self = (ky == 0) || (2 * ky == Ny);
 #pragma unroll
         for (int g = 0; g < G; ++g)
 #pragma unroll
@@ -915,8 +1101,8 @@ template <typename T> struct RowsC2CPower {
                 const cplx<T> f = v[g + t * G];
                 const T val = (f.x * f.x + f.y * f.y) * scale;
                 const int kx = final_index<LOG2L, LOGE>(u, g, t);
-                rowd[(kx + sx) & (Nx - 1)] = val;
-                if (mirror) rowm[(Nx - kx + sx) & (Nx - 1)] = val;
+                if (!self || 2 * kx <= Nx) rowd[(kx + sx) & (Nx - 1)] = val;
+                if (!self || (kx > 0 && 2 * kx < Nx)) rowm[(Nx - kx + sx) & (Nx - 1)] = val;
             }
     }
     template <int LOG2L, int LOGE, int SEQ>
@@ -960,6 +1146,7 @@ __device__ __forceinline__ double2 wscale(double2 v, double w) { v.x *= w; v.y *
 template <typename T, int MODE> struct ColsFused {
     static constexpr bool kTwoFields = (MODE == EPI_CROSS || MODE == EPI_PHASE || MODE == EPI_BINS_CROSS);
     static constexpr bool kBins = (MODE == EPI_BINS_POWER || MODE == EPI_BINS_CROSS);
+    static constexpr int kExtraSmemBytes = 0;
     static constexpr bool kCplxStage = (MODE == EPI_COMPLEX || MODE == EPI_CROSS || MODE == EPI_PHASE || MODE == EPI_BINS_CROSS);
     static constexpr bool kCplxOut = (MODE == EPI_COMPLEX || MODE == EPI_CROSS);
     using StageT = typename std::conditional<kCplxStage, cplx<T>, T>::type;
@@ -979,8 +1166,17 @@ template <typename T, int MODE> struct ColsFused {
         using G_ = Geometry<LOG2L, LOGE>;
         return (G_::LPAD * C * (kTwoFields ? 2 : 1)) * (int)sizeof(cplx<T>);
     }
-    // the tile as one contiguous chunk of global memory (single-field modes; cols_async_kernel)
-    template <int LOG2L, int C> __device__ __forceinline__ const cplx<T>* tile_src(long tile) const { return in1 + tile * (long)(1 << LOG2L) * C; }
+    // cols_async_kernel: the tile is one contiguous chunk of global memory (single-field modes) -> 1-D bulk copies
+    static constexpr bool kSplitEpilogue = false;
+    template <int LOG2L, int C> __device__ __forceinline__ void issue_load(long tile, cplx<T>* smL, uint64_t* bar) const {
+        constexpr unsigned TILE_BYTES = (unsigned)((1u << LOG2L) * C * sizeof(cplx<T>));
+        constexpr unsigned PIECE = TILE_BYTES > 32768u ? 32768u : TILE_BYTES;
+        static_assert(TILE_BYTES % PIECE == 0 && PIECE % 16 == 0, "bulk copies are multiples of 16 bytes");
+        const char* src = reinterpret_cast<const char*>(in1 + tile * (long)(1 << LOG2L) * C);
+        mbar_expect_tx(bar, TILE_BYTES);
+#pragma unroll
+        for (unsigned off = 0; off < TILE_BYTES; off += PIECE) bulk_load_g2s(reinterpret_cast<char*>(smL) + off, src + off, PIECE, bar);
+    }
     template <int LOG2L, int LOGE, int C, int V> __device__ __forceinline__ void init(cplx<T>* smem) const {
         if constexpr (kBins) {
             HistT* hist = reinterpret_cast<HistT*>(reinterpret_cast<char*>(smem) + hist_off);
@@ -1039,7 +1235,7 @@ template <typename T, int MODE> struct ColsFused {
         for (int q = 0; q < (1 << LOGE); ++q) a[q] = __ldg(pa + q * NT);
     }
     template <int LOG2L, int LOGE, int C, int V>
-    __device__ __forceinline__ void fix_apply(long tile, int, int cg, const cplx<T> (&a)[1 << LOGE], cplx<T> (&v)[V][1 << LOGE]) const {
+    __device__ __forceinline__ void fix_apply(long tile, int, int cg, const cplx<T> (&a)[1 << LOGE], cplx<T> (&v)[V][1 << LOGE], float* = nullptr) const {
         if (ag == nullptr) return;
         const long b = tile / ntile;
         const int kx0 = (int)(tile - b * ntile) * C + cg * V;

@@ -45,7 +45,7 @@ template <typename T> int rows_r2c(RowsR2CFused<T> io, int log2M, long nseq, cud
 template <typename T> int rows_c2r(const cplx<T>* in, long in_stride, T* out, long out_stride, int log2M, long nseq, T scale,
                                    cudaStream_t st);
 template <typename T> int rows_c2c_power(const RowsC2CPower<T>& io, int log2L, long nseq, cudaStream_t st);
-template <typename T> int cols_r2c_pack(const ColsR2CPack<T>& io, int log2L, long ntiles, cudaStream_t st);
+template <typename T> int cols_r2c_pack(const ColsR2CPack<T>& io, int log2L, long ntiles, bool use_async, cudaStream_t st);
 template <typename T> int cols_c2c(const cplx<T>* in, cplx<T>* out, int log2L, long A, long B, int inverse, T scale,
                                    cudaStream_t st);
 // one explicit instantiation per (T, MODE), spread over several translation units

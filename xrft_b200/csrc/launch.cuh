@@ -75,7 +75,7 @@ static int launch_cols(const IO& io, long ntiles, cudaStream_t st, size_t extra_
     using G_ = Geometry<LOG2L, LOGE>;
     auto kern = [] { if constexpr (IO::kTwoFields) return cols2f_kernel<T, LOG2L, LOGE, C, IO>; else return cols_kernel<T, LOG2L, LOGE, C, V, IO>; }();
     constexpr int threads = IO::kTwoFields ? G_::NT * C : G_::NT * (C / V);
-    constexpr size_t smem_fixed = (size_t)G_::LPAD * C * sizeof(cplx<T>) * (IO::kTwoFields ? 2 : 1);
+    constexpr size_t smem_fixed = (size_t)G_::LPAD * C * sizeof(cplx<T>) * (IO::kTwoFields ? 2 : 1) + IO::kExtraSmemBytes;
     // bins modes append a histogram of up to kMaxFusedBins (x2 for complex) doubles
     constexpr size_t smem_cap = smem_fixed + (IO::kBins ? (size_t)kMaxFusedBins * 2 * sizeof(double) : 0);
     const size_t smem = smem_fixed + extra_smem;
@@ -98,11 +98,11 @@ static int launch_cols_async(IO io, long ntiles, cudaStream_t st, size_t extra_s
     using G_ = Geometry<LOG2L, LOGE>;
     auto kern = cols_async_kernel<T, LOG2L, LOGE, C, IO>;
     constexpr int threads = G_::NT * (C / 2);
-    constexpr size_t smem_fixed = (size_t)G_::LPAD * (C + C / 2) * sizeof(cplx<T>) + 16;
+    constexpr size_t smem_fixed = (size_t)G_::LPAD * (C + C / 2) * sizeof(cplx<T>) + 16 + IO::kExtraSmemBytes;
     constexpr size_t smem_cap = smem_fixed + (IO::kBins ? (size_t)kMaxFusedBins * 2 * sizeof(double) : 0);
     const size_t smem = smem_fixed + extra_smem;
     if (smem > smem_cap) { set_error("launch_cols_async: too many bins for the fused path"); return -2; }
-    io.hist_off = (int)((size_t)G_::LPAD * (C / 2) * sizeof(cplx<T>) + 16);   // relative to the X buffer
+    if constexpr (IO::kBins) io.hist_off = (int)((size_t)G_::LPAD * (C / 2) * sizeof(cplx<T>) + 16);   // relative to the X buffer
     static int occ = -1;
     if (int rc = prepare_kernel(kern, threads, smem_cap, &occ)) return rc;
     const cplx<T>* tw = twiddle_fft<T>(LOG2L);
