@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--ny", type=int, default=4096)
     ap.add_argument("--nx", type=int, default=4096)
     ap.add_argument("--e2e-time", type=int, default=64, help="time slices per end-to-end step (host buffers)")
-    ap.add_argument("--chunk", type=int, default=8, help="time slices per fused kernel chain (dask chunk {'time':16})")
+    ap.add_argument("--chunk", type=int, default=16, help="time slices per fused kernel chain (the reference's dask chunk {'time':16})")
     ap.add_argument("--cpu-slices", type=int, default=0, help="slices in the CPU sample (0 = one per worker)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -268,11 +268,19 @@ def run_b200(args):
     del out
 
     # ---- roofline of the dominant kernel (achieved algorithmic bytes / CUDA-event duration)
-    names = ["moments_kernel", "rows2_kernel<RowsR2CFused>", "cols_kernel<ColsFused POWER>", "mirror_fill_kernel"]
-    # algorithmic bytes per real-space point each kernel must move: read f32 | read f32 + write c64 half spectrum |
-    # read half spectrum + write the direct half of the f32 output | read + write the mirrored half
-    half = (nx // 2 + 1) / nx
-    bpp = [4.0, 4.0 + 8.0 * half, 8.0 * half + 4.0 * half, 4.0 * (1 - half) * 2]
+    if int(lib.xrftb_spectrum2d_last_path()) == 1:
+        # columns-first chain: completion tables (O(nx) per slice) | pass 2: read the c64 half spectrum rows, write the f32
+        # output | pass 1: read the f32 input, write the c64 half spectrum (ny/2+1 of ny rows) | no mirror pass
+        names = ["rowline_fix_kernel (column-line completion tables)", "rows2c_power_kernel (pass 2: row C2C + |F|^2 + mirrored row)",
+                 "cols_async_kernel<ColsR2CPack> (pass 1: detrend + window + column R2C)", "mirror_fill_kernel (not launched)"]
+        halfy = (ny // 2 + 1) / ny
+        bpp = [0.0, 8.0 * halfy + 4.0, 4.0 + 8.0 * halfy, 0.0]
+    else:
+        names = ["moments_kernel", "rows2_kernel<RowsR2CFused>", "cols_kernel<ColsFused POWER>", "mirror_fill_kernel"]
+        # algorithmic bytes per real-space point each kernel must move: read f32 | read f32 + write c64 half spectrum |
+        # read half spectrum + write the direct half of the f32 output | read + write the mirrored half
+        half = (nx // 2 + 1) / nx
+        bpp = [4.0, 4.0 + 8.0 * half, 8.0 * half + 4.0 * half, 4.0 * (1 - half) * 2]
     peak, peak_src = peaks()
     tot_ms = [float(pms[i]) for i in range(4)]
     dom = int(np.argmax(tot_ms)) if sum(tot_ms) > 0 else 1

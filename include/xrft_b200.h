@@ -59,6 +59,10 @@ long xrftb_launch_count(int reset);
  * summed milliseconds and launch counts for {moments, row pass, column pass, mirror fill}. */
 int xrftb_profile_begin(void);
 int xrftb_profile_end(double ms[4], long counts[4]);
+/* which kernel chain the last xrftb_spectrum2d call took: 0 = rows first (moments | row R2C | column pass | Hermitian
+ * mirror), 1 = columns first (column R2C with column-line detrend | completion tables | row C2C + epilogue, no mirror pass).
+ * In chain 1 the profile classes read {completion tables, row pass = pass 2, column pass = pass 1, unused}. */
+int xrftb_spectrum2d_last_path(void);
 
 /* ---- (S1) np.fft.fftn / ifftn / rfftn / irfftn --------------------------------------------------
  * N-D transform over `axes` of a C-contiguous array.  `shape[ndim]` is the REAL-SPACE shape.

@@ -19,6 +19,7 @@ EXPORTS = [
     "xrftb_launch_count",
     "xrftb_profile_begin",
     "xrftb_profile_end",
+    "xrftb_spectrum2d_last_path",
     "xrftb_fftn_workspace",
     "xrftb_fftn",
     "xrftb_moments",

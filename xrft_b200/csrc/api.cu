@@ -240,7 +240,8 @@ __global__ void __maxnreg__(32) moments_side_kernel(const float* __restrict__ in
 //                        b = c = 0 for detrend=constant) -- the same centred-moment closed form as moments_kernel
 //   still to subtract    plane - ph_i = -(alpha_i + gamma_i (j - jc)),  alpha_i = A0 + B jc - a - b (i - ic), gamma_i = B - c
 // Output: ag[b][i] = w_y(i) (alpha_i, gamma_i); the column pass adds ag.x What(kx) + ag.y Jhat(kx) to row i of the
-// half-spectrum (What, Jhat = transforms of w_x(j) and w_x(j)(j - jc)).  One CTA per item, fp64 throughout.
+// half-spectrum (What, Jhat = transforms of w_x(j) and w_x(j)(j - jc)).  Grid (items, splits): every CTA redoes the
+// small reduction over the item's lines (L2-resident) and completes its share of them; fp64 throughout.
 // ------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) rowline_fix_kernel(const float4* __restrict__ rowstats, cplx<T>* __restrict__ ag, const T* __restrict__ wy,
@@ -277,7 +278,7 @@ __global__ void __launch_bounds__(256) rowline_fix_kernel(const float4* __restri
     const double a = plane[0] / ((double)ny * (double)nx);
     const double bb = (detrend == 2 && ny > 1) ? plane[1] / ((double)nx * vy) : 0.0;
     const double c = (detrend == 2) ? plane[2] / ((double)ny * vx) : 0.0;
-    for (int i = threadIdx.x; i < ny; i += blockDim.x) {
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < ny; i += gridDim.y * blockDim.x) {
         const float4 r = rs[i];
         const double w = wy ? (double)wy[i] : 1.0;
         const double alpha = (double)r.x + (double)r.y * jc - a - bb * ((double)i - ic);
@@ -1019,9 +1020,10 @@ static bool rowline_enabled() {
 }
 
 // "columns first" order (see ColsR2CPack / RowsC2CPower): eligible for the full-width power spectrum
+static std::atomic<int> g_last_path{0};   // 0: rows first (+ Hermitian mirror pass), 1: columns first
 static bool colsfirst_enabled() {
     static int on = -1;
-    if (on < 0) { const char* e = getenv("XRFTB_COLS_FIRST"); on = e ? atoi(e) : 0; }
+    if (on < 0) { const char* e = getenv("XRFTB_COLS_FIRST"); on = e ? atoi(e) : 1; }
     return on != 0;
 }
 template <typename T> static bool colsfirst_eligible(int mode, int keep_half, const void* weight_x, int ly, int lx, int nx) {
@@ -1107,7 +1109,7 @@ static int spectrum2d_colsfirst(const xrftb_spectrum2d_desc& q, int ly, int lx, 
         if (colline) {
             // the row-line completion kernel with the roles of the axes swapped: nx lines (columns) of length ny
             ProfScope ps_(PROF_MOMENTS, st);
-            rowline_fix_kernel<T><<<(unsigned)nb, 256, 0, st>>>(colstats, ag, reinterpret_cast<const T*>(q.win_x), q.nx, q.ny, q.detrend);
+            rowline_fix_kernel<T><<<dim3((unsigned)nb, (unsigned)((q.nx + 1023) / 1024)), 256, 0, st>>>(colstats, ag, reinterpret_cast<const T*>(q.win_x), q.nx, q.ny, q.detrend);
             if (int rc = check_launch("rowline_fix_kernel")) return rc;
         }
         {
@@ -1126,7 +1128,8 @@ static int spectrum2d_impl(const xrftb_spectrum2d_desc& q, cudaStream_t st) {
     if (ly < 1 || lx < 2) { set_error("spectrum2d: ny, nx must be powers of two (ny>=2, nx>=4), got %d x %d", q.ny, q.nx); return XRFTB_EUNSUPPORTED; }
     const bool two = (q.mode == XRFTB_EPI_CROSS || q.mode == XRFTB_EPI_PHASE || q.mode == XRFTB_EPI_BINS_CROSS);
     if (two && !q.in2) { set_error("spectrum2d: mode %d needs in2", q.mode); return XRFTB_EINVAL; }
-    if (colsfirst_enabled() && colsfirst_eligible<T>(q.mode, q.keep_half, q.weight_x, ly, lx, q.nx)) return spectrum2d_colsfirst<T>(q, ly, lx, st);
+    if (colsfirst_enabled() && colsfirst_eligible<T>(q.mode, q.keep_half, q.weight_x, ly, lx, q.nx)) { g_last_path.store(1); return spectrum2d_colsfirst<T>(q, ly, lx, st); }
+    g_last_path.store(0);
     const int C = cols_tile_width<T>(ly, two);
     if (C < 1 || ly > TypeCfg<T>::MAX_COLS_LOG2 || lx - 1 > TypeCfg<T>::MAX_ROWS_LOG2) { set_error("spectrum2d: size %d x %d unsupported", q.ny, q.nx); return XRFTB_EUNSUPPORTED; }
     if (q.shift_x && q.keep_half) { set_error("spectrum2d: shift_x is incompatible with keep_half"); return XRFTB_EINVAL; }
@@ -1232,7 +1235,7 @@ static int spectrum2d_impl(const xrftb_spectrum2d_desc& q, cudaStream_t st) {
         }
         if (rowline) {
             ProfScope ps_(PROF_MOMENTS, st);
-            rowline_fix_kernel<T><<<(unsigned)nb, 256, 0, st>>>(rowstats, ag, reinterpret_cast<const T*>(q.win_y), q.ny, q.nx, q.detrend);
+            rowline_fix_kernel<T><<<dim3((unsigned)nb, (unsigned)((q.ny + 1023) / 1024)), 256, 0, st>>>(rowstats, ag, reinterpret_cast<const T*>(q.win_y), q.ny, q.nx, q.detrend);
             if (int rc = check_launch("rowline_fix_kernel")) return rc;
         }
         if (side && ci + 1 < nchunks) {
@@ -1309,6 +1312,7 @@ int xrftb_profile_end(double* ms, long* counts) {
     return 0;
 }
 const char* xrftb_last_error(void) { return g_err; }
+int xrftb_spectrum2d_last_path(void) { return g_last_path.load(); }
 
 int xrftb_device_info(int* sms, int* major, int* minor, size_t* smem_optin) {
     int dev = 0;

@@ -575,6 +575,79 @@ template <typename T> struct RowsC2R {
     }
 };
 
+// pass 2 of the columns-first order, TWO rows per thread (like rows2_kernel): each thread owns the same E points of two
+// consecutive half-spectrum rows, interleaved in shared memory ([pad(o)][2]) so that every exchange is one 128-bit
+// access for both rows, the stage twiddles are generated once per pair and the completion vector ag is loaded once.
+// Epilogue straight from registers: |F|^2 * scale to output row ky and, reversed, to row -ky (fully coalesced).
+template <typename T> struct RowsC2CPower;
+template <typename T, int LOG2L, int LOGE, int PAIRS>
+__global__ void __launch_bounds__((1 << (LOG2L - LOGE)) * PAIRS, min_blocks_for((1 << (LOG2L - LOGE)) * PAIRS))
+rows2c_power_kernel(RowsC2CPower<T> io, const cplx<T>* __restrict__ tw, long nseq) {
+    using G_ = Geometry<LOG2L, LOGE>;
+    constexpr int E = G_::E, NT = G_::NT, SEQ = 2 * PAIRS, Nx = 1 << LOG2L;
+    constexpr int PAIR_STRIDE = 2 * G_::LPAD + 8;
+    constexpr int R = 1 << G_::LOGR_LAST, G = E / R;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx<T>* smem = reinterpret_cast<cplx<T>*>(smem_raw);
+    const int pr = threadIdx.x / NT, u = threadIdx.x % NT;
+    cplx<T>* sm = smem + pr * PAIR_STRIDE;
+    const long ngroups = (nseq + SEQ - 1) / SEQ;
+    const int Ny = 1 << io.logNy;
+    const int sy = io.shift_y ? Ny / 2 : 0, sx = io.shift_x ? Nx / 2 : 0;
+    for (long grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+        const long nxt = grp + gridDim.x;
+        if (threadIdx.x == 0 && nxt < ngroups) io.template prefetch<LOG2L, SEQ>(nxt * SEQ, nseq);
+        const long seq0 = grp * SEQ + 2 * pr;
+        cplx<T> v[2][E];
+        long bb[2]; int kys[2]; bool act[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            act[r] = seq0 + r < nseq;
+            const cplx<T>* p = io.in + (seq0 + r) * (long)Nx + u;
+#pragma unroll
+            for (int q = 0; q < E; ++q) v[r][q] = act[r] ? p[q * NT] : mk<T>(0, 0);
+            bb[r] = (seq0 + r) / io.H;
+            kys[r] = (int)((seq0 + r) - bb[r] * io.H);
+        }
+        if (io.ag != nullptr) {
+            // completion of the column-line detrend; both rows usually belong to the same item: one ag load serves both
+            cplx<T> W[2], J[2];
+#pragma unroll
+            for (int r = 0; r < 2; ++r) { W[r] = mk<T>(0, 0); J[r] = mk<T>(0, 0); if (act[r]) { W[r] = __ldg(io.wj + 2 * kys[r]); J[r] = __ldg(io.wj + 2 * kys[r] + 1); } }
+            const cplx<T>* pa0 = io.ag + (bb[0] << LOG2L) + u;
+            const bool same = bb[1] == bb[0];
+            const cplx<T>* pa1 = io.ag + ((act[1] ? bb[1] : bb[0]) << LOG2L) + u;
+#pragma unroll
+            for (int q = 0; q < E; ++q) {
+                const cplx<T> a0 = __ldg(pa0 + q * NT);
+                const cplx<T> a1 = same ? a0 : __ldg(pa1 + q * NT);
+                v[0][q].x += a0.x * W[0].x + a0.y * J[0].x; v[0][q].y += a0.x * W[0].y + a0.y * J[0].y;
+                v[1][q].x += a1.x * W[1].x + a1.y * J[1].x; v[1][q].y += a1.x * W[1].y + a1.y * J[1].y;
+            }
+        }
+        block_fft<T, LOG2L, LOGE, 2, 2>(v, u, sm, 1, tw);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            if (!act[r]) continue;
+            const int ky = kys[r];
+            T* rowd = io.out + ((bb[r] << io.logNy) + ((ky + sy) & (Ny - 1))) * (long)Nx;
+            T* rowm = io.out + ((bb[r] << io.logNy) + ((Ny - ky + sy) & (Ny - 1))) * (long)Nx;
+            const bool self = (ky == 0) || (2 * ky == Ny);   // see RowsC2CPower::store_a
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+#pragma unroll
+                for (int t = 0; t < R; ++t) {
+                    const cplx<T> f = v[r][g + t * G];
+                    const T val = (f.x * f.x + f.y * f.y) * io.scale;
+                    const int kx = final_index<LOG2L, LOGE>(u, g, t);
+                    if (!self || 2 * kx <= Nx) rowd[(kx + sx) & (Nx - 1)] = val;
+                    if (!self || (kx > 0 && 2 * kx < Nx)) rowm[(Nx - kx + sx) & (Nx - 1)] = val;
+                }
+        }
+        __syncthreads();   // the exchange buffer is reused by the next group
+    }
+}
+
 // =============================================================================================
 // K-B : columns
 // =============================================================================================

@@ -68,6 +68,25 @@ static int launch_rows2(const RowsR2CFused<T>& io, long nseq, cudaStream_t st) {
     return check_launch("rows2_kernel");
 }
 
+template <typename T, int LOG2L, int PAIRS>
+static int launch_rows2c_power(const RowsC2CPower<T>& io, long nseq, cudaStream_t st) {
+    constexpr int LOGE = cmin(TypeCfg<T>::LOGE, LOG2L);
+    using G_ = Geometry<LOG2L, LOGE>;
+    auto kern = rows2c_power_kernel<T, LOG2L, LOGE, PAIRS>;
+    constexpr int threads = G_::NT * PAIRS;
+    constexpr size_t smem = (size_t)PAIRS * (2 * G_::LPAD + 8) * sizeof(cplx<T>);
+    static int occ = -1;
+    if (int rc = prepare_kernel(kern, threads, smem, &occ)) return rc;
+    const cplx<T>* tw = twiddle_fft<T>(LOG2L);
+    if (!tw) return -3;
+    long ngroups = (nseq + 2 * PAIRS - 1) / (2 * PAIRS);
+    long grid = (long)sm_count() * occ;
+    if (grid > ngroups) grid = ngroups;
+    if (grid < 1) return 0;
+    kern<<<(unsigned)grid, threads, smem, st>>>(io, tw, nseq);
+    return check_launch("rows2c_power_kernel");
+}
+
 template <typename T, int LOG2L, int C, class IO>
 static int launch_cols(const IO& io, long ntiles, cudaStream_t st, size_t extra_smem = 0) {
     constexpr int LOGE = cmin(TypeCfg<T>::LOGE, LOG2L);

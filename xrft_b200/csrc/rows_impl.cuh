@@ -67,6 +67,19 @@ int rows_r2c(RowsR2CFused<T> io, int log2M, long nseq, cudaStream_t st) {
 
 template <typename T>
 int rows_c2c_power(const RowsC2CPower<T>& io, int log2L, long nseq, cudaStream_t st) {
+    // float32: two rows per thread, PAIRS row pairs per 256-thread CTA (XRFTB_ROWS_V2=0 selects the one-row kernel)
+    if constexpr (sizeof(T) == 4) {
+        static int v2 = -1;
+        if (v2 < 0) { const char* e = getenv("XRFTB_ROWS_V2"); v2 = e ? atoi(e) : 1; }
+        if (v2 > 0) {
+            switch (log2L) {
+#define Z(K, P) case K: return launch_rows2c_power<T, K, P>(io, nseq, st);
+                Z(11, 2) Z(12, 1) Z(13, 1)   // measured: shorter rows are faster one row per thread
+#undef Z
+                default: break;
+            }
+        }
+    }
     switch (log2L) {
 #define X(K) case K: return launch_rows<T, K, rows_seq_generic<K, cmin(TypeCfg<T>::LOGE, K)>()>(io, nseq, st);
         XRFTB_ROWS_CASES(X)
