@@ -1026,9 +1026,15 @@ static bool colsfirst_enabled() {
     if (on < 0) { const char* e = getenv("XRFTB_COLS_FIRST"); on = e ? atoi(e) : 1; }
     return on != 0;
 }
+// experiment: start delay (ns) of the second-wave CTAs of pass 1 (which = 0, XRFTB_STAGGER1_NS) / pass 2 (which = 1, XRFTB_STAGGER2_NS)
+static int stagger_knob(int which) {
+    static int v[2] = {-1, -1};
+    if (v[which] < 0) { const char* e = getenv(which ? "XRFTB_STAGGER2_NS" : "XRFTB_STAGGER1_NS"); v[which] = e ? atoi(e) : 0; }
+    return v[which];
+}
 template <typename T> static bool colsfirst_eligible(int mode, int keep_half, const void* weight_x, int ly, int lx, int nx) {
     if (mode != XRFTB_EPI_POWER || keep_half || weight_x) return false;
-    const int C = cols_tile_width<T>(ly, false);
+    const int C = colsfirst_tile_width<T>(ly);
     return C >= 1 && ly >= 1 && ly <= TypeCfg<T>::MAX_COLS_LOG2 && lx >= 1 && lx <= TypeCfg<T>::MAX_ROWS_LOG2 && nx >= 2 * C;
 }
 template <typename T> static size_t colsfirst_item_bytes(int ny, int nx) { return (size_t)(ny / 2 + 1) * nx * sizeof(cplx<T>); }
@@ -1043,7 +1049,9 @@ template <typename T> static size_t colline_fixed_bytes(int ny) {
 template <typename T>
 static int spectrum2d_colsfirst(const xrftb_spectrum2d_desc& q, int ly, int lx, cudaStream_t st) {
     using C_ = cplx<T>;
-    const int C = cols_tile_width<T>(ly, false);
+    int C = colsfirst_tile_width<T>(ly);
+    // half-width tiles exist only for the tensor-map fed kernel (16-byte aligned rows, cuTensorMapEncodeTiled available)
+    if (C != cols_tile_width<T>(ly, false) && (q.nx * sizeof(T)) % 16 != 0) C = cols_tile_width<T>(ly, false);
     const int H = q.ny / 2 + 1;
     // column-line detrend (no moments pass): float32 with two packed columns per thread, ny long enough for the fp64 table transform
     const bool colline = std::is_same<T, float>::value && q.detrend && rowline_enabled() && C >= 2 && ly >= 3;
@@ -1092,6 +1100,7 @@ static int spectrum2d_colsfirst(const xrftb_spectrum2d_desc& q, int ly, int lx, 
     const int tiles_per_item = q.nx / (2 * C);
     for (long b0 = 0; b0 < q.batch; b0 += bchunk) {
         const long nb = (q.batch - b0 < bchunk) ? q.batch - b0 : bchunk;
+        bool zmode = false;
         {
             ColsR2CPack<T> io{in + b0 * item, q.nx, tiles_per_item, q.detrend, mom + b0 * 4,
                               reinterpret_cast<const T*>(q.win_y), reinterpret_cast<const T*>(q.win_x), interm, colstats, 0, {}};
@@ -1099,12 +1108,23 @@ static int spectrum2d_colsfirst(const xrftb_spectrum2d_desc& q, int ly, int lx, 
             static int async_on = -1;
             if (async_on < 0) { const char* e = getenv("XRFTB_COLS_ASYNC"); async_on = e ? atoi(e) : 2; }
             bool use_async = false;
+            io.stagger_ns = stagger_knob(0);
+            {   // waves of row runs pulled into L2 ahead of the tile loads (XRFTB_P1_PREFETCH, 0 = off)
+                static int pf = -1;
+                if (pf < 0) { const char* e = getenv("XRFTB_P1_PREFETCH"); pf = e ? atoi(e) : 0; }
+                io.pf_waves = pf;
+            }
             if (async_on && std::is_same<T, float>::value && ly > TypeCfg<T>::LOGE && C >= 2 && (q.nx * sizeof(T)) % 16 == 0) {
                 const int box_rows = q.ny < 256 ? q.ny : 256;
                 if (encode_out_tmap(&io.tmap, const_cast<T*>(in + b0 * item), nb * q.ny, q.nx, 2 * C, box_rows)) { io.box_rows = box_rows; use_async = true; }
             }
+            // "z" mode: pass 1 stores the packed column spectra, pass 2 separates the real columns in its loads (RowsZPower)
+            static int zpack_on = -1;
+            if (zpack_on < 0) { const char* e = getenv("XRFTB_ZPACK"); zpack_on = e ? atoi(e) : 1; }
+            zmode = use_async && zpack_on && rows_z_supported(lx - 1);
+            io.zout = zmode ? interm : nullptr;
             ProfScope ps_(PROF_COLS, st);
-            if (int rc = cols_r2c_pack<T>(io, ly, nb * tiles_per_item, use_async, st)) return rc;
+            if (int rc = cols_r2c_pack<T>(io, ly, C, nb * tiles_per_item, use_async, st)) return rc;
         }
         if (colline) {
             // the row-line completion kernel with the roles of the axes swapped: nx lines (columns) of length ny
@@ -1112,8 +1132,12 @@ static int spectrum2d_colsfirst(const xrftb_spectrum2d_desc& q, int ly, int lx, 
             rowline_fix_kernel<T><<<dim3((unsigned)nb, (unsigned)((q.nx + 1023) / 1024)), 256, 0, st>>>(colstats, ag, reinterpret_cast<const T*>(q.win_x), q.nx, q.ny, q.detrend);
             if (int rc = check_launch("rowline_fix_kernel")) return rc;
         }
-        {
-            RowsC2CPower<T> io{interm, reinterpret_cast<T*>(q.out) + b0 * item, ly, H, q.shift_y, q.shift_x, (T)q.scale, colline ? ag : nullptr, wj};
+        if (zmode) {
+            RowsZPower<T> io{interm, reinterpret_cast<T*>(q.out) + b0 * item, ly, H, q.shift_y, q.shift_x, (T)q.scale, colline ? ag : nullptr, wj, nullptr};
+            ProfScope ps_(PROF_ROWS, st);
+            if (int rc = rows_z_power<T>(io, lx - 1, nb * H, st)) return rc;
+        } else {
+            RowsC2CPower<T> io{interm, reinterpret_cast<T*>(q.out) + b0 * item, ly, H, q.shift_y, q.shift_x, (T)q.scale, colline ? ag : nullptr, wj, stagger_knob(1)};
             ProfScope ps_(PROF_ROWS, st);
             if (int rc = rows_c2c_power<T>(io, lx, nb * H, st)) return rc;
         }

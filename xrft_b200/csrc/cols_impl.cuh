@@ -31,8 +31,18 @@ int cols_c2c(const cplx<T>* in, cplx<T>* out, int log2L, long A, long B, int inv
 }
 
 template <typename T>
-int cols_r2c_pack(const ColsR2CPack<T>& io, int log2L, long ntiles, bool use_async, cudaStream_t st) {
+int cols_r2c_pack(const ColsR2CPack<T>& io, int log2L, int C, long ntiles, bool use_async, cudaStream_t st) {
     if constexpr (sizeof(T) == 4) {
+        if (use_async && C != cols_tile_width<T>(log2L, false)) {   // half-width tiles (colsfirst_tile_width): two CTAs per SM
+            switch (log2L) {
+#define X(K) case K: if constexpr (K >= 11 && TileC<T, K, false>::value >= 4) { if (C == TileC<T, K, false>::value / 2) return launch_cols_async<T, K, TileC<T, K, false>::value / 2>(io, ntiles, st); } break;
+                XRFTB_COLS_CASES(X)
+#undef X
+                default: break;
+            }
+            set_error("cols_r2c_pack: no half-width variant for length 2^%d, C = %d", log2L, C);
+            return -2;
+        }
         if (use_async) {   // tensor-map fed variant (io.tmap / io.box_rows are set); float32, two packed columns per thread
             switch (log2L) {
 #define X(K) case K: if constexpr (K > TypeCfg<T>::LOGE && TileC<T, K, false>::value >= 2) return launch_cols_async<T, K, TileC<T, K, false>::value>(io, ntiles, st); break;
@@ -44,6 +54,7 @@ int cols_r2c_pack(const ColsR2CPack<T>& io, int log2L, long ntiles, bool use_asy
             return -2;
         }
     }
+    if (C != cols_tile_width<T>(log2L, false)) { set_error("cols_r2c_pack: tile width %d needs the tensor-map fed kernel", C); return -2; }
     switch (log2L) {
 #define X(K) case K: if constexpr (TileC<T, K, false>::value >= 1) return launch_cols<T, K, TileC<T, K, false>::value>(io, ntiles, st); break;
         XRFTB_COLS_CASES(X)

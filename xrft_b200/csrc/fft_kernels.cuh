@@ -594,6 +594,7 @@ rows2c_power_kernel(RowsC2CPower<T> io, const cplx<T>* __restrict__ tw, long nse
     const long ngroups = (nseq + SEQ - 1) / SEQ;
     const int Ny = 1 << io.logNy;
     const int sy = io.shift_y ? Ny / 2 : 0, sx = io.shift_x ? Nx / 2 : 0;
+    if (io.stagger_ns > 0 && blockIdx.x >= gridDim.x / 2) __nanosleep((unsigned)io.stagger_ns);
     for (long grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
         const long nxt = grp + gridDim.x;
         if (threadIdx.x == 0 && nxt < ngroups) io.template prefetch<LOG2L, SEQ>(nxt * SEQ, nseq);
@@ -645,6 +646,108 @@ rows2c_power_kernel(RowsC2CPower<T> io, const cplx<T>* __restrict__ tw, long nse
                 }
         }
         __syncthreads();   // the exchange buffer is reused by the next group
+    }
+}
+
+// Pass 2 of the columns-first order when pass 1 leaves the PACKED column spectra Z[batch][Ny][M] (M = Nx/2 packed columns,
+// ColsR2CPack::zout): row ky of the half-spectrum is A_c[ky] = Z[ky][c] + conj Z[Ny-ky][c] (real column 2c) and
+// B_c[ky] = -i (Z[ky][c] - conj Z[Ny-ky][c]) (real column 2c+1) -- the factors 1/2 and w_x were applied in pass 1 -- and
+// both land in the thread that loaded (Z[ky][c], Z[Ny-ky][c]): the separation costs four additions and no exchange.
+// The row transform of the interleaved sequence (A_0, B_0, A_1, B_1, ...) of length Nx is computed as two M-point
+// transforms (one block_fft call, the two sequences interleaved in shared memory) and a final radix-2 step in registers:
+// F[k] = FA[k] + w^k FB[k], F[k + M] = FA[k] - w^k FB[k], w = exp(-2 pi i / Nx) (table staged in shared memory once per CTA).
+// ROWS half-spectrum rows per CTA, NT = M / E threads each.
+template <typename T> struct RowsZPower {
+    const cplx<T>* z; T* out; int logNy; int H; int shift_y, shift_x; T scale;
+    const cplx<T>* ag; const cplx<T>* wj;   // column-line detrend completion (see RowsC2CPower); nullptr = none
+    const cplx<T>* tw2;                     // exp(-2 pi i k / Nx), k in [0, Nx): twiddle_fft(log2 Nx)
+};
+template <typename T, int LOG2M, int LOGE, int ROWS>
+__global__ void __launch_bounds__((1 << (LOG2M - LOGE)) * ROWS, min_blocks_for((1 << (LOG2M - LOGE)) * ROWS))
+rowsz_power_kernel(RowsZPower<T> io, const cplx<T>* __restrict__ tw, long nseq) {
+    using G_ = Geometry<LOG2M, LOGE>;
+    constexpr int E = G_::E, NT = G_::NT, M = 1 << LOG2M, Nx = 2 * M;
+    constexpr int ROW_STRIDE = 2 * G_::LPAD + 8;
+    constexpr int R = 1 << G_::LOGR_LAST, G = E / R;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx<T>* smem = reinterpret_cast<cplx<T>*>(smem_raw);
+    cplx<T>* smw = smem + ROWS * ROW_STRIDE;   // [M] radix-2 twiddles
+    const int r = threadIdx.x / NT, u = threadIdx.x % NT;
+    cplx<T>* sm = smem + r * ROW_STRIDE;
+    for (int k = threadIdx.x; k < M; k += NT * ROWS) smw[k] = __ldg(io.tw2 + k);
+    __syncthreads();
+    const long ngroups = (nseq + ROWS - 1) / ROWS;
+    const int Ny = 1 << io.logNy;
+    const int sy = io.shift_y ? Ny / 2 : 0, sx = io.shift_x ? Nx / 2 : 0;
+    for (long grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+        const long nxt = grp + gridDim.x;
+        if (threadIdx.x < 2 * ROWS && nxt < ngroups) {   // next group's rows -> L2
+            const long s2 = nxt * ROWS + (threadIdx.x >> 1);
+            if (s2 < nseq) {
+                const long b2 = s2 / io.H;
+                const int k2 = (int)(s2 - b2 * io.H);
+                const int row = (threadIdx.x & 1) ? ((Ny - k2) & (Ny - 1)) : k2;
+                prefetch_l2_bulk(io.z + ((b2 << io.logNy) + row) * (long)M, (unsigned)(M * sizeof(cplx<T>)));
+            }
+        }
+        const long seq = grp * ROWS + r;
+        const bool act = seq < nseq;
+        const long b = act ? seq / io.H : 0;
+        const int ky = act ? (int)(seq - b * io.H) : 0;
+        cplx<T> v[2][E];
+        {
+            const cplx<T>* pa = io.z + ((b << io.logNy) + ky) * (long)M + u;
+            const cplx<T>* pb = io.z + ((b << io.logNy) + ((Ny - ky) & (Ny - 1))) * (long)M + u;
+            cplx<T> za[E], zb[E];
+#pragma unroll
+            for (int q = 0; q < E; ++q) { za[q] = act ? pa[q * NT] : mk<T>(0, 0); zb[q] = act ? pb[q * NT] : mk<T>(0, 0); }
+#pragma unroll
+            for (int q = 0; q < E; ++q) {
+                v[0][q] = mk<T>(za[q].x + zb[q].x, za[q].y - zb[q].y);
+                v[1][q] = mk<T>(za[q].y + zb[q].y, zb[q].x - za[q].x);
+            }
+        }
+        if (io.ag != nullptr && act) {
+            const cplx<T> W = __ldg(io.wj + 2 * ky), J = __ldg(io.wj + 2 * ky + 1);
+            const cplx<T>* pa = io.ag + b * (long)Nx + 2 * u;
+#pragma unroll
+            for (int q = 0; q < E; ++q) {
+                cplx<T> a0, a1;
+                if constexpr (sizeof(T) == 4) {
+                    const float4 a = __ldg(reinterpret_cast<const float4*>(pa + 2 * q * NT));
+                    a0 = mk<T>(a.x, a.y); a1 = mk<T>(a.z, a.w);
+                } else {
+                    a0 = __ldg(pa + 2 * q * NT); a1 = __ldg(pa + 2 * q * NT + 1);
+                }
+                v[0][q].x += a0.x * W.x + a0.y * J.x; v[0][q].y += a0.x * W.y + a0.y * J.y;
+                v[1][q].x += a1.x * W.x + a1.y * J.x; v[1][q].y += a1.x * W.y + a1.y * J.y;
+            }
+        }
+        block_fft<T, LOG2M, LOGE, 2, 2>(v, u, sm, 1, tw);
+        if (act) {
+            T* rowd = io.out + ((b << io.logNy) + ((ky + sy) & (Ny - 1))) * (long)Nx;
+            T* rowm = io.out + ((b << io.logNy) + ((Ny - ky + sy) & (Ny - 1))) * (long)Nx;
+            // rows 0 and Ny/2 are their own mirror image (rowm == rowd): their kx <= Nx/2 half is written and mirrored inside
+            // the row, so the result is exactly symmetric like every other row pair
+            const bool self = (ky == 0) || (2 * ky == Ny);
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+#pragma unroll
+                for (int t = 0; t < R; ++t) {
+                    const int k = final_index<LOG2M, LOGE>(u, g, t);
+                    const cplx<T> fa = v[0][g + t * G];
+                    const cplx<T> wb = cmul(v[1][g + t * G], smw[k]);
+                    const cplx<T> f0 = cadd(fa, wb), f1 = csub(fa, wb);
+                    const T p0 = (f0.x * f0.x + f0.y * f0.y) * io.scale;   // kx = k
+                    const T p1 = (f1.x * f1.x + f1.y * f1.y) * io.scale;   // kx = k + M
+                    rowd[(k + sx) & (Nx - 1)] = p0;
+                    if (!self || k > 0) rowm[(Nx - k + sx) & (Nx - 1)] = p0;
+                    if (!self || k == 0) rowd[(k + M + sx) & (Nx - 1)] = p1;
+                    if (!self) rowm[(M - k + sx) & (Nx - 1)] = p1;
+                }
+        }
+        // block_fft ends with the last gather's barrier only when there are >= 2 stages; the exchange buffer of this row is
+        // rewritten by the next group's first scatter, which every thread reaches only after finishing its own gather
     }
 }
 
@@ -728,12 +831,24 @@ cols_async_kernel(const __grid_constant__ IO io, const cplx<T>* __restrict__ tw,
     io.template init<LOG2L, LOGE, C, 2>(smX);   // ends with a barrier when there is a histogram
     __syncthreads();
     auto issue = [&](long tile) { io.template issue_load<LOG2L, C>(tile, smL, bar); };
+    if constexpr (IO::kSplitEpilogue) io.stagger();
     if (threadIdx.x == 0 && (long)blockIdx.x < ntiles) issue((long)blockIdx.x);
+    if constexpr (IO::kSplitEpilogue) {   // row runs of the waves between the first one and the steady-state prefetch distance
+        if (io.pf_waves > 0 && threadIdx.x < 32)
+            for (int w = 1; w < io.pf_waves; ++w) io.template prefetch_wave<LOG2L, C>((long)w * gridDim.x, ntiles, threadIdx.x);
+    }
     unsigned phase = 0;
     for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long nxt = tile + gridDim.x;
+        if constexpr (IO::kSplitEpilogue) {
+            if (io.pf_waves > 0 && threadIdx.x < 32)
+                io.template prefetch_wave<LOG2L, C>(tile - blockIdx.x + (long)io.pf_waves * gridDim.x, ntiles, threadIdx.x);
+        }
         cplx<T> ag_[E];
         io.template fix_fetch<LOG2L, LOGE>(tile, u, ag_);   // issued before the wait: their latency hides behind it
+        float4 wc4 = make_float4(1.f, 1.f, 1.f, 1.f);
+        float* extra_t = extra;   // IO scratch of this tile (ColsR2CPack: alternate tiles use alternate copies, no barrier needed)
+        if constexpr (IO::kSplitEpilogue) { wc4 = io.template col_fetch<C>(tile, cg); extra_t += phase ? IO::kExtraHalf : 0; }
         mbar_wait(bar, phase);
         phase ^= 1u;
         cplx<T> v[2][E];
@@ -745,12 +860,13 @@ cols_async_kernel(const __grid_constant__ IO io, const cplx<T>* __restrict__ tw,
                 v[1][q] = pl[q * (NT * C) + 1];
             }
         }
-        io.template fix_apply<LOG2L, LOGE, C, 2>(tile, u, cg, ag_, v, extra);
+        io.template fix_apply<LOG2L, LOGE, C, 2>(tile, u, cg, ag_, v, extra_t, smL, wc4);
         io.tma_reads_done();  // asynchronous stores of the previous tile have finished reading the staging buffer X
         StagesAsync<T, LOG2L, LOGE, 0, C>::run(v, u, smL + cg * 2, smX + cg, tw,
                                                [&]() { if (threadIdx.x == 0 && nxt < ntiles) issue(nxt); });
         if constexpr (IO::kSplitEpilogue) {
-            io.template store_split<LOG2L, LOGE, C, NTHR>(tile, u, cg, v, smX, extra);
+            if (io.zout != nullptr) io.template store_z<LOG2L, LOGE, C, NTHR>(tile, u, cg, v, extra_t);
+            else io.template store_split<LOG2L, LOGE, C, NTHR>(tile, u, cg, v, smX, extra_t);
         } else {
             io.template store_a<LOG2L, LOGE, C, 2>(tile, u, cg, v, smX);
             io.template store_b<LOG2L, LOGE, C, NTHR>(tile, smX);
@@ -772,7 +888,7 @@ template <typename T> struct ColsC2C {
     __device__ __forceinline__ void tma_drain() const {}
     template <int LOG2L, int LOGE> __device__ __forceinline__ void fix_fetch(long, int, cplx<T> (&)[1 << LOGE]) const {}
     template <int LOG2L, int LOGE, int C, int V>
-    __device__ __forceinline__ void fix_apply(long, int, int, const cplx<T> (&)[1 << LOGE], cplx<T> (&)[V][1 << LOGE], float* = nullptr) const {}
+    __device__ __forceinline__ void fix_apply(long, int, int, const cplx<T> (&)[1 << LOGE], cplx<T> (&)[V][1 << LOGE], float* = nullptr, const cplx<T>* = nullptr, float4 = make_float4(1.f, 1.f, 1.f, 1.f)) const {}
 
     template <int LOG2L, int LOGE, int C, int V>
     __device__ __forceinline__ void load(long tile, int u, int cg, cplx<T> (&v)[V][1 << LOGE], int) const {
@@ -830,7 +946,9 @@ template <typename T> struct ColsC2C {
 template <typename T> struct ColsR2CPack {
     static constexpr bool kTwoFields = false;
     static constexpr bool kBins = false;
-    static constexpr int kExtraSmemBytes = 8192;   // column-line partial sums [warps][2C][2] + lines [2C][2] (floats)
+    // column-line partial sums [warps][2C][2] + lines [2C][2] (floats), two copies used by alternate tiles (kExtraHalf floats each)
+    static constexpr int kExtraSmemBytes = 9216;
+    static constexpr int kExtraHalf = 1152;
     const T* in;            // [batch][Ny][Nx] real
     int Nx;                 // row length (elements)
     int tiles_per_item;     // Nx / (2 C)
@@ -846,7 +964,68 @@ template <typename T> struct ColsR2CPack {
     // input viewed as [batch * Ny][Nx]; a dense box row = 2C reals = C packed points, i.e. the [ky][C] layout the kernel reads
     int box_rows;
     alignas(64) CUtensorMap tmap;
+    int stagger_ns;         // experiment knob XRFTB_STAGGER_NS: second-wave CTAs start this much later (de-phases co-resident CTAs)
+    // cols_async_kernel, "z" mode (zout != nullptr): the packed column spectra Z[batch][Ny][Nx/2] are stored as they leave the
+    // registers -- no staging, no separation of the two real columns (RowsZPower does it in its loads); w_x / 2 is then
+    // applied here, to the real and imaginary part of the packed input, which commutes with the column transform
+    cplx<T>* zout;
     static constexpr bool kSplitEpilogue = true;
+    // DRAM-friendly feed of the narrow tiles: the tiles [T0, T0 + G) that the G CTAs of the grid load concurrently ("wave")
+    // cover, in every image row, ONE contiguous run of G * 2C reals -- but each CTA asks for its 2C-real piece of a row at
+    // its own time, so DRAM sees isolated 32-byte reads.  Instead every CTA pulls whole row runs of an upcoming wave
+    // into L2 (rows cta, cta + G, ... ; one bulk prefetch per row and item, issued by the lanes of one warp); the tile
+    // loads then hit L2.  pf_waves = how many waves ahead (0 = off).
+    int pf_waves;
+    template <int LOG2L, int C> __device__ __forceinline__ void prefetch_wave(long T0, long ntiles, int lane) const {
+        constexpr int Ny = 1 << LOG2L;
+        const long G = gridDim.x;
+        if (T0 >= ntiles) return;
+        const long T1 = T0 + G < ntiles ? T0 + G : ntiles;
+        for (long t = T0; t < T1;) {
+            const long b = t / tiles_per_item;
+            const int tin = (int)(t - b * tiles_per_item);
+            const long tend = (b + 1) * (long)tiles_per_item < T1 ? (b + 1) * (long)tiles_per_item : T1;
+            const unsigned bytes = (unsigned)((tend - t) * (2 * C) * sizeof(T));
+            const T* base = in + (b << LOG2L) * (long)Nx + tin * (2 * C);
+            for (long r = blockIdx.x + (long)lane * G; r < Ny; r += 32 * G) prefetch_l2_bulk(base + r * Nx, bytes);
+            t = tend;
+        }
+    }
+    template <int C> __device__ __forceinline__ float4 col_fetch(long tile, int cg) const {
+        float4 w = make_float4(1.f, 1.f, 1.f, 1.f);
+        if constexpr (sizeof(T) == 4) {
+            if (zout != nullptr) {
+                w = make_float4(.5f, .5f, .5f, .5f);
+                if (wx != nullptr) {
+                    const long b = tile / tiles_per_item;
+                    const int x0 = (int)(tile - b * tiles_per_item) * (2 * C) + cg * 4;
+                    const float4 a = __ldg(reinterpret_cast<const float4*>(wx + x0));
+                    w = make_float4(.5f * a.x, .5f * a.y, .5f * a.z, .5f * a.w);
+                }
+            }
+        }
+        return w;
+    }
+    template <int LOG2L, int LOGE, int C, int NTHR>
+    __device__ __forceinline__ void store_z(long tile, int u, int cg, cplx<T> (&v)[2][1 << LOGE], const float* extra) const {
+        using G_ = Geometry<LOG2L, LOGE>;
+        constexpr int R = 1 << G_::LOGR_LAST, G = G_::E / R;
+        const long b = tile / tiles_per_item;
+        const int t0 = (int)(tile - b * tiles_per_item);
+        write_colstats<C, NTHR>(b, t0 * (2 * C), extra);
+        const int M = Nx >> 1;
+        cplx<T>* ob = zout + (b << LOG2L) * (long)M + t0 * C + cg * 2;
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+#pragma unroll
+            for (int t = 0; t < R; ++t) {
+                const int ky = final_index<LOG2L, LOGE>(u, g, t);
+                const cplx<T> a = v[0][g + t * G], c = v[1][g + t * G];
+                if constexpr (sizeof(T) == 4) *reinterpret_cast<float4*>(ob + (long)ky * M) = make_float4(a.x, a.y, c.x, c.y);
+                else { ob[(long)ky * M] = a; ob[(long)ky * M + 1] = c; }
+            }
+    }
+    __device__ __forceinline__ void stagger() const { if (stagger_ns > 0 && blockIdx.x >= gridDim.x / 2) __nanosleep((unsigned)stagger_ns); }
     template <int LOG2L, int C> __device__ __forceinline__ void issue_load(long tile, cplx<T>* smL, uint64_t* bar) const {
         constexpr int Ny = 1 << LOG2L;
         const long b = tile / tiles_per_item;
@@ -889,18 +1068,28 @@ template <typename T> struct ColsR2CPack {
     // detrend + w_y(i) on the freshly loaded tile: rows u + q NT, real columns x0 + 2 vv (+1).  w_x(j) is applied when the
     // two spectra of a packed column are separated (store_b).  `extra` = the partial-sum area behind the exchange buffer.
     template <int LOG2L, int LOGE, int C, int V>
-    __device__ __forceinline__ void fix_apply(long tile, int u, int cg, const cplx<T> (&a)[1 << LOGE], cplx<T> (&v)[V][1 << LOGE], float* extra) const {
+    __device__ __forceinline__ void fix_apply(long tile, int u, int cg, const cplx<T> (&a)[1 << LOGE], cplx<T> (&v)[V][1 << LOGE], float* extra,
+                                              const cplx<T>* landed = nullptr, float4 wc4 = make_float4(1.f, 1.f, 1.f, 1.f)) const {
         constexpr int NT = Geometry<LOG2L, LOGE>::NT, Ny = 1 << LOG2L, CG = C / V;
         const long b = tile / tiles_per_item;
         const int x0 = (int)(tile - b * tiles_per_item) * (2 * C) + cg * (2 * V);
         if (colstats != nullptr) {
             if constexpr (sizeof(T) == 4 && V == 2) {
                 if (detrend) {
-                    const float* top = in + (b << LOG2L) * (long)Nx + x0;
-                    const float4 e0 = *reinterpret_cast<const float4*>(top);
-                    const float4 e1 = *reinterpret_cast<const float4*>(top + (long)(Ny - 1) * Nx);
+                    // first and last row of the thread's four real columns: from the landed tile ([row][C] packed points, dense)
+                    // when there is one, else from global memory
+                    float4 e0, e1;
+                    if (landed != nullptr) {
+                        e0 = *reinterpret_cast<const float4*>(landed + cg * 2);
+                        e1 = *reinterpret_cast<const float4*>(landed + (Ny - 1) * C + cg * 2);
+                    } else {
+                        const float* top = in + (b << LOG2L) * (long)Nx + x0;
+                        e0 = *reinterpret_cast<const float4*>(top);
+                        e1 = *reinterpret_cast<const float4*>(top + (long)(Ny - 1) * Nx);
+                    }
                     const float x0v[4] = {e0.x, e0.y, e0.z, e0.w}, x1v[4] = {e1.x, e1.y, e1.z, e1.w};
                     float A0[4], B[4], sx[4] = {0.f, 0.f, 0.f, 0.f}, tq[4] = {0.f, 0.f, 0.f, 0.f};
+                    const float wc[4] = {wc4.x, wc4.y, wc4.z, wc4.w};
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const float m = fmaxf(fabsf(x0v[k]), fabsf(x1v[k]));
@@ -923,7 +1112,7 @@ template <typename T> struct ColsR2CPack {
                             r[k] -= fmaf(B[k], fi, A0[k]);
                             sx[k] += r[k];
                             tq[k] = fmaf((float)q, r[k], tq[k]);
-                            r[k] *= wrow;
+                            r[k] = r[k] * wrow * wc[k];
                         }
                         v[0][q] = mk<T>(r[0], r[1]);
                         v[1][q] = mk<T>(r[2], r[3]);
@@ -980,6 +1169,10 @@ template <typename T> struct ColsR2CPack {
                 }
                 y.x *= wrow;
                 y.y *= wrow;
+                if constexpr (V == 2 && sizeof(T) == 4) {   // z mode: w_x / 2 of the two real columns (1 otherwise: exact)
+                    y.x *= vv == 0 ? wc4.x : wc4.z;
+                    y.y *= vv == 0 ? wc4.y : wc4.w;
+                }
                 v[vv][q] = y;
             }
         }
@@ -1120,6 +1313,7 @@ template <typename T> struct RowsC2CPower {
     // column-line detrend completion: row ky of item b gets ag[b][j].x * wj[2 ky] + ag[b][j].y * wj[2 ky + 1] added at column j
     // (ag = w_x(j) (alpha_j, gamma_j), wj = transforms of w_y(i) and w_y(i)(i - ic)); nullptr = none
     const cplx<T>* ag; const cplx<T>* wj;
+    int stagger_ns;   // see ColsR2CPack::stagger_ns
 
     template <int LOG2L, int SEQ> __device__ __forceinline__ void prefetch(long seq0, long nseq) const {
         constexpr unsigned row_bytes = (unsigned)((1u << LOG2L) * sizeof(cplx<T>));
@@ -1308,7 +1502,7 @@ template <typename T, int MODE> struct ColsFused {
         for (int q = 0; q < (1 << LOGE); ++q) a[q] = __ldg(pa + q * NT);
     }
     template <int LOG2L, int LOGE, int C, int V>
-    __device__ __forceinline__ void fix_apply(long tile, int, int cg, const cplx<T> (&a)[1 << LOGE], cplx<T> (&v)[V][1 << LOGE], float* = nullptr) const {
+    __device__ __forceinline__ void fix_apply(long tile, int, int cg, const cplx<T> (&a)[1 << LOGE], cplx<T> (&v)[V][1 << LOGE], float* = nullptr, const cplx<T>* = nullptr, float4 = make_float4(1.f, 1.f, 1.f, 1.f)) const {
         if (ag == nullptr) return;
         const long b = tile / ntile;
         const int kx0 = (int)(tile - b * ntile) * C + cg * V;

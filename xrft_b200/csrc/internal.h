@@ -31,6 +31,19 @@ template <typename T> inline int cols_tile_width(int log2L, bool two_fields) {
     return c;  // 0 => unsupported
 }
 
+// pass 1 of the columns-first order (ColsR2CPack): tile width in PACKED columns.  XRFTB_P1_NARROW=1 halves the default width
+// where the tensor-map fed kernel exists for it (two 256-thread CTAs per SM instead of one 512-thread CTA at 4096 rows)
+inline int p1_narrow_knob() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("XRFTB_P1_NARROW"); v = e ? atoi(e) : 0; }
+    return v;
+}
+template <typename T> inline int colsfirst_tile_width(int log2L) {
+    int c = cols_tile_width<T>(log2L, false);
+    if (sizeof(T) == 4 && p1_narrow_knob() && log2L >= 11 && c >= 4) c >>= 1;
+    return c;
+}
+
 // the two-rows-per-thread row kernel (float32, blocked output) handles half lengths 2^7..2^12 with 2^(12 - log2M) row pairs
 // per CTA; the 2 * pairs rows of a CTA must be consecutive rows of one item
 inline bool rows2_eligible(int log2M, int logNy) {
@@ -45,7 +58,9 @@ template <typename T> int rows_r2c(RowsR2CFused<T> io, int log2M, long nseq, cud
 template <typename T> int rows_c2r(const cplx<T>* in, long in_stride, T* out, long out_stride, int log2M, long nseq, T scale,
                                    cudaStream_t st);
 template <typename T> int rows_c2c_power(const RowsC2CPower<T>& io, int log2L, long nseq, cudaStream_t st);
-template <typename T> int cols_r2c_pack(const ColsR2CPack<T>& io, int log2L, long ntiles, bool use_async, cudaStream_t st);
+template <typename T> int rows_z_power(RowsZPower<T> io, int log2M, long nseq, cudaStream_t st);
+inline bool rows_z_supported(int log2M) { return log2M >= 9 && log2M <= 12; }
+template <typename T> int cols_r2c_pack(const ColsR2CPack<T>& io, int log2L, int C, long ntiles, bool use_async, cudaStream_t st);
 template <typename T> int cols_c2c(const cplx<T>* in, cplx<T>* out, int log2L, long A, long B, int inverse, T scale,
                                    cudaStream_t st);
 // one explicit instantiation per (T, MODE), spread over several translation units

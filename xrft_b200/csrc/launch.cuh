@@ -87,6 +87,26 @@ static int launch_rows2c_power(const RowsC2CPower<T>& io, long nseq, cudaStream_
     return check_launch("rows2c_power_kernel");
 }
 
+// pass 2 on packed column spectra (rowsz_power_kernel): ROWS half-spectrum rows per CTA, two M-point sequences per thread
+template <typename T, int LOG2M, int ROWS>
+static int launch_rowsz_power(const RowsZPower<T>& io, long nseq, cudaStream_t st) {
+    constexpr int LOGE = cmin(TypeCfg<T>::LOGE, LOG2M);
+    using G_ = Geometry<LOG2M, LOGE>;
+    auto kern = rowsz_power_kernel<T, LOG2M, LOGE, ROWS>;
+    constexpr int threads = G_::NT * ROWS;
+    constexpr size_t smem = ((size_t)ROWS * (2 * G_::LPAD + 8) + (size_t)(1 << LOG2M)) * sizeof(cplx<T>);
+    static int occ = -1;
+    if (int rc = prepare_kernel(kern, threads, smem, &occ)) return rc;
+    const cplx<T>* tw = twiddle_fft<T>(LOG2M);
+    if (!tw) return -3;
+    long ngroups = (nseq + ROWS - 1) / ROWS;
+    long grid = (long)sm_count() * occ;
+    if (grid > ngroups) grid = ngroups;
+    if (grid < 1) return 0;
+    kern<<<(unsigned)grid, threads, smem, st>>>(io, tw, nseq);
+    return check_launch("rowsz_power_kernel");
+}
+
 template <typename T, int LOG2L, int C, class IO>
 static int launch_cols(const IO& io, long ntiles, cudaStream_t st, size_t extra_smem = 0) {
     constexpr int LOGE = cmin(TypeCfg<T>::LOGE, LOG2L);

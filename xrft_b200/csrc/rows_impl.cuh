@@ -92,6 +92,23 @@ int rows_c2c_power(const RowsC2CPower<T>& io, int log2L, long nseq, cudaStream_t
     return -2;
 }
 
+// pass 2 of the columns-first order on packed column spectra (float32; M = Nx/2 in 2^9 .. 2^12)
+template <typename T>
+int rows_z_power(RowsZPower<T> io, int log2M, long nseq, cudaStream_t st) {
+    if constexpr (sizeof(T) == 4) {
+        io.tw2 = twiddle_fft<T>(log2M + 1);
+        if (!io.tw2) return -3;
+        switch (log2M) {
+#define Z(K, P) case K: return launch_rowsz_power<T, K, P>(io, nseq, st);
+            Z(9, 8) Z(10, 4) Z(11, 2) Z(12, 1)
+#undef Z
+            default: break;
+        }
+    }
+    set_error("rows_z_power: unsupported half length 2^%d", log2M);
+    return -2;
+}
+
 template <typename T>
 int rows_c2r(const cplx<T>* in, long in_stride, T* out, long out_stride, int log2M, long nseq, T scale, cudaStream_t st) {
     RowsC2R<T> io{in, in_stride, out, out_stride, scale, twiddle_r2c<T>(log2M + 1)};
