@@ -1123,6 +1123,12 @@ static int spectrum2d_colsfirst(const xrftb_spectrum2d_desc& q, int ly, int lx, 
             if (zpack_on < 0) { const char* e = getenv("XRFTB_ZPACK"); zpack_on = e ? atoi(e) : 1; }
             zmode = use_async && zpack_on && rows_z_supported(lx - 1);
             io.zout = zmode ? interm : nullptr;
+            io.ztma = 0;
+            if (zmode && C * sizeof(C_) >= 32 && q.ny >= 512) {   // tensor stores of Z (XRFTB_ZTMA=0: 16-byte stores from registers)
+                static int ztma_on = -1;
+                if (ztma_on < 0) { const char* e = getenv("XRFTB_ZTMA"); ztma_on = e ? atoi(e) : 1; }
+                if (ztma_on && encode_out_tmap(&io.ztmap, interm, nb * q.ny, q.nx, 2 * C, io.box_rows)) io.ztma = 1;
+            }
             ProfScope ps_(PROF_COLS, st);
             if (int rc = cols_r2c_pack<T>(io, ly, C, nb * tiles_per_item, use_async, st)) return rc;
         }

@@ -43,6 +43,14 @@ int cols_r2c_pack(const ColsR2CPack<T>& io, int log2L, int C, long ntiles, bool 
             set_error("cols_r2c_pack: no half-width variant for length 2^%d, C = %d", log2L, C);
             return -2;
         }
+        if (use_async && io.zout != nullptr && f32x2_enabled() && C == cols_tile_width<T>(log2L, false)) {   // packed FP32x2 z-mode kernel
+            switch (log2L) {
+#define X(K) case K: if constexpr (K > TypeCfg<T>::LOGE && TileC<T, K, false>::value >= 2) return launch_colszp<K, TileC<T, K, false>::value>(io, ntiles, st); break;
+                XRFTB_COLS_CASES(X)
+#undef X
+                default: break;
+            }
+        }
         if (use_async) {   // tensor-map fed variant (io.tmap / io.box_rows are set); float32, two packed columns per thread
             switch (log2L) {
 #define X(K) case K: if constexpr (K > TypeCfg<T>::LOGE && TileC<T, K, false>::value >= 2) return launch_cols_async<T, K, TileC<T, K, false>::value>(io, ntiles, st); break;

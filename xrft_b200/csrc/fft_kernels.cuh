@@ -751,6 +751,88 @@ rowsz_power_kernel(RowsZPower<T> io, const cplx<T>* __restrict__ tw, long nseq) 
     }
 }
 
+// Packed (FP32x2) variant of rowsz_power_kernel: the A and B sequences of a row live in one cplx2 per point, so the
+// separation is one FADD2 + two FADDs per packed column, every butterfly / twiddle product of the two M-point transforms
+// is issued once (FADD2 / FMUL2 / FFMA2), and |F|^2 of the output pair (kx, kx + M) is three packed instructions.
+template <int LOG2M, int LOGE, int ROWS>
+__global__ void __launch_bounds__((1 << (LOG2M - LOGE)) * ROWS, min_blocks_for((1 << (LOG2M - LOGE)) * ROWS))
+rowszp_power_kernel(RowsZPower<float> io, const float2* __restrict__ tw, long nseq) {
+    using G_ = Geometry<LOG2M, LOGE>;
+    constexpr int E = G_::E, NT = G_::NT, M = 1 << LOG2M, Nx = 2 * M;
+    constexpr int ROW_STRIDE = G_::LPAD + 4;   // float4 per point
+    constexpr int R = 1 << G_::LOGR_LAST, G = E / R;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4* smem = reinterpret_cast<float4*>(smem_raw);
+    float2* smw = reinterpret_cast<float2*>(smem + ROWS * ROW_STRIDE);   // [M] radix-2 twiddles
+    const int r = threadIdx.x / NT, u = threadIdx.x % NT;
+    float4* sm = smem + r * ROW_STRIDE;
+    for (int k = threadIdx.x; k < M; k += NT * ROWS) smw[k] = __ldg(io.tw2 + k);
+    __syncthreads();
+    const long ngroups = (nseq + ROWS - 1) / ROWS;
+    const int Ny = 1 << io.logNy;
+    const int sy = io.shift_y ? Ny / 2 : 0, sx = io.shift_x ? Nx / 2 : 0;
+    for (long grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+        const long nxt = grp + gridDim.x;
+        if (threadIdx.x < 2 * ROWS && nxt < ngroups) {   // next group's rows -> L2
+            const long s2 = nxt * ROWS + (threadIdx.x >> 1);
+            if (s2 < nseq) {
+                const long b2 = s2 / io.H;
+                const int k2 = (int)(s2 - b2 * io.H);
+                const int row = (threadIdx.x & 1) ? ((Ny - k2) & (Ny - 1)) : k2;
+                prefetch_l2_bulk(io.z + ((b2 << io.logNy) + row) * (long)M, (unsigned)(M * sizeof(float2)));
+            }
+        }
+        const long seq = grp * ROWS + r;
+        const bool act = seq < nseq;
+        const long b = act ? seq / io.H : 0;
+        const int ky = act ? (int)(seq - b * io.H) : 0;
+        cplx2 v[E];
+        {
+            const float2* pa = io.z + ((b << io.logNy) + ky) * (long)M + u;
+            const float2* pb = io.z + ((b << io.logNy) + ((Ny - ky) & (Ny - 1))) * (long)M + u;
+            float2 za[E], zb[E];
+#pragma unroll
+            for (int q = 0; q < E; ++q) { za[q] = act ? pa[q * NT] : make_float2(0.f, 0.f); zb[q] = act ? pb[q * NT] : make_float2(0.f, 0.f); }
+#pragma unroll
+            for (int q = 0; q < E; ++q) {
+                v[q].x.v = __fadd2_rn(za[q], zb[q]);                              // (A.x, B.x)
+                v[q].y = mk2(za[q].y - zb[q].y, zb[q].x - za[q].x);               // (A.y, B.y)
+            }
+        }
+        if (io.ag != nullptr && act) {
+            const float2 W = __ldg(io.wj + 2 * ky), J = __ldg(io.wj + 2 * ky + 1);
+            const float2* pa = io.ag + b * (long)Nx + 2 * u;
+#pragma unroll
+            for (int q = 0; q < E; ++q) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(pa + 2 * q * NT));   // (alpha, gamma) of columns 2c, 2c+1
+                v[q].x.v.x += a.x * W.x + a.y * J.x; v[q].y.v.x += a.x * W.y + a.y * J.y;
+                v[q].x.v.y += a.z * W.x + a.w * J.x; v[q].y.v.y += a.z * W.y + a.w * J.y;
+            }
+        }
+        block_fft_p<LOG2M, LOGE>(v, u, sm, tw);
+        if (act) {
+            float* rowd = io.out + ((b << io.logNy) + ((ky + sy) & (Ny - 1))) * (long)Nx;
+            float* rowm = io.out + ((b << io.logNy) + ((Ny - ky + sy) & (Ny - 1))) * (long)Nx;
+            const bool self = (ky == 0) || (2 * ky == Ny);   // see rowsz_power_kernel
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+#pragma unroll
+                for (int t = 0; t < R; ++t) {
+                    const int k = final_index<LOG2M, LOGE>(u, g, t);
+                    const cplx2 c = v[g + t * G];
+                    const float2 w = smw[k];
+                    const float wbx = c.x.v.y * w.x - c.y.v.y * w.y, wby = c.x.v.y * w.y + c.y.v.y * w.x;   // w^k FB[k]
+                    const f32x2 fx = mk2(c.x.v.x + wbx, c.x.v.x - wbx), fy = mk2(c.y.v.x + wby, c.y.v.x - wby);  // (F[k], F[k+M])
+                    const f32x2 pw = (fx * fx + fy * fy) * io.scale;
+                    rowd[(k + sx) & (Nx - 1)] = pw.v.x;
+                    if (!self || k > 0) rowm[(Nx - k + sx) & (Nx - 1)] = pw.v.x;
+                    if (!self || k == 0) rowd[(k + M + sx) & (Nx - 1)] = pw.v.y;
+                    if (!self) rowm[(M - k + sx) & (Nx - 1)] = pw.v.y;
+                }
+        }
+    }
+}
+
 // =============================================================================================
 // K-B : columns
 // =============================================================================================
@@ -865,7 +947,10 @@ cols_async_kernel(const __grid_constant__ IO io, const cplx<T>* __restrict__ tw,
         StagesAsync<T, LOG2L, LOGE, 0, C>::run(v, u, smL + cg * 2, smX + cg, tw,
                                                [&]() { if (threadIdx.x == 0 && nxt < ntiles) issue(nxt); });
         if constexpr (IO::kSplitEpilogue) {
-            if (io.zout != nullptr) io.template store_z<LOG2L, LOGE, C, NTHR>(tile, u, cg, v, extra_t);
+            if (io.zout != nullptr) {
+                if (io.ztma) io.template store_z_tma<LOG2L, LOGE, C, NTHR>(tile, u, cg, v, smX, extra_t);
+                else io.template store_z<LOG2L, LOGE, C, NTHR>(tile, u, cg, v, extra_t);
+            }
             else io.template store_split<LOG2L, LOGE, C, NTHR>(tile, u, cg, v, smX, extra_t);
         } else {
             io.template store_a<LOG2L, LOGE, C, 2>(tile, u, cg, v, smX);
@@ -969,7 +1054,48 @@ template <typename T> struct ColsR2CPack {
     // registers -- no staging, no separation of the two real columns (RowsZPower does it in its loads); w_x / 2 is then
     // applied here, to the real and imaginary part of the packed input, which commutes with the column transform
     cplx<T>* zout;
+    // z mode, rows of >= 32 bytes: Z is written by TMA tensor stores (SASS UTMASTG) from the half-size buffer, half a tile
+    // at a time -- the LSU never sees the 4096 scattered 32-byte row segments of a tile.  ztmap describes Z as
+    // [batch * Ny][Nx] floats with the box of the input map.
+    int ztma;
+    alignas(64) CUtensorMap ztmap;
     static constexpr bool kSplitEpilogue = true;
+    template <int LOG2L, int LOGE, int C, int NTHR>
+    __device__ __forceinline__ void store_z_tma(long tile, int u, int cg, cplx<T> (&v)[2][1 << LOGE], cplx<T>* smX, const float* extra) const {
+        using G_ = Geometry<LOG2L, LOGE>;
+        constexpr int R = 1 << G_::LOGR_LAST, G = G_::E / R, Ny = 1 << LOG2L, HALF = Ny / 2;
+        const long b = tile / tiles_per_item;
+        const int t0 = (int)(tile - b * tiles_per_item);
+        write_colstats<C, NTHR>(b, t0 * (2 * C), extra);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            if (half == 1) {   // the stores of the first half have finished reading the buffer
+                if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncthreads();
+            }
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+#pragma unroll
+                for (int t = 0; t < R; ++t) {
+                    const int ky = final_index<LOG2L, LOGE>(u, g, t);
+                    if ((ky >= HALF) == (half == 1)) {
+                        const cplx<T> a = v[0][g + t * G], c = v[1][g + t * G];
+                        if constexpr (sizeof(T) == 4)
+                            *reinterpret_cast<float4*>(smX + (ky - half * HALF) * C + cg * 2) = make_float4(a.x, a.y, c.x, c.y);
+                    }
+                }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async-proxy (TMA) reads
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                const unsigned sbase = (unsigned)__cvta_generic_to_shared(smX);
+                const int row0 = (int)(b << LOG2L) + half * HALF;
+                for (int r0 = 0; r0 < HALF; r0 += box_rows)
+                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                                 :: "l"(&ztmap), "r"(t0 * (2 * C)), "r"(row0 + r0), "r"(sbase + (unsigned)(r0 * C * sizeof(cplx<T>))) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        }
+    }
     // DRAM-friendly feed of the narrow tiles: the tiles [T0, T0 + G) that the G CTAs of the grid load concurrently ("wave")
     // cover, in every image row, ONE contiguous run of G * 2C reals -- but each CTA asks for its 2C-real piece of a row at
     // its own time, so DRAM sees isolated 32-byte reads.  Instead every CTA pulls whole row runs of an upcoming wave
@@ -1037,8 +1163,14 @@ template <typename T> struct ColsR2CPack {
 
     template <int LOG2L, int C> __device__ __forceinline__ void prefetch(long) const {}
     template <int LOG2L, int LOGE, int C, int V> __device__ __forceinline__ void init(cplx<T>*) const {}
-    __device__ __forceinline__ void tma_reads_done() const {}
-    __device__ __forceinline__ void tma_drain() const {}
+    // z mode with tensor stores: the previous tile's stores may still be reading the half-size buffer; only thread 0 waits,
+    // the barriers of exchange #0 (which precede every write of that buffer) publish it to the CTA
+    __device__ __forceinline__ void tma_reads_done() const {
+        if (ztma && threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+    __device__ __forceinline__ void tma_drain() const {
+        if (ztma && threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
     // window factors of the rows this thread owns, fetched ahead of use
     template <int LOG2L, int LOGE> __device__ __forceinline__ void fix_fetch(long, int u, cplx<T> (&a)[1 << LOGE]) const {
         constexpr int NT = Geometry<LOG2L, LOGE>::NT;
@@ -1305,6 +1437,71 @@ template <typename T> struct ColsR2CPack {
         __syncthreads();
     }
 };
+
+// Packed (FP32x2) pass 1 of the columns-first order in z mode (ColsR2CPack<float>::zout): cols_async_kernel with the two
+// packed columns of a thread held as one cplx2 per row from the first butterfly to the store -- every butterfly and
+// twiddle product is issued once for both columns.  The landed rows (x0, y0, x1, y1) are re-paired to (x0, x1), (y0, y1)
+// after the detrend / window prologue and paired back in the 16-byte stores of Z.
+template <int LOG2L, int LOGE, int C>
+__global__ void __launch_bounds__((1 << (LOG2L - LOGE)) * (C / 2), min_blocks_for((1 << (LOG2L - LOGE)) * (C / 2)))
+colszp_kernel(const __grid_constant__ ColsR2CPack<float> io, const float2* __restrict__ tw, long ntiles) {
+    using IO = ColsR2CPack<float>;
+    using G_ = Geometry<LOG2L, LOGE>;
+    constexpr int E = G_::E, CG = C / 2, NT = G_::NT, NTHR = NT * CG;
+    constexpr int R = 1 << G_::LOGR_LAST, G = E / R;
+    static_assert(LOG2L > LOGE, "needs at least one exchange");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float2* smL = reinterpret_cast<float2*>(smem_raw);
+    float2* smX = smL + G_::LPAD * C;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smX + G_::LPAD * CG);
+    float* extra = reinterpret_cast<float*>(bar + 2);
+    const int cg = threadIdx.x % CG, u = threadIdx.x / CG;
+    if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_init_fence(); }
+    __syncthreads();
+    auto issue = [&](long tile) { io.template issue_load<LOG2L, C>(tile, smL, bar); };
+    if (threadIdx.x == 0 && (long)blockIdx.x < ntiles) issue((long)blockIdx.x);
+    unsigned phase = 0;
+    const int M = io.Nx >> 1;
+    for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long nxt = tile + gridDim.x;
+        float2 ag_[E];
+        io.template fix_fetch<LOG2L, LOGE>(tile, u, ag_);   // issued before the wait: their latency hides behind it
+        const float4 wc4 = io.template col_fetch<C>(tile, cg);
+        float* extra_t = extra + (phase ? IO::kExtraHalf : 0);
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+        cplx2 v[E];
+        {
+            float2 vv[2][E];
+            const float2* pl = smL + u * C + cg * 2;
+#pragma unroll
+            for (int q = 0; q < E; ++q) {
+                const float4 f = *reinterpret_cast<const float4*>(pl + q * (NT * C));
+                vv[0][q] = make_float2(f.x, f.y);
+                vv[1][q] = make_float2(f.z, f.w);
+            }
+            io.template fix_apply<LOG2L, LOGE, C, 2>(tile, u, cg, ag_, vv, extra_t, smL, wc4);
+#pragma unroll
+            for (int q = 0; q < E; ++q) { v[q].x = mk2(vv[0][q].x, vv[1][q].x); v[q].y = mk2(vv[0][q].y, vv[1][q].y); }
+        }
+        StagesAsyncP<LOG2L, LOGE, 0, C>::run(v, u, reinterpret_cast<float4*>(smL) + cg, smX + cg, tw,
+                                             [&]() { if (threadIdx.x == 0 && nxt < ntiles) issue(nxt); });
+        {
+            const long b = tile / io.tiles_per_item;
+            const int t0 = (int)(tile - b * io.tiles_per_item);
+            io.template write_colstats<C, NTHR>(b, t0 * (2 * C), extra_t);
+            float2* ob = io.zout + (b << LOG2L) * (long)M + t0 * C + cg * 2;
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+#pragma unroll
+                for (int t = 0; t < R; ++t) {
+                    const int ky = final_index<LOG2L, LOGE>(u, g, t);
+                    const cplx2 c = v[g + t * G];
+                    *reinterpret_cast<float4*>(ob + (long)ky * M) = make_float4(c.x.v.x, c.y.v.x, c.x.v.y, c.y.v.y);
+                }
+        }
+    }
+}
 
 // pass 2: rows of the half-spectrum [batch][H][Nx] complex -> power spectrum rows ky and -ky of out [batch][Ny][Nx] real
 template <typename T> struct RowsC2CPower {

@@ -38,6 +38,13 @@ inline int p1_narrow_knob() {
     if (v < 0) { const char* e = getenv("XRFTB_P1_NARROW"); v = e ? atoi(e) : 0; }
     return v;
 }
+// packed FP32x2 (FADD2 / FMUL2 / FFMA2) kernels of the z-mode chain: measured 4-7 % SLOWER than the scalar ones on B200
+// (profiles/README.md), so they are off unless XRFTB_F32X2=1
+inline bool f32x2_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("XRFTB_F32X2"); v = e ? atoi(e) : 0; }
+    return v != 0;
+}
 template <typename T> inline int colsfirst_tile_width(int log2L) {
     int c = cols_tile_width<T>(log2L, false);
     if (sizeof(T) == 4 && p1_narrow_knob() && log2L >= 11 && c >= 4) c >>= 1;

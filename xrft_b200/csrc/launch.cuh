@@ -107,6 +107,26 @@ static int launch_rowsz_power(const RowsZPower<T>& io, long nseq, cudaStream_t s
     return check_launch("rowsz_power_kernel");
 }
 
+// packed (FP32x2) variant of launch_rowsz_power (float32)
+template <int LOG2M, int ROWS>
+static int launch_rowszp_power(const RowsZPower<float>& io, long nseq, cudaStream_t st) {
+    constexpr int LOGE = cmin(TypeCfg<float>::LOGE, LOG2M);
+    using G_ = Geometry<LOG2M, LOGE>;
+    auto kern = rowszp_power_kernel<LOG2M, LOGE, ROWS>;
+    constexpr int threads = G_::NT * ROWS;
+    constexpr size_t smem = (size_t)ROWS * (G_::LPAD + 4) * sizeof(float4) + (size_t)(1 << LOG2M) * sizeof(float2);
+    static int occ = -1;
+    if (int rc = prepare_kernel(kern, threads, smem, &occ)) return rc;
+    const float2* tw = twiddle_fft<float>(LOG2M);
+    if (!tw) return -3;
+    long ngroups = (nseq + ROWS - 1) / ROWS;
+    long grid = (long)sm_count() * occ;
+    if (grid > ngroups) grid = ngroups;
+    if (grid < 1) return 0;
+    kern<<<(unsigned)grid, threads, smem, st>>>(io, tw, nseq);
+    return check_launch("rowszp_power_kernel");
+}
+
 template <typename T, int LOG2L, int C, class IO>
 static int launch_cols(const IO& io, long ntiles, cudaStream_t st, size_t extra_smem = 0) {
     constexpr int LOGE = cmin(TypeCfg<T>::LOGE, LOG2L);
@@ -151,6 +171,26 @@ static int launch_cols_async(IO io, long ntiles, cudaStream_t st, size_t extra_s
     if (grid < 1) return 0;
     kern<<<(unsigned)grid, threads, smem, st>>>(io, tw, ntiles);
     return check_launch("cols_async_kernel");
+}
+
+// packed (FP32x2) pass 1 in z mode: same shared-memory plan as launch_cols_async
+template <int LOG2L, int C>
+static int launch_colszp(const ColsR2CPack<float>& io, long ntiles, cudaStream_t st) {
+    using IO = ColsR2CPack<float>;
+    constexpr int LOGE = cmin(TypeCfg<float>::LOGE, LOG2L);
+    using G_ = Geometry<LOG2L, LOGE>;
+    auto kern = colszp_kernel<LOG2L, LOGE, C>;
+    constexpr int threads = G_::NT * (C / 2);
+    constexpr size_t smem = (size_t)G_::LPAD * (C + C / 2) * sizeof(float2) + 16 + IO::kExtraSmemBytes;
+    static int occ = -1;
+    if (int rc = prepare_kernel(kern, threads, smem, &occ)) return rc;
+    const float2* tw = twiddle_fft<float>(LOG2L);
+    if (!tw) return -3;
+    long grid = (long)sm_count() * occ;
+    if (grid > ntiles) grid = ntiles;
+    if (grid < 1) return 0;
+    kern<<<(unsigned)grid, threads, smem, st>>>(io, tw, ntiles);
+    return check_launch("colszp_kernel");
 }
 
 }  // namespace xrftb

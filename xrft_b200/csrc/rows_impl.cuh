@@ -98,6 +98,14 @@ int rows_z_power(RowsZPower<T> io, int log2M, long nseq, cudaStream_t st) {
     if constexpr (sizeof(T) == 4) {
         io.tw2 = twiddle_fft<T>(log2M + 1);
         if (!io.tw2) return -3;
+        if (f32x2_enabled()) {   // packed FP32x2 butterflies (XRFTB_F32X2=0 selects the scalar kernel)
+            switch (log2M) {
+#define Z(K, P) case K: return launch_rowszp_power<K, P>(io, nseq, st);
+                Z(9, 8) Z(10, 4) Z(11, 2) Z(12, 1)
+#undef Z
+                default: break;
+            }
+        }
         switch (log2M) {
 #define Z(K, P) case K: return launch_rowsz_power<T, K, P>(io, nseq, st);
             Z(9, 8) Z(10, 4) Z(11, 2) Z(12, 1)
