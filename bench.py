@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--ny", type=int, default=4096)
     ap.add_argument("--nx", type=int, default=4096)
     ap.add_argument("--e2e-time", type=int, default=64, help="time slices per end-to-end step (host buffers)")
-    ap.add_argument("--chunk", type=int, default=16, help="time slices per fused kernel chain (the reference's dask chunk {'time':16})")
+    ap.add_argument("--chunk", type=int, default=32, help="time slices per fused kernel chain (bounds the workspace: 64 MiB per 4096^2 slice)")
     ap.add_argument("--cpu-slices", type=int, default=0, help="slices in the CPU sample (0 = one per worker)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -268,7 +268,14 @@ def run_b200(args):
     del out
 
     # ---- roofline of the dominant kernel (achieved algorithmic bytes / CUDA-event duration)
-    if int(lib.xrftb_spectrum2d_last_path()) == 1:
+    last_path = int(lib.xrftb_spectrum2d_last_path())
+    if last_path == 2:
+        # columns-first chain, z mode: pass 1 reads the f32 input and writes the packed column spectra Z (ny x nx/2 c64 =
+        # 4 B/point) | pass 2 reads Z and writes the f32 output | completion tables O(nx) per slice | no mirror pass
+        names = ["rowline_fix_kernel (column-line completion tables)", "rowsz_power_kernel (pass 2: column separation + row FFT + |F|^2 + mirrored row)",
+                 "cols_async_kernel<ColsR2CPack> (pass 1: detrend + window + packed column FFT, TMA in / TMA out)", "mirror_fill_kernel (not launched)"]
+        bpp = [0.0, 4.0 + 4.0, 4.0 + 4.0, 0.0]
+    elif last_path == 1:
         # columns-first chain: completion tables (O(nx) per slice) | pass 2: read the c64 half spectrum rows, write the f32
         # output | pass 1: read the f32 input, write the c64 half spectrum (ny/2+1 of ny rows) | no mirror pass
         names = ["rowline_fix_kernel (column-line completion tables)", "rows2c_power_kernel (pass 2: row C2C + |F|^2 + mirrored row)",

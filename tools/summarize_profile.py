@@ -44,7 +44,10 @@ for d in data:
         b = tobytes("dram__bytes_read.sum") + tobytes("dram__bytes_write.sum")
         t = tosec("gpu__time_duration.sum")
         md.append(f"- **dram traffic per launch: {b/1e6:.1f} MB = {b/pts_per_launch:.2f} B/point; {b/t/1e9:.0f} GB/s while running**")
-        cls = "moments_kernel" if "moments" in name else "rows2_kernel<RowsR2CFused>" if "rows" in name else "cols_kernel<ColsFused POWER>" if "cols_kernel" in name else "mirror_fill_kernel"
+        cls = ("moments_kernel" if "moments" in name else
+               "rowsz_power_kernel (pass 2: column separation + row FFT + |F|^2 + mirrored row)" if "rowsz" in name else
+               "cols_async_kernel<ColsR2CPack> (pass 1: detrend + window + packed column FFT, TMA in / TMA out)" if "cols_async_kernel" in name and "ColsR2CPack" in name else
+               "rows2_kernel<RowsR2CFused>" if "rows" in name else "cols_kernel<ColsFused POWER>" if "cols_kernel" in name else "mirror_fill_kernel")
         traffic[cls] = {"dram_bytes_per_point": b / pts_per_launch, "launch_us": t * 1e6}
     except Exception as e:
         md.append(f"- (traffic parse failed: {e})")

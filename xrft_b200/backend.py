@@ -255,7 +255,7 @@ def binned_sum(arr: torch.Tensor, lut: torch.Tensor, nbins: int, ncore: int) -> 
 # fused hot path
 # ---------------------------------------------------------------------------------------------
 _WORK = {}
-_FUSED_CHUNK = 16  # batch items (dask-style chunks along the outer axis) per fused kernel chain
+_FUSED_CHUNK = 32  # batch items (dask-style chunks along the outer axis) per fused kernel chain (measured: 16 -> 32 is +3-4 %)
 
 
 def set_fused_chunk(n: int):

@@ -1020,7 +1020,7 @@ static bool rowline_enabled() {
 }
 
 // "columns first" order (see ColsR2CPack / RowsC2CPower): eligible for the full-width power spectrum
-static std::atomic<int> g_last_path{0};   // 0: rows first (+ Hermitian mirror pass), 1: columns first
+static std::atomic<int> g_last_path{0};   // 0: rows first (+ Hermitian mirror pass), 1: columns first, 2: columns first, packed column spectra (z mode)
 static bool colsfirst_enabled() {
     static int on = -1;
     if (on < 0) { const char* e = getenv("XRFTB_COLS_FIRST"); on = e ? atoi(e) : 1; }
@@ -1123,11 +1123,13 @@ static int spectrum2d_colsfirst(const xrftb_spectrum2d_desc& q, int ly, int lx, 
             if (zpack_on < 0) { const char* e = getenv("XRFTB_ZPACK"); zpack_on = e ? atoi(e) : 1; }
             zmode = use_async && zpack_on && rows_z_supported(lx - 1);
             io.zout = zmode ? interm : nullptr;
+            if (zmode) g_last_path.store(2);
             io.ztma = 0;
             if (zmode && C * sizeof(C_) >= 32 && q.ny >= 512) {   // tensor stores of Z (XRFTB_ZTMA=0: 16-byte stores from registers)
                 static int ztma_on = -1;
                 if (ztma_on < 0) { const char* e = getenv("XRFTB_ZTMA"); ztma_on = e ? atoi(e) : 1; }
-                if (ztma_on && encode_out_tmap(&io.ztmap, interm, nb * q.ny, q.nx, 2 * C, io.box_rows)) io.ztma = 1;
+                const int zbox = q.ny / 4 < 256 ? q.ny / 4 : 256;
+                if (ztma_on && encode_out_tmap(&io.ztmap, interm, nb * q.ny, q.nx, 2 * C, zbox)) { io.ztma = 1; io.zbox_rows = zbox; }
             }
             ProfScope ps_(PROF_COLS, st);
             if (int rc = cols_r2c_pack<T>(io, ly, C, nb * tiles_per_item, use_async, st)) return rc;
@@ -1139,7 +1141,13 @@ static int spectrum2d_colsfirst(const xrftb_spectrum2d_desc& q, int ly, int lx, 
             if (int rc = check_launch("rowline_fix_kernel")) return rc;
         }
         if (zmode) {
-            RowsZPower<T> io{interm, reinterpret_cast<T*>(q.out) + b0 * item, ly, H, q.shift_y, q.shift_x, (T)q.scale, colline ? ag : nullptr, wj, nullptr};
+            RowsZPower<T> io{interm, reinterpret_cast<T*>(q.out) + b0 * item, ly, H, q.shift_y, q.shift_x, (T)q.scale, colline ? ag : nullptr, wj, nullptr, 0};
+            {   // XRFTB_P2_BULK=1: rows staged in shared memory and written by bulk copies (measured 8 % slower than the
+                // 4-byte stores from registers: the staging barriers cost more than the stores)
+                static int bulk_on = -1;
+                if (bulk_on < 0) { const char* e = getenv("XRFTB_P2_BULK"); bulk_on = e ? atoi(e) : 0; }
+                io.bulk = bulk_on;
+            }
             ProfScope ps_(PROF_ROWS, st);
             if (int rc = rows_z_power<T>(io, lx - 1, nb * H, st)) return rc;
         } else {

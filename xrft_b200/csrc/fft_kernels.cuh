@@ -661,6 +661,7 @@ template <typename T> struct RowsZPower {
     const cplx<T>* z; T* out; int logNy; int H; int shift_y, shift_x; T scale;
     const cplx<T>* ag; const cplx<T>* wj;   // column-line detrend completion (see RowsC2CPower); nullptr = none
     const cplx<T>* tw2;                     // exp(-2 pi i k / Nx), k in [0, Nx): twiddle_fft(log2 Nx)
+    int bulk;                               // rowsz_power_kernel: rows staged in shared memory and written by bulk copies (TMA)
 };
 template <typename T, int LOG2M, int LOGE, int ROWS>
 __global__ void __launch_bounds__((1 << (LOG2M - LOGE)) * ROWS, min_blocks_for((1 << (LOG2M - LOGE)) * ROWS))
@@ -723,7 +724,53 @@ rowsz_power_kernel(RowsZPower<T> io, const cplx<T>* __restrict__ tw, long nseq) 
                 v[1][q].x += a1.x * W.x + a1.y * J.x; v[1][q].y += a1.x * W.y + a1.y * J.y;
             }
         }
+        if (io.bulk) {   // the bulk stores of the previous group have finished reading the exchange buffer (their staging area)
+            if (u == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncthreads();
+        }
         block_fft<T, LOG2M, LOGE, 2, 2>(v, u, sm, 1, tw);
+        if (io.bulk) {
+            // Output rows staged in shared memory in their final (fftshift-ed) order -- the direct row, then its Hermitian
+            // mirror -- and written by one bulk copy (TMA) each: 16 KB contiguous instead of 4-byte stores.
+            T* sd = reinterpret_cast<T*>(sm);
+            T* smr = sd + Nx;
+            const bool self = (ky == 0) || (2 * ky == Ny);
+            if (act) {
+#pragma unroll
+                for (int g = 0; g < G; ++g)
+#pragma unroll
+                    for (int t = 0; t < R; ++t) {
+                        const int k = final_index<LOG2M, LOGE>(u, g, t);
+                        const cplx<T> fa = v[0][g + t * G];
+                        const cplx<T> wb = cmul(v[1][g + t * G], smw[k]);
+                        const cplx<T> f0 = cadd(fa, wb), f1 = csub(fa, wb);
+                        const T p0 = (f0.x * f0.x + f0.y * f0.y) * io.scale;   // kx = k
+                        const T p1 = (f1.x * f1.x + f1.y * f1.y) * io.scale;   // kx = k + M
+                        sd[(k + sx) & (Nx - 1)] = p0;
+                        if (!self) {
+                            sd[(k + M + sx) & (Nx - 1)] = p1;
+                            smr[(Nx - k + sx) & (Nx - 1)] = p0;
+                            smr[(M - k + sx) & (Nx - 1)] = p1;
+                        } else {   // rows 0 and Ny/2 mirror into themselves: kx <= M computed, the rest copied
+                            if (k == 0) sd[(M + sx) & (Nx - 1)] = p1;
+                            else sd[(Nx - k + sx) & (Nx - 1)] = p0;
+                        }
+                    }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            if (act && u == 0) {
+                T* rowd = io.out + ((b << io.logNy) + ((ky + sy) & (Ny - 1))) * (long)Nx;
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                             :: "l"(rowd), "r"(smem_u32(sd)), "r"((unsigned)(Nx * sizeof(T))) : "memory");
+                if (!self) {
+                    T* rowm = io.out + ((b << io.logNy) + ((Ny - ky + sy) & (Ny - 1))) * (long)Nx;
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                 :: "l"(rowm), "r"(smem_u32(smr)), "r"((unsigned)(Nx * sizeof(T))) : "memory");
+                }
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        } else
         if (act) {
             T* rowd = io.out + ((b << io.logNy) + ((ky + sy) & (Ny - 1))) * (long)Nx;
             T* rowm = io.out + ((b << io.logNy) + ((Ny - ky + sy) & (Ny - 1))) * (long)Nx;
@@ -746,9 +793,8 @@ rowsz_power_kernel(RowsZPower<T> io, const cplx<T>* __restrict__ tw, long nseq) 
                     if (!self) rowm[(M - k + sx) & (Nx - 1)] = p1;
                 }
         }
-        // block_fft ends with the last gather's barrier only when there are >= 2 stages; the exchange buffer of this row is
-        // rewritten by the next group's first scatter, which every thread reaches only after finishing its own gather
     }
+    if (io.bulk && u == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // Packed (FP32x2) variant of rowsz_power_kernel: the A and B sequences of a row live in one cplx2 per point, so the
@@ -1058,19 +1104,23 @@ template <typename T> struct ColsR2CPack {
     // at a time -- the LSU never sees the 4096 scattered 32-byte row segments of a tile.  ztmap describes Z as
     // [batch * Ny][Nx] floats with the box of the input map.
     int ztma;
+    int zbox_rows;          // rows per box of ztmap (divides Ny / 4)
     alignas(64) CUtensorMap ztmap;
     static constexpr bool kSplitEpilogue = true;
     template <int LOG2L, int LOGE, int C, int NTHR>
     __device__ __forceinline__ void store_z_tma(long tile, int u, int cg, cplx<T> (&v)[2][1 << LOGE], cplx<T>* smX, const float* extra) const {
         using G_ = Geometry<LOG2L, LOGE>;
-        constexpr int R = 1 << G_::LOGR_LAST, G = G_::E / R, Ny = 1 << LOG2L, HALF = Ny / 2;
+        // the tile leaves in NPIECE pieces of PR rows through two alternating halves of the buffer: piece p is staged while
+        // the stores of piece p-1 are still reading the other half
+        constexpr int R = 1 << G_::LOGR_LAST, G = G_::E / R, Ny = 1 << LOG2L, NPIECE = 4, PR = Ny / NPIECE;
         const long b = tile / tiles_per_item;
         const int t0 = (int)(tile - b * tiles_per_item);
         write_colstats<C, NTHR>(b, t0 * (2 * C), extra);
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            if (half == 1) {   // the stores of the first half have finished reading the buffer
-                if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        for (int pc = 0; pc < NPIECE; ++pc) {
+            cplx<T>* buf = smX + (pc & 1) * (PR * C);
+            if (pc >= 2) {   // the stores of piece pc-2 have finished reading this half
+                if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                 __syncthreads();
             }
 #pragma unroll
@@ -1078,18 +1128,18 @@ template <typename T> struct ColsR2CPack {
 #pragma unroll
                 for (int t = 0; t < R; ++t) {
                     const int ky = final_index<LOG2L, LOGE>(u, g, t);
-                    if ((ky >= HALF) == (half == 1)) {
+                    if (ky / PR == pc) {
                         const cplx<T> a = v[0][g + t * G], c = v[1][g + t * G];
                         if constexpr (sizeof(T) == 4)
-                            *reinterpret_cast<float4*>(smX + (ky - half * HALF) * C + cg * 2) = make_float4(a.x, a.y, c.x, c.y);
+                            *reinterpret_cast<float4*>(buf + (ky - pc * PR) * C + cg * 2) = make_float4(a.x, a.y, c.x, c.y);
                     }
                 }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async-proxy (TMA) reads
             __syncthreads();
             if (threadIdx.x == 0) {
-                const unsigned sbase = (unsigned)__cvta_generic_to_shared(smX);
-                const int row0 = (int)(b << LOG2L) + half * HALF;
-                for (int r0 = 0; r0 < HALF; r0 += box_rows)
+                const unsigned sbase = (unsigned)__cvta_generic_to_shared(buf);
+                const int row0 = (int)(b << LOG2L) + pc * PR;
+                for (int r0 = 0; r0 < PR; r0 += zbox_rows)
                     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
                                  :: "l"(&ztmap), "r"(t0 * (2 * C)), "r"(row0 + r0), "r"(sbase + (unsigned)(r0 * C * sizeof(cplx<T>))) : "memory");
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
