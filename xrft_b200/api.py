@@ -350,7 +350,7 @@ def _label_output(P, data, new_last_sizes=None, extra_attrs=True):
 
 
 _STREAM_MIN_BYTES = 256 << 20    # host inputs at least this large are streamed chunk-wise (H2D | compute | D2H overlap)
-_STREAM_CHUNK_BYTES = 256 << 20  # target input bytes per streamed chunk
+_STREAM_CHUNK_BYTES = 128 << 20  # target input bytes per streamed chunk (PCIe-bound: small chunks shorten the pipeline fill/drain)
 
 
 def _stream_host_chunks(arrs, ntrans, out_host, core):
