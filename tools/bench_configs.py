@@ -9,6 +9,9 @@ from xrft_b200 import shard
 
 warnings.simplefilter("ignore")
 which = sys.argv[1] if len(sys.argv) > 1 else "3,4,5"
+if len(sys.argv) > 2:   # fused-chain chunk (batch items per kernel chain)
+    from xrft_b200 import backend as _B
+    _B.set_fused_chunk(int(sys.argv[2]))
 world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local); dev = torch.device("cuda", local)
 if world > 1:
