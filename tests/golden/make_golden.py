@@ -111,8 +111,12 @@ def main():
     store = {}
     cases = []
 
-    def add(name, fn, inputs, kwargs, dims, coords):
+    cpu_cases = []   # cases added after the last GPU run of the round: they pin the oracle only (promote to `cases` next round)
+
+    def add(name, fn, inputs, kwargs, dims, coords, gpu=True, chunks=None):
         das = [da_of(a, dims, coords) for a in inputs]
+        if chunks:
+            das = [d.chunk(chunks) for d in das]
         out = fn(*das, **kwargs)
         store[f"{name}__out"] = np.asarray(out.values)
         for i, a in enumerate(inputs):
@@ -123,7 +127,7 @@ def main():
                 for k, v in out[d].attrs.items():
                     if isinstance(v, (int, float, np.floating, np.integer)):
                         store[f"{name}__attr__{d}__{k}"] = np.asarray(float(v))
-        cases.append((name, fn.__name__, repr(kwargs), dims, list(out.dims)))
+        (cases if gpu else cpu_cases).append((name, fn.__name__, repr(kwargs), dims, list(out.dims)))
         print(name, fn.__name__, kwargs, "->", out.dims, out.shape)
 
     c2 = {"y": 0.5 * np.arange(16) - 3.0, "x": 0.25 * np.arange(32) + 7.0}
@@ -165,6 +169,20 @@ def main():
     add("detrend_2d", lambda d, **k: ref.detrend(d, ["y", "x"], **k), [a3], dict(detrend_type="linear"), ("t", "y", "x"), c3)
     add("detrend_1d", lambda d, **k: ref.detrend(d, ["x"], **k), [a3], dict(detrend_type="linear"), ("t", "y", "x"), c3)
     add("detrend_3d", lambda d, **k: ref.detrend(d, ["t", "y", "x"], **k), [a3], dict(detrend_type="linear"), ("t", "y", "x"), c3)
+    # ---- oracle-only additions (gpu=False)
+    add("ps1d_tukey_realdim", ref.power_spectrum, [a1], dict(real_dim="x", detrend="linear", window="tukey"), ("x",), c1, gpu=False)
+    add("ps1d_segments", ref.power_spectrum, [a1], dict(dim="x", chunks_to_segments=True, window="hann", detrend="constant"), ("x",), c1,
+        gpu=False, chunks={"x": 16})
+    add("fft2d_noshift", ref.fft, [a2], dict(shift=False, true_phase=True, detrend="constant"), ("y", "x"), c2, gpu=False)
+    add("cphase1d", ref.cross_phase, [a1, a1[::-1].copy()], dict(), ("x",), c1, gpu=False)
+    add("cs2d_realdim_corr", ref.cross_spectrum, [a3, b3], dict(dim=["y", "x"], real_dim="x", window="hann", window_correction=True,
+                                                                 detrend="linear"), ("t", "y", "x"), c3, gpu=False)
+    add("ps3d_all_linear", ref.power_spectrum, [a3], dict(detrend="linear", window="hann", scaling="spectrum"), ("t", "y", "x"), c3, gpu=False)
+    add("iso_ps_nfactor2", ref.isotropic_power_spectrum, [iso_in], dict(dim=["y", "x"], nfactor=2, truncate=False, window="hann"),
+        ("t", "y", "x"), ciso, gpu=False)
+    add("iso_cs_truncate", ref.isotropic_cross_spectrum, [iso_in, iso_in[:, ::-1].copy()], dict(dim=["y", "x"], detrend="linear", window="hann",
+                                                                                               truncate=True), ("t", "y", "x"), ciso, gpu=False)
+
     # round trips through the reference's own ifft
     ft = ref.fft(da_of(a2, ("y", "x"), c2))
     back = ref.ifft(ft)
@@ -190,7 +208,13 @@ def main():
     store["pad__out"] = np.asarray(p.values)
     store["pad__coord__x"] = np.asarray(p["x"].values, dtype=float)
     store["pad__coord__y"] = np.asarray(p["y"].values, dtype=float)
+    # unpad of the padded array (xrft/padding.py:321-446): data and coordinates come back
+    up = ref.unpad(p, dict(x=(3, 5), y=2))
+    store["unpad__out"] = np.asarray(up.values)
+    store["unpad__coord__x"] = np.asarray(up["x"].values, dtype=float)
+    store["unpad__coord__y"] = np.asarray(up["y"].values, dtype=float)
     store["__cases__"] = np.array([repr(c) for c in cases])
+    store["__cases_cpu__"] = np.array([repr(c) for c in cpu_cases])
     out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_cases.npz")
     np.savez_compressed(out, **store)
     print("wrote", out, os.path.getsize(out), "bytes")
