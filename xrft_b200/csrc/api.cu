@@ -1121,7 +1121,8 @@ static int spectrum2d_colsfirst(const xrftb_spectrum2d_desc& q, int ly, int lx, 
             // "z" mode: pass 1 stores the packed column spectra, pass 2 separates the real columns in its loads (RowsZPower)
             static int zpack_on = -1;
             if (zpack_on < 0) { const char* e = getenv("XRFTB_ZPACK"); zpack_on = e ? atoi(e) : 1; }
-            zmode = use_async && zpack_on && rows_z_supported(lx - 1);
+            // tiles of >= 4 packed columns only: with 2 the rows of Z are 16 bytes (half sectors: measured 2.7x slower stores)
+            zmode = use_async && zpack_on && rows_z_supported(lx - 1) && C >= 4;
             io.zout = zmode ? interm : nullptr;
             if (zmode) g_last_path.store(2);
             io.ztma = 0;
