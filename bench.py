@@ -127,8 +127,10 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals),
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 in / f64 arithmetic (numpy>=2 promotion, SURVEY F6)", "data": "synthetic",
-        "config": {"workload": "power_spectrum 2-D 4096x4096xtime float32, detrend='linear', window='hann' (CPU sample)",
-                   "ny": args.ny, "nx": args.nx, "slices_per_step": ns},
+        # the GPU arm's config; a step here is a bounded sample of that workload (the full job would take hours on the host)
+        "config": {"workload": "power_spectrum 2-D 4096x4096x1024-time float32, detrend='linear', window='hann', 1 GPU (BASELINE configs[1])",
+                   "time": args.time, "ny": args.ny, "nx": args.nx, "slices_per_step": ns,
+                   "sample": f"{ns} of {args.time} time slices per step, one slice per worker thread"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
