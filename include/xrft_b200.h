@@ -60,8 +60,9 @@ long xrftb_launch_count(int reset);
 int xrftb_profile_begin(void);
 int xrftb_profile_end(double ms[4], long counts[4]);
 /* which kernel chain the last xrftb_spectrum2d call took: 0 = rows first (moments | row R2C | column pass | Hermitian
- * mirror), 1 = columns first (column R2C with column-line detrend | completion tables | row C2C + epilogue, no mirror pass).
- * In chain 1 the profile classes read {completion tables, row pass = pass 2, column pass = pass 1, unused}. */
+ * mirror), 1 = columns first (column R2C with column-line detrend | completion tables | row C2C + epilogue, no mirror pass),
+ * 2 = columns first in "z mode" (pass 1 leaves the packed column spectra, pass 2 separates the real columns in its loads).
+ * In chains 1 and 2 the profile classes read {completion tables, row pass = pass 2, column pass = pass 1, unused}. */
 int xrftb_spectrum2d_last_path(void);
 
 /* ---- (S1) np.fft.fftn / ifftn / rfftn / irfftn --------------------------------------------------
