@@ -1160,6 +1160,101 @@ static int spectrum2d_colsfirst(const xrftb_spectrum2d_desc& q, int ly, int lx, 
     return 0;
 }
 
+// EXPERIMENTAL (XRFTB_CROSS_Z=1, off by default; not yet run on hardware -- see rowszx_kernel): the z-mode chain for the
+// cross spectrum / cross phase of two real fields.  Pass 1 (the config-2 kernel, unchanged) runs once per field and leaves
+// Z1, Z2; the completion tables are built per field; one two-field pass 2 combines them.  Per item the workspace holds two
+// Z arrays and two sets of column-line tables; the chunk adapts to the workspace the caller sized for the rows-first chain.
+static bool crossz_enabled() {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("XRFTB_CROSS_Z"); on = e ? atoi(e) : 0; }
+    return on != 0;
+}
+template <typename T> static bool crossz_eligible(const xrftb_spectrum2d_desc& q, int ly, int lx) {
+    if (!std::is_same<T, float>::value) return false;
+    if (!(q.mode == XRFTB_EPI_CROSS || q.mode == XRFTB_EPI_PHASE) || q.keep_half || q.weight_x || q.ramp_y || q.ramp_x) return false;
+    const int C = cols_tile_width<T>(ly, false);
+    if (C < 4 || ly <= TypeCfg<T>::LOGE || ly > TypeCfg<T>::MAX_COLS_LOG2 || !rows_z_supported(lx - 1)) return false;
+    if ((q.nx * sizeof(T)) % 16 != 0) return false;
+    return !q.detrend || (rowline_enabled() && ly >= 3);   // detrend only through the column-line tables
+}
+template <typename T>
+static int spectrum2d_crossz(const xrftb_spectrum2d_desc& q, int ly, int lx, cudaStream_t st) {
+    using C_ = cplx<T>;
+    const int C = cols_tile_width<T>(ly, false);
+    const int H = q.ny / 2 + 1;
+    const bool colline = q.detrend != 0;
+    const size_t zbytes = (size_t)q.ny * (q.nx / 2) * sizeof(C_);
+    const size_t per_item = 2 * (zbytes + (colline ? colline_item_bytes<T>(q.nx) : 0));
+    const size_t fixed = colline ? colline_fixed_bytes<T>(q.ny) : 0;
+    if (!q.work || q.work_bytes < fixed + per_item) return XRFTB_EWORKSPACE;   // caller falls back to the rows-first chain
+    long bchunk = (long)((q.work_bytes - fixed) / per_item);
+    if (bchunk > q.batch) bchunk = q.batch;
+    { const long nch = (q.batch + bchunk - 1) / bchunk; bchunk = (q.batch + nch - 1) / nch; }
+    char* base = reinterpret_cast<char*>(q.work);
+    C_* wj = nullptr;
+    if (colline) {
+        const int My = q.ny / 2;
+        wj = reinterpret_cast<C_*>(base);
+        double* wrows = reinterpret_cast<double*>(base + align256((size_t)H * 2 * sizeof(C_)));
+        double2* wspec = reinterpret_cast<double2*>(reinterpret_cast<char*>(wrows) + align256((size_t)2 * q.ny * sizeof(double)));
+        rowline_wj_in_kernel<T><<<(q.ny + 255) / 256, 256, 0, st>>>(reinterpret_cast<const T*>(q.win_y), wrows, q.ny);
+        if (int rc = check_launch("rowline_wj_in_kernel")) return rc;
+        RowsR2CFused<double> wio{};
+        wio.in = wrows; wio.in_row_stride = q.ny; wio.logNy = 0; wio.detrend = 0; wio.moments = nullptr; wio.wy = nullptr; wio.wx = nullptr;
+        wio.out = wspec; wio.logC = -1; wio.out_seq_stride = H; wio.rowstats = nullptr;
+        if (int rc = rows_r2c<double>(wio, ly - 1, 2, st)) return rc;
+        rowline_wj_out_kernel<T><<<(unsigned)((H + 255) / 256), 256, 0, st>>>(wspec, wj, My, H);
+        if (int rc = check_launch("rowline_wj_out_kernel")) return rc;
+    }
+    char* items = base + fixed;
+    C_* zf[2] = {reinterpret_cast<C_*>(items), reinterpret_cast<C_*>(items + (size_t)bchunk * zbytes)};
+    char* tabs = items + 2 * (size_t)bchunk * zbytes;
+    float4* colstats[2] = {nullptr, nullptr};
+    C_* ag[2] = {nullptr, nullptr};
+    if (colline) {
+        for (int f = 0; f < 2; ++f) {
+            colstats[f] = reinterpret_cast<float4*>(tabs + (size_t)f * bchunk * colline_item_bytes<T>(q.nx));
+            ag[f] = reinterpret_cast<C_*>(colstats[f] + (size_t)bchunk * q.nx);
+        }
+    }
+    const long item = (long)q.ny * q.nx;
+    const T* ins[2] = {reinterpret_cast<const T*>(q.in1), reinterpret_cast<const T*>(q.in2)};
+    const int tiles_per_item = q.nx / (2 * C);
+    const int box_rows = q.ny < 256 ? q.ny : 256;
+    const size_t out_elem = q.mode == XRFTB_EPI_PHASE ? sizeof(T) : sizeof(C_);
+    for (long b0 = 0; b0 < q.batch; b0 += bchunk) {
+        const long nb = (q.batch - b0 < bchunk) ? q.batch - b0 : bchunk;
+        for (int f = 0; f < 2; ++f) {
+            ColsR2CPack<T> io{ins[f] + b0 * item, q.nx, tiles_per_item, q.detrend, nullptr,
+                              reinterpret_cast<const T*>(q.win_y), reinterpret_cast<const T*>(q.win_x), zf[f], colstats[f], 0, {}};
+            if (!encode_out_tmap(&io.tmap, const_cast<T*>(ins[f] + b0 * item), nb * q.ny, q.nx, 2 * C, box_rows)) {
+                set_error("spectrum2d (cross z): tensor map encoding failed"); return XRFTB_ECUDA;
+            }
+            io.box_rows = box_rows;
+            io.zout = zf[f];
+            io.ztma = 0;
+            if (q.ny >= 512) {
+                const int zbox = q.ny / 4 < 256 ? q.ny / 4 : 256;
+                if (encode_out_tmap(&io.ztmap, zf[f], nb * q.ny, q.nx, 2 * C, zbox)) { io.ztma = 1; io.zbox_rows = zbox; }
+            }
+            {
+                ProfScope ps_(PROF_COLS, st);
+                if (int rc = cols_r2c_pack<T>(io, ly, C, nb * tiles_per_item, true, st)) return rc;
+            }
+            if (colline) {
+                ProfScope ps_(PROF_MOMENTS, st);
+                rowline_fix_kernel<T><<<dim3((unsigned)nb, (unsigned)((q.nx + 1023) / 1024)), 256, 0, st>>>(colstats[f], ag[f], reinterpret_cast<const T*>(q.win_x), q.nx, q.ny, q.detrend);
+                if (int rc = check_launch("rowline_fix_kernel")) return rc;
+            }
+        }
+        RowsZCross<T> io{zf[0], zf[1], reinterpret_cast<char*>(q.out) + (size_t)b0 * item * out_elem, ly, H, q.shift_y, q.shift_x, (T)q.scale,
+                         ag[0], ag[1], wj, nullptr};
+        ProfScope ps_(PROF_ROWS, st);
+        if (int rc = rows_z_cross<T>(io, lx - 1, nb * H, q.mode, st)) return rc;
+    }
+    return 0;
+}
+
 template <typename T>
 static int spectrum2d_impl(const xrftb_spectrum2d_desc& q, cudaStream_t st) {
     using C_ = cplx<T>;
@@ -1168,6 +1263,10 @@ static int spectrum2d_impl(const xrftb_spectrum2d_desc& q, cudaStream_t st) {
     const bool two = (q.mode == XRFTB_EPI_CROSS || q.mode == XRFTB_EPI_PHASE || q.mode == XRFTB_EPI_BINS_CROSS);
     if (two && !q.in2) { set_error("spectrum2d: mode %d needs in2", q.mode); return XRFTB_EINVAL; }
     if (colsfirst_enabled() && colsfirst_eligible<T>(q.mode, q.keep_half, q.weight_x, ly, lx, q.nx)) { g_last_path.store(1); return spectrum2d_colsfirst<T>(q, ly, lx, st); }
+    if (crossz_enabled() && crossz_eligible<T>(q, ly, lx)) {   // experimental, off by default
+        const int rc = spectrum2d_crossz<T>(q, ly, lx, st);
+        if (rc != XRFTB_EWORKSPACE) { g_last_path.store(3); return rc; }
+    }
     g_last_path.store(0);
     const int C = cols_tile_width<T>(ly, two);
     if (C < 1 || ly > TypeCfg<T>::MAX_COLS_LOG2 || lx - 1 > TypeCfg<T>::MAX_ROWS_LOG2) { set_error("spectrum2d: size %d x %d unsupported", q.ny, q.nx); return XRFTB_EUNSUPPORTED; }

@@ -797,6 +797,108 @@ rowsz_power_kernel(RowsZPower<T> io, const cplx<T>* __restrict__ tw, long nseq) 
     if (io.bulk && u == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+// EXPERIMENTAL (XRFTB_CROSS_Z=1; written at the end of round 1 after the GPU budget was spent: NOT yet run on hardware, off
+// by default, no product path reaches it).  Two-field pass 2 of the columns-first z-mode chain: cross spectrum
+// F1 conj(F2) or its phase from the packed column spectra Z1, Z2 of the two fields (each written by the unchanged pass 1).
+// One group of NT threads per (row, field): it separates the real columns of its field's rows ky / Ny-ky, transforms the
+// row exactly like rowsz_power_kernel and leaves F_f[0 .. Nx) in its own (by then free) exchange buffer; after one
+// barrier the 2 NT threads of the row combine F1 conj(F2) cooperatively and write rows ky and -ky (conjugate / negated
+// angle) with coalesced stores.
+template <typename T> struct RowsZCross {
+    const cplx<T>* z1; const cplx<T>* z2; void* out; int logNy; int H; int shift_y, shift_x; T scale;
+    const cplx<T>* ag1; const cplx<T>* ag2; const cplx<T>* wj;   // column-line detrend completion per field (nullptr = none)
+    const cplx<T>* tw2;                                          // exp(-2 pi i k / Nx), k in [0, Nx)
+};
+template <int LOG2M, int LOGE, int ROWS, int MODE>
+__global__ void __launch_bounds__((1 << (LOG2M - LOGE)) * 2 * ROWS, min_blocks_for((1 << (LOG2M - LOGE)) * 2 * ROWS))
+rowszx_kernel(RowsZCross<float> io, const float2* __restrict__ tw, long nseq) {
+    using T = float;
+    using G_ = Geometry<LOG2M, LOGE>;
+    constexpr int E = G_::E, NT = G_::NT, M = 1 << LOG2M, Nx = 2 * M;
+    constexpr int ROW_STRIDE = 2 * G_::LPAD + 8;   // >= Nx complex: the buffer later holds the field's whole transformed row
+    constexpr int R = 1 << G_::LOGR_LAST, G = E / R;
+    static_assert(MODE == EPI_CROSS || MODE == EPI_PHASE, "two-field modes only");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx<T>* smem = reinterpret_cast<cplx<T>*>(smem_raw);
+    cplx<T>* smw = smem + 2 * ROWS * ROW_STRIDE;   // [M] radix-2 twiddles
+    const int r = threadIdx.x / (2 * NT), f = (threadIdx.x / NT) & 1, u = threadIdx.x % NT;
+    cplx<T>* sm = smem + (2 * r + f) * ROW_STRIDE;
+    for (int k = threadIdx.x; k < M; k += 2 * NT * ROWS) smw[k] = __ldg(io.tw2 + k);
+    __syncthreads();
+    const long ngroups = (nseq + ROWS - 1) / ROWS;
+    const int Ny = 1 << io.logNy;
+    const int sy = io.shift_y ? Ny / 2 : 0, sx = io.shift_x ? Nx / 2 : 0;
+    const cplx<T>* zf = f ? io.z2 : io.z1;
+    const cplx<T>* agf = f ? io.ag2 : io.ag1;
+    for (long grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+        const long seq = grp * ROWS + r;
+        const bool act = seq < nseq;
+        const long b = act ? seq / io.H : 0;
+        const int ky = act ? (int)(seq - b * io.H) : 0;
+        cplx<T> v[2][E];
+        {
+            const cplx<T>* pa = zf + ((b << io.logNy) + ky) * (long)M + u;
+            const cplx<T>* pb = zf + ((b << io.logNy) + ((Ny - ky) & (Ny - 1))) * (long)M + u;
+            cplx<T> za[E], zb[E];
+#pragma unroll
+            for (int q = 0; q < E; ++q) { za[q] = act ? pa[q * NT] : mk<T>(0, 0); zb[q] = act ? pb[q * NT] : mk<T>(0, 0); }
+#pragma unroll
+            for (int q = 0; q < E; ++q) {
+                v[0][q] = mk<T>(za[q].x + zb[q].x, za[q].y - zb[q].y);
+                v[1][q] = mk<T>(za[q].y + zb[q].y, zb[q].x - za[q].x);
+            }
+        }
+        if (agf != nullptr && act) {
+            const cplx<T> W = __ldg(io.wj + 2 * ky), J = __ldg(io.wj + 2 * ky + 1);
+            const cplx<T>* pa = agf + b * (long)Nx + 2 * u;
+#pragma unroll
+            for (int q = 0; q < E; ++q) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(pa + 2 * q * NT));
+                v[0][q].x += a.x * W.x + a.y * J.x; v[0][q].y += a.x * W.y + a.y * J.y;
+                v[1][q].x += a.z * W.x + a.w * J.x; v[1][q].y += a.z * W.y + a.w * J.y;
+            }
+        }
+        block_fft<T, LOG2M, LOGE, 2, 2>(v, u, sm, 1, tw);   // ends with a barrier: the exchange buffers are free
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+#pragma unroll
+            for (int t = 0; t < R; ++t) {
+                const int k = final_index<LOG2M, LOGE>(u, g, t);
+                const cplx<T> fa = v[0][g + t * G];
+                const cplx<T> wb = cmul(v[1][g + t * G], smw[k]);
+                sm[k] = cadd(fa, wb);
+                sm[k + M] = csub(fa, wb);
+            }
+        __syncthreads();
+        if (act) {
+            const cplx<T>* s1 = smem + (2 * r) * ROW_STRIDE;
+            const cplx<T>* s2 = s1 + ROW_STRIDE;
+            const int tt = threadIdx.x % (2 * NT);
+            const long rd = ((b << io.logNy) + ((ky + sy) & (Ny - 1))) * (long)Nx;
+            const long rm = ((b << io.logNy) + ((Ny - ky + sy) & (Ny - 1))) * (long)Nx;
+            const bool self = (ky == 0) || (2 * ky == Ny);   // the row mirrors into itself: kx <= Nx/2 computed, the rest mirrored
+#pragma unroll
+            for (int j = 0; j < Nx / (2 * NT); ++j) {
+                const int kx = tt + j * (2 * NT);
+                const cplx<T> c = cscale(cmulc(s1[kx], s2[kx]), io.scale);
+                const int pd = (kx + sx) & (Nx - 1), pm = (Nx - kx + sx) & (Nx - 1);
+                const bool wd = !self || 2 * kx <= Nx, wm = !self || (kx > 0 && 2 * kx < Nx);
+                if constexpr (MODE == EPI_PHASE) {
+                    T* o = reinterpret_cast<T*>(io.out);
+                    const T ph = xatan2(c.y, c.x);
+                    if (wd) o[rd + pd] = ph;
+                    if (wm) o[rm + pm] = -ph;
+                } else {
+                    cplx<T>* o = reinterpret_cast<cplx<T>*>(io.out);
+                    if (wd) o[rd + pd] = c;
+                    if (wm) o[rm + pm] = cconj(c);
+                }
+            }
+        }
+        __syncthreads();   // the buffers are scattered into again by the next group
+    }
+}
+
 // Packed (FP32x2) variant of rowsz_power_kernel: the A and B sequences of a row live in one cplx2 per point, so the
 // separation is one FADD2 + two FADDs per packed column, every butterfly / twiddle product of the two M-point transforms
 // is issued once (FADD2 / FMUL2 / FFMA2), and |F|^2 of the output pair (kx, kx + M) is three packed instructions.

@@ -66,6 +66,7 @@ template <typename T> int rows_c2r(const cplx<T>* in, long in_stride, T* out, lo
                                    cudaStream_t st);
 template <typename T> int rows_c2c_power(const RowsC2CPower<T>& io, int log2L, long nseq, cudaStream_t st);
 template <typename T> int rows_z_power(RowsZPower<T> io, int log2M, long nseq, cudaStream_t st);
+template <typename T> int rows_z_cross(RowsZCross<T> io, int log2M, long nseq, int mode, cudaStream_t st);
 // half lengths the z-mode pass 2 is dispatched for (Nx = 1024 .. 4096: the sizes covered by the GPU parity tests; the
 // 2^12 instantiation exists but stays off until it has been through them)
 inline bool rows_z_supported(int log2M) { return log2M >= 9 && log2M <= 11; }

@@ -107,6 +107,26 @@ static int launch_rowsz_power(const RowsZPower<T>& io, long nseq, cudaStream_t s
     return check_launch("rowsz_power_kernel");
 }
 
+// EXPERIMENTAL two-field pass 2 on packed column spectra (rowszx_kernel): ROWS rows per CTA, one NT-thread group per (row, field)
+template <int LOG2M, int ROWS, int MODE>
+static int launch_rowszx(const RowsZCross<float>& io, long nseq, cudaStream_t st) {
+    constexpr int LOGE = cmin(TypeCfg<float>::LOGE, LOG2M);
+    using G_ = Geometry<LOG2M, LOGE>;
+    auto kern = rowszx_kernel<LOG2M, LOGE, ROWS, MODE>;
+    constexpr int threads = G_::NT * 2 * ROWS;
+    constexpr size_t smem = ((size_t)2 * ROWS * (2 * G_::LPAD + 8) + (size_t)(1 << LOG2M)) * sizeof(float2);
+    static int occ = -1;
+    if (int rc = prepare_kernel(kern, threads, smem, &occ)) return rc;
+    const float2* tw = twiddle_fft<float>(LOG2M);
+    if (!tw) return -3;
+    long ngroups = (nseq + ROWS - 1) / ROWS;
+    long grid = (long)sm_count() * occ;
+    if (grid > ngroups) grid = ngroups;
+    if (grid < 1) return 0;
+    kern<<<(unsigned)grid, threads, smem, st>>>(io, tw, nseq);
+    return check_launch("rowszx_kernel");
+}
+
 // packed (FP32x2) variant of launch_rowsz_power (float32)
 template <int LOG2M, int ROWS>
 static int launch_rowszp_power(const RowsZPower<float>& io, long nseq, cudaStream_t st) {

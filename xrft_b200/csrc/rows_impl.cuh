@@ -117,6 +117,23 @@ int rows_z_power(RowsZPower<T> io, int log2M, long nseq, cudaStream_t st) {
     return -2;
 }
 
+// EXPERIMENTAL two-field pass 2 of the z-mode chain (float32; mode = EPI_CROSS or EPI_PHASE)
+template <typename T>
+int rows_z_cross(RowsZCross<T> io, int log2M, long nseq, int mode, cudaStream_t st) {
+    if constexpr (sizeof(T) == 4) {
+        io.tw2 = twiddle_fft<T>(log2M + 1);
+        if (!io.tw2) return -3;
+        switch (log2M) {
+#define Z(K, P) case K: return mode == EPI_PHASE ? launch_rowszx<K, P, EPI_PHASE>(io, nseq, st) : launch_rowszx<K, P, EPI_CROSS>(io, nseq, st);
+            Z(9, 4) Z(10, 2) Z(11, 1)
+#undef Z
+            default: break;
+        }
+    }
+    set_error("rows_z_cross: unsupported half length 2^%d", log2M);
+    return -2;
+}
+
 template <typename T>
 int rows_c2r(const cplx<T>* in, long in_stride, T* out, long out_stride, int log2M, long nseq, T scale, cudaStream_t st) {
     RowsC2R<T> io{in, in_stride, out, out_stride, scale, twiddle_r2c<T>(log2M + 1)};
