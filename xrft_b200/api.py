@@ -22,6 +22,7 @@ import warnings
 from collections import OrderedDict
 from typing import List, Optional, Sequence
 
+import os
 import numpy as np
 import scipy.signal as sps
 
@@ -231,6 +232,18 @@ def _spectral_core(x1, x2, ntrans, mode, *, detrend=None, windows=None, keep_hal
     # ---- fused path: real 2-D, power-of-two sizes
     if (is_real and ntrans == 2 and B.spectrum2d_supported(shape[-2], shape[-1], x1.dtype, two)
             and (not bins_mode or nbins <= 1024) and not (keep_half and shift[1])):
+        if mode == L.EPI_BINS_POWER and not keep_half and weight is None and os.environ.get("XRFTB_BINS_UNFUSED", "0") == "1":
+            # EXPERIMENT for round 2 (off by default): power spectrum of an L2-sized chunk of planes through the config-2
+            # chain, then one coalesced radial-bin pass over it, instead of the LUT + histogram epilogue fused into the
+            # column pass (which costs more than the transform at 512^2: DESIGN.md section 7)
+            flat = x1.reshape((-1,) + tuple(shape[-2:]))
+            per = max(1, int((64 << 20) // (shape[-2] * shape[-1] * x1.element_size())))
+            parts = []
+            for lo in range(0, flat.shape[0], per):
+                ps = B.spectrum2d(flat[lo:lo + per], None, L.EPI_POWER, detrend=det, win_y=tt(wins[0]), win_x=tt(wins[1]),
+                                  shift_y=shift[0], shift_x=shift[1], scale=scale)
+                parts.append(B.binned_sum(ps, lut, nbins, 2))
+            return torch.cat(parts, 0).reshape(tuple(shape[:-2]) + (nbins,))
         return B.spectrum2d(
             x1, x2, mode, detrend=det, win_y=tt(wins[0]), win_x=tt(wins[1]), keep_half=keep_half, shift_y=shift[0],
             shift_x=shift[1], scale=scale, ramp_y=tt(ramps[0]), ramp_x=tt(ramps[1]), weight_x=tt(weight), lut=lut, nbins=nbins,
