@@ -53,3 +53,67 @@ def test_power_chain_variant(env):
     assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-4000:])
     worst = float(r.stdout.strip().split("WORST")[-1])
     assert worst < 2e-6, worst   # measured: 3e-7 (fp32 FFT with fp64-derived tables)
+
+
+# ---- experimental chains written at the end of round 1 without GPU time left: opt in with XRFTB_TEST_EXPERIMENTAL=1
+EXPERIMENTAL = os.environ.get("XRFTB_TEST_EXPERIMENTAL", "0") == "1"
+
+CROSS_SCRIPT = r'''
+import sys, numpy as np, torch, scipy.signal as sps
+sys.path.insert(0, %(root)r)
+from xrft_b200 import backend as B, _lib as L
+worst = 0.0
+for (ny, nx, T, detrend) in [(1024, 1024, 3, 1), (512, 2048, 2, 2), (2048, 4096, 1, 0)]:
+    g = torch.Generator(device="cuda").manual_seed(11 + ny)
+    x1 = torch.randn((T, ny, nx), generator=g, device="cuda") + 0.01 * torch.arange(nx, device="cuda") + 2
+    x2 = torch.roll(x1, shifts=(3, 5), dims=(1, 2)) + 0.5 * torch.randn((T, ny, nx), generator=g, device="cuda") - 1
+    wy = torch.from_numpy(sps.windows.hann(ny, sym=False)); wx = torch.from_numpy(sps.windows.hann(nx, sym=False))
+    w = wy.numpy()[:, None] * wx.numpy()[None, :]
+    def prep(x):
+        xd = x.double().cpu().numpy()
+        ii = np.arange(ny)[:, None] - 0.5 * (ny - 1); jj = np.arange(nx)[None, :] - 0.5 * (nx - 1)
+        pl = 0.0 if detrend == 0 else xd.mean() + (0 if detrend == 1 else ii * ((ii * xd).sum() / (nx * ny * (ny * ny - 1) / 12)) + jj * ((jj * xd).sum() / (ny * nx * (nx * nx - 1) / 12)))
+        return np.fft.fftshift(np.fft.fft2((xd - pl).astype(np.float32).astype(np.float64) * w))
+    cs = B.spectrum2d(x1, x2, L.EPI_CROSS, detrend=detrend, win_y=wy, win_x=wx, shift_y=True, shift_x=True, scale=1.0 / (ny * nx))
+    ph = B.spectrum2d(x1, x2, L.EPI_PHASE, detrend=detrend, win_y=wy, win_x=wx, shift_y=True, shift_x=True, scale=1.0 / (ny * nx))
+    assert L.load().xrftb_spectrum2d_last_path() == 3, "the experimental chain did not run"
+    for t in (0, T - 1):
+        ref = prep(x1[t]) * np.conj(prep(x2[t])) / (ny * nx)
+        worst = max(worst, np.linalg.norm(cs[t].cpu().numpy() - ref) / np.linalg.norm(ref))
+        big = np.abs(ref) > 1e-5 * np.abs(ref).max()
+        assert np.abs(np.angle(np.exp(1j * (ph[t].cpu().numpy() - np.angle(ref)))))[big].max() < 1e-2
+print("WORST", worst)
+'''
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not EXPERIMENTAL, reason="experimental two-field z-mode chain: not yet validated on hardware (XRFTB_TEST_EXPERIMENTAL=1)")
+def test_experimental_cross_z_chain():
+    e = dict(os.environ)
+    e["XRFTB_CROSS_Z"] = "1"
+    r = subprocess.run([sys.executable, "-c", CROSS_SCRIPT % {"root": ROOT}], env=e, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-4000:])
+    assert float(r.stdout.strip().split("WORST")[-1]) < 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not EXPERIMENTAL, reason="experimental unfused radial binning: not yet validated on hardware (XRFTB_TEST_EXPERIMENTAL=1)")
+def test_experimental_bins_unfused_matches_fused():
+    script = r'''
+import os, sys, numpy as np
+sys.path.insert(0, %(root)r)
+import xrft_b200 as xrft
+rng = np.random.default_rng(5)
+x = rng.standard_normal((3, 4, 256, 512)).astype(np.float32)
+c = {"a": np.arange(3.0), "b": np.arange(4.0), "y": np.arange(256) * 1.0, "x": np.arange(512) * 1.0}
+da = xrft.DataArray(x, dims=["a", "b", "y", "x"], coords=c)
+os.environ["XRFTB_BINS_UNFUSED"] = "0"
+fused = xrft.isotropic_power_spectrum(da, dim=["y", "x"], detrend="constant", window="hann").values
+os.environ["XRFTB_BINS_UNFUSED"] = "1"
+unf = xrft.isotropic_power_spectrum(da, dim=["y", "x"], detrend="constant", window="hann").values
+assert fused.shape == unf.shape
+print("ERR", np.abs(fused - unf).max() / np.abs(fused).max())
+''' % {"root": ROOT}
+    r = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-4000:])
+    assert float(r.stdout.strip().split("ERR")[-1]) < 1e-5
