@@ -235,7 +235,8 @@ def _spectral_core(x1, x2, ntrans, mode, *, detrend=None, windows=None, keep_hal
         if mode == L.EPI_BINS_POWER and not keep_half and weight is None and os.environ.get("XRFTB_BINS_UNFUSED", "0") == "1":
             # EXPERIMENT for round 2 (off by default): power spectrum of an L2-sized chunk of planes through the config-2
             # chain, then one coalesced radial-bin pass over it, instead of the LUT + histogram epilogue fused into the
-            # column pass (which costs more than the transform at 512^2: DESIGN.md section 7)
+            # column pass (which costs more than the transform at 512^2: DESIGN.md section 7).  XRFTB_BINSUM_RL=1 selects the
+            # run-length radial-bin kernel for the second step (also experimental).
             flat = x1.reshape((-1,) + tuple(shape[-2:]))
             per = max(1, int((64 << 20) // (shape[-2] * shape[-1] * x1.element_size())))
             parts = []

@@ -545,6 +545,48 @@ __global__ void __launch_bounds__(256) binned_sum_kernel(const T* __restrict__ a
         if (hist[i] != 0.0) atomicAdd(bins + b * nbins * width + i, hist[i]);
 }
 
+// EXPERIMENTAL (XRFTB_BINSUM_RL=1, off by default; written at the end of round 1, not yet run on hardware): float32 real
+// radial-bin sum for the unfused isotropic spectrum.  Every thread takes 16 consecutive cells (four 16-byte loads of the
+// values and of the LUT), accumulates runs of equal bins in a register -- radial bins change slowly along a row -- and
+// issues one native fp32 shared-memory atomic per run; a CTA's fp32 partial sums (a few hundred values per bin) go to the
+// item's fp64 bins with one atomic per bin, as in the fused epilogue.
+__global__ void __launch_bounds__(256) binned_sum_f32_rl_kernel(const float* __restrict__ arr, const int* __restrict__ lut,
+                                                                double* __restrict__ bins, long ncell, int nbins, int chunks) {
+    extern __shared__ float histf[];
+    const long b = blockIdx.y;
+    for (int i = threadIdx.x; i < nbins; i += blockDim.x) histf[i] = 0.f;
+    __syncthreads();
+    constexpr int SEG = 16;
+    const long nseg = ncell / SEG;   // ncell % 16 == 0 (checked by the launcher)
+    const long s0 = nseg * blockIdx.x / chunks, s1 = nseg * (blockIdx.x + 1) / chunks;
+    const float4* p = reinterpret_cast<const float4*>(arr + b * ncell);
+    const int4* q = reinterpret_cast<const int4*>(lut);
+    for (long sgm = s0 + threadIdx.x; sgm < s1; sgm += blockDim.x) {
+        float v[SEG]; int c[SEG];
+#pragma unroll
+        for (int j = 0; j < SEG / 4; ++j) {
+            const float4 x = p[sgm * (SEG / 4) + j];
+            const int4 y = __ldg(q + sgm * (SEG / 4) + j);
+            v[4 * j] = x.x; v[4 * j + 1] = x.y; v[4 * j + 2] = x.z; v[4 * j + 3] = x.w;
+            c[4 * j] = y.x; c[4 * j + 1] = y.y; c[4 * j + 2] = y.z; c[4 * j + 3] = y.w;
+        }
+        int cur = -1;
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < SEG; ++j) {
+            if (c[j] != cur) {
+                if (cur >= 0) atomicAdd(histf + cur, acc);
+                cur = c[j]; acc = 0.f;
+            }
+            acc += v[j];
+        }
+        if (cur >= 0) atomicAdd(histf + cur, acc);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nbins; i += blockDim.x)
+        if (histf[i] != 0.f) atomicAdd(bins + b * nbins + i, (double)histf[i]);
+}
+
 // ------------------------------------------------------------------------------------------------
 // arbitrary lengths (the reference's tests use 10, 15, 19, 20, 30, 40, 100, 1000 ...)
 //   N <= kSmallDft : direct O(N^2) DFT, one thread per sequence, twiddles in shared memory
@@ -1549,6 +1591,18 @@ int xrftb_binned_sum(const void* array, const int32_t* lut, double* bins, int dt
     if ((long)chunks * 1024 > ncell) chunks = (int)((ncell + 1023) / 1024);
     dim3 grid(chunks, (unsigned)batch);
     const size_t smem = (size_t)nbins * (is_complex ? 2 : 1) * sizeof(double);
+    {   // experimental run-length kernel (off by default)
+        static int rl_on = -1;
+        if (rl_on < 0) { const char* e = getenv("XRFTB_BINSUM_RL"); rl_on = e ? atoi(e) : 0; }
+        if (rl_on && dtype == XRFTB_F32 && !is_complex && ncell % 16 == 0 && (reinterpret_cast<uintptr_t>(array) & 15) == 0 &&
+            (reinterpret_cast<uintptr_t>(lut) & 15) == 0) {
+            int ch = (int)(ncell / (16L * 256 * 8));   // ~8 sweeps of 256 threads x 16 cells per CTA
+            if (ch < 1) ch = 1;
+            binned_sum_f32_rl_kernel<<<dim3(ch, (unsigned)batch), 256, (size_t)nbins * sizeof(float), st>>>(
+                reinterpret_cast<const float*>(array), lut, bins, ncell, nbins, ch);
+            return check_launch("binned_sum_f32_rl_kernel");
+        }
+    }
     if (dtype == XRFTB_F32) {
         if (is_complex) binned_sum_kernel<float, true><<<grid, 256, smem, st>>>(reinterpret_cast<const float*>(array), lut, bins, ncell, nbins, chunks);
         else binned_sum_kernel<float, false><<<grid, 256, smem, st>>>(reinterpret_cast<const float*>(array), lut, bins, ncell, nbins, chunks);
