@@ -114,6 +114,9 @@ unf = xrft.isotropic_power_spectrum(da, dim=["y", "x"], detrend="constant", wind
 assert fused.shape == unf.shape
 print("ERR", np.abs(fused - unf).max() / np.abs(fused).max())
 ''' % {"root": ROOT}
-    r = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-4000:])
-    assert float(r.stdout.strip().split("ERR")[-1]) < 1e-5
+    for rl in ("0", "1"):   # second step: the fp64-atomic kernel, then the run-length fp32 kernel
+        e = dict(os.environ)
+        e["XRFTB_BINSUM_RL"] = rl
+        r = subprocess.run([sys.executable, "-c", script], env=e, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, (rl, r.stdout[-2000:], r.stderr[-4000:])
+        assert float(r.stdout.strip().split("ERR")[-1]) < 1e-5, rl
