@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--cpu-slices", type=int, default=0, help="slices in the CPU sample (0 = one per worker)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-other", action="store_true", help="skip BASELINE configs 3, 4, 5 (other_configs)")
     return ap.parse_args()
 
 
@@ -186,6 +187,50 @@ class Clocks:
 
 
 # ------------------------------------------------------------------------------------------------
+# host link probe (the end-to-end number's denominator)
+# ------------------------------------------------------------------------------------------------
+def pcie_probe(dev, world, barrier, nbytes=1 << 30):
+    """pinned H2D alone, D2H alone, both concurrently (two streams); all ranks at once, slowest rank reported"""
+    import torch
+    import torch.distributed as dist
+    try:
+        h_in = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        h_out = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    except Exception:
+        return None
+    d_a = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    d_b = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def h2d():
+        with torch.cuda.stream(s1):
+            d_a.copy_(h_in, non_blocking=True)
+
+    def d2h():
+        with torch.cuda.stream(s2):
+            h_out.copy_(d_b, non_blocking=True)
+
+    def timed(fns, reps=3):
+        for f in fns:
+            f()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            for f in fns:
+                f()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / reps
+        t = torch.tensor([dt], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return nbytes / float(t.item()) / 1e9
+
+    out = {"h2d_GBs": timed([h2d]), "d2h_GBs": timed([d2h]), "both_each_GBs": timed([h2d, d2h]), "ranks_at_once": world}
+    del h_in, h_out, d_a, d_b
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 def run_b200(args):
@@ -315,6 +360,7 @@ def run_b200(args):
     # ---- end to end: host (pinned) buffers in, result copied back, every step
     e2e = None
     if not args.no_e2e:
+        probe = pcie_probe(dev, world, barrier)
         Te = min(args.e2e_time, T)
         hin = torch.empty((Te, ny, nx), dtype=torch.float32).pin_memory()
         hin.copy_(x[:Te])
@@ -340,9 +386,14 @@ def run_b200(args):
         tt = torch.tensor([dt], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        each_way = Te * slice_b / float(tt.item()) / 1e9   # GB/s per direction per GPU (slowest rank)
         e2e = {"value": world * Te * ny * nx / float(tt.item()) / 1e9, "unit": UNIT, "h2d_bytes_per_step": Te * slice_b,
                "d2h_bytes_per_step": Te * slice_b, "slices_per_step": Te, "ms_per_step": float(tt.item()) * 1e3,
-               "path": "xrft_b200.power_spectrum(DataArray(pinned numpy), out=pinned) -> chunk-streamed H2D | C-ABI kernels | D2H"}
+               "path": "xrft_b200.power_spectrum(DataArray(pinned numpy), out=pinned) -> chunk-streamed H2D | C-ABI kernels | D2H",
+               # the limiter: 4 B/point in and 4 B/point out over the host link.  Probe = pinned 1 GiB copies on two streams,
+               # every rank at once (min over ranks), measured in this run just before the end-to-end steps
+               "link_GBs_each_way": each_way, "pcie_probe": probe,
+               "pcie_frac": each_way / probe["both_each_GBs"] if probe and probe.get("both_each_GBs") else None}
         del hin, hout
     del x
     torch.cuda.empty_cache()
@@ -356,6 +407,23 @@ def run_b200(args):
         cpu = {"value": v, "unit": UNIT, "cores": workers, "kind": "port",
                "sample": f"{ns} slices of {ny}x{nx} float32 ({dt:.1f} s), oracle power_spectrum(detrend='linear', window='hann'), {workers} threads"}
 
+    # ---- the other BASELINE configs (3: cross spectrum + phase, 4: isotropic spectrum sharded over the ranks + the NCCL
+    #      radial-bin all-reduce, 5: padded rfft/irfft round trip), each with its SURVEY section 8(d) bytes per point
+    other = None
+    if not args.no_other:
+        from tools import bench_configs as BC
+        other = {}
+        try:
+            r4 = BC.run_config4(dev, rank, world)
+            if rank == 0:
+                other["config4_isotropic_power_spectrum"] = r4
+            if rank == 0 and world == 1:
+                other["config3_cross_spectrum_phase"] = BC.run_config3(dev)
+                other["config5_rfft_irfft_padded_f64"] = BC.run_config5(dev)
+        except Exception as exc:  # the headline line must still be printed
+            other["error"] = repr(exc)[:500]
+        barrier()
+
     if rank == 0:
         sys.stdout.flush()
         print(json.dumps({
@@ -367,7 +435,7 @@ def run_b200(args):
                        "l2": "inputs (%.1f GiB/step) far exceed the 126 MB L2; no flush needed" % (T * slice_b / 2 ** 30),
                        "parallelism": f"time sharded over {world} GPU(s), no data-path collective"},
             "gpu_launches": launches, "clocks": clk, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
-            "checksum": checksum,
+            "other_configs": other, "checksum": checksum,
         }))
     if world > 1:
         dist.destroy_process_group()

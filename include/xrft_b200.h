@@ -155,6 +155,21 @@ typedef struct {
 size_t xrftb_spectrum2d_workspace(int dtype, int ny, int nx, int two_fields, int64_t batch_in_flight);
 int xrftb_spectrum2d(const xrftb_spectrum2d_desc* desc, void* stream);
 
+/* ---- (e) multi-GPU: the one exchange step of the path -----------------------------------------------
+ * The reference shards chunks of the non-transform axes over dask workers (xrft.py:32-36); transforms never cross
+ * workers, so fft / power_spectrum / cross_* need no collective.  Averaging an isotropic spectrum over the sharded axis
+ * (isotropic_power_spectrum(...).mean(dim), xrft.py:1013-1095; tests/test_xrft.py:1011-1013) needs ONE sum of
+ * nbins (+1 count) float64 over the ranks: xrftb_allreduce_bins == ncclAllReduce(sum, float64, in place) on `stream`.
+ * One process per GPU; rank 0 calls xrftb_comm_unique_id and ships the 128 bytes to the other ranks through any side
+ * channel; every rank then calls xrftb_comm_init on its current device.  NCCL is bound at run time (dlopen), so these
+ * return XRFTB_EUNSUPPORTED when libnccl.so.2 is absent. */
+#define XRFTB_COMM_ID_BYTES 128
+int xrftb_comm_unique_id(void* id128);
+int xrftb_comm_init(void** comm, int nranks, int rank, const void* id128);
+int xrftb_comm_destroy(void* comm);
+int xrftb_comm_nccl_version(void);
+int xrftb_allreduce_bins(void* comm, double* buf, size_t count, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

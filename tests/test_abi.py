@@ -44,8 +44,6 @@ def test_no_cpu_fallback():
     da = xrft.DataArray(np.random.rand(8, 8), dims=["y", "x"])
     with pytest.raises(XrftbError):
         xrft.power_spectrum(da)
-    src = "".join(open(os.path.join(ROOT, "xrft_b200", f)).read() for f in os.listdir(os.path.join(ROOT, "xrft_b200")) if f.endswith(".py"))
-    assert "oracle" not in src.replace("the oracle", "").replace("oracle/", "").replace("oracle (", "").lower() or True
     for f in os.listdir(os.path.join(ROOT, "xrft_b200")):
         if f.endswith(".py"):
             code = open(os.path.join(ROOT, "xrft_b200", f)).read()

@@ -12,7 +12,8 @@ from oracle import xrft_oracle as O
 
 G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_cases.npz"), allow_pickle=False)
 CASES = [ast.literal_eval(s) for s in G["__cases__"]]
-# cases generated after the last GPU run of round 1: they pin the oracle; the CUDA comparison of these starts next round
+# second batch of reference cases (1-D one-sided tukey PSD, Welch segments, unshifted true-phase fft, 1-D cross phase, one-sided
+# cross spectrum with window correction, 3-D PSD with 3-D linear detrend, isotropic nfactor / truncate): oracle AND CUDA
 CPU_CASES = [ast.literal_eval(s) for s in G["__cases_cpu__"]] if "__cases_cpu__" in G.files else []
 CHUNKS = {"ps1d_segments": {"x": 16}}
 warnings.simplefilter("ignore")
@@ -117,7 +118,7 @@ def test_oracle_ifft_pad_golden():
 
 # ------------------------------------------------------------------------------------------- GPU
 @pytest.mark.gpu
-@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+@pytest.mark.parametrize("case", CASES + CPU_CASES, ids=[c[0] for c in CASES + CPU_CASES])
 def test_cuda_matches_reference_golden(case):
     import xrft_b200 as xrft
 
@@ -126,6 +127,8 @@ def test_cuda_matches_reference_golden(case):
     ins = inputs(name)
     coords = coords_for(name, tuple(dims), ins[0].shape)
     das = [xrft.DataArray(a, dims=list(dims), coords=coords) for a in ins]
+    if name in CHUNKS:
+        das = [d.chunk(CHUNKS[name]) for d in das]
     if fn == "<lambda>":
         dd = {"detrend_2d": ["y", "x"], "detrend_1d": ["x"], "detrend_3d": ["t", "y", "x"]}[name]
         out = xrft.detrend(das[0], dd, kw["detrend_type"])
@@ -158,3 +161,13 @@ def test_cuda_ifft_pad_golden():
     p = xrft.pad(xrft.DataArray(G["pad__in0"], dims=["y", "x"], coords=c2), x=(3, 5), y=2)
     np.testing.assert_array_equal(p.values, G["pad__out"])
     np.testing.assert_allclose(p["x"].values, G["pad__coord__x"])
+    np.testing.assert_allclose(p["y"].values, G["pad__coord__y"])
+    up = xrft.unpad(p, {"x": (3, 5), "y": 2})
+    np.testing.assert_array_equal(up.values, G["unpad__out"])
+    np.testing.assert_allclose(up["x"].values, G["unpad__coord__x"])
+    np.testing.assert_allclose(up["y"].values, G["unpad__coord__y"])
+    # device-resident data takes the CUDA pad / crop kernels
+    import torch
+    pd = xrft.pad(xrft.DataArray(torch.from_numpy(G["pad__in0"]).cuda(), dims=["y", "x"], coords=c2), x=(3, 5), y=2)
+    np.testing.assert_array_equal(pd.values, G["pad__out"])
+    np.testing.assert_array_equal(xrft.unpad(pd).values, G["unpad__out"])

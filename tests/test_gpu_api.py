@@ -492,3 +492,65 @@ def test_cross_spectrum_phase_large(dt, shape):
     # Hermitian structure of the cross spectrum of real fields: C(-k) = conj(C(k))
     c = xrft.cross_spectrum(a, b, **kw).values[0]
     np.testing.assert_allclose(c[1:, 1:], np.conj(c[1:, 1:][::-1, ::-1]), rtol=1e-4, atol=1e-6 * np.abs(c).max())
+
+
+# ------------------------------------------------------------------ advisor findings of round 1
+def test_batch_over_65535_composed_paths():
+    """more than 65535 batch items through the composed path (moments / detrend / transform / radial bins stride over
+    the items beyond one grid dimension); the reference has no such limit"""
+    rng = np.random.default_rng(65)
+    T = 66000
+    da = mk((T, 16), ("t", "x"), rng, dt=np.float32)
+    da = da + 0.3 * np.arange(16, dtype=np.float32)
+    out = xrft.power_spectrum(da, dim=["x"], detrend="linear")
+    ref = O.power_spectrum(lab(da), dim=["x"], detrend="linear")
+    assert relerr(out.values, ref.data) < 1e-3
+    det = xrft.detrend(da, ["x"], "linear")
+    assert relerr(det.values, O.detrend(lab(da), ["x"], "linear").data) < 1e-4
+    # fused 2-D chain with more than 65535 items in one call
+    small = mk((66000, 8, 16), ("t", "y", "x"), rng, dt=np.float32, spacing={"t": 1.0, "y": 1.0, "x": 1.0})
+    out2 = xrft.power_spectrum(small, dim=["y", "x"], detrend="constant", window="hann")
+    ref2 = O.power_spectrum(lab(small), dim=["y", "x"], detrend="constant", window="hann")
+    assert relerr(out2.values[-3:], ref2.data[-3:]) < 1e-3 and relerr(out2.values, ref2.data) < 1e-3
+
+
+def test_isotropize_more_than_2048_bins():
+    rng = np.random.default_rng(66)
+    n = 2100
+    ps = DataArray(rng.random((2, n, n)), dims=["t", "freq_y", "freq_x"],
+                   coords={"t": np.arange(2.0), "freq_y": np.fft.fftshift(np.fft.fftfreq(n)), "freq_x": np.fft.fftshift(np.fft.fftfreq(n))})
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        iso = xrft.isotropize(ps, ["freq_y", "freq_x"], nfactor=1, truncate=False)
+        ref = O.isotropize(lab(ps), ["freq_y", "freq_x"], nfactor=1, truncate=False)
+    assert iso.shape == (2, n) and relerr(iso.values, ref.data) < 1e-10
+
+
+def test_cross_spectrum_opposite_coordinate_orientation():
+    """true_phase flips each array by ITS OWN decreasing coordinates (xrft.py:436-441)"""
+    rng = np.random.default_rng(67)
+    a = mk((3, 16, 32), ("t", "y", "x"), rng)
+    b = mk((3, 16, 32), ("t", "y", "x"), rng)
+    b = DataArray(b.values, dims=b.dims, coords={"t": b["t"].values, "y": b["y"].values, "x": b["x"].values[::-1].copy()})
+    kw = dict(dim=["y", "x"], true_phase=True)
+    same(xrft.cross_spectrum(a, b, **kw), O.cross_spectrum(lab(a), lab(b), **kw), tol=1e-9, check_attrs=False)
+
+
+def test_container_convention_and_out_validation():
+    """numpy in -> numpy out, torch (CUDA) in -> torch (CUDA) out; out= is validated up front"""
+    import torch
+    rng = np.random.default_rng(68)
+    da = mk((4, 16, 32), ("t", "y", "x"), rng)
+    assert isinstance(xrft.power_spectrum(da, dim=["y", "x"]).data, np.ndarray)
+    assert isinstance(xrft.fft(da, dim=["x"]).data, np.ndarray)
+    assert isinstance(xrft.detrend(da, ["x"], "linear").data, np.ndarray)
+    dd = DataArray(torch.from_numpy(da.values).cuda(), dims=da.dims, coords={d: da[d].values for d in da.dims})
+    r = xrft.power_spectrum(dd, dim=["y", "x"])
+    assert isinstance(r.data, torch.Tensor) and r.data.is_cuda
+    with pytest.raises(ValueError):
+        xrft.power_spectrum(da, dim=["y", "x"], out=np.empty((4, 16, 31)))
+    with pytest.raises(ValueError):
+        xrft.power_spectrum(da, dim=["y", "x"], out=np.empty((4, 16, 32), dtype=np.float32))
+    buf = np.empty((4, 16, 32))
+    r2 = xrft.power_spectrum(da, dim=["y", "x"], out=buf)
+    np.testing.assert_array_equal(buf, r2.values)

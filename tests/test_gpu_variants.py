@@ -94,29 +94,3 @@ def test_experimental_cross_z_chain():
     r = subprocess.run([sys.executable, "-c", CROSS_SCRIPT % {"root": ROOT}], env=e, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-4000:])
     assert float(r.stdout.strip().split("WORST")[-1]) < 1e-5
-
-
-@pytest.mark.gpu
-@pytest.mark.skipif(not EXPERIMENTAL, reason="experimental unfused radial binning: not yet validated on hardware (XRFTB_TEST_EXPERIMENTAL=1)")
-def test_experimental_bins_unfused_matches_fused():
-    script = r'''
-import os, sys, numpy as np
-sys.path.insert(0, %(root)r)
-import xrft_b200 as xrft
-rng = np.random.default_rng(5)
-x = rng.standard_normal((3, 4, 256, 512)).astype(np.float32)
-c = {"a": np.arange(3.0), "b": np.arange(4.0), "y": np.arange(256) * 1.0, "x": np.arange(512) * 1.0}
-da = xrft.DataArray(x, dims=["a", "b", "y", "x"], coords=c)
-os.environ["XRFTB_BINS_UNFUSED"] = "0"
-fused = xrft.isotropic_power_spectrum(da, dim=["y", "x"], detrend="constant", window="hann").values
-os.environ["XRFTB_BINS_UNFUSED"] = "1"
-unf = xrft.isotropic_power_spectrum(da, dim=["y", "x"], detrend="constant", window="hann").values
-assert fused.shape == unf.shape
-print("ERR", np.abs(fused - unf).max() / np.abs(fused).max())
-''' % {"root": ROOT}
-    for rl in ("0", "1"):   # second step: the fp64-atomic kernel, then the run-length fp32 kernel
-        e = dict(os.environ)
-        e["XRFTB_BINSUM_RL"] = rl
-        r = subprocess.run([sys.executable, "-c", script], env=e, capture_output=True, text=True, timeout=600)
-        assert r.returncode == 0, (rl, r.stdout[-2000:], r.stderr[-4000:])
-        assert float(r.stdout.strip().split("ERR")[-1]) < 1e-5, rl

@@ -109,8 +109,8 @@ def test_errors_raised_before_numerics():
         xrft.fft(DataArray(np.ones(4), dims=["x"], coords={"x": np.zeros(4)}))
     with pytest.raises(ValueError):  # test_xrft.py:240-241 real_dim not a dim
         xrft.fft(a, real_dim="w")
-    with pytest.raises(TypeError):  # test_xrft.py:1303-1327 spacing_tol must be float
-        xrft.fft(a, dim=["x"], spacing_tol=1)
+    with pytest.raises(TypeError):  # test_xrft.py:1132-1135 spacing_tol must be a number
+        xrft.fft(a, dim=["x"], spacing_tol="string")
     with pytest.raises(ValueError):  # test_xrft.py:1364-1379 string coordinate
         xrft.fft(DataArray(np.ones(3), dims=["x"], coords={"x": np.array(["a", "b", "c"])}))
     extra = a.assign_coords(lon=DataArray(np.ones((6, 8)), dims=["y", "x"]))

@@ -1,85 +1,163 @@
 #!/usr/bin/env python
-"""Secondary BASELINE.json configs (3, 4, 5) through the public API; prints one JSON line per config.
-(bench.py keeps the driver contract for the headline config 2.)  Run under torchrun for config 4 at N > 1."""
-import json, os, sys, time, warnings
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np, torch
-import xrft_b200 as xrft
-from xrft_b200 import shard
+"""BASELINE.json configs 3, 4 and 5 through the public API: device-resident synthetic inputs, CUDA-event timing, the
+SURVEY.md section 8(d) algorithmic bytes per point, the fraction of the measured HBM peak and a parity check of a
+sub-batch against the oracle.  bench.py imports run_config3/4/5 and emits their dicts under `other_configs`; as a script
+it prints one JSON line per config (torchrun for config 4 at N > 1):  python tools/bench_configs.py [3,4,5]"""
+import json
+import os
+import sys
+import warnings
 
-warnings.simplefilter("ignore")
-which = sys.argv[1] if len(sys.argv) > 1 else "3,4,5"
-if len(sys.argv) > 2:   # fused-chain chunk (batch items per kernel chain)
-    from xrft_b200 import backend as _B
-    _B.set_fused_chunk(int(sys.argv[2]))
-world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
-torch.cuda.set_device(local); dev = torch.device("cuda", local)
-if world > 1:
-    import torch.distributed as dist
-    dist.init_process_group("nccl", device_id=dev)
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
 
 
-def timeit(fn, reps=3, warm=2):
-    for _ in range(warm): out = fn()
+def _peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def _timeit(fn, reps=3, warm=2, sync=None):
+    import torch
+    out = None
+    for _ in range(warm):
+        del out
+        out = fn()
+    if sync:
+        sync()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(reps): out = fn()
-    e1.record(); torch.cuda.synchronize()
+    for _ in range(reps):
+        del out
+        out = fn()
+    e1.record()
+    torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps, out
 
 
-def emit(d):
-    if rank == 0: print(json.dumps(d), flush=True)
+def _relerr(a, b):
+    den = np.linalg.norm(np.asarray(b).ravel())
+    return float(np.linalg.norm((np.asarray(a) - np.asarray(b)).ravel()) / (den if den > 0 else 1.0))
 
 
-if "3" in which:  # cross_spectrum + cross_phase of two 2048^2 x 512 fields
-    T, n = 512, 2048
+def _roof(gpts, bytes_per_point):
+    peak, src = _peak()
+    gbs = gpts * bytes_per_point
+    return {"algorithmic_bytes_per_point": bytes_per_point, "achieved_GBs": gbs, "frac_of_hbm_peak": gbs / peak, "peak_GBs": peak, "peak_source": src}
+
+
+def run_config3(dev, T=512, n=2048, parity=True):
+    """cross_spectrum + cross_phase of two 2048^2 x 512 float32 fields, detrend='constant', window='hann' (xrft.py:753-874)"""
+    import torch
+    import xrft_b200 as xrft
+    from xrft_b200 import _lib as L
+    warnings.simplefilter("ignore")
+    lib = L.load()
     g = torch.Generator(device=dev).manual_seed(1)
     a = torch.randn((T, n, n), generator=g, device=dev)
-    b = torch.roll(a, shifts=(3, 5), dims=(1, 2)) + 0.5 * torch.randn((T, n, n), generator=g, device=dev)
+    b = torch.roll(a, shifts=(3, 5), dims=(1, 2))
+    b += 0.5 * torch.randn((T, n, n), generator=g, device=dev)
     c = {"time": np.arange(T) * 1.0, "y": np.arange(n) * 1.0, "x": np.arange(n) * 1.0}
     da, db = xrft.DataArray(a, dims=["time", "y", "x"], coords=c), xrft.DataArray(b, dims=["time", "y", "x"], coords=c)
-    ms_cs, cs = timeit(lambda: xrft.cross_spectrum(da, db, dim=["y", "x"], detrend="constant", window="hann"))
-    del cs
-    ms_cp, cp = timeit(lambda: xrft.cross_phase(da, db, dim=["y", "x"], detrend="constant", window="hann"))
+    kw = dict(dim=["y", "x"], detrend="constant", window="hann")
     pts = T * n * n
-    emit({"config": 3, "workload": "cross_spectrum + cross_phase, two 2048^2 x 512 float32 fields, detrend=constant, window=hann",
-          "cross_spectrum_GPts_s": pts / ms_cs / 1e6, "cross_phase_GPts_s": pts / ms_cp / 1e6, "both_GPts_s": pts / (ms_cs + ms_cp) / 1e6,
-          "ms": [ms_cs, ms_cp], "points_per_field": pts, "phase_range": [float(cp.data.min()), float(cp.data.max())]})
-    del a, b, da, db, cp
+    lib.xrftb_launch_count(1)
+    ms_cs, cs = _timeit(lambda: xrft.cross_spectrum(da, db, **kw))
+    res = {"config": 3, "workload": "cross_spectrum + cross_phase, two %d^2 x %d float32 fields, detrend=constant, window=hann" % (n, T),
+           "points_per_field": pts, "unit": "GPoints/s per field"}
+    par = {}
+    if parity:
+        from oracle import xrft_oracle as O
+        c1 = {k: (v[:1] if k == "time" else v) for k, v in c.items()}
+        ref = O.cross_spectrum(O.Labelled(a[:1].cpu().numpy().astype(np.float64), ("time", "y", "x"), c1),
+                               O.Labelled(b[:1].cpu().numpy().astype(np.float64), ("time", "y", "x"), c1), **kw).data
+        par["cross_spectrum_relerr_slice0"] = _relerr(cs.data[:1].cpu().numpy(), ref)
+    del cs
+    ms_cp, cp = _timeit(lambda: xrft.cross_phase(da, db, **kw))
+    if parity:
+        d = np.abs(np.angle(np.exp(1j * (cp.data[:1].cpu().numpy() - np.angle(ref)))))
+        par["cross_phase_max_abs_err_slice0"] = float(d[np.abs(ref) > 1e-4 * np.abs(ref).max()].max())
+        del ref
+    del cp
+    res.update({"cross_spectrum": dict(value=pts / ms_cs / 1e6, ms=ms_cs, **_roof(pts / ms_cs / 1e6, 16.0)),
+                "cross_phase": dict(value=pts / ms_cp / 1e6, ms=ms_cp, **_roof(pts / ms_cp / 1e6, 12.0))})
+    if hasattr(xrft, "cross_spectrum_and_phase"):
+        ms_b, both = _timeit(lambda: xrft.cross_spectrum_and_phase(da, db, **kw))
+        del both
+        res["cross_spectrum_and_phase"] = dict(value=pts / ms_b / 1e6, ms=ms_b, **_roof(pts / ms_b / 1e6, 20.0))
+    res["gpu_launches"] = int(lib.xrftb_launch_count(0))
+    res["parity"] = par
+    del a, b, da, db
     torch.cuda.empty_cache()
+    return res
 
-if "4" in which:  # isotropic_power_spectrum of 512^2 planes x (64 chunks x 512 z), sharded over ranks, one all-reduce
-    chunks, z, n = 64, 512, 512
+
+def run_config4(dev, rank=0, world=1, chunks=64, z=512, n=512, parity=True):
+    """isotropic_power_spectrum of 512^2 planes x (64 chunks x 512 z) float32, detrend='constant', window='hann', mean
+    over (chunk, z); `chunk` sharded over the ranks, ONE all-reduce of nbins + 1 float64 (xrft.py:1013-1095)."""
+    import torch
+    import xrft_b200 as xrft
+    from xrft_b200 import shard, _lib as L
+    warnings.simplefilter("ignore")
+    lib = L.load()
     lo, hi = shard.shard_bounds(chunks, rank, world)
-    g = torch.Generator(device=dev).manual_seed(100 + rank)
-    x = torch.randn((hi - lo, z, n, n), generator=g, device=dev)
+    x = torch.empty((hi - lo, z, n, n), dtype=torch.float32, device=dev)
+    for i in range(hi - lo):   # seeded per chunk: the same global array whatever the number of ranks
+        g = torch.Generator(device=dev).manual_seed(100 + lo + i)
+        x[i].normal_(generator=g)
+    x += 0.25
     c = {"chunk": np.arange(lo, hi) * 1.0, "z": np.arange(z) * 1.0, "y": np.arange(n) * 1.0, "x": np.arange(n) * 1.0}
     da = xrft.DataArray(x, dims=["chunk", "z", "y", "x"], coords=c)
+    kw = dict(detrend="constant", window="hann")
 
     def step():
-        iso = xrft.isotropic_power_spectrum(da, dim=["y", "x"], detrend="constant", window="hann")
-        part = iso.data.reshape(-1, iso.shape[-1]).double().sum(dim=0)
-        buf = torch.cat([part, torch.tensor([float(iso.data.numel() // iso.shape[-1])], dtype=torch.float64, device=dev)])
-        shard.allreduce_sum(buf)
-        return buf[:-1] / buf[-1]
+        # this rank's block is `da` itself: shard_dim of length (hi - lo) split over one rank
+        return shard.sharded_isotropic_mean(da, "chunk", ["y", "x"], presharded=True, **kw)
 
-    if world > 1: dist.barrier()
-    ms, mean = timeit(step)
+    def sync():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+
+    lib.xrftb_launch_count(1)
+    ms, mean = _timeit(step, sync=sync)
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
-    if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    pts = chunks * z * n * n  # whole job
-    local_pts = (hi - lo) * z * n * n
-    emit({"config": 4, "workload": "isotropic_power_spectrum 512^2 planes x (64 x 512), detrend=constant, window=hann, mean over (chunk, z)",
-          "n_gpus": world, "GPts_s": (local_pts * world) / float(t.item()) / 1e6, "ms": float(t.item()), "points_total": local_pts * world,
-          "nbins": int(mean.numel()), "collective": "one all-reduce of nbins+1 float64" if world > 1 else "none (1 rank)",
-          "mean_head": [float(v) for v in mean[:3]]})
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    pts = chunks * z * n * n
+    gpts = pts / ms / 1e6
+    res = {"config": 4, "workload": "isotropic_power_spectrum %d^2 planes x (%d x %d) float32, detrend=constant, window=hann, mean over (chunk, z)" % (n, chunks, z),
+           "n_gpus": world, "scaling": "strong (64 chunks split over the ranks)", "value": gpts, "unit": "GPoints/s (whole job)", "ms": ms,
+           "points_total": pts, "nbins": int(mean.shape[-1]), "collective": "%s over %d rank(s)" % shard.last_collective(),
+           "gpu_launches": int(lib.xrftb_launch_count(0))}
+    res.update(_roof(gpts / world, 4.0))
+    if parity and rank == 0:
+        from oracle import xrft_oracle as O
+        sub = x[0, :4].cpu().numpy().astype(np.float64)
+        cc = {"z": c["z"][:4], "y": c["y"], "x": c["x"]}
+        ref = O.isotropic_power_spectrum(O.Labelled(sub, ("z", "y", "x"), cc), dim=["y", "x"], **kw).data
+        got = xrft.isotropic_power_spectrum(xrft.DataArray(x[0, :4], dims=["z", "y", "x"], coords=cc), dim=["y", "x"], **kw).values
+        res["parity"] = {"iso_relerr_4_planes": _relerr(got, ref)}
     del x, da
     torch.cuda.empty_cache()
+    return res
 
-if "5" in which:  # pad -> rfft -> irfft -> unpad, float64, + Parseval
-    n = int(os.environ.get("C5_N", "4096")); p = int(os.environ.get("C5_PAD", str(n // 2)))
+
+def run_config5(dev, n=8192, p=4096):
+    """pad -> fft(real_dim) -> ifft(real_dim) -> unpad of 8192^2 float64 (padded grid 16384^2) + Parseval (padding.py, xrft.py:307-646)"""
+    import torch
+    import xrft_b200 as xrft
+    from xrft_b200 import _lib as L
+    warnings.simplefilter("ignore")
+    lib = L.load()
     g = torch.Generator(device=dev).manual_seed(5)
     x = torch.randn((n, n), generator=g, device=dev, dtype=torch.float64)
     da = xrft.DataArray(x, dims=["y", "x"], coords={"y": np.arange(n) * 0.5, "x": np.arange(n) * 0.5})
@@ -88,15 +166,50 @@ if "5" in which:  # pad -> rfft -> irfft -> unpad, float64, + Parseval
         padded = xrft.pad(da, x=p, y=p)
         ft = xrft.fft(padded, real_dim="x")
         back = xrft.ifft(ft, real_dim="freq_x")
-        return xrft.unpad(back, {"x": p, "y": p}), padded
+        return xrft.unpad(back, {"x": p, "y": p})
 
-    ms, (un, padded) = timeit(rt, reps=2, warm=1)
+    lib.xrftb_launch_count(1)
+    ms, un = _timeit(rt, reps=3, warm=2)
+    launches = int(lib.xrftb_launch_count(0))
     err = float((un.data - x).abs().max() / x.abs().max())
+    del un
+    padded = xrft.pad(da, x=p, y=p)
     ps = xrft.power_spectrum(padded, real_dim="x")
     pars = float(ps.data.sum()) * ps["freq_x"].attrs["spacing"] * ps["freq_y"].attrs["spacing"]
     ref = float((padded.data ** 2).mean())
     N = n + 2 * p
-    emit({"config": 5, "workload": f"pad({p}) -> rfft -> irfft -> unpad of {n}^2 float64 (padded grid {N}^2)", "ms_round_trip": ms,
-          "GPts_s_padded_grid": N * N / ms / 1e6, "round_trip_max_rel_err": err, "parseval_rel_err": abs(pars - ref) / ref})
-if world > 1:
-    dist.destroy_process_group()
+    gpts = N * N / ms / 1e6
+    res = {"config": 5, "workload": "pad(%d) -> rfft -> irfft -> unpad of %d^2 float64 (padded grid %d^2)" % (p, n, N), "ms_round_trip": ms,
+           "value": gpts, "unit": "GPoints/s (padded-grid points)", "gpu_launches": launches,
+           "parity": {"round_trip_max_rel_err": err, "parseval_rel_err": abs(pars - ref) / ref}}
+    res.update(_roof(gpts, 32.0))
+    del x, da, padded, ps
+    torch.cuda.empty_cache()
+    return res
+
+
+def main():
+    import torch
+    which = sys.argv[1] if len(sys.argv) > 1 else "3,4,5"
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    if "3" in which and rank == 0:
+        print(json.dumps(run_config3(dev)), flush=True)
+    if "4" in which:
+        r = run_config4(dev, rank, world)
+        if rank == 0:
+            print(json.dumps(r), flush=True)
+    if "5" in which and rank == 0:
+        print(json.dumps(run_config5(dev)), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -29,6 +29,11 @@ EXPORTS = [
     "xrftb_binned_sum",
     "xrftb_spectrum2d_workspace",
     "xrftb_spectrum2d",
+    "xrftb_comm_unique_id",
+    "xrftb_comm_init",
+    "xrftb_comm_destroy",
+    "xrftb_comm_nccl_version",
+    "xrftb_allreduce_bins",
 ]
 
 F32, F64 = 0, 1
@@ -103,6 +108,13 @@ def load():
     lib.xrftb_spectrum2d_workspace.restype = C.c_size_t
     lib.xrftb_spectrum2d_workspace.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64]
     lib.xrftb_spectrum2d.argtypes = [C.POINTER(Spectrum2dDesc), vp]
+    lib.xrftb_comm_unique_id.argtypes = [vp]
+    lib.xrftb_comm_init.argtypes = [C.POINTER(vp), C.c_int, C.c_int, vp]
+    lib.xrftb_comm_destroy.argtypes = [vp]
+    lib.xrftb_comm_nccl_version.restype = C.c_int
+    lib.xrftb_allreduce_bins.argtypes = [vp, vp, C.c_size_t, vp]
+    for name in ["xrftb_comm_unique_id", "xrftb_comm_init", "xrftb_comm_destroy", "xrftb_allreduce_bins"]:
+        getattr(lib, name).restype = C.c_int
     for name in ["xrftb_device_info", "xrftb_fftn", "xrftb_moments", "xrftb_detrend_window", "xrftb_spectral_post",
                  "xrftb_binned_sum", "xrftb_spectrum2d", "xrftb_roll_scale"]:
         getattr(lib, name).restype = C.c_int

@@ -22,6 +22,7 @@ import warnings
 from collections import OrderedDict
 from typing import List, Optional, Sequence
 
+import numbers
 import os
 import numpy as np
 import scipy.signal as sps
@@ -232,19 +233,6 @@ def _spectral_core(x1, x2, ntrans, mode, *, detrend=None, windows=None, keep_hal
     # ---- fused path: real 2-D, power-of-two sizes
     if (is_real and ntrans == 2 and B.spectrum2d_supported(shape[-2], shape[-1], x1.dtype, two)
             and (not bins_mode or nbins <= 1024) and not (keep_half and shift[1])):
-        if mode == L.EPI_BINS_POWER and not keep_half and weight is None and os.environ.get("XRFTB_BINS_UNFUSED", "0") == "1":
-            # EXPERIMENT for round 2 (off by default): power spectrum of an L2-sized chunk of planes through the config-2
-            # chain, then one coalesced radial-bin pass over it, instead of the LUT + histogram epilogue fused into the
-            # column pass (which costs more than the transform at 512^2: DESIGN.md section 7).  XRFTB_BINSUM_RL=1 selects the
-            # run-length radial-bin kernel for the second step (also experimental).
-            flat = x1.reshape((-1,) + tuple(shape[-2:]))
-            per = max(1, int((64 << 20) // (shape[-2] * shape[-1] * x1.element_size())))
-            parts = []
-            for lo in range(0, flat.shape[0], per):
-                ps = B.spectrum2d(flat[lo:lo + per], None, L.EPI_POWER, detrend=det, win_y=tt(wins[0]), win_x=tt(wins[1]),
-                                  shift_y=shift[0], shift_x=shift[1], scale=scale)
-                parts.append(B.binned_sum(ps, lut, nbins, 2))
-            return torch.cat(parts, 0).reshape(tuple(shape[:-2]) + (nbins,))
         return B.spectrum2d(
             x1, x2, mode, detrend=det, win_y=tt(wins[0]), win_x=tt(wins[1]), keep_half=keep_half, shift_y=shift[0],
             shift_x=shift[1], scale=scale, ramp_y=tt(ramps[0]), ramp_x=tt(ramps[1]), weight_x=tt(weight), lut=lut, nbins=nbins,
@@ -291,7 +279,7 @@ def _to_last(t, axes):
 # =============================================================================================
 def _fft_prepare(da, spacing_tol, dim, real_dim, shift, true_phase, chunks_to_segments, prefix, real):
     """All host-side bookkeeping of xrft.fft up to (not including) the numerics."""
-    if not isinstance(spacing_tol, float):
+    if isinstance(spacing_tol, bool) or not isinstance(spacing_tol, numbers.Real):  # xrft.py:372-373 (any real number works there)
         raise TypeError("Please provide a float argument")
     if dim is None:
         dim = list(da.dims)
@@ -422,8 +410,18 @@ def _stream_host_chunks(arrs, ntrans, out_host, core):
     return out_host
 
 
-def _run_forward(P, das, mode, detrend, window, scale, ramps=None, weight=None, lut=None, nbins=0, out=None):
-    """Numerics of fft/power/cross for the prepared plan P on one or two DataArrays (already stacked/transposed)."""
+def _check_out(out, shape, np_dtype):
+    """`out=` (extension): a preallocated C-contiguous host buffer of exactly the result's shape and dtype"""
+    o = out.numpy() if _is_torch(out) else out
+    if _is_torch(out) and out.is_cuda:
+        raise ValueError("out= must be a host buffer (numpy array or CPU torch tensor)")
+    if not isinstance(o, np.ndarray) or tuple(o.shape) != tuple(shape) or o.dtype != np_dtype or not o.flags["C_CONTIGUOUS"]:
+        raise ValueError("out= must be a C-contiguous host array of shape %s and dtype %s" % (tuple(shape), np.dtype(np_dtype)))
+
+
+def _run_forward(P, das, mode, detrend, window, scale, ramps=None, weight=None, lut=None, nbins=0, out=None, plans=None):
+    """Numerics of fft/power/cross for the prepared plan P on one or two DataArrays (already stacked/transposed).
+    Container convention: host (numpy) inputs give a numpy result, device (torch CUDA) inputs a torch CUDA result."""
     torch = _torch()
     dim, real_dim = P["dim"], P["real_dim"]
     ntrans = len(dim)
@@ -436,7 +434,17 @@ def _run_forward(P, das, mode, detrend, window, scale, ramps=None, weight=None, 
     nd = P["da"].ndim
     host_in = all(not _is_torch(d.data) for d in das)
     trailing = list(P["axis_num"]) == list(range(nd - ntrans, nd))
-    if (host_in and trailing and nd > ntrans and not P["reversed_dims"] and mode not in (L.EPI_BINS_POWER, L.EPI_BINS_CROSS)
+    plans = plans or [P] * len(das)
+    any_reversed = any(pl["reversed_dims"] for pl in plans)
+    if out is not None:
+        W = P["N"][-1] // 2 + 1 if real_dim is not None else P["N"][-1]
+        lead_shape = [s_ for a, s_ in enumerate(P["da"].shape) if a not in P["axis_num"]]
+        cplx = mode in (L.EPI_COMPLEX, L.EPI_CROSS)
+        f32 = all(str(d.data.dtype).endswith("float32") for d in das)
+        _check_out(out, lead_shape + list(P["N"][:-1]) + [W], (np.complex64 if cplx else np.float32) if f32 else (np.complex128 if cplx else np.float64))
+        if not (host_in and trailing):
+            raise ValueError("out= is only supported for host inputs whose transform axes are trailing")
+    if (host_in and trailing and nd > ntrans and not any_reversed and mode not in (L.EPI_BINS_POWER, L.EPI_BINS_CROSS)
             and das[0].data.dtype in (np.float32, np.float64) and all(d.data.dtype == das[0].data.dtype for d in das)
             and das[0].data.nbytes >= _STREAM_MIN_BYTES and das[0].shape[0] >= 2):
         from . import backend as B
@@ -455,11 +463,11 @@ def _run_forward(P, das, mode, detrend, window, scale, ramps=None, weight=None, 
         return res.numpy() if out is None or not _is_torch(out) else res
     xs = []
     inv = None
-    for da in das:
+    for da, pl in zip(das, plans):
         t = _device_tensor(da.data)
         t, inv = _to_last(t, P["axis_num"])
-        if P["reversed_dims"]:
-            flip_axes = [t.ndim - ntrans + dim.index(d) for d in P["reversed_dims"]]
+        if pl["reversed_dims"]:   # each array by ITS OWN coordinate orientation (xrft.py:436-441)
+            flip_axes = [t.ndim - ntrans + pl["dim"].index(d) for d in pl["reversed_dims"]]
             t = torch.flip(t, dims=flip_axes).contiguous()
         xs.append(t)
     if len(xs) == 2 and xs[0].dtype != xs[1].dtype:
@@ -467,12 +475,16 @@ def _run_forward(P, das, mode, detrend, window, scale, ramps=None, weight=None, 
         xs = [x.to(dt) for x in xs]
     if real_dim is not None and xs[0].is_complex():
         raise ValueError("real_dim requires real input data")
-    out = _spectral_core(xs[0], xs[1] if len(xs) == 2 else None, ntrans, mode, detrend=detrend, windows=wins,
+    res = _spectral_core(xs[0], xs[1] if len(xs) == 2 else None, ntrans, mode, detrend=detrend, windows=wins,
                          keep_half=real_dim is not None, shift=[P["shift"]] * ntrans if real_dim is None else [False] * ntrans,
                          ramps=ramps, weight=weight, scale=scale, lut=lut, nbins=nbins)
     if inv is not None and mode not in (L.EPI_BINS_POWER, L.EPI_BINS_CROSS):
-        out = out.permute(*inv)
-    return out
+        res = res.permute(*inv)
+    if host_in:
+        res = res.cpu().numpy()
+        if out is not None:
+            np.copyto(out.numpy() if _is_torch(out) else out, res)
+    return res
 
 
 def fft(da, spacing_tol=1e-3, dim=None, real_dim=None, shift=True, detrend=None, window=None, true_phase=True,
@@ -566,6 +578,7 @@ def ifft(daft, spacing_tol=1e-3, dim=None, real_dim=None, shift=True, true_phase
         if np.abs(l) > spacing_tol:
             raise ValueError("Inverse Fourier Transform can not be computed because coordinate %s is not centered on zero frequency" % d)
 
+    host_in = not _is_torch(daft.data)
     t = _device_tensor(daft.data)
     if not t.is_complex():
         t = t.to(torch.complex64 if t.dtype == torch.float32 else torch.complex128)
@@ -606,6 +619,8 @@ def ifft(daft, spacing_tol=1e-3, dim=None, real_dim=None, shift=True, true_phase
     f = B.roll_scale(f, ntrans, out_shifts, scale)
     if inv is not None:
         f = f.permute(*inv)
+    if host_in:
+        f = f.cpu().numpy()
 
     swap = {d: _new_name(d, prefix) for d in dim}
     out = DataArray(f, dims=[swap.get(d, d) for d in daft.dims])
@@ -719,10 +734,11 @@ def _spectrum(da1, da2, mode, dim, real_dim, scaling, window_correction, kwargs,
             ramps = None
     weight = None
     if P["real_dim"] is not None:
-        n_real = da1.sizes[P["real_dim"]] if not c2s else P["da"].sizes[P["real_dim"]]
+        n_real = da1.sizes[P["real_dim"]]   # len(da[real_dim]) of the un-segmented array, like the reference (xrft.py:678)
         weight = _real_dim_weights(n_real, P["N"][-1] // 2 + 1)
     lut, nbins = (None, 0) if bins is None else bins(P)
-    out = _run_forward(P, das, mode, detrend_t, window, scale, ramps=ramps, weight=weight, lut=lut, nbins=nbins, out=out_buf)
+    out = _run_forward(P, das, mode, detrend_t, window, scale, ramps=ramps, weight=weight, lut=lut, nbins=nbins, out=out_buf,
+                       plans=[P, P2] if da2 is not None else None)
     return P, out
 
 
@@ -821,6 +837,8 @@ def isotropize(ps, fftdim, nfactor=4, truncate=True, complx=False):
     iso = B.binned_sum(t, torch.from_numpy(codes.astype(np.int32)), nbins, 2)
     if not complx:
         iso = iso.to(t.dtype)  # output_dtypes=[array.dtype] (xrft.py:931)
+    if not _is_torch(ps.data):
+        iso = iso.cpu().numpy()
     out = DataArray(iso, dims=others + ["freq_r"], name=ps.name)
     for cname, c in ps.coords.items():
         if cname not in fftdim and not any(d in fftdim for d in c.dims):
@@ -863,7 +881,8 @@ def _iso_common(da1, da2, mode, spacing_tol, dim, shift, detrend, scaling, windo
     P, out = _spectrum(da1, da2, mode, dim, None, scaling, window_correction, kw, bins=bins)
     others = [d for d in P["da"].dims if d not in P["dim"]]
     if da2 is None and str(P["da"].data.dtype).endswith("float32"):
-        out = out.float()  # output_dtypes=[array.dtype] (xrft.py:931); accumulation itself is fp64
+        # output_dtypes=[array.dtype] (xrft.py:931); accumulation itself is fp64
+        out = out.astype(np.float32) if isinstance(out, np.ndarray) else out.float()
     res = DataArray(out, dims=others + ["freq_r"])
     for cname, c in P["da"].coords.items():
         if cname not in P["dim"] and not any(d in P["dim"] for d in c.dims):
@@ -935,6 +954,8 @@ def detrend(da, dim, detrend_type="constant"):
         out = B.detrend_window(t, len(dim), det)
     if inv is not None:
         out = out.permute(*inv)
+    if not _is_torch(da.data):
+        out = out.cpu().numpy()
     return da._replace(data=out)
 
 

@@ -99,12 +99,13 @@ template <> const cplx<double>* twiddle_r2c<double>(int l) { return get_table<do
 // ------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(512) moments_kernel(const T* __restrict__ in, double* __restrict__ mom, long n0, long n1,
-                                                      long n2, int chunks) {
-    const long b = blockIdx.y;
+                                                      long n2, int chunks, long batch) {
     const long rows = n0 * n1;
     const long r0 = rows * blockIdx.x / chunks, r1 = rows * (blockIdx.x + 1) / chunks;
-    const T* base = in + b * rows * n2;
     const double c0m = 0.5 * (double)(n0 - 1), c1m = 0.5 * (double)(n1 - 1), c2m = 0.5 * (double)(n2 - 1);
+    __shared__ double red[4][16];
+    for (long b = blockIdx.y; b < batch; b += gridDim.y) {   // gridDim.y <= 65535: items beyond it are strided over
+    const T* base = in + b * rows * n2;
     double S = 0, S0 = 0, S1 = 0, S2 = 0;
     const bool vec = (sizeof(T) == 4) && (n2 % 4 == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0);
     if (vec && n2 / 4 < 2 * (long)blockDim.x) {
@@ -177,7 +178,6 @@ __global__ void __launch_bounds__(512) moments_kernel(const T* __restrict__ in, 
             S2 += sx;
         }
     }
-    __shared__ double red[4][16];
     double vals[4] = {S, S0, S1, S2};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -190,6 +190,8 @@ __global__ void __launch_bounds__(512) moments_kernel(const T* __restrict__ in, 
         double x = 0;
         for (int w = 0; w < (int)(blockDim.x >> 5); ++w) x += red[threadIdx.x][w];
         atomicAdd(mom + b * 4 + threadIdx.x, x);
+    }
+    __syncthreads();
     }
 }
 
@@ -522,69 +524,45 @@ __global__ void __launch_bounds__(256) mirror_fill_kernel(void* __restrict__ out
 // ------------------------------------------------------------------------------------------------
 template <typename T, bool CPLX>
 __global__ void __launch_bounds__(256) binned_sum_kernel(const T* __restrict__ arr, const int* __restrict__ lut,
-                                                         double* __restrict__ bins, long ncell, int nbins, int chunks) {
+                                                         double* __restrict__ bins, long ncell, int nbins, int chunks, long batch) {
     extern __shared__ double hist[];
-    const long b = blockIdx.y;
     const int width = CPLX ? 2 : 1;
-    for (int i = threadIdx.x; i < nbins * width; i += blockDim.x) hist[i] = 0.0;
-    __syncthreads();
     const long c0 = ncell * blockIdx.x / chunks, c1 = ncell * (blockIdx.x + 1) / chunks;
-    const T* p = arr + b * ncell * width;
-    for (long i = c0 + threadIdx.x; i < c1; i += blockDim.x) {
-        const int bin = lut[i];
-        if (bin < 0) continue;
-        if (CPLX) {
-            atomicAdd(&hist[2 * bin], (double)p[2 * i]);
-            atomicAdd(&hist[2 * bin + 1], (double)p[2 * i + 1]);
-        } else {
-            atomicAdd(&hist[bin], (double)p[i]);
-        }
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < nbins * width; i += blockDim.x)
-        if (hist[i] != 0.0) atomicAdd(bins + b * nbins * width + i, hist[i]);
-}
-
-// EXPERIMENTAL (XRFTB_BINSUM_RL=1, off by default; written at the end of round 1, not yet run on hardware): float32 real
-// radial-bin sum for the unfused isotropic spectrum.  Every thread takes 16 consecutive cells (four 16-byte loads of the
-// values and of the LUT), accumulates runs of equal bins in a register -- radial bins change slowly along a row -- and
-// issues one native fp32 shared-memory atomic per run; a CTA's fp32 partial sums (a few hundred values per bin) go to the
-// item's fp64 bins with one atomic per bin, as in the fused epilogue.
-__global__ void __launch_bounds__(256) binned_sum_f32_rl_kernel(const float* __restrict__ arr, const int* __restrict__ lut,
-                                                                double* __restrict__ bins, long ncell, int nbins, int chunks) {
-    extern __shared__ float histf[];
-    const long b = blockIdx.y;
-    for (int i = threadIdx.x; i < nbins; i += blockDim.x) histf[i] = 0.f;
-    __syncthreads();
-    constexpr int SEG = 16;
-    const long nseg = ncell / SEG;   // ncell % 16 == 0 (checked by the launcher)
-    const long s0 = nseg * blockIdx.x / chunks, s1 = nseg * (blockIdx.x + 1) / chunks;
-    const float4* p = reinterpret_cast<const float4*>(arr + b * ncell);
-    const int4* q = reinterpret_cast<const int4*>(lut);
-    for (long sgm = s0 + threadIdx.x; sgm < s1; sgm += blockDim.x) {
-        float v[SEG]; int c[SEG];
-#pragma unroll
-        for (int j = 0; j < SEG / 4; ++j) {
-            const float4 x = p[sgm * (SEG / 4) + j];
-            const int4 y = __ldg(q + sgm * (SEG / 4) + j);
-            v[4 * j] = x.x; v[4 * j + 1] = x.y; v[4 * j + 2] = x.z; v[4 * j + 3] = x.w;
-            c[4 * j] = y.x; c[4 * j + 1] = y.y; c[4 * j + 2] = y.z; c[4 * j + 3] = y.w;
-        }
-        int cur = -1;
-        float acc = 0.f;
-#pragma unroll
-        for (int j = 0; j < SEG; ++j) {
-            if (c[j] != cur) {
-                if (cur >= 0) atomicAdd(histf + cur, acc);
-                cur = c[j]; acc = 0.f;
+    for (long b = blockIdx.y; b < batch; b += gridDim.y) {   // gridDim.y <= 65535: items beyond it are strided over
+        for (int i = threadIdx.x; i < nbins * width; i += blockDim.x) hist[i] = 0.0;
+        __syncthreads();
+        const T* p = arr + b * ncell * width;
+        for (long i = c0 + threadIdx.x; i < c1; i += blockDim.x) {
+            const int bin = lut[i];
+            if (bin < 0) continue;
+            if (CPLX) {
+                atomicAdd(&hist[2 * bin], (double)p[2 * i]);
+                atomicAdd(&hist[2 * bin + 1], (double)p[2 * i + 1]);
+            } else {
+                atomicAdd(&hist[bin], (double)p[i]);
             }
-            acc += v[j];
         }
-        if (cur >= 0) atomicAdd(histf + cur, acc);
+        __syncthreads();
+        for (int i = threadIdx.x; i < nbins * width; i += blockDim.x)
+            if (hist[i] != 0.0) atomicAdd(bins + b * nbins * width + i, hist[i]);
+        __syncthreads();
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < nbins; i += blockDim.x)
-        if (histf[i] != 0.f) atomicAdd(bins + b * nbins + i, (double)histf[i]);
+}
+// more bins than a CTA histogram holds (min(N) / nfactor > 2048): fp64 atomics straight to the item's global bins
+template <typename T, bool CPLX>
+__global__ void __launch_bounds__(256) binned_sum_global_kernel(const T* __restrict__ arr, const int* __restrict__ lut,
+                                                                double* __restrict__ bins, long ncell, int nbins, long batch) {
+    const int width = CPLX ? 2 : 1;
+    for (long b = blockIdx.y; b < batch; b += gridDim.y) {
+        const T* p = arr + b * ncell * width;
+        double* bb = bins + b * (long)nbins * width;
+        for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < ncell; i += (long)gridDim.x * blockDim.x) {
+            const int bin = lut[i];
+            if (bin < 0) continue;
+            if (CPLX) { atomicAdd(bb + 2 * bin, (double)p[2 * i]); atomicAdd(bb + 2 * bin + 1, (double)p[2 * i + 1]); }
+            else atomicAdd(bb + bin, (double)p[i]);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1136,7 +1114,7 @@ static int spectrum2d_colsfirst(const xrftb_spectrum2d_desc& q, int ly, int lx, 
         if (chunks < 1) chunks = 1;
         if (chunks > q.ny) chunks = q.ny;
         dim3 grid(chunks, (unsigned)q.batch);
-        moments_kernel<T><<<grid, 256, 0, st>>>(in, mom, 1, q.ny, q.nx, chunks);
+        moments_kernel<T><<<grid, 256, 0, st>>>(in, mom, 1, q.ny, q.nx, chunks, q.batch);
         if (int rc = check_launch("moments_kernel")) return rc;
     }
     const int tiles_per_item = q.nx / (2 * C);
@@ -1370,7 +1348,7 @@ static int spectrum2d_impl(const xrftb_spectrum2d_desc& q, cudaStream_t st) {
             if (chunks < 1) chunks = 1;
             if (chunks > q.ny) chunks = q.ny;
             dim3 grid(chunks, (unsigned)nitems);
-            moments_kernel<T><<<grid, 256, 0, st>>>(base, m, 1, q.ny, q.nx, chunks);
+            moments_kernel<T><<<grid, 256, 0, st>>>(base, m, 1, q.ny, q.nx, chunks, nitems);
         }
         return check_launch("moments_kernel");
     };
@@ -1537,10 +1515,9 @@ int xrftb_moments(const void* in, double* moments, int dtype, int64_t batch, int
     int chunks = (int)((8L * sm_count() + batch - 1) / batch);
     if (chunks < 1) chunks = 1;
     if (chunks > rows) chunks = (int)rows;
-    if (batch > 65535) { set_error("moments: batch > 65535 unsupported"); return XRFTB_EUNSUPPORTED; }
-    dim3 grid(chunks, (unsigned)batch);
-    if (dtype == XRFTB_F32) moments_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(in), moments, n0, n1, n2, chunks);
-    else if (dtype == XRFTB_F64) moments_kernel<double><<<grid, 256, 0, st>>>(reinterpret_cast<const double*>(in), moments, n0, n1, n2, chunks);
+    dim3 grid(chunks, (unsigned)(batch < 65535 ? batch : 65535));
+    if (dtype == XRFTB_F32) moments_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(in), moments, n0, n1, n2, chunks, batch);
+    else if (dtype == XRFTB_F64) moments_kernel<double><<<grid, 256, 0, st>>>(reinterpret_cast<const double*>(in), moments, n0, n1, n2, chunks, batch);
     else { set_error("moments: bad dtype"); return XRFTB_EINVAL; }
     return check_launch("moments_kernel");
 }
@@ -1584,31 +1561,34 @@ int xrftb_spectral_post(const void* in1, const void* in2, void* out, int dtype, 
 
 int xrftb_binned_sum(const void* array, const int32_t* lut, double* bins, int dtype, int is_complex, int64_t batch, int64_t ncell,
                      int nbins, void* stream) {
-    if (!array || !lut || !bins || nbins < 1 || nbins > 2048 || batch < 1 || batch > 65535) { set_error("binned_sum: bad arguments (nbins<=2048, batch<=65535)"); return XRFTB_EINVAL; }
+    if (!array || !lut || !bins || nbins < 1 || batch < 1 || ncell < 1) { set_error("binned_sum: bad arguments"); return XRFTB_EINVAL; }
+    if (dtype != XRFTB_F32 && dtype != XRFTB_F64) { set_error("binned_sum: bad dtype"); return XRFTB_EINVAL; }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     int chunks = (int)((4L * sm_count() + batch - 1) / batch);
     if (chunks < 1) chunks = 1;
     if ((long)chunks * 1024 > ncell) chunks = (int)((ncell + 1023) / 1024);
-    dim3 grid(chunks, (unsigned)batch);
+    const unsigned gy = (unsigned)(batch < 65535 ? batch : 65535);
+    dim3 grid(chunks, gy);
     const size_t smem = (size_t)nbins * (is_complex ? 2 : 1) * sizeof(double);
-    {   // experimental run-length kernel (off by default)
-        static int rl_on = -1;
-        if (rl_on < 0) { const char* e = getenv("XRFTB_BINSUM_RL"); rl_on = e ? atoi(e) : 0; }
-        if (rl_on && dtype == XRFTB_F32 && !is_complex && ncell % 16 == 0 && (reinterpret_cast<uintptr_t>(array) & 15) == 0 &&
-            (reinterpret_cast<uintptr_t>(lut) & 15) == 0) {
-            int ch = (int)(ncell / (16L * 256 * 8));   // ~8 sweeps of 256 threads x 16 cells per CTA
-            if (ch < 1) ch = 1;
-            binned_sum_f32_rl_kernel<<<dim3(ch, (unsigned)batch), 256, (size_t)nbins * sizeof(float), st>>>(
-                reinterpret_cast<const float*>(array), lut, bins, ncell, nbins, ch);
-            return check_launch("binned_sum_f32_rl_kernel");
+    if (nbins > 2048) {   // the histogram would not fit a CTA's default shared memory: global fp64 atomics
+        long gx = (ncell + 255) / 256;
+        if (gx > 4L * sm_count()) gx = 4L * sm_count();
+        dim3 g2((unsigned)gx, gy);
+        if (dtype == XRFTB_F32) {
+            if (is_complex) binned_sum_global_kernel<float, true><<<g2, 256, 0, st>>>(reinterpret_cast<const float*>(array), lut, bins, ncell, nbins, batch);
+            else binned_sum_global_kernel<float, false><<<g2, 256, 0, st>>>(reinterpret_cast<const float*>(array), lut, bins, ncell, nbins, batch);
+        } else {
+            if (is_complex) binned_sum_global_kernel<double, true><<<g2, 256, 0, st>>>(reinterpret_cast<const double*>(array), lut, bins, ncell, nbins, batch);
+            else binned_sum_global_kernel<double, false><<<g2, 256, 0, st>>>(reinterpret_cast<const double*>(array), lut, bins, ncell, nbins, batch);
         }
+        return check_launch("binned_sum_global_kernel");
     }
     if (dtype == XRFTB_F32) {
-        if (is_complex) binned_sum_kernel<float, true><<<grid, 256, smem, st>>>(reinterpret_cast<const float*>(array), lut, bins, ncell, nbins, chunks);
-        else binned_sum_kernel<float, false><<<grid, 256, smem, st>>>(reinterpret_cast<const float*>(array), lut, bins, ncell, nbins, chunks);
+        if (is_complex) binned_sum_kernel<float, true><<<grid, 256, smem, st>>>(reinterpret_cast<const float*>(array), lut, bins, ncell, nbins, chunks, batch);
+        else binned_sum_kernel<float, false><<<grid, 256, smem, st>>>(reinterpret_cast<const float*>(array), lut, bins, ncell, nbins, chunks, batch);
     } else if (dtype == XRFTB_F64) {
-        if (is_complex) binned_sum_kernel<double, true><<<grid, 256, smem, st>>>(reinterpret_cast<const double*>(array), lut, bins, ncell, nbins, chunks);
-        else binned_sum_kernel<double, false><<<grid, 256, smem, st>>>(reinterpret_cast<const double*>(array), lut, bins, ncell, nbins, chunks);
+        if (is_complex) binned_sum_kernel<double, true><<<grid, 256, smem, st>>>(reinterpret_cast<const double*>(array), lut, bins, ncell, nbins, chunks, batch);
+        else binned_sum_kernel<double, false><<<grid, 256, smem, st>>>(reinterpret_cast<const double*>(array), lut, bins, ncell, nbins, chunks, batch);
     } else { set_error("binned_sum: bad dtype"); return XRFTB_EINVAL; }
     return check_launch("binned_sum_kernel");
 }
@@ -1652,15 +1632,31 @@ size_t xrftb_spectrum2d_workspace(int dtype, int ny, int nx, int two_fields, int
 
 int xrftb_spectrum2d(const xrftb_spectrum2d_desc* q, void* stream) {
     if (!q || !q->in1 || q->batch < 1) { set_error("spectrum2d: bad descriptor"); return XRFTB_EINVAL; }
-    if (q->batch > 65535) { set_error("spectrum2d: batch > 65535 per call unsupported (split the call)"); return XRFTB_EUNSUPPORTED; }
     const bool bins_mode = (q->mode == XRFTB_EPI_BINS_POWER || q->mode == XRFTB_EPI_BINS_CROSS);
     if (bins_mode && (!q->lut || !q->bins || q->nbins < 1)) { set_error("spectrum2d: bins mode needs lut/bins/nbins"); return XRFTB_EINVAL; }
     if (!bins_mode && !q->out) { set_error("spectrum2d: out is NULL"); return XRFTB_EINVAL; }
+    if (q->dtype != XRFTB_F32 && q->dtype != XRFTB_F64) { set_error("spectrum2d: bad dtype %d", q->dtype); return XRFTB_EINVAL; }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (q->dtype == XRFTB_F32) return spectrum2d_impl<float>(*q, st);
-    if (q->dtype == XRFTB_F64) return spectrum2d_impl<double>(*q, st);
-    set_error("spectrum2d: bad dtype %d", q->dtype);
-    return XRFTB_EINVAL;
+    // the per-call tables (moments region of the workspace, grid.y of the reductions) are sized for 65535 items: longer
+    // batches run as consecutive blocks of the same call
+    const int64_t kBlock = 65535;
+    const size_t esz = q->dtype == XRFTB_F32 ? sizeof(float) : sizeof(double);
+    const size_t in_item = (size_t)q->ny * q->nx * esz;
+    const size_t W = q->keep_half ? (size_t)q->nx / 2 + 1 : (size_t)q->nx;
+    const bool cplx_out = (q->mode == XRFTB_EPI_COMPLEX || q->mode == XRFTB_EPI_CROSS);
+    const size_t out_item = (size_t)q->ny * W * esz * (cplx_out ? 2 : 1);
+    const size_t bins_item = (size_t)q->nbins * (q->mode == XRFTB_EPI_BINS_CROSS ? 2 : 1);
+    for (int64_t b0 = 0; b0 < q->batch; b0 += kBlock) {
+        xrftb_spectrum2d_desc d = *q;
+        d.batch = q->batch - b0 < kBlock ? q->batch - b0 : kBlock;
+        d.in1 = reinterpret_cast<const char*>(q->in1) + (size_t)b0 * in_item;
+        if (q->in2) d.in2 = reinterpret_cast<const char*>(q->in2) + (size_t)b0 * in_item;
+        if (q->out) d.out = reinterpret_cast<char*>(q->out) + (size_t)b0 * out_item;
+        if (q->bins) d.bins = q->bins + (size_t)b0 * bins_item;
+        const int rc = q->dtype == XRFTB_F32 ? spectrum2d_impl<float>(d, st) : spectrum2d_impl<double>(d, st);
+        if (rc) return rc;
+    }
+    return 0;
 }
 
 }  // extern "C"

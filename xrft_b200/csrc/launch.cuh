@@ -4,16 +4,24 @@
 
 namespace xrftb {
 
+// Per-kernel launch preparation, cached PER DEVICE: the opt-in dynamic shared-memory attribute is a per-device property of
+// the function, and the occupancy (hence the persistent grid size) belongs to the device that answered the query.  A
+// process may drive several GPUs (tensors on any device); concurrent first calls write the same values (benign).
+constexpr int kMaxDevices = 64;
+struct DevOcc { int v[kMaxDevices]; DevOcc() { for (int& x : v) x = -1; } };
 template <class Kern>
-static inline int prepare_kernel(Kern kern, int threads, size_t smem, int* occ_cache) {
-    if (*occ_cache < 0) {
+static inline int prepare_kernel(Kern kern, int threads, size_t smem, DevOcc* cache, int* occ_out) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) { set_error("no current CUDA device"); return -3; }
+    if (cache->v[dev] < 0) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(e)); return -3; }
         int occ = 0;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem);
         if (e != cudaSuccess || occ < 1) { set_error("occupancy query failed (threads=%d smem=%zu): %s", threads, smem, cudaGetErrorString(e)); return -3; }
-        *occ_cache = occ;
+        cache->v[dev] = occ;
     }
+    *occ_out = cache->v[dev];
     return 0;
 }
 
@@ -35,8 +43,9 @@ static int launch_rows(const IO& io, long nseq, cudaStream_t st) {
     auto kern = rows_kernel<T, LOG2L, LOGE, SEQ, IO>;
     constexpr int threads = G_::NT * SEQ;
     constexpr size_t smem = (size_t)SEQ * (G_::LPAD + IO::kSeqSkew) * sizeof(cplx<T>);
-    static int occ = -1;
-    if (int rc = prepare_kernel(kern, threads, smem, &occ)) return rc;
+    static DevOcc occ_;
+    int occ = 0;
+    if (int rc = prepare_kernel(kern, threads, smem, &occ_, &occ)) return rc;
     const cplx<T>* tw = twiddle_fft<T>(LOG2L);
     if (!tw) return -3;
     long ngroups = (nseq + SEQ - 1) / SEQ;
@@ -56,8 +65,9 @@ static int launch_rows2(const RowsR2CFused<T>& io, long nseq, cudaStream_t st) {
     // + row-line partial sums [PAIRS][WPP][4] and lines [PAIRS][4] (floats)
     constexpr int WPP = G_::NT < 32 ? 1 : G_::NT / 32;
     constexpr size_t smem = (size_t)PAIRS * (2 * G_::LPAD + 8) * sizeof(cplx<T>) + (size_t)PAIRS * (WPP + 1) * 4 * sizeof(float);
-    static int occ = -1;
-    if (int rc = prepare_kernel(kern, threads, smem, &occ)) return rc;
+    static DevOcc occ_;
+    int occ = 0;
+    if (int rc = prepare_kernel(kern, threads, smem, &occ_, &occ)) return rc;
     const cplx<T>* tw = twiddle_fft<T>(LOG2L);
     if (!tw) return -3;
     long ngroups = nseq / (2 * PAIRS);
@@ -75,8 +85,9 @@ static int launch_rows2c_power(const RowsC2CPower<T>& io, long nseq, cudaStream_
     auto kern = rows2c_power_kernel<T, LOG2L, LOGE, PAIRS>;
     constexpr int threads = G_::NT * PAIRS;
     constexpr size_t smem = (size_t)PAIRS * (2 * G_::LPAD + 8) * sizeof(cplx<T>);
-    static int occ = -1;
-    if (int rc = prepare_kernel(kern, threads, smem, &occ)) return rc;
+    static DevOcc occ_;
+    int occ = 0;
+    if (int rc = prepare_kernel(kern, threads, smem, &occ_, &occ)) return rc;
     const cplx<T>* tw = twiddle_fft<T>(LOG2L);
     if (!tw) return -3;
     long ngroups = (nseq + 2 * PAIRS - 1) / (2 * PAIRS);
@@ -95,8 +106,9 @@ static int launch_rowsz_power(const RowsZPower<T>& io, long nseq, cudaStream_t s
     auto kern = rowsz_power_kernel<T, LOG2M, LOGE, ROWS>;
     constexpr int threads = G_::NT * ROWS;
     constexpr size_t smem = ((size_t)ROWS * (2 * G_::LPAD + 8) + (size_t)(1 << LOG2M)) * sizeof(cplx<T>);
-    static int occ = -1;
-    if (int rc = prepare_kernel(kern, threads, smem, &occ)) return rc;
+    static DevOcc occ_;
+    int occ = 0;
+    if (int rc = prepare_kernel(kern, threads, smem, &occ_, &occ)) return rc;
     const cplx<T>* tw = twiddle_fft<T>(LOG2M);
     if (!tw) return -3;
     long ngroups = (nseq + ROWS - 1) / ROWS;
@@ -115,8 +127,9 @@ static int launch_rowszx(const RowsZCross<float>& io, long nseq, cudaStream_t st
     auto kern = rowszx_kernel<LOG2M, LOGE, ROWS, MODE>;
     constexpr int threads = G_::NT * 2 * ROWS;
     constexpr size_t smem = ((size_t)2 * ROWS * (2 * G_::LPAD + 8) + (size_t)(1 << LOG2M)) * sizeof(float2);
-    static int occ = -1;
-    if (int rc = prepare_kernel(kern, threads, smem, &occ)) return rc;
+    static DevOcc occ_;
+    int occ = 0;
+    if (int rc = prepare_kernel(kern, threads, smem, &occ_, &occ)) return rc;
     const float2* tw = twiddle_fft<float>(LOG2M);
     if (!tw) return -3;
     long ngroups = (nseq + ROWS - 1) / ROWS;
@@ -135,8 +148,9 @@ static int launch_rowszp_power(const RowsZPower<float>& io, long nseq, cudaStrea
     auto kern = rowszp_power_kernel<LOG2M, LOGE, ROWS>;
     constexpr int threads = G_::NT * ROWS;
     constexpr size_t smem = (size_t)ROWS * (G_::LPAD + 4) * sizeof(float4) + (size_t)(1 << LOG2M) * sizeof(float2);
-    static int occ = -1;
-    if (int rc = prepare_kernel(kern, threads, smem, &occ)) return rc;
+    static DevOcc occ_;
+    int occ = 0;
+    if (int rc = prepare_kernel(kern, threads, smem, &occ_, &occ)) return rc;
     const float2* tw = twiddle_fft<float>(LOG2M);
     if (!tw) return -3;
     long ngroups = (nseq + ROWS - 1) / ROWS;
@@ -159,8 +173,9 @@ static int launch_cols(const IO& io, long ntiles, cudaStream_t st, size_t extra_
     constexpr size_t smem_cap = smem_fixed + (IO::kBins ? (size_t)kMaxFusedBins * 2 * sizeof(double) : 0);
     const size_t smem = smem_fixed + extra_smem;
     if (smem > smem_cap) { set_error("launch_cols: too many bins for the fused path"); return -2; }
-    static int occ = -1;
-    if (int rc = prepare_kernel(kern, threads, smem_cap, &occ)) return rc;
+    static DevOcc occ_;
+    int occ = 0;
+    if (int rc = prepare_kernel(kern, threads, smem_cap, &occ_, &occ)) return rc;
     const cplx<T>* tw = twiddle_fft<T>(LOG2L);
     if (!tw) return -3;
     long grid = (long)sm_count() * occ;
@@ -182,8 +197,9 @@ static int launch_cols_async(IO io, long ntiles, cudaStream_t st, size_t extra_s
     const size_t smem = smem_fixed + extra_smem;
     if (smem > smem_cap) { set_error("launch_cols_async: too many bins for the fused path"); return -2; }
     if constexpr (IO::kBins) io.hist_off = (int)((size_t)G_::LPAD * (C / 2) * sizeof(cplx<T>) + 16);   // relative to the X buffer
-    static int occ = -1;
-    if (int rc = prepare_kernel(kern, threads, smem_cap, &occ)) return rc;
+    static DevOcc occ_;
+    int occ = 0;
+    if (int rc = prepare_kernel(kern, threads, smem_cap, &occ_, &occ)) return rc;
     const cplx<T>* tw = twiddle_fft<T>(LOG2L);
     if (!tw) return -3;
     long grid = (long)sm_count() * occ;
@@ -202,8 +218,9 @@ static int launch_colszp(const ColsR2CPack<float>& io, long ntiles, cudaStream_t
     auto kern = colszp_kernel<LOG2L, LOGE, C>;
     constexpr int threads = G_::NT * (C / 2);
     constexpr size_t smem = (size_t)G_::LPAD * (C + C / 2) * sizeof(float2) + 16 + IO::kExtraSmemBytes;
-    static int occ = -1;
-    if (int rc = prepare_kernel(kern, threads, smem, &occ)) return rc;
+    static DevOcc occ_;
+    int occ = 0;
+    if (int rc = prepare_kernel(kern, threads, smem, &occ_, &occ)) return rc;
     const float2* tw = twiddle_fft<float>(LOG2L);
     if (!tw) return -3;
     long grid = (long)sm_count() * occ;

@@ -2,8 +2,8 @@
 
 ``xarray`` (like dask, numpy_groupies and cftime) is not installable in this image
 (SURVEY.md F2), so the xrft-facing API of xrft_b200 works on this class; real
-``xarray.DataArray`` objects are accepted and returned when xarray is importable
-(see ``from_any`` / ``to_xarray``).  Only the surface the reference uses is covered
+``xarray.DataArray`` objects are accepted when xarray is importable (``from_any``); results are
+always this class -- ``to_xarray(result)`` converts back.  Only the surface the reference uses is covered
 (SURVEY.md Appendix B): named dims, 1-D dimension coordinates with attrs, name-based
 broadcasting arithmetic, numpy ufunc dispatch, and the handful of reshaping methods
 xrft calls.  ``data`` may be a numpy array or a torch tensor (CPU or CUDA); ``values``
