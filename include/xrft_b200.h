@@ -149,6 +149,8 @@ typedef struct {
     int lut_symmetric;    /* 1 if lut[-ky][-kx] == lut[ky][kx] for all cells (radial bins): lets mirrored cells reuse the bin */
     void* work;
     size_t work_bytes;
+    void* out2;           /* mode CROSS only, nullable: ALSO write angle(F1 conj(F2) ramps), real [batch][ny][W] -- cross_spectrum and
+                             cross_phase (xrft.py:753-874) from one read of the two fields instead of the reference's two pipelines */
 } xrftb_spectrum2d_desc;
 
 /* minimum workspace (one batch item in flight) and the size that keeps `batch` items in flight */

@@ -554,3 +554,21 @@ def test_container_convention_and_out_validation():
     buf = np.empty((4, 16, 32))
     r2 = xrft.power_spectrum(da, dim=["y", "x"], out=buf)
     np.testing.assert_array_equal(buf, r2.values)
+
+
+def test_cross_spectrum_and_phase_all_paths():
+    """cross_spectrum_and_phase == (cross_spectrum, cross_phase) on the fused z-mode chain (float32 1024^2), the rows-first
+    two-field chain (float64; lagged coordinates -> ramps) and the composed path (non power-of-two)"""
+    rng = np.random.default_rng(69)
+    for shape, dt, off in (((2, 1024, 1024), np.float32, None), ((2, 64, 128), np.float64, {"x": 2.5}), ((2, 20, 30), np.float64, None)):
+        a = mk(shape, ("t", "y", "x"), rng, dt=dt, spacing={"t": 1.0, "y": 1.0, "x": 1.0})
+        b = mk(shape, ("t", "y", "x"), rng, dt=dt, spacing={"t": 1.0, "y": 1.0, "x": 1.0}, offset=off)
+        kw = dict(dim=["y", "x"], detrend="linear", window="hann")
+        cs, ph = xrft.cross_spectrum_and_phase(a, b, **kw)
+        cs1, ph1 = xrft.cross_spectrum(a, b, **kw), xrft.cross_phase(a, b, **kw)
+        assert cs.dims == cs1.dims and ph.dims == ph1.dims
+        np.testing.assert_allclose(cs.values, cs1.values, rtol=1e-6, atol=1e-6 * np.abs(cs1.values).max())
+        d = np.abs(np.angle(np.exp(1j * (ph.values - ph1.values))))
+        assert d[np.abs(cs1.values) > 1e-3 * np.abs(cs1.values).max()].max() < 1e-4
+        ref = O.cross_spectrum(lab(a), lab(b), **kw)
+        assert relerr(cs.values, ref.data) < (1e-3 if dt == np.float32 else 1e-8)

@@ -8,12 +8,13 @@ See DESIGN.md and INTEGRATION.md.
 """
 from .dataarray import DataArray, set_options  # noqa: F401
 from .api import (  # noqa: F401
-    fft, ifft, dft, idft, power_spectrum, cross_spectrum, cross_phase, isotropize, isotropic_power_spectrum,
-    isotropic_cross_spectrum, fit_loglog, detrend, pad, unpad,
+    fft, ifft, dft, idft, power_spectrum, cross_spectrum, cross_phase, cross_spectrum_and_phase, isotropize,
+    isotropic_power_spectrum, isotropic_cross_spectrum, fit_loglog, detrend, pad, unpad,
 )
 
 __version__ = "0.1.0"
 __all__ = [
-    "DataArray", "fft", "ifft", "dft", "idft", "power_spectrum", "cross_spectrum", "cross_phase", "isotropize",
+    "DataArray", "fft", "ifft", "dft", "idft", "power_spectrum", "cross_spectrum", "cross_phase", "cross_spectrum_and_phase",
+    "isotropize",
     "isotropic_power_spectrum", "isotropic_cross_spectrum", "fit_loglog", "detrend", "pad", "unpad",
 ]

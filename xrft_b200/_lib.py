@@ -67,6 +67,7 @@ class Spectrum2dDesc(C.Structure):
         ("lut_symmetric", C.c_int),
         ("work", C.c_void_p),
         ("work_bytes", C.c_size_t),
+        ("out2", C.c_void_p),
     ]
 
 

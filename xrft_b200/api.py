@@ -31,7 +31,7 @@ from .dataarray import DataArray, Coordinates, from_any, either_dict_or_kwargs, 
 from . import _lib as L
 
 __all__ = [
-    "fft", "ifft", "dft", "idft", "power_spectrum", "cross_spectrum", "cross_phase", "isotropize",
+    "fft", "ifft", "dft", "idft", "power_spectrum", "cross_spectrum", "cross_phase", "cross_spectrum_and_phase", "isotropize",
     "isotropic_power_spectrum", "isotropic_cross_spectrum", "fit_loglog", "detrend", "pad", "unpad",
 ]
 
@@ -211,7 +211,7 @@ def _is_pow2(n):
 
 
 def _spectral_core(x1, x2, ntrans, mode, *, detrend=None, windows=None, keep_half=False, shift=None, ramps=None,
-                   weight=None, scale=1.0, lut=None, nbins=0):
+                   weight=None, scale=1.0, lut=None, nbins=0, with_phase=False):
     """Transform the last `ntrans` axes of device tensor(s) x1 (,x2) and apply the epilogue.
 
     Picks the fused 2-D real kernel chain when it applies, otherwise composes
@@ -236,6 +236,7 @@ def _spectral_core(x1, x2, ntrans, mode, *, detrend=None, windows=None, keep_hal
         return B.spectrum2d(
             x1, x2, mode, detrend=det, win_y=tt(wins[0]), win_x=tt(wins[1]), keep_half=keep_half, shift_y=shift[0],
             shift_x=shift[1], scale=scale, ramp_y=tt(ramps[0]), ramp_x=tt(ramps[1]), weight_x=tt(weight), lut=lut, nbins=nbins,
+            with_phase=with_phase,
         )
 
     # ---- composed path
@@ -258,6 +259,10 @@ def _spectral_core(x1, x2, ntrans, mode, *, detrend=None, windows=None, keep_hal
                           keep_half=keep_half, shift=shift, ramps=[tt(r) for r in ramps], weight=tt(weight), scale=scale)
     if bins_mode:
         return B.binned_sum(out, lut, nbins, 2)
+    if with_phase:   # composed path: the phase is a second epilogue over the same two transforms
+        ph = B.spectral_post(fs[0], fs[1], L.EPI_PHASE, ntrans, shape[-1], hermitian=is_real, keep_half=keep_half, shift=shift,
+                             ramps=[tt(r) for r in ramps], weight=None, scale=1.0)
+        return out, ph
     return out
 
 
@@ -419,7 +424,8 @@ def _check_out(out, shape, np_dtype):
         raise ValueError("out= must be a C-contiguous host array of shape %s and dtype %s" % (tuple(shape), np.dtype(np_dtype)))
 
 
-def _run_forward(P, das, mode, detrend, window, scale, ramps=None, weight=None, lut=None, nbins=0, out=None, plans=None):
+def _run_forward(P, das, mode, detrend, window, scale, ramps=None, weight=None, lut=None, nbins=0, out=None, plans=None,
+                 with_phase=False):
     """Numerics of fft/power/cross for the prepared plan P on one or two DataArrays (already stacked/transposed).
     Container convention: host (numpy) inputs give a numpy result, device (torch CUDA) inputs a torch CUDA result."""
     torch = _torch()
@@ -444,7 +450,7 @@ def _run_forward(P, das, mode, detrend, window, scale, ramps=None, weight=None, 
         _check_out(out, lead_shape + list(P["N"][:-1]) + [W], (np.complex64 if cplx else np.float32) if f32 else (np.complex128 if cplx else np.float64))
         if not (host_in and trailing):
             raise ValueError("out= is only supported for host inputs whose transform axes are trailing")
-    if (host_in and trailing and nd > ntrans and not any_reversed and mode not in (L.EPI_BINS_POWER, L.EPI_BINS_CROSS)
+    if (host_in and trailing and nd > ntrans and not any_reversed and not with_phase and mode not in (L.EPI_BINS_POWER, L.EPI_BINS_CROSS)
             and das[0].data.dtype in (np.float32, np.float64) and all(d.data.dtype == das[0].data.dtype for d in das)
             and das[0].data.nbytes >= _STREAM_MIN_BYTES and das[0].shape[0] >= 2):
         from . import backend as B
@@ -477,7 +483,10 @@ def _run_forward(P, das, mode, detrend, window, scale, ramps=None, weight=None, 
         raise ValueError("real_dim requires real input data")
     res = _spectral_core(xs[0], xs[1] if len(xs) == 2 else None, ntrans, mode, detrend=detrend, windows=wins,
                          keep_half=real_dim is not None, shift=[P["shift"]] * ntrans if real_dim is None else [False] * ntrans,
-                         ramps=ramps, weight=weight, scale=scale, lut=lut, nbins=nbins)
+                         ramps=ramps, weight=weight, scale=scale, lut=lut, nbins=nbins, with_phase=with_phase)
+    if with_phase:
+        res = tuple(r.permute(*inv) if inv is not None else r for r in res)
+        return tuple(r.cpu().numpy() for r in res) if host_in else res
     if inv is not None and mode not in (L.EPI_BINS_POWER, L.EPI_BINS_CROSS):
         res = res.permute(*inv)
     if host_in:
@@ -699,7 +708,7 @@ def power_spectrum(da, dim=None, real_dim=None, scaling="density", window_correc
     return _label_spectrum(P, out)
 
 
-def _spectrum(da1, da2, mode, dim, real_dim, scaling, window_correction, kwargs, bins=None):
+def _spectrum(da1, da2, mode, dim, real_dim, scaling, window_correction, kwargs, bins=None, with_phase=False):
     kw = dict(kwargs)
     out_buf = kw.pop("out", None)  # extension: preallocated (pinned) host result buffer for streamed host inputs
     detrend_t = kw.pop("detrend", None)
@@ -738,7 +747,7 @@ def _spectrum(da1, da2, mode, dim, real_dim, scaling, window_correction, kwargs,
         weight = _real_dim_weights(n_real, P["N"][-1] // 2 + 1)
     lut, nbins = (None, 0) if bins is None else bins(P)
     out = _run_forward(P, das, mode, detrend_t, window, scale, ramps=ramps, weight=weight, lut=lut, nbins=nbins, out=out_buf,
-                       plans=[P, P2] if da2 is not None else None)
+                       plans=[P, P2] if da2 is not None else None, with_phase=with_phase)
     return P, out
 
 
@@ -763,6 +772,24 @@ def cross_spectrum(da1, da2, dim=None, real_dim=None, scaling="density", window_
     kwargs.update({"true_amplitude": True, "true_phase": true_phase})
     P, out = _spectrum(da1, da2, L.EPI_CROSS, dim, real_dim, scaling, window_correction, kwargs)
     return _label_spectrum(P, out)
+
+
+def cross_spectrum_and_phase(da1, da2, dim=None, real_dim=None, scaling="density", window_correction=False, true_phase=True, **kwargs):
+    """(cross_spectrum(da1, da2, ...), cross_phase(da1, da2, ...)) from ONE pass over the two fields.  The reference computes
+    the phase by running the whole cross-spectrum pipeline a second time (xrft/xrft.py:865-869 calls cross_spectrum, which
+    runs two more fft pipelines); here the angle is a second store of the same epilogue.  Arguments as cross_spectrum."""
+    da1, da2 = from_any(da1), from_any(da2)
+    if "real" in kwargs:
+        real_dim = kwargs.pop("real")
+        warnings.warn(_real_flag_warning, FutureWarning)
+    if "density" in kwargs:
+        scaling = "density" if kwargs.pop("density") else "false_density"
+    kwargs.update({"true_amplitude": True, "true_phase": true_phase})
+    P, (cs, ph) = _spectrum(da1, da2, L.EPI_CROSS, dim, real_dim, scaling, window_correction, kwargs, with_phase=True)
+    cs, cp = _label_spectrum(P, cs), _label_spectrum(P, ph)
+    if da1.name and da2.name:
+        cp.name = "{}_{}_phase".format(da1.name, da2.name)
+    return cs, cp
 
 
 def cross_phase(da1, da2, dim=None, true_phase=True, **kwargs):

@@ -265,6 +265,22 @@ def set_fused_chunk(n: int):
 
 
 
+# points in flight per kernel chain (None = the default policy below); the tools/probe_*.py sweeps set these
+_BINS_CHUNK_POINTS = None   # radial-bin modes
+_CHUNK_POINTS = None        # every other mode
+
+
+def chunk_items(ny: int, nx: int, mode: int) -> int:
+    """Batch items per kernel chain (one launch of each pass): _FUSED_CHUNK items of >= 4096^2 points; smaller grids keep
+    about twice as many points in flight (measured in round 1: 4-12 items of 4096^2 per chain are equivalent)."""
+    if mode in (L.EPI_BINS_POWER, L.EPI_BINS_CROSS):
+        if _BINS_CHUNK_POINTS:
+            return max(1, int(_BINS_CHUNK_POINTS) // (ny * nx))
+    elif _CHUNK_POINTS:
+        return max(1, int(_CHUNK_POINTS) // (ny * nx))
+    return _FUSED_CHUNK if ny * nx >= 4096 * 4096 else max(_FUSED_CHUNK, (2 * _FUSED_CHUNK * 4096 * 4096) // (ny * nx))
+
+
 def _workspace(device, nbytes):
     key = (device.type, device.index)
     w = _WORK.get(key)
@@ -286,8 +302,9 @@ def spectrum2d_supported(ny: int, nx: int, dtype, two_fields: bool) -> bool:
 
 def spectrum2d(x1: torch.Tensor, x2: Optional[torch.Tensor], mode: int, detrend: int = 0, win_y=None, win_x=None,
                keep_half=False, shift_y=False, shift_x=False, scale=1.0, ramp_y=None, ramp_x=None, weight_x=None,
-               lut=None, nbins=0, max_work_bytes: Optional[int] = None) -> torch.Tensor:
-    """Fused detrend + window + 2-D real FFT + epilogue over the last two axes of x1 (and x2)."""
+               lut=None, nbins=0, max_work_bytes: Optional[int] = None, with_phase: bool = False):
+    """Fused detrend + window + 2-D real FFT + epilogue over the last two axes of x1 (and x2).
+    with_phase (mode CROSS only): also return angle(cross spectrum) from the same pass -> (cross, phase)."""
     lib = require_cuda()
     x1 = _dev(x1)
     rdt = x1.dtype
@@ -323,6 +340,9 @@ def spectrum2d(x1: torch.Tensor, x2: Optional[torch.Tensor], mode: int, detrend:
     else:
         odt = cdt if mode in (L.EPI_COMPLEX, L.EPI_CROSS) else rdt
         out = torch.empty(lead + [ny, W], dtype=odt, device=dev)
+    if with_phase and mode != L.EPI_CROSS:
+        raise ValueError("with_phase goes with mode CROSS")
+    out2 = torch.empty(lead + [ny, W], dtype=rdt, device=dev) if with_phase else None
     dt = _REAL[rdt]
     with torch.cuda.device(dev):
         need1 = lib.xrftb_spectrum2d_workspace(dt, ny, nx, 1 if two else 0, 1)
@@ -330,16 +350,14 @@ def spectrum2d(x1: torch.Tensor, x2: Optional[torch.Tensor], mode: int, detrend:
             raise NotImplementedError(f"spectrum2d: unsupported size {ny}x{nx}")
         needall = lib.xrftb_spectrum2d_workspace(dt, ny, nx, 1 if two else 0, batch)
         if max_work_bytes is None:
-            # default: _FUSED_CHUNK items of >= 4096^2 points; smaller grids keep ~the same bytes in flight
-            # measured: 4-12 items of 4096^2 per kernel chain are equivalent, smaller grids prefer ~2x more points in flight
-            items = _FUSED_CHUNK if ny * nx >= 4096 * 4096 else max(_FUSED_CHUNK, (2 * _FUSED_CHUNK * 4096 * 4096) // (ny * nx))
-            max_work_bytes = lib.xrftb_spectrum2d_workspace(dt, ny, nx, 1 if two else 0, items)
+            max_work_bytes = lib.xrftb_spectrum2d_workspace(dt, ny, nx, 1 if two else 0, chunk_items(ny, nx, mode))
         wbytes = max(need1, min(needall, max_work_bytes))
         work = _workspace(dev, wbytes)
         # batch is limited to 65535 items per call by the C-ABI
         flat1 = x1.reshape(batch, ny, nx)
         flat2 = x2.reshape(batch, ny, nx) if x2 is not None else None
         oflat = out.reshape(batch, -1)
+        o2flat = out2.reshape(batch, -1) if out2 is not None else None
         step = 65535
         for b0 in range(0, batch, step):
             nb = min(step, batch - b0)
@@ -360,8 +378,9 @@ def spectrum2d(x1: torch.Tensor, x2: Optional[torch.Tensor], mode: int, detrend:
             else:
                 d.out, d.lut, d.bins, d.nbins = oflat[b0:].data_ptr(), None, None, 0
             d.work, d.work_bytes = work.data_ptr(), work.numel()
+            d.out2 = o2flat[b0:].data_ptr() if o2flat is not None else None
             rc = lib.xrftb_spectrum2d(C.byref(d), _stream())
             L.check(rc, "xrftb_spectrum2d")
     if mode == L.EPI_BINS_CROSS:
         return torch.view_as_complex(out)
-    return out
+    return (out, out2) if with_phase else out

@@ -1180,13 +1180,14 @@ static int spectrum2d_colsfirst(const xrftb_spectrum2d_desc& q, int ly, int lx, 
     return 0;
 }
 
-// EXPERIMENTAL (XRFTB_CROSS_Z=1, off by default; not yet run on hardware -- see rowszx_kernel): the z-mode chain for the
-// cross spectrum / cross phase of two real fields.  Pass 1 (the config-2 kernel, unchanged) runs once per field and leaves
-// Z1, Z2; the completion tables are built per field; one two-field pass 2 combines them.  Per item the workspace holds two
+// The z-mode chain for the cross spectrum / cross phase of two real fields (config 3).  Pass 1 (the config-2 kernel,
+// unchanged) runs once per field and leaves Z1, Z2; the completion tables are built per field; one two-field pass 2
+// combines them (and writes the phase next to the cross spectrum when desc.out2 is set).  Per item the workspace holds two
 // Z arrays and two sets of column-line tables; the chunk adapts to the workspace the caller sized for the rows-first chain.
+// XRFTB_CROSS_Z=0 selects the rows-first two-field chain (A/B switch).
 static bool crossz_enabled() {
     static int on = -1;
-    if (on < 0) { const char* e = getenv("XRFTB_CROSS_Z"); on = e ? atoi(e) : 0; }
+    if (on < 0) { const char* e = getenv("XRFTB_CROSS_Z"); on = e ? atoi(e) : 1; }
     return on != 0;
 }
 template <typename T> static bool crossz_eligible(const xrftb_spectrum2d_desc& q, int ly, int lx) {
@@ -1267,10 +1268,11 @@ static int spectrum2d_crossz(const xrftb_spectrum2d_desc& q, int ly, int lx, cud
                 if (int rc = check_launch("rowline_fix_kernel")) return rc;
             }
         }
-        RowsZCross<T> io{zf[0], zf[1], reinterpret_cast<char*>(q.out) + (size_t)b0 * item * out_elem, ly, H, q.shift_y, q.shift_x, (T)q.scale,
+        RowsZCross<T> io{zf[0], zf[1], reinterpret_cast<char*>(q.out) + (size_t)b0 * item * out_elem,
+                         q.out2 ? reinterpret_cast<char*>(q.out2) + (size_t)b0 * item * sizeof(T) : nullptr, ly, H, q.shift_y, q.shift_x, (T)q.scale,
                          ag[0], ag[1], wj, nullptr};
         ProfScope ps_(PROF_ROWS, st);
-        if (int rc = rows_z_cross<T>(io, lx - 1, nb * H, q.mode, st)) return rc;
+        if (int rc = rows_z_cross<T>(io, lx - 1, nb * H, (q.mode == XRFTB_EPI_CROSS && q.out2) ? (int)EPI_CROSS_AND_PHASE : q.mode, st)) return rc;
     }
     return 0;
 }
@@ -1283,9 +1285,16 @@ static int spectrum2d_impl(const xrftb_spectrum2d_desc& q, cudaStream_t st) {
     const bool two = (q.mode == XRFTB_EPI_CROSS || q.mode == XRFTB_EPI_PHASE || q.mode == XRFTB_EPI_BINS_CROSS);
     if (two && !q.in2) { set_error("spectrum2d: mode %d needs in2", q.mode); return XRFTB_EINVAL; }
     if (colsfirst_enabled() && colsfirst_eligible<T>(q.mode, q.keep_half, q.weight_x, ly, lx, q.nx)) { g_last_path.store(1); return spectrum2d_colsfirst<T>(q, ly, lx, st); }
-    if (crossz_enabled() && crossz_eligible<T>(q, ly, lx)) {   // experimental, off by default
+    if (crossz_enabled() && crossz_eligible<T>(q, ly, lx)) {
         const int rc = spectrum2d_crossz<T>(q, ly, lx, st);
         if (rc != XRFTB_EWORKSPACE) { g_last_path.store(3); return rc; }
+    }
+    if (q.mode == XRFTB_EPI_CROSS && q.out2) {   // no fused chain for this shape: cross spectrum, then its phase
+        xrftb_spectrum2d_desc a = q, b = q;
+        a.out2 = nullptr;
+        if (int rc = spectrum2d_impl<T>(a, st)) return rc;
+        b.mode = XRFTB_EPI_PHASE; b.out = q.out2; b.out2 = nullptr;
+        return spectrum2d_impl<T>(b, st);
     }
     g_last_path.store(0);
     const int C = cols_tile_width<T>(ly, two);
@@ -1417,7 +1426,7 @@ static int spectrum2d_impl(const xrftb_spectrum2d_desc& q, cudaStream_t st) {
         static int tma_on = -1;
         if (tma_on < 0) { const char* e = getenv("XRFTB_TMA_STORE"); tma_on = e ? atoi(e) : 1; }
         if (tma_on && q.mode == XRFTB_EPI_POWER && std::is_same<T, float>::value && C >= 8 /* >= 32-byte rows: 16-byte boxes measured slower than LSU stores */ && (mirror_pass || q.keep_half) && !q.weight_x
-            && (W * sizeof(float)) % 16 == 0 && q.ny >= 4) {
+            && (W * sizeof(float)) % 16 == 0 && q.ny >= 4 && q.nx / 2 >= C /* the Nyquist column starts its own tile: no box wraps around the fftshift */) {
             const int box_rows = q.ny / 2 < 256 ? q.ny / 2 : 256;
             if (encode_out_tmap(&tmap, d.out, nb * q.ny, W, C, box_rows)) { d.use_tma = 1; d.tma_box_rows = box_rows; ptm = &tmap; }
         }
@@ -1635,6 +1644,7 @@ int xrftb_spectrum2d(const xrftb_spectrum2d_desc* q, void* stream) {
     const bool bins_mode = (q->mode == XRFTB_EPI_BINS_POWER || q->mode == XRFTB_EPI_BINS_CROSS);
     if (bins_mode && (!q->lut || !q->bins || q->nbins < 1)) { set_error("spectrum2d: bins mode needs lut/bins/nbins"); return XRFTB_EINVAL; }
     if (!bins_mode && !q->out) { set_error("spectrum2d: out is NULL"); return XRFTB_EINVAL; }
+    if (q->out2 && q->mode != XRFTB_EPI_CROSS) { set_error("spectrum2d: out2 (phase) goes with mode CROSS only"); return XRFTB_EINVAL; }
     if (q->dtype != XRFTB_F32 && q->dtype != XRFTB_F64) { set_error("spectrum2d: bad dtype %d", q->dtype); return XRFTB_EINVAL; }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     // the per-call tables (moments region of the workspace, grid.y of the reductions) are sized for 65535 items: longer
@@ -1652,6 +1662,7 @@ int xrftb_spectrum2d(const xrftb_spectrum2d_desc* q, void* stream) {
         d.in1 = reinterpret_cast<const char*>(q->in1) + (size_t)b0 * in_item;
         if (q->in2) d.in2 = reinterpret_cast<const char*>(q->in2) + (size_t)b0 * in_item;
         if (q->out) d.out = reinterpret_cast<char*>(q->out) + (size_t)b0 * out_item;
+        if (q->out2) d.out2 = reinterpret_cast<char*>(q->out2) + (size_t)b0 * (size_t)q->ny * W * esz;
         if (q->bins) d.bins = q->bins + (size_t)b0 * bins_item;
         const int rc = q->dtype == XRFTB_F32 ? spectrum2d_impl<float>(d, st) : spectrum2d_impl<double>(d, st);
         if (rc) return rc;

@@ -85,6 +85,14 @@ static int cols_fused_k(const cplx<T>* in1, const cplx<T>* in2, long ntiles_tota
         io.hist_off = IO::template hist_offset_bytes<K, cmin(TypeCfg<T>::LOGE, K), C, 1>();
         if (tmap) io.tmap = *tmap;
         const size_t extra = IO::kBins ? (size_t)d.nbins * (IO::kCplxStage ? 2 : 1) * sizeof(double) : 0;
+        // isotropic power spectrum, the usual case (radial bins: symmetric LUT, <= 255 bins, full-width counting, no one-sided
+        // weights): the kernel that keeps each thread's bin indices in registers
+        if constexpr (sizeof(T) == 4 && MODE == EPI_BINS_POWER && (K > TypeCfg<T>::LOGE) && C >= 4 && C % 4 == 0) {
+            if (d.lut_symmetric && d.full && !d.weight_x && d.nbins <= 255 && bins_static_enabled()) {
+                const int rc = launch_cols_bins<K, C>(io, ntiles_total, st);
+                if (rc <= 0) return rc;
+            }
+        }
         // real-valued single-field epilogues of the float32 path: bulk-copy fed variant (the staging buffer fits the
         // half-size exchange buffer).  XRFTB_COLS_ASYNC=0 selects the register-prefetch kernel.
         if constexpr (sizeof(T) == 4 && (MODE == EPI_POWER || MODE == EPI_BINS_POWER) && (K > TypeCfg<T>::LOGE) && C >= 2 && C % 2 == 0) {

