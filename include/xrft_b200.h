@@ -59,9 +59,22 @@ long xrftb_launch_count(int reset);
  * summed milliseconds and launch counts for {moments, row pass, column pass, mirror fill}. */
 int xrftb_profile_begin(void);
 int xrftb_profile_end(double ms[4], long counts[4]);
-/* which kernel chain the last xrftb_spectrum2d call took: 0 = rows first (moments | row R2C | column pass | Hermitian
+/* Chain-selection options (process-wide; every value selects a kernel chain that is also the regular path of some shape or
+ * dtype, and tests/test_gpu_variants.py runs each of them against the reference formulas):
+ *   "cols_first"  1  columns-first chain for the full-width power spectrum and the radial bins (0: rows first + mirror pass)
+ *   "zpack"       1  pass 1 leaves packed column spectra ("z mode") where pass 2 supports it
+ *   "ztma"        1  TMA tensor stores of the packed column spectra
+ *   "cols_async"  2  TMA-fed column kernels: 0 never, 1 always, 2 where measured faster
+ *   "rowline"     1  float32 detrend as exact per-line subtraction + rank-2 completion (0: moments pass + fp64 plane)
+ *   "cross_z"     1  two-field z-mode chain for cross spectrum / phase (0: rows-first two-field chain)
+ *   "bins_static" 1  radial-bin kernels with a static cell-to-bin mapping (0: generic LUT epilogue)
+ * The environment variable XRFTB_<NAME> (upper case) only supplies the value an option starts with. */
+int xrftb_set_option(const char* name, int value);
+int xrftb_get_option(const char* name, int* value);
+/* which kernel chain the last xrftb_spectrum2d call OF THE CALLING THREAD took: 0 = rows first (moments | row R2C | column pass | Hermitian
  * mirror), 1 = columns first (column R2C with column-line detrend | completion tables | row C2C + epilogue, no mirror pass),
- * 2 = columns first in "z mode" (pass 1 leaves the packed column spectra, pass 2 separates the real columns in its loads).
+ * 2 = columns first in "z mode" (pass 1 leaves the packed column spectra, pass 2 separates the real columns in its loads),
+ * 3 = the two-field z-mode chain (cross spectrum / phase).
  * In chains 1 and 2 the profile classes read {completion tables, row pass = pass 2, column pass = pass 1, unused}. */
 int xrftb_spectrum2d_last_path(void);
 

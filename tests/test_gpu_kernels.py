@@ -174,3 +174,38 @@ def test_long_strided_16384(dt):
     xr = rng.standard_normal((16384, 64)).astype(dt)
     yr = B.rfftn(torch.from_numpy(xr).cuda(), axes=[0, 1]).cpu().numpy()
     assert relerr(yr, np.fft.rfftn(xr.astype(np.float64))) < (5e-5 if dt == np.float32 else 1e-11)
+
+
+@pytest.mark.gpu
+def test_fft_module_matches_numpy_fft_at_the_reference_call_sites():
+    """backend.fft_module() driven exactly like xrft/xrft.py:398-404, 439-447 (forward) and :586-591, 612-621 (inverse)
+    drives the object `_fft_module` returns: numpy in, numpy out, numpy.fft semantics."""
+    import numpy as np
+    from xrft_b200.backend import fft_module
+    fftm = fft_module()
+    rng = np.random.default_rng(3)
+    for shape, axis_num in (((6, 32, 64), [1, 2]), ((20, 30), [0, 1]), ((5, 16, 8), [0]), ((4, 15, 19), [2, 1])):
+        a = rng.standard_normal(shape)
+        # forward: fftn(ifftshift(a, axes), axes) then fftshift   (xrft.py:439-447)
+        f = fftm.fftshift(fftm.fftn(fftm.ifftshift(a, axes=axis_num), axes=axis_num), axes=axis_num)
+        ref = np.fft.fftshift(np.fft.fftn(np.fft.ifftshift(a, axes=axis_num), axes=axis_num), axes=axis_num)
+        assert isinstance(f, np.ndarray) and f.dtype == np.complex128
+        np.testing.assert_allclose(f, ref, rtol=1e-9, atol=1e-9 * np.abs(ref).max())
+        # real transform over the last listed axis, no shift on it   (xrft.py:398-404)
+        fr = fftm.rfftn(a, axes=axis_num)
+        np.testing.assert_allclose(fr, np.fft.rfftn(a, axes=axis_num), rtol=1e-9, atol=1e-9 * np.abs(ref).max())
+        # inverse   (xrft.py:586-591, 612-621)
+        b = fftm.ifftshift(fftm.ifftn(fftm.ifftshift(f, axes=axis_num), axes=axis_num), axes=axis_num)
+        refb = np.fft.ifftshift(np.fft.ifftn(np.fft.ifftshift(ref, axes=axis_num), axes=axis_num), axes=axis_num)
+        np.testing.assert_allclose(b, refb, rtol=1e-9, atol=1e-9)
+        if shape[axis_num[-1]] % 2 == 0:
+            br = fftm.irfftn(fr, axes=axis_num)
+            np.testing.assert_allclose(br, np.fft.irfftn(np.fft.rfftn(a, axes=axis_num), axes=axis_num), rtol=1e-9, atol=1e-9)
+            np.testing.assert_allclose(br, a, rtol=1e-9, atol=1e-9)
+    a32 = rng.standard_normal((3, 64, 128)).astype(np.float32)
+    f32 = fftm.fftn(a32, axes=[1, 2])
+    assert f32.dtype == np.complex64
+    np.testing.assert_allclose(f32, np.fft.fftn(a32.astype(np.float64), axes=[1, 2]), rtol=1e-4, atol=1e-4 * 128)
+    with pytest.raises(NotImplementedError):
+        fftm.fftn(a32, s=(8, 8))
+    np.testing.assert_array_equal(fftm.fftfreq(8, 0.5), np.fft.fftfreq(8, 0.5))

@@ -19,6 +19,8 @@ EXPORTS = [
     "xrftb_launch_count",
     "xrftb_profile_begin",
     "xrftb_profile_end",
+    "xrftb_set_option",
+    "xrftb_get_option",
     "xrftb_spectrum2d_last_path",
     "xrftb_fftn_workspace",
     "xrftb_fftn",
@@ -109,6 +111,10 @@ def load():
     lib.xrftb_spectrum2d_workspace.restype = C.c_size_t
     lib.xrftb_spectrum2d_workspace.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64]
     lib.xrftb_spectrum2d.argtypes = [C.POINTER(Spectrum2dDesc), vp]
+    lib.xrftb_set_option.argtypes = [C.c_char_p, C.c_int]
+    lib.xrftb_set_option.restype = C.c_int
+    lib.xrftb_get_option.argtypes = [C.c_char_p, ip]
+    lib.xrftb_get_option.restype = C.c_int
     lib.xrftb_comm_unique_id.argtypes = [vp]
     lib.xrftb_comm_init.argtypes = [C.POINTER(vp), C.c_int, C.c_int, vp]
     lib.xrftb_comm_destroy.argtypes = [vp]
@@ -121,6 +127,17 @@ def load():
         getattr(lib, name).restype = C.c_int
     _lib = lib
     return lib
+
+
+def set_option(name: str, value: int):
+    """xrftb_set_option: choose a kernel chain explicitly (see include/xrft_b200.h for the names)"""
+    check(load().xrftb_set_option(name.encode(), int(value)), "xrftb_set_option")
+
+
+def get_option(name: str) -> int:
+    v = C.c_int(0)
+    check(load().xrftb_get_option(name.encode(), C.byref(v)), "xrftb_get_option")
+    return v.value
 
 
 def check(rc: int, what: str):

@@ -384,3 +384,122 @@ def spectrum2d(x1: torch.Tensor, x2: Optional[torch.Tensor], mode: int, detrend:
     if mode == L.EPI_BINS_CROSS:
         return torch.view_as_complex(out)
     return (out, out2) if with_phase else out
+
+
+# ---------------------------------------------------------------------------------------------
+# the numpy.fft-shaped module object of the reference's seam (S1)
+# ---------------------------------------------------------------------------------------------
+class FFTModule:
+    """Drop-in for the object `_fft_module(da)` returns in the reference (xrft/xrft.py:32-36): exposes exactly the
+    functions the reference calls on it -- fftn / rfftn (xrft.py:398-404, 439-447), ifftn / irfftn (:586-591, 612-621),
+    fftshift / ifftshift (:439-447, :612-621) -- with numpy.fft's signatures and semantics (forward unnormalised,
+    inverse 1/N, rfftn over the LAST listed axis, irfftn output length 2 (m - 1)).  numpy arrays in give numpy arrays out
+    (what the reference's call sites expect); CUDA torch tensors in give CUDA torch tensors out.  Every function runs
+    the CUDA kernels of the C-ABI: there is no CPU fallback."""
+
+    @staticmethod
+    def _in(a):
+        import numpy as np
+        if isinstance(a, torch.Tensor):
+            if not a.is_cuda:
+                raise L.XrftbError("FFTModule expects numpy arrays or CUDA tensors")
+            return a, False
+        a = np.asarray(a)
+        if a.dtype.kind in "iub":
+            a = a.astype(np.float64)
+        elif a.dtype == np.float16:
+            a = a.astype(np.float32)
+        require_cuda()
+        return torch.from_numpy(np.ascontiguousarray(a)).cuda(), True
+
+    @staticmethod
+    def _out(t, to_numpy):
+        return t.cpu().numpy() if to_numpy else t
+
+    @staticmethod
+    def _check(s, norm):
+        if s is not None or norm not in (None, "backward"):
+            raise NotImplementedError("FFTModule: `s` and `norm` are not supported (the reference never passes them)")
+
+    def _move_last(self, t, axes):
+        """numpy transforms the LAST listed axis as the real one; the C-ABI wants it to be the last array axis"""
+        axes = _norm_axes(t.ndim, axes)
+        if axes[-1] == t.ndim - 1:
+            return t, axes, None
+        perm = [d for d in range(t.ndim) if d != axes[-1]] + [axes[-1]]
+        inv = [perm.index(d) for d in range(t.ndim)]
+        return t.permute(*perm).contiguous(), [perm.index(a) for a in axes], inv
+
+    def fftn(self, a, s=None, axes=None, norm=None):
+        self._check(s, norm)
+        t, np_out = self._in(a)
+        return self._out(fftn(t, axes), np_out)
+
+    def ifftn(self, a, s=None, axes=None, norm=None):
+        self._check(s, norm)
+        t, np_out = self._in(a)
+        return self._out(ifftn(t, axes), np_out)
+
+    def rfftn(self, a, s=None, axes=None, norm=None):
+        self._check(s, norm)
+        t, np_out = self._in(a)
+        if t.is_complex():
+            raise TypeError("rfftn expects real input")
+        t, ax, inv = self._move_last(t, axes)
+        f = rfftn(t, ax)
+        return self._out(f.permute(*inv) if inv is not None else f, np_out)
+
+    def irfftn(self, a, s=None, axes=None, norm=None):
+        self._check(s, norm)
+        t, np_out = self._in(a)
+        t, ax, inv = self._move_last(t, axes)
+        f = irfftn(t, ax)
+        return self._out(f.permute(*inv) if inv is not None else f, np_out)
+
+    def _shift(self, a, axes, inverse):
+        t, np_out = self._in(a)
+        axes = _norm_axes(t.ndim, range(t.ndim) if axes is None else ([axes] if isinstance(axes, int) else axes))
+        lib = require_cuda()
+        t = _dev(t)
+        is_c = t.dtype in _CPLX
+        dt = _CPLX[t.dtype] if is_c else _REAL[t.dtype]
+        for ax in axes:     # one roll kernel per axis on the [A][n][B] view: no permutes
+            n = t.shape[ax]
+            sh = (n - n // 2) if inverse else n // 2
+            if n < 2 or sh % n == 0:
+                continue
+            A = 1
+            for d in t.shape[:ax]:
+                A *= d
+            Bc = t.numel() // (A * n)
+            out = torch.empty_like(t)
+            with torch.cuda.device(t.device):
+                rc = lib.xrftb_roll_scale(_ptr(t), _ptr(out), dt, 1 if is_c else 0, A, 1, n, Bc, 0, sh, 0, 1.0, _stream())
+            L.check(rc, "xrftb_roll_scale")
+            t = out
+        return self._out(t, np_out)
+
+    def fftshift(self, x, axes=None):
+        return self._shift(x, axes, False)
+
+    def ifftshift(self, x, axes=None):
+        return self._shift(x, axes, True)
+
+    # frequency tables are O(N) host vectors in the reference too (xrft.py:139-175)
+    @staticmethod
+    def fftfreq(n, d=1.0):
+        import numpy as np
+        return np.fft.fftfreq(n, d)
+
+    @staticmethod
+    def rfftfreq(n, d=1.0):
+        import numpy as np
+        return np.fft.rfftfreq(n, d)
+
+
+_FFT_MODULE = FFTModule()
+
+
+def fft_module() -> FFTModule:
+    """The object to return from the reference's `_fft_module`: `xrft.xrft._fft_module = lambda da: fft_module()`."""
+    return _FFT_MODULE

@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdlib>
 #include <cstdio>
+#include <cstring>
 #include <cmath>
 #include <map>
 #include <mutex>
@@ -32,6 +33,39 @@ int check_launch(const char* what) {
     if (e != cudaSuccess) { set_error("%s launch failed: %s", what, cudaGetErrorString(e)); return XRFTB_ECUDA; }
     return 0;
 }
+// ------------------------------------------------------------------------------------------------
+// chain-selection options: process-wide, set explicitly through xrftb_set_option (the environment variable XRFTB_<NAME> in
+// upper case only provides the value an option starts with)
+// ------------------------------------------------------------------------------------------------
+struct OptionDef { const char* name; int def; const char* env; };
+static const OptionDef kOptions[OPT_COUNT] = {
+    {"cols_first", 1, "XRFTB_COLS_FIRST"},   // 1: columns-first chain for the full-width power spectrum / radial bins; 0: rows first
+    {"zpack", 1, "XRFTB_ZPACK"},             // 1: pass 1 leaves packed column spectra (z mode) where pass 2 supports it
+    {"ztma", 1, "XRFTB_ZTMA"},               // 1: TMA tensor stores of the packed column spectra (rows >= 32 bytes)
+    {"cols_async", 2, "XRFTB_COLS_ASYNC"},   // column kernels fed by TMA: 0 never, 1 always, 2 where measured faster
+    {"rowline", 1, "XRFTB_ROWLINE"},         // 1: per-line exact detrend + rank-2 completion (float32); 0: moments pass + plane subtract
+    {"cross_z", 1, "XRFTB_CROSS_Z"},         // 1: two-field z-mode chain for cross spectrum / phase; 0: rows-first two-field chain
+    {"bins_static", 1, "XRFTB_BINS_STATIC"}, // 1: radial-bin kernels with a static cell-to-bin mapping; 0: generic LUT epilogue
+};
+static std::atomic<int> g_opt[OPT_COUNT];
+static std::once_flag g_opt_once;
+static void options_init() {
+    for (int i = 0; i < OPT_COUNT; ++i) {
+        const char* e = getenv(kOptions[i].env);
+        g_opt[i].store(e ? atoi(e) : kOptions[i].def);
+    }
+}
+int option(Option o) {
+    std::call_once(g_opt_once, options_init);
+    return g_opt[o].load(std::memory_order_relaxed);
+}
+static int option_index(const char* name) {
+    if (!name) return -1;
+    for (int i = 0; i < OPT_COUNT; ++i)
+        if (strcmp(name, kOptions[i].name) == 0) return i;
+    return -1;
+}
+
 int sm_count() {
     static thread_local int cached_dev = -1, cached = 0;
     int dev = 0;
@@ -192,45 +226,6 @@ __global__ void __launch_bounds__(512) moments_kernel(const T* __restrict__ in, 
         atomicAdd(mom + b * 4 + threadIdx.x, x);
     }
     __syncthreads();
-    }
-}
-
-// light variant for the side stream: one 128-thread CTA per SM at <= 32 registers so it fits beside the hot FFT
-// kernels (which leave 4 K registers per SM free); float32 rows whose length is a power of two >= 4
-__global__ void __maxnreg__(32) moments_side_kernel(const float* __restrict__ in, double* __restrict__ mom, int log_n4, int log_ny, long nitems) {
-    const long per_item4 = 1L << (log_n4 + log_ny);
-    const long n4 = 1L << log_n4, ny = 1L << log_ny;
-    const double c1m = 0.5 * (double)(ny - 1), c2m = 0.5 * (double)(4 * n4 - 1);
-    const float4* p4 = reinterpret_cast<const float4*>(in);
-    // CTA -> (item, slab of the item); slabs = gridDim.x / nitems rounded down to >= 1
-    const long slabs = gridDim.x >= nitems ? gridDim.x / nitems : 1;
-    for (long w = blockIdx.x; w < nitems * slabs; w += gridDim.x) {
-        const long b = w / slabs, sl = w - b * slabs;
-        const long lo = per_item4 * sl / slabs, hi = per_item4 * (sl + 1) / slabs;
-        double S = 0, Sy = 0, Sx = 0;
-        for (long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-            const float4 x = __ldg(p4 + b * per_item4 + i);
-            const long r = i >> log_n4, c4 = i & (n4 - 1);
-            const float c = (float)((double)(4 * c4) - c2m);
-            const double s4 = (double)((x.x + x.y) + (x.z + x.w));
-            S += s4;
-            Sy += ((double)r - c1m) * s4;
-            Sx += (double)((c * x.x + (c + 1.f) * x.y) + ((c + 2.f) * x.z + (c + 3.f) * x.w));
-        }
-        __shared__ double red[3][4];
-        double vals[3] = {S, Sy, Sx};
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            double x = vals[k];
-            for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
-            if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = x;
-        }
-        __syncthreads();
-        if (threadIdx.x < 3) {
-            double x = red[threadIdx.x][0] + red[threadIdx.x][1] + red[threadIdx.x][2] + red[threadIdx.x][3];
-            atomicAdd(mom + b * 4 + (threadIdx.x == 0 ? 0 : threadIdx.x + 1), x);   // {S, -, Sy, Sx}
-        }
-        __syncthreads();
     }
 }
 
@@ -1033,29 +1028,25 @@ template <typename T> static size_t rowline_fixed_bytes(int nx, int C) {
     const size_t ncols = (size_t)((nx / 2) / C + 1) * C;
     return align256(ncols * 2 * sizeof(cplx<T>)) + align256((size_t)2 * nx * sizeof(double)) + align256((size_t)2 * (nx / 2 + 1) * sizeof(double2));
 }
-static bool rowline_enabled() {
-    static int on = -1;
-    if (on < 0) { const char* e = getenv("XRFTB_ROWLINE"); on = e ? atoi(e) : 1; }
-    return on != 0;
-}
+static bool rowline_enabled() { return option(OPT_ROWLINE) != 0; }
 
 // "columns first" order (see ColsR2CPack / RowsC2CPower): eligible for the full-width power spectrum
-static std::atomic<int> g_last_path{0};   // 0: rows first (+ Hermitian mirror pass), 1: columns first, 2: columns first, packed column spectra (z mode)
-static bool colsfirst_enabled() {
-    static int on = -1;
-    if (on < 0) { const char* e = getenv("XRFTB_COLS_FIRST"); on = e ? atoi(e) : 1; }
-    return on != 0;
-}
-// experiment: start delay (ns) of the second-wave CTAs of pass 1 (which = 0, XRFTB_STAGGER1_NS) / pass 2 (which = 1, XRFTB_STAGGER2_NS)
-static int stagger_knob(int which) {
-    static int v[2] = {-1, -1};
-    if (v[which] < 0) { const char* e = getenv(which ? "XRFTB_STAGGER2_NS" : "XRFTB_STAGGER1_NS"); v[which] = e ? atoi(e) : 0; }
-    return v[which];
-}
-template <typename T> static bool colsfirst_eligible(int mode, int keep_half, const void* weight_x, int ly, int lx, int nx) {
-    if (mode != XRFTB_EPI_POWER || keep_half || weight_x) return false;
+// chain taken by this thread's last xrftb_spectrum2d call: 0 rows first (+ Hermitian mirror pass), 1 columns first, 2 columns
+// first with packed column spectra (z mode), 3 two-field z mode
+struct LastPath { int v = 0; void store(int x) { v = x; } int load() const { return v; } };
+static thread_local LastPath g_last_path;
+static bool colsfirst_enabled() { return option(OPT_COLS_FIRST) != 0; }
+template <typename T> static bool colsfirst_eligible(const xrftb_spectrum2d_desc& q, int ly, int lx) {
+    if (q.keep_half || q.weight_x) return false;
+    if (q.mode == XRFTB_EPI_BINS_POWER) {
+        // radial bins in pass 2 (rows_bins_kernel): float32, symmetric LUT (radial bins), shapes with a static row mapping
+        if (!std::is_same<T, float>::value || !q.lut_symmetric || !bins_static_enabled()) return false;
+        if (!rows_bins_shape_ok(lx, q.ny) || q.nbins > q.nx || q.nbins > 4096) return false;
+    } else if (q.mode != XRFTB_EPI_POWER) {
+        return false;
+    }
     const int C = colsfirst_tile_width<T>(ly);
-    return C >= 1 && ly >= 1 && ly <= TypeCfg<T>::MAX_COLS_LOG2 && lx >= 1 && lx <= TypeCfg<T>::MAX_ROWS_LOG2 && nx >= 2 * C;
+    return C >= 1 && ly >= 1 && ly <= TypeCfg<T>::MAX_COLS_LOG2 && lx >= 1 && lx <= TypeCfg<T>::MAX_ROWS_LOG2 && q.nx >= 2 * C;
 }
 template <typename T> static size_t colsfirst_item_bytes(int ny, int nx) { return (size_t)(ny / 2 + 1) * nx * sizeof(cplx<T>); }
 
@@ -1069,9 +1060,7 @@ template <typename T> static size_t colline_fixed_bytes(int ny) {
 template <typename T>
 static int spectrum2d_colsfirst(const xrftb_spectrum2d_desc& q, int ly, int lx, cudaStream_t st) {
     using C_ = cplx<T>;
-    int C = colsfirst_tile_width<T>(ly);
-    // half-width tiles exist only for the tensor-map fed kernel (16-byte aligned rows, cuTensorMapEncodeTiled available)
-    if (C != cols_tile_width<T>(ly, false) && (q.nx * sizeof(T)) % 16 != 0) C = cols_tile_width<T>(ly, false);
+    const int C = colsfirst_tile_width<T>(ly);
     const int H = q.ny / 2 + 1;
     // column-line detrend (no moments pass): float32 with two packed columns per thread, ny long enough for the fp64 table transform
     const bool colline = std::is_same<T, float>::value && q.detrend && rowline_enabled() && C >= 2 && ly >= 3;
@@ -1125,30 +1114,21 @@ static int spectrum2d_colsfirst(const xrftb_spectrum2d_desc& q, int ly, int lx, 
             ColsR2CPack<T> io{in + b0 * item, q.nx, tiles_per_item, q.detrend, mom + b0 * 4,
                               reinterpret_cast<const T*>(q.win_y), reinterpret_cast<const T*>(q.win_x), interm, colstats, 0, {}};
             // tensor-map fed (asynchronous) variant: float32, >= 2 exchange stages, 16-byte aligned rows
-            static int async_on = -1;
-            if (async_on < 0) { const char* e = getenv("XRFTB_COLS_ASYNC"); async_on = e ? atoi(e) : 2; }
+            const int async_on = option(OPT_COLS_ASYNC);
             bool use_async = false;
-            io.stagger_ns = stagger_knob(0);
-            {   // waves of row runs pulled into L2 ahead of the tile loads (XRFTB_P1_PREFETCH, 0 = off)
-                static int pf = -1;
-                if (pf < 0) { const char* e = getenv("XRFTB_P1_PREFETCH"); pf = e ? atoi(e) : 0; }
-                io.pf_waves = pf;
-            }
             if (async_on && std::is_same<T, float>::value && ly > TypeCfg<T>::LOGE && C >= 2 && (q.nx * sizeof(T)) % 16 == 0) {
                 const int box_rows = q.ny < 256 ? q.ny : 256;
                 if (encode_out_tmap(&io.tmap, const_cast<T*>(in + b0 * item), nb * q.ny, q.nx, 2 * C, box_rows)) { io.box_rows = box_rows; use_async = true; }
             }
             // "z" mode: pass 1 stores the packed column spectra, pass 2 separates the real columns in its loads (RowsZPower)
-            static int zpack_on = -1;
-            if (zpack_on < 0) { const char* e = getenv("XRFTB_ZPACK"); zpack_on = e ? atoi(e) : 1; }
+            const int zpack_on = option(OPT_ZPACK);
             // tiles of >= 4 packed columns only: with 2 the rows of Z are 16 bytes (half sectors: measured 2.7x slower stores)
-            zmode = use_async && zpack_on && rows_z_supported(lx - 1) && C >= 4;
+            zmode = use_async && zpack_on && rows_z_supported(lx - 1) && C >= 4 && q.mode == XRFTB_EPI_POWER;
             io.zout = zmode ? interm : nullptr;
             if (zmode) g_last_path.store(2);
             io.ztma = 0;
             if (zmode && C * sizeof(C_) >= 32 && q.ny >= 512) {   // tensor stores of Z (XRFTB_ZTMA=0: 16-byte stores from registers)
-                static int ztma_on = -1;
-                if (ztma_on < 0) { const char* e = getenv("XRFTB_ZTMA"); ztma_on = e ? atoi(e) : 1; }
+                const int ztma_on = option(OPT_ZTMA);
                 const int zbox = q.ny / 4 < 256 ? q.ny / 4 : 256;
                 if (ztma_on && encode_out_tmap(&io.ztmap, interm, nb * q.ny, q.nx, 2 * C, zbox)) { io.ztma = 1; io.zbox_rows = zbox; }
             }
@@ -1161,18 +1141,21 @@ static int spectrum2d_colsfirst(const xrftb_spectrum2d_desc& q, int ly, int lx, 
             rowline_fix_kernel<T><<<dim3((unsigned)nb, (unsigned)((q.nx + 1023) / 1024)), 256, 0, st>>>(colstats, ag, reinterpret_cast<const T*>(q.win_x), q.nx, q.ny, q.detrend);
             if (int rc = check_launch("rowline_fix_kernel")) return rc;
         }
-        if (zmode) {
-            RowsZPower<T> io{interm, reinterpret_cast<T*>(q.out) + b0 * item, ly, H, q.shift_y, q.shift_x, (T)q.scale, colline ? ag : nullptr, wj, nullptr, 0};
-            {   // XRFTB_P2_BULK=1: rows staged in shared memory and written by bulk copies (measured 8 % slower than the
-                // 4-byte stores from registers: the staging barriers cost more than the stores)
-                static int bulk_on = -1;
-                if (bulk_on < 0) { const char* e = getenv("XRFTB_P2_BULK"); bulk_on = e ? atoi(e) : 0; }
-                io.bulk = bulk_on;
+        if (q.mode == XRFTB_EPI_BINS_POWER) {
+            // rows ky in [0, Ny/2) of every plane, then the Nyquist row: |F|^2 goes straight into the planes' radial bins
+            if constexpr (std::is_same<T, float>::value) {
+                RowsBins io{{interm, nullptr, ly, H, q.shift_y, q.shift_x, (T)q.scale, colline ? ag : nullptr, wj}, q.lut, q.bins + b0 * q.nbins, q.nbins, 0, q.ny / 2, nb};
+                ProfScope ps_(PROF_ROWS, st);
+                if (int rc = rows_bins(io, lx, st)) { if (rc > 0) set_error("spectrum2d: radial-bin pass does not cover %d x %d", q.ny, q.nx); return rc > 0 ? XRFTB_EUNSUPPORTED : rc; }
+                io.ky0 = q.ny / 2; io.rows = 1;
+                if (int rc = rows_bins(io, lx, st)) { if (rc > 0) set_error("spectrum2d: radial-bin pass does not cover %d x %d", q.ny, q.nx); return rc > 0 ? XRFTB_EUNSUPPORTED : rc; }
             }
+        } else if (zmode) {
+            RowsZPower<T> io{interm, reinterpret_cast<T*>(q.out) + b0 * item, ly, H, q.shift_y, q.shift_x, (T)q.scale, colline ? ag : nullptr, wj, nullptr};
             ProfScope ps_(PROF_ROWS, st);
             if (int rc = rows_z_power<T>(io, lx - 1, nb * H, st)) return rc;
         } else {
-            RowsC2CPower<T> io{interm, reinterpret_cast<T*>(q.out) + b0 * item, ly, H, q.shift_y, q.shift_x, (T)q.scale, colline ? ag : nullptr, wj, stagger_knob(1)};
+            RowsC2CPower<T> io{interm, reinterpret_cast<T*>(q.out) + b0 * item, ly, H, q.shift_y, q.shift_x, (T)q.scale, colline ? ag : nullptr, wj};
             ProfScope ps_(PROF_ROWS, st);
             if (int rc = rows_c2c_power<T>(io, lx, nb * H, st)) return rc;
         }
@@ -1184,12 +1167,8 @@ static int spectrum2d_colsfirst(const xrftb_spectrum2d_desc& q, int ly, int lx, 
 // unchanged) runs once per field and leaves Z1, Z2; the completion tables are built per field; one two-field pass 2
 // combines them (and writes the phase next to the cross spectrum when desc.out2 is set).  Per item the workspace holds two
 // Z arrays and two sets of column-line tables; the chunk adapts to the workspace the caller sized for the rows-first chain.
-// XRFTB_CROSS_Z=0 selects the rows-first two-field chain (A/B switch).
-static bool crossz_enabled() {
-    static int on = -1;
-    if (on < 0) { const char* e = getenv("XRFTB_CROSS_Z"); on = e ? atoi(e) : 1; }
-    return on != 0;
-}
+// Option cross_z = 0 selects the rows-first two-field chain.
+static bool crossz_enabled() { return option(OPT_CROSS_Z) != 0; }
 template <typename T> static bool crossz_eligible(const xrftb_spectrum2d_desc& q, int ly, int lx) {
     if (!std::is_same<T, float>::value) return false;
     if (!(q.mode == XRFTB_EPI_CROSS || q.mode == XRFTB_EPI_PHASE) || q.keep_half || q.weight_x || q.ramp_y || q.ramp_x) return false;
@@ -1284,7 +1263,7 @@ static int spectrum2d_impl(const xrftb_spectrum2d_desc& q, cudaStream_t st) {
     if (ly < 1 || lx < 2) { set_error("spectrum2d: ny, nx must be powers of two (ny>=2, nx>=4), got %d x %d", q.ny, q.nx); return XRFTB_EUNSUPPORTED; }
     const bool two = (q.mode == XRFTB_EPI_CROSS || q.mode == XRFTB_EPI_PHASE || q.mode == XRFTB_EPI_BINS_CROSS);
     if (two && !q.in2) { set_error("spectrum2d: mode %d needs in2", q.mode); return XRFTB_EINVAL; }
-    if (colsfirst_enabled() && colsfirst_eligible<T>(q.mode, q.keep_half, q.weight_x, ly, lx, q.nx)) { g_last_path.store(1); return spectrum2d_colsfirst<T>(q, ly, lx, st); }
+    if (colsfirst_enabled() && colsfirst_eligible<T>(q, ly, lx)) { g_last_path.store(1); return spectrum2d_colsfirst<T>(q, ly, lx, st); }
     if (crossz_enabled() && crossz_eligible<T>(q, ly, lx)) {
         const int rc = spectrum2d_crossz<T>(q, ly, lx, st);
         if (rc != XRFTB_EWORKSPACE) { g_last_path.store(3); return rc; }
@@ -1339,43 +1318,17 @@ static int spectrum2d_impl(const xrftb_spectrum2d_desc& q, cudaStream_t st) {
     const long item = (long)q.ny * q.nx;
     const T* ins[2] = {reinterpret_cast<const T*>(q.in1), reinterpret_cast<const T*>(q.in2)};
 
-    // Moments of chunk c+1 run on a side stream while the row/column passes of chunk c run on the caller's stream:
-    // the reduce is bandwidth-bound, the FFT passes are issue-bound, and the hot kernels leave room for one light CTA/SM.
-    static int side_on = -1;
-    if (side_on < 0) { const char* e = getenv("XRFTB_SIDE_MOMENTS"); side_on = e ? atoi(e) : 0; }  // measured slower: off by default
-    const long nchunks = (q.batch + bchunk - 1) / bchunk;
-    const bool side = side_on && q.detrend && !rowline && std::is_same<T, float>::value && nchunks > 1 && lx >= 2 && fields == 1;
-    static thread_local cudaStream_t s_side = nullptr;
-    std::vector<cudaEvent_t> ev_mom;
-    auto launch_moments = [&](const T* base, double* m, long nitems, cudaStream_t stream, bool light) -> int {
-        ProfScope ps_(PROF_MOMENTS, stream);
-        if (light) {
-            if constexpr (std::is_same<T, float>::value)
-                moments_side_kernel<<<sm_count(), 128, 0, stream>>>(base, m, lx - 2, ly, nitems);
-        } else {
-            int chunks = (int)((8L * sm_count() + nitems - 1) / nitems);
-            if (chunks < 1) chunks = 1;
-            if (chunks > q.ny) chunks = q.ny;
-            dim3 grid(chunks, (unsigned)nitems);
-            moments_kernel<T><<<grid, 256, 0, st>>>(base, m, 1, q.ny, q.nx, chunks, nitems);
-        }
-        return check_launch("moments_kernel");
-    };
-    if (q.detrend && !rowline) {
+    if (q.detrend && !rowline) {   // global-plane detrend: one moments reduce per field ahead of the passes
         cudaError_t e = cudaMemsetAsync(mom, 0, mom_bytes, st);
         if (e != cudaSuccess) { set_error("memset: %s", cudaGetErrorString(e)); return XRFTB_ECUDA; }
-        if (!side) {
-            for (int f = 0; f < fields; ++f)
-                if (int rc = launch_moments(ins[f], mom + (size_t)f * q.batch * 4, q.batch, st, false)) return rc;
-        } else {
-            if (!s_side) cudaStreamCreateWithFlags(&s_side, cudaStreamNonBlocking);
-            ev_mom.resize(nchunks);
-            for (auto& ev : ev_mom) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
-            // chunk 0 on the caller's stream (nothing to overlap with yet); the side stream starts after the memset
-            const long nb0 = q.batch < bchunk ? q.batch : bchunk;
-            if (int rc = launch_moments(ins[0], mom, nb0, st, false)) return rc;
-            cudaEventRecord(ev_mom[0], st);
-            cudaStreamWaitEvent(s_side, ev_mom[0], 0);
+        for (int f = 0; f < fields; ++f) {
+            ProfScope ps_(PROF_MOMENTS, st);
+            int chunks = (int)((8L * sm_count() + q.batch - 1) / q.batch);
+            if (chunks < 1) chunks = 1;
+            if (chunks > q.ny) chunks = q.ny;
+            dim3 grid(chunks, (unsigned)q.batch);
+            moments_kernel<T><<<grid, 256, 0, st>>>(ins[f], mom + (size_t)f * q.batch * 4, 1, q.ny, q.nx, chunks, q.batch);
+            if (int rc = check_launch("moments_kernel")) return rc;
         }
     }
     EpilogueDesc d{};
@@ -1388,8 +1341,6 @@ static int spectrum2d_impl(const xrftb_spectrum2d_desc& q, cudaStream_t st) {
     const size_t out_elem = (q.mode == XRFTB_EPI_COMPLEX || q.mode == XRFTB_EPI_CROSS) ? sizeof(C_) : sizeof(T);
     for (long b0 = 0; b0 < q.batch; b0 += bchunk) {
         const long nb = (q.batch - b0 < bchunk) ? q.batch - b0 : bchunk;
-        const long ci = b0 / bchunk;
-        if (side && ci > 0) cudaStreamWaitEvent(st, ev_mom[ci], 0);
         for (int f = 0; f < fields; ++f) {
             RowsR2CFused<T> io{};
             io.in = ins[f] + b0 * item; io.in_row_stride = q.nx; io.logNy = ly; io.detrend = q.detrend;
@@ -1405,27 +1356,16 @@ static int spectrum2d_impl(const xrftb_spectrum2d_desc& q, cudaStream_t st) {
             rowline_fix_kernel<T><<<dim3((unsigned)nb, (unsigned)((q.ny + 1023) / 1024)), 256, 0, st>>>(rowstats, ag, reinterpret_cast<const T*>(q.win_y), q.ny, q.nx, q.detrend);
             if (int rc = check_launch("rowline_fix_kernel")) return rc;
         }
-        if (side && ci + 1 < nchunks) {
-            const long b1 = b0 + bchunk;
-            const long nb1 = (q.batch - b1 < bchunk) ? q.batch - b1 : bchunk;
-            if (int rc = launch_moments(ins[0] + b1 * item, mom + b1 * 4, nb1, s_side, true)) return rc;
-            cudaEventRecord(ev_mom[ci + 1], s_side);
-        }
         d.out = bins_mode ? nullptr : reinterpret_cast<char*>(q.out) + (size_t)b0 * q.ny * W * out_elem;
         d.bins = bins_mode ? q.bins + (size_t)b0 * q.nbins * (q.mode == XRFTB_EPI_BINS_CROSS ? 2 : 1) : nullptr;
         const C_* i1 = interm;
         const C_* i2 = two ? interm + (size_t)bchunk * (per_item / sizeof(C_)) : nullptr;
-        static int hints_on = -1;
-        if (hints_on < 0) { const char* e = getenv("XRFTB_L2_HINTS"); hints_on = e ? atoi(e) : 0; }
-        d.l2_hints = hints_on;
         d.fix_ag = rowline ? ag : nullptr;
         d.fix_wj = rowline ? wj : nullptr;
         CUtensorMap tmap;
         const CUtensorMap* ptm = nullptr;
         d.use_tma = 0;
-        static int tma_on = -1;
-        if (tma_on < 0) { const char* e = getenv("XRFTB_TMA_STORE"); tma_on = e ? atoi(e) : 1; }
-        if (tma_on && q.mode == XRFTB_EPI_POWER && std::is_same<T, float>::value && C >= 8 /* >= 32-byte rows: 16-byte boxes measured slower than LSU stores */ && (mirror_pass || q.keep_half) && !q.weight_x
+        if (q.mode == XRFTB_EPI_POWER && std::is_same<T, float>::value && C >= 8 /* >= 32-byte rows: 16-byte boxes measured slower than LSU stores */ && (mirror_pass || q.keep_half) && !q.weight_x
             && (W * sizeof(float)) % 16 == 0 && q.ny >= 4 && q.nx / 2 >= C /* the Nyquist column starts its own tile: no box wraps around the fftshift */) {
             const int box_rows = q.ny / 2 < 256 ? q.ny / 2 : 256;
             if (encode_out_tmap(&tmap, d.out, nb * q.ny, W, C, box_rows)) { d.use_tma = 1; d.tma_box_rows = box_rows; ptm = &tmap; }
@@ -1444,7 +1384,6 @@ static int spectrum2d_impl(const xrftb_spectrum2d_desc& q, cudaStream_t st) {
             if (int rc = check_launch("mirror_fill_kernel")) return rc;
         }
     }
-    for (auto& ev : ev_mom) cudaEventDestroy(ev);
     return 0;
 }
 
@@ -1479,6 +1418,19 @@ int xrftb_profile_end(double* ms, long* counts) {
     return 0;
 }
 const char* xrftb_last_error(void) { return g_err; }
+int xrftb_set_option(const char* name, int value) {
+    const int i = option_index(name);
+    if (i < 0) { set_error("unknown option '%s'", name ? name : "(null)"); return XRFTB_EINVAL; }
+    std::call_once(g_opt_once, options_init);
+    g_opt[i].store(value);
+    return 0;
+}
+int xrftb_get_option(const char* name, int* value) {
+    const int i = option_index(name);
+    if (i < 0 || !value) { set_error("unknown option '%s'", name ? name : "(null)"); return XRFTB_EINVAL; }
+    *value = option((Option)i);
+    return 0;
+}
 int xrftb_spectrum2d_last_path(void) { return g_last_path.load(); }
 
 int xrftb_device_info(int* sms, int* major, int* minor, size_t* smem_optin) {

@@ -33,24 +33,6 @@ int cols_c2c(const cplx<T>* in, cplx<T>* out, int log2L, long A, long B, int inv
 template <typename T>
 int cols_r2c_pack(const ColsR2CPack<T>& io, int log2L, int C, long ntiles, bool use_async, cudaStream_t st) {
     if constexpr (sizeof(T) == 4) {
-        if (use_async && C != cols_tile_width<T>(log2L, false)) {   // half-width tiles (colsfirst_tile_width): two CTAs per SM
-            switch (log2L) {
-#define X(K) case K: if constexpr (K >= 11 && TileC<T, K, false>::value >= 4) { if (C == TileC<T, K, false>::value / 2) return launch_cols_async<T, K, TileC<T, K, false>::value / 2>(io, ntiles, st); } break;
-                XRFTB_COLS_CASES(X)
-#undef X
-                default: break;
-            }
-            set_error("cols_r2c_pack: no half-width variant for length 2^%d, C = %d", log2L, C);
-            return -2;
-        }
-        if (use_async && io.zout != nullptr && f32x2_enabled() && C == cols_tile_width<T>(log2L, false)) {   // packed FP32x2 z-mode kernel
-            switch (log2L) {
-#define X(K) case K: if constexpr (K > TypeCfg<T>::LOGE && TileC<T, K, false>::value >= 2) return launch_colszp<K, TileC<T, K, false>::value>(io, ntiles, st); break;
-                XRFTB_COLS_CASES(X)
-#undef X
-                default: break;
-            }
-        }
         if (use_async) {   // tensor-map fed variant (io.tmap / io.box_rows are set); float32, two packed columns per thread
             switch (log2L) {
 #define X(K) case K: if constexpr (K > TypeCfg<T>::LOGE && TileC<T, K, false>::value >= 2) return launch_cols_async<T, K, TileC<T, K, false>::value>(io, ntiles, st); break;
@@ -98,8 +80,7 @@ static int cols_fused_k(const cplx<T>* in1, const cplx<T>* in2, long ntiles_tota
         if constexpr (sizeof(T) == 4 && (MODE == EPI_POWER || MODE == EPI_BINS_POWER) && (K > TypeCfg<T>::LOGE) && C >= 2 && C % 2 == 0) {
             // measured (profiles/README.md): wins where the epilogue stores are asynchronous too (TMA tensor stores, C >= 8);
             // at C = 4 the 16-byte row-segment stores dominate and the extra exchange barriers cost more than the loads hide
-            static int async_on = -1;
-            if (async_on < 0) { const char* e = getenv("XRFTB_COLS_ASYNC"); async_on = e ? atoi(e) : 2; }
+            const int async_on = option(OPT_COLS_ASYNC);
             // the binned epilogue has no stores to hide: there the register-prefetch kernel is 36 % faster (config 4: 111 vs 81 GPoints/s)
             if (async_on == 1 || (async_on == 2 && C >= 8 && MODE == EPI_POWER)) return launch_cols_async<T, K, C>(io, ntiles_total, st, extra);
         }

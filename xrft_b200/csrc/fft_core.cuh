@@ -43,24 +43,6 @@ template <typename CA, typename CW> __device__ __forceinline__ CA cmulw(CA a, CW
 }
 
 // ---------------------------------------------------------------------------------------------
-// Packed float32 pairs (Blackwell FP32x2: SASS FADD2 / FMUL2 / FFMA2).  One f32x2 holds the SAME
-// scalar of TWO sequences (lo = sequence 0, hi = sequence 1) in an aligned register pair, so every
-// add / multiply of the butterflies and twiddle products is issued once for both sequences.  The
-// operators map to the sm_100 intrinsics; the compiler folds negations into operand modifiers,
-// broadcasts plain floats (twiddles, radix constants) as .F32 operands and contracts a*b+c to FFMA2.
-// cplx2 = a complex number of each of the two sequences: (x: both real parts, y: both imaginary parts).
-// ---------------------------------------------------------------------------------------------
-struct f32x2 { float2 v; };
-__device__ __forceinline__ f32x2 mk2(float lo, float hi) { f32x2 r; r.v = make_float2(lo, hi); return r; }
-__device__ __forceinline__ f32x2 operator+(f32x2 a, f32x2 b) { f32x2 r; r.v = __fadd2_rn(a.v, b.v); return r; }
-__device__ __forceinline__ f32x2 operator-(f32x2 a, f32x2 b) { f32x2 r; r.v = __fadd2_rn(a.v, make_float2(-b.v.x, -b.v.y)); return r; }
-__device__ __forceinline__ f32x2 operator-(f32x2 a) { f32x2 r; r.v = make_float2(-a.v.x, -a.v.y); return r; }
-__device__ __forceinline__ f32x2 operator*(f32x2 a, f32x2 b) { f32x2 r; r.v = __fmul2_rn(a.v, b.v); return r; }
-__device__ __forceinline__ f32x2 operator*(f32x2 a, float s) { f32x2 r; r.v = __fmul2_rn(a.v, make_float2(s, s)); return r; }
-__device__ __forceinline__ f32x2 operator*(float s, f32x2 a) { return a * s; }
-struct cplx2 { f32x2 x, y; };
-
-// ---------------------------------------------------------------------------------------------
 // register radix kernels, forward sign (exp(-i..)), natural-order output, in place
 // ---------------------------------------------------------------------------------------------
 template <typename C> __device__ __forceinline__ void fft2(C& a, C& b) { C t = a; a = cadd(t, b); b = csub(t, b); }
@@ -105,7 +87,6 @@ template <typename T, typename C> __device__ __forceinline__ void fft16(C* a) {
     for (int i = 0; i < 8; ++i) { a[i] = cadd(e[i], o[i]); a[i + 8] = csub(e[i], o[i]); }
 }
 
-// CA = cplx<T>, or cplx2 (two float32 sequences at once)
 template <typename T, int R> struct Radix;
 template <typename T> struct Radix<T, 1> { template <typename CA> static __device__ __forceinline__ void run(CA*) {} };
 template <typename T> struct Radix<T, 2> { template <typename CA> static __device__ __forceinline__ void run(CA* a) { fft2(a[0], a[1]); } };
@@ -395,137 +376,6 @@ struct StagesAsync {
                 __syncthreads();
             }
             StagesAsync<T, LOG2L, LOGE, LOGNS + LOGR, C>::run(v, u, smL, smX, tw, hook);
-        }
-    }
-};
-
-// ---------------------------------------------------------------------------------------------
-// Packed (FP32x2) stage drivers: two float32 sequences per thread held as cplx2 v[E] from the first
-// butterfly to the epilogue.  Same Stockham index map and padding as Stages / StagesAsync; an
-// exchange element is either one float4 (x0, x1, y0, y1) per point -- both sequences, 128-bit
-// accesses -- or one float2 (the x pair, then the y pair) when the buffer is half size.
-// ---------------------------------------------------------------------------------------------
-template <int LOG2L, int LOGE, int LOGNS> struct StageGeomP {
-    using G_ = Geometry<LOG2L, LOGE>;
-    static constexpr int E = G_::E;
-    static constexpr int REM = LOG2L - LOGNS;
-    static constexpr int LOGR = REM >= LOGE ? LOGE : REM;
-    static constexpr int R = 1 << LOGR;
-    static constexpr int G = E / R;
-    static constexpr int Ns = 1 << LOGNS;
-    static constexpr bool LAST = (LOGNS + LOGR == LOG2L);
-    static constexpr int PADW = 1 << G_::LOGPAD;
-    // smem element index (in units of SI elements) of register element g + t*G in the scatter of this stage
-    static __device__ __forceinline__ int scatter_index(int u, int g, int t) {
-        const int j = u + g * G_::NT;
-        const int jm = j & (Ns - 1);
-        const int o0 = (j - jm) * R + jm;
-        if constexpr (Ns == 1 && R == PADW) return j * (R + 1) + t;
-        else if constexpr (Ns >= PADW) return padded<G_::LOGPAD>(o0) + t * (Ns + Ns / PADW);
-        else return padded<G_::LOGPAD>(o0 + t * Ns);
-    }
-    static __device__ __forceinline__ int gather_index(int u, int q) {
-        if constexpr (G_::NT % PADW == 0) return padded<G_::LOGPAD>(u) + q * (G_::NT + G_::NT / PADW);
-        else return padded<G_::LOGPAD>(u + q * G_::NT);
-    }
-    // twiddle + radix-R butterflies of this stage on both sequences at once
-    static __device__ __forceinline__ void butterflies(cplx2 (&v)[E], int u, const float2* __restrict__ tw) {
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-            const int j = u + g * G_::NT;
-            const int jm = j & (Ns - 1);
-            cplx2 a[R];
-#pragma unroll
-            for (int t = 0; t < R; ++t) a[t] = v[g + t * G];
-            if constexpr (LOGNS > 0) apply_twiddles<float, R>(a, tw, jm * (G_::L / (Ns * R)));
-            Radix<float, R>::run(a);
-#pragma unroll
-            for (int t = 0; t < R; ++t) v[g + t * G] = a[t];
-        }
-    }
-};
-
-// rows: one float4 per point in `sm` ([pad(o)] float4), in-place exchange, two barriers per stage
-template <int LOG2L, int LOGE, int LOGNS>
-struct StagesP {
-    using S_ = StageGeomP<LOG2L, LOGE, LOGNS>;
-    static constexpr int E = S_::E;
-    static __device__ __forceinline__ void run(cplx2 (&v)[E], int u, float4* sm, const float2* __restrict__ tw) {
-        S_::butterflies(v, u, tw);
-        if constexpr (!S_::LAST) {
-#pragma unroll
-            for (int g = 0; g < S_::G; ++g)
-#pragma unroll
-                for (int t = 0; t < S_::R; ++t) {
-                    const cplx2 c = v[g + t * S_::G];
-                    sm[S_::scatter_index(u, g, t)] = make_float4(c.x.v.x, c.x.v.y, c.y.v.x, c.y.v.y);
-                }
-            __syncthreads();
-#pragma unroll
-            for (int q = 0; q < E; ++q) {
-                const float4 f = sm[S_::gather_index(u, q)];
-                v[q].x = mk2(f.x, f.y);
-                v[q].y = mk2(f.z, f.w);
-            }
-            __syncthreads();
-            StagesP<LOG2L, LOGE, LOGNS + S_::LOGR>::run(v, u, sm, tw);
-        }
-    }
-};
-template <int LOG2L, int LOGE>
-__device__ __forceinline__ void block_fft_p(cplx2 (&v)[1 << LOGE], int u, float4* sm, const float2* __restrict__ tw) {
-    StagesP<LOG2L, LOGE, 0>::run(v, u, sm, tw);
-}
-
-// columns (see StagesAsync): exchange #0 through the landing buffer (float4 per point and column pair, CG pairs per
-// row of the tile), then hook() re-arms it; later exchanges through the half-size buffer, x pairs then y pairs
-template <int LOG2L, int LOGE, int LOGNS, int C>
-struct StagesAsyncP {
-    using S_ = StageGeomP<LOG2L, LOGE, LOGNS>;
-    static constexpr int E = S_::E;
-    static constexpr int CG = C / 2;
-    template <class Hook>
-    static __device__ __forceinline__ void run(cplx2 (&v)[E], int u, float4* smL4, float2* smX, const float2* __restrict__ tw, Hook&& hook) {
-        S_::butterflies(v, u, tw);
-        if constexpr (!S_::LAST) {
-            if constexpr (LOGNS == 0) {
-                __syncthreads();            // every thread has taken its points of the landed tile out of the buffer
-#pragma unroll
-                for (int g = 0; g < S_::G; ++g)
-#pragma unroll
-                    for (int t = 0; t < S_::R; ++t) {
-                        const cplx2 c = v[g + t * S_::G];
-                        smL4[S_::scatter_index(u, g, t) * CG] = make_float4(c.x.v.x, c.x.v.y, c.y.v.x, c.y.v.y);
-                    }
-                __syncthreads();
-#pragma unroll
-                for (int q = 0; q < E; ++q) {
-                    const float4 f = smL4[S_::gather_index(u, q) * CG];
-                    v[q].x = mk2(f.x, f.y);
-                    v[q].y = mk2(f.z, f.w);
-                }
-                fence_proxy_async_smem();   // generic-proxy accesses of the buffer are ordered before the bulk copy that re-fills it
-                __syncthreads();
-                hook();
-            } else {
-#pragma unroll
-                for (int g = 0; g < S_::G; ++g)
-#pragma unroll
-                    for (int t = 0; t < S_::R; ++t) smX[S_::scatter_index(u, g, t) * CG] = v[g + t * S_::G].x.v;
-                __syncthreads();
-#pragma unroll
-                for (int q = 0; q < E; ++q) v[q].x.v = smX[S_::gather_index(u, q) * CG];
-                __syncthreads();
-#pragma unroll
-                for (int g = 0; g < S_::G; ++g)
-#pragma unroll
-                    for (int t = 0; t < S_::R; ++t) smX[S_::scatter_index(u, g, t) * CG] = v[g + t * S_::G].y.v;
-                __syncthreads();
-#pragma unroll
-                for (int q = 0; q < E; ++q) v[q].y.v = smX[S_::gather_index(u, q) * CG];
-                __syncthreads();
-            }
-            StagesAsyncP<LOG2L, LOGE, LOGNS + S_::LOGR, C>::run(v, u, smL4, smX, tw, hook);
         }
     }
 };

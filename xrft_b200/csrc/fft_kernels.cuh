@@ -27,22 +27,6 @@ constexpr int ilog2c(int n) { return n <= 1 ? 0 : 1 + ilog2c(n / 2); }
 enum : int { EPI_COMPLEX = 0, EPI_POWER = 1, EPI_CROSS = 2, EPI_PHASE = 3, EPI_BINS_POWER = 4, EPI_BINS_CROSS = 5,
              EPI_CROSS_AND_PHASE = 6 /* internal: CROSS with the optional second output (desc.out2) */ };
 
-// L2 cache-policy hinted 16-byte accesses (experiment knob XRFTB_L2_HINTS): the intermediate is read exactly once
-// (evict-first), the 16-byte output row segments should stay in L2 until the neighbouring tile completes the sector
-// (evict-last), so that partial sectors are merged instead of written back early
-__device__ __forceinline__ float4 ld16_evict_first(const void* p) {
-    float4 r;
-    asm volatile("{\n\t.reg .b64 pol;\n\tcreatepolicy.fractional.L2::evict_first.b64 pol, 1.0;\n\t"
-                 "ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], pol;\n\t}"
-                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
-    return r;
-}
-__device__ __forceinline__ void st16_evict_last(void* p, float4 v) {
-    asm volatile("{\n\t.reg .b64 pol;\n\tcreatepolicy.fractional.L2::evict_last.b64 pol, 1.0;\n\t"
-                 "st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, pol;\n\t}"
-                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-
 __device__ __forceinline__ float xatan2(float y, float x) { return atan2f(y, x); }
 __device__ __forceinline__ double xatan2(double y, double x) { return atan2(y, x); }
 
@@ -595,7 +579,6 @@ rows2c_power_kernel(RowsC2CPower<T> io, const cplx<T>* __restrict__ tw, long nse
     const long ngroups = (nseq + SEQ - 1) / SEQ;
     const int Ny = 1 << io.logNy;
     const int sy = io.shift_y ? Ny / 2 : 0, sx = io.shift_x ? Nx / 2 : 0;
-    if (io.stagger_ns > 0 && blockIdx.x >= gridDim.x / 2) __nanosleep((unsigned)io.stagger_ns);
     for (long grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
         const long nxt = grp + gridDim.x;
         if (threadIdx.x == 0 && nxt < ngroups) io.template prefetch<LOG2L, SEQ>(nxt * SEQ, nseq);
@@ -662,7 +645,6 @@ template <typename T> struct RowsZPower {
     const cplx<T>* z; T* out; int logNy; int H; int shift_y, shift_x; T scale;
     const cplx<T>* ag; const cplx<T>* wj;   // column-line detrend completion (see RowsC2CPower); nullptr = none
     const cplx<T>* tw2;                     // exp(-2 pi i k / Nx), k in [0, Nx): twiddle_fft(log2 Nx)
-    int bulk;                               // rowsz_power_kernel: rows staged in shared memory and written by bulk copies (TMA)
 };
 template <typename T, int LOG2M, int LOGE, int ROWS>
 __global__ void __launch_bounds__((1 << (LOG2M - LOGE)) * ROWS, min_blocks_for((1 << (LOG2M - LOGE)) * ROWS))
@@ -725,53 +707,7 @@ rowsz_power_kernel(RowsZPower<T> io, const cplx<T>* __restrict__ tw, long nseq) 
                 v[1][q].x += a1.x * W.x + a1.y * J.x; v[1][q].y += a1.x * W.y + a1.y * J.y;
             }
         }
-        if (io.bulk) {   // the bulk stores of the previous group have finished reading the exchange buffer (their staging area)
-            if (u == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            __syncthreads();
-        }
         block_fft<T, LOG2M, LOGE, 2, 2>(v, u, sm, 1, tw);
-        if (io.bulk) {
-            // Output rows staged in shared memory in their final (fftshift-ed) order -- the direct row, then its Hermitian
-            // mirror -- and written by one bulk copy (TMA) each: 16 KB contiguous instead of 4-byte stores.
-            T* sd = reinterpret_cast<T*>(sm);
-            T* smr = sd + Nx;
-            const bool self = (ky == 0) || (2 * ky == Ny);
-            if (act) {
-#pragma unroll
-                for (int g = 0; g < G; ++g)
-#pragma unroll
-                    for (int t = 0; t < R; ++t) {
-                        const int k = final_index<LOG2M, LOGE>(u, g, t);
-                        const cplx<T> fa = v[0][g + t * G];
-                        const cplx<T> wb = cmul(v[1][g + t * G], smw[k]);
-                        const cplx<T> f0 = cadd(fa, wb), f1 = csub(fa, wb);
-                        const T p0 = (f0.x * f0.x + f0.y * f0.y) * io.scale;   // kx = k
-                        const T p1 = (f1.x * f1.x + f1.y * f1.y) * io.scale;   // kx = k + M
-                        sd[(k + sx) & (Nx - 1)] = p0;
-                        if (!self) {
-                            sd[(k + M + sx) & (Nx - 1)] = p1;
-                            smr[(Nx - k + sx) & (Nx - 1)] = p0;
-                            smr[(M - k + sx) & (Nx - 1)] = p1;
-                        } else {   // rows 0 and Ny/2 mirror into themselves: kx <= M computed, the rest copied
-                            if (k == 0) sd[(M + sx) & (Nx - 1)] = p1;
-                            else sd[(Nx - k + sx) & (Nx - 1)] = p0;
-                        }
-                    }
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncthreads();
-            if (act && u == 0) {
-                T* rowd = io.out + ((b << io.logNy) + ((ky + sy) & (Ny - 1))) * (long)Nx;
-                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                             :: "l"(rowd), "r"(smem_u32(sd)), "r"((unsigned)(Nx * sizeof(T))) : "memory");
-                if (!self) {
-                    T* rowm = io.out + ((b << io.logNy) + ((Ny - ky + sy) & (Ny - 1))) * (long)Nx;
-                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                                 :: "l"(rowm), "r"(smem_u32(smr)), "r"((unsigned)(Nx * sizeof(T))) : "memory");
-                }
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            }
-        } else
         if (act) {
             T* rowd = io.out + ((b << io.logNy) + ((ky + sy) & (Ny - 1))) * (long)Nx;
             T* rowm = io.out + ((b << io.logNy) + ((Ny - ky + sy) & (Ny - 1))) * (long)Nx;
@@ -795,7 +731,6 @@ rowsz_power_kernel(RowsZPower<T> io, const cplx<T>* __restrict__ tw, long nseq) 
                 }
         }
     }
-    if (io.bulk && u == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // Two-field pass 2 of the columns-first z-mode chain (BASELINE config 3): cross spectrum F1 conj(F2), its phase, or BOTH from
@@ -901,88 +836,6 @@ rowszx_kernel(RowsZCross<float> io, const float2* __restrict__ tw, long nseq) {
     }
 }
 
-// Packed (FP32x2) variant of rowsz_power_kernel: the A and B sequences of a row live in one cplx2 per point, so the
-// separation is one FADD2 + two FADDs per packed column, every butterfly / twiddle product of the two M-point transforms
-// is issued once (FADD2 / FMUL2 / FFMA2), and |F|^2 of the output pair (kx, kx + M) is three packed instructions.
-template <int LOG2M, int LOGE, int ROWS>
-__global__ void __launch_bounds__((1 << (LOG2M - LOGE)) * ROWS, min_blocks_for((1 << (LOG2M - LOGE)) * ROWS))
-rowszp_power_kernel(RowsZPower<float> io, const float2* __restrict__ tw, long nseq) {
-    using G_ = Geometry<LOG2M, LOGE>;
-    constexpr int E = G_::E, NT = G_::NT, M = 1 << LOG2M, Nx = 2 * M;
-    constexpr int ROW_STRIDE = G_::LPAD + 4;   // float4 per point
-    constexpr int R = 1 << G_::LOGR_LAST, G = E / R;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float4* smem = reinterpret_cast<float4*>(smem_raw);
-    float2* smw = reinterpret_cast<float2*>(smem + ROWS * ROW_STRIDE);   // [M] radix-2 twiddles
-    const int r = threadIdx.x / NT, u = threadIdx.x % NT;
-    float4* sm = smem + r * ROW_STRIDE;
-    for (int k = threadIdx.x; k < M; k += NT * ROWS) smw[k] = __ldg(io.tw2 + k);
-    __syncthreads();
-    const long ngroups = (nseq + ROWS - 1) / ROWS;
-    const int Ny = 1 << io.logNy;
-    const int sy = io.shift_y ? Ny / 2 : 0, sx = io.shift_x ? Nx / 2 : 0;
-    for (long grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
-        const long nxt = grp + gridDim.x;
-        if (threadIdx.x < 2 * ROWS && nxt < ngroups) {   // next group's rows -> L2
-            const long s2 = nxt * ROWS + (threadIdx.x >> 1);
-            if (s2 < nseq) {
-                const long b2 = s2 / io.H;
-                const int k2 = (int)(s2 - b2 * io.H);
-                const int row = (threadIdx.x & 1) ? ((Ny - k2) & (Ny - 1)) : k2;
-                prefetch_l2_bulk(io.z + ((b2 << io.logNy) + row) * (long)M, (unsigned)(M * sizeof(float2)));
-            }
-        }
-        const long seq = grp * ROWS + r;
-        const bool act = seq < nseq;
-        const long b = act ? seq / io.H : 0;
-        const int ky = act ? (int)(seq - b * io.H) : 0;
-        cplx2 v[E];
-        {
-            const float2* pa = io.z + ((b << io.logNy) + ky) * (long)M + u;
-            const float2* pb = io.z + ((b << io.logNy) + ((Ny - ky) & (Ny - 1))) * (long)M + u;
-            float2 za[E], zb[E];
-#pragma unroll
-            for (int q = 0; q < E; ++q) { za[q] = act ? pa[q * NT] : make_float2(0.f, 0.f); zb[q] = act ? pb[q * NT] : make_float2(0.f, 0.f); }
-#pragma unroll
-            for (int q = 0; q < E; ++q) {
-                v[q].x.v = __fadd2_rn(za[q], zb[q]);                              // (A.x, B.x)
-                v[q].y = mk2(za[q].y - zb[q].y, zb[q].x - za[q].x);               // (A.y, B.y)
-            }
-        }
-        if (io.ag != nullptr && act) {
-            const float2 W = __ldg(io.wj + 2 * ky), J = __ldg(io.wj + 2 * ky + 1);
-            const float2* pa = io.ag + b * (long)Nx + 2 * u;
-#pragma unroll
-            for (int q = 0; q < E; ++q) {
-                const float4 a = __ldg(reinterpret_cast<const float4*>(pa + 2 * q * NT));   // (alpha, gamma) of columns 2c, 2c+1
-                v[q].x.v.x += a.x * W.x + a.y * J.x; v[q].y.v.x += a.x * W.y + a.y * J.y;
-                v[q].x.v.y += a.z * W.x + a.w * J.x; v[q].y.v.y += a.z * W.y + a.w * J.y;
-            }
-        }
-        block_fft_p<LOG2M, LOGE>(v, u, sm, tw);
-        if (act) {
-            float* rowd = io.out + ((b << io.logNy) + ((ky + sy) & (Ny - 1))) * (long)Nx;
-            float* rowm = io.out + ((b << io.logNy) + ((Ny - ky + sy) & (Ny - 1))) * (long)Nx;
-            const bool self = (ky == 0) || (2 * ky == Ny);   // see rowsz_power_kernel
-#pragma unroll
-            for (int g = 0; g < G; ++g)
-#pragma unroll
-                for (int t = 0; t < R; ++t) {
-                    const int k = final_index<LOG2M, LOGE>(u, g, t);
-                    const cplx2 c = v[g + t * G];
-                    const float2 w = smw[k];
-                    const float wbx = c.x.v.y * w.x - c.y.v.y * w.y, wby = c.x.v.y * w.y + c.y.v.y * w.x;   // w^k FB[k]
-                    const f32x2 fx = mk2(c.x.v.x + wbx, c.x.v.x - wbx), fy = mk2(c.y.v.x + wby, c.y.v.x - wby);  // (F[k], F[k+M])
-                    const f32x2 pw = (fx * fx + fy * fy) * io.scale;
-                    rowd[(k + sx) & (Nx - 1)] = pw.v.x;
-                    if (!self || k > 0) rowm[(Nx - k + sx) & (Nx - 1)] = pw.v.x;
-                    if (!self || k == 0) rowd[(k + M + sx) & (Nx - 1)] = pw.v.y;
-                    if (!self) rowm[(M - k + sx) & (Nx - 1)] = pw.v.y;
-                }
-        }
-    }
-}
-
 // =============================================================================================
 // K-B : columns
 // =============================================================================================
@@ -1063,19 +916,10 @@ cols_async_kernel(const __grid_constant__ IO io, const cplx<T>* __restrict__ tw,
     io.template init<LOG2L, LOGE, C, 2>(smX);   // ends with a barrier when there is a histogram
     __syncthreads();
     auto issue = [&](long tile) { io.template issue_load<LOG2L, C>(tile, smL, bar); };
-    if constexpr (IO::kSplitEpilogue) io.stagger();
     if (threadIdx.x == 0 && (long)blockIdx.x < ntiles) issue((long)blockIdx.x);
-    if constexpr (IO::kSplitEpilogue) {   // row runs of the waves between the first one and the steady-state prefetch distance
-        if (io.pf_waves > 0 && threadIdx.x < 32)
-            for (int w = 1; w < io.pf_waves; ++w) io.template prefetch_wave<LOG2L, C>((long)w * gridDim.x, ntiles, threadIdx.x);
-    }
     unsigned phase = 0;
     for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long nxt = tile + gridDim.x;
-        if constexpr (IO::kSplitEpilogue) {
-            if (io.pf_waves > 0 && threadIdx.x < 32)
-                io.template prefetch_wave<LOG2L, C>(tile - blockIdx.x + (long)io.pf_waves * gridDim.x, ntiles, threadIdx.x);
-        }
         cplx<T> ag_[E];
         io.template fix_fetch<LOG2L, LOGE>(tile, u, ag_);   // issued before the wait: their latency hides behind it
         float4 wc4 = make_float4(1.f, 1.f, 1.f, 1.f);
@@ -1199,7 +1043,6 @@ template <typename T> struct ColsR2CPack {
     // input viewed as [batch * Ny][Nx]; a dense box row = 2C reals = C packed points, i.e. the [ky][C] layout the kernel reads
     int box_rows;
     alignas(64) CUtensorMap tmap;
-    int stagger_ns;         // experiment knob XRFTB_STAGGER_NS: second-wave CTAs start this much later (de-phases co-resident CTAs)
     // cols_async_kernel, "z" mode (zout != nullptr): the packed column spectra Z[batch][Ny][Nx/2] are stored as they leave the
     // registers -- no staging, no separation of the two real columns (RowsZPower does it in its loads); w_x / 2 is then
     // applied here, to the real and imaginary part of the packed input, which commutes with the column transform
@@ -1250,27 +1093,6 @@ template <typename T> struct ColsR2CPack {
             }
         }
     }
-    // DRAM-friendly feed of the narrow tiles: the tiles [T0, T0 + G) that the G CTAs of the grid load concurrently ("wave")
-    // cover, in every image row, ONE contiguous run of G * 2C reals -- but each CTA asks for its 2C-real piece of a row at
-    // its own time, so DRAM sees isolated 32-byte reads.  Instead every CTA pulls whole row runs of an upcoming wave
-    // into L2 (rows cta, cta + G, ... ; one bulk prefetch per row and item, issued by the lanes of one warp); the tile
-    // loads then hit L2.  pf_waves = how many waves ahead (0 = off).
-    int pf_waves;
-    template <int LOG2L, int C> __device__ __forceinline__ void prefetch_wave(long T0, long ntiles, int lane) const {
-        constexpr int Ny = 1 << LOG2L;
-        const long G = gridDim.x;
-        if (T0 >= ntiles) return;
-        const long T1 = T0 + G < ntiles ? T0 + G : ntiles;
-        for (long t = T0; t < T1;) {
-            const long b = t / tiles_per_item;
-            const int tin = (int)(t - b * tiles_per_item);
-            const long tend = (b + 1) * (long)tiles_per_item < T1 ? (b + 1) * (long)tiles_per_item : T1;
-            const unsigned bytes = (unsigned)((tend - t) * (2 * C) * sizeof(T));
-            const T* base = in + (b << LOG2L) * (long)Nx + tin * (2 * C);
-            for (long r = blockIdx.x + (long)lane * G; r < Ny; r += 32 * G) prefetch_l2_bulk(base + r * Nx, bytes);
-            t = tend;
-        }
-    }
     template <int C> __device__ __forceinline__ float4 col_fetch(long tile, int cg) const {
         float4 w = make_float4(1.f, 1.f, 1.f, 1.f);
         if constexpr (sizeof(T) == 4) {
@@ -1305,7 +1127,6 @@ template <typename T> struct ColsR2CPack {
                 else { ob[(long)ky * M] = a; ob[(long)ky * M + 1] = c; }
             }
     }
-    __device__ __forceinline__ void stagger() const { if (stagger_ns > 0 && blockIdx.x >= gridDim.x / 2) __nanosleep((unsigned)stagger_ns); }
     template <int LOG2L, int C> __device__ __forceinline__ void issue_load(long tile, cplx<T>* smL, uint64_t* bar) const {
         constexpr int Ny = 1 << LOG2L;
         const long b = tile / tiles_per_item;
@@ -1592,71 +1413,6 @@ template <typename T> struct ColsR2CPack {
     }
 };
 
-// Packed (FP32x2) pass 1 of the columns-first order in z mode (ColsR2CPack<float>::zout): cols_async_kernel with the two
-// packed columns of a thread held as one cplx2 per row from the first butterfly to the store -- every butterfly and
-// twiddle product is issued once for both columns.  The landed rows (x0, y0, x1, y1) are re-paired to (x0, x1), (y0, y1)
-// after the detrend / window prologue and paired back in the 16-byte stores of Z.
-template <int LOG2L, int LOGE, int C>
-__global__ void __launch_bounds__((1 << (LOG2L - LOGE)) * (C / 2), min_blocks_for((1 << (LOG2L - LOGE)) * (C / 2)))
-colszp_kernel(const __grid_constant__ ColsR2CPack<float> io, const float2* __restrict__ tw, long ntiles) {
-    using IO = ColsR2CPack<float>;
-    using G_ = Geometry<LOG2L, LOGE>;
-    constexpr int E = G_::E, CG = C / 2, NT = G_::NT, NTHR = NT * CG;
-    constexpr int R = 1 << G_::LOGR_LAST, G = E / R;
-    static_assert(LOG2L > LOGE, "needs at least one exchange");
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float2* smL = reinterpret_cast<float2*>(smem_raw);
-    float2* smX = smL + G_::LPAD * C;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smX + G_::LPAD * CG);
-    float* extra = reinterpret_cast<float*>(bar + 2);
-    const int cg = threadIdx.x % CG, u = threadIdx.x / CG;
-    if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_init_fence(); }
-    __syncthreads();
-    auto issue = [&](long tile) { io.template issue_load<LOG2L, C>(tile, smL, bar); };
-    if (threadIdx.x == 0 && (long)blockIdx.x < ntiles) issue((long)blockIdx.x);
-    unsigned phase = 0;
-    const int M = io.Nx >> 1;
-    for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const long nxt = tile + gridDim.x;
-        float2 ag_[E];
-        io.template fix_fetch<LOG2L, LOGE>(tile, u, ag_);   // issued before the wait: their latency hides behind it
-        const float4 wc4 = io.template col_fetch<C>(tile, cg);
-        float* extra_t = extra + (phase ? IO::kExtraHalf : 0);
-        mbar_wait(bar, phase);
-        phase ^= 1u;
-        cplx2 v[E];
-        {
-            float2 vv[2][E];
-            const float2* pl = smL + u * C + cg * 2;
-#pragma unroll
-            for (int q = 0; q < E; ++q) {
-                const float4 f = *reinterpret_cast<const float4*>(pl + q * (NT * C));
-                vv[0][q] = make_float2(f.x, f.y);
-                vv[1][q] = make_float2(f.z, f.w);
-            }
-            io.template fix_apply<LOG2L, LOGE, C, 2>(tile, u, cg, ag_, vv, extra_t, smL, wc4);
-#pragma unroll
-            for (int q = 0; q < E; ++q) { v[q].x = mk2(vv[0][q].x, vv[1][q].x); v[q].y = mk2(vv[0][q].y, vv[1][q].y); }
-        }
-        StagesAsyncP<LOG2L, LOGE, 0, C>::run(v, u, reinterpret_cast<float4*>(smL) + cg, smX + cg, tw,
-                                             [&]() { if (threadIdx.x == 0 && nxt < ntiles) issue(nxt); });
-        {
-            const long b = tile / io.tiles_per_item;
-            const int t0 = (int)(tile - b * io.tiles_per_item);
-            io.template write_colstats<C, NTHR>(b, t0 * (2 * C), extra_t);
-            float2* ob = io.zout + (b << LOG2L) * (long)M + t0 * C + cg * 2;
-#pragma unroll
-            for (int g = 0; g < G; ++g)
-#pragma unroll
-                for (int t = 0; t < R; ++t) {
-                    const int ky = final_index<LOG2L, LOGE>(u, g, t);
-                    const cplx2 c = v[g + t * G];
-                    *reinterpret_cast<float4*>(ob + (long)ky * M) = make_float4(c.x.v.x, c.y.v.x, c.x.v.y, c.y.v.y);
-                }
-        }
-    }
-}
-
 // pass 2: rows of the half-spectrum [batch][H][Nx] complex -> power spectrum rows ky and -ky of out [batch][Ny][Nx] real
 template <typename T> struct RowsC2CPower {
     static constexpr int kSeqSkew = 0;
@@ -1664,7 +1420,6 @@ template <typename T> struct RowsC2CPower {
     // column-line detrend completion: row ky of item b gets ag[b][j].x * wj[2 ky] + ag[b][j].y * wj[2 ky + 1] added at column j
     // (ag = w_x(j) (alpha_j, gamma_j), wj = transforms of w_y(i) and w_y(i)(i - ic)); nullptr = none
     const cplx<T>* ag; const cplx<T>* wj;
-    int stagger_ns;   // see ColsR2CPack::stagger_ns
 
     template <int LOG2L, int SEQ> __device__ __forceinline__ void prefetch(long seq0, long nseq) const {
         constexpr unsigned row_bytes = (unsigned)((1u << LOG2L) * sizeof(cplx<T>));
@@ -1748,7 +1503,6 @@ struct EpilogueDesc {
     int nbins;
     int use_tma;           // POWER: write the direct cells with TMA tensor stores (tmap describes out as [rows][W] float)
     int tma_box_rows;      // rows per TMA box (<= 256, divides Ny/2 so a box never straddles the fftshift wrap)
-    int l2_hints;          // 1: evict-first tile loads / evict-last row-segment stores
     const void* fix_ag;    // row-line detrend completion (see ColsFused::ag / wj); nullptr = none
     const void* fix_wj;
     int lut_symmetric;     // bins: lut[-ky][-kx] == lut[ky][kx] for every cell (true for radial bins): mirror cells reuse the bin
@@ -1832,7 +1586,7 @@ template <typename T, int MODE> struct ColsFused {
 #pragma unroll
         for (int q = 0; q < (1 << LOGE); ++q) {
             if constexpr (V == 2 && sizeof(T) == 4) {
-                float4 x = d.l2_hints ? ld16_evict_first(p + q * (NT * C)) : *reinterpret_cast<const float4*>(p + q * (NT * C));
+                float4 x = *reinterpret_cast<const float4*>(p + q * (NT * C));
                 v[0][q] = mk<T>(x.x, x.y);
                 v[V - 1][q] = mk<T>(x.z, x.w);
             } else {
@@ -2026,12 +1780,7 @@ template <typename T, int MODE> struct ColsFused {
                     Vec vv_;
 #pragma unroll
                     for (int c = 0; c < C; ++c) vv_.e[c] = q[c];
-                    if constexpr (sizeof(Vec) == 16) {
-                        if (d.l2_hints) st16_evict_last(rowd, *reinterpret_cast<const float4*>(&vv_));
-                        else *reinterpret_cast<Vec*>(rowd) = vv_;
-                    } else {
-                        *reinterpret_cast<Vec*>(rowd) = vv_;
-                    }
+                    *reinterpret_cast<Vec*>(rowd) = vv_;
                 } else {
 #pragma unroll
                     for (int c = 0; c < C; ++c) if (kx0 + c <= M) outb[(long)oy * W + ((kx0 + c + sx) & (Nx - 1))] = q[c];
@@ -2216,6 +1965,144 @@ cols_bins_kernel(const __grid_constant__ ColsFused<float, EPI_BINS_POWER> io, co
             }
         }
         __syncthreads();
+    }
+}
+
+// =============================================================================================
+// Pass 2 of the columns-first order with the radial-bin epilogue of the isotropic power spectrum (BASELINE config 4;
+// xrft/xrft.py:895-906, 948-1010): rows ky in [0, Ny/2] of the half spectrum are transformed along x exactly like
+// rows_kernel<RowsC2CPower>, but |F|^2 never leaves the SM -- it is summed into the plane's radial bins.
+//
+// No floating-point shared-memory atomics (they compile to compare-and-swap loops and serialise when neighbouring rows hit
+// the same bin).  Instead the mapping from cells to bins is made STATIC per CTA: a launch covers `rows` consecutive
+// half-spectrum rows of every plane starting at ky0 (rows % SEQ == 0, or rows == 1 for the Nyquist row), the grid is a
+// multiple of the rows / SEQ row groups of a plane, so a CTA meets the same rows of every plane it processes.  Once per
+// launch each thread looks up the bins of its E cells in the host-built LUT and the CTA counting-sorts its cells by bin
+// (native integer atomics): every cell gets a fixed slot `pos` in a staging array ordered by bin, every bin a fixed
+// segment.  Per tile: each thread drops its E values at their slots, one barrier, then one thread per segment adds its
+// contiguous run in fp32 and issues ONE fp64 atomic to the plane's bins.  The mirror image (-ky, -kx) of a cell shares
+// its bin (radial bins): rows 0 < ky < Ny/2 count twice, rows 0 and Ny/2 (which hold both signs of kx) once.
+// rows == 1: the SEQ row slots of a CTA are the same row (ky0) of SEQ consecutive planes; segments are per (slot, bin).
+// =============================================================================================
+struct RowsBins {
+    RowsC2CPower<float> base;   // in, logNy, H, shifts, scale, column-line completion tables (out unused)
+    const int* lut;             // int32 [Ny][Nx], bin of each OUTPUT cell (negative = skip)
+    double* bins;               // [plane][nbins], accumulated
+    int nbins;
+    int ky0, rows;              // half-spectrum rows [ky0, ky0 + rows) of every plane
+    long nplanes;
+};
+template <int LOG2L, int LOGE, int SEQ>
+__global__ void __launch_bounds__((1 << (LOG2L - LOGE)) * SEQ, min_blocks_for((1 << (LOG2L - LOGE)) * SEQ))
+rows_bins_kernel(RowsBins io, const float2* __restrict__ tw) {
+    using T = float;
+    using G_ = Geometry<LOG2L, LOGE>;
+    constexpr int E = G_::E, NT = G_::NT, NTHR = NT * SEQ, Nx = 1 << LOG2L;
+    constexpr int R = 1 << G_::LOGR_LAST, G = E / R;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx<T>* smem = reinterpret_cast<cplx<T>*>(smem_raw);
+    float* stage = reinterpret_cast<float*>(smem_raw);                               // aliases the exchange buffer
+    int2* segtab = reinterpret_cast<int2*>(smem_raw + (size_t)SEQ * G_::LPAD * sizeof(cplx<T>));   // (start, count) per segment
+    const int s = threadIdx.x / NT, u = threadIdx.x % NT;
+    cplx<T>* sm = smem + s * G_::LPAD;
+    const bool per_slot = io.rows == 1;              // Nyquist-row launch: one plane per row slot
+    const int P = per_slot ? SEQ : 1;
+    const int nseg = P * io.nbins;
+    const int groups = per_slot ? 1 : io.rows / SEQ;  // row groups per plane; gridDim.x % groups == 0
+    const int g0 = (int)(blockIdx.x % (unsigned)groups);
+    const int ky = io.ky0 + (per_slot ? 0 : g0 * SEQ + s);
+    const int Ny = 1 << io.base.logNy;
+    const int sy = io.base.shift_y ? Ny / 2 : 0, sx = io.base.shift_x ? Nx / 2 : 0;
+    // ---- once per launch: bins of this thread's cells, counting sort of the CTA's cells by (slot, bin)
+    int* cnt = reinterpret_cast<int*>(segtab);        // nseg counters, then turned into (start, count)
+    for (int i = threadIdx.x; i < 2 * nseg; i += NTHR) cnt[i] = 0;
+    __syncthreads();
+    unsigned short key[E], rank[E];
+    {
+        const int* lrow = io.lut + (long)((ky + sy) & (Ny - 1)) * Nx;
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+#pragma unroll
+            for (int t = 0; t < R; ++t) {
+                const int kx = final_index<LOG2L, LOGE>(u, g, t);
+                const int b = __ldg(lrow + ((kx + sx) & (Nx - 1)));
+                const int i = g + t * G;
+                key[i] = 0xFFFFu; rank[i] = 0;
+                if (b >= 0 && b < io.nbins) {
+                    const int k = (per_slot ? s * io.nbins : 0) + b;
+                    key[i] = (unsigned short)k;
+                    rank[i] = (unsigned short)atomicAdd(cnt + k, 1);
+                }
+            }
+    }
+    __syncthreads();
+    // exclusive prefix sum of the counters (nseg <= 4096): one thread per run of consecutive segments
+    __shared__ int scan_part[32];
+    {
+        const int per = (nseg + NTHR - 1) / NTHR;
+        const int lo = threadIdx.x * per, hi = lo + per < nseg ? lo + per : nseg;
+        int local = 0;
+        for (int i = lo; i < hi; ++i) local += cnt[i];
+        int incl = local;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) { const int o = __shfl_up_sync(0xffffffffu, incl, off); if ((threadIdx.x & 31) >= off) incl += o; }
+        if ((threadIdx.x & 31) == 31) scan_part[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        int base = 0;
+        for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) base += scan_part[w];
+        int run = base + incl - local;
+        int counts[16];   // per <= 16 (nseg <= 4096, NTHR = 256)
+        for (int i = lo, j = 0; i < hi; ++i, ++j) counts[j] = cnt[i];
+        __syncthreads();
+        for (int i = lo, j = 0; i < hi; ++i, ++j) { segtab[i] = make_int2(run, counts[j]); run += counts[j]; }
+    }
+    __syncthreads();
+    unsigned short pos[E];
+#pragma unroll
+    for (int i = 0; i < E; ++i) pos[i] = key[i] == 0xFFFFu ? (unsigned short)0xFFFFu : (unsigned short)(segtab[key[i]].x + rank[i]);
+    const float mult = ((ky == 0 || 2 * ky == Ny) ? 1.f : 2.f) * io.base.scale;
+    // ---- tiles: mode A: plane = blockIdx.x / groups + k * (gridDim.x / groups); mode B: SEQ planes per tile
+    const long tiles_total = per_slot ? (io.nplanes + SEQ - 1) / SEQ : io.nplanes;
+    const long tstep = gridDim.x / groups;
+    long tile = blockIdx.x / groups;
+    auto seq_of = [&](long tl, bool& act) -> long {
+        const long plane = per_slot ? tl * SEQ + s : tl;
+        act = tl < tiles_total && plane < io.nplanes;
+        return plane * io.base.H + ky;
+    };
+    cplx<T> raw[E];
+    {
+        bool act; const long sq = seq_of(tile, act);
+        io.base.template fetch<LOG2L, LOGE>(sq, act, u, raw);
+    }
+    for (; tile < tiles_total; tile += tstep) {
+        bool act; const long sq = seq_of(tile, act);
+        cplx<T> v[1][E];
+        io.base.template prologue<LOG2L, LOGE>(sq, act, u, raw, v[0]);
+        block_fft<T, LOG2L, LOGE, 1, 1>(v, u, sm, 0, tw);
+        {   // the next tile's rows travel while this one is binned
+            bool actn; const long sqn = seq_of(tile + tstep, actn);
+            io.base.template fetch<LOG2L, LOGE>(sqn, actn, u, raw);
+        }
+        __syncthreads();   // every gather of the last exchange is done: the buffer becomes the staging array
+#pragma unroll
+        for (int i = 0; i < E; ++i) {
+            const cplx<T> f = v[0][i];
+            if (pos[i] != 0xFFFFu) stage[pos[i]] = (f.x * f.x + f.y * f.y) * mult;
+        }
+        __syncthreads();
+        for (int sg = threadIdx.x; sg < nseg; sg += NTHR) {
+            const int2 sc = segtab[sg];
+            if (sc.y == 0) continue;
+            const float* p = stage + sc.x;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            int j = 0;
+            for (; j + 4 <= sc.y; j += 4) { a0 += p[j]; a1 += p[j + 1]; a2 += p[j + 2]; a3 += p[j + 3]; }
+            for (; j < sc.y; ++j) a0 += p[j];
+            const long plane = per_slot ? tile * SEQ + sg / io.nbins : tile;
+            if (plane < io.nplanes) atomicAdd(io.bins + plane * (long)io.nbins + (per_slot ? sg % io.nbins : sg), (double)((a0 + a1) + (a2 + a3)));
+        }
+        __syncthreads();   // the staging array is scattered into again by the next transform
     }
 }
 

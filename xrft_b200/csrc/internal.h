@@ -31,39 +31,17 @@ template <typename T> inline int cols_tile_width(int log2L, bool two_fields) {
     return c;  // 0 => unsupported
 }
 
-// pass 1 of the columns-first order (ColsR2CPack): tile width in PACKED columns.  XRFTB_P1_NARROW=1 halves the default width
-// where the tensor-map fed kernel exists for it (two 256-thread CTAs per SM instead of one 512-thread CTA at 4096 rows)
-inline int p1_narrow_knob() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("XRFTB_P1_NARROW"); v = e ? atoi(e) : 0; }
-    return v;
-}
-// packed FP32x2 (FADD2 / FMUL2 / FFMA2) kernels of the z-mode chain: measured 4-7 % SLOWER than the scalar ones on B200
-// (profiles/README.md), so they are off unless XRFTB_F32X2=1
-inline bool f32x2_enabled() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("XRFTB_F32X2"); v = e ? atoi(e) : 0; }
-    return v != 0;
-}
-// A/B switch of the register-LUT radial-bin kernel (cols_bins_kernel); XRFTB_BINS_STATIC=0 selects the generic epilogue
-inline bool bins_static_enabled() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("XRFTB_BINS_STATIC"); v = e ? atoi(e) : 1; }
-    return v != 0;
-}
-template <typename T> inline int colsfirst_tile_width(int log2L) {
-    int c = cols_tile_width<T>(log2L, false);
-    if (sizeof(T) == 4 && p1_narrow_knob() && log2L >= 11 && c >= 4) c >>= 1;
-    return c;
-}
+// Chain-selection options (include/xrft_b200.h: xrftb_set_option / xrftb_get_option).  Each one names a kernel chain that
+// also serves other shapes or dtypes as the regular path, so every setting is a tested configuration, not an experiment.
+enum Option : int { OPT_COLS_FIRST = 0, OPT_ZPACK, OPT_ZTMA, OPT_COLS_ASYNC, OPT_ROWLINE, OPT_CROSS_Z, OPT_BINS_STATIC, OPT_COUNT };
+int option(Option o);
+inline bool bins_static_enabled() { return option(OPT_BINS_STATIC) != 0; }
+// pass 1 of the columns-first order (ColsR2CPack): tile width in PACKED columns
+template <typename T> inline int colsfirst_tile_width(int log2L) { return cols_tile_width<T>(log2L, false); }
 
 // the two-rows-per-thread row kernel (float32, blocked output) handles half lengths 2^7..2^12 with 2^(12 - log2M) row pairs
 // per CTA; the 2 * pairs rows of a CTA must be consecutive rows of one item
-inline bool rows2_eligible(int log2M, int logNy) {
-    static int v2 = -1;
-    if (v2 < 0) { const char* e = getenv("XRFTB_ROWS_V2"); v2 = e ? atoi(e) : 1; }
-    return v2 > 0 && log2M >= 7 && log2M <= 12 && logNy >= (12 - log2M) + 1;
-}
+inline bool rows2_eligible(int log2M, int logNy) { return log2M >= 7 && log2M <= 12 && logNy >= (12 - log2M) + 1; }
 
 template <typename T> int rows_c2c(const cplx<T>* in, cplx<T>* out, int log2L, long nseq, long in_stride, long out_stride,
                                    int inverse, T scale, cudaStream_t st);
@@ -73,6 +51,9 @@ template <typename T> int rows_c2r(const cplx<T>* in, long in_stride, T* out, lo
 template <typename T> int rows_c2c_power(const RowsC2CPower<T>& io, int log2L, long nseq, cudaStream_t st);
 template <typename T> int rows_z_power(RowsZPower<T> io, int log2M, long nseq, cudaStream_t st);
 template <typename T> int rows_z_cross(RowsZCross<T> io, int log2M, long nseq, int mode, cudaStream_t st);
+// pass 2 of the columns-first order with the radial-bin epilogue (float32); returns 1 when the shape is not covered
+int rows_bins(const RowsBins& io, int log2L, cudaStream_t st);
+bool rows_bins_shape_ok(int log2L, int ny);
 // half lengths the z-mode pass 2 is dispatched for (Nx = 1024 .. 4096: the sizes covered by the GPU parity tests; the
 // 2^12 instantiation exists but stays off until it has been through them)
 inline bool rows_z_supported(int log2M) { return log2M >= 9 && log2M <= 11; }

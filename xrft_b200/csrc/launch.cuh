@@ -98,6 +98,34 @@ static int launch_rows2c_power(const RowsC2CPower<T>& io, long nseq, cudaStream_
     return check_launch("rows2c_power_kernel");
 }
 
+// pass 2 + radial bins (rows_bins_kernel).  Returns 1 when the launch shape does not fit (caller falls back).
+template <int LOG2L, int SEQ>
+static int launch_rows_bins(const RowsBins& io, cudaStream_t st) {
+    constexpr int LOGE = cmin(TypeCfg<float>::LOGE, LOG2L);
+    using G_ = Geometry<LOG2L, LOGE>;
+    auto kern = rows_bins_kernel<LOG2L, LOGE, SEQ>;
+    constexpr int threads = G_::NT * SEQ;
+    const int P = io.rows == 1 ? SEQ : 1;
+    const int nseg = P * io.nbins;
+    if (nseg > 4096 || (io.rows != 1 && io.rows % SEQ != 0)) return 1;
+    constexpr size_t smem_x = (size_t)SEQ * G_::LPAD * sizeof(float2);
+    static_assert(smem_x >= (size_t)SEQ * (1 << LOG2L) * sizeof(float), "the staging array fits the exchange buffer");
+    constexpr size_t smem = smem_x + 4096 * sizeof(int2);
+    static DevOcc occ_;
+    int occ = 0;
+    if (int rc = prepare_kernel(kern, threads, smem, &occ_, &occ)) return rc;
+    const float2* tw = twiddle_fft<float>(LOG2L);
+    if (!tw) return -3;
+    const long groups = io.rows == 1 ? 1 : io.rows / SEQ;
+    const long tiles = io.rows == 1 ? (io.nplanes + SEQ - 1) / SEQ : io.nplanes;
+    long grid = (long)sm_count() * occ;
+    if (grid > tiles * groups) grid = tiles * groups;
+    grid -= grid % groups;
+    if (grid < groups) return 1;
+    kern<<<(unsigned)grid, threads, smem, st>>>(io, tw);
+    return check_launch("rows_bins_kernel");
+}
+
 // pass 2 on packed column spectra (rowsz_power_kernel): ROWS half-spectrum rows per CTA, two M-point sequences per thread
 template <typename T, int LOG2M, int ROWS>
 static int launch_rowsz_power(const RowsZPower<T>& io, long nseq, cudaStream_t st) {
@@ -138,27 +166,6 @@ static int launch_rowszx(const RowsZCross<float>& io, long nseq, cudaStream_t st
     if (grid < 1) return 0;
     kern<<<(unsigned)grid, threads, smem, st>>>(io, tw, nseq);
     return check_launch("rowszx_kernel");
-}
-
-// packed (FP32x2) variant of launch_rowsz_power (float32)
-template <int LOG2M, int ROWS>
-static int launch_rowszp_power(const RowsZPower<float>& io, long nseq, cudaStream_t st) {
-    constexpr int LOGE = cmin(TypeCfg<float>::LOGE, LOG2M);
-    using G_ = Geometry<LOG2M, LOGE>;
-    auto kern = rowszp_power_kernel<LOG2M, LOGE, ROWS>;
-    constexpr int threads = G_::NT * ROWS;
-    constexpr size_t smem = (size_t)ROWS * (G_::LPAD + 4) * sizeof(float4) + (size_t)(1 << LOG2M) * sizeof(float2);
-    static DevOcc occ_;
-    int occ = 0;
-    if (int rc = prepare_kernel(kern, threads, smem, &occ_, &occ)) return rc;
-    const float2* tw = twiddle_fft<float>(LOG2M);
-    if (!tw) return -3;
-    long ngroups = (nseq + ROWS - 1) / ROWS;
-    long grid = (long)sm_count() * occ;
-    if (grid > ngroups) grid = ngroups;
-    if (grid < 1) return 0;
-    kern<<<(unsigned)grid, threads, smem, st>>>(io, tw, nseq);
-    return check_launch("rowszp_power_kernel");
 }
 
 template <typename T, int LOG2L, int C, class IO>
@@ -232,27 +239,6 @@ static int launch_cols_async(IO io, long ntiles, cudaStream_t st, size_t extra_s
     if (grid < 1) return 0;
     kern<<<(unsigned)grid, threads, smem, st>>>(io, tw, ntiles);
     return check_launch("cols_async_kernel");
-}
-
-// packed (FP32x2) pass 1 in z mode: same shared-memory plan as launch_cols_async
-template <int LOG2L, int C>
-static int launch_colszp(const ColsR2CPack<float>& io, long ntiles, cudaStream_t st) {
-    using IO = ColsR2CPack<float>;
-    constexpr int LOGE = cmin(TypeCfg<float>::LOGE, LOG2L);
-    using G_ = Geometry<LOG2L, LOGE>;
-    auto kern = colszp_kernel<LOG2L, LOGE, C>;
-    constexpr int threads = G_::NT * (C / 2);
-    constexpr size_t smem = (size_t)G_::LPAD * (C + C / 2) * sizeof(float2) + 16 + IO::kExtraSmemBytes;
-    static DevOcc occ_;
-    int occ = 0;
-    if (int rc = prepare_kernel(kern, threads, smem, &occ_, &occ)) return rc;
-    const float2* tw = twiddle_fft<float>(LOG2L);
-    if (!tw) return -3;
-    long grid = (long)sm_count() * occ;
-    if (grid > ntiles) grid = ntiles;
-    if (grid < 1) return 0;
-    kern<<<(unsigned)grid, threads, smem, st>>>(io, tw, ntiles);
-    return check_launch("colszp_kernel");
 }
 
 }  // namespace xrftb

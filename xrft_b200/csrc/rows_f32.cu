@@ -7,3 +7,22 @@ template int rows_c2c_power<float>(const RowsC2CPower<float>&, int, long, cudaSt
 template int rows_z_power<float>(RowsZPower<float>, int, long, cudaStream_t);
 template int rows_z_cross<float>(RowsZCross<float>, int, long, int, cudaStream_t);
 }
+
+namespace xrftb {
+// pass 2 of the columns-first order with the radial-bin epilogue (float32, Nx = 256 .. 2048); 1 = shape not covered
+int rows_bins(const RowsBins& io, int log2L, cudaStream_t st) {
+    switch (log2L) {
+#define Z(K) case K: return launch_rows_bins<K, rows_seq_generic<K, TypeCfg<float>::LOGE>()>(io, st);
+        Z(8) Z(9) Z(10) Z(11)
+#undef Z
+        default: break;
+    }
+    return 1;
+}
+bool rows_bins_shape_ok(int log2L, int ny) {
+    int seq = 0;
+    switch (log2L) { case 8: seq = rows_seq_generic<8, 4>(); break; case 9: seq = rows_seq_generic<9, 4>(); break;
+                     case 10: seq = rows_seq_generic<10, 4>(); break; case 11: seq = rows_seq_generic<11, 4>(); break; default: return false; }
+    return ny / 2 >= seq && (ny / 2) % seq == 0;
+}
+}  // namespace xrftb

@@ -42,17 +42,6 @@ int rows_r2c(RowsR2CFused<T> io, int log2M, long nseq, cudaStream_t st) {
         }
     }
     if (io.rowstats != nullptr) { set_error("rows_r2c: row-line detrend needs the two-rows-per-thread kernel"); return -2; }
-    // tuning knob (experiments): rows per CTA of the fused pass for the large sizes
-    static int seq_override = -1;
-    if (seq_override < 0) { const char* e = getenv("XRFTB_ROWS_SEQ"); seq_override = e ? atoi(e) : 0; }
-    if (seq_override > 0 && log2M >= 9 && log2M <= 12) {
-        switch (log2M * 10 + seq_override) {
-#define Y(K, S) case K * 10 + S: return launch_rows<T, K, S>(io, nseq, st);
-            Y(9, 1) Y(9, 2) Y(9, 4) Y(10, 1) Y(10, 2) Y(10, 4) Y(11, 1) Y(11, 2) Y(11, 4) Y(12, 1) Y(12, 2)
-#undef Y
-            default: break;
-        }
-    }
     switch (log2M) {
 #define X(K) case K: return launch_rows<T, K, rows_seq_fused<K, cmin(TypeCfg<T>::LOGE, K)>()>(io, nseq, st);
         XRFTB_ROWS_CASES(X)
@@ -67,17 +56,13 @@ int rows_r2c(RowsR2CFused<T> io, int log2M, long nseq, cudaStream_t st) {
 
 template <typename T>
 int rows_c2c_power(const RowsC2CPower<T>& io, int log2L, long nseq, cudaStream_t st) {
-    // float32: two rows per thread, PAIRS row pairs per 256-thread CTA (XRFTB_ROWS_V2=0 selects the one-row kernel)
+    // float32: two rows per thread, PAIRS row pairs per 256-thread CTA
     if constexpr (sizeof(T) == 4) {
-        static int v2 = -1;
-        if (v2 < 0) { const char* e = getenv("XRFTB_ROWS_V2"); v2 = e ? atoi(e) : 1; }
-        if (v2 > 0) {
-            switch (log2L) {
+        switch (log2L) {
 #define Z(K, P) case K: return launch_rows2c_power<T, K, P>(io, nseq, st);
-                Z(11, 2) Z(12, 1) Z(13, 1)   // measured: shorter rows are faster one row per thread
+            Z(11, 2) Z(12, 1) Z(13, 1)   // measured: shorter rows are faster one row per thread
 #undef Z
-                default: break;
-            }
+            default: break;
         }
     }
     switch (log2L) {
@@ -98,14 +83,6 @@ int rows_z_power(RowsZPower<T> io, int log2M, long nseq, cudaStream_t st) {
     if constexpr (sizeof(T) == 4) {
         io.tw2 = twiddle_fft<T>(log2M + 1);
         if (!io.tw2) return -3;
-        if (f32x2_enabled()) {   // packed FP32x2 butterflies (XRFTB_F32X2=0 selects the scalar kernel)
-            switch (log2M) {
-#define Z(K, P) case K: return launch_rowszp_power<K, P>(io, nseq, st);
-                Z(9, 8) Z(10, 4) Z(11, 2) Z(12, 1)
-#undef Z
-                default: break;
-            }
-        }
         switch (log2M) {
 #define Z(K, P) case K: return launch_rowsz_power<T, K, P>(io, nseq, st);
             Z(9, 8) Z(10, 4) Z(11, 2) Z(12, 1)
