@@ -94,6 +94,38 @@ size_t xrftb_fftn_workspace(int dtype, int kind, int ndim, const int64_t* shape,
 int xrftb_fftn(const void* in, void* out, void* work, size_t work_bytes, int dtype, int kind, int ndim,
                const int64_t* shape, int naxes, const int* axes, void* stream);
 
+/* ---- (S1) + neighbours: 2-D real transform with xrft.fft / xrft.ifft's elementwise steps folded into its passes -------
+ * One call == pad -> rfftn -> x phase ramps x prod(dx)        (forward: xrft.py:398-404, 462-472; padding.py:157-181), or
+ *             x phase ramps, ifftshift -> irfftn -> fftshift / ifftshift, / prod(df), unpad crop
+ *                                                               (inverse: xrft.py:574-621, 641-642; padding.py:425-446)
+ * over the two trailing axes of [batch][ny][nx] real <-> [batch][ny][nx/2+1] complex, numpy normalisation (inverse 1/(ny nx)).
+ *   forward (inverse = 0): `in` is real [batch][in_ny][in_nx] sitting at (in_off_y, in_off_x) inside a zero [ny][nx] grid that is
+ *     never materialised (in_ny = 0: `in` has the full shape); out = rfft2 * ramp_y[ky] * ramp_x[kx] * scale.
+ *   inverse (inverse = 1): transform row r reads input row (r + in_roll_y) % ny (sortby + ifftshift of xrft.ifft folded into
+ *     the loads) multiplied by ramp_y[that input row] * ramp_x[kx]; real result element (i, j) lands at ((i + out_roll_y) % ny,
+ *     (j + out_roll_x) % nx), multiplied by scale; only the out_ny x out_nx box at (out_off_y, out_off_x) of that rolled
+ *     result is stored, densely (out_ny = 0: everything).
+ * ramps are complex vectors of the transform dtype, nullable.  Power-of-two sizes (nx within the single-pass row limits, ny
+ * up to 2^26 by the four-step decomposition); other sizes return XRFTB_EUNSUPPORTED.  `in` is never modified. */
+typedef struct {
+    int dtype;
+    int inverse;
+    int64_t batch, ny, nx;
+    const void* in;
+    void* out;
+    int64_t in_ny, in_nx, in_off_y, in_off_x;
+    const void* ramp_y;
+    const void* ramp_x;
+    double scale;
+    int64_t in_roll_y;
+    int64_t out_roll_y, out_roll_x;
+    int64_t out_ny, out_nx, out_off_y, out_off_x;
+    void* work;
+    size_t work_bytes;
+} xrftb_fft2r_desc;
+size_t xrftb_fft2r_workspace(const xrftb_fft2r_desc* desc);
+int xrftb_fft2r(const xrftb_fft2r_desc* desc, void* stream);
+
 /* ---- (S2) detrend -------------------------------------------------------------------------------
  * Real input viewed as [batch][n0][n1][n2] (use 1 for unused leading dims).  `moments` receives
  * per item {S, S0, S1, S2}: the sum and the centred first moments sum((i_d - (n_d-1)/2) * x).
@@ -123,6 +155,14 @@ int xrftb_spectral_post(const void* in1, const void* in2, void* out, int dtype, 
  * (xrft.py:617-621, 641-642).  Out of place only. */
 int xrftb_roll_scale(const void* in, void* out, int dtype, int is_complex, int64_t batch, int64_t n0, int64_t n1, int64_t n2,
                      int64_t s0, int64_t s1, int64_t s2, double scale, void* stream);
+
+/* ---- xrft.pad (padding.py:157-181 -> DataArray.pad -> numpy.pad) on device-resident data ---------------
+ * out[ndim] = in surrounded by pad_before[a] / pad_after[a] cells on axis a (ndim <= 4; fold leading axes).  mode: 0 constant
+ * (`fill` points at one element, NULL = zeros), 1 edge, 2 reflect, 3 symmetric, 4 wrap (numpy semantics, reflect_type "even",
+ * pads wider than the array allowed).  elem_bytes 4 / 8 / 16 (float32; float64 or complex64; complex128).  unpad needs no
+ * kernel: it is a strided view of the result (padding.py:425-446). */
+int xrftb_pad(const void* in, void* out, int elem_bytes, int ndim, const int64_t* in_shape, const int64_t* pad_before,
+              const int64_t* pad_after, int mode, const void* fill, void* stream);
 
 /* ---- (S5) _binned_agg(func="sum") ---------------------------------------------------------------
  * array: real (is_complex = 0) or complex [batch][ncell]; lut: int32 [ncell], negative = masked

@@ -572,3 +572,52 @@ def test_cross_spectrum_and_phase_all_paths():
         assert d[np.abs(cs1.values) > 1e-3 * np.abs(cs1.values).max()].max() < 1e-4
         ref = O.cross_spectrum(lab(a), lab(b), **kw)
         assert relerr(cs.values, ref.data) < (1e-3 if dt == np.float32 else 1e-8)
+
+
+@pytest.mark.parametrize("mode", ["constant", "edge", "reflect", "symmetric", "wrap"])
+def test_pad_modes_on_device(mode):
+    """xrft.pad of device-resident data runs the CUDA pad kernel and equals numpy.pad (padding.py:157-181), incl. pads wider
+    than the array; the statistic modes fail loudly instead of leaving the device"""
+    import torch
+    rng = np.random.default_rng(70)
+    for dt in (np.float32, np.float64, np.complex128):
+        x = rng.standard_normal((3, 5, 7)).astype(dt)
+        da = DataArray(torch.from_numpy(x).cuda(), dims=["t", "y", "x"], coords={"t": np.arange(3.0), "y": np.arange(5) * 0.5, "x": np.arange(7) * 0.25})
+        kw = dict(constant_values=1.5) if mode == "constant" else {}
+        out = xrft.pad(da, {"x": (2, 9), "y": 4}, mode=mode, **kw)
+        assert isinstance(out.data, torch.Tensor) and out.data.is_cuda
+        np.testing.assert_array_equal(out.values, np.pad(x, ((0, 0), (4, 4), (2, 9)), mode=mode, **kw))
+        ref = O.pad(lab(DataArray(x, dims=["t", "y", "x"], coords={"t": np.arange(3.0), "y": np.arange(5) * 0.5, "x": np.arange(7) * 0.25})), {"x": (2, 9), "y": 4})
+        np.testing.assert_allclose(out["x"].values, ref.coords["x"])
+        np.testing.assert_array_equal(xrft.unpad(out).values, x)
+    with pytest.raises(NotImplementedError):
+        xrft.pad(da, {"x": 2}, mode="mean")
+
+
+def test_lazy_pad_fft_ifft_matches_materialised_path():
+    """xrft.pad of a CUDA tensor defers the zero padding; xrft.fft(real_dim) reads the unpadded array through load predicates
+    (xrftb_fft2r) and must equal the oracle on the materialised padding; xrft.ifft(real_dim) uses the fused inverse chain"""
+    import torch
+    rng = np.random.default_rng(71)
+    for dt, tol in ((np.float64, 1e-9), (np.float32, 1e-3)):
+        x = rng.standard_normal((2, 48, 96)).astype(dt)
+        c = {"t": np.arange(2.0), "y": np.arange(48) * 0.5 - 3.0, "x": np.arange(96) * 0.25 + 1.0}
+        da = DataArray(torch.from_numpy(x).cuda(), dims=["t", "y", "x"], coords=c)
+        padded = xrft.pad(da, y=8, x=16)
+        assert padded.lazy_pad is not None and padded.shape == (2, 64, 128)
+        ft = xrft.fft(padded, dim=["y", "x"], real_dim="x")
+        assert padded.lazy_pad is not None            # the transform did not materialise the padding
+        ref_p = O.pad(lab(DataArray(x, dims=["t", "y", "x"], coords=c)), {"y": 8, "x": 16})
+        ref = O.fft(ref_p, dim=["y", "x"], real_dim="x")
+        same(ft, ref, tol=tol)
+        np.testing.assert_array_equal(padded.values, ref_p.data)      # materialised on demand by the CUDA pad kernel
+        back = xrft.ifft(ft, dim=["freq_y", "freq_x"], real_dim="freq_x")
+        refb = O.ifft(ref, dim=["freq_y", "freq_x"], real_dim="freq_x")
+        same(back, refb, tol=tol, check_attrs=False)
+        un = xrft.unpad(back, {"y": 8, "x": 16})
+        assert relerr(un.values, x) < tol
+        # variants of the inverse: unshifted output, true_phase off, explicit lag
+        for kw in (dict(shift=False), dict(true_phase=False), dict(lag=[0.0, 0.0])):
+            b2 = xrft.ifft(ft, dim=["freq_y", "freq_x"], real_dim="freq_x", **kw)
+            r2 = O.ifft(ref, dim=["freq_y", "freq_x"], real_dim="freq_x", **kw)
+            same(b2, r2, tol=tol, check_attrs=False)

@@ -209,3 +209,41 @@ def test_fft_module_matches_numpy_fft_at_the_reference_call_sites():
     with pytest.raises(NotImplementedError):
         fftm.fftn(a32, s=(8, 8))
     np.testing.assert_array_equal(fftm.fftfreq(8, 0.5), np.fft.fftfreq(8, 0.5))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dt,ny,nx", [(np.float64, 64, 128), (np.float32, 256, 64), (np.float64, 16384, 32), (np.float32, 32768, 16), (np.float64, 8, 4096)])
+def test_fft2r_fused_forward_and_inverse(dt, ny, nx):
+    """xrftb_fft2r (pad predicate / ramps / rolls / crop folded into the passes of a 2-D real transform, single-pass and
+    four-step strided axis) against numpy: pad -> rfft2 -> x ramps x scale, and x ramps -> roll -> irfft2 -> roll -> crop"""
+    from xrft_b200 import backend as B
+    rng = np.random.default_rng(ny + nx)
+    tol = 1e-10 if dt == np.float64 else 2e-4
+    cdt = np.complex128 if dt == np.float64 else np.complex64
+    # ---- forward, padded input
+    py, px = (ny // 4, ny // 8), (nx // 4, nx // 2)
+    iny, inx = ny - sum(py), nx - sum(px)
+    x = rng.standard_normal((3, iny, inx)).astype(dt)
+    ry = np.exp(1j * rng.uniform(0, 6.28, ny)).astype(cdt); rx = np.exp(1j * rng.uniform(0, 6.28, nx // 2 + 1)).astype(cdt)
+    got = B.fft2r_forward(torch.from_numpy(x).cuda(), (py, px), torch.from_numpy(ry), torch.from_numpy(rx), 0.37).cpu().numpy()
+    xp = np.pad(x.astype(np.float64), ((0, 0), py, px))
+    ref = np.fft.rfft2(xp) * ry[None, :, None] * rx[None, None, :] * 0.37
+    assert got.shape == ref.shape and relerr(got, ref) < tol
+    # ---- forward, no padding, no ramps
+    got0 = B.fft2r_forward(torch.from_numpy(xp.astype(dt)).cuda(), None, None, None, 1.0).cpu().numpy()
+    assert relerr(got0, np.fft.rfft2(xp.astype(dt).astype(np.float64))) < tol
+    # ---- inverse with rolled rows, ramps, output rolls, scale and crop
+    f = (rng.standard_normal((2, ny, nx // 2 + 1)) + 1j * rng.standard_normal((2, ny, nx // 2 + 1))).astype(cdt)
+    roll_in, (sy, sx) = ny // 2 + 3, (5 % ny, (nx // 2 + 2) % nx)
+    got = B.fft2r_inverse(torch.from_numpy(f).cuda(), roll_in, torch.from_numpy(ry), torch.from_numpy(rx), (sy, sx), 1.7).cpu().numpy()
+    g = f.astype(np.complex128) * ry[None, :, None] * rx[None, None, :]
+    g = np.roll(g, -roll_in, axis=1)                       # transform row r reads input row (r + roll_in) % ny
+    full = np.roll(np.fft.irfft2(g, s=(ny, nx)), (sy, sx), axis=(1, 2)) * 1.7
+    assert relerr(got, full) < tol
+    crop = ((ny // 4, ny // 2), (2, nx - 6))
+    gotc = B.fft2r_inverse(torch.from_numpy(f).cuda(), roll_in, torch.from_numpy(ry), torch.from_numpy(rx), (sy, sx), 1.7, crop=crop).cpu().numpy()
+    assert relerr(gotc, full[:, crop[0][0]:crop[0][0] + crop[0][1], crop[1][0]:crop[1][0] + crop[1][1]]) < tol
+    # odd roll / odd crop offsets take the scalar store path
+    goto = B.fft2r_inverse(torch.from_numpy(f).cuda(), 0, None, None, (0, 3), 1.0, crop=((1, ny - 2), (1, nx - 3))).cpu().numpy()
+    fullo = np.roll(np.fft.irfft2(f.astype(np.complex128), s=(ny, nx)), 3, axis=2)
+    assert relerr(goto, fullo[:, 1:ny - 1, 1:nx - 2]) < tol

@@ -24,10 +24,13 @@ EXPORTS = [
     "xrftb_spectrum2d_last_path",
     "xrftb_fftn_workspace",
     "xrftb_fftn",
+    "xrftb_fft2r_workspace",
+    "xrftb_fft2r",
     "xrftb_moments",
     "xrftb_detrend_window",
     "xrftb_spectral_post",
     "xrftb_roll_scale",
+    "xrftb_pad",
     "xrftb_binned_sum",
     "xrftb_spectrum2d_workspace",
     "xrftb_spectrum2d",
@@ -73,6 +76,18 @@ class Spectrum2dDesc(C.Structure):
     ]
 
 
+class Fft2rDesc(C.Structure):
+    _fields_ = [
+        ("dtype", C.c_int), ("inverse", C.c_int), ("batch", C.c_int64), ("ny", C.c_int64), ("nx", C.c_int64),
+        ("in_", C.c_void_p), ("out", C.c_void_p),
+        ("in_ny", C.c_int64), ("in_nx", C.c_int64), ("in_off_y", C.c_int64), ("in_off_x", C.c_int64),
+        ("ramp_y", C.c_void_p), ("ramp_x", C.c_void_p), ("scale", C.c_double),
+        ("in_roll_y", C.c_int64), ("out_roll_y", C.c_int64), ("out_roll_x", C.c_int64),
+        ("out_ny", C.c_int64), ("out_nx", C.c_int64), ("out_off_y", C.c_int64), ("out_off_x", C.c_int64),
+        ("work", C.c_void_p), ("work_bytes", C.c_size_t),
+    ]
+
+
 _lib = None
 
 
@@ -107,6 +122,12 @@ def load():
     lib.xrftb_spectral_post.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int,
                                         C.c_int, ip, C.POINTER(vp), vp, C.c_double, vp]
     lib.xrftb_roll_scale.argtypes = [vp, vp, C.c_int, C.c_int] + [C.c_int64] * 7 + [C.c_double, vp]
+    lib.xrftb_fft2r_workspace.restype = C.c_size_t
+    lib.xrftb_fft2r_workspace.argtypes = [C.POINTER(Fft2rDesc)]
+    lib.xrftb_fft2r.restype = C.c_int
+    lib.xrftb_fft2r.argtypes = [C.POINTER(Fft2rDesc), vp]
+    lib.xrftb_pad.argtypes = [vp, vp, C.c_int, C.c_int, i64p, i64p, i64p, C.c_int, vp, vp]
+    lib.xrftb_pad.restype = C.c_int
     lib.xrftb_binned_sum.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int, vp]
     lib.xrftb_spectrum2d_workspace.restype = C.c_size_t
     lib.xrftb_spectrum2d_workspace.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64]
@@ -123,7 +144,8 @@ def load():
     for name in ["xrftb_comm_unique_id", "xrftb_comm_init", "xrftb_comm_destroy", "xrftb_allreduce_bins"]:
         getattr(lib, name).restype = C.c_int
     for name in ["xrftb_device_info", "xrftb_fftn", "xrftb_moments", "xrftb_detrend_window", "xrftb_spectral_post",
-                 "xrftb_binned_sum", "xrftb_spectrum2d", "xrftb_roll_scale"]:
+                 "xrftb_pad",
+    "xrftb_binned_sum", "xrftb_spectrum2d", "xrftb_roll_scale"]:
         getattr(lib, name).restype = C.c_int
     _lib = lib
     return lib

@@ -27,7 +27,7 @@ import os
 import numpy as np
 import scipy.signal as sps
 
-from .dataarray import DataArray, Coordinates, from_any, either_dict_or_kwargs, _is_torch
+from .dataarray import DataArray, Coordinates, LazyPad, from_any, either_dict_or_kwargs, _is_torch
 from . import _lib as L
 
 __all__ = [
@@ -211,7 +211,7 @@ def _is_pow2(n):
 
 
 def _spectral_core(x1, x2, ntrans, mode, *, detrend=None, windows=None, keep_half=False, shift=None, ramps=None,
-                   weight=None, scale=1.0, lut=None, nbins=0, with_phase=False):
+                   weight=None, scale=1.0, lut=None, nbins=0, with_phase=False, pad2=None):
     """Transform the last `ntrans` axes of device tensor(s) x1 (,x2) and apply the epilogue.
 
     Picks the fused 2-D real kernel chain when it applies, otherwise composes
@@ -226,9 +226,19 @@ def _spectral_core(x1, x2, ntrans, mode, *, detrend=None, windows=None, keep_hal
     wins = list(windows) if windows is not None else [None] * ntrans
     two = x2 is not None
     is_real = not x1.is_complex()
-    shape = x1.shape
-    bins_mode = mode in (L.EPI_BINS_POWER, L.EPI_BINS_CROSS)
     tt = lambda v: torch.from_numpy(np.ascontiguousarray(v)) if isinstance(v, np.ndarray) else v
+    bins_mode = mode in (L.EPI_BINS_POWER, L.EPI_BINS_CROSS)
+    # ---- real_dim transform without detrend / window whose input is a deferred zero padding, or whose size the fused spectrum
+    #      chain below does not cover: pad predicate + R2C + ramps + scale in one chain of passes (xrftb_fft2r)
+    if (is_real and not two and ntrans == 2 and keep_half and mode == L.EPI_COMPLEX and det == 0 and all(w is None for w in wins)
+            and weight is None and not any(shift)):
+        pny = x1.shape[-2] + (sum(pad2[0]) if pad2 else 0)
+        pnx = x1.shape[-1] + (sum(pad2[1]) if pad2 else 0)
+        if (pad2 is not None or not B.spectrum2d_supported(pny, pnx, x1.dtype, False)) and B.fft2r_supported(pny, pnx, x1.dtype):
+            return B.fft2r_forward(x1, pad2, tt(ramps[0]), tt(ramps[1]), scale)
+    if pad2 is not None:   # no fused chain for this shape: carry the padding out
+        x1 = B.pad(x1, [(0, 0)] * (x1.ndim - 2) + [pad2[0], pad2[1]], "constant", 0)
+    shape = x1.shape
 
     # ---- fused path: real 2-D, power-of-two sizes
     if (is_real and ntrans == 2 and B.spectrum2d_supported(shape[-2], shape[-1], x1.dtype, two)
@@ -469,7 +479,14 @@ def _run_forward(P, das, mode, detrend, window, scale, ramps=None, weight=None, 
         return res.numpy() if out is None or not _is_torch(out) else res
     xs = []
     inv = None
-    for da, pl in zip(das, plans):
+    pad2 = None
+    lp = das[0].lazy_pad if len(das) == 1 else None
+    if (lp is not None and trailing and ntrans == 2 and real_dim is not None and mode == L.EPI_COMPLEX and detrend is None and window is None
+            and not any_reversed and all(w == (0, 0) for w in lp.widths[:-2])):
+        # xrft.pad -> xrft.fft(real_dim=...): the zero padding stays deferred, the transform reads the unpadded array
+        pad2 = (lp.widths[-2], lp.widths[-1])
+        xs.append(lp.base)
+    for da, pl in zip(das if pad2 is None else [], plans):
         t = _device_tensor(da.data)
         t, inv = _to_last(t, P["axis_num"])
         if pl["reversed_dims"]:   # each array by ITS OWN coordinate orientation (xrft.py:436-441)
@@ -483,7 +500,7 @@ def _run_forward(P, das, mode, detrend, window, scale, ramps=None, weight=None, 
         raise ValueError("real_dim requires real input data")
     res = _spectral_core(xs[0], xs[1] if len(xs) == 2 else None, ntrans, mode, detrend=detrend, windows=wins,
                          keep_half=real_dim is not None, shift=[P["shift"]] * ntrans if real_dim is None else [False] * ntrans,
-                         ramps=ramps, weight=weight, scale=scale, lut=lut, nbins=nbins, with_phase=with_phase)
+                         ramps=ramps, weight=weight, scale=scale, lut=lut, nbins=nbins, with_phase=with_phase, pad2=pad2)
     if with_phase:
         res = tuple(r.permute(*inv) if inv is not None else r for r in res)
         return tuple(r.cpu().numpy() for r in res) if host_in else res
@@ -595,28 +612,10 @@ def ifft(daft, spacing_tol=1e-3, dim=None, real_dim=None, shift=True, true_phase
     ntrans = len(dim)
     if ntrans > 3:
         raise NotImplementedError("transforms over more than 3 dimensions are not supported")
-    # sort + ramp + ifftshift of the input: data movement (gather) + one per-axis complex vector
-    for i, d in enumerate(dim):
-        ax = t.ndim - ntrans + i
-        order = orders[d]
-        if not np.array_equal(order, np.arange(order.size)):
-            t = t.index_select(ax, torch.as_tensor(order, device=t.device))
-    ramps = []
-    shifts = []
-    for i, d in enumerate(dim):
-        r = in_ramps[d][orders[d]] if true_phase else None
-        ramps.append(r)
-        shifts.append(2 if d != real_dim else 0)  # ifftshift on the non-real axes (xrft.py:608-614)
-    kin = list(t.shape[-ntrans:])
-    t = B.spectral_post(t, None, L.EPI_COMPLEX, ntrans, kin[-1], hermitian=False, keep_half=False, shift=shifts,
-                        ramps=[torch.from_numpy(np.ascontiguousarray(r)) if r is not None else None for r in ramps],
-                        weight=None, scale=1.0)
-    axes = list(range(t.ndim - ntrans, t.ndim))
-    f = B.ifftn(t, axes) if real_dim is None else B.irfftn(t, axes)
     k = _ifreq(N, delta_x, real_dim, shift)
+    n_outs = [kk.size for kk in k]
     out_shifts = []
-    for i in range(ntrans):
-        n_out = f.shape[f.ndim - ntrans + i]
+    for n_out in n_outs:
         s = 0
         if not true_phase:
             s += n_out - n_out // 2      # ifftshift  (xrft.py:617-618)
@@ -625,7 +624,38 @@ def ifft(daft, spacing_tol=1e-3, dim=None, real_dim=None, shift=True, true_phase
         out_shifts.append(s % n_out)
     spacings = [kk[1] - kk[0] for kk in k]
     scale = 1.0 / float(np.prod([float(s) for s in spacings])) if true_amplitude else 1.0
-    f = B.roll_scale(f, ntrans, out_shifts, scale)
+    f = None
+    if real_dim is not None and ntrans == 2:
+        # one chain of passes (xrftb_fft2r): sortby + ifftshift of the strided axis are a cyclic roll of its rows (folded into
+        # the loads together with the phase ramps); output shifts and 1 / prod(df) ride on the stores
+        ny_ = t.shape[-2]
+        oy_, ox_ = orders[dim[0]], orders[dim[1]]
+        s0 = int(oy_[0])
+        if (np.array_equal(oy_, (np.arange(ny_) + s0) % ny_) and np.array_equal(ox_, np.arange(ox_.size))
+                and B.fft2r_supported(ny_, n_outs[1], torch.float32 if t.dtype == torch.complex64 else torch.float64)):
+            tr = lambda v: torch.from_numpy(np.ascontiguousarray(v)) if v is not None else None
+            f = B.fft2r_inverse(t, (ny_ // 2 + s0) % ny_, tr(in_ramps[dim[0]]) if true_phase else None,
+                                tr(in_ramps[dim[1]]) if true_phase else None, out_shifts, scale)
+    if f is None:
+        # sort + ramp + ifftshift of the input: data movement (gather) + one per-axis complex vector
+        for i, d in enumerate(dim):
+            ax = t.ndim - ntrans + i
+            order = orders[d]
+            if not np.array_equal(order, np.arange(order.size)):
+                t = t.index_select(ax, torch.as_tensor(order, device=t.device))
+        ramps = []
+        shifts = []
+        for i, d in enumerate(dim):
+            r = in_ramps[d][orders[d]] if true_phase else None
+            ramps.append(r)
+            shifts.append(2 if d != real_dim else 0)  # ifftshift on the non-real axes (xrft.py:608-614)
+        kin = list(t.shape[-ntrans:])
+        t = B.spectral_post(t, None, L.EPI_COMPLEX, ntrans, kin[-1], hermitian=False, keep_half=False, shift=shifts,
+                            ramps=[torch.from_numpy(np.ascontiguousarray(r)) if r is not None else None for r in ramps],
+                            weight=None, scale=1.0)
+        axes = list(range(t.ndim - ntrans, t.ndim))
+        f = B.ifftn(t, axes) if real_dim is None else B.irfftn(t, axes)
+        f = B.roll_scale(f, ntrans, out_shifts, scale)
     if inv is not None:
         f = f.permute(*inv)
     if host_in:
@@ -1017,20 +1047,29 @@ def pad(da, pad_width=None, mode="constant", stat_length=None, constant_values=0
     if bad_coords:
         bad = "'" + "', '".join(bad_coords) + "'"
         raise ValueError("Please, drop the following coordinates from the passed DataArray " + f"before trying to pad it: {bad}.")
-    torch = _torch()
-    if mode == "constant" and _is_torch(da.data) and da.data.is_cuda and np.isscalar(constant_values):
-        # device-resident data: zero/constant pad stays on the device (pure data movement)
-        flat = []
-        for d in reversed(da.dims):
+    if _is_torch(da.data) and da.data.is_cuda:
+        # device-resident data is padded on the device (xrftb_pad): constant / edge / reflect / symmetric / wrap.  The statistic
+        # modes of numpy.pad (mean, median, minimum, maximum, linear_ramp, empty) have no device kernel and fail loudly
+        from . import backend as B
+        if mode not in B.PAD_MODES or stat_length is not None or end_values is not None or reflect_type not in (None, "even"):
+            raise NotImplementedError(
+                f"pad(mode={mode!r}, stat_length={stat_length}, end_values={end_values}, reflect_type={reflect_type}) is not available for "
+                f"device-resident data; supported modes: {sorted(B.PAD_MODES)} (reflect_type='even')")
+        if mode == "constant" and not np.isscalar(constant_values):
+            raise NotImplementedError("pad: per-axis constant_values are not available for device-resident data")
+        widths = []
+        for d in da.dims:
             w = pad_width.get(d, 0)
-            w = (w, w) if isinstance(w, (int, np.integer)) else tuple(w)
-            flat += [int(w[0]), int(w[1])]
-        data = torch.nn.functional.pad(da.data, flat, mode="constant", value=float(constant_values))
+            widths.append((int(w), int(w)) if isinstance(w, (int, np.integer)) else (int(w[0]), int(w[1])))
+        if mode == "constant" and constant_values == 0 and da.data.dtype in (_torch().float32, _torch().float64):
+            data = LazyPad(da.data.contiguous(), widths)   # deferred: xrft.fft reads the unpadded array through load predicates
+        else:
+            data = B.pad(da.data, widths, mode, constant_values if mode == "constant" else 0)
         padded = da._replace(data=data)
         for d in pad_width:
             if d in padded._coords:
                 OrderedDict.__delitem__(padded._coords, d)
-    else:
+    else:   # host-resident data stays on the host: numpy.pad, as in the reference (pure data movement where the data lives)
         padded = da.pad(pad_width, mode, stat_length, constant_values, end_values, reflect_type)
     for d in pad_width:
         cvals = da[d].values

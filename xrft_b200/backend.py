@@ -9,7 +9,7 @@ CUDA or the library is unavailable.
 from __future__ import annotations
 
 import ctypes as C
-from typing import Optional, Sequence
+from typing import Optional, Sequence, Tuple
 
 import torch
 
@@ -123,6 +123,85 @@ def irfftn(x: torch.Tensor, axes=None) -> torch.Tensor:
 
 
 # ---------------------------------------------------------------------------------------------
+# 2-D real transform with the neighbouring elementwise steps folded in (xrftb_fft2r)
+# ---------------------------------------------------------------------------------------------
+def fft2r_supported(ny: int, nx: int, dtype) -> bool:
+    """power-of-two sizes within the fused passes of xrftb_fft2r (asked of the library: workspace query)"""
+    if dtype not in _REAL or ny < 2 or nx < 4 or (ny & (ny - 1)) or (nx & (nx - 1)):
+        return False
+    d = L.Fft2rDesc()
+    d.dtype, d.inverse, d.batch, d.ny, d.nx = _REAL[dtype], 0, 1, ny, nx
+    return require_cuda().xrftb_fft2r_workspace(C.byref(d)) > 0
+
+
+def _fft2r_call(d: "L.Fft2rDesc", dev):
+    lib = require_cuda()
+    with torch.cuda.device(dev):
+        wb = lib.xrftb_fft2r_workspace(C.byref(d))
+        if wb == 0:
+            raise NotImplementedError("xrftb_fft2r: size not covered")
+        work = _workspace(dev, wb)
+        d.work, d.work_bytes = work.data_ptr(), work.numel()
+        rc = lib.xrftb_fft2r(C.byref(d), _stream())
+    L.check(rc, "xrftb_fft2r")
+
+
+def fft2r_forward(x: torch.Tensor, pad2, ramp_y, ramp_x, scale: float) -> torch.Tensor:
+    """rfft2 over the last two axes of real x, optionally of x zero-padded by pad2 = ((before_y, after_y), (before_x, after_x))
+    without materialising the padding; times ramp_y[ky] ramp_x[kx] scale."""
+    x = _dev(x)
+    rdt, cdt = x.dtype, _TO_CPLX[x.dtype]
+    iny, inx = x.shape[-2], x.shape[-1]
+    (by, ay), (bx, ax) = pad2 if pad2 is not None else ((0, 0), (0, 0))
+    ny, nx = iny + by + ay, inx + bx + ax
+    lead = list(x.shape[:-2])
+    batch = 1
+    for s_ in lead:
+        batch *= s_
+    out = torch.empty(lead + [ny, nx // 2 + 1], dtype=cdt, device=x.device)
+    ry = ramp_y.to(device=x.device, dtype=cdt).contiguous() if ramp_y is not None else None
+    rx = ramp_x.to(device=x.device, dtype=cdt).contiguous() if ramp_x is not None else None
+    d = L.Fft2rDesc()
+    d.dtype, d.inverse, d.batch, d.ny, d.nx = _REAL[rdt], 0, batch, ny, nx
+    d.in_, d.out = x.data_ptr(), out.data_ptr()
+    if pad2 is not None:
+        d.in_ny, d.in_nx, d.in_off_y, d.in_off_x = iny, inx, by, bx
+    d.ramp_y = ry.data_ptr() if ry is not None else None
+    d.ramp_x = rx.data_ptr() if rx is not None else None
+    d.scale = float(scale)
+    _fft2r_call(d, x.device)
+    return out
+
+
+def fft2r_inverse(f: torch.Tensor, in_roll_y: int, ramp_y, ramp_x, out_roll, scale: float, crop=None) -> torch.Tensor:
+    """irfft2 over the last two axes of the half spectrum f [.., ny, nx/2+1]: transform row r reads f[(r + in_roll_y) % ny]
+    times ramp_y[that row] ramp_x[kx]; the real result is rolled by out_roll = (sy, sx), scaled, and optionally cropped to
+    crop = ((off_y, n_y), (off_x, n_x)) of the rolled result."""
+    f = _dev(f)
+    cdt, rdt = f.dtype, _TO_REAL[f.dtype]
+    ny, nx = f.shape[-2], 2 * (f.shape[-1] - 1)
+    lead = list(f.shape[:-2])
+    batch = 1
+    for s_ in lead:
+        batch *= s_
+    (oy, cy), (ox, cx) = crop if crop is not None else ((0, ny), (0, nx))
+    out = torch.empty(lead + [cy, cx], dtype=rdt, device=f.device)
+    ry = ramp_y.to(device=f.device, dtype=cdt).contiguous() if ramp_y is not None else None
+    rx = ramp_x.to(device=f.device, dtype=cdt).contiguous() if ramp_x is not None else None
+    d = L.Fft2rDesc()
+    d.dtype, d.inverse, d.batch, d.ny, d.nx = _CPLX[cdt], 1, batch, ny, nx
+    d.in_, d.out = f.data_ptr(), out.data_ptr()
+    d.ramp_y = ry.data_ptr() if ry is not None else None
+    d.ramp_x = rx.data_ptr() if rx is not None else None
+    d.scale = float(scale)
+    d.in_roll_y, d.out_roll_y, d.out_roll_x = int(in_roll_y), int(out_roll[0]), int(out_roll[1])
+    if crop is not None:
+        d.out_ny, d.out_nx, d.out_off_y, d.out_off_x = cy, cx, oy, ox
+    _fft2r_call(d, f.device)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
 # (S2/S3) detrend + window
 # ---------------------------------------------------------------------------------------------
 def _view4(x: torch.Tensor, ntrail: int):
@@ -223,6 +302,45 @@ def roll_scale(x: torch.Tensor, ntrail: int, shifts: Sequence[int], scale: float
         rc = lib.xrftb_roll_scale(_ptr(x), _ptr(out), dt, 1 if is_c else 0, batch, core[0], core[1], core[2], sh[0], sh[1], sh[2],
                                   float(scale), _stream())
     L.check(rc, "xrftb_roll_scale")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# pad (device-resident data)
+# ---------------------------------------------------------------------------------------------
+PAD_MODES = {"constant": 0, "edge": 1, "reflect": 2, "symmetric": 3, "wrap": 4}
+
+
+def pad(x: torch.Tensor, widths: Sequence[Tuple[int, int]], mode: str = "constant", value=0) -> torch.Tensor:
+    """numpy.pad(x, widths, mode) on the device (xrftb_pad); widths = one (before, after) per axis."""
+    lib = require_cuda()
+    x = _dev(x)
+    if mode not in PAD_MODES:
+        raise NotImplementedError(f"pad mode {mode!r} is not available for device-resident data (supported: {sorted(PAD_MODES)})")
+    if x.dtype not in (torch.float32, torch.float64, torch.complex64, torch.complex128):
+        raise TypeError(f"pad: unsupported dtype {x.dtype}")
+    widths = [(int(a), int(b)) for a, b in widths]
+    # fold: axes without padding merge with their neighbours so that at most 4 remain
+    shape, wl = list(x.shape), list(widths)
+    i = 0
+    while len(shape) > 1 and i < len(shape) - 1:
+        if wl[i] == (0, 0) and wl[i + 1] == (0, 0):
+            shape[i:i + 2] = [shape[i] * shape[i + 1]]
+            wl[i:i + 2] = [(0, 0)]
+        else:
+            i += 1
+    if len(shape) > 4:
+        # leading unpadded axis is a pure batch: fold it into the first padded one is not possible -> loop over it
+        if wl[0] == (0, 0):
+            return torch.stack([pad(xi, widths[1:], mode, value) for xi in x], 0)
+        raise NotImplementedError("pad: more than 4 padded axes")
+    oshape = [n + a + b for n, (a, b) in zip(x.shape, widths)]
+    out = torch.empty(oshape, dtype=x.dtype, device=x.device)
+    fill = torch.tensor([value], dtype=x.dtype).numpy().tobytes()
+    with torch.cuda.device(x.device):
+        rc = lib.xrftb_pad(_ptr(x), _ptr(out), x.element_size(), len(shape), _i64(shape), _i64([a for a, _ in wl]), _i64([b for _, b in wl]),
+                           PAD_MODES[mode], C.c_char_p(fill), _stream())
+    L.check(rc, "xrftb_pad")
     return out
 
 

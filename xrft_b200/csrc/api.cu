@@ -108,7 +108,7 @@ template <typename T> static const cplx<T>* get_table(int kind, int log2n) {
     auto it = g_tw.find(key);
     if (it != g_tw.end()) return reinterpret_cast<const cplx<T>*>(it->second);
     const long n = 1L << log2n;
-    const long count = kind == 0 ? n : n / 2 + 1;
+    const long count = kind == 0 ? n : kind == 1 ? n / 2 + 1 : (n < 8192 ? n : 8192);
     std::vector<cplx<T>> h(count);
     for (long m = 0; m < count; ++m) {
         // exact octant symmetries are not needed at 1e-6 / 1e-3 tolerances; double sincos is exact enough
@@ -127,6 +127,8 @@ template <> const cplx<float>* twiddle_fft<float>(int l) { return get_table<floa
 template <> const cplx<double>* twiddle_fft<double>(int l) { return get_table<double>(0, l); }
 template <> const cplx<float>* twiddle_r2c<float>(int l) { return get_table<float>(1, l); }
 template <> const cplx<double>* twiddle_r2c<double>(int l) { return get_table<double>(1, l); }
+template <> const cplx<float>* twiddle_head<float>(int l) { return get_table<float>(2, l); }
+template <> const cplx<double>* twiddle_head<double>(int l) { return get_table<double>(2, l); }
 
 // ------------------------------------------------------------------------------------------------
 // K1: moments.  item = [n0][n1][n2]; rows = n0*n1 of length n2.  fp64 accumulation.
@@ -676,22 +678,9 @@ __global__ void __launch_bounds__(256) herm_extend_kernel(const cplx<T>* __restr
     }
 }
 
-// four-step helpers for power-of-two lengths beyond one CTA's shared memory: n = n1 * n2,
+// four-step decomposition of power-of-two lengths beyond one CTA's shared memory: n = n1 * n2,
 //   x[i1*n2 + i2] --FFT over i1--> Y[k1][i2] --* w_n^(k1 i2)--> --FFT over i2--> Z[k1][k2] --transpose--> X[k1 + n1 k2]
-template <typename T>
-__global__ void __launch_bounds__(256) fourstep_twiddle_kernel(cplx<T>* __restrict__ y, long n1, long n2, long B, int conj_tw, long total) {
-    const double inv_n = 1.0 / (double)(n1 * n2);
-    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-        const long i2 = (i / B) % n2;
-        const long k1 = (i / (B * n2)) % n1;
-        const long r = (k1 * i2) % (n1 * n2);
-        double sn, cs;
-        sincospi(-2.0 * (double)r * inv_n, &sn, &cs);
-        if (conj_tw) sn = -sn;
-        cplx<T> v = y[i];
-        y[i] = mk<T>((T)((double)v.x * cs - (double)v.y * sn), (T)((double)v.x * sn + (double)v.y * cs));
-    }
-}
+// (twiddle and transposition are store hooks of ColsC2C; the kernel below serves the contiguous case B == 1)
 // out[a][k2][k1][b] = in[a][k1][k2][b] * scale
 template <typename T>
 __global__ void __launch_bounds__(256) fourstep_transpose_kernel(const cplx<T>* __restrict__ in, cplx<T>* __restrict__ out, long n1, long n2, long B,
@@ -721,6 +710,46 @@ __global__ void __launch_bounds__(256) crop_kernel(const cplx<T>* __restrict__ i
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// pad (xrft/padding.py:157-181 -> xarray.DataArray.pad -> numpy.pad): out = in surrounded by pad_before / pad_after cells per
+// axis, the new cells filled by a constant or by an index map of the input (edge / reflect / symmetric / wrap, numpy
+// semantics incl. pads wider than the array).  Pure data movement: one gather per output element, any element size.
+// ------------------------------------------------------------------------------------------------
+struct PadDesc { long in_n[4], out_n[4], before[4]; int mode; };
+__device__ __forceinline__ long pad_src_index(long j, long n, int mode) {   // j = output index - pad_before, may be outside [0, n)
+    if (j >= 0 && j < n) return j;
+    if (mode == 1) return j < 0 ? 0 : n - 1;                       // edge
+    if (n == 1) return 0;
+    if (mode == 4) { long r = j % n; return r < 0 ? r + n : r; }    // wrap
+    const long p = mode == 2 ? 2 * (n - 1) : 2 * n;                 // reflect (edge not repeated) / symmetric (edge repeated)
+    long r = j % p;
+    if (r < 0) r += p;
+    return r < n ? r : (mode == 2 ? p - r : p - 1 - r);
+}
+template <typename E>
+__global__ void __launch_bounds__(256) pad_kernel(const E* __restrict__ in, E* __restrict__ out, PadDesc d, E fill, long total) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        long r = i, src = 0, mul = 1;
+        bool inside = true;
+        long idx[4];
+#pragma unroll
+        for (int a = 3; a >= 0; --a) { idx[a] = r % d.out_n[a]; r /= d.out_n[a]; }
+#pragma unroll
+        for (int a = 3; a >= 0; --a) {
+            const long j = idx[a] - d.before[a];
+            long sidx = j;
+            if (j < 0 || j >= d.in_n[a]) {
+                if (d.mode == 0) inside = false; else sidx = pad_src_index(j, d.in_n[a], d.mode);
+            }
+            src += sidx * mul;
+            mul *= d.in_n[a];
+        }
+        out[i] = inside ? in[src] : fill;
+    }
+}
+
+static inline size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
 static inline int next_pow2_log(long n) { int l = 0; while ((1L << l) < n) ++l; return l; }
 
 static inline int ilog2_exact(int64_t n) {
@@ -765,7 +794,7 @@ template <typename T> static size_t pass_workspace(long A, long n, long B) {
 
 template <typename T>
 static int c2c_pass(const cplx<T>* src, cplx<T>* dst, long A, long n, long B, int inverse, T scale, void* work, size_t work_bytes,
-                    cudaStream_t st);
+                    cudaStream_t st, const ColsC2C<T>* hooks = nullptr);
 
 template <typename T> static int get_chirp(long N, int log2M, const cplx<T>** chirp, const cplx<T>** filt, cudaStream_t st) {
     int dev = 0;
@@ -812,7 +841,8 @@ template <typename T> static int get_chirp(long N, int log2M, const cplx<T>** ch
 // one C2C pass along the middle axis of [A][n][B]; src may equal dst
 template <typename T>
 static int c2c_pass(const cplx<T>* src, cplx<T>* dst, long A, long n, long B, int inverse, T scale, void* work, size_t work_bytes,
-                    cudaStream_t st) {
+                    cudaStream_t st, const ColsC2C<T>* hooks) {
+    if (hooks && !(ilog2_exact(n) > 0 && B > 1)) { set_error("fft2r: strided power-of-two axis required"); return XRFTB_EUNSUPPORTED; }
     if (n == 1) {
         if (src != dst || scale != (T)1) {
             const long total = A * B;
@@ -824,7 +854,7 @@ static int c2c_pass(const cplx<T>* src, cplx<T>* dst, long A, long n, long B, in
     if (fast_len<T>(n, B == 1)) {
         const int l2 = ilog2_exact(n);
         if (B == 1) return rows_c2c<T>(src, dst, l2, A, n, n, inverse, scale, st);
-        return cols_c2c<T>(src, dst, l2, A, B, inverse, scale, st);
+        return cols_c2c<T>(src, dst, l2, A, B, inverse, scale, st, hooks);
     }
     if (n <= kSmallDft) {
         const long nseq = A * B;
@@ -840,11 +870,21 @@ static int c2c_pass(const cplx<T>* src, cplx<T>* dst, long A, long n, long B, in
         const long n1 = 1L << (l2 / 2), n2 = n / n1;
         if (ilog2_exact(n2) > TypeCfg<T>::MAX_COLS_LOG2) { set_error("fftn: length %ld too long", n); return XRFTB_EUNSUPPORTED; }
         const long total = A * n * B;
-        if (int rc = cols_c2c<T>(src, w, ilog2_exact(n1), A, n2 * B, inverse, (T)1, st)) return rc;              // FFT over i1
-        fourstep_twiddle_kernel<T><<<ew_grid(total), 256, 0, st>>>(w, n1, n2, B, inverse, total);
-        if (int rc = check_launch("fourstep_twiddle")) return rc;
-        if (int rc = (B == 1 ? rows_c2c<T>(w, w, ilog2_exact(n2), A * n1, n2, n2, inverse, (T)1, st)
-                             : cols_c2c<T>(w, w, ilog2_exact(n2), A * n1, B, inverse, (T)1, st))) return rc;       // FFT over i2
+        // the twiddle product w_n^(k1 i2) rides on the stores of the first pass; with B > 1 (strided second pass) the final
+        // transposition rides on the stores of the second: two passes over the data instead of four
+        // (w_n^m from a table of n entries up to n = 2^13, else from a coarse and a fine table of n / 8192 and 8192 entries)
+        const cplx<T>* tw4 = l2 <= 13 ? twiddle_fft<T>(l2) : twiddle_head<T>(l2);
+        const cplx<T>* tw4_hi = l2 <= 13 ? nullptr : twiddle_fft<T>(l2 - 13);
+        if (!tw4 || (l2 > 13 && !tw4_hi)) return XRFTB_ECUDA;
+        ColsC2C<T> ea{}, eb{};
+        if (hooks) { ea = *hooks; eb = *hooks; }
+        ea.tw4 = tw4; ea.tw4_div = B; ea.tw4_hi = tw4_hi; ea.row_mul = n2; ea.row_div = B;   // step A: rows r = i1 n2 + i2; store hooks belong to step B
+        ea.out_ramp = nullptr; ea.out_roll = 0; ea.out_hi = 0;
+        eb.tr_n1 = (int)n1; eb.in_ramp = nullptr; eb.in_roll = 0; eb.in_hi = 0;                 // step B: load hooks belong to step A
+        if (int rc = cols_c2c<T>(src, w, ilog2_exact(n1), A, n2 * B, inverse, (T)1, st, &ea)) return rc;            // FFT over i1, x twiddle
+        if (B > 1) return cols_c2c<T>(w, dst, ilog2_exact(n2), A * n1, B, inverse, scale, st, &eb);                  // FFT over i2, transposed store
+        if (hooks) { set_error("fft2r: contiguous four-step pass has no hooks"); return XRFTB_EUNSUPPORTED; }
+        if (int rc = rows_c2c<T>(w, w, ilog2_exact(n2), A * n1, n2, n2, inverse, (T)1, st)) return rc;                // FFT over i2 (contiguous)
         fourstep_transpose_kernel<T><<<ew_grid(total), 256, 0, st>>>(w, dst, n1, n2, B, scale, total);
         return check_launch("fourstep_transpose");
     }
@@ -993,6 +1033,75 @@ static int fftn_impl(const void* in, void* out, void* work, size_t work_bytes, i
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// 2-D real transform with the neighbouring elementwise steps of xrft.fft / xrft.ifft folded into its passes (xrftb_fft2r):
+//   forward: zero padding (xrft.pad) as load predicates + skipped padding rows | R2C rows x ramp_x x scale | strided passes,
+//            the last one x ramp_y                                              (xrft.py:398-404, 462-472; padding.py:157-181)
+//   inverse: strided passes reading rolled rows x ramp_y, the last one storing rolled + cropped rows | C2R rows x ramp_x on
+//            the way in, rolled + cropped + scaled on the way out                (xrft.py:574-621, 641-642; padding.py:425-446)
+// Power-of-two sizes on the single-pass / four-step kernels; anything else reports XRFTB_EUNSUPPORTED and the caller composes
+// xrftb_pad / xrftb_spectral_post / xrftb_fftn / xrftb_roll_scale instead.
+// ------------------------------------------------------------------------------------------------
+template <typename T> static bool fft2r_supported(const xrftb_fft2r_desc& q) {
+    const int ly = ilog2_exact(q.ny), lx = ilog2_exact(q.nx);
+    if (ly < 1 || lx < 2 || !fast_real_len<T>(q.nx)) return false;
+    if (fast_len<T>(q.ny, false)) return true;
+    const long n1 = 1L << (ly / 2), n2 = q.ny / n1;
+    return ilog2_exact(n2) <= TypeCfg<T>::MAX_COLS_LOG2 && ly <= 26;
+}
+template <typename T> static size_t fft2r_workspace_impl(const xrftb_fft2r_desc& q) {
+    if (!fft2r_supported<T>(q)) return 0;
+    const size_t H = (size_t)q.nx / 2 + 1;
+    size_t need = pass_workspace<T>(q.batch, q.ny, (long)H);
+    if (q.inverse) need += align256((size_t)q.batch * (size_t)(q.out_ny > 0 ? q.out_ny : q.ny) * H * sizeof(cplx<T>));
+    return need + 512;
+}
+template <typename T> static int fft2r_impl(const xrftb_fft2r_desc& q, cudaStream_t st) {
+    using C = cplx<T>;
+    if (!fft2r_supported<T>(q)) { set_error("fft2r: size %ld x %ld is not covered by the fused passes", (long)q.ny, (long)q.nx); return XRFTB_EUNSUPPORTED; }
+    const long H = q.nx / 2 + 1;
+    const int lx = ilog2_exact(q.nx);
+    char* wbase = reinterpret_cast<char*>(q.work);
+    if (q.work_bytes < fft2r_workspace_impl<T>(q) - 512 || (!q.work && fft2r_workspace_impl<T>(q) > 512)) { set_error("fft2r: workspace too small"); return XRFTB_EWORKSPACE; }
+    if (!q.inverse) {
+        const bool padded = q.in_ny > 0;
+        if (padded && (q.in_off_y < 0 || q.in_off_x < 0 || q.in_off_y + q.in_ny > q.ny || q.in_off_x + q.in_nx > q.nx || q.in_nx < 1)) { set_error("fft2r: input placement outside the transform"); return XRFTB_EINVAL; }
+        RowsR2CFused<T> io{};
+        io.in = reinterpret_cast<const T*>(q.in); io.in_row_stride = padded ? q.in_nx : q.nx; io.logNy = 0; io.detrend = 0; io.moments = nullptr;
+        io.wy = nullptr; io.wx = nullptr; io.out = reinterpret_cast<C*>(q.out); io.logC = -1; io.out_seq_stride = H; io.rowstats = nullptr;
+        if (padded) { io.rows_in = q.in_ny; io.rows_out = q.ny; io.row_off = q.in_off_y; io.col_lo = (int)q.in_off_x; io.col_hi = (int)(q.in_off_x + q.in_nx); }
+        io.out_ramp = reinterpret_cast<const C*>(q.ramp_x); io.out_scale = (T)q.scale;
+        if (int rc = rows_r2c<T>(io, lx - 1, q.batch * (padded ? q.in_ny : q.ny), st)) return rc;
+        ColsC2C<T> hk{};
+        hk.hook_n = q.ny;
+        if (padded) { hk.in_lo = q.in_off_y; hk.in_hi = q.in_off_y + q.in_ny; }
+        hk.out_ramp = reinterpret_cast<const C*>(q.ramp_y);
+        const bool any = padded || q.ramp_y;
+        return c2c_pass<T>(reinterpret_cast<C*>(q.out), reinterpret_cast<C*>(q.out), q.batch, q.ny, H, 0, (T)1, wbase, q.work_bytes, st, any ? &hk : nullptr);
+    }
+    // ---- inverse
+    const long cy = q.out_ny > 0 ? q.out_ny : q.ny, cx = q.out_nx > 0 ? q.out_nx : q.nx;
+    const long oy = q.out_ny > 0 ? q.out_off_y : 0, ox = q.out_nx > 0 ? q.out_off_x : 0;
+    if (oy < 0 || ox < 0 || oy + cy > q.ny || ox + cx > q.nx) { set_error("fft2r: crop outside the transform"); return XRFTB_EINVAL; }
+    const size_t w2_bytes = align256((size_t)q.batch * cy * H * sizeof(C));
+    C* w2 = reinterpret_cast<C*>(wbase);
+    ColsC2C<T> hk{};
+    hk.hook_n = q.ny;
+    hk.in_roll = ((q.in_roll_y % q.ny) + q.ny) % q.ny;
+    hk.in_ramp = reinterpret_cast<const C*>(q.ramp_y);
+    hk.out_roll = ((q.out_roll_y % q.ny) + q.ny) % q.ny;
+    if (q.out_ny > 0) { hk.out_lo = oy; hk.out_hi = oy + cy; }
+    const bool any = hk.in_roll || hk.in_ramp || hk.out_roll || hk.out_hi;
+    if (int rc = c2c_pass<T>(reinterpret_cast<const C*>(q.in), w2, q.batch, q.ny, H, 1, (T)1, wbase + w2_bytes, q.work_bytes - w2_bytes, st, any ? &hk : nullptr)) return rc;
+    RowsC2R<T> ex{};
+    ex.in_ramp = reinterpret_cast<const C*>(q.ramp_x);
+    ex.out_roll = (int)(((q.out_roll_x % q.nx) + q.nx) % q.nx);
+    if (q.out_nx > 0) { ex.out_lo = (int)ox; ex.out_hi = (int)(ox + cx); }
+    const double norm = (double)q.ny * (double)q.nx;
+    return rows_c2r<T>(w2, H, reinterpret_cast<T*>(q.out), cx, lx - 1, q.batch * cy, (T)(2.0 * q.scale / norm), st, &ex);
+}
+
 // ------------------------------------------------------------------------------------------------
 // fused 2-D real spectrum
 // ------------------------------------------------------------------------------------------------
@@ -1022,7 +1131,6 @@ template <typename T> static size_t interm_bytes_per_item(int ny, int nx, int C)
 }
 
 // row-line detrend: per-item rowstats (float4 / row) + ag (cplx<T> / row); fixed: wj table + its fp64 transform scratch
-static inline size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
 template <typename T> static size_t rowline_item_bytes(int ny) { return (size_t)ny * (sizeof(float4) + sizeof(cplx<T>)); }
 template <typename T> static size_t rowline_fixed_bytes(int nx, int C) {
     const size_t ncols = (size_t)((nx / 2) / C + 1) * C;
@@ -1568,6 +1676,46 @@ int xrftb_roll_scale(const void* in, void* out, int dtype, int is_complex, int64
             ((s0 % n0) + n0) % n0, ((s1 % n1) + n1) % n1, ((s2 % n2) + n2) % n2, width, scale, total);
     else { set_error("roll_scale: bad dtype"); return XRFTB_EINVAL; }
     return check_launch("roll_scale_kernel");
+}
+
+size_t xrftb_fft2r_workspace(const xrftb_fft2r_desc* q) {
+    if (!q || q->batch < 1 || q->ny < 2 || q->nx < 4) return 0;
+    return q->dtype == XRFTB_F32 ? fft2r_workspace_impl<float>(*q) : q->dtype == XRFTB_F64 ? fft2r_workspace_impl<double>(*q) : 0;
+}
+int xrftb_fft2r(const xrftb_fft2r_desc* q, void* stream) {
+    if (!q || !q->in || !q->out || q->batch < 1) { set_error("fft2r: bad descriptor"); return XRFTB_EINVAL; }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (q->dtype == XRFTB_F32) return fft2r_impl<float>(*q, st);
+    if (q->dtype == XRFTB_F64) return fft2r_impl<double>(*q, st);
+    set_error("fft2r: bad dtype %d", q->dtype);
+    return XRFTB_EINVAL;
+}
+
+int xrftb_pad(const void* in, void* out, int elem_bytes, int ndim, const int64_t* in_shape, const int64_t* pad_before,
+              const int64_t* pad_after, int mode, const void* fill, void* stream) {
+    if (!in || !out || ndim < 1 || ndim > 4 || !in_shape || !pad_before || !pad_after || mode < 0 || mode > 4) { set_error("pad: bad arguments"); return XRFTB_EINVAL; }
+    PadDesc d{};
+    long total = 1;
+    for (int a = 0; a < 4; ++a) { d.in_n[a] = 1; d.out_n[a] = 1; d.before[a] = 0; }
+    for (int a = 0; a < ndim; ++a) {
+        const int k = 4 - ndim + a;
+        if (in_shape[a] < 1 || pad_before[a] < 0 || pad_after[a] < 0) { set_error("pad: bad shape or widths"); return XRFTB_EINVAL; }
+        d.in_n[k] = in_shape[a]; d.before[k] = pad_before[a]; d.out_n[k] = in_shape[a] + pad_before[a] + pad_after[a];
+        total *= d.out_n[k];
+    }
+    d.mode = mode;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (elem_bytes == 4) {
+        float f = 0.f; if (fill) memcpy(&f, fill, 4);
+        pad_kernel<float><<<ew_grid(total), 256, 0, st>>>(reinterpret_cast<const float*>(in), reinterpret_cast<float*>(out), d, f, total);
+    } else if (elem_bytes == 8) {
+        double f = 0.0; if (fill) memcpy(&f, fill, 8);
+        pad_kernel<double><<<ew_grid(total), 256, 0, st>>>(reinterpret_cast<const double*>(in), reinterpret_cast<double*>(out), d, f, total);
+    } else if (elem_bytes == 16) {
+        double2 f = make_double2(0.0, 0.0); if (fill) memcpy(&f, fill, 16);
+        pad_kernel<double2><<<ew_grid(total), 256, 0, st>>>(reinterpret_cast<const double2*>(in), reinterpret_cast<double2*>(out), d, f, total);
+    } else { set_error("pad: element size %d unsupported (4, 8 or 16 bytes)", elem_bytes); return XRFTB_EINVAL; }
+    return check_launch("pad_kernel");
 }
 
 size_t xrftb_spectrum2d_workspace(int dtype, int ny, int nx, int two_fields, int64_t batch_in_flight) {

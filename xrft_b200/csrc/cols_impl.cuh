@@ -15,11 +15,13 @@ template <typename T, int LOG2L, bool TWO> struct TileC {
     X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13)
 
 template <typename T>
-int cols_c2c(const cplx<T>* in, cplx<T>* out, int log2L, long A, long B, int inverse, T scale, cudaStream_t st) {
+int cols_c2c(const cplx<T>* in, cplx<T>* out, int log2L, long A, long B, int inverse, T scale, cudaStream_t st, const ColsC2C<T>* extra) {
     const int C = cols_tile_width<T>(log2L, false);
     if (C < 1) { set_error("cols_c2c: unsupported length 2^%d", log2L); return -2; }
     const long tpr = (B + C - 1) / C;
-    ColsC2C<T> io{in, out, B, tpr, inverse, scale};
+    ColsC2C<T> io{};
+    if (extra) io = *extra;
+    io.in = in; io.out = out; io.B = B; io.tiles_per_row = tpr; io.inverse = inverse; io.scale = scale;
     switch (log2L) {
 #define X(K) case K: return launch_cols<T, K, TileC<T, K, false>::value>(io, A * tpr, st);
         XRFTB_COLS_CASES(X)

@@ -137,6 +137,20 @@ template <typename T> struct RowsR2CFused {
     // the residual r; the difference between the row lines and the least-squares plane is added back in the column pass
     // (ColsFused::fix), where it is a rank-2 update of the half-spectrum.  rowstats == nullptr: global-plane prologue.
     float4* rowstats;
+    // ---- hooks of the padded / scaled 2-D real transform (xrftb_fft2r, natural layout only; all off by default) ----
+    // xrft.pad folded into the loads: the sequences enumerate only the rows_in input rows of every item (the padding rows are
+    // never transformed); real element j of a padded row is in[j - col_lo] for col_lo <= j < col_hi and zero elsewhere;
+    // row r of item b lands in output row b * rows_out + row_off + r.  The half spectrum leaves multiplied by out_ramp[k] * out_scale.
+    long rows_in = 0, rows_out = 0, row_off = 0;
+    int col_lo = 0, col_hi = 0;
+    const cplx<T>* out_ramp = nullptr;
+    T out_scale = 1;
+
+    __device__ __forceinline__ long out_row(long seq) const {
+        if (rows_in == 0) return seq;
+        const long b = seq / rows_in;
+        return b * rows_out + row_off + (seq - b * rows_in);
+    }
 
     template <int LOG2L, int SEQ> __device__ __forceinline__ void prefetch(long seq0, long nseq) const {
         constexpr unsigned row_bytes = (unsigned)(2u << LOG2L) * sizeof(T);
@@ -147,6 +161,17 @@ template <typename T> struct RowsR2CFused {
     template <int LOG2L, int LOGE>
     __device__ __forceinline__ void fetch(long seq, bool active, int u, cplx<T> (&raw)[1 << LOGE]) const {
         constexpr int NT = Geometry<LOG2L, LOGE>::NT;
+        if (col_hi > 0) {   // zero-padded row: predicated scalar loads
+            const T* rowp = in + seq * in_row_stride - col_lo;
+#pragma unroll
+            for (int q = 0; q < (1 << LOGE); ++q) {
+                const int j0 = 2 * (u + q * NT);
+                raw[q] = mk<T>(0, 0);
+                if (active && j0 >= col_lo && j0 < col_hi) raw[q].x = rowp[j0];
+                if (active && j0 + 1 >= col_lo && j0 + 1 < col_hi) raw[q].y = rowp[j0 + 1];
+            }
+            return;
+        }
         const cplx<T>* p = reinterpret_cast<const cplx<T>*>(in + seq * in_row_stride) + u;
 #pragma unroll
         for (int q = 0; q < (1 << LOGE); ++q) {
@@ -227,8 +252,16 @@ template <typename T> struct RowsR2CFused {
         cplx<T>* sm = smem + s * seq_stride;
         if (logC < 0) {
             if (active) {
-                cplx<T>* p = out + seq * out_seq_stride;
-                for (int k = u; k <= M; k += NT) p[k] = split_at<LOG2L, LOGE>(sm, k);
+                cplx<T>* p = out + out_row(seq) * out_seq_stride;
+                if (out_ramp != nullptr || out_scale != (T)1) {
+                    for (int k = u; k <= M; k += NT) {
+                        cplx<T> x = cscale(split_at<LOG2L, LOGE>(sm, k), out_scale);
+                        if (out_ramp != nullptr) x = cmul(x, __ldg(out_ramp + k));
+                        p[k] = x;
+                    }
+                } else {
+                    for (int k = u; k <= M; k += NT) p[k] = split_at<LOG2L, LOGE>(sm, k);
+                }
             }
         } else {
             // thread -> (tile t, row s2, column c), c fastest: SEQ*C consecutive threads write one contiguous run
@@ -516,6 +549,11 @@ rows2_kernel(RowsR2CFused<T> io, const cplx<T>* __restrict__ tw, long nseq) {
 template <typename T> struct RowsC2R {
     static constexpr int kSeqSkew = 0;
     const cplx<T>* in; long in_stride; T* out; long out_stride; T scale; const cplx<T>* tw_r2c;
+    // ---- hooks of xrftb_fft2r (all off by default): the half spectrum is multiplied by in_ramp[k] on its way in (before the
+    // imaginary parts of DC and Nyquist are dropped, like spectral_post -> irfftn); real output element n is stored at position
+    // (n + out_roll) % N; with out_hi > 0 only positions in [out_lo, out_hi) are written, at out[pos - out_lo] (crop)
+    const cplx<T>* in_ramp = nullptr;
+    int out_roll = 0, out_lo = 0, out_hi = 0;
 
     template <int LOG2L, int SEQ> __device__ __forceinline__ void prefetch(long, long) const {}
 
@@ -531,6 +569,7 @@ template <typename T> struct RowsC2R {
             cplx<T> z = mk<T>(0, 0);
             if (active) {
                 cplx<T> xk = p[k], xm = p[M - k];
+                if (in_ramp != nullptr) { xk = cmul(xk, __ldg(in_ramp + k)); xm = cmul(xm, __ldg(in_ramp + (M - k))); }
                 if (k == 0) { xk.y = 0; xm.y = 0; }  // numpy/pocketfft ignore Im of DC and Nyquist
                 cplx<T> e = mk<T>((T)0.5 * (xk.x + xm.x), (T)0.5 * (xk.y - xm.y));
                 cplx<T> d = mk<T>((T)0.5 * (xk.x - xm.x), (T)0.5 * (xk.y + xm.y));
@@ -549,6 +588,26 @@ template <typename T> struct RowsC2R {
         constexpr int R = 1 << G_::LOGR_LAST, G = G_::E / R;
         if (!active) return;
         T* p = out + seq * out_stride;
+        if (out_roll != 0 || out_hi > 0) {
+            constexpr int N = 2 << LOG2L;
+            const int lo = out_hi > 0 ? out_lo : 0, hi = out_hi > 0 ? out_hi : N;
+            const bool pairs = ((out_roll | lo) & 1) == 0 && (hi & 1) == 0 && (out_stride & 1) == 0;   // pairs stay aligned pairs
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+#pragma unroll
+                for (int t = 0; t < R; ++t) {
+                    const cplx<T> x = v[g + t * G];
+                    const int pos = (2 * final_index<LOG2L, LOGE>(u, g, t) + out_roll) & (N - 1);
+                    if (pairs) {
+                        if (pos >= lo && pos < hi) *reinterpret_cast<cplx<T>*>(p + (pos - lo)) = mk<T>(x.x * scale, -x.y * scale);
+                    } else {
+                        const int pos1 = (pos + 1) & (N - 1);
+                        if (pos >= lo && pos < hi) p[pos - lo] = x.x * scale;
+                        if (pos1 >= lo && pos1 < hi) p[pos1 - lo] = -x.y * scale;
+                    }
+                }
+            return;
+        }
 #pragma unroll
         for (int g = 0; g < G; ++g)
 #pragma unroll
@@ -960,6 +1019,27 @@ template <typename T> struct ColsC2C {
     static constexpr bool kBins = false;
     static constexpr int kExtraSmemBytes = 0;
     const cplx<T>* in; cplx<T>* out; long B; long tiles_per_row; int inverse; T scale;
+    // Hooks of the four-step decomposition n = n1 n2 of a transform too long for one CTA (c2c_pass): the twiddle product and
+    // the final transposition ride on the stores of the two strided passes instead of being passes of their own.
+    //   step A (FFT over i1 on the view [A][n1][n2 B]): output point k1 of column b is multiplied by w_n^(k1 i2), i2 = b / tw4_div
+    //   step B (FFT over i2 on the view [A n1][n2][B]): output point k2 of item (a, k1) is stored at row k1 + n1 k2 of item a
+    const cplx<T>* tw4 = nullptr;   // exp(-2 pi i m / n), m in [0, min(n, 8192)); nullptr = no twiddle
+    long tw4_div = 1;
+    int tr_n1 = 0;                  // n1 of the transposed store; 0 = natural order
+    const cplx<T>* tw4_hi = nullptr;   // n > 8192: exp(-2 pi i 8192 h / n), h in [0, n / 8192); w^m = tw4_hi[m >> 13] tw4[m & 8191]
+    // ---- hooks of xrftb_fft2r on the strided axis of length hook_n (0 = off).  Element (l, column b) of this pass is row
+    // r = l * row_mul + b / row_div of the full axis (row_mul = n2, row_div = B in step A of a four-step pass; 1 and 0 = "no
+    // division" in a single pass).  Loads: row r reads SOURCE row (r + in_roll) % hook_n of a source array with row pitch
+    // (row_div ? row_div : B); source rows outside [in_lo, in_hi) are zero and never read (in_hi = 0: all valid); the element
+    // is multiplied by in_ramp[source row].  Stores (last pass): output row R is multiplied by out_ramp[R] and stored at row
+    // (R + out_roll) % hook_n; with out_hi > 0 only stored rows in [out_lo, out_hi) are written, into items of out_hi - out_lo rows.
+    long hook_n = 0, row_mul = 1, row_div = 0;
+    long in_roll = 0, in_lo = 0, in_hi = 0;
+    const cplx<T>* in_ramp = nullptr;
+    const cplx<T>* out_ramp = nullptr;
+    long out_roll = 0, out_lo = 0, out_hi = 0;
+    __device__ __forceinline__ bool in_hooks() const { return hook_n > 0 && (in_roll != 0 || in_hi > 0 || in_ramp != nullptr); }
+    __device__ __forceinline__ bool out_hooks() const { return hook_n > 0 && (out_roll != 0 || out_hi > 0 || out_ramp != nullptr); }
 
     template <int LOG2L, int C> __device__ __forceinline__ void prefetch(long) const {}
     template <int LOG2L, int LOGE, int C, int V> __device__ __forceinline__ void init(cplx<T>*) const {}
@@ -974,6 +1054,31 @@ template <typename T> struct ColsC2C {
         constexpr int NT = Geometry<LOG2L, LOGE>::NT, L = 1 << LOG2L;
         const long a = tile / tiles_per_row;
         const long b0 = (tile - a * tiles_per_row) * C + cg * V;
+        if (in_hooks()) {
+            const long pitch = row_div ? row_div : B;
+            const cplx<T>* base = in + a * hook_n * pitch;
+#pragma unroll
+            for (int vv = 0; vv < V; ++vv) {
+                const long bb = b0 + vv;
+                const long i2 = row_div ? bb / row_div : 0;
+                const long bcol = row_div ? bb - i2 * row_div : bb;
+#pragma unroll
+                for (int q = 0; q < (1 << LOGE); ++q) {
+                    cplx<T> x = mk<T>(0, 0);
+                    if (bb < B) {
+                        long rs = (long)(u + q * NT) * row_mul + i2 + in_roll;
+                        if (rs >= hook_n) rs -= hook_n;
+                        if (in_hi == 0 || (rs >= in_lo && rs < in_hi)) {
+                            x = base[rs * pitch + bcol];
+                            if (in_ramp != nullptr) x = cmul(x, __ldg(in_ramp + rs));
+                        }
+                    }
+                    if (inverse) x.y = -x.y;
+                    v[vv][q] = x;
+                }
+            }
+            return;
+        }
         const cplx<T>* p = in + a * L * B + b0 + (long)u * B;
         const long qstep = (long)NT * B;
 #pragma unroll
@@ -995,6 +1100,45 @@ template <typename T> struct ColsC2C {
         const long a = tile / tiles_per_row;
         const long b0 = (tile - a * tiles_per_row) * C + cg * V;
         cplx<T>* p = out + a * L * B + b0;
+        long ostride = B;
+        if (tr_n1) {
+            const long ao = a / tr_n1;
+            p = out + (ao * tr_n1 * L + (a - ao * tr_n1)) * B + b0;
+            ostride = (long)tr_n1 * B;
+        }
+        long i2[V];
+#pragma unroll
+        for (int vv = 0; vv < V; ++vv) i2[vv] = tw4 ? (b0 + vv) / tw4_div : 0;
+        if (out_hooks()) {   // last pass of the strided axis: factor, roll and crop ride on the stores
+            const long ao = tr_n1 ? a / tr_n1 : a;
+            const long k1 = tr_n1 ? a - ao * tr_n1 : 0;
+            const long rstep = tr_n1 ? tr_n1 : 1;
+            const long rows_item = out_hi > 0 ? out_hi - out_lo : hook_n;
+            const long lo = out_hi > 0 ? out_lo : 0, hi = out_hi > 0 ? out_hi : hook_n;
+            cplx<T>* ob = out + ao * rows_item * B + b0;
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+#pragma unroll
+                for (int t = 0; t < R; ++t) {
+                    const long Rr = k1 + rstep * final_index<LOG2L, LOGE>(u, g, t);
+                    long Rs = Rr + out_roll;
+                    if (Rs >= hook_n) Rs -= hook_n;
+                    if (Rs < lo || Rs >= hi) continue;
+                    cplx<T> f = mk<T>(1, 0);
+                    if (out_ramp != nullptr) f = __ldg(out_ramp + Rr);
+#pragma unroll
+                    for (int vv = 0; vv < V; ++vv) {
+                        if (b0 + vv < B) {
+                            cplx<T> x = v[vv][g + t * G];
+                            if (inverse) x.y = -x.y;
+                            x = cscale(x, scale);
+                            if (out_ramp != nullptr) x = cmul(x, f);
+                            ob[(Rs - lo) * B + vv] = x;
+                        }
+                    }
+                }
+            return;
+        }
 #pragma unroll
         for (int g = 0; g < G; ++g)
 #pragma unroll
@@ -1005,7 +1149,14 @@ template <typename T> struct ColsC2C {
                     if (b0 + vv < B) {
                         cplx<T> x = v[vv][g + t * G];
                         if (inverse) x.y = -x.y;
-                        p[o * B + vv] = cscale(x, scale);
+                        x = cscale(x, scale);
+                        if (tw4) {
+                            const long m = o * i2[vv];
+                            cplx<T> w = tw4_hi ? cmul(__ldg(tw4_hi + (m >> 13)), __ldg(tw4 + (m & 8191))) : __ldg(tw4 + m);
+                            if (inverse) w.y = -w.y;
+                            x = cmul(x, w);
+                        }
+                        p[o * ostride + vv] = x;
                     }
                 }
             }

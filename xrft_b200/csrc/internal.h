@@ -15,6 +15,7 @@ int check_launch(const char* what);
 // device-resident twiddle tables, computed in double on the host, cached per (device, length)
 template <typename T> const cplx<T>* twiddle_fft(int log2L);  // exp(-2 pi i m / L), m in [0, L)
 template <typename T> const cplx<T>* twiddle_r2c(int log2N);  // exp(-2 pi i k / N), k in [0, N/2]
+template <typename T> const cplx<T>* twiddle_head(int log2N); // exp(-2 pi i m / N), m in [0, min(N, 8192))
 
 template <typename T> struct TypeCfg;
 #ifndef XRFTB_F32_LOGE
@@ -47,7 +48,7 @@ template <typename T> int rows_c2c(const cplx<T>* in, cplx<T>* out, int log2L, l
                                    int inverse, T scale, cudaStream_t st);
 template <typename T> int rows_r2c(RowsR2CFused<T> io, int log2M, long nseq, cudaStream_t st);
 template <typename T> int rows_c2r(const cplx<T>* in, long in_stride, T* out, long out_stride, int log2M, long nseq, T scale,
-                                   cudaStream_t st);
+                                   cudaStream_t st, const RowsC2R<T>* extra = nullptr);
 template <typename T> int rows_c2c_power(const RowsC2CPower<T>& io, int log2L, long nseq, cudaStream_t st);
 template <typename T> int rows_z_power(RowsZPower<T> io, int log2M, long nseq, cudaStream_t st);
 template <typename T> int rows_z_cross(RowsZCross<T> io, int log2M, long nseq, int mode, cudaStream_t st);
@@ -58,8 +59,10 @@ bool rows_bins_shape_ok(int log2L, int ny);
 // 2^12 instantiation exists but stays off until it has been through them)
 inline bool rows_z_supported(int log2M) { return log2M >= 9 && log2M <= 11; }
 template <typename T> int cols_r2c_pack(const ColsR2CPack<T>& io, int log2L, int C, long ntiles, bool use_async, cudaStream_t st);
+// `extra` (nullable) carries the optional members of ColsC2C: the four-step hooks (twiddle product on the stores, transposed
+// store) and the xrftb_fft2r hooks (row predicate / roll / ramps / crop); its in / out / B / inverse / scale are ignored
 template <typename T> int cols_c2c(const cplx<T>* in, cplx<T>* out, int log2L, long A, long B, int inverse, T scale,
-                                   cudaStream_t st);
+                                   cudaStream_t st, const ColsC2C<T>* extra = nullptr);
 // one explicit instantiation per (T, MODE), spread over several translation units
 template <typename T, int MODE> int cols_fused_mode(const cplx<T>* in1, const cplx<T>* in2, int log2L, long ntiles_total, int ntile,
                                                     const EpilogueDesc& d, const CUtensorMap* tmap, cudaStream_t st);

@@ -113,8 +113,10 @@ int rows_z_cross(RowsZCross<T> io, int log2M, long nseq, int mode, cudaStream_t 
 }
 
 template <typename T>
-int rows_c2r(const cplx<T>* in, long in_stride, T* out, long out_stride, int log2M, long nseq, T scale, cudaStream_t st) {
-    RowsC2R<T> io{in, in_stride, out, out_stride, scale, twiddle_r2c<T>(log2M + 1)};
+int rows_c2r(const cplx<T>* in, long in_stride, T* out, long out_stride, int log2M, long nseq, T scale, cudaStream_t st, const RowsC2R<T>* extra) {
+    RowsC2R<T> io{};
+    if (extra) io = *extra;
+    io.in = in; io.in_stride = in_stride; io.out = out; io.out_stride = out_stride; io.scale = scale; io.tw_r2c = twiddle_r2c<T>(log2M + 1);
     if (!io.tw_r2c) return -3;
     switch (log2M) {
 #define X(K) case K: return launch_rows<T, K, rows_seq_generic<K, cmin(TypeCfg<T>::LOGE, K)>()>(io, nseq, st);

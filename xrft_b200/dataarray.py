@@ -101,6 +101,25 @@ def _normalize_coords(coords, dims, shape) -> "Coordinates":
     return out
 
 
+class LazyPad:
+    """Zero padding of a device-resident array that has not been carried out yet (xrft.pad of a CUDA tensor, mode
+    'constant', value 0): the transform kernels read the unpadded array through load predicates (xrftb_fft2r), so the padded
+    copy is only materialised -- by the CUDA pad kernel -- if something else asks for the data."""
+
+    def __init__(self, base, widths):
+        self.base = base
+        self.widths = [(int(a), int(b)) for a, b in widths]
+        self.shape = tuple(int(n) + a + b for n, (a, b) in zip(base.shape, self.widths))
+        self.ndim = len(self.shape)
+        self._mat = None
+
+    def materialize(self):
+        if self._mat is None:
+            from . import backend as B
+            self._mat = B.pad(self.base, self.widths, "constant", 0)
+        return self._mat
+
+
 class DataArray:
     __array_priority__ = 60
 
@@ -111,9 +130,9 @@ class DataArray:
             name = name if name is not None else data.name
             attrs = attrs if attrs is not None else data.attrs
             data = data.data
-        if not _is_torch(data):
+        if not _is_torch(data) and not isinstance(data, LazyPad):
             data = np.asarray(data)
-        self._data = data
+        self._store = data
         ndim = data.ndim
         if dims is None:
             if coords is not None and not isinstance(coords, Mapping):
@@ -139,6 +158,22 @@ class DataArray:
 
     # ------------------------------------------------------------------ basic properties
     @property
+    def _data(self):
+        st = self._store
+        if type(st) is LazyPad:   # deferred zero padding: carried out (CUDA pad kernel) on first real access
+            st = self._store = st.materialize()
+        return st
+
+    @_data.setter
+    def _data(self, v):
+        self._store = v
+
+    @property
+    def lazy_pad(self):
+        """the deferred zero padding of this array (LazyPad), or None; does not materialise it"""
+        return self._store if type(self._store) is LazyPad else None
+
+    @property
     def data(self):
         return self._data
 
@@ -156,11 +191,11 @@ class DataArray:
 
     @property
     def shape(self):
-        return tuple(self._data.shape)
+        return tuple(self._store.shape)
 
     @property
     def ndim(self):
-        return self._data.ndim
+        return len(self._store.shape)
 
     @property
     def size(self):
@@ -272,7 +307,7 @@ class DataArray:
     # ------------------------------------------------------------------ construction helpers
     def _replace(self, data=None, dims=None, coords=None, name="__keep__", attrs="__keep__", chunks="__keep__"):
         out = DataArray.__new__(DataArray)
-        out._data = self._data if data is None else data
+        out._store = self._store if data is None else data
         out._dims = self._dims if dims is None else tuple(dims)
         out.name = self.name if name == "__keep__" else name
         out.attrs = dict(self.attrs) if attrs == "__keep__" else dict(attrs or {})
@@ -502,10 +537,18 @@ class DataArray:
             kwargs["end_values"] = end_values
         if reflect_type is not None:
             kwargs["reflect_type"] = reflect_type
-        vals = self.values
-        if mode == "constant" and kwargs["constant_values"] is not None and np.issubdtype(vals.dtype, np.integer) and isinstance(kwargs["constant_values"], float) and np.isnan(kwargs["constant_values"]):
-            vals = vals.astype(float)
-        data = np.pad(vals, widths, mode=mode, **kwargs)
+        if _is_torch(self._data) and self._data.is_cuda:
+            # device-resident data never leaves the device: xrftb_pad (constant / edge / reflect / symmetric / wrap) or a loud error
+            from . import backend as B
+            if mode not in B.PAD_MODES or stat_length is not None or end_values is not None or reflect_type not in (None, "even") \
+                    or (mode == "constant" and not np.isscalar(kwargs["constant_values"])):
+                raise NotImplementedError(f"pad(mode={mode!r}) with these options is not available for device-resident data")
+            data = B.pad(self._data, widths, mode, kwargs.get("constant_values", 0))
+        else:
+            vals = self.values
+            if mode == "constant" and kwargs["constant_values"] is not None and np.issubdtype(vals.dtype, np.integer) and isinstance(kwargs["constant_values"], float) and np.isnan(kwargs["constant_values"]):
+                vals = vals.astype(float)
+            data = np.pad(vals, widths, mode=mode, **kwargs)
         coords = Coordinates()
         for name, c in self._coords.items():
             if any(d in pw for d in c.dims):
