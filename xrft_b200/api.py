@@ -448,7 +448,7 @@ def _run_forward(P, das, mode, detrend, window, scale, ramps=None, weight=None, 
     wins = _window_vectors(P["N"], window) if window is not None else None
     # ---- host inputs: stream chunks of the leading axis (numpy in -> numpy out, like the reference)
     nd = P["da"].ndim
-    host_in = all(not _is_torch(d.data) for d in das)
+    host_in = all(d.lazy_pad is None and not _is_torch(d.data) for d in das)   # (a deferred zero padding is device-resident)
     trailing = list(P["axis_num"]) == list(range(nd - ntrans, nd))
     plans = plans or [P] * len(das)
     any_reversed = any(pl["reversed_dims"] for pl in plans)

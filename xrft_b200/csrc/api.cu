@@ -842,7 +842,9 @@ template <typename T> static int get_chirp(long N, int log2M, const cplx<T>** ch
 template <typename T>
 static int c2c_pass(const cplx<T>* src, cplx<T>* dst, long A, long n, long B, int inverse, T scale, void* work, size_t work_bytes,
                     cudaStream_t st, const ColsC2C<T>* hooks) {
-    if (hooks && !(ilog2_exact(n) > 0 && B > 1)) { set_error("fft2r: strided power-of-two axis required"); return XRFTB_EUNSUPPORTED; }
+    if (hooks && !(ilog2_exact(n) > 0 && B > 1 && (double)n * (double)B < 2147483648.0 && (double)A * (double)n < 2147483648.0)) {
+        set_error("fft2r: strided power-of-two axis with fewer than 2^31 elements per item required"); return XRFTB_EUNSUPPORTED;
+    }
     if (n == 1) {
         if (src != dst || scale != (T)1) {
             const long total = A * B;
@@ -869,6 +871,7 @@ static int c2c_pass(const cplx<T>* src, cplx<T>* dst, long A, long n, long B, in
         // ---- four-step: n = n1 * n2, both within the single-pass limits
         const long n1 = 1L << (l2 / 2), n2 = n / n1;
         if (ilog2_exact(n2) > TypeCfg<T>::MAX_COLS_LOG2) { set_error("fftn: length %ld too long", n); return XRFTB_EUNSUPPORTED; }
+        if ((double)n2 * (double)B >= 2147483648.0 || (double)A * (double)n1 >= 2147483648.0) { set_error("fftn: four-step view of length %ld x %ld columns too large", n, B); return XRFTB_EUNSUPPORTED; }
         const long total = A * n * B;
         // the twiddle product w_n^(k1 i2) rides on the stores of the first pass; with B > 1 (strided second pass) the final
         // transposition rides on the stores of the second: two passes over the data instead of four

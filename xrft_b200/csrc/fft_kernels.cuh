@@ -1055,23 +1055,27 @@ template <typename T> struct ColsC2C {
         const long a = tile / tiles_per_row;
         const long b0 = (tile - a * tiles_per_row) * C + cg * V;
         if (in_hooks()) {
-            const long pitch = row_div ? row_div : B;
+            // 32-bit index arithmetic inside an item (the launcher guarantees hook_n * pitch < 2^31): the row of element q is
+            // r0 + q * rstep, wrapped once by the roll
+            const int pitch = (int)(row_div ? row_div : B);
+            const int n = (int)hook_n, lo = (int)in_lo, hi = in_hi > 0 ? (int)in_hi : n;
             const cplx<T>* base = in + a * hook_n * pitch;
+            const int rstep = NT * (int)row_mul;
 #pragma unroll
             for (int vv = 0; vv < V; ++vv) {
-                const long bb = b0 + vv;
-                const long i2 = row_div ? bb / row_div : 0;
-                const long bcol = row_div ? bb - i2 * row_div : bb;
+                const unsigned bb = (unsigned)(b0 + vv);
+                const int i2 = row_div ? (int)(bb / (unsigned)row_div) : 0;
+                const int bcol = row_div ? (int)(bb - (unsigned)i2 * (unsigned)row_div) : (int)bb;
+                const int r0 = u * (int)row_mul + i2 + (int)in_roll;
+                const bool colok = (long)bb < B;
 #pragma unroll
                 for (int q = 0; q < (1 << LOGE); ++q) {
+                    int rs = r0 + q * rstep;
+                    if (rs >= n) rs -= n;
                     cplx<T> x = mk<T>(0, 0);
-                    if (bb < B) {
-                        long rs = (long)(u + q * NT) * row_mul + i2 + in_roll;
-                        if (rs >= hook_n) rs -= hook_n;
-                        if (in_hi == 0 || (rs >= in_lo && rs < in_hi)) {
-                            x = base[rs * pitch + bcol];
-                            if (in_ramp != nullptr) x = cmul(x, __ldg(in_ramp + rs));
-                        }
+                    if (colok && rs >= lo && rs < hi) {
+                        x = base[rs * pitch + bcol];
+                        if (in_ramp != nullptr) x = cmul(x, __ldg(in_ramp + rs));
                     }
                     if (inverse) x.y = -x.y;
                     v[vv][q] = x;
@@ -1106,23 +1110,24 @@ template <typename T> struct ColsC2C {
             p = out + (ao * tr_n1 * L + (a - ao * tr_n1)) * B + b0;
             ostride = (long)tr_n1 * B;
         }
-        long i2[V];
+        int i2[V];   // (b0 + vv < n2 B < 2^31, o * i2 < n <= 2^26: 32-bit arithmetic)
 #pragma unroll
-        for (int vv = 0; vv < V; ++vv) i2[vv] = tw4 ? (b0 + vv) / tw4_div : 0;
+        for (int vv = 0; vv < V; ++vv) i2[vv] = tw4 ? (int)((unsigned)(b0 + vv) / (unsigned)tw4_div) : 0;
         if (out_hooks()) {   // last pass of the strided axis: factor, roll and crop ride on the stores
-            const long ao = tr_n1 ? a / tr_n1 : a;
-            const long k1 = tr_n1 ? a - ao * tr_n1 : 0;
-            const long rstep = tr_n1 ? tr_n1 : 1;
-            const long rows_item = out_hi > 0 ? out_hi - out_lo : hook_n;
-            const long lo = out_hi > 0 ? out_lo : 0, hi = out_hi > 0 ? out_hi : hook_n;
-            cplx<T>* ob = out + ao * rows_item * B + b0;
+            const long ao = tr_n1 ? (long)((unsigned)a / (unsigned)tr_n1) : a;
+            const int k1 = tr_n1 ? (int)(a - ao * tr_n1) : 0;
+            const int rstep = tr_n1 ? tr_n1 : 1;
+            const int n = (int)hook_n;
+            const int lo = out_hi > 0 ? (int)out_lo : 0, hi = out_hi > 0 ? (int)out_hi : n;
+            const int Bi = (int)B;
+            cplx<T>* ob = out + ao * (long)(hi - lo) * B + b0;
 #pragma unroll
             for (int g = 0; g < G; ++g)
 #pragma unroll
                 for (int t = 0; t < R; ++t) {
-                    const long Rr = k1 + rstep * final_index<LOG2L, LOGE>(u, g, t);
-                    long Rs = Rr + out_roll;
-                    if (Rs >= hook_n) Rs -= hook_n;
+                    const int Rr = k1 + rstep * final_index<LOG2L, LOGE>(u, g, t);
+                    int Rs = Rr + (int)out_roll;
+                    if (Rs >= n) Rs -= n;
                     if (Rs < lo || Rs >= hi) continue;
                     cplx<T> f = mk<T>(1, 0);
                     if (out_ramp != nullptr) f = __ldg(out_ramp + Rr);
@@ -1133,7 +1138,7 @@ template <typename T> struct ColsC2C {
                             if (inverse) x.y = -x.y;
                             x = cscale(x, scale);
                             if (out_ramp != nullptr) x = cmul(x, f);
-                            ob[(Rs - lo) * B + vv] = x;
+                            ob[(Rs - lo) * Bi + vv] = x;
                         }
                     }
                 }
@@ -1151,7 +1156,7 @@ template <typename T> struct ColsC2C {
                         if (inverse) x.y = -x.y;
                         x = cscale(x, scale);
                         if (tw4) {
-                            const long m = o * i2[vv];
+                            const int m = (int)o * i2[vv];
                             cplx<T> w = tw4_hi ? cmul(__ldg(tw4_hi + (m >> 13)), __ldg(tw4 + (m & 8191))) : __ldg(tw4 + m);
                             if (inverse) w.y = -w.y;
                             x = cmul(x, w);
@@ -2129,11 +2134,13 @@ cols_bins_kernel(const __grid_constant__ ColsFused<float, EPI_BINS_POWER> io, co
 // half-spectrum rows of every plane starting at ky0 (rows % SEQ == 0, or rows == 1 for the Nyquist row), the grid is a
 // multiple of the rows / SEQ row groups of a plane, so a CTA meets the same rows of every plane it processes.  Once per
 // launch each thread looks up the bins of its E cells in the host-built LUT and the CTA counting-sorts its cells by bin
-// (native integer atomics): every cell gets a fixed slot `pos` in a staging array ordered by bin, every bin a fixed
-// segment.  Per tile: each thread drops its E values at their slots, one barrier, then one thread per segment adds its
-// contiguous run in fp32 and issues ONE fp64 atomic to the plane's bins.  The mirror image (-ky, -kx) of a cell shares
-// its bin (radial bins): rows 0 < ky < Ny/2 count twice, rows 0 and Ny/2 (which hold both signs of kx) once.
-// rows == 1: the SEQ row slots of a CTA are the same row (ky0) of SEQ consecutive planes; segments are per (slot, bin).
+// (native integer atomics; cells of one warp that share a bin get consecutive slots, so the per-tile scatter is nearly
+// conflict-free): every cell gets a fixed slot `pos` in a staging array ordered by bin, and a static table names the bin
+// of every slot.  Per tile: each thread drops its E values at their slots, one barrier, then every thread adds up its own
+// E CONSECUTIVE slots (perfectly balanced, 128-bit loads) -- runs that end inside its slots are complete after a warp-wide
+// segmented scan of the partial sums and go to the plane's fp64 bins with one atomic each.  The mirror image (-ky, -kx) of
+// a cell shares its bin (radial bins): rows 0 < ky < Ny/2 count twice, rows 0 and Ny/2 (which hold both signs of kx) once.
+// rows == 1: the SEQ row slots of a CTA are the same row (ky0) of SEQ consecutive planes; bins are keyed per (slot, bin).
 // =============================================================================================
 struct RowsBins {
     RowsC2CPower<float> base;   // in, logNy, H, shifts, scale, column-line completion tables (out unused)
@@ -2148,13 +2155,16 @@ __global__ void __launch_bounds__((1 << (LOG2L - LOGE)) * SEQ, min_blocks_for((1
 rows_bins_kernel(RowsBins io, const float2* __restrict__ tw) {
     using T = float;
     using G_ = Geometry<LOG2L, LOGE>;
-    constexpr int E = G_::E, NT = G_::NT, NTHR = NT * SEQ, Nx = 1 << LOG2L;
+    constexpr int E = G_::E, NT = G_::NT, NTHR = NT * SEQ, Nx = 1 << LOG2L, NCELL = SEQ * Nx;
     constexpr int R = 1 << G_::LOGR_LAST, G = E / R;
+    static_assert(NCELL == NTHR * E && E == 16, "every thread sums E = 16 consecutive slots");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx<T>* smem = reinterpret_cast<cplx<T>*>(smem_raw);
     float* stage = reinterpret_cast<float*>(smem_raw);                               // aliases the exchange buffer
-    int2* segtab = reinterpret_cast<int2*>(smem_raw + (size_t)SEQ * G_::LPAD * sizeof(cplx<T>));   // (start, count) per segment
-    const int s = threadIdx.x / NT, u = threadIdx.x % NT;
+    unsigned char* tail = smem_raw + (size_t)SEQ * G_::LPAD * sizeof(cplx<T>);
+    unsigned short* binid = reinterpret_cast<unsigned short*>(tail);                 // [NCELL] key of every slot (0xFFFF = unused)
+    int* cnt = reinterpret_cast<int*>(tail + NCELL * sizeof(unsigned short));        // [nseg] counters -> segment starts (setup only)
+    const int s = threadIdx.x / NT, u = threadIdx.x % NT, lane = threadIdx.x & 31;
     cplx<T>* sm = smem + s * G_::LPAD;
     const bool per_slot = io.rows == 1;              // Nyquist-row launch: one plane per row slot
     const int P = per_slot ? SEQ : 1;
@@ -2165,10 +2175,10 @@ rows_bins_kernel(RowsBins io, const float2* __restrict__ tw) {
     const int Ny = 1 << io.base.logNy;
     const int sy = io.base.shift_y ? Ny / 2 : 0, sx = io.base.shift_x ? Nx / 2 : 0;
     // ---- once per launch: bins of this thread's cells, counting sort of the CTA's cells by (slot, bin)
-    int* cnt = reinterpret_cast<int*>(segtab);        // nseg counters, then turned into (start, count)
-    for (int i = threadIdx.x; i < 2 * nseg; i += NTHR) cnt[i] = 0;
+    for (int i = threadIdx.x; i < nseg; i += NTHR) cnt[i] = 0;
+    for (int i = threadIdx.x; i < NCELL; i += NTHR) binid[i] = 0xFFFFu;
     __syncthreads();
-    unsigned short key[E], rank[E];
+    unsigned short key[E];
     {
         const int* lrow = io.lut + (long)((ky + sy) & (Ny - 1)) * Nx;
 #pragma unroll
@@ -2177,13 +2187,8 @@ rows_bins_kernel(RowsBins io, const float2* __restrict__ tw) {
             for (int t = 0; t < R; ++t) {
                 const int kx = final_index<LOG2L, LOGE>(u, g, t);
                 const int b = __ldg(lrow + ((kx + sx) & (Nx - 1)));
-                const int i = g + t * G;
-                key[i] = 0xFFFFu; rank[i] = 0;
-                if (b >= 0 && b < io.nbins) {
-                    const int k = (per_slot ? s * io.nbins : 0) + b;
-                    key[i] = (unsigned short)k;
-                    rank[i] = (unsigned short)atomicAdd(cnt + k, 1);
-                }
+                key[g + t * G] = (b >= 0 && b < io.nbins) ? (unsigned short)((per_slot ? s * io.nbins : 0) + b) : (unsigned short)0xFFFFu;
+                if (b >= 0 && b < io.nbins) atomicAdd(cnt + key[g + t * G], 1);
             }
     }
     __syncthreads();
@@ -2196,22 +2201,47 @@ rows_bins_kernel(RowsBins io, const float2* __restrict__ tw) {
         for (int i = lo; i < hi; ++i) local += cnt[i];
         int incl = local;
 #pragma unroll
-        for (int off = 1; off < 32; off <<= 1) { const int o = __shfl_up_sync(0xffffffffu, incl, off); if ((threadIdx.x & 31) >= off) incl += o; }
-        if ((threadIdx.x & 31) == 31) scan_part[threadIdx.x >> 5] = incl;
+        for (int off = 1; off < 32; off <<= 1) { const int o = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += o; }
+        if (lane == 31) scan_part[threadIdx.x >> 5] = incl;
         __syncthreads();
-        int base = 0;
-        for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) base += scan_part[w];
-        int run = base + incl - local;
-        int counts[16];   // per <= 16 (nseg <= 4096, NTHR = 256)
-        for (int i = lo, j = 0; i < hi; ++i, ++j) counts[j] = cnt[i];
-        __syncthreads();
-        for (int i = lo, j = 0; i < hi; ++i, ++j) { segtab[i] = make_int2(run, counts[j]); run += counts[j]; }
+        int run = incl - local;
+        for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) run += scan_part[w];
+        for (int i = lo; i < hi; ++i) {   // slots [run, run + count) belong to segment i; the counter becomes the fill cursor
+            const int c = cnt[i];
+            for (int j = 0; j < c; ++j) binid[run + j] = (unsigned short)i;
+            cnt[i] = run;
+            run += c;
+        }
     }
     __syncthreads();
+    // slots: the cells of a warp that share a key take consecutive slots (consecutive kx of a row mostly share the bin)
     unsigned short pos[E];
 #pragma unroll
-    for (int i = 0; i < E; ++i) pos[i] = key[i] == 0xFFFFu ? (unsigned short)0xFFFFu : (unsigned short)(segtab[key[i]].x + rank[i]);
+    for (int i = 0; i < E; ++i) {
+        const unsigned k = key[i];
+        const unsigned grp = __match_any_sync(0xffffffffu, k);
+        const int leader = __ffs(grp) - 1;
+        int base = 0;
+        if (lane == leader && k != 0xFFFFu) base = atomicAdd(cnt + k, __popc(grp));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        pos[i] = k == 0xFFFFu ? (unsigned short)0xFFFFu : (unsigned short)(base + __popc(grp & ((1u << lane) - 1u)));
+    }
     const float mult = ((ky == 0 || 2 * ky == Ny) ? 1.f : 2.f) * io.base.scale;
+    __syncthreads();
+    // this thread's E consecutive slots: their keys never change
+    unsigned short id[E];
+    {
+        const uint4* pid = reinterpret_cast<const uint4*>(binid + threadIdx.x * E);
+        const uint4 a = pid[0], b = pid[1];
+        const unsigned w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < E; ++i) id[i] = (unsigned short)((w[i >> 1] >> (16 * (i & 1))) & 0xFFFFu);
+    }
+    // the run that reaches this thread's first slot started in an earlier lane of the warp?
+    const unsigned prev_last = __shfl_up_sync(0xffffffffu, (unsigned)id[E - 1], 1);
+    const bool cont_in = lane > 0 && prev_last == id[0];
+    const unsigned next_first = __shfl_down_sync(0xffffffffu, (unsigned)id[0], 1);
+    const bool cont_out = lane < 31 && next_first == id[E - 1];
     // ---- tiles: mode A: plane = blockIdx.x / groups + k * (gridDim.x / groups); mode B: SEQ planes per tile
     const long tiles_total = per_slot ? (io.nplanes + SEQ - 1) / SEQ : io.nplanes;
     const long tstep = gridDim.x / groups;
@@ -2242,16 +2272,41 @@ rows_bins_kernel(RowsBins io, const float2* __restrict__ tw) {
             if (pos[i] != 0xFFFFu) stage[pos[i]] = (f.x * f.x + f.y * f.y) * mult;
         }
         __syncthreads();
-        for (int sg = threadIdx.x; sg < nseg; sg += NTHR) {
-            const int2 sc = segtab[sg];
-            if (sc.y == 0) continue;
-            const float* p = stage + sc.x;
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-            int j = 0;
-            for (; j + 4 <= sc.y; j += 4) { a0 += p[j]; a1 += p[j + 1]; a2 += p[j + 2]; a3 += p[j + 3]; }
-            for (; j < sc.y; ++j) a0 += p[j];
-            const long plane = per_slot ? tile * SEQ + sg / io.nbins : tile;
-            if (plane < io.nplanes) atomicAdd(io.bins + plane * (long)io.nbins + (per_slot ? sg % io.nbins : sg), (double)((a0 + a1) + (a2 + a3)));
+        {
+            auto emit = [&](unsigned k, float val) {
+                if (k == 0xFFFFu) return;
+                const long plane = per_slot ? tile * SEQ + (long)(k / (unsigned)io.nbins) : tile;
+                if (plane < io.nplanes) atomicAdd(io.bins + plane * (long)io.nbins + (per_slot ? k % (unsigned)io.nbins : k), (double)val);
+            };
+            float x[E];
+            const float4* pv = reinterpret_cast<const float4*>(stage + threadIdx.x * E);
+#pragma unroll
+            for (int i = 0; i < E / 4; ++i) { const float4 q = pv[i]; x[4 * i] = q.x; x[4 * i + 1] = q.y; x[4 * i + 2] = q.z; x[4 * i + 3] = q.w; }
+            // runs inside this thread's slots: the first one may have begun in earlier lanes (head), the last one may go on (tail)
+            float acc = x[0], head = 0.f;
+            bool split = false;     // a run boundary inside these slots
+            const unsigned head_key = id[0];
+#pragma unroll
+            for (int i = 1; i < E; ++i) {
+                if (id[i] != id[i - 1]) {
+                    if (!split) { head = acc; split = true; } else emit(id[i - 1], acc);
+                    acc = x[i];
+                } else {
+                    acc += x[i];
+                }
+            }
+            // segmented inclusive scan over the lanes of the partial sum that is still open at the end of each lane
+            float open = acc;
+            bool flag = split || !cont_in;     // the open run began in this lane
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const float y = __shfl_up_sync(0xffffffffu, open, off);
+                const bool fy = __shfl_up_sync(0xffffffffu, (int)flag, off) != 0;
+                if (lane >= off && !flag) { open += y; flag = fy; }
+            }
+            const float before = __shfl_up_sync(0xffffffffu, open, 1);   // sum of the run that reaches this lane's first slot
+            if (split) emit(head_key, head + (cont_in ? before : 0.f));
+            if (!cont_out) emit(id[E - 1], open);
         }
         __syncthreads();   // the staging array is scattered into again by the next transform
     }

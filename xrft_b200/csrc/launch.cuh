@@ -110,7 +110,7 @@ static int launch_rows_bins(const RowsBins& io, cudaStream_t st) {
     if (nseg > 4096 || (io.rows != 1 && io.rows % SEQ != 0)) return 1;
     constexpr size_t smem_x = (size_t)SEQ * G_::LPAD * sizeof(float2);
     static_assert(smem_x >= (size_t)SEQ * (1 << LOG2L) * sizeof(float), "the staging array fits the exchange buffer");
-    constexpr size_t smem = smem_x + 4096 * sizeof(int2);
+    constexpr size_t smem = smem_x + (size_t)SEQ * (1 << LOG2L) * sizeof(unsigned short) + 4096 * sizeof(int);   // + slot keys + counters
     static DevOcc occ_;
     int occ = 0;
     if (int rc = prepare_kernel(kern, threads, smem, &occ_, &occ)) return rc;
