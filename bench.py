@@ -342,18 +342,27 @@ def run_b200(args):
     pts_launch = pts_step * args.steps / n_launch
     avg_ms = tot_ms[dom] / n_launch if n_launch else float("nan")
     achieved = bpp[dom] * pts_launch / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
-    traffic = None
+    # DRAM traffic of the dominant kernel: from the ncu capture in profiles/traffic.json, quoted only while the kernel sources
+    # are the ones the capture was taken from (source hash stored beside it); otherwise null
+    traffic, traffic_note = None, "no ncu capture for the current kernel sources"
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
+            import hashlib
             tj = json.load(open(tp))
-            traffic = tj.get(names[dom], {}).get("dram_bytes_per_point", None)
-            traffic = traffic * pts_launch if traffic is not None else None
+            h = hashlib.sha256()
+            for f in ("fft_core.cuh", "fft_kernels.cuh"):
+                h.update(open(os.path.join(ROOT, "xrft_b200", "csrc", f), "rb").read())
+            if tj.get("kernel_source_sha16") == h.hexdigest()[:16]:
+                bpp_t = tj.get("kernels", {}).get(names[dom], {}).get("dram_bytes_per_point", None)
+                if bpp_t is not None:
+                    traffic = bpp_t * pts_launch
+                    traffic_note = "ncu capture of %s (profiles/traffic.json), same kernel sources" % tj.get("captured")
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": bpp[dom] * pts_launch, "avg_launch_ms": avg_ms,
-                "traffic": traffic,
+                "traffic": traffic, "traffic_source": traffic_note,
                 "kernel_share_of_step": {names[i]: tot_ms[i] / (ms_total if ms_total else 1) for i in range(4)},
                 "pipeline": {"algorithmic_bytes_per_point": 8.0, "achieved": 8.0 * value / world, "frac": 8.0 * value / world / peak}}
 

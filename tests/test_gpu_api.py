@@ -449,12 +449,19 @@ def test_host_streaming_matches_device_path():
         outbuf = torch.empty((24, 128, 256), dtype=torch.float32).pin_memory()
         host2 = xrft.power_spectrum(DataArray(x, dims=["t", "y", "x"], coords=c), dim=["y", "x"], detrend="linear", window="hann", out=outbuf)
         cs = xrft.cross_spectrum(DataArray(x, dims=["t", "y", "x"], coords=c), DataArray(x[::-1].copy(), dims=["t", "y", "x"], coords=c), dim=["y", "x"])
+        iso_h = xrft.isotropic_power_spectrum(DataArray(x, dims=["t", "y", "x"], coords=c), dim=["y", "x"], detrend="constant", window="hann")
+        assert isinstance(iso_h.data, np.ndarray)
     finally:
         A._STREAM_MIN_BYTES, A._STREAM_CHUNK_BYTES = old
     devres = xrft.power_spectrum(DataArray(torch.from_numpy(x).cuda(), dims=["t", "y", "x"], coords=c), dim=["y", "x"], detrend="linear", window="hann")
     np.testing.assert_array_equal(host.values, devres.values)
     np.testing.assert_array_equal(host2.values, devres.values)
     np.testing.assert_array_equal(outbuf.numpy(), devres.values)
+    # radial-bin modes stream too (config 4 from host memory): chunk-wise result == device-resident result == oracle
+    iso_d = xrft.isotropic_power_spectrum(DataArray(torch.from_numpy(x).cuda(), dims=["t", "y", "x"], coords=c), dim=["y", "x"], detrend="constant", window="hann")
+    np.testing.assert_allclose(iso_h.values, iso_d.values, rtol=1e-6)
+    iso_r = O.isotropic_power_spectrum(lab(DataArray(x, dims=["t", "y", "x"], coords=c)), dim=["y", "x"], detrend="constant", window="hann")
+    assert relerr(iso_h.values, iso_r.data) < 1e-3
     ref = O.cross_spectrum(lab(DataArray(x, dims=["t", "y", "x"], coords=c)), lab(DataArray(x[::-1].copy(), dims=["t", "y", "x"], coords=c)), dim=["y", "x"])
     assert relerr(cs.values, ref.data) < 1e-3
 
@@ -616,6 +623,16 @@ def test_lazy_pad_fft_ifft_matches_materialised_path():
         same(back, refb, tol=tol, check_attrs=False)
         un = xrft.unpad(back, {"y": 8, "x": 16})
         assert relerr(un.values, x) < tol
+        # unpad of a deferred inverse transform narrows the stored box (crop in the transform's stores): nothing is computed
+        # until the cropped data is asked for, and the full-size result is never produced
+        from xrft_b200.dataarray import Deferred
+        back2 = xrft.ifft(ft, dim=["freq_y", "freq_x"], real_dim="freq_x")
+        un2 = xrft.unpad(back2, {"y": 8, "x": 16})
+        assert isinstance(back2._store, Deferred) and isinstance(un2._store, Deferred) and un2.shape == (2, 48, 96)
+        assert relerr(un2.values, x) < tol and isinstance(back2._store, Deferred)
+        np.testing.assert_allclose(un2["x"].values, c["x"], atol=1e-9)
+        odd = back2.isel(y=slice(3, 40), x=slice(5, 100))          # odd offsets: scalar store path
+        assert relerr(odd.values, refb.data[:, 3:40, 5:100]) < tol
         # variants of the inverse: unshifted output, true_phase off, explicit lag
         for kw in (dict(shift=False), dict(true_phase=False), dict(lag=[0.0, 0.0])):
             b2 = xrft.ifft(ft, dim=["freq_y", "freq_x"], real_dim="freq_x", **kw)

@@ -53,5 +53,13 @@ for d in data:
         md.append(f"- (traffic parse failed: {e})")
     md.append("")
 open(out_md, "w").write("\n".join(md) + "\n")
+# keyed by the kernel sources the capture was taken from: bench.py only quotes the traffic while the sources are unchanged
+import datetime, hashlib, os
+_root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_h = hashlib.sha256()
+for _f in ("fft_core.cuh", "fft_kernels.cuh"):
+    _h.update(open(os.path.join(_root, "xrft_b200", "csrc", _f), "rb").read())
+traffic = {"kernel_source_sha16": _h.hexdigest()[:16], "captured": datetime.date.today().isoformat(),
+           "how": "ncu --set full --clock-control none, one launch per kernel (dram__bytes_read.sum + dram__bytes_write.sum)", "kernels": traffic}
 json.dump(traffic, open(traffic_json, "w"), indent=1)
 print("\n".join(md[:16])); print(json.dumps(traffic))

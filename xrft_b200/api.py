@@ -27,7 +27,7 @@ import os
 import numpy as np
 import scipy.signal as sps
 
-from .dataarray import DataArray, Coordinates, LazyPad, from_any, either_dict_or_kwargs, _is_torch
+from .dataarray import DataArray, Coordinates, LazyPad, LazyIrfft2, from_any, either_dict_or_kwargs, _is_torch
 from . import _lib as L
 
 __all__ = [
@@ -460,7 +460,7 @@ def _run_forward(P, das, mode, detrend, window, scale, ramps=None, weight=None, 
         _check_out(out, lead_shape + list(P["N"][:-1]) + [W], (np.complex64 if cplx else np.float32) if f32 else (np.complex128 if cplx else np.float64))
         if not (host_in and trailing):
             raise ValueError("out= is only supported for host inputs whose transform axes are trailing")
-    if (host_in and trailing and nd > ntrans and not any_reversed and not with_phase and mode not in (L.EPI_BINS_POWER, L.EPI_BINS_CROSS)
+    if (host_in and trailing and nd > ntrans and not any_reversed and not with_phase
             and das[0].data.dtype in (np.float32, np.float64) and all(d.data.dtype == das[0].data.dtype for d in das)
             and das[0].data.nbytes >= _STREAM_MIN_BYTES and das[0].shape[0] >= 2):
         from . import backend as B
@@ -470,7 +470,7 @@ def _run_forward(P, das, mode, detrend, window, scale, ramps=None, weight=None, 
 
         def core(x1, x2):
             return _spectral_core(x1, x2, ntrans, mode, detrend=detrend, windows=wins, keep_half=keep_half, shift=shifts,
-                                  ramps=ramps, weight=weight, scale=scale)
+                                  ramps=ramps, weight=weight, scale=scale, lut=lut, nbins=nbins)
 
         oh = None
         if out is not None:
@@ -634,8 +634,11 @@ def ifft(daft, spacing_tol=1e-3, dim=None, real_dim=None, shift=True, true_phase
         if (np.array_equal(oy_, (np.arange(ny_) + s0) % ny_) and np.array_equal(ox_, np.arange(ox_.size))
                 and B.fft2r_supported(ny_, n_outs[1], torch.float32 if t.dtype == torch.complex64 else torch.float64)):
             tr = lambda v: torch.from_numpy(np.ascontiguousarray(v)) if v is not None else None
-            f = B.fft2r_inverse(t, (ny_ // 2 + s0) % ny_, tr(in_ramps[dim[0]]) if true_phase else None,
-                                tr(in_ramps[dim[1]]) if true_phase else None, out_shifts, scale)
+            # deferred: xrft.unpad of the result narrows the box the inverse transform stores before anything is computed
+            f = LazyIrfft2(t, (ny_ // 2 + s0) % ny_, tr(in_ramps[dim[0]]) if true_phase else None,
+                           tr(in_ramps[dim[1]]) if true_phase else None, out_shifts, scale)
+            if inv is not None or host_in:
+                f = f.materialize()
     if f is None:
         # sort + ramp + ifftshift of the input: data movement (gather) + one per-axis complex vector
         for i, d in enumerate(dim):

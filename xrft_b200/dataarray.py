@@ -101,7 +101,24 @@ def _normalize_coords(coords, dims, shape) -> "Coordinates":
     return out
 
 
-class LazyPad:
+class Deferred:
+    """A device-resident array that has not been computed yet.  DataArray keeps such an object in place of the data until
+    something asks for it (`.data`, `.values`, arithmetic ...); shape / ndim are known up front.  Two kinds exist, both so
+    that pure data movement between two transforms is folded into the transform kernels (xrftb_fft2r) instead of being a
+    pass of its own: LazyPad (xrft.pad -> xrft.fft) and LazyIrfft2 (xrft.ifft -> xrft.unpad)."""
+
+    shape: tuple = ()
+    ndim: int = 0
+
+    def materialize(self):   # pragma: no cover - interface
+        raise NotImplementedError
+
+    def try_slice(self, key):
+        """a deferred array equal to this one indexed by `key` (one entry per axis), or None if that needs the data"""
+        return None
+
+
+class LazyPad(Deferred):
     """Zero padding of a device-resident array that has not been carried out yet (xrft.pad of a CUDA tensor, mode
     'constant', value 0): the transform kernels read the unpadded array through load predicates (xrftb_fft2r), so the padded
     copy is only materialised -- by the CUDA pad kernel -- if something else asks for the data."""
@@ -120,6 +137,44 @@ class LazyPad:
         return self._mat
 
 
+class LazyIrfft2(Deferred):
+    """Result of xrft.ifft(real_dim=...) over two trailing axes that has not been computed yet: slicing the two transform
+    axes (xrft.unpad, padding.py:425-446) only narrows the box of the result that the inverse transform will store
+    (xrftb_fft2r crop), so the padding region is never transformed back along x nor written."""
+
+    def __init__(self, f, in_roll_y, ramp_y, ramp_x, out_roll, scale, crop=None):
+        self.f, self.in_roll_y, self.ramp_y, self.ramp_x, self.out_roll, self.scale = f, in_roll_y, ramp_y, ramp_x, tuple(out_roll), scale
+        ny, nx = f.shape[-2], 2 * (f.shape[-1] - 1)
+        self.crop = crop if crop is not None else ((0, ny), (0, nx))
+        self.shape = tuple(f.shape[:-2]) + (self.crop[0][1], self.crop[1][1])
+        self.ndim = len(self.shape)
+        self._mat = None
+
+    def materialize(self):
+        if self._mat is None:
+            from . import backend as B
+            ny, nx = self.f.shape[-2], 2 * (self.f.shape[-1] - 1)
+            full = self.crop == ((0, ny), (0, nx))
+            self._mat = B.fft2r_inverse(self.f, self.in_roll_y, self.ramp_y, self.ramp_x, self.out_roll, self.scale, None if full else self.crop)
+        return self._mat
+
+    def try_slice(self, key):
+        if self._mat is not None or len(key) != self.ndim:
+            return None
+        for k, n in zip(key[:-2], self.shape[:-2]):
+            if not (isinstance(k, slice) and k.indices(n) == (0, n, 1)):
+                return None
+        crop = []
+        for k, (off, n) in zip(key[-2:], self.crop):
+            if not isinstance(k, slice):
+                return None
+            start, stop, step = k.indices(n)
+            if step != 1 or stop <= start:
+                return None
+            crop.append((off + start, stop - start))
+        return LazyIrfft2(self.f, self.in_roll_y, self.ramp_y, self.ramp_x, self.out_roll, self.scale, tuple(crop))
+
+
 class DataArray:
     __array_priority__ = 60
 
@@ -130,7 +185,7 @@ class DataArray:
             name = name if name is not None else data.name
             attrs = attrs if attrs is not None else data.attrs
             data = data.data
-        if not _is_torch(data) and not isinstance(data, LazyPad):
+        if not _is_torch(data) and not isinstance(data, Deferred):
             data = np.asarray(data)
         self._store = data
         ndim = data.ndim
@@ -160,7 +215,7 @@ class DataArray:
     @property
     def _data(self):
         st = self._store
-        if type(st) is LazyPad:   # deferred zero padding: carried out (CUDA pad kernel) on first real access
+        if isinstance(st, Deferred):   # deferred padding / inverse transform: carried out on first real access
             st = self._store = st.materialize()
         return st
 
@@ -390,15 +445,19 @@ class DataArray:
             key.append(k)
             if not isinstance(k, numbers.Integral):
                 newdims.append(d)
-        # apply one axis at a time (avoids numpy fancy-index broadcasting between axes)
-        data = self._data
-        ax = 0
-        for d, k in zip(self._dims, key):
-            sl = [slice(None)] * data.ndim
-            sl[ax] = k if not (isinstance(k, np.ndarray) and _is_torch(data)) else torch.as_tensor(k, device=data.device)
-            data = data[tuple(sl)]
-            if not isinstance(k, numbers.Integral):
-                ax += 1
+        deferred = self._store.try_slice(key) if isinstance(self._store, Deferred) else None
+        if deferred is not None:   # slicing a deferred inverse transform narrows what it will store (unpad crop)
+            data = deferred
+        else:
+            # apply one axis at a time (avoids numpy fancy-index broadcasting between axes)
+            data = self._data
+            ax = 0
+            for d, k in zip(self._dims, key):
+                sl = [slice(None)] * data.ndim
+                sl[ax] = k if not (isinstance(k, np.ndarray) and _is_torch(data)) else torch.as_tensor(k, device=data.device)
+                data = data[tuple(sl)]
+                if not isinstance(k, numbers.Integral):
+                    ax += 1
         coords = Coordinates()
         for name, c in self._coords.items():
             cidx = {d: idx[d] for d in c.dims if d in idx}
