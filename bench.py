@@ -109,18 +109,20 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     workers = min(cores, 32)
     ns = args.cpu_slices or workers
-    # one slice costs ~8 s on one core (dense least-squares detrend): keep the whole run within a few minutes
+    # one slice costs ~4-8 s on one core (dense least-squares detrend).  Every one of the W + K steps runs: the first step is
+    # timed, and if W + K steps of that size would not fit the budget the sample per step shrinks (fewer slices per step,
+    # the metric is per point) instead of the run being cut short
     vals = []
-    budget_s = 240.0
-    t_start = time.perf_counter()
-    for i in range(args.warmup + args.steps):
+    budget_s = 200.0
+    nsteps = args.warmup + args.steps
+    v, dt = cpu_sample(args.ny, args.nx, ns, workers)
+    if dt * nsteps > budget_s:
+        ns = max(1, int(ns * budget_s / (dt * nsteps)))
+        workers = min(workers, ns)
+    for i in range(nsteps):
         v, dt = cpu_sample(args.ny, args.nx, ns, workers)
         if i >= args.warmup:
             vals.append((v, dt))
-        if time.perf_counter() - t_start > budget_s and vals:
-            break
-    if not vals:
-        vals.append((v, dt))
     value = float(np.mean([v for v, _ in vals]))
     ms = float(np.mean([d for _, d in vals])) * 1e3
     sample = f"{ns} slices of {args.ny}x{args.nx} float32 per step, {workers} threads (BLAS threads = 1)"

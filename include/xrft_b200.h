@@ -150,6 +150,14 @@ int xrftb_spectral_post(const void* in1, const void* in2, void* out, int dtype, 
                         int64_t k1, int64_t k2, int hermitian, int keep_half, const int* shift, const void* const* ramp,
                         const void* weight, double scale, void* stream);
 
+/* The same epilogue with the Welch segment mean folded in (chunks_to_segments=True followed by .mean over the `<dim>_segment`
+ * axis: xrft.py:106-136, 390-391; tests/test_xrft.py:273-337): the batch is viewed as [outer][seg_n][seg_inner] and `out`
+ * ([outer][seg_inner][k0][k1][W]) receives the mean over seg_n -- the per-segment spectra are never written.  Modes COMPLEX,
+ * POWER, CROSS (a mean of phases is not a phase).  `out` is zeroed by the call; accumulation uses global atomics. */
+int xrftb_spectral_post_segmean(const void* in1, const void* in2, void* out, int dtype, int mode, int64_t batch, int64_t k0,
+                                int64_t k1, int64_t k2, int hermitian, int keep_half, const int* shift, const void* const* ramp,
+                                const void* weight, double scale, int64_t seg_n, int64_t seg_inner, void* stream);
+
 /* circular roll + scale over up to 3 trailing axes, real or complex: out[(i + s) % n] = in[i] * scale.
  * Replaces the output-side fftm.ifftshift / fftm.fftshift and the `/ prod(spacing)` of xrft.ifft
  * (xrft.py:617-621, 641-642).  Out of place only. */

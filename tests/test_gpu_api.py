@@ -638,3 +638,38 @@ def test_lazy_pad_fft_ifft_matches_materialised_path():
             b2 = xrft.ifft(ft, dim=["freq_y", "freq_x"], real_dim="freq_x", **kw)
             r2 = O.ifft(ref, dim=["freq_y", "freq_x"], real_dim="freq_x", **kw)
             same(b2, r2, tol=tol, check_attrs=False)
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_welch_segment_mean_is_an_epilogue_reduction(dt):
+    """chunks_to_segments=True followed by .mean('<dim>_segment') (Welch; xrft/tests/test_xrft.py:273-337, 406-442): on device
+    data the per-segment spectra stay deferred and the mean is reduced inside the spectral epilogue
+    (xrftb_spectral_post_segmean); any other access computes the per-segment spectra as before"""
+    import torch
+    from xrft_b200.dataarray import Deferred
+    rng = np.random.default_rng(72)
+    tol = 1e-9 if dt == np.float64 else 1e-3
+    x = (rng.standard_normal((3, 256, 5)) + 0.2 * np.arange(256)[None, :, None]).astype(dt)
+    c = {"a": np.arange(3.0), "t": np.arange(256) * 0.5, "b": np.arange(5.0)}
+    da_h = DataArray(x, dims=["a", "t", "b"], coords=c).chunk({"t": 64})
+    da_d = DataArray(torch.from_numpy(x).cuda(), dims=["a", "t", "b"], coords=c).chunk({"t": 64})
+    for kw in (dict(dim="t", chunks_to_segments=True, window="hann", detrend="linear"),
+               dict(dim="t", real_dim="t", chunks_to_segments=True, window="hann", detrend="constant", window_correction=True)):
+        ref = O.power_spectrum(lab(da_h), **kw)
+        ps = xrft.power_spectrum(da_d, **kw)
+        assert isinstance(ps._store, Deferred) and ps.dims == ref.dims and ps.shape == ref.data.shape
+        welch = ps.mean("t_segment")
+        assert isinstance(ps._store, Deferred)                       # the per-segment spectra were never materialised
+        assert welch.dims == tuple(d for d in ref.dims if d != "t_segment")
+        ax = ref.dims.index("t_segment")
+        assert relerr(welch.values, ref.data.mean(axis=ax)) < tol
+        same(ps, ref, tol=tol, check_attrs=False)                   # other accesses compute them
+        np.testing.assert_allclose(welch["freq_t"].values, ref.coords["freq_t"], rtol=1e-12)
+    # cross spectrum of two chunked series, segments on the trailing axis
+    y = (rng.standard_normal((4, 512))).astype(dt); z = (y + 0.3 * rng.standard_normal((4, 512))).astype(dt)
+    cc = {"a": np.arange(4.0), "t": np.arange(512) * 1.0}
+    kw = dict(dim="t", chunks_to_segments=True, window="hann", detrend="constant")
+    mk2 = lambda v, dev: DataArray(torch.from_numpy(v).cuda() if dev else v, dims=["a", "t"], coords=cc).chunk({"t": 128})
+    cs = xrft.cross_spectrum(mk2(y, True), mk2(z, True), **kw)
+    refc = O.cross_spectrum(lab(mk2(y, False)), lab(mk2(z, False)), **kw)
+    assert relerr(cs.mean("t_segment").values, refc.data.mean(axis=refc.dims.index("t_segment"))) < tol

@@ -29,6 +29,7 @@ EXPORTS = [
     "xrftb_moments",
     "xrftb_detrend_window",
     "xrftb_spectral_post",
+    "xrftb_spectral_post_segmean",
     "xrftb_roll_scale",
     "xrftb_pad",
     "xrftb_binned_sum",
@@ -121,6 +122,9 @@ def load():
     lib.xrftb_detrend_window.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64, vp]
     lib.xrftb_spectral_post.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int,
                                         C.c_int, ip, C.POINTER(vp), vp, C.c_double, vp]
+    lib.xrftb_spectral_post_segmean.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int,
+                                                C.c_int, ip, C.POINTER(vp), vp, C.c_double, C.c_int64, C.c_int64, vp]
+    lib.xrftb_spectral_post_segmean.restype = C.c_int
     lib.xrftb_roll_scale.argtypes = [vp, vp, C.c_int, C.c_int] + [C.c_int64] * 7 + [C.c_double, vp]
     lib.xrftb_fft2r_workspace.restype = C.c_size_t
     lib.xrftb_fft2r_workspace.argtypes = [C.POINTER(Fft2rDesc)]

@@ -27,7 +27,7 @@ import os
 import numpy as np
 import scipy.signal as sps
 
-from .dataarray import DataArray, Coordinates, LazyPad, LazyIrfft2, from_any, either_dict_or_kwargs, _is_torch
+from .dataarray import DataArray, Coordinates, LazyPad, LazyIrfft2, LazySegSpectrum, from_any, either_dict_or_kwargs, _is_torch
 from . import _lib as L
 
 __all__ = [
@@ -211,7 +211,7 @@ def _is_pow2(n):
 
 
 def _spectral_core(x1, x2, ntrans, mode, *, detrend=None, windows=None, keep_half=False, shift=None, ramps=None,
-                   weight=None, scale=1.0, lut=None, nbins=0, with_phase=False, pad2=None):
+                   weight=None, scale=1.0, lut=None, nbins=0, with_phase=False, pad2=None, seg_axis=None):
     """Transform the last `ntrans` axes of device tensor(s) x1 (,x2) and apply the epilogue.
 
     Picks the fused 2-D real kernel chain when it applies, otherwise composes
@@ -241,7 +241,7 @@ def _spectral_core(x1, x2, ntrans, mode, *, detrend=None, windows=None, keep_hal
     shape = x1.shape
 
     # ---- fused path: real 2-D, power-of-two sizes
-    if (is_real and ntrans == 2 and B.spectrum2d_supported(shape[-2], shape[-1], x1.dtype, two)
+    if (is_real and ntrans == 2 and B.spectrum2d_supported(shape[-2], shape[-1], x1.dtype, two) and seg_axis is None
             and (not bins_mode or nbins <= 1024) and not (keep_half and shift[1])):
         return B.spectrum2d(
             x1, x2, mode, detrend=det, win_y=tt(wins[0]), win_x=tt(wins[1]), keep_half=keep_half, shift_y=shift[0],
@@ -266,7 +266,8 @@ def _spectral_core(x1, x2, ntrans, mode, *, detrend=None, windows=None, keep_hal
         fs.append(B.rfftn(x, axes) if is_real else B.fftn(x, axes))
     post_mode = {L.EPI_BINS_POWER: L.EPI_POWER, L.EPI_BINS_CROSS: L.EPI_CROSS}.get(mode, mode)
     out = B.spectral_post(fs[0], fs[1] if two else None, post_mode, ntrans, shape[-1], hermitian=is_real,
-                          keep_half=keep_half, shift=shift, ramps=[tt(r) for r in ramps], weight=tt(weight), scale=scale)
+                          keep_half=keep_half, shift=shift, ramps=[tt(r) for r in ramps], weight=tt(weight), scale=scale,
+                          seg_axis=seg_axis)
     if bins_mode:
         return B.binned_sum(out, lut, nbins, 2)
     if with_phase:   # composed path: the phase is a second epilogue over the same two transforms
@@ -435,7 +436,7 @@ def _check_out(out, shape, np_dtype):
 
 
 def _run_forward(P, das, mode, detrend, window, scale, ramps=None, weight=None, lut=None, nbins=0, out=None, plans=None,
-                 with_phase=False):
+                 with_phase=False, seg_dim=None):
     """Numerics of fft/power/cross for the prepared plan P on one or two DataArrays (already stacked/transposed).
     Container convention: host (numpy) inputs give a numpy result, device (torch CUDA) inputs a torch CUDA result."""
     torch = _torch()
@@ -498,9 +499,19 @@ def _run_forward(P, das, mode, detrend, window, scale, ramps=None, weight=None, 
         xs = [x.to(dt) for x in xs]
     if real_dim is not None and xs[0].is_complex():
         raise ValueError("real_dim requires real input data")
+    seg_axis = None
+    if seg_dim is not None:   # Welch: mean over the segment axis inside the spectral epilogue
+        lead_axes = [a for a in range(nd) if a not in P["axis_num"]]
+        seg_axis = lead_axes.index(P["da"].get_axis_num(seg_dim))
     res = _spectral_core(xs[0], xs[1] if len(xs) == 2 else None, ntrans, mode, detrend=detrend, windows=wins,
                          keep_half=real_dim is not None, shift=[P["shift"]] * ntrans if real_dim is None else [False] * ntrans,
-                         ramps=ramps, weight=weight, scale=scale, lut=lut, nbins=nbins, with_phase=with_phase, pad2=pad2)
+                         ramps=ramps, weight=weight, scale=scale, lut=lut, nbins=nbins, with_phase=with_phase, pad2=pad2,
+                         seg_axis=seg_axis)
+    if seg_dim is not None:   # axes are now [leading axes without the segment axis] + [transform axes]: back to the array's order
+        dims_all = list(P["da"].dims)
+        cur = [dims_all[a] for a in lead_axes if dims_all[a] != seg_dim] + [dims_all[a] for a in P["axis_num"]]
+        perm = [cur.index(d) for d in dims_all if d != seg_dim]
+        return res.permute(*perm) if perm != list(range(len(perm))) else res
     if with_phase:
         res = tuple(r.permute(*inv) if inv is not None else r for r in res)
         return tuple(r.cpu().numpy() for r in res) if host_in else res
@@ -779,8 +790,21 @@ def _spectrum(da1, da2, mode, dim, real_dim, scaling, window_correction, kwargs,
         n_real = da1.sizes[P["real_dim"]]   # len(da[real_dim]) of the un-segmented array, like the reference (xrft.py:678)
         weight = _real_dim_weights(n_real, P["N"][-1] // 2 + 1)
     lut, nbins = (None, 0) if bins is None else bins(P)
+    plans = [P, P2] if da2 is not None else None
+    seg_dims = [d for d in P["da"].dims if d.endswith("_segment")] if c2s else []
+    if (seg_dims and mode in (L.EPI_POWER, L.EPI_CROSS) and not with_phase and bins is None and out_buf is None
+            and all(_is_torch(d.data) and d.data.is_cuda for d in das) and not any(pl["reversed_dims"] for pl in (plans or [P]))):
+        # chunks_to_segments on device data: the per-segment spectra are deferred, so that a following .mean over a segment
+        # axis (Welch) is reduced inside the spectral epilogue instead of being a pass over spectra written to memory
+        def run(seg_dim):
+            return _run_forward(P, das, mode, detrend_t, window, scale, ramps=ramps, weight=weight, plans=plans, seg_dim=seg_dim)
+
+        shape = list(P["da"].shape)
+        if P["real_dim"] is not None:
+            shape[P["axis_num"][-1]] = P["N"][-1] // 2 + 1
+        return P, LazySegSpectrum(run, shape, seg_dims)
     out = _run_forward(P, das, mode, detrend_t, window, scale, ramps=ramps, weight=weight, lut=lut, nbins=nbins, out=out_buf,
-                       plans=[P, P2] if da2 is not None else None, with_phase=with_phase)
+                       plans=plans, with_phase=with_phase)
     return P, out
 
 

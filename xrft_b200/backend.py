@@ -248,9 +248,11 @@ def detrend_window(x: torch.Tensor, ntrail: int, detrend: int, windows: Sequence
 # (S4) generic spectral epilogue
 # ---------------------------------------------------------------------------------------------
 def spectral_post(f1: torch.Tensor, f2: Optional[torch.Tensor], mode: int, ntrail: int, full_last: int, hermitian: bool,
-                  keep_half: bool, shift: Sequence[bool], ramps: Sequence[Optional[torch.Tensor]], weight, scale: float):
+                  keep_half: bool, shift: Sequence[bool], ramps: Sequence[Optional[torch.Tensor]], weight, scale: float,
+                  seg_axis: Optional[int] = None):
     """f1/f2: complex spectra whose last `ntrail` axes are transform axes; full_last = real-space
-    length of the last axis (needed when hermitian)."""
+    length of the last axis (needed when hermitian).  seg_axis (index of a leading axis): the result is the MEAN over that
+    axis (Welch segments), reduced inside the kernel -- the per-segment spectra are never written."""
     lib = require_cuda()
     f1 = _dev(f1)
     if f2 is not None:
@@ -268,6 +270,15 @@ def spectral_post(f1: torch.Tensor, f2: Optional[torch.Tensor], mode: int, ntrai
     rdt = _TO_REAL[f1.dtype]
     odt = f1.dtype if mode in (L.EPI_COMPLEX, L.EPI_CROSS) else rdt
     oshape = list(f1.shape[: f1.ndim - 1]) + [W]
+    seg_n = seg_inner = 0
+    if seg_axis is not None:
+        lead = list(f1.shape[: f1.ndim - ntrail])
+        if not 0 <= seg_axis < len(lead) or mode == L.EPI_PHASE:
+            raise ValueError("spectral_post: bad segment axis / mode")
+        seg_n, seg_inner = lead[seg_axis], 1
+        for s_ in lead[seg_axis + 1:]:
+            seg_inner *= s_
+        del oshape[seg_axis]
     out = torch.empty(oshape, dtype=odt, device=f1.device)
     sh = [0, 0, 0]
     rp = [None, None, None]
@@ -278,9 +289,14 @@ def spectral_post(f1: torch.Tensor, f2: Optional[torch.Tensor], mode: int, ntrai
     rarr = (C.c_void_p * 3)(*[r.data_ptr() if r is not None else None for r in rp])
     wt = weight.to(device=f1.device, dtype=rdt).contiguous() if weight is not None else None
     with torch.cuda.device(f1.device):
-        rc = lib.xrftb_spectral_post(_ptr(f1), _ptr(f2), _ptr(out), _CPLX[f1.dtype], mode, batch, k[0], k[1], k[2],
-                                     1 if hermitian else 0, 1 if keep_half else 0, _ints(sh), rarr, _ptr(wt), float(scale),
-                                     _stream())
+        if seg_n:
+            rc = lib.xrftb_spectral_post_segmean(_ptr(f1), _ptr(f2), _ptr(out), _CPLX[f1.dtype], mode, batch, k[0], k[1], k[2],
+                                                 1 if hermitian else 0, 1 if keep_half else 0, _ints(sh), rarr, _ptr(wt), float(scale),
+                                                 seg_n, seg_inner, _stream())
+        else:
+            rc = lib.xrftb_spectral_post(_ptr(f1), _ptr(f2), _ptr(out), _CPLX[f1.dtype], mode, batch, k[0], k[1], k[2],
+                                         1 if hermitian else 0, 1 if keep_half else 0, _ints(sh), rarr, _ptr(wt), float(scale),
+                                         _stream())
     L.check(rc, "xrftb_spectral_post")
     return out
 

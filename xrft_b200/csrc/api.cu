@@ -355,6 +355,7 @@ struct PostDesc {
     const void* ramp[3];
     const void* weight;
     double scale;
+    long seg_n, seg_inner;   // seg_n > 0: mean over an axis of the batch (Welch segments): batch = [outer][seg_n][seg_inner]
 };
 
 template <typename T>
@@ -394,6 +395,17 @@ __global__ void __launch_bounds__(256) spectral_post_kernel(const cplx<T>* __res
         T sc = (T)d.scale;
         if (d.weight) sc *= reinterpret_cast<const T*>(d.weight)[f2];
         val = cscale(val, sc);
+        if (d.seg_n > 0) {
+            // segment mean as an epilogue reduction: the per-segment spectra are never written; every value is added (already
+            // divided by the number of segments) to the cell of the reduced array
+            const long span = d.seg_n * d.seg_inner;
+            const long outer = b / span;
+            const long ob = outer * d.seg_inner + (b - outer * span) % d.seg_inner;
+            const long oi = ((ob * d.k0 + o0) * d.k1 + o1) * d.W + o2;
+            if (d.mode == EPI_POWER) atomicAdd(reinterpret_cast<T*>(out) + oi, val.x);
+            else { atomicAdd(reinterpret_cast<T*>(out) + 2 * oi, val.x); atomicAdd(reinterpret_cast<T*>(out) + 2 * oi + 1, val.y); }
+            continue;
+        }
         if (d.mode == EPI_COMPLEX || d.mode == EPI_CROSS) reinterpret_cast<cplx<T>*>(out)[i] = val;
         else if (d.mode == EPI_POWER) reinterpret_cast<T*>(out)[i] = val.x;
         else reinterpret_cast<T*>(out)[i] = xatan2(val.y, val.x);
@@ -1609,12 +1621,13 @@ int xrftb_detrend_window(const void* in, void* out, const double* moments, int d
     return check_launch("detrend_window_kernel");
 }
 
-int xrftb_spectral_post(const void* in1, const void* in2, void* out, int dtype, int mode, int64_t batch, int64_t k0, int64_t k1,
-                        int64_t k2, int hermitian, int keep_half, const int* shift, const void* const* ramp, const void* weight,
-                        double scale, void* stream) {
+static int spectral_post_launch(const void* in1, const void* in2, void* out, int dtype, int mode, int64_t batch, int64_t k0, int64_t k1,
+                                int64_t k2, int hermitian, int keep_half, const int* shift, const void* const* ramp, const void* weight,
+                                double scale, int64_t seg_n, int64_t seg_inner, void* stream) {
     if (!in1 || !out || mode < 0 || mode > XRFTB_EPI_PHASE) { set_error("spectral_post: bad arguments"); return XRFTB_EINVAL; }
     if ((mode == XRFTB_EPI_CROSS || mode == XRFTB_EPI_PHASE) && !in2) { set_error("spectral_post: in2 required"); return XRFTB_EINVAL; }
     if (keep_half && !hermitian) { set_error("spectral_post: keep_half requires hermitian input"); return XRFTB_EINVAL; }
+    if (dtype != XRFTB_F32 && dtype != XRFTB_F64) { set_error("spectral_post: bad dtype"); return XRFTB_EINVAL; }
     PostDesc d{};
     d.mode = mode; d.k0 = k0; d.k1 = k1; d.k2 = k2; d.k2in = hermitian ? k2 / 2 + 1 : k2; d.W = keep_half ? k2 / 2 + 1 : k2;
     d.hermitian = (hermitian && !keep_half) ? 1 : 0;
@@ -1622,13 +1635,33 @@ int xrftb_spectral_post(const void* in1, const void* in2, void* out, int dtype, 
     if (keep_half && d.shift[2]) { set_error("spectral_post: cannot shift the half axis"); return XRFTB_EINVAL; }
     d.weight = weight; d.scale = scale;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (seg_n > 0) {
+        if (mode == XRFTB_EPI_PHASE || seg_inner < 1 || batch % (seg_n * seg_inner) != 0) { set_error("spectral_post_segmean: bad segment layout or mode"); return XRFTB_EINVAL; }
+        d.seg_n = seg_n; d.seg_inner = seg_inner;
+        d.scale = scale / (double)seg_n;
+        const size_t esz = (dtype == XRFTB_F32 ? sizeof(float) : sizeof(double)) * (mode == XRFTB_EPI_POWER ? 1 : 2);
+        cudaError_t e = cudaMemsetAsync(out, 0, (size_t)(batch / seg_n) * k0 * k1 * d.W * esz, st);
+        if (e != cudaSuccess) { set_error("memset: %s", cudaGetErrorString(e)); return XRFTB_ECUDA; }
+    }
     const long total = batch * k0 * k1 * d.W;
     if (dtype == XRFTB_F32)
         spectral_post_kernel<float><<<ew_grid(total), 256, 0, st>>>(reinterpret_cast<const float2*>(in1), reinterpret_cast<const float2*>(in2), out, d, total);
-    else if (dtype == XRFTB_F64)
+    else
         spectral_post_kernel<double><<<ew_grid(total), 256, 0, st>>>(reinterpret_cast<const double2*>(in1), reinterpret_cast<const double2*>(in2), out, d, total);
-    else { set_error("spectral_post: bad dtype"); return XRFTB_EINVAL; }
     return check_launch("spectral_post_kernel");
+}
+
+int xrftb_spectral_post(const void* in1, const void* in2, void* out, int dtype, int mode, int64_t batch, int64_t k0, int64_t k1,
+                        int64_t k2, int hermitian, int keep_half, const int* shift, const void* const* ramp, const void* weight,
+                        double scale, void* stream) {
+    return spectral_post_launch(in1, in2, out, dtype, mode, batch, k0, k1, k2, hermitian, keep_half, shift, ramp, weight, scale, 0, 0, stream);
+}
+
+int xrftb_spectral_post_segmean(const void* in1, const void* in2, void* out, int dtype, int mode, int64_t batch, int64_t k0, int64_t k1,
+                                int64_t k2, int hermitian, int keep_half, const int* shift, const void* const* ramp, const void* weight,
+                                double scale, int64_t seg_n, int64_t seg_inner, void* stream) {
+    if (seg_n < 1) { set_error("spectral_post_segmean: seg_n < 1"); return XRFTB_EINVAL; }
+    return spectral_post_launch(in1, in2, out, dtype, mode, batch, k0, k1, k2, hermitian, keep_half, shift, ramp, weight, scale, seg_n, seg_inner, stream);
 }
 
 int xrftb_binned_sum(const void* array, const int32_t* lut, double* bins, int dtype, int is_complex, int64_t batch, int64_t ncell,

@@ -153,9 +153,12 @@ template <typename T> struct RowsR2CFused {
     }
 
     template <int LOG2L, int SEQ> __device__ __forceinline__ void prefetch(long seq0, long nseq) const {
-        constexpr unsigned row_bytes = (unsigned)(2u << LOG2L) * sizeof(T);
-        if (in_row_stride == (2 << LOG2L) && seq0 + SEQ <= nseq && (row_bytes * SEQ) % 16 == 0)
-            prefetch_l2_bulk(in + seq0 * in_row_stride, row_bytes * SEQ);
+        // the SEQ input rows of an upcoming group are one contiguous block when the rows are dense (full rows, or the
+        // unpadded rows of a zero-padded transform)
+        const long dense = col_hi > 0 ? (long)(col_hi - col_lo) : (long)(2 << LOG2L);
+        const unsigned bytes = (unsigned)(dense * sizeof(T)) * SEQ;
+        if (in_row_stride == dense && seq0 + SEQ <= nseq && bytes % 16 == 0 && ((in_row_stride * sizeof(T) * seq0) % 16) == 0)
+            prefetch_l2_bulk(in + seq0 * in_row_stride, bytes);
     }
 
     template <int LOG2L, int LOGE>
@@ -555,7 +558,12 @@ template <typename T> struct RowsC2R {
     const cplx<T>* in_ramp = nullptr;
     int out_roll = 0, out_lo = 0, out_hi = 0;
 
-    template <int LOG2L, int SEQ> __device__ __forceinline__ void prefetch(long, long) const {}
+    // the half-spectrum rows of an upcoming group -> L2 (the loads of a row happen at the start of its transform)
+    template <int LOG2L, int SEQ> __device__ __forceinline__ void prefetch(long seq0, long nseq) const {
+        const unsigned bytes = (unsigned)(in_stride * sizeof(cplx<T>)) * SEQ;
+        if (seq0 + SEQ <= nseq && bytes % 16 == 0 && ((in_stride * sizeof(cplx<T>) * seq0) % 16) == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0)
+            prefetch_l2_bulk(in + seq0 * in_stride, bytes);
+    }
 
     template <int LOG2L, int LOGE>
     __device__ __forceinline__ void fetch(long, bool, int, cplx<T> (&)[1 << LOGE]) const {}
@@ -1046,8 +1054,37 @@ template <typename T> struct ColsC2C {
     __device__ __forceinline__ void tma_reads_done() const {}
     __device__ __forceinline__ void tma_drain() const {}
     template <int LOG2L, int LOGE> __device__ __forceinline__ void fix_fetch(long, int, cplx<T> (&)[1 << LOGE]) const {}
+    // Everything that CONSUMES the loaded values (input ramp, conjugation of the inverse-through-forward trick) happens here,
+    // at the start of the tile's transform -- not in load(), which runs one tile ahead: values consumed right after their
+    // load would stall the thread on the memory latency that the software pipeline is there to hide.
     template <int LOG2L, int LOGE, int C, int V>
-    __device__ __forceinline__ void fix_apply(long, int, int, const cplx<T> (&)[1 << LOGE], cplx<T> (&)[V][1 << LOGE], float* = nullptr, const cplx<T>* = nullptr, float4 = make_float4(1.f, 1.f, 1.f, 1.f)) const {}
+    __device__ __forceinline__ void fix_apply(long tile, int u, int cg, const cplx<T> (&)[1 << LOGE], cplx<T> (&v)[V][1 << LOGE], float* = nullptr, const cplx<T>* = nullptr, float4 = make_float4(1.f, 1.f, 1.f, 1.f)) const {
+        constexpr int NT = Geometry<LOG2L, LOGE>::NT;
+        if (hook_n > 0 && in_ramp != nullptr) {
+            const long a = tile / tiles_per_row;
+            const long b0 = (tile - a * tiles_per_row) * C + cg * V;
+            const int n = (int)hook_n;
+            const int rstep = NT * (int)row_mul;
+#pragma unroll
+            for (int vv = 0; vv < V; ++vv) {
+                const unsigned bb = (unsigned)(b0 + vv);
+                const int i2 = row_div ? (int)(bb / (unsigned)row_div) : 0;
+                const int r0 = u * (int)row_mul + i2 + (int)in_roll;
+#pragma unroll
+                for (int q = 0; q < (1 << LOGE); ++q) {
+                    int rs = r0 + q * rstep;
+                    if (rs >= n) rs -= n;
+                    v[vv][q] = cmul(v[vv][q], __ldg(in_ramp + rs));
+                }
+            }
+        }
+        if (inverse) {
+#pragma unroll
+            for (int vv = 0; vv < V; ++vv)
+#pragma unroll
+                for (int q = 0; q < (1 << LOGE); ++q) v[vv][q].y = -v[vv][q].y;
+        }
+    }
 
     template <int LOG2L, int LOGE, int C, int V>
     __device__ __forceinline__ void load(long tile, int u, int cg, cplx<T> (&v)[V][1 << LOGE], int) const {
@@ -1073,11 +1110,7 @@ template <typename T> struct ColsC2C {
                     int rs = r0 + q * rstep;
                     if (rs >= n) rs -= n;
                     cplx<T> x = mk<T>(0, 0);
-                    if (colok && rs >= lo && rs < hi) {
-                        x = base[rs * pitch + bcol];
-                        if (in_ramp != nullptr) x = cmul(x, __ldg(in_ramp + rs));
-                    }
-                    if (inverse) x.y = -x.y;
+                    if (colok && rs >= lo && rs < hi) x = base[rs * pitch + bcol];
                     v[vv][q] = x;
                 }
             }
@@ -1091,7 +1124,6 @@ template <typename T> struct ColsC2C {
             for (int vv = 0; vv < V; ++vv) {
                 cplx<T> x = mk<T>(0, 0);
                 if (b0 + vv < B) x = p[q * qstep + vv];
-                if (inverse) x.y = -x.y;
                 v[vv][q] = x;
             }
         }

@@ -117,6 +117,10 @@ class Deferred:
         """a deferred array equal to this one indexed by `key` (one entry per axis), or None if that needs the data"""
         return None
 
+    def try_mean(self, dims, dim):
+        """the mean of this array over `dim` (a name out of `dims`) computed without materialising it, or None"""
+        return None
+
 
 class LazyPad(Deferred):
     """Zero padding of a device-resident array that has not been carried out yet (xrft.pad of a CUDA tensor, mode
@@ -173,6 +177,31 @@ class LazyIrfft2(Deferred):
                 return None
             crop.append((off + start, stop - start))
         return LazyIrfft2(self.f, self.in_roll_y, self.ramp_y, self.ramp_x, self.out_roll, self.scale, tuple(crop))
+
+
+class LazySegSpectrum(Deferred):
+    """Per-segment spectra (chunks_to_segments=True, xrft.py:106-136) that have not been computed yet: `.mean("<dim>_segment")`
+    -- Welch's method, xrft/tests/test_xrft.py:273-337 -- runs the transform with the segment mean folded into the spectral
+    epilogue (xrftb_spectral_post_segmean), so the per-segment spectra are never written; any other access computes them."""
+
+    def __init__(self, run, shape, seg_dims):
+        self.run, self.shape, self.seg_dims = run, tuple(int(n) for n in shape), tuple(seg_dims)
+        self.ndim = len(self.shape)
+        self._mat = None
+
+    def materialize(self):
+        if self._mat is None:
+            self._mat = self.run(None)
+        return self._mat
+
+    def try_mean(self, dims, dim):
+        if isinstance(dim, (list, tuple)):
+            if len(dim) != 1:
+                return None
+            dim = dim[0]
+        if self._mat is not None or dim not in self.seg_dims or dim not in dims:
+            return None
+        return self.run(dim)
 
 
 class DataArray:
@@ -641,6 +670,16 @@ class DataArray:
         return self._replace(data=data, dims=newdims, coords=coords, attrs=self.attrs if _KeepAttrs.value else None)
 
     def mean(self, dim=None, **kw):
+        if isinstance(self._store, Deferred) and dim is not None:
+            data = self._store.try_mean(self._dims, dim)   # e.g. Welch: segment mean inside the spectral epilogue
+            if data is not None:
+                dims = [dim] if isinstance(dim, str) else list(dim)
+                coords = Coordinates()
+                for name, c in self._coords.items():
+                    if not any(d in dims for d in c.dims):
+                        OrderedDict.__setitem__(coords, name, c)
+                return self._replace(data=data, dims=[d for d in self._dims if d not in dims], coords=coords,
+                                     attrs=self.attrs if _KeepAttrs.value else None)
         return self._reduce(np.mean, (lambda t, ax: t.mean(dim=ax)) if torch is not None else None, dim)
 
     def sum(self, dim=None, **kw):
