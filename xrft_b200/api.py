@@ -802,7 +802,8 @@ def _spectrum(da1, da2, mode, dim, real_dim, scaling, window_correction, kwargs,
         shape = list(P["da"].shape)
         if P["real_dim"] is not None:
             shape[P["axis_num"][-1]] = P["N"][-1] // 2 + 1
-        return P, LazySegSpectrum(run, shape, seg_dims)
+        nat_dims = [_new_name(d, prefix) if d in P["dim"] else d for d in P["da"].dims]
+        return P, LazySegSpectrum(run, shape, nat_dims, seg_dims)
     out = _run_forward(P, das, mode, detrend_t, window, scale, ramps=ramps, weight=weight, lut=lut, nbins=nbins, out=out_buf,
                        plans=plans, with_phase=with_phase)
     return P, out
@@ -888,8 +889,26 @@ def _cut_codes(values, nbins):
     return (edges.searchsorted(v, side="left") - 1).astype(np.int64)
 
 
+_LUT_TENSORS = OrderedDict()    # id(codes) -> (codes, int32 LUT tensor laid out like the spectrum): same object every call
+_RADIAL_CACHE = OrderedDict()   # (k bytes, l bytes, nfactor, truncate) -> (codes, nbins, kr): the LUT of a grid is built once
+
+
 def _radial_bins(k, l, nfactor, truncate):
     """freq_r, LUT codes [len(k), len(l)], nbins and the bin-mean radius coordinate (xrft.py:975-991)."""
+    key = (k.tobytes(), l.tobytes(), nfactor, bool(truncate))
+    hit = _RADIAL_CACHE.get(key)
+    if hit is not None:
+        if not truncate:
+            warnings.warn("Isotropic wavenumber larger than the Nyquist wavenumber may result.", FutureWarning)
+        return hit
+    res = _radial_bins_build(k, l, nfactor, truncate)
+    _RADIAL_CACHE[key] = res
+    while len(_RADIAL_CACHE) > 8:
+        _RADIAL_CACHE.popitem(last=False)
+    return res
+
+
+def _radial_bins_build(k, l, nfactor, truncate):
     N = [k.size, l.size]
     nbins = int(min(N) / nfactor)
     freq_r = np.sqrt(k[:, None] ** 2 + l[None, :] ** 2)
@@ -952,9 +971,16 @@ def _iso_common(da1, da2, mode, spacing_tol, dim, shift, detrend, scaling, windo
         codes, nbins, kr = _radial_bins(k, l, nfactor, truncate)  # codes[i_k, i_l]
         state["kr"], state["nbins"] = kr, nbins
         order = [P["dim"].index(dim[0]), P["dim"].index(dim[1])]
-        lut = codes.T if order == [0, 1] else codes  # -> [axis of P.dim[0]][axis of P.dim[1]]
         import torch
-        return torch.from_numpy(np.ascontiguousarray(lut.astype(np.int32))), nbins
+        ck = (id(codes), order[0])
+        hit = _LUT_TENSORS.get(ck)
+        if hit is None or hit[0] is not codes:
+            lut = codes.T if order == [0, 1] else codes  # -> [axis of P.dim[0]][axis of P.dim[1]]
+            hit = (codes, torch.from_numpy(np.ascontiguousarray(lut.astype(np.int32))))
+            _LUT_TENSORS[ck] = hit
+            while len(_LUT_TENSORS) > 8:
+                _LUT_TENSORS.popitem(last=False)
+        return hit[1], nbins
 
     kw = dict(kwargs)
     kw.update(dict(spacing_tol=spacing_tol, shift=shift, detrend=detrend, window=window, true_amplitude=True))

@@ -389,6 +389,7 @@ def binned_sum(arr: torch.Tensor, lut: torch.Tensor, nbins: int, ncore: int) -> 
 # fused hot path
 # ---------------------------------------------------------------------------------------------
 _WORK = {}
+_LUT_DEV = {}   # id(host LUT) -> (host LUT, device LUT, symmetric flag)
 _FUSED_CHUNK = 32  # batch items (dask-style chunks along the outer axis) per fused kernel chain (measured: 16 -> 32 is +3-4 %)
 
 
@@ -464,12 +465,20 @@ def spectrum2d(x1: torch.Tensor, x2: Optional[torch.Tensor], mode: int, detrend:
     bins_mode = mode in (L.EPI_BINS_POWER, L.EPI_BINS_CROSS)
     lut_sym = 0
     if bins_mode:
-        lc = lut.to(dtype=torch.int32)
-        if lc.ndim == 2 and lc.shape == (ny, W) and not keep_half:
-            # symmetric under (ky, kx) -> (-ky, -kx) in the unshifted frame == same test in the shifted frame (even sizes)
-            us = torch.roll(lc, shifts=(-(ny // 2) if shift_y else 0, -(nx // 2) if shift_x else 0), dims=(0, 1))
-            lut_sym = int(torch.equal(us, torch.roll(torch.flip(us, dims=(0, 1)), shifts=(1, 1), dims=(0, 1))))
-        lut = lut.to(device=dev, dtype=torch.int32).contiguous()
+        # the device copy of a LUT and its symmetry flag are kept per host LUT object (api.py hands the same one every call)
+        ck = (id(lut), dev.index, bool(shift_y), bool(shift_x), bool(keep_half))
+        hit = _LUT_DEV.get(ck)
+        if hit is None or hit[0] is not lut:
+            lc = lut.to(dtype=torch.int32)
+            if lc.ndim == 2 and lc.shape == (ny, W) and not keep_half:
+                # symmetric under (ky, kx) -> (-ky, -kx) in the unshifted frame == same test in the shifted frame (even sizes)
+                us = torch.roll(lc, shifts=(-(ny // 2) if shift_y else 0, -(nx // 2) if shift_x else 0), dims=(0, 1))
+                lut_sym = int(torch.equal(us, torch.roll(torch.flip(us, dims=(0, 1)), shifts=(1, 1), dims=(0, 1))))
+            hit = (lut, lut.to(device=dev, dtype=torch.int32).contiguous(), lut_sym)
+            _LUT_DEV[ck] = hit
+            while len(_LUT_DEV) > 8:
+                _LUT_DEV.pop(next(iter(_LUT_DEV)))
+        lut, lut_sym = hit[1], hit[2]
         out = torch.zeros(lead + [nbins] + ([2] if mode == L.EPI_BINS_CROSS else []), dtype=torch.float64, device=dev)
     else:
         odt = cdt if mode in (L.EPI_COMPLEX, L.EPI_CROSS) else rdt

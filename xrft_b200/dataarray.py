@@ -121,6 +121,10 @@ class Deferred:
         """the mean of this array over `dim` (a name out of `dims`) computed without materialising it, or None"""
         return None
 
+    def try_transpose(self, dims, new_dims):
+        """this array (axes named `dims`) with its axes reordered to `new_dims`, still deferred, or None"""
+        return None
+
 
 class LazyPad(Deferred):
     """Zero padding of a device-resident array that has not been carried out yet (xrft.pad of a CUDA tensor, mode
@@ -182,16 +186,24 @@ class LazyIrfft2(Deferred):
 class LazySegSpectrum(Deferred):
     """Per-segment spectra (chunks_to_segments=True, xrft.py:106-136) that have not been computed yet: `.mean("<dim>_segment")`
     -- Welch's method, xrft/tests/test_xrft.py:273-337 -- runs the transform with the segment mean folded into the spectral
-    epilogue (xrftb_spectral_post_segmean), so the per-segment spectra are never written; any other access computes them."""
+    epilogue (xrftb_spectral_post_segmean), so the per-segment spectra are never written; any other access computes them.
+    `run(seg_dim)` returns the data with axes in the order `nat_dims` (minus seg_dim); `dims` is the order this view shows."""
 
-    def __init__(self, run, shape, seg_dims):
-        self.run, self.shape, self.seg_dims = run, tuple(int(n) for n in shape), tuple(seg_dims)
+    def __init__(self, run, nat_shape, nat_dims, seg_dims, dims=None):
+        self.run, self.nat_dims, self.seg_dims = run, tuple(nat_dims), tuple(seg_dims)
+        self.nat_shape = tuple(int(n) for n in nat_shape)
+        self.dims = tuple(dims) if dims is not None else self.nat_dims
+        self.shape = tuple(self.nat_shape[self.nat_dims.index(d)] for d in self.dims)
         self.ndim = len(self.shape)
         self._mat = None
 
+    def _ordered(self, t, have, want):
+        perm = [have.index(d) for d in want]
+        return t if perm == list(range(len(perm))) else t.permute(*perm)
+
     def materialize(self):
         if self._mat is None:
-            self._mat = self.run(None)
+            self._mat = self._ordered(self.run(None), list(self.nat_dims), list(self.dims))
         return self._mat
 
     def try_mean(self, dims, dim):
@@ -199,9 +211,14 @@ class LazySegSpectrum(Deferred):
             if len(dim) != 1:
                 return None
             dim = dim[0]
-        if self._mat is not None or dim not in self.seg_dims or dim not in dims:
+        if self._mat is not None or dim not in self.seg_dims or tuple(dims) != self.dims:
             return None
-        return self.run(dim)
+        return self._ordered(self.run(dim), [d for d in self.nat_dims if d != dim], [d for d in self.dims if d != dim])
+
+    def try_transpose(self, dims, new_dims):
+        if self._mat is not None or tuple(dims) != self.dims or sorted(new_dims) != sorted(self.dims):
+            return None
+        return LazySegSpectrum(self.run, self.nat_shape, self.nat_dims, self.seg_dims, new_dims)
 
 
 class DataArray:
@@ -532,6 +549,10 @@ class DataArray:
             raise ValueError(f"{dims} must be a permutation of {self._dims}")
         if tuple(dims) == self._dims:
             return self._replace()
+        if isinstance(self._store, Deferred):
+            moved = self._store.try_transpose(self._dims, tuple(dims))
+            if moved is not None:
+                return self._replace(data=moved, dims=dims)
         perm = [self._dims.index(d) for d in dims]
         data = self._data.permute(*perm) if _is_torch(self._data) else np.transpose(self._data, perm)
         return self._replace(data=data, dims=dims)
