@@ -108,7 +108,8 @@ def test_cross_chain_variant(over, options):
     assert worst < 1e-5, worst
 
 
-@pytest.mark.parametrize("over", [{}, {"bins_static": 0}, {"cols_first": 0}, {"cols_first": 0, "bins_static": 0}],
+@pytest.mark.parametrize("over", [{}, {"bins_static": 0}, {"cols_first": 0}, {"cols_first": 0, "bins_static": 0},
+                                  {"cols_first": 0, "bins_static": 0, "cols_async": 1}],
                          ids=lambda e: ",".join(f"{k}={v}" for k, v in e.items()) or "default")
 def test_bins_chain_variant(over, options):
     """isotropic power spectrum: radial bins in pass 2 of the columns-first chain (default), the register-LUT column kernel of
