@@ -673,3 +673,39 @@ def test_welch_segment_mean_is_an_epilogue_reduction(dt):
     cs = xrft.cross_spectrum(mk2(y, True), mk2(z, True), **kw)
     refc = O.cross_spectrum(lab(mk2(y, False)), lab(mk2(z, False)), **kw)
     assert relerr(cs.mean("t_segment").values, refc.data.mean(axis=refc.dims.index("t_segment"))) < tol
+
+
+def test_lazy_chunk_iterator_streams_through_the_gpu():
+    """xrft_b200.stream: a generator of host chunks in, a generator of host results out (the role dask's chunk iteration
+    plays in the reference, xrft.py:925-943); equals the whole-array call chunk by chunk"""
+    import types
+    rng = np.random.default_rng(73)
+    x = (rng.standard_normal((10, 64, 128)) + 0.1 * np.arange(128)).astype(np.float32)
+    y = (x[::-1] + 0.2 * rng.standard_normal(x.shape)).astype(np.float32)
+    c = lambda lo, hi: {"t": np.arange(lo, hi) * 1.0, "y": np.arange(64) * 1.0, "x": np.arange(128) * 1.0}
+    consumed = []
+
+    def chunks(a):
+        for lo in range(0, 10, 3):       # ragged last chunk
+            consumed.append(lo)
+            yield DataArray(a[lo:lo + 3], dims=["t", "y", "x"], coords=c(lo, min(lo + 3, 10)))
+
+    kw = dict(dim=["y", "x"], detrend="linear", window="hann")
+    it = xrft.stream(xrft.power_spectrum, chunks(x), **kw)
+    assert isinstance(it, types.GeneratorType) and consumed == []          # nothing happens before the first request
+    parts = []
+    for r in it:
+        assert isinstance(r.data, np.ndarray) and r.dims == ("t", "freq_y", "freq_x")
+        parts.append(r)
+    whole = xrft.power_spectrum(DataArray(x, dims=["t", "y", "x"], coords=c(0, 10)), **kw)
+    np.testing.assert_array_equal(np.concatenate([p.values for p in parts]), whole.values)
+    np.testing.assert_array_equal(np.concatenate([p["t"].values for p in parts]), np.arange(10.0))
+    # two zipped iterables (cross spectrum) and the radial-bin mode
+    cs = np.concatenate([r.values for r in xrft.stream(xrft.cross_spectrum, chunks(x), chunks(y), **kw)])
+    ref = O.cross_spectrum(lab(DataArray(x, dims=["t", "y", "x"], coords=c(0, 10))), lab(DataArray(y, dims=["t", "y", "x"], coords=c(0, 10))), **kw)
+    assert relerr(cs, ref.data) < 1e-3
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        iso = np.concatenate([r.values for r in xrft.stream(xrft.isotropic_power_spectrum, chunks(x), **kw)])
+        riso = O.isotropic_power_spectrum(lab(DataArray(x, dims=["t", "y", "x"], coords=c(0, 10))), **kw)
+    assert relerr(iso, riso.data) < 1e-3

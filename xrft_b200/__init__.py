@@ -12,9 +12,11 @@ from .api import (  # noqa: F401
     isotropic_power_spectrum, isotropic_cross_spectrum, fit_loglog, detrend, pad, unpad,
 )
 
-__version__ = "0.1.0"
+from .stream import stream  # noqa: F401,E402
+
+__version__ = "0.2.0"
 __all__ = [
     "DataArray", "fft", "ifft", "dft", "idft", "power_spectrum", "cross_spectrum", "cross_phase", "cross_spectrum_and_phase",
     "isotropize",
-    "isotropic_power_spectrum", "isotropic_cross_spectrum", "fit_loglog", "detrend", "pad", "unpad",
+    "isotropic_power_spectrum", "isotropic_cross_spectrum", "fit_loglog", "detrend", "pad", "unpad", "stream",
 ]
