@@ -120,7 +120,8 @@ def test_bins_chain_variant(over, options):
     options(over)
     warnings.simplefilter("ignore")
     rng = np.random.default_rng(5)
-    for (T, ny, nx, detrend) in [(5, 512, 512, "constant"), (3, 256, 1024, "linear"), (2, 1024, 256, None), (3, 64, 64, "constant")]:
+    for (T, ny, nx, detrend) in [(5, 512, 512, "constant"), (3, 256, 1024, "linear"), (2, 1024, 256, None), (3, 64, 64, "constant"),
+                                 (2, 256, 4096, "constant"), (1, 128, 8192, "linear"), (3, 256, 64, "constant"), (2, 512, 128, None)]:
         x = (rng.standard_normal((T, ny, nx)) + 0.5).astype(np.float32)
         c = {"t": np.arange(T) * 1.0, "y": np.arange(ny) * 1.0, "x": np.arange(nx) * 1.0}
         iso = xrft.isotropic_power_spectrum(xrft.DataArray(torch.from_numpy(x).cuda(), dims=["t", "y", "x"], coords=c), dim=["y", "x"],

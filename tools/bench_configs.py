@@ -46,6 +46,25 @@ def _relerr(a, b):
     return float(np.linalg.norm((np.asarray(a) - np.asarray(b)).ravel()) / (den if den > 0 else 1.0))
 
 
+def _cpu_threads(work, nitems):
+    """time `work(i)` for i in range(nitems) on a thread pool of the host cores (BLAS threads = 1): the reference's
+    chunk-parallel CPU model (dask threaded scheduler over independent chunks).  Returns (seconds, threads)."""
+    import contextlib
+    import time
+    from concurrent.futures import ThreadPoolExecutor
+    try:
+        from threadpoolctl import threadpool_limits
+        ctx = threadpool_limits(limits=1)
+    except Exception:  # pragma: no cover
+        ctx = contextlib.nullcontext()
+    workers = max(1, min(os.cpu_count() or 1, 32, nitems))
+    t0 = time.perf_counter()
+    with ctx:
+        with ThreadPoolExecutor(workers) as ex:
+            list(ex.map(work, range(nitems)))
+    return time.perf_counter() - t0, workers
+
+
 def _roof(gpts, bytes_per_point):
     peak, src = _peak()
     gbs = gpts * bytes_per_point
@@ -93,6 +112,20 @@ def run_config3(dev, T=512, n=2048, parity=True):
         res["cross_spectrum_and_phase"] = dict(value=pts / ms_b / 1e6, ms=ms_b, **_roof(pts / ms_b / 1e6, 20.0))
     res["gpu_launches"] = int(lib.xrftb_launch_count(0))
     res["parity"] = par
+    if parity:   # the reference's CPU path (oracle port) on a bounded sample: one slice pair per worker thread
+        from oracle import xrft_oracle as O
+        ns = max(1, min(os.cpu_count() or 1, 16, T))
+        ah, bh = a[:ns].cpu().numpy(), b[:ns].cpu().numpy()
+        c1 = {k: (v[:1] if k == "time" else v) for k, v in c.items()}
+
+        def work(i):
+            la = O.Labelled(ah[i:i + 1].astype(np.float64), ("time", "y", "x"), c1)
+            lb = O.Labelled(bh[i:i + 1].astype(np.float64), ("time", "y", "x"), c1)
+            O.cross_spectrum(la, lb, **kw); O.cross_phase(la, lb, **kw)
+
+        sec, thr = _cpu_threads(work, ns)
+        res["cpu_baseline"] = {"value": ns * n * n / sec / 1e9, "unit": "GPoints/s per field (cross_spectrum + cross_phase)", "cores": thr, "kind": "port",
+                               "sample": "%d slice pairs of %d^2 float32 (%.1f s)" % (ns, n, sec)}
     del a, b, da, db
     torch.cuda.empty_cache()
     return res
@@ -146,12 +179,23 @@ def run_config4(dev, rank=0, world=1, chunks=64, z=512, n=512, parity=True):
         ref = O.isotropic_power_spectrum(O.Labelled(sub, ("z", "y", "x"), cc), dim=["y", "x"], **kw).data
         got = xrft.isotropic_power_spectrum(xrft.DataArray(x[0, :4], dims=["z", "y", "x"], coords=cc), dim=["y", "x"], **kw).values
         res["parity"] = {"iso_relerr_4_planes": _relerr(got, ref)}
+        if world == 1:
+            npl = 4 * max(1, min(os.cpu_count() or 1, 32))
+            xh = x.reshape(-1, n, n)[:npl].cpu().numpy()
+            c4 = {"z": np.arange(4.0), "y": c["y"], "x": c["x"]}
+
+            def work(i):
+                O.isotropic_power_spectrum(O.Labelled(xh[4 * i:4 * i + 4].astype(np.float64), ("z", "y", "x"), c4), dim=["y", "x"], **kw)
+
+            sec, thr = _cpu_threads(work, npl // 4)
+            res["cpu_baseline"] = {"value": npl * n * n / sec / 1e9, "unit": "GPoints/s", "cores": thr, "kind": "port",
+                                   "sample": "%d planes of %d^2 float32 (%.1f s)" % (npl, n, sec)}
     del x, da
     torch.cuda.empty_cache()
     return res
 
 
-def run_config5(dev, n=8192, p=4096):
+def run_config5(dev, n=8192, p=4096, cpu=True):
     """pad -> fft(real_dim) -> ifft(real_dim) -> unpad of 8192^2 float64 (padded grid 16384^2) + Parseval (padding.py, xrft.py:307-646)"""
     import torch
     import xrft_b200 as xrft
@@ -185,6 +229,20 @@ def run_config5(dev, n=8192, p=4096):
            "value": gpts, "unit": "GPoints/s (padded-grid points)", "gpu_launches": launches,
            "parity": {"round_trip_max_rel_err": err, "parseval_rel_err": abs(pars - ref) / ref}}
     res.update(_roof(gpts, 32.0))
+    if cpu:
+        import time
+        from oracle import xrft_oracle as O
+        nh, ph = min(n, 4096), min(p, 2048)     # bounded sample: a quarter-size grid, scaled by points
+        xh = x[:nh, :nh].cpu().numpy()
+        la = O.Labelled(xh, ("y", "x"), {"y": np.arange(nh) * 0.5, "x": np.arange(nh) * 0.5})
+        t0 = time.perf_counter()
+        pd = O.pad(la, {"x": ph, "y": ph})
+        back = O.unpad(O.ifft(O.fft(pd, real_dim="x"), real_dim="freq_x"), {"x": ph, "y": ph})
+        sec = time.perf_counter() - t0
+        Nh = nh + 2 * ph
+        res["cpu_baseline"] = {"value": Nh * Nh / sec / 1e9, "unit": "GPoints/s (padded-grid points)", "cores": 1, "kind": "port",
+                               "sample": "pad(%d) -> fft -> ifft -> unpad of %d^2 float64 (%.1f s, numpy pocketfft, one array = one thread)" % (ph, nh, sec),
+                               "round_trip_max_rel_err": float(np.abs(back.data - xh).max() / np.abs(xh).max())}
     del x, da, padded, ps
     torch.cuda.empty_cache()
     return res

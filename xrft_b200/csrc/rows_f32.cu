@@ -9,11 +9,11 @@ template int rows_z_cross<float>(RowsZCross<float>, int, long, int, cudaStream_t
 }
 
 namespace xrftb {
-// pass 2 of the columns-first order with the radial-bin epilogue (float32, Nx = 256 .. 2048); 1 = shape not covered
+// pass 2 of the columns-first order with the radial-bin epilogue (float32, Nx = 64 .. 8192); 1 = shape not covered
 int rows_bins(const RowsBins& io, int log2L, cudaStream_t st) {
     switch (log2L) {
 #define Z(K) case K: return launch_rows_bins<K, rows_seq_generic<K, TypeCfg<float>::LOGE>()>(io, st);
-        Z(8) Z(9) Z(10) Z(11)
+        Z(6) Z(7) Z(8) Z(9) Z(10) Z(11) Z(12) Z(13)
 #undef Z
         default: break;
     }
@@ -21,8 +21,12 @@ int rows_bins(const RowsBins& io, int log2L, cudaStream_t st) {
 }
 bool rows_bins_shape_ok(int log2L, int ny) {
     int seq = 0;
-    switch (log2L) { case 8: seq = rows_seq_generic<8, 4>(); break; case 9: seq = rows_seq_generic<9, 4>(); break;
-                     case 10: seq = rows_seq_generic<10, 4>(); break; case 11: seq = rows_seq_generic<11, 4>(); break; default: return false; }
+    switch (log2L) {
+#define Z(K) case K: seq = rows_seq_generic<K, 4>(); break;
+        Z(6) Z(7) Z(8) Z(9) Z(10) Z(11) Z(12) Z(13)
+#undef Z
+        default: return false;
+    }
     return ny / 2 >= seq && (ny / 2) % seq == 0;
 }
 }  // namespace xrftb
