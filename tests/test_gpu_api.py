@@ -495,7 +495,9 @@ def test_cross_spectrum_phase_large(dt, shape):
     out = xrft.cross_phase(a, b, **kw)
     d = np.abs(np.angle(np.exp(1j * (out.values - np.angle(ref.data)))))
     sig = np.abs(ref.data) > 1e-3 * np.abs(ref.data).max()
-    assert d[sig].max() < (2e-2 if dt == np.float32 else 1e-6)
+    # float32: a cell's angle is as accurate as its cross spectrum relative to its own magnitude: cells above 1e-3 of the peak
+    # with a normwise error of ~3e-7 of the peak are within ~3e-4 rad; the bound leaves a factor of a few
+    assert d[sig].max() < (2e-3 if dt == np.float32 else 1e-6)
     # Hermitian structure of the cross spectrum of real fields: C(-k) = conj(C(k))
     c = xrft.cross_spectrum(a, b, **kw).values[0]
     np.testing.assert_allclose(c[1:, 1:], np.conj(c[1:, 1:][::-1, ::-1]), rtol=1e-4, atol=1e-6 * np.abs(c).max())

@@ -894,8 +894,8 @@ static int c2c_pass(const cplx<T>* src, cplx<T>* dst, long A, long n, long B, in
         ColsC2C<T> ea{}, eb{};
         if (hooks) { ea = *hooks; eb = *hooks; }
         ea.tw4 = tw4; ea.tw4_div = B; ea.tw4_hi = tw4_hi; ea.row_mul = n2; ea.row_div = B;   // step A: rows r = i1 n2 + i2; store hooks belong to step B
-        ea.out_ramp = nullptr; ea.out_roll = 0; ea.out_hi = 0;
-        eb.tr_n1 = (int)n1; eb.in_ramp = nullptr; eb.in_roll = 0; eb.in_hi = 0;                 // step B: load hooks belong to step A
+        ea.out_ramp = nullptr; ea.out_roll = 0; ea.out_hi = 0; ea.out_conj = 0;
+        eb.tr_n1 = (int)n1; eb.in_ramp = nullptr; eb.in_roll = 0; eb.in_hi = 0; eb.in_rows = 0; eb.in_conj = 0;   // step B: load hooks belong to step A
         if (int rc = cols_c2c<T>(src, w, ilog2_exact(n1), A, n2 * B, inverse, (T)1, st, &ea)) return rc;            // FFT over i1, x twiddle
         if (B > 1) return cols_c2c<T>(w, dst, ilog2_exact(n2), A * n1, B, inverse, scale, st, &eb);                  // FFT over i2, transposed store
         if (hooks) { set_error("fft2r: contiguous four-step pass has no hooks"); return XRFTB_EUNSUPPORTED; }
@@ -912,6 +912,24 @@ static int c2c_pass(const cplx<T>* src, cplx<T>* dst, long A, long n, long B, in
     const size_t sub_bytes = work_bytes - mine;
     const cplx<T>*chirp, *filt;
     if (int rc = get_chirp<T>(n, lm, &chirp, &filt, st)) return rc;
+    // The chirp products, the zero padding to M, the filter product and the final crop ride on the loads and stores of the two
+    // power-of-two transforms (hooks of ColsC2C / RowsC2C): two passes over the data instead of five.
+    const T s2 = (T)((double)scale / (double)M);
+    if (B > 1 && (double)M * (double)B < 2147483648.0 && (double)A * (double)M < 2147483648.0) {
+        ColsC2C<T> h1{}, h2{};
+        h1.hook_n = M; h1.in_rows = n; h1.in_hi = n; h1.in_ramp = chirp; h1.in_conj = inverse; h1.out_ramp = filt;
+        h2.hook_n = M; h2.out_ramp = chirp; h2.out_conj = inverse; h2.out_hi = n;
+        if (int rc = c2c_pass<T>(src, w, A, M, B, 0, (T)1, sub, sub_bytes, st, &h1)) return rc;
+        return c2c_pass<T>(w, dst, A, M, B, 1, s2, sub, sub_bytes, st, &h2);
+    }
+    if (B == 1 && fast_len<T>(M, true)) {
+        RowsC2C<T> r1{}, r2{};
+        r1.in_len = (int)n; r1.in_conj = inverse; r1.in_ramp = chirp; r1.out_ramp = filt;
+        r2.out_ramp = chirp; r2.out_conj = inverse; r2.out_len = (int)n;
+        if (int rc = rows_c2c<T>(src, w, lm, A, n, M, 0, (T)1, st, &r1)) return rc;
+        return rows_c2c<T>(w, dst, lm, A, M, n, 1, s2, st, &r2);
+    }
+    // contiguous sequences longer than one CTA's shared memory: separate chirp / filter passes around the four-step transforms
     const long tw_ = A * M * B;
     bluestein_pre_kernel<T, false><<<ew_grid(tw_), 256, 0, st>>>(src, w, chirp, A, n, M, B, inverse, tw_);
     if (int rc = check_launch("bluestein_pre")) return rc;

@@ -65,6 +65,12 @@ rows_kernel(IO io, const cplx<T>* __restrict__ tw, long nseq) {
 template <typename T> struct RowsC2C {
     static constexpr int kSeqSkew = 0;
     const cplx<T>* in; cplx<T>* out; long in_stride, out_stride; int inverse; T scale;
+    // ---- hooks of Bluestein's chirp-z on the power-of-two rows (c2c_pass; all off by default): only the first in_len points
+    // of a source row exist (the rest of the row is zero), source point j is conjugated (in_conj) and multiplied by in_ramp[j];
+    // output point k is multiplied by out_ramp[k], conjugated (out_conj), and stored only for k < out_len
+    int in_len = 0, in_conj = 0, out_conj = 0, out_len = 0;
+    const cplx<T>* in_ramp = nullptr;
+    const cplx<T>* out_ramp = nullptr;
 
     template <int LOG2L, int SEQ> __device__ __forceinline__ void prefetch(long, long) const {}
 
@@ -75,14 +81,17 @@ template <typename T> struct RowsC2C {
 #pragma unroll
         for (int q = 0; q < (1 << LOGE); ++q) {
             raw[q] = mk<T>(0, 0);
-            if (active) raw[q] = p[q * NT];
+            if (active && (in_len == 0 || u + q * NT < in_len)) raw[q] = p[q * NT];
         }
     }
     template <int LOG2L, int LOGE>
-    __device__ __forceinline__ void prologue(long, bool, int, cplx<T> (&raw)[1 << LOGE], cplx<T> (&v)[1 << LOGE]) const {
+    __device__ __forceinline__ void prologue(long, bool, int u, cplx<T> (&raw)[1 << LOGE], cplx<T> (&v)[1 << LOGE]) const {
+        constexpr int NT = Geometry<LOG2L, LOGE>::NT;
 #pragma unroll
         for (int q = 0; q < (1 << LOGE); ++q) {
             cplx<T> x = raw[q];
+            if (in_conj) x.y = -x.y;
+            if (in_ramp != nullptr && (in_len == 0 || u + q * NT < in_len)) x = cmul(x, __ldg(in_ramp + u + q * NT));
             if (inverse) x.y = -x.y;
             v[q] = x;
         }
@@ -97,9 +106,14 @@ template <typename T> struct RowsC2C {
         for (int g = 0; g < G; ++g)
 #pragma unroll
             for (int t = 0; t < R; ++t) {
+                const int k = final_index<LOG2L, LOGE>(u, g, t);
+                if (out_len > 0 && k >= out_len) continue;
                 cplx<T> x = v[g + t * G];
                 if (inverse) x.y = -x.y;
-                p[final_index<LOG2L, LOGE>(u, g, t)] = cscale(x, scale);
+                x = cscale(x, scale);
+                if (out_ramp != nullptr) x = cmul(x, __ldg(out_ramp + k));
+                if (out_conj) x.y = -x.y;
+                p[k] = x;
             }
     }
     template <int LOG2L, int LOGE, int SEQ>
@@ -1046,8 +1060,12 @@ template <typename T> struct ColsC2C {
     const cplx<T>* in_ramp = nullptr;
     const cplx<T>* out_ramp = nullptr;
     long out_roll = 0, out_lo = 0, out_hi = 0;
-    __device__ __forceinline__ bool in_hooks() const { return hook_n > 0 && (in_roll != 0 || in_hi > 0 || in_ramp != nullptr); }
-    __device__ __forceinline__ bool out_hooks() const { return hook_n > 0 && (out_roll != 0 || out_hi > 0 || out_ramp != nullptr); }
+    // Bluestein's chirp-z (c2c_pass): the source holds only in_rows (< hook_n) rows per item, is conjugated before the ramp
+    // (in_conj), and the result is conjugated after the ramp (out_conj)
+    long in_rows = 0;
+    int in_conj = 0, out_conj = 0;
+    __device__ __forceinline__ bool in_hooks() const { return hook_n > 0 && (in_roll != 0 || in_hi > 0 || in_ramp != nullptr || in_rows > 0 || in_conj); }
+    __device__ __forceinline__ bool out_hooks() const { return hook_n > 0 && (out_roll != 0 || out_hi > 0 || out_ramp != nullptr || out_conj); }
 
     template <int LOG2L, int C> __device__ __forceinline__ void prefetch(long) const {}
     template <int LOG2L, int LOGE, int C, int V> __device__ __forceinline__ void init(cplx<T>*) const {}
@@ -1060,10 +1078,16 @@ template <typename T> struct ColsC2C {
     template <int LOG2L, int LOGE, int C, int V>
     __device__ __forceinline__ void fix_apply(long tile, int u, int cg, const cplx<T> (&)[1 << LOGE], cplx<T> (&v)[V][1 << LOGE], float* = nullptr, const cplx<T>* = nullptr, float4 = make_float4(1.f, 1.f, 1.f, 1.f)) const {
         constexpr int NT = Geometry<LOG2L, LOGE>::NT;
+        if (hook_n > 0 && in_conj) {
+#pragma unroll
+            for (int vv = 0; vv < V; ++vv)
+#pragma unroll
+                for (int q = 0; q < (1 << LOGE); ++q) v[vv][q].y = -v[vv][q].y;
+        }
         if (hook_n > 0 && in_ramp != nullptr) {
             const long a = tile / tiles_per_row;
             const long b0 = (tile - a * tiles_per_row) * C + cg * V;
-            const int n = (int)hook_n;
+            const int n = (int)hook_n, lo = (int)in_lo, hi = in_hi > 0 ? (int)in_hi : n;
             const int rstep = NT * (int)row_mul;
 #pragma unroll
             for (int vv = 0; vv < V; ++vv) {
@@ -1074,7 +1098,7 @@ template <typename T> struct ColsC2C {
                 for (int q = 0; q < (1 << LOGE); ++q) {
                     int rs = r0 + q * rstep;
                     if (rs >= n) rs -= n;
-                    v[vv][q] = cmul(v[vv][q], __ldg(in_ramp + rs));
+                    if (rs >= lo && rs < hi) v[vv][q] = cmul(v[vv][q], __ldg(in_ramp + rs));   // (rows outside are zero; the ramp ends at hi)
                 }
             }
         }
@@ -1096,7 +1120,7 @@ template <typename T> struct ColsC2C {
             // r0 + q * rstep, wrapped once by the roll
             const int pitch = (int)(row_div ? row_div : B);
             const int n = (int)hook_n, lo = (int)in_lo, hi = in_hi > 0 ? (int)in_hi : n;
-            const cplx<T>* base = in + a * hook_n * pitch;
+            const cplx<T>* base = in + a * (in_rows > 0 ? in_rows : hook_n) * pitch;
             const int rstep = NT * (int)row_mul;
 #pragma unroll
             for (int vv = 0; vv < V; ++vv) {
@@ -1170,6 +1194,7 @@ template <typename T> struct ColsC2C {
                             if (inverse) x.y = -x.y;
                             x = cscale(x, scale);
                             if (out_ramp != nullptr) x = cmul(x, f);
+                            if (out_conj) x.y = -x.y;
                             ob[(Rs - lo) * Bi + vv] = x;
                         }
                     }

@@ -44,8 +44,9 @@ template <typename T> inline int colsfirst_tile_width(int log2L) { return cols_t
 // per CTA; the 2 * pairs rows of a CTA must be consecutive rows of one item
 inline bool rows2_eligible(int log2M, int logNy) { return log2M >= 7 && log2M <= 12 && logNy >= (12 - log2M) + 1; }
 
+// `extra` (nullable) carries the optional members of RowsC2C (the chirp-z hooks); its in / out / strides / inverse / scale are ignored
 template <typename T> int rows_c2c(const cplx<T>* in, cplx<T>* out, int log2L, long nseq, long in_stride, long out_stride,
-                                   int inverse, T scale, cudaStream_t st);
+                                   int inverse, T scale, cudaStream_t st, const RowsC2C<T>* extra = nullptr);
 template <typename T> int rows_r2c(RowsR2CFused<T> io, int log2M, long nseq, cudaStream_t st);
 template <typename T> int rows_c2r(const cplx<T>* in, long in_stride, T* out, long out_stride, int log2M, long nseq, T scale,
                                    cudaStream_t st, const RowsC2R<T>* extra = nullptr);

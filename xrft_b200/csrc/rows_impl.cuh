@@ -10,8 +10,10 @@ namespace xrftb {
 
 template <typename T>
 int rows_c2c(const cplx<T>* in, cplx<T>* out, int log2L, long nseq, long in_stride, long out_stride, int inverse, T scale,
-             cudaStream_t st) {
-    RowsC2C<T> io{in, out, in_stride, out_stride, inverse, scale};
+             cudaStream_t st, const RowsC2C<T>* extra) {
+    RowsC2C<T> io{};
+    if (extra) io = *extra;
+    io.in = in; io.out = out; io.in_stride = in_stride; io.out_stride = out_stride; io.inverse = inverse; io.scale = scale;
     switch (log2L) {
 #define X(K) case K: return launch_rows<T, K, rows_seq_generic<K, cmin(TypeCfg<T>::LOGE, K)>()>(io, nseq, st);
         XRFTB_ROWS_CASES(X)
