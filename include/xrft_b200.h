@@ -164,6 +164,13 @@ int xrftb_spectral_post_segmean(const void* in1, const void* in2, void* out, int
 int xrftb_roll_scale(const void* in, void* out, int dtype, int is_complex, int64_t batch, int64_t n0, int64_t n1, int64_t n2,
                      int64_t s0, int64_t s1, int64_t s2, double scale, void* stream);
 
+/* ---- the data movement around the transforms that the reference does with xarray / numpy views: moving the transform axes
+ * last (da.transpose, xrft.py:386-396, 474-476) and reversing axes with decreasing coordinates (xrft.py:436-441).
+ * out (C-contiguous) has shape in_shape[perm[0]], in_shape[perm[1]], ...; axis p of the INPUT is reversed when flip[p] != 0
+ * (flip nullable).  ndim <= 6 (fold unpermuted neighbours); elem_bytes 4 / 8 / 16.  Out of place. */
+int xrftb_permute(const void* in, void* out, int elem_bytes, int ndim, const int64_t* in_shape, const int* perm, const int* flip,
+                  void* stream);
+
 /* ---- xrft.pad (padding.py:157-181 -> DataArray.pad -> numpy.pad) on device-resident data ---------------
  * out[ndim] = in surrounded by pad_before[a] / pad_after[a] cells on axis a (ndim <= 4; fold leading axes).  mode: 0 constant
  * (`fill` points at one element, NULL = zeros), 1 edge, 2 reflect, 3 symmetric, 4 wrap (numpy semantics, reflect_type "even",

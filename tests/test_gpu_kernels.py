@@ -247,3 +247,35 @@ def test_fft2r_fused_forward_and_inverse(dt, ny, nx):
     goto = B.fft2r_inverse(torch.from_numpy(f).cuda(), 0, None, None, (0, 3), 1.0, crop=((1, ny - 2), (1, nx - 3))).cpu().numpy()
     fullo = np.roll(np.fft.irfft2(f.astype(np.complex128), s=(ny, nx)), 3, axis=2)
     assert relerr(goto, fullo[:, 1:ny - 1, 1:nx - 2]) < tol
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_chirpz_strided_long_and_inverse(dt):
+    """Bluestein on a strided axis whose padded length needs the four-step decomposition (hooks travel through both
+    decompositions), forward and inverse, plus in-place"""
+    from xrft_b200 import backend as B
+    rng = np.random.default_rng(11)
+    for n, b in ((5000, 3), (4099, 2), (777, 5)):
+        x = cplx(rng, (2, n, b), dt)
+        t = torch.from_numpy(x).cuda()
+        y = B.fftn(t, axes=[1]).cpu().numpy()
+        assert relerr(y, np.fft.fft(x.astype(np.complex128), axis=1)) < TOL[dt] * 20
+        yi = B.ifftn(t, axes=[1]).cpu().numpy()
+        assert relerr(yi, np.fft.ifft(x.astype(np.complex128), axis=1)) < TOL[dt] * 20
+    x2 = cplx(rng, (3, 100, 30), dt)     # two non-power-of-two axes: strided then contiguous chirp-z
+    y2 = B.fftn(torch.from_numpy(x2).cuda(), axes=[1, 2]).cpu().numpy()
+    assert relerr(y2, np.fft.fftn(x2.astype(np.complex128), axes=[1, 2])) < TOL[dt] * 20
+
+
+@pytest.mark.gpu
+def test_permute_flip_kernel():
+    """xrftb_permute (axis permutation + reversal; the reference's da.transpose / flipped coordinates) equals numpy"""
+    from xrft_b200 import backend as B
+    rng = np.random.default_rng(12)
+    for dt in (np.float32, np.float64, np.complex64, np.complex128):
+        x = rng.standard_normal((3, 4, 5, 6, 7)).astype(dt) if np.dtype(dt).kind != "c" else cplx(rng, (3, 4, 5, 6, 7), np.float32 if dt == np.complex64 else np.float64)
+        for perm, flips in (((0, 2, 3, 4, 1), ()), ((4, 3, 2, 1, 0), (1, 3)), ((0, 1, 2, 3, 4), (4,)), ((1, 0, 2, 3, 4), (0,)), ((0, 3, 4, 1, 2), (2,))):
+            got = B.permute_flip(torch.from_numpy(x).cuda(), perm, flips).cpu().numpy()
+            ref = np.transpose(np.flip(x, axis=flips) if flips else x, perm)
+            np.testing.assert_array_equal(got, ref)

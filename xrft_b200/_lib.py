@@ -31,6 +31,7 @@ EXPORTS = [
     "xrftb_spectral_post",
     "xrftb_spectral_post_segmean",
     "xrftb_roll_scale",
+    "xrftb_permute",
     "xrftb_pad",
     "xrftb_binned_sum",
     "xrftb_spectrum2d_workspace",
@@ -130,6 +131,8 @@ def load():
     lib.xrftb_fft2r_workspace.argtypes = [C.POINTER(Fft2rDesc)]
     lib.xrftb_fft2r.restype = C.c_int
     lib.xrftb_fft2r.argtypes = [C.POINTER(Fft2rDesc), vp]
+    lib.xrftb_permute.argtypes = [vp, vp, C.c_int, C.c_int, i64p, ip, ip, vp]
+    lib.xrftb_permute.restype = C.c_int
     lib.xrftb_pad.argtypes = [vp, vp, C.c_int, C.c_int, i64p, i64p, i64p, C.c_int, vp, vp]
     lib.xrftb_pad.restype = C.c_int
     lib.xrftb_binned_sum.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int, vp]
@@ -148,7 +151,8 @@ def load():
     for name in ["xrftb_comm_unique_id", "xrftb_comm_init", "xrftb_comm_destroy", "xrftb_allreduce_bins"]:
         getattr(lib, name).restype = C.c_int
     for name in ["xrftb_device_info", "xrftb_fftn", "xrftb_moments", "xrftb_detrend_window", "xrftb_spectral_post",
-                 "xrftb_pad",
+                 "xrftb_permute",
+    "xrftb_pad",
     "xrftb_binned_sum", "xrftb_spectrum2d", "xrftb_roll_scale"]:
         getattr(lib, name).restype = C.c_int
     _lib = lib

@@ -287,7 +287,8 @@ def _to_last(t, axes):
         inv[p] = i
     if perm == list(range(nd)):
         return t.contiguous(), None
-    return t.permute(*perm).contiguous(), inv
+    from . import backend as B
+    return B.permute_flip(t, perm), inv   # the reference's da.transpose (xrft.py:386-396): one CUDA gather, no eager torch
 
 
 # =============================================================================================
@@ -491,8 +492,9 @@ def _run_forward(P, das, mode, detrend, window, scale, ramps=None, weight=None, 
         t = _device_tensor(da.data)
         t, inv = _to_last(t, P["axis_num"])
         if pl["reversed_dims"]:   # each array by ITS OWN coordinate orientation (xrft.py:436-441)
+            from . import backend as B
             flip_axes = [t.ndim - ntrans + pl["dim"].index(d) for d in pl["reversed_dims"]]
-            t = torch.flip(t, dims=flip_axes).contiguous()
+            t = B.permute_flip(t, list(range(t.ndim)), flip_axes)
         xs.append(t)
     if len(xs) == 2 and xs[0].dtype != xs[1].dtype:
         dt = torch.promote_types(xs[0].dtype, xs[1].dtype)

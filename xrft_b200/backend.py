@@ -322,6 +322,47 @@ def roll_scale(x: torch.Tensor, ntrail: int, shifts: Sequence[int], scale: float
 
 
 # ---------------------------------------------------------------------------------------------
+# axis permutation / reversal (device-resident data)
+# ---------------------------------------------------------------------------------------------
+def permute_flip(x: torch.Tensor, perm: Sequence[int], flip_axes: Sequence[int] = ()) -> torch.Tensor:
+    """contiguous x.permute(perm) with the INPUT axes in flip_axes reversed first, by the CUDA kernel of the C-ABI"""
+    lib = require_cuda()
+    x = _dev(x)
+    perm = [int(p) for p in perm]
+    nd = x.ndim
+    if sorted(perm) != list(range(nd)):
+        raise ValueError("permute_flip: not a permutation")
+    flips = [1 if a in set(int(f) % nd for f in flip_axes) else 0 for a in range(nd)]
+    if perm == list(range(nd)) and not any(flips):
+        return x
+    if x.dtype not in (torch.float32, torch.float64, torch.complex64, torch.complex128):
+        raise TypeError(f"permute_flip: unsupported dtype {x.dtype}")
+    # fold runs of input axes that stay adjacent and in order in the output (and are not flipped) into one axis
+    groups = []                       # lists of input axes, in OUTPUT order
+    for p in perm:
+        if groups and groups[-1][-1] + 1 == p and not flips[p] and not flips[groups[-1][-1]]:
+            groups[-1].append(p)
+        else:
+            groups.append([p])
+    order = sorted(range(len(groups)), key=lambda g: groups[g][0])          # groups in INPUT order
+    in_shape, gflip = [], []
+    for g in order:
+        n = 1
+        for a in groups[g]:
+            n *= x.shape[a]
+        in_shape.append(n)
+        gflip.append(flips[groups[g][0]] if len(groups[g]) == 1 else 0)
+    gperm = [order.index(g) for g in range(len(groups))]
+    if len(groups) > 6:
+        raise NotImplementedError("permute_flip: more than 6 axis groups")
+    out = torch.empty([x.shape[p] for p in perm], dtype=x.dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = lib.xrftb_permute(_ptr(x), _ptr(out), x.element_size(), len(groups), _i64(in_shape), _ints(gperm), _ints(gflip), _stream())
+    L.check(rc, "xrftb_permute")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
 # pad (device-resident data)
 # ---------------------------------------------------------------------------------------------
 PAD_MODES = {"constant": 0, "edge": 1, "reflect": 2, "symmetric": 3, "wrap": 4}

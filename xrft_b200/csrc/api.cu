@@ -761,6 +761,23 @@ __global__ void __launch_bounds__(256) pad_kernel(const E* __restrict__ in, E* _
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// axis permutation + per-axis reversal (the transpose that moves the transform axes last, xrft.py:386-396, and the flip of
+// decreasing coordinates under true_phase, xrft.py:436-441): out[o0..] = in[perm / flip of the indices], any element size
+// ------------------------------------------------------------------------------------------------
+struct PermDesc { long out_n[6]; long in_stride[6]; long in_off; int ndim; };   // in_stride: of the input axis feeding output axis a (negative when flipped)
+template <typename E>
+__global__ void __launch_bounds__(256) permute_kernel(const E* __restrict__ in, E* __restrict__ out, PermDesc d, long total) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        long r = i, src = d.in_off;
+#pragma unroll
+        for (int a = 5; a >= 0; --a) {
+            if (a < d.ndim) { const long idx = r % d.out_n[a]; r /= d.out_n[a]; src += idx * d.in_stride[a]; }
+        }
+        out[i] = in[src];
+    }
+}
+
 static inline size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
 static inline int next_pow2_log(long n) { int l = 0; while ((1L << l) < n) ++l; return l; }
 
@@ -1743,6 +1760,29 @@ int xrftb_fft2r(const xrftb_fft2r_desc* q, void* stream) {
     if (q->dtype == XRFTB_F64) return fft2r_impl<double>(*q, st);
     set_error("fft2r: bad dtype %d", q->dtype);
     return XRFTB_EINVAL;
+}
+
+int xrftb_permute(const void* in, void* out, int elem_bytes, int ndim, const int64_t* in_shape, const int* perm, const int* flip, void* stream) {
+    if (!in || !out || in == out || ndim < 1 || ndim > 6 || !in_shape || !perm) { set_error("permute: bad arguments"); return XRFTB_EINVAL; }
+    long istride[6], total = 1;
+    { long sacc = 1; for (int a = ndim - 1; a >= 0; --a) { istride[a] = sacc; sacc *= in_shape[a]; total *= in_shape[a]; } }
+    PermDesc d{};
+    d.ndim = ndim; d.in_off = 0;
+    int seen = 0;
+    for (int a = 0; a < ndim; ++a) {
+        const int p = perm[a];
+        if (p < 0 || p >= ndim || (seen >> p) & 1) { set_error("permute: not a permutation"); return XRFTB_EINVAL; }
+        seen |= 1 << p;
+        d.out_n[a] = in_shape[p];
+        d.in_stride[a] = istride[p];
+        if (flip && flip[p]) { d.in_off += (in_shape[p] - 1) * istride[p]; d.in_stride[a] = -istride[p]; }
+    }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (elem_bytes == 4) permute_kernel<float><<<ew_grid(total), 256, 0, st>>>(reinterpret_cast<const float*>(in), reinterpret_cast<float*>(out), d, total);
+    else if (elem_bytes == 8) permute_kernel<double><<<ew_grid(total), 256, 0, st>>>(reinterpret_cast<const double*>(in), reinterpret_cast<double*>(out), d, total);
+    else if (elem_bytes == 16) permute_kernel<double2><<<ew_grid(total), 256, 0, st>>>(reinterpret_cast<const double2*>(in), reinterpret_cast<double2*>(out), d, total);
+    else { set_error("permute: element size %d unsupported (4, 8 or 16 bytes)", elem_bytes); return XRFTB_EINVAL; }
+    return check_launch("permute_kernel");
 }
 
 int xrftb_pad(const void* in, void* out, int elem_bytes, int ndim, const int64_t* in_shape, const int64_t* pad_before,
