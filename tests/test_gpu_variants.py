@@ -135,3 +135,32 @@ def test_bins_chain_variant(over, options):
             ps = np.fft.fftshift(np.abs(np.fft.fft2(d * w)) ** 2) / (ny * nx)
             ref = np.bincount(codes.T.ravel(), weights=ps.ravel(), minlength=nbins)
             assert np.linalg.norm(iso[t] - ref) / np.linalg.norm(ref) < 1e-5
+
+
+@pytest.mark.parametrize("over", [{}, {"bins_static": 0}, {"cross_z": 0}], ids=lambda e: ",".join(f"{k}={v}" for k, v in e.items()) or "default")
+def test_bins_cross_chain_variant(over, options):
+    """isotropic cross spectrum: radial bins in the two-field pass 2 of the z-mode chain (default) and the generic two-field
+    LUT epilogue agree with numpy's bincount of the reference's codes (real part; the imaginary part cancels)"""
+    import torch
+    import xrft_b200 as xrft
+    from xrft_b200 import api as A
+    options(over)
+    warnings.simplefilter("ignore")
+    rng = np.random.default_rng(6)
+    for (T, ny, nx, detrend) in [(3, 1024, 1024, "constant"), (2, 512, 2048, "linear"), (2, 2048, 1024, None), (3, 64, 128, "constant")]:
+        x = (rng.standard_normal((T, ny, nx)) + 0.5).astype(np.float32)
+        y = (np.roll(x, (2, 3), axis=(1, 2)) + 0.3 * rng.standard_normal((T, ny, nx))).astype(np.float32)
+        c = {"t": np.arange(T) * 1.0, "y": np.arange(ny) * 1.0, "x": np.arange(nx) * 1.0}
+        mk_ = lambda v: xrft.DataArray(torch.from_numpy(v).cuda(), dims=["t", "y", "x"], coords=c)
+        iso = xrft.isotropic_cross_spectrum(mk_(x), mk_(y), dim=["y", "x"], detrend=detrend, window="hann").values
+        det = {None: 0, "constant": 1, "linear": 2}[detrend]
+        w = sps.windows.hann(ny, sym=False)[:, None] * sps.windows.hann(nx, sym=False)[None, :]
+        k = np.fft.fftshift(np.fft.fftfreq(nx, 1.0)); l = np.fft.fftshift(np.fft.fftfreq(ny, 1.0))
+        codes, nbins, _ = A._radial_bins(k, l, 4, False)
+        for t in range(T):
+            fa = np.fft.fftshift(np.fft.fft2(plane_detrend(x[t].astype(np.float64), det).astype(np.float32).astype(np.float64) * w))
+            fb = np.fft.fftshift(np.fft.fft2(plane_detrend(y[t].astype(np.float64), det).astype(np.float32).astype(np.float64) * w))
+            cs = fa * np.conj(fb) / (ny * nx)
+            ref = np.bincount(codes.T.ravel(), weights=cs.real.ravel(), minlength=nbins)
+            assert np.linalg.norm(iso[t].real - ref) / np.linalg.norm(ref) < 1e-5
+            assert np.abs(iso[t].imag).max() < 1e-5 * np.abs(ref).max()

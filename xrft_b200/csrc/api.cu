@@ -1329,7 +1329,12 @@ static int spectrum2d_colsfirst(const xrftb_spectrum2d_desc& q, int ly, int lx, 
 static bool crossz_enabled() { return option(OPT_CROSS_Z) != 0; }
 template <typename T> static bool crossz_eligible(const xrftb_spectrum2d_desc& q, int ly, int lx) {
     if (!std::is_same<T, float>::value) return false;
-    if (!(q.mode == XRFTB_EPI_CROSS || q.mode == XRFTB_EPI_PHASE) || q.keep_half || q.weight_x || q.ramp_y || q.ramp_x) return false;
+    if (q.keep_half || q.weight_x || q.ramp_y || q.ramp_x) return false;
+    if (q.mode == XRFTB_EPI_BINS_CROSS) {   // radial bins of the cross spectrum in the two-field pass 2 (rowszx_bins_kernel)
+        if (!q.lut_symmetric || !bins_static_enabled() || !rows_zx_bins_shape_ok(lx - 1, q.ny) || q.nbins > q.nx || q.nbins > 4096) return false;
+    } else if (!(q.mode == XRFTB_EPI_CROSS || q.mode == XRFTB_EPI_PHASE)) {
+        return false;
+    }
     const int C = cols_tile_width<T>(ly, false);
     if (C < 4 || ly <= TypeCfg<T>::LOGE || ly > TypeCfg<T>::MAX_COLS_LOG2 || !rows_z_supported(lx - 1)) return false;
     if ((q.nx * sizeof(T)) % 16 != 0) return false;
@@ -1380,6 +1385,7 @@ static int spectrum2d_crossz(const xrftb_spectrum2d_desc& q, int ly, int lx, cud
     const int tiles_per_item = q.nx / (2 * C);
     const int box_rows = q.ny < 256 ? q.ny : 256;
     const size_t out_elem = q.mode == XRFTB_EPI_PHASE ? sizeof(T) : sizeof(C_);
+    const bool bins = q.mode == XRFTB_EPI_BINS_CROSS;
     for (long b0 = 0; b0 < q.batch; b0 += bchunk) {
         const long nb = (q.batch - b0 < bchunk) ? q.batch - b0 : bchunk;
         for (int f = 0; f < 2; ++f) {
@@ -1404,6 +1410,20 @@ static int spectrum2d_crossz(const xrftb_spectrum2d_desc& q, int ly, int lx, cud
                 rowline_fix_kernel<T><<<dim3((unsigned)nb, (unsigned)((q.nx + 1023) / 1024)), 256, 0, st>>>(colstats[f], ag[f], reinterpret_cast<const T*>(q.win_x), q.nx, q.ny, q.detrend);
                 if (int rc = check_launch("rowline_fix_kernel")) return rc;
             }
+        }
+        if (bins) {
+            if constexpr (std::is_same<T, float>::value) {
+                RowsZCrossBins bio{{zf[0], zf[1], nullptr, nullptr, ly, H, q.shift_y, q.shift_x, (T)q.scale, ag[0], ag[1], wj, nullptr},
+                                   q.lut, q.bins + (size_t)b0 * q.nbins * 2, q.nbins, 0, q.ny / 2, nb};
+                ProfScope ps_(PROF_ROWS, st);
+                for (int part = 0; part < 2; ++part) {   // rows ky in [0, Ny/2) of every plane, then the Nyquist row
+                    if (part) { bio.ky0 = q.ny / 2; bio.rows = 1; }
+                    const int rc = rows_zx_bins(bio, lx - 1, st);
+                    if (rc > 0) { set_error("spectrum2d: radial-bin pass does not cover %d x %d", q.ny, q.nx); return XRFTB_EUNSUPPORTED; }
+                    if (rc) return rc;
+                }
+            }
+            continue;
         }
         RowsZCross<T> io{zf[0], zf[1], reinterpret_cast<char*>(q.out) + (size_t)b0 * item * out_elem,
                          q.out2 ? reinterpret_cast<char*>(q.out2) + (size_t)b0 * item * sizeof(T) : nullptr, ly, H, q.shift_y, q.shift_x, (T)q.scale,

@@ -2199,6 +2199,102 @@ cols_bins_kernel(const __grid_constant__ ColsFused<float, EPI_BINS_POWER> io, co
 // a cell shares its bin (radial bins): rows 0 < ky < Ny/2 count twice, rows 0 and Ny/2 (which hold both signs of kx) once.
 // rows == 1: the SEQ row slots of a CTA are the same row (ky0) of SEQ consecutive planes; bins are keyed per (slot, bin).
 // =============================================================================================
+// ---- shared pieces of the static cell-to-bin machinery (rows_bins_kernel, rowszx_bins_kernel): NTHR threads own 16 cells each
+// Counting sort of the CTA's cells by key (once per launch): key[i] in [0, nseg) or 0xFFFF (masked).  On return pos[i] is the
+// cell's slot in the key-ordered staging array, id[] are the keys of THIS thread's 16 consecutive slots and cont_in / cont_out
+// tell whether the run of equal keys at its first / last slot continues in the neighbouring lane of the warp.
+template <int NTHR>
+__device__ __forceinline__ void bins_assign_slots(const unsigned short (&key)[16], int nseg, int* cnt, unsigned short* binid, int* scan_part,
+                                                  unsigned short (&pos)[16], unsigned short (&id)[16], bool& cont_in, bool& cont_out) {
+    constexpr int NCELL = NTHR * 16;
+    const int lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < nseg; i += NTHR) cnt[i] = 0;
+    for (int i = threadIdx.x; i < NCELL; i += NTHR) binid[i] = 0xFFFFu;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+        if (key[i] != 0xFFFFu) atomicAdd(cnt + key[i], 1);
+    __syncthreads();
+    {   // exclusive prefix sum of the counters (nseg <= 4096): one thread per run of consecutive segments
+        const int per = (nseg + NTHR - 1) / NTHR;
+        const int lo = threadIdx.x * per, hi = lo + per < nseg ? lo + per : nseg;
+        int local = 0;
+        for (int i = lo; i < hi; ++i) local += cnt[i];
+        int incl = local;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) { const int o = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += o; }
+        if (lane == 31) scan_part[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        int run = incl - local;
+        for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) run += scan_part[w];
+        for (int i = lo; i < hi; ++i) {   // slots [run, run + count) belong to segment i; the counter becomes the fill cursor
+            const int c = cnt[i];
+            for (int j = 0; j < c; ++j) binid[run + j] = (unsigned short)i;
+            cnt[i] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+    // the cells of a warp that share a key take consecutive slots (neighbouring cells mostly share the bin): the per-tile
+    // scatter into the staging array is then nearly free of bank conflicts
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const unsigned k = key[i];
+        const unsigned grp = __match_any_sync(0xffffffffu, k);
+        const int leader = __ffs(grp) - 1;
+        int base = 0;
+        if (lane == leader && k != 0xFFFFu) base = atomicAdd(cnt + k, __popc(grp));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        pos[i] = k == 0xFFFFu ? (unsigned short)0xFFFFu : (unsigned short)(base + __popc(grp & ((1u << lane) - 1u)));
+    }
+    __syncthreads();
+    {
+        const uint4* pid = reinterpret_cast<const uint4*>(binid + threadIdx.x * 16);
+        const uint4 a = pid[0], b = pid[1];
+        const unsigned w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 16; ++i) id[i] = (unsigned short)((w[i >> 1] >> (16 * (i & 1))) & 0xFFFFu);
+    }
+    const unsigned prev_last = __shfl_up_sync(0xffffffffu, (unsigned)id[15], 1);
+    cont_in = lane > 0 && prev_last == id[0];
+    const unsigned next_first = __shfl_down_sync(0xffffffffu, (unsigned)id[0], 1);
+    cont_out = lane < 31 && next_first == id[15];
+}
+// Sums of the runs of equal keys in the key-ordered staging array: every thread adds up its own 16 consecutive slots
+// (128-bit loads, perfectly balanced); runs that span lanes are completed by a warp-wide segmented scan of the partial sums
+// still open at the end of each lane; emit(key, sum) is called once per run and warp (a run that crosses a warp boundary is
+// emitted in two parts).
+template <class Emit>
+__device__ __forceinline__ void bins_segmented_sum(const float* slots, const unsigned short (&id)[16], bool cont_in, bool cont_out, Emit&& emit) {
+    const int lane = threadIdx.x & 31;
+    float x[16];
+    const float4* pv = reinterpret_cast<const float4*>(slots);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float4 q = pv[i]; x[4 * i] = q.x; x[4 * i + 1] = q.y; x[4 * i + 2] = q.z; x[4 * i + 3] = q.w; }
+    float acc = x[0], head = 0.f;
+    bool split = false;     // a run boundary inside these slots
+#pragma unroll
+    for (int i = 1; i < 16; ++i) {
+        if (id[i] != id[i - 1]) {
+            if (!split) { head = acc; split = true; } else emit((unsigned)id[i - 1], acc);
+            acc = x[i];
+        } else {
+            acc += x[i];
+        }
+    }
+    float open = acc;
+    bool flag = split || !cont_in;     // the run still open at the end of this lane began in this lane
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const float y = __shfl_up_sync(0xffffffffu, open, off);
+        const bool fy = __shfl_up_sync(0xffffffffu, (int)flag, off) != 0;
+        if (lane >= off && !flag) { open += y; flag = fy; }
+    }
+    const float before = __shfl_up_sync(0xffffffffu, open, 1);   // sum of the run that reaches this lane's first slot
+    if (split) emit((unsigned)id[0], head + (cont_in ? before : 0.f));
+    if (!cont_out) emit((unsigned)id[15], open);
+}
+
 struct RowsBins {
     RowsC2CPower<float> base;   // in, logNy, H, shifts, scale, column-line completion tables (out unused)
     const int* lut;             // int32 [Ny][Nx], bin of each OUTPUT cell (negative = skip)
@@ -2220,8 +2316,9 @@ rows_bins_kernel(RowsBins io, const float2* __restrict__ tw) {
     float* stage = reinterpret_cast<float*>(smem_raw);                               // aliases the exchange buffer
     unsigned char* tail = smem_raw + (size_t)SEQ * G_::LPAD * sizeof(cplx<T>);
     unsigned short* binid = reinterpret_cast<unsigned short*>(tail);                 // [NCELL] key of every slot (0xFFFF = unused)
-    int* cnt = reinterpret_cast<int*>(tail + NCELL * sizeof(unsigned short));        // [nseg] counters -> segment starts (setup only)
-    const int s = threadIdx.x / NT, u = threadIdx.x % NT, lane = threadIdx.x & 31;
+    int* cnt = reinterpret_cast<int*>(tail + NCELL * sizeof(unsigned short));        // [nseg] counters -> fill cursors (setup only)
+    __shared__ int scan_part[32];
+    const int s = threadIdx.x / NT, u = threadIdx.x % NT;
     cplx<T>* sm = smem + s * G_::LPAD;
     const bool per_slot = io.rows == 1;              // Nyquist-row launch: one plane per row slot
     const int P = per_slot ? SEQ : 1;
@@ -2232,10 +2329,8 @@ rows_bins_kernel(RowsBins io, const float2* __restrict__ tw) {
     const int Ny = 1 << io.base.logNy;
     const int sy = io.base.shift_y ? Ny / 2 : 0, sx = io.base.shift_x ? Nx / 2 : 0;
     // ---- once per launch: bins of this thread's cells, counting sort of the CTA's cells by (slot, bin)
-    for (int i = threadIdx.x; i < nseg; i += NTHR) cnt[i] = 0;
-    for (int i = threadIdx.x; i < NCELL; i += NTHR) binid[i] = 0xFFFFu;
-    __syncthreads();
-    unsigned short key[E];
+    unsigned short key[E], pos[E], id[E];
+    bool cont_in, cont_out;
     {
         const int* lrow = io.lut + (long)((ky + sy) & (Ny - 1)) * Nx;
 #pragma unroll
@@ -2245,60 +2340,10 @@ rows_bins_kernel(RowsBins io, const float2* __restrict__ tw) {
                 const int kx = final_index<LOG2L, LOGE>(u, g, t);
                 const int b = __ldg(lrow + ((kx + sx) & (Nx - 1)));
                 key[g + t * G] = (b >= 0 && b < io.nbins) ? (unsigned short)((per_slot ? s * io.nbins : 0) + b) : (unsigned short)0xFFFFu;
-                if (b >= 0 && b < io.nbins) atomicAdd(cnt + key[g + t * G], 1);
             }
     }
-    __syncthreads();
-    // exclusive prefix sum of the counters (nseg <= 4096): one thread per run of consecutive segments
-    __shared__ int scan_part[32];
-    {
-        const int per = (nseg + NTHR - 1) / NTHR;
-        const int lo = threadIdx.x * per, hi = lo + per < nseg ? lo + per : nseg;
-        int local = 0;
-        for (int i = lo; i < hi; ++i) local += cnt[i];
-        int incl = local;
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) { const int o = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += o; }
-        if (lane == 31) scan_part[threadIdx.x >> 5] = incl;
-        __syncthreads();
-        int run = incl - local;
-        for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) run += scan_part[w];
-        for (int i = lo; i < hi; ++i) {   // slots [run, run + count) belong to segment i; the counter becomes the fill cursor
-            const int c = cnt[i];
-            for (int j = 0; j < c; ++j) binid[run + j] = (unsigned short)i;
-            cnt[i] = run;
-            run += c;
-        }
-    }
-    __syncthreads();
-    // slots: the cells of a warp that share a key take consecutive slots (consecutive kx of a row mostly share the bin)
-    unsigned short pos[E];
-#pragma unroll
-    for (int i = 0; i < E; ++i) {
-        const unsigned k = key[i];
-        const unsigned grp = __match_any_sync(0xffffffffu, k);
-        const int leader = __ffs(grp) - 1;
-        int base = 0;
-        if (lane == leader && k != 0xFFFFu) base = atomicAdd(cnt + k, __popc(grp));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        pos[i] = k == 0xFFFFu ? (unsigned short)0xFFFFu : (unsigned short)(base + __popc(grp & ((1u << lane) - 1u)));
-    }
+    bins_assign_slots<NTHR>(key, nseg, cnt, binid, scan_part, pos, id, cont_in, cont_out);
     const float mult = ((ky == 0 || 2 * ky == Ny) ? 1.f : 2.f) * io.base.scale;
-    __syncthreads();
-    // this thread's E consecutive slots: their keys never change
-    unsigned short id[E];
-    {
-        const uint4* pid = reinterpret_cast<const uint4*>(binid + threadIdx.x * E);
-        const uint4 a = pid[0], b = pid[1];
-        const unsigned w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-        for (int i = 0; i < E; ++i) id[i] = (unsigned short)((w[i >> 1] >> (16 * (i & 1))) & 0xFFFFu);
-    }
-    // the run that reaches this thread's first slot started in an earlier lane of the warp?
-    const unsigned prev_last = __shfl_up_sync(0xffffffffu, (unsigned)id[E - 1], 1);
-    const bool cont_in = lane > 0 && prev_last == id[0];
-    const unsigned next_first = __shfl_down_sync(0xffffffffu, (unsigned)id[0], 1);
-    const bool cont_out = lane < 31 && next_first == id[E - 1];
     // ---- tiles: mode A: plane = blockIdx.x / groups + k * (gridDim.x / groups); mode B: SEQ planes per tile
     const long tiles_total = per_slot ? (io.nplanes + SEQ - 1) / SEQ : io.nplanes;
     const long tstep = gridDim.x / groups;
@@ -2329,43 +2374,148 @@ rows_bins_kernel(RowsBins io, const float2* __restrict__ tw) {
             if (pos[i] != 0xFFFFu) stage[pos[i]] = (f.x * f.x + f.y * f.y) * mult;
         }
         __syncthreads();
-        {
-            auto emit = [&](unsigned k, float val) {
-                if (k == 0xFFFFu) return;
-                const long plane = per_slot ? tile * SEQ + (long)(k / (unsigned)io.nbins) : tile;
-                if (plane < io.nplanes) atomicAdd(io.bins + plane * (long)io.nbins + (per_slot ? k % (unsigned)io.nbins : k), (double)val);
-            };
-            float x[E];
-            const float4* pv = reinterpret_cast<const float4*>(stage + threadIdx.x * E);
-#pragma unroll
-            for (int i = 0; i < E / 4; ++i) { const float4 q = pv[i]; x[4 * i] = q.x; x[4 * i + 1] = q.y; x[4 * i + 2] = q.z; x[4 * i + 3] = q.w; }
-            // runs inside this thread's slots: the first one may have begun in earlier lanes (head), the last one may go on (tail)
-            float acc = x[0], head = 0.f;
-            bool split = false;     // a run boundary inside these slots
-            const unsigned head_key = id[0];
-#pragma unroll
-            for (int i = 1; i < E; ++i) {
-                if (id[i] != id[i - 1]) {
-                    if (!split) { head = acc; split = true; } else emit(id[i - 1], acc);
-                    acc = x[i];
-                } else {
-                    acc += x[i];
-                }
-            }
-            // segmented inclusive scan over the lanes of the partial sum that is still open at the end of each lane
-            float open = acc;
-            bool flag = split || !cont_in;     // the open run began in this lane
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                const float y = __shfl_up_sync(0xffffffffu, open, off);
-                const bool fy = __shfl_up_sync(0xffffffffu, (int)flag, off) != 0;
-                if (lane >= off && !flag) { open += y; flag = fy; }
-            }
-            const float before = __shfl_up_sync(0xffffffffu, open, 1);   // sum of the run that reaches this lane's first slot
-            if (split) emit(head_key, head + (cont_in ? before : 0.f));
-            if (!cont_out) emit(id[E - 1], open);
-        }
+        bins_segmented_sum(stage + threadIdx.x * E, id, cont_in, cont_out, [&](unsigned k, float val) {
+            if (k == 0xFFFFu) return;
+            const long plane = per_slot ? tile * SEQ + (long)(k / (unsigned)io.nbins) : tile;
+            if (plane < io.nplanes) atomicAdd(io.bins + plane * (long)io.nbins + (per_slot ? k % (unsigned)io.nbins : k), (double)val);
+        });
         __syncthreads();   // the staging array is scattered into again by the next transform
+    }
+}
+
+// =============================================================================================
+// Two-field pass 2 with the radial-bin epilogue of the isotropic cross spectrum (xrft/xrft.py:1098-1187): the front end of
+// rowszx_kernel (separation of the packed column spectra, row transforms of both fields) and the static cell-to-bin machinery
+// of rows_bins_kernel.  Each of the 2 NT ROWS threads owns 16 cells of a row (kx = tt + 2 NT j).  Cells of rows 0 < ky < Ny/2
+// stand for their mirror images too: C(-k) = conj C(k) lands in the same radial bin, so the bin receives 2 Re C and the
+// imaginary parts cancel; rows 0 and Ny/2 hold both signs of kx and contribute C as it is.  bins: [plane][nbins][2].
+// =============================================================================================
+struct RowsZCrossBins {
+    RowsZCross<float> base;     // z1, z2, logNy, H, shifts, scale, completion tables, tw2 (out / out2 unused)
+    const int* lut;
+    double* bins;
+    int nbins;
+    int ky0, rows;
+    long nplanes;
+};
+template <int LOG2M, int LOGE, int ROWS>
+__global__ void __launch_bounds__((1 << (LOG2M - LOGE)) * 2 * ROWS, min_blocks_for((1 << (LOG2M - LOGE)) * 2 * ROWS))
+rowszx_bins_kernel(RowsZCrossBins io, const float2* __restrict__ tw) {
+    using T = float;
+    using G_ = Geometry<LOG2M, LOGE>;
+    constexpr int E = G_::E, NT = G_::NT, M = 1 << LOG2M, Nx = 2 * M, NTHR = 2 * NT * ROWS, NCELL = ROWS * Nx;
+    constexpr int ROW_STRIDE = 2 * G_::LPAD + 8;
+    constexpr int R = 1 << G_::LOGR_LAST, G = E / R;
+    static_assert(NCELL == NTHR * 16 && E == 16, "every thread owns 16 cells");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx<T>* smem = reinterpret_cast<cplx<T>*>(smem_raw);
+    float* stage_re = reinterpret_cast<float*>(smem_raw);          // both alias the exchange buffers (2 ROWS ROW_STRIDE complex)
+    float* stage_im = stage_re + NCELL;
+    cplx<T>* smw = smem + 2 * ROWS * ROW_STRIDE;                    // [M] radix-2 twiddles
+    unsigned short* binid = reinterpret_cast<unsigned short*>(smw + M);
+    int* cnt = reinterpret_cast<int*>(binid + NCELL);
+    __shared__ int scan_part[32];
+    const int r = threadIdx.x / (2 * NT), f = (threadIdx.x / NT) & 1, u = threadIdx.x % NT, tt = threadIdx.x % (2 * NT);
+    cplx<T>* sm = smem + (2 * r + f) * ROW_STRIDE;
+    for (int k = threadIdx.x; k < M; k += NTHR) smw[k] = __ldg(io.base.tw2 + k);
+    const bool per_slot = io.rows == 1;
+    const int P = per_slot ? ROWS : 1;
+    const int nseg = P * io.nbins;
+    const int groups = per_slot ? 1 : io.rows / ROWS;
+    const int g0 = (int)(blockIdx.x % (unsigned)groups);
+    const int ky = io.ky0 + (per_slot ? 0 : g0 * ROWS + r);
+    const int Ny = 1 << io.base.logNy;
+    const int sy = io.base.shift_y ? Ny / 2 : 0, sx = io.base.shift_x ? Nx / 2 : 0;
+    const bool self = (ky == 0) || (2 * ky == Ny);
+    // only tiles with a self-mirrored row have imaginary parts to add up (uniform per CTA)
+    const bool has_im = per_slot ? (io.ky0 == 0 || 2 * io.ky0 == Ny) : (io.ky0 == 0 && g0 == 0) || (2 * (io.ky0 + g0 * ROWS) <= Ny && 2 * (io.ky0 + g0 * ROWS + ROWS - 1) >= Ny);
+    unsigned short key[16], pos[16], id[16];
+    bool cont_in, cont_out;
+    {
+        const int* lrow = io.lut + (long)((ky + sy) & (Ny - 1)) * Nx;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int kx = tt + j * (2 * NT);
+            const int b = __ldg(lrow + ((kx + sx) & (Nx - 1)));
+            key[j] = (b >= 0 && b < io.nbins) ? (unsigned short)((per_slot ? r * io.nbins : 0) + b) : (unsigned short)0xFFFFu;
+        }
+    }
+    bins_assign_slots<NTHR>(key, nseg, cnt, binid, scan_part, pos, id, cont_in, cont_out);
+    const float mult = (self ? 1.f : 2.f) * io.base.scale;
+    const cplx<T>* zf = f ? io.base.z2 : io.base.z1;
+    const cplx<T>* agf = f ? io.base.ag2 : io.base.ag1;
+    const long tiles_total = per_slot ? (io.nplanes + ROWS - 1) / ROWS : io.nplanes;
+    const long tstep = gridDim.x / groups;
+    for (long tile = blockIdx.x / groups; tile < tiles_total; tile += tstep) {
+        const long b = per_slot ? tile * ROWS + r : tile;
+        const bool act = b < io.nplanes;
+        cplx<T> v[2][E];
+        {
+            const long bb = act ? b : 0;
+            const cplx<T>* pa = zf + ((bb << io.base.logNy) + ky) * (long)M + u;
+            const cplx<T>* pb = zf + ((bb << io.base.logNy) + ((Ny - ky) & (Ny - 1))) * (long)M + u;
+            cplx<T> za[E], zb[E];
+#pragma unroll
+            for (int q = 0; q < E; ++q) { za[q] = act ? pa[q * NT] : mk<T>(0, 0); zb[q] = act ? pb[q * NT] : mk<T>(0, 0); }
+#pragma unroll
+            for (int q = 0; q < E; ++q) {
+                v[0][q] = mk<T>(za[q].x + zb[q].x, za[q].y - zb[q].y);
+                v[1][q] = mk<T>(za[q].y + zb[q].y, zb[q].x - za[q].x);
+            }
+        }
+        if (agf != nullptr && act) {
+            const cplx<T> W = __ldg(io.base.wj + 2 * ky), J = __ldg(io.base.wj + 2 * ky + 1);
+            const cplx<T>* pa = agf + b * (long)Nx + 2 * u;
+#pragma unroll
+            for (int q = 0; q < E; ++q) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(pa + 2 * q * NT));
+                v[0][q].x += a.x * W.x + a.y * J.x; v[0][q].y += a.x * W.y + a.y * J.y;
+                v[1][q].x += a.z * W.x + a.w * J.x; v[1][q].y += a.z * W.y + a.w * J.y;
+            }
+        }
+        block_fft<T, LOG2M, LOGE, 2, 2>(v, u, sm, 1, tw);   // ends with a barrier: the exchange buffers are free
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+#pragma unroll
+            for (int t = 0; t < R; ++t) {
+                const int k = final_index<LOG2M, LOGE>(u, g, t);
+                const cplx<T> fa = v[0][g + t * G];
+                const cplx<T> wb = cmul(v[1][g + t * G], smw[k]);
+                sm[k] = cadd(fa, wb);
+                sm[k + M] = csub(fa, wb);
+            }
+        __syncthreads();
+        float cre[16], cim[16];
+        {
+            const cplx<T>* s1 = smem + (2 * r) * ROW_STRIDE;
+            const cplx<T>* s2 = s1 + ROW_STRIDE;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int kx = tt + j * (2 * NT);
+                const cplx<T> c = cmulc(s1[kx], s2[kx]);
+                cre[j] = act ? c.x * mult : 0.f;
+                cim[j] = (act && self) ? c.y * mult : 0.f;
+            }
+        }
+        __syncthreads();   // both fields' rows have been read: the buffers become the staging arrays
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            if (pos[j] != 0xFFFFu) { stage_re[pos[j]] = cre[j]; if (has_im) stage_im[pos[j]] = cim[j]; }
+        __syncthreads();
+        auto target = [&](unsigned k) -> double* {
+            const long plane = per_slot ? tile * ROWS + (long)(k / (unsigned)io.nbins) : tile;
+            return plane < io.nplanes ? io.bins + (plane * (long)io.nbins + (per_slot ? k % (unsigned)io.nbins : k)) * 2 : nullptr;
+        };
+        bins_segmented_sum(stage_re + threadIdx.x * 16, id, cont_in, cont_out, [&](unsigned k, float val) {
+            if (k == 0xFFFFu) return;
+            if (double* p = target(k)) atomicAdd(p, (double)val);
+        });
+        if (has_im)
+            bins_segmented_sum(stage_im + threadIdx.x * 16, id, cont_in, cont_out, [&](unsigned k, float val) {
+                if (k == 0xFFFFu) return;
+                if (double* p = target(k)) atomicAdd(p + 1, (double)val);
+            });
+        __syncthreads();   // the buffers are scattered into again by the next tile
     }
 }
 

@@ -56,6 +56,8 @@ template <typename T> int rows_z_cross(RowsZCross<T> io, int log2M, long nseq, i
 // pass 2 of the columns-first order with the radial-bin epilogue (float32); returns 1 when the shape is not covered
 int rows_bins(const RowsBins& io, int log2L, cudaStream_t st);
 bool rows_bins_shape_ok(int log2L, int ny);
+int rows_zx_bins(RowsZCrossBins io, int log2M, cudaStream_t st);
+bool rows_zx_bins_shape_ok(int log2M, int ny);
 // half lengths the z-mode pass 2 is dispatched for (Nx = 1024 .. 4096: the sizes covered by the GPU parity tests; the
 // 2^12 instantiation exists but stays off until it has been through them)
 inline bool rows_z_supported(int log2M) { return log2M >= 9 && log2M <= 11; }

@@ -126,6 +126,32 @@ static int launch_rows_bins(const RowsBins& io, cudaStream_t st) {
     return check_launch("rows_bins_kernel");
 }
 
+// two-field pass 2 + radial bins (rowszx_bins_kernel).  Returns 1 when the launch shape does not fit (caller falls back).
+template <int LOG2M, int ROWS>
+static int launch_rowszx_bins(const RowsZCrossBins& io, cudaStream_t st) {
+    constexpr int LOGE = cmin(TypeCfg<float>::LOGE, LOG2M);
+    using G_ = Geometry<LOG2M, LOGE>;
+    auto kern = rowszx_bins_kernel<LOG2M, LOGE, ROWS>;
+    constexpr int threads = G_::NT * 2 * ROWS;
+    const int P = io.rows == 1 ? ROWS : 1;
+    if (P * io.nbins > 4096 || (io.rows != 1 && io.rows % ROWS != 0)) return 1;
+    constexpr size_t smem = ((size_t)2 * ROWS * (2 * G_::LPAD + 8) + (size_t)(1 << LOG2M)) * sizeof(float2)
+                            + (size_t)ROWS * (2 << LOG2M) * sizeof(unsigned short) + 4096 * sizeof(int);
+    static DevOcc occ_;
+    int occ = 0;
+    if (int rc = prepare_kernel(kern, threads, smem, &occ_, &occ)) return rc;
+    const float2* tw = twiddle_fft<float>(LOG2M);
+    if (!tw) return -3;
+    const long groups = io.rows == 1 ? 1 : io.rows / ROWS;
+    const long tiles = io.rows == 1 ? (io.nplanes + ROWS - 1) / ROWS : io.nplanes;
+    long grid = (long)sm_count() * occ;
+    if (grid > tiles * groups) grid = tiles * groups;
+    grid -= grid % groups;
+    if (grid < groups) return 1;
+    kern<<<(unsigned)grid, threads, smem, st>>>(io, tw);
+    return check_launch("rowszx_bins_kernel");
+}
+
 // pass 2 on packed column spectra (rowsz_power_kernel): ROWS half-spectrum rows per CTA, two M-point sequences per thread
 template <typename T, int LOG2M, int ROWS>
 static int launch_rowsz_power(const RowsZPower<T>& io, long nseq, cudaStream_t st) {

@@ -29,4 +29,20 @@ bool rows_bins_shape_ok(int log2L, int ny) {
     }
     return ny / 2 >= seq && (ny / 2) % seq == 0;
 }
+// two-field pass 2 of the z-mode chain with the radial-bin epilogue (float32, M = Nx/2 in 2^9 .. 2^11); 1 = shape not covered
+int rows_zx_bins(RowsZCrossBins io, int log2M, cudaStream_t st) {
+    io.base.tw2 = twiddle_fft<float>(log2M + 1);
+    if (!io.base.tw2) return -3;
+    switch (log2M) {
+#define Z(K, P) case K: return launch_rowszx_bins<K, P>(io, st);
+        Z(9, 4) Z(10, 2) Z(11, 1)
+#undef Z
+        default: break;
+    }
+    return 1;
+}
+bool rows_zx_bins_shape_ok(int log2M, int ny) {
+    const int rows = log2M == 9 ? 4 : log2M == 10 ? 2 : log2M == 11 ? 1 : 0;
+    return rows > 0 && ny / 2 >= rows && (ny / 2) % rows == 0;
+}
 }  // namespace xrftb
