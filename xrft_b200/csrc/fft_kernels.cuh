@@ -2182,24 +2182,8 @@ cols_bins_kernel(const __grid_constant__ ColsFused<float, EPI_BINS_POWER> io, co
 }
 
 // =============================================================================================
-// Pass 2 of the columns-first order with the radial-bin epilogue of the isotropic power spectrum (BASELINE config 4;
-// xrft/xrft.py:895-906, 948-1010): rows ky in [0, Ny/2] of the half spectrum are transformed along x exactly like
-// rows_kernel<RowsC2CPower>, but |F|^2 never leaves the SM -- it is summed into the plane's radial bins.
-//
-// No floating-point shared-memory atomics (they compile to compare-and-swap loops and serialise when neighbouring rows hit
-// the same bin).  Instead the mapping from cells to bins is made STATIC per CTA: a launch covers `rows` consecutive
-// half-spectrum rows of every plane starting at ky0 (rows % SEQ == 0, or rows == 1 for the Nyquist row), the grid is a
-// multiple of the rows / SEQ row groups of a plane, so a CTA meets the same rows of every plane it processes.  Once per
-// launch each thread looks up the bins of its E cells in the host-built LUT and the CTA counting-sorts its cells by bin
-// (native integer atomics; cells of one warp that share a bin get consecutive slots, so the per-tile scatter is nearly
-// conflict-free): every cell gets a fixed slot `pos` in a staging array ordered by bin, and a static table names the bin
-// of every slot.  Per tile: each thread drops its E values at their slots, one barrier, then every thread adds up its own
-// E CONSECUTIVE slots (perfectly balanced, 128-bit loads) -- runs that end inside its slots are complete after a warp-wide
-// segmented scan of the partial sums and go to the plane's fp64 bins with one atomic each.  The mirror image (-ky, -kx) of
-// a cell shares its bin (radial bins): rows 0 < ky < Ny/2 count twice, rows 0 and Ny/2 (which hold both signs of kx) once.
-// rows == 1: the SEQ row slots of a CTA are the same row (ky0) of SEQ consecutive planes; bins are keyed per (slot, bin).
-// =============================================================================================
-// ---- shared pieces of the static cell-to-bin machinery (rows_bins_kernel, rowszx_bins_kernel): NTHR threads own 16 cells each
+// Radial bins summed on chip.  Shared pieces of the static cell-to-bin machinery (rows_bins_kernel, rowszx_bins_kernel):
+// NTHR threads own 16 cells each.
 // Counting sort of the CTA's cells by key (once per launch): key[i] in [0, nseg) or 0xFFFF (masked).  On return pos[i] is the
 // cell's slot in the key-ordered staging array, id[] are the keys of THIS thread's 16 consecutive slots and cont_in / cont_out
 // tell whether the run of equal keys at its first / last slot continues in the neighbouring lane of the warp.
@@ -2295,6 +2279,24 @@ __device__ __forceinline__ void bins_segmented_sum(const float* slots, const uns
     if (!cont_out) emit((unsigned)id[15], open);
 }
 
+// =============================================================================================
+// Pass 2 of the columns-first order with the radial-bin epilogue of the isotropic power spectrum (BASELINE config 4;
+// xrft/xrft.py:895-906, 948-1010): rows ky in [0, Ny/2] of the half spectrum are transformed along x exactly like
+// rows_kernel<RowsC2CPower>, but |F|^2 never leaves the SM -- it is summed into the plane's radial bins.
+//
+// No floating-point shared-memory atomics (they compile to compare-and-swap loops and serialise when neighbouring rows hit
+// the same bin).  Instead the mapping from cells to bins is made STATIC per CTA: a launch covers `rows` consecutive
+// half-spectrum rows of every plane starting at ky0 (rows % SEQ == 0, or rows == 1 for the Nyquist row), the grid is a
+// multiple of the rows / SEQ row groups of a plane, so a CTA meets the same rows of every plane it processes.  Once per
+// launch each thread looks up the bins of its E cells in the host-built LUT and the CTA counting-sorts its cells by bin
+// (native integer atomics; cells of one warp that share a bin get consecutive slots, so the per-tile scatter is nearly
+// conflict-free): every cell gets a fixed slot `pos` in a staging array ordered by bin, and a static table names the bin
+// of every slot.  Per tile: each thread drops its E values at their slots, one barrier, then every thread adds up its own
+// E CONSECUTIVE slots (perfectly balanced, 128-bit loads) -- runs that end inside its slots are complete after a warp-wide
+// segmented scan of the partial sums and go to the plane's fp64 bins with one atomic each.  The mirror image (-ky, -kx) of
+// a cell shares its bin (radial bins): rows 0 < ky < Ny/2 count twice, rows 0 and Ny/2 (which hold both signs of kx) once.
+// rows == 1: the SEQ row slots of a CTA are the same row (ky0) of SEQ consecutive planes; bins are keyed per (slot, bin).
+// =============================================================================================
 struct RowsBins {
     RowsC2CPower<float> base;   // in, logNy, H, shifts, scale, column-line completion tables (out unused)
     const int* lut;             // int32 [Ny][Nx], bin of each OUTPUT cell (negative = skip)
