@@ -362,9 +362,8 @@ struct StagesAsync {
                 scatter<C, 0, 2>(v, u, smL);
                 __syncthreads();
                 gather<C, 0, 2>(v, u, smL);
-                fence_proxy_async_smem();   // generic-proxy accesses of smL are ordered before the bulk copy that re-fills it
                 __syncthreads();
-                hook();
+                hook();                     // (the issuing thread fences the proxies itself: see cols_async_kernel)
             } else {
                 scatter<CG, 0, 1>(v, u, smX);
                 __syncthreads();

@@ -394,8 +394,9 @@ rows2_kernel(RowsR2CFused<T> io, const cplx<T>* __restrict__ tw, long nseq) {
                 if (m > 1e-30f && m < 1e30f) {
                     // quantum Q = 2^(floor(log2 m) - 21): A0, B are multiples of Q and |A0 + B j| < 2^(floor(log2 m) + 2),
                     // so every line value is representable: fmaf(B, j, A0) and (that + B) return them exactly
-                    const float p2 = __int_as_float(__float_as_int(m) & 0x7f800000);
-                    const float Q = p2 * 4.76837158203125e-07f, iQ = 2097152.0f / p2;
+                    const int p2b = __float_as_int(m) & 0x7f800000;
+                    const float p2 = __int_as_float(p2b);
+                    const float Q = p2 * 4.76837158203125e-07f, iQ = __int_as_float((275 << 23) - p2b);   // 2^21 / p2, exactly
                     A0[r] = rintf(x0 * iQ) * Q;
                     B[r] = rintf((x1 - x0) * (1.0f / (float)(Nx - 1)) * iQ) * Q;
                 }
@@ -996,7 +997,9 @@ cols_async_kernel(const __grid_constant__ IO io, const cplx<T>* __restrict__ tw,
     if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_init_fence(); }
     io.template init<LOG2L, LOGE, C, 2>(smX);   // ends with a barrier when there is a histogram
     __syncthreads();
-    auto issue = [&](long tile) { io.template issue_load<LOG2L, C>(tile, smL, bar); };
+    // the landing buffer was last touched through the generic proxy (exchange #0); the barrier before the issue orders those
+    // accesses before this thread, whose proxy fence orders them before the bulk copies that re-fill the buffer
+    auto issue = [&](long tile) { fence_proxy_async_smem(); io.template issue_load<LOG2L, C>(tile, smL, bar); };
     if (threadIdx.x == 0 && (long)blockIdx.x < ntiles) issue((long)blockIdx.x);
     unsigned phase = 0;
     for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -1306,17 +1309,15 @@ template <typename T> struct ColsR2CPack {
             }
         }
     }
+    // z mode: w_x of the thread's four real columns, RAW -- the load is issued ahead of the wait for the tile and nothing may
+    // consume it before (fix_apply halves it); other modes: ones
     template <int C> __device__ __forceinline__ float4 col_fetch(long tile, int cg) const {
         float4 w = make_float4(1.f, 1.f, 1.f, 1.f);
         if constexpr (sizeof(T) == 4) {
-            if (zout != nullptr) {
-                w = make_float4(.5f, .5f, .5f, .5f);
-                if (wx != nullptr) {
-                    const long b = tile / tiles_per_item;
-                    const int x0 = (int)(tile - b * tiles_per_item) * (2 * C) + cg * 4;
-                    const float4 a = __ldg(reinterpret_cast<const float4*>(wx + x0));
-                    w = make_float4(.5f * a.x, .5f * a.y, .5f * a.z, .5f * a.w);
-                }
+            if (zout != nullptr && wx != nullptr) {
+                const long b = tile / tiles_per_item;
+                const int x0 = (int)(tile - b * tiles_per_item) * (2 * C) + cg * 4;
+                w = __ldg(reinterpret_cast<const float4*>(wx + x0));
             }
         }
         return w;
@@ -1409,14 +1410,17 @@ template <typename T> struct ColsR2CPack {
                     }
                     const float x0v[4] = {e0.x, e0.y, e0.z, e0.w}, x1v[4] = {e1.x, e1.y, e1.z, e1.w};
                     float A0[4], B[4], sx[4] = {0.f, 0.f, 0.f, 0.f}, tq[4] = {0.f, 0.f, 0.f, 0.f};
-                    const float wc[4] = {wc4.x, wc4.y, wc4.z, wc4.w};
+                    const float hf = zout != nullptr ? .5f : 1.f;   // z mode: w_x / 2 (exact halving)
+                    const float wc[4] = {hf * wc4.x, hf * wc4.y, hf * wc4.z, hf * wc4.w};
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const float m = fmaxf(fabsf(x0v[k]), fabsf(x1v[k]));
                         A0[k] = 0.f; B[k] = 0.f;
                         if (m > 1e-30f && m < 1e30f) {   // same exact-line construction as the row-line prologue of rows2_kernel
-                            const float p2 = __int_as_float(__float_as_int(m) & 0x7f800000);
-                            const float Q = p2 * 4.76837158203125e-07f, iQ = 2097152.0f / p2;
+                            const int p2b = __float_as_int(m) & 0x7f800000;
+                            const float p2 = __int_as_float(p2b);
+                            // 2^21 / p2 for a power of two p2 = 2^(e-127): the exponent field 127 + 21 - (e - 127), no division
+                            const float Q = p2 * 4.76837158203125e-07f, iQ = __int_as_float((275 << 23) - p2b);
                             A0[k] = rintf(x0v[k] * iQ) * Q;
                             B[k] = rintf((x1v[k] - x0v[k]) * (1.0f / (float)(Ny > 1 ? Ny - 1 : 1)) * iQ) * Q;
                         }
@@ -1490,8 +1494,9 @@ template <typename T> struct ColsR2CPack {
                 y.x *= wrow;
                 y.y *= wrow;
                 if constexpr (V == 2 && sizeof(T) == 4) {   // z mode: w_x / 2 of the two real columns (1 otherwise: exact)
-                    y.x *= vv == 0 ? wc4.x : wc4.z;
-                    y.y *= vv == 0 ? wc4.y : wc4.w;
+                    const float hf = zout != nullptr ? .5f : 1.f;
+                    y.x *= hf * (vv == 0 ? wc4.x : wc4.z);
+                    y.y *= hf * (vv == 0 ? wc4.y : wc4.w);
                 }
                 v[vv][q] = y;
             }
