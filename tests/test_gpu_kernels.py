@@ -256,16 +256,56 @@ def test_chirpz_strided_long_and_inverse(dt):
     decompositions), forward and inverse, plus in-place"""
     from xrft_b200 import backend as B
     rng = np.random.default_rng(11)
-    for n, b in ((5000, 3), (4099, 2), (777, 5)):
+    for n, b in ((5003, 3), (4099, 2), (777, 5)):
         x = cplx(rng, (2, n, b), dt)
         t = torch.from_numpy(x).cuda()
         y = B.fftn(t, axes=[1]).cpu().numpy()
         assert relerr(y, np.fft.fft(x.astype(np.complex128), axis=1)) < TOL[dt] * 20
         yi = B.ifftn(t, axes=[1]).cpu().numpy()
         assert relerr(yi, np.fft.ifft(x.astype(np.complex128), axis=1)) < TOL[dt] * 20
-    x2 = cplx(rng, (3, 100, 30), dt)     # two non-power-of-two axes: strided then contiguous chirp-z
+    x2 = cplx(rng, (3, 101, 67), dt)     # two prime axes: strided then contiguous chirp-z
     y2 = B.fftn(torch.from_numpy(x2).cuda(), axes=[1, 2]).cpu().numpy()
     assert relerr(y2, np.fft.fftn(x2.astype(np.complex128), axes=[1, 2])) < TOL[dt] * 20
+
+
+SMOOTH = [72, 96, 100, 120, 360, 720, 1000, 1440, 2187, 2401, 3125, 3000, 3600, 5000, 6144, 6300]
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("n", SMOOTH + [10000, 12288, 12600])
+def test_c2c_smooth_lengths(dt, n):
+    """2^a 3^b 5^c 7^d lengths run the mixed-radix shared-memory kernel (smooth.cu) instead of Bluestein: contiguous and strided
+    axes, forward and inverse, partial tiles, against numpy's pocketfft in double (the reference's backend, xrft.py:32-36)"""
+    from xrft_b200 import backend as B
+    if dt == np.float64 and n > 6399:
+        pytest.skip("beyond the float64 shared-memory capacity: Bluestein (covered by test_c2c_any_length)")
+    rng = np.random.default_rng(n)
+    tol = TOL[dt] * 10
+    rows = 70 if n < 200 else 5
+    x = cplx(rng, (rows, n), dt)
+    t = torch.from_numpy(x).cuda()
+    assert relerr(B.fftn(t, axes=[1]).cpu().numpy(), np.fft.fft(x.astype(np.complex128), axis=1)) < tol
+    assert relerr(B.ifftn(t, axes=[1]).cpu().numpy(), np.fft.ifft(x.astype(np.complex128), axis=1)) < tol
+    for b in (7, 37):
+        if n * b > 400000:
+            continue
+        xs = cplx(rng, (2, n, b), dt)
+        ts = torch.from_numpy(xs).cuda()
+        assert relerr(B.fftn(ts, axes=[1]).cpu().numpy(), np.fft.fft(xs.astype(np.complex128), axis=1)) < tol
+        assert relerr(B.ifftn(ts, axes=[1]).cpu().numpy(), np.fft.ifft(xs.astype(np.complex128), axis=1)) < tol
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_smooth_real_transforms_2d(dt):
+    """real 2-D transforms of a 360 x 720 grid (a 0.5-degree globe): rfftn / irfftn compose the mixed-radix passes"""
+    from xrft_b200 import backend as B
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((3, 360, 720)).astype(dt)
+    y = B.rfftn(torch.from_numpy(x).cuda(), axes=[1, 2]).cpu().numpy()
+    ref = np.fft.rfftn(x.astype(np.float64), axes=[1, 2])
+    assert relerr(y, ref) < TOL[dt] * 10
+    back = B.irfftn(torch.from_numpy(ref.astype(y.dtype)).cuda(), axes=[1, 2]).cpu().numpy()
+    assert relerr(back, x) < TOL[dt] * 10
 
 
 @pytest.mark.gpu

@@ -577,6 +577,7 @@ __global__ void __launch_bounds__(256) binned_sum_global_kernel(const T* __restr
 // ------------------------------------------------------------------------------------------------
 // arbitrary lengths (the reference's tests use 10, 15, 19, 20, 30, 40, 100, 1000 ...)
 //   N <= kSmallDft : direct O(N^2) DFT, one thread per sequence, twiddles in shared memory
+//   2^a 3^b 5^c 7^d: mixed-radix Stockham kernel in shared memory (smooth.cu), up to 12800 (float32) / 6400 (float64) points
 //   otherwise      : Bluestein chirp-z on top of the power-of-two passes (no cuFFT, no CPU fallback)
 // All operate on a [A][N][B] row-major view (FFT along the middle axis), in-place safe.
 // ------------------------------------------------------------------------------------------------
@@ -813,7 +814,7 @@ template <typename T> static bool fast_len(long n, bool contiguous) {
 }
 // workspace (bytes) one C2C pass of length n over an [A][n][B] view needs
 template <typename T> static size_t pass_workspace(long A, long n, long B) {
-    if (n <= 1 || fast_len<T>(n, B == 1) || n <= kSmallDft) return 0;
+    if (n <= 1 || fast_len<T>(n, B == 1) || n <= kSmallDft || smooth_len_ok<T>(n)) return 0;
     const size_t al = 256;
     if (ilog2_exact(n) > 0) return (((size_t)A * n * B * sizeof(cplx<T>)) + al) & ~(al - 1);   // four-step scratch
     const int lm = next_pow2_log(2 * n - 1);
@@ -892,6 +893,7 @@ static int c2c_pass(const cplx<T>* src, cplx<T>* dst, long A, long n, long B, in
         dft_small_kernel<T><<<(unsigned)((nseq + 127) / 128 > 4096 ? 4096 : (nseq + 127) / 128), 128, 0, st>>>(src, dst, (int)n, A, B, inverse ? 1 : 0, scale);
         return check_launch("dft_small_kernel");
     }
+    if (smooth_len_ok<T>(n)) return smooth_c2c<T>(src, dst, A, n, B, inverse, scale, st);   // 2^a 3^b 5^c 7^d: mixed-radix kernel
     const size_t need = pass_workspace<T>(A, n, B);
     if (!work || work_bytes < need) { set_error("fftn: workspace too small for length %ld (%zu < %zu)", n, work_bytes, need); return XRFTB_EWORKSPACE; }
     cplx<T>* w = reinterpret_cast<cplx<T>*>(work);
@@ -1398,8 +1400,9 @@ static int spectrum2d_crossz(const xrftb_spectrum2d_desc& q, int ly, int lx, cud
             io.zout = zf[f];
             io.ztma = 0;
             if (q.ny >= 512) {
+                const int ztma_on = option(OPT_ZTMA);
                 const int zbox = q.ny / 4 < 256 ? q.ny / 4 : 256;
-                if (encode_out_tmap(&io.ztmap, zf[f], nb * q.ny, q.nx, 2 * C, zbox)) { io.ztma = 1; io.zbox_rows = zbox; }
+                if (ztma_on && encode_out_tmap(&io.ztmap, zf[f], nb * q.ny, q.nx, 2 * C, zbox)) { io.ztma = 1; io.zbox_rows = zbox; }
             }
             {
                 ProfScope ps_(PROF_COLS, st);

@@ -66,6 +66,10 @@ template <typename T> int cols_r2c_pack(const ColsR2CPack<T>& io, int log2L, int
 // store) and the xrftb_fft2r hooks (row predicate / roll / ramps / crop); its in / out / B / inverse / scale are ignored
 template <typename T> int cols_c2c(const cplx<T>* in, cplx<T>* out, int log2L, long A, long B, int inverse, T scale,
                                    cudaStream_t st, const ColsC2C<T>* extra = nullptr);
+// smooth.cu: mixed-radix transform of the lengths 2^a 3^b 5^c 7^d that are not powers of two, along the middle axis of an
+// [A][n][B] view (in-place safe); smooth_len_ok = the length is covered (factors and shared-memory capacity)
+template <typename T> bool smooth_len_ok(long n);
+template <typename T> int smooth_c2c(const cplx<T>* src, cplx<T>* dst, long A, long n, long B, int inverse, T scale, cudaStream_t st);
 // one explicit instantiation per (T, MODE), spread over several translation units
 template <typename T, int MODE> int cols_fused_mode(const cplx<T>* in1, const cplx<T>* in2, int log2L, long ntiles_total, int ntile,
                                                     const EpilogueDesc& d, const CUtensorMap* tmap, cudaStream_t st);
