@@ -33,7 +33,11 @@ int cols_c2c(const cplx<T>* in, cplx<T>* out, int log2L, long A, long B, int inv
 }
 
 template <typename T>
-int cols_r2c_pack(const ColsR2CPack<T>& io, int log2L, int C, long ntiles, bool use_async, cudaStream_t st) {
+int cols_r2c_pack(const ColsR2CPack<T>& io_, int log2L, int C, long ntiles, bool use_async, cudaStream_t st) {
+    ColsR2CPack<T> io = io_;
+    if (io.tiles_per_item < 1 || (io.tiles_per_item & (io.tiles_per_item - 1))) { set_error("cols_r2c_pack: %d tiles per item (a power of two is required)", io.tiles_per_item); return -2; }
+    io.log_tpi = 0;
+    while ((1 << io.log_tpi) < io.tiles_per_item) ++io.log_tpi;
     if constexpr (sizeof(T) == 4) {
         if (use_async) {   // tensor-map fed variant (io.tmap / io.box_rows are set); float32, two packed columns per thread
             switch (log2L) {

@@ -745,7 +745,15 @@ rowsz_power_kernel(RowsZPower<T> io, const cplx<T>* __restrict__ tw, long nseq) 
     const long ngroups = (nseq + ROWS - 1) / ROWS;
     const int Ny = 1 << io.logNy;
     const int sy = io.shift_y ? Ny / 2 : 0, sx = io.shift_x ? Nx / 2 : 0;
-    for (long grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+    // (item, row) of this thread's sequence, advanced by the grid stride without a division per group
+    const long gstep = (long)gridDim.x * ROWS;
+    const long bstep = gstep / io.H;
+    const int kstep = (int)(gstep - bstep * io.H);
+    long seq = (long)blockIdx.x * ROWS + r;
+    long b = seq / io.H;
+    int ky = (int)(seq - b * io.H);
+    for (long grp = blockIdx.x; grp < ngroups; grp += gridDim.x, seq += gstep, b += bstep, ky += kstep) {
+        if (ky >= io.H) { ky -= io.H; ++b; }
         const long nxt = grp + gridDim.x;
         if (threadIdx.x < 2 * ROWS && nxt < ngroups) {   // next group's rows -> L2
             const long s2 = nxt * ROWS + (threadIdx.x >> 1);
@@ -756,10 +764,7 @@ rowsz_power_kernel(RowsZPower<T> io, const cplx<T>* __restrict__ tw, long nseq) 
                 prefetch_l2_bulk(io.z + ((b2 << io.logNy) + row) * (long)M, (unsigned)(M * sizeof(cplx<T>)));
             }
         }
-        const long seq = grp * ROWS + r;
         const bool act = seq < nseq;
-        const long b = act ? seq / io.H : 0;
-        const int ky = act ? (int)(seq - b * io.H) : 0;
         cplx<T> v[2][E];
         {
             const cplx<T>* pa = io.z + ((b << io.logNy) + ky) * (long)M + u;
@@ -796,21 +801,50 @@ rowsz_power_kernel(RowsZPower<T> io, const cplx<T>* __restrict__ tw, long nseq) 
             // rows 0 and Ny/2 are their own mirror image (rowm == rowd): their kx <= Nx/2 half is written and mirrored inside
             // the row, so the result is exactly symmetric like every other row pair
             const bool self = (ky == 0) || (2 * ky == Ny);
+            if (!self) {
+                // k = u + c with c = g NT + t Ns known at compile time and k < M, sx in {0, M}: the four destinations are
+                // base pointers plus immediate offsets (no index arithmetic per point).  Only k = 0 wraps in a mirrored row.
+                constexpr int NsL = 1 << G_::LOGNS_LAST;
+                T* pd0 = rowd + u + sx;                         // kx = k       at (k + sx) mod Nx
+                T* pd1 = rowd + u + ((M + sx) & (Nx - 1));      // kx = k + M   at (k + M + sx) mod Nx
+                T* pm0 = rowm + ((sx ? M : Nx) - u);            // mirror of kx = k      at (Nx - k + sx) mod Nx = pm0[-c]
+                T* pm1 = rowm + ((sx ? Nx : M) - u);            // mirror of kx = k + M  at (M - k + sx) mod Nx  = pm1[-c]
 #pragma unroll
-            for (int g = 0; g < G; ++g)
+                for (int g = 0; g < G; ++g)
 #pragma unroll
-                for (int t = 0; t < R; ++t) {
-                    const int k = final_index<LOG2M, LOGE>(u, g, t);
-                    const cplx<T> fa = v[0][g + t * G];
-                    const cplx<T> wb = cmul(v[1][g + t * G], smw[k]);
-                    const cplx<T> f0 = cadd(fa, wb), f1 = csub(fa, wb);
-                    const T p0 = (f0.x * f0.x + f0.y * f0.y) * io.scale;   // kx = k
-                    const T p1 = (f1.x * f1.x + f1.y * f1.y) * io.scale;   // kx = k + M
-                    rowd[(k + sx) & (Nx - 1)] = p0;
-                    if (!self || k > 0) rowm[(Nx - k + sx) & (Nx - 1)] = p0;
-                    if (!self || k == 0) rowd[(k + M + sx) & (Nx - 1)] = p1;
-                    if (!self) rowm[(M - k + sx) & (Nx - 1)] = p1;
-                }
+                    for (int t = 0; t < R; ++t) {
+                        const int c = g * NT + t * NsL;
+                        const cplx<T> fa = v[0][g + t * G];
+                        const cplx<T> wb = cmul(v[1][g + t * G], smw[u + c]);
+                        const cplx<T> f0 = cadd(fa, wb), f1 = csub(fa, wb);
+                        const T p0 = (f0.x * f0.x + f0.y * f0.y) * io.scale;
+                        const T p1 = (f1.x * f1.x + f1.y * f1.y) * io.scale;
+                        pd0[c] = p0;
+                        pd1[c] = p1;
+                        if (c == 0) {   // k = u: u = 0 is the one point whose mirror index wraps
+                            rowm[(Nx - u + sx) & (Nx - 1)] = p0;
+                            rowm[(M - u + sx) & (Nx - 1)] = p1;
+                        } else {
+                            pm0[-c] = p0;
+                            pm1[-c] = p1;
+                        }
+                    }
+            } else {
+#pragma unroll
+                for (int g = 0; g < G; ++g)
+#pragma unroll
+                    for (int t = 0; t < R; ++t) {
+                        const int k = final_index<LOG2M, LOGE>(u, g, t);
+                        const cplx<T> fa = v[0][g + t * G];
+                        const cplx<T> wb = cmul(v[1][g + t * G], smw[k]);
+                        const cplx<T> f0 = cadd(fa, wb), f1 = csub(fa, wb);
+                        const T p0 = (f0.x * f0.x + f0.y * f0.y) * io.scale;   // kx = k
+                        const T p1 = (f1.x * f1.x + f1.y * f1.y) * io.scale;   // kx = k + M
+                        rowd[(k + sx) & (Nx - 1)] = p0;
+                        if (k > 0) rowm[(Nx - k + sx) & (Nx - 1)] = p0;
+                        if (k == 0) rowd[(k + M + sx) & (Nx - 1)] = p1;
+                    }
+            }
         }
     }
 }
@@ -848,11 +882,16 @@ rowszx_kernel(RowsZCross<float> io, const float2* __restrict__ tw, long nseq) {
     const int sy = io.shift_y ? Ny / 2 : 0, sx = io.shift_x ? Nx / 2 : 0;
     const cplx<T>* zf = f ? io.z2 : io.z1;
     const cplx<T>* agf = f ? io.ag2 : io.ag1;
-    for (long grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
-        const long seq = grp * ROWS + r;
+    // (item, row) of this thread's sequence, advanced by the grid stride without a division per group
+    const long gstep = (long)gridDim.x * ROWS;
+    const long bstep = gstep / io.H;
+    const int kstep = (int)(gstep - bstep * io.H);
+    long seq = (long)blockIdx.x * ROWS + r;
+    long b = seq / io.H;
+    int ky = (int)(seq - b * io.H);
+    for (long grp = blockIdx.x; grp < ngroups; grp += gridDim.x, seq += gstep, b += bstep, ky += kstep) {
+        if (ky >= io.H) { ky -= io.H; ++b; }
         const bool act = seq < nseq;
-        const long b = act ? seq / io.H : 0;
-        const int ky = act ? (int)(seq - b * io.H) : 0;
         cplx<T> v[2][E];
         {
             const cplx<T>* pa = zf + ((b << io.logNy) + ky) * (long)M + u;
@@ -895,22 +934,49 @@ rowszx_kernel(RowsZCross<float> io, const float2* __restrict__ tw, long nseq) {
             const long rd = ((b << io.logNy) + ((ky + sy) & (Ny - 1))) * (long)Nx;
             const long rm = ((b << io.logNy) + ((Ny - ky + sy) & (Ny - 1))) * (long)Nx;
             const bool self = (ky == 0) || (2 * ky == Ny);   // the row mirrors into itself: kx <= Nx/2 computed, the rest mirrored
+            constexpr int J = Nx / (2 * NT);
+            if (!self) {
+                // kx = tt + j 2NT with tt < 2NT and sx in {0, M}: kx < M exactly for j < J/2, so every destination is a base
+                // pointer plus an immediate offset; only kx = 0 and kx = M can wrap in the mirrored row (index 0)
+                const long dlo = rd + tt + sx, dhi = rd + tt - sx;                       // (kx + sx) mod Nx for kx < M / kx >= M
+                const long mlo = rm + ((sx ? M : Nx) - tt), mhi = rm + ((Nx + sx) - tt);   // (Nx - kx + sx) mod Nx likewise
+                const long m0 = rm + ((Nx - tt + sx) & (Nx - 1)), mM = rm + ((Nx - (tt + M) + sx) & (Nx - 1));
 #pragma unroll
-            for (int j = 0; j < Nx / (2 * NT); ++j) {
-                const int kx = tt + j * (2 * NT);
-                const cplx<T> c = cscale(cmulc(s1[kx], s2[kx]), io.scale);
-                const int pd = (kx + sx) & (Nx - 1), pm = (Nx - kx + sx) & (Nx - 1);
-                const bool wd = !self || 2 * kx <= Nx, wm = !self || (kx > 0 && 2 * kx < Nx);
-                if constexpr (MODE == EPI_PHASE || MODE == EPI_CROSS_AND_PHASE) {
-                    T* o = reinterpret_cast<T*>(MODE == EPI_PHASE ? io.out : io.out2);
-                    const T ph = xatan2(c.y, c.x);
-                    if (wd) o[rd + pd] = ph;
-                    if (wm) o[rm + pm] = -ph;
+                for (int j = 0; j < J; ++j) {
+                    const int off = j * (2 * NT);
+                    const cplx<T> c = cscale(cmulc(s1[tt + off], s2[tt + off]), io.scale);
+                    const long pd = (j < J / 2 ? dlo : dhi) + off;
+                    const long pm = j == 0 ? m0 : j == J / 2 ? mM : (j < J / 2 ? mlo : mhi) - off;
+                    if constexpr (MODE == EPI_PHASE || MODE == EPI_CROSS_AND_PHASE) {
+                        T* o = reinterpret_cast<T*>(MODE == EPI_PHASE ? io.out : io.out2);
+                        const T ph = xatan2(c.y, c.x);
+                        o[pd] = ph;
+                        o[pm] = -ph;
+                    }
+                    if constexpr (MODE == EPI_CROSS || MODE == EPI_CROSS_AND_PHASE) {
+                        cplx<T>* o = reinterpret_cast<cplx<T>*>(io.out);
+                        o[pd] = c;
+                        o[pm] = cconj(c);
+                    }
                 }
-                if constexpr (MODE == EPI_CROSS || MODE == EPI_CROSS_AND_PHASE) {
-                    cplx<T>* o = reinterpret_cast<cplx<T>*>(io.out);
-                    if (wd) o[rd + pd] = c;
-                    if (wm) o[rm + pm] = cconj(c);
+            } else {
+#pragma unroll
+                for (int j = 0; j < J; ++j) {
+                    const int kx = tt + j * (2 * NT);
+                    const cplx<T> c = cscale(cmulc(s1[kx], s2[kx]), io.scale);
+                    const int pd = (kx + sx) & (Nx - 1), pm = (Nx - kx + sx) & (Nx - 1);
+                    const bool wd = 2 * kx <= Nx, wm = kx > 0 && 2 * kx < Nx;
+                    if constexpr (MODE == EPI_PHASE || MODE == EPI_CROSS_AND_PHASE) {
+                        T* o = reinterpret_cast<T*>(MODE == EPI_PHASE ? io.out : io.out2);
+                        const T ph = xatan2(c.y, c.x);
+                        if (wd) o[rd + pd] = ph;
+                        if (wm) o[rm + pm] = -ph;
+                    }
+                    if constexpr (MODE == EPI_CROSS || MODE == EPI_CROSS_AND_PHASE) {
+                        cplx<T>* o = reinterpret_cast<cplx<T>*>(io.out);
+                        if (wd) o[rd + pd] = c;
+                        if (wm) o[rm + pm] = cconj(c);
+                    }
                 }
             }
         }
@@ -1246,7 +1312,7 @@ template <typename T> struct ColsR2CPack {
     static constexpr int kExtraHalf = 1152;
     const T* in;            // [batch][Ny][Nx] real
     int Nx;                 // row length (elements)
-    int tiles_per_item;     // Nx / (2 C)
+    int tiles_per_item;     // Nx / (2 C): a power of two = 1 << log_tpi (tiles are split into (item, column block) by shifts)
     int detrend;            // 0 none | 1 constant | 2 linear
     const double* moments;  // global-plane variant: [batch][4] : S, -, Sy, Sx (moments_kernel)
     const T* wy; const T* wx;
@@ -1269,6 +1335,7 @@ template <typename T> struct ColsR2CPack {
     int ztma;
     int zbox_rows;          // rows per box of ztmap (divides Ny / 4)
     alignas(64) CUtensorMap ztmap;
+    int log_tpi;            // log2(tiles_per_item), set by cols_r2c_pack
     static constexpr bool kSplitEpilogue = true;
     template <int LOG2L, int LOGE, int C, int NTHR>
     __device__ __forceinline__ void store_z_tma(long tile, int u, int cg, cplx<T> (&v)[2][1 << LOGE], cplx<T>* smX, const float* extra) const {
@@ -1276,8 +1343,8 @@ template <typename T> struct ColsR2CPack {
         // the tile leaves in NPIECE pieces of PR rows through two alternating halves of the buffer: piece p is staged while
         // the stores of piece p-1 are still reading the other half
         constexpr int R = 1 << G_::LOGR_LAST, G = G_::E / R, Ny = 1 << LOG2L, NPIECE = 4, PR = Ny / NPIECE;
-        const long b = tile / tiles_per_item;
-        const int t0 = (int)(tile - b * tiles_per_item);
+        const long b = tile >> log_tpi;
+        const int t0 = (int)(tile & (long)(tiles_per_item - 1));
         write_colstats<C, NTHR>(b, t0 * (2 * C), extra);
 #pragma unroll
         for (int pc = 0; pc < NPIECE; ++pc) {
@@ -1315,8 +1382,8 @@ template <typename T> struct ColsR2CPack {
         float4 w = make_float4(1.f, 1.f, 1.f, 1.f);
         if constexpr (sizeof(T) == 4) {
             if (zout != nullptr && wx != nullptr) {
-                const long b = tile / tiles_per_item;
-                const int x0 = (int)(tile - b * tiles_per_item) * (2 * C) + cg * 4;
+                const long b = tile >> log_tpi;
+                const int x0 = (int)(tile & (long)(tiles_per_item - 1)) * (2 * C) + cg * 4;
                 w = __ldg(reinterpret_cast<const float4*>(wx + x0));
             }
         }
@@ -1326,8 +1393,8 @@ template <typename T> struct ColsR2CPack {
     __device__ __forceinline__ void store_z(long tile, int u, int cg, cplx<T> (&v)[2][1 << LOGE], const float* extra) const {
         using G_ = Geometry<LOG2L, LOGE>;
         constexpr int R = 1 << G_::LOGR_LAST, G = G_::E / R;
-        const long b = tile / tiles_per_item;
-        const int t0 = (int)(tile - b * tiles_per_item);
+        const long b = tile >> log_tpi;
+        const int t0 = (int)(tile & (long)(tiles_per_item - 1));
         write_colstats<C, NTHR>(b, t0 * (2 * C), extra);
         const int M = Nx >> 1;
         cplx<T>* ob = zout + (b << LOG2L) * (long)M + t0 * C + cg * 2;
@@ -1343,8 +1410,8 @@ template <typename T> struct ColsR2CPack {
     }
     template <int LOG2L, int C> __device__ __forceinline__ void issue_load(long tile, cplx<T>* smL, uint64_t* bar) const {
         constexpr int Ny = 1 << LOG2L;
-        const long b = tile / tiles_per_item;
-        const int x0 = (int)(tile - b * tiles_per_item) * (2 * C);
+        const long b = tile >> log_tpi;
+        const int x0 = (int)(tile & (long)(tiles_per_item - 1)) * (2 * C);
         const int row0 = (int)(b << LOG2L);
         mbar_expect_tx(bar, (unsigned)(Ny * C * sizeof(cplx<T>)));
         for (int r0 = 0; r0 < Ny; r0 += box_rows) tensor_load_2d_g2s(smL + r0 * C, &tmap, x0, row0 + r0, bar);
@@ -1363,15 +1430,21 @@ template <typename T> struct ColsR2CPack {
     // window factors of the rows this thread owns, fetched ahead of use
     template <int LOG2L, int LOGE> __device__ __forceinline__ void fix_fetch(long, int u, cplx<T> (&a)[1 << LOGE]) const {
         constexpr int NT = Geometry<LOG2L, LOGE>::NT;
+        if (wy != nullptr) {
+            const T* p = wy + u;
 #pragma unroll
-        for (int q = 0; q < (1 << LOGE); ++q) a[q].x = wy != nullptr ? __ldg(wy + u + q * NT) : (T)1;
+            for (int q = 0; q < (1 << LOGE); ++q) a[q].x = __ldg(p + q * NT);
+        } else {
+#pragma unroll
+            for (int q = 0; q < (1 << LOGE); ++q) a[q].x = (T)1;
+        }
     }
 
     template <int LOG2L, int LOGE, int C, int V>
     __device__ __forceinline__ void load(long tile, int u, int cg, cplx<T> (&v)[V][1 << LOGE], int) const {
         constexpr int NT = Geometry<LOG2L, LOGE>::NT;
-        const long b = tile / tiles_per_item;
-        const int x0 = (int)(tile - b * tiles_per_item) * (2 * C) + cg * (2 * V);
+        const long b = tile >> log_tpi;
+        const int x0 = (int)(tile & (long)(tiles_per_item - 1)) * (2 * C) + cg * (2 * V);
         const T* p = in + ((b << LOG2L) + u) * (long)Nx + x0;
         const long qstep = (long)NT * Nx;
 #pragma unroll
@@ -1392,8 +1465,8 @@ template <typename T> struct ColsR2CPack {
     __device__ __forceinline__ void fix_apply(long tile, int u, int cg, const cplx<T> (&a)[1 << LOGE], cplx<T> (&v)[V][1 << LOGE], float* extra,
                                               const cplx<T>* landed = nullptr, float4 wc4 = make_float4(1.f, 1.f, 1.f, 1.f)) const {
         constexpr int NT = Geometry<LOG2L, LOGE>::NT, Ny = 1 << LOG2L, CG = C / V;
-        const long b = tile / tiles_per_item;
-        const int x0 = (int)(tile - b * tiles_per_item) * (2 * C) + cg * (2 * V);
+        const long b = tile >> log_tpi;
+        const int x0 = (int)(tile & (long)(tiles_per_item - 1)) * (2 * C) + cg * (2 * V);
         if (colstats != nullptr) {
             if constexpr (sizeof(T) == 4 && V == 2) {
                 if (detrend) {
@@ -1414,21 +1487,21 @@ template <typename T> struct ColsR2CPack {
                     const float wc[4] = {hf * wc4.x, hf * wc4.y, hf * wc4.z, hf * wc4.w};
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
+                        // same exact-line construction as the row-line prologue of rows2_kernel, without a branch: outside
+                        // (1e-30, 1e30) both the quantum Q and its reciprocal are zero, i.e. A0 = B = 0
                         const float m = fmaxf(fabsf(x0v[k]), fabsf(x1v[k]));
-                        A0[k] = 0.f; B[k] = 0.f;
-                        if (m > 1e-30f && m < 1e30f) {   // same exact-line construction as the row-line prologue of rows2_kernel
-                            const int p2b = __float_as_int(m) & 0x7f800000;
-                            const float p2 = __int_as_float(p2b);
-                            // 2^21 / p2 for a power of two p2 = 2^(e-127): the exponent field 127 + 21 - (e - 127), no division
-                            const float Q = p2 * 4.76837158203125e-07f, iQ = __int_as_float((275 << 23) - p2b);
-                            A0[k] = rintf(x0v[k] * iQ) * Q;
-                            B[k] = rintf((x1v[k] - x0v[k]) * (1.0f / (float)(Ny > 1 ? Ny - 1 : 1)) * iQ) * Q;
-                        }
+                        const bool ok = m > 1e-30f && m < 1e30f;
+                        const int p2b = __float_as_int(m) & 0x7f800000;
+                        // 2^21 / p2 for a power of two p2 = 2^(e-127): the exponent field 127 + 21 - (e - 127), no division
+                        const float Q = ok ? __int_as_float(p2b) * 4.76837158203125e-07f : 0.f;
+                        const float iQ = ok ? __int_as_float((275 << 23) - p2b) : 0.f;
+                        A0[k] = rintf(x0v[k] * iQ) * Q;
+                        B[k] = rintf((x1v[k] - x0v[k]) * (1.0f / (float)(Ny > 1 ? Ny - 1 : 1)) * iQ) * Q;
                     }
                     const float if0 = (float)u;
 #pragma unroll
                     for (int q = 0; q < (1 << LOGE); ++q) {
-                        const float fi = if0 + (float)(q * NT);
+                        const float fi = __fadd_rn(if0, (float)(q * NT));   // (one FADD; not an integer add and a conversion)
                         const float wrow = a[q].x;
                         float r[4] = {v[0][q].x, v[0][q].y, v[1][q].x, v[1][q].y};
 #pragma unroll
@@ -1524,8 +1597,8 @@ template <typename T> struct ColsR2CPack {
     __device__ __forceinline__ void store_split(long tile, int u, int cg, cplx<T> (&v)[2][1 << LOGE], cplx<T>* smX, const float* extra) const {
         using G_ = Geometry<LOG2L, LOGE>;
         constexpr int R = 1 << G_::LOGR_LAST, G = G_::E / R, Ny = 1 << LOG2L, Q = Ny / 4, H = Ny / 2 + 1;
-        const long b = tile / tiles_per_item;
-        const int x0 = (int)(tile - b * tiles_per_item) * (2 * C);
+        const long b = tile >> log_tpi;
+        const int x0 = (int)(tile & (long)(tiles_per_item - 1)) * (2 * C);
         write_colstats<C, NTHR>(b, x0, extra);
         cplx<T>* ob = out + (b * H) * (long)Nx + x0;
         constexpr bool FIXED_C = (NTHR % C == 0);
@@ -1599,8 +1672,8 @@ template <typename T> struct ColsR2CPack {
     __device__ __forceinline__ void store_b(long tile, cplx<T>* smem) const {
         using G_ = Geometry<LOG2L, LOGE>;
         constexpr int Ny = 1 << LOG2L, H = Ny / 2 + 1;
-        const long b = tile / tiles_per_item;
-        const int x0 = (int)(tile - b * tiles_per_item) * (2 * C);
+        const long b = tile >> log_tpi;
+        const int x0 = (int)(tile & (long)(tiles_per_item - 1)) * (2 * C);
         write_colstats<C, NTHR>(b, x0, reinterpret_cast<const float*>(smem + G_::LPAD * C));
         cplx<T>* ob = out + (b * H) * (long)Nx + x0;
         constexpr int ITEMS = H * C;

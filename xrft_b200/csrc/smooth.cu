@@ -44,6 +44,7 @@ bool factorize(long n, SmoothPlan* p, bool wide) {   // wide (float32): radix 16
     return n == 1;
 }
 
+constexpr int kSmoothMaxDynSmem = 224 * 1024;   // dynamic part; the kernel also has a few hundred bytes of static shared memory
 template <typename T> struct SmoothCfg;
 // points per buffer: the cap (two buffers within the 227 KB of one CTA) and the tile size aimed at (several CTAs per SM)
 template <> struct SmoothCfg<float> { static constexpr int kMaxPoints = 12800, kTilePoints = 4096, kColsWide = 16; };
@@ -305,7 +306,7 @@ int smooth_c2c(const cplx<T>* src, cplx<T>* dst, long A, long n, long B, int inv
     const long ntiles = contig ? (A + C - 1) / C : A * tiles_per_item;
     const size_t tile_elems = contig ? (size_t)C * (n + 1) : (size_t)n * C;
     const size_t smem = 2 * tile_elems * sizeof(cplx<T>);
-    if (smem > 227 * 1024) { set_error("smooth_c2c: tile of length %ld does not fit shared memory", n); return XRFTB_EUNSUPPORTED; }
+    if (smem > (size_t)kSmoothMaxDynSmem) { set_error("smooth_c2c: tile of length %ld does not fit shared memory", n); return XRFTB_EUNSUPPORTED; }
     const cplx<T>* tw = smooth_table<T>(n);
     if (!tw) return XRFTB_ECUDA;
     auto kern = smooth_c2c_kernel<T>;
@@ -315,7 +316,7 @@ int smooth_c2c(const cplx<T>* src, cplx<T>* dst, long A, long n, long B, int inv
         std::lock_guard<std::mutex> lk(g_smooth_mu);
         bool& done = g_smooth_attr[sizeof(T) == 4 ? 0 : 1][dev & 63];
         if (!done) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmoothMaxDynSmem);
             if (e != cudaSuccess) { set_error("smooth_c2c: %s", cudaGetErrorString(e)); return XRFTB_ECUDA; }
             done = true;
         }
