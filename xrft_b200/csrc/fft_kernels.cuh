@@ -27,6 +27,30 @@ constexpr int ilog2c(int n) { return n <= 1 ? 0 : 1 + ilog2c(n / 2); }
 enum : int { EPI_COMPLEX = 0, EPI_POWER = 1, EPI_CROSS = 2, EPI_PHASE = 3, EPI_BINS_POWER = 4, EPI_BINS_CROSS = 5,
              EPI_CROSS_AND_PHASE = 6 /* internal: CROSS with the optional second output (desc.out2) */ };
 
+// read-once rows of pass 2 (packed column spectra): optionally loaded without allocating in L1, so that the tables every row
+// of an item re-reads (completion vector, twiddles) stay there
+#ifndef XRFTB_Z_LDNA
+#define XRFTB_Z_LDNA 0
+#endif
+__device__ __forceinline__ float2 ld_once(const float2* p) {
+#if XRFTB_Z_LDNA
+    float2 r;
+    asm volatile("ld.global.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+    return r;
+#else
+    return *p;
+#endif
+}
+__device__ __forceinline__ double2 ld_once(const double2* p) {
+#if XRFTB_Z_LDNA
+    double2 r;
+    asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    return r;
+#else
+    return *p;
+#endif
+}
+
 __device__ __forceinline__ float xatan2(float y, float x) { return atan2f(y, x); }
 __device__ __forceinline__ double xatan2(double y, double x) { return atan2(y, x); }
 
@@ -771,7 +795,7 @@ rowsz_power_kernel(RowsZPower<T> io, const cplx<T>* __restrict__ tw, long nseq) 
             const cplx<T>* pb = io.z + ((b << io.logNy) + ((Ny - ky) & (Ny - 1))) * (long)M + u;
             cplx<T> za[E], zb[E];
 #pragma unroll
-            for (int q = 0; q < E; ++q) { za[q] = act ? pa[q * NT] : mk<T>(0, 0); zb[q] = act ? pb[q * NT] : mk<T>(0, 0); }
+            for (int q = 0; q < E; ++q) { za[q] = act ? ld_once(pa + q * NT) : mk<T>(0, 0); zb[q] = act ? ld_once(pb + q * NT) : mk<T>(0, 0); }
 #pragma unroll
             for (int q = 0; q < E; ++q) {
                 v[0][q] = mk<T>(za[q].x + zb[q].x, za[q].y - zb[q].y);
@@ -891,6 +915,16 @@ rowszx_kernel(RowsZCross<float> io, const float2* __restrict__ tw, long nseq) {
     int ky = (int)(seq - b * io.H);
     for (long grp = blockIdx.x; grp < ngroups; grp += gridDim.x, seq += gstep, b += bstep, ky += kstep) {
         if (ky >= io.H) { ky -= io.H; ++b; }
+        const long nxt = grp + gridDim.x;
+        if (threadIdx.x < 4 * ROWS && nxt < ngroups) {   // next group's rows (ky and Ny - ky of both fields) -> L2
+            const long s2 = nxt * ROWS + (threadIdx.x >> 2);
+            if (s2 < nseq) {
+                const long b2 = s2 / io.H;
+                const int k2 = (int)(s2 - b2 * io.H);
+                const int row = (threadIdx.x & 1) ? ((Ny - k2) & (Ny - 1)) : k2;
+                prefetch_l2_bulk(((threadIdx.x & 2) ? io.z2 : io.z1) + ((b2 << io.logNy) + row) * (long)M, (unsigned)(M * sizeof(cplx<T>)));
+            }
+        }
         const bool act = seq < nseq;
         cplx<T> v[2][E];
         {
@@ -898,7 +932,7 @@ rowszx_kernel(RowsZCross<float> io, const float2* __restrict__ tw, long nseq) {
             const cplx<T>* pb = zf + ((b << io.logNy) + ((Ny - ky) & (Ny - 1))) * (long)M + u;
             cplx<T> za[E], zb[E];
 #pragma unroll
-            for (int q = 0; q < E; ++q) { za[q] = act ? pa[q * NT] : mk<T>(0, 0); zb[q] = act ? pb[q * NT] : mk<T>(0, 0); }
+            for (int q = 0; q < E; ++q) { za[q] = act ? ld_once(pa + q * NT) : mk<T>(0, 0); zb[q] = act ? ld_once(pb + q * NT) : mk<T>(0, 0); }
 #pragma unroll
             for (int q = 0; q < E; ++q) {
                 v[0][q] = mk<T>(za[q].x + zb[q].x, za[q].y - zb[q].y);
@@ -1623,6 +1657,33 @@ template <typename T> struct ColsR2CPack {
             __syncthreads();
             const int k0 = round == 0 ? 0 : Q;
             const int nk = round == 0 ? Q : Q + 1;
+            if constexpr (FIXED_C && Q % (NTHR / C) == 0) {
+                // Affine form of the loop below: a thread keeps its packed column c and walks the rows kr0 + it STEP.  In both
+                // rounds Z[k] sits in slot kr and its partner Z[Ny-k] in slot 2Q - kr (k = 0 pairs with itself), so every
+                // shared-memory access is a base pointer plus an immediate offset and the output pointer advances by a constant.
+                constexpr int STEP = NTHR / C, SWEEPS = Q / STEP;
+                const int kr0 = threadIdx.x / C;
+                const cplx<T>* pa = smX + kr0 * C + c;
+                const cplx<T>* pb = smX + (2 * Q - kr0) * C + c;
+                cplx<T>* po = ob + (long)(k0 + kr0) * Nx + 2 * c;
+                const long ostep = (long)STEP * Nx;
+#pragma unroll
+                for (int it = 0; it <= SWEEPS; ++it) {
+                    if (it < SWEEPS || (round == 1 && kr0 == 0)) {   // the extra sweep is row k = 2Q (the Nyquist row), round 1 only
+                        const cplx<T> za = pa[it * (STEP * C)];
+                        cplx<T> zb = pb[-(it * (STEP * C))];
+                        if (round == 0 && it == 0 && kr0 == 0) zb = za;
+                        const cplx<T> A = mk<T>(ha * (za.x + zb.x), ha * (za.y - zb.y));
+                        const cplx<T> B = mk<T>(hb * (za.y + zb.y), hb * (zb.x - za.x));
+                        cplx<T>* q = po + it * ostep;
+                        if constexpr (sizeof(T) == 4) {
+                            *reinterpret_cast<float4*>(q) = make_float4(A.x, A.y, B.x, B.y);
+                        } else {
+                            q[0] = A; q[1] = B;
+                        }
+                    }
+                }
+            } else
 #pragma unroll 4
             for (int idx = threadIdx.x; idx < nk * C; idx += NTHR) {
                 const int kr = idx / C;
@@ -2263,11 +2324,16 @@ cols_bins_kernel(const __grid_constant__ ColsFused<float, EPI_BINS_POWER> io, co
 // Radial bins summed on chip.  Shared pieces of the static cell-to-bin machinery (rows_bins_kernel, rowszx_bins_kernel):
 // NTHR threads own 16 cells each.
 // Counting sort of the CTA's cells by key (once per launch): key[i] in [0, nseg) or 0xFFFF (masked).  On return pos[i] is the
-// cell's slot in the key-ordered staging array, id[] are the keys of THIS thread's 16 consecutive slots and cont_in / cont_out
+// cell's slot in the key-ordered staging array, id holds the keys of THIS thread's 16 consecutive slots and cont_in / cont_out
 // tell whether the run of equal keys at its first / last slot continues in the neighbouring lane of the warp.
+// sixteen 16-bit values in eight registers (the slot and key tables of a thread live across the whole tile loop)
+struct Packed16 {
+    unsigned w[8];
+    __device__ __forceinline__ unsigned get(int i) const { return (w[i >> 1] >> (16 * (i & 1))) & 0xFFFFu; }
+};
 template <int NTHR>
 __device__ __forceinline__ void bins_assign_slots(const unsigned short (&key)[16], int nseg, int* cnt, unsigned short* binid, int* scan_part,
-                                                  unsigned short (&pos)[16], unsigned short (&id)[16], bool& cont_in, bool& cont_out) {
+                                                  Packed16& pos, Packed16& id, bool& cont_in, bool& cont_out) {
     constexpr int NCELL = NTHR * 16;
     const int lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < nseg; i += NTHR) cnt[i] = 0;
@@ -2300,6 +2366,8 @@ __device__ __forceinline__ void bins_assign_slots(const unsigned short (&key)[16
     // the cells of a warp that share a key take consecutive slots (neighbouring cells mostly share the bin): the per-tile
     // scatter into the staging array is then nearly free of bank conflicts
 #pragma unroll
+    for (int i = 0; i < 8; ++i) pos.w[i] = 0u;
+#pragma unroll
     for (int i = 0; i < 16; ++i) {
         const unsigned k = key[i];
         const unsigned grp = __match_any_sync(0xffffffffu, k);
@@ -2307,27 +2375,26 @@ __device__ __forceinline__ void bins_assign_slots(const unsigned short (&key)[16
         int base = 0;
         if (lane == leader && k != 0xFFFFu) base = atomicAdd(cnt + k, __popc(grp));
         base = __shfl_sync(0xffffffffu, base, leader);
-        pos[i] = k == 0xFFFFu ? (unsigned short)0xFFFFu : (unsigned short)(base + __popc(grp & ((1u << lane) - 1u)));
+        const unsigned p = k == 0xFFFFu ? 0xFFFFu : (unsigned)(base + __popc(grp & ((1u << lane) - 1u))) & 0xFFFFu;
+        pos.w[i >> 1] |= p << (16 * (i & 1));
     }
     __syncthreads();
     {
         const uint4* pid = reinterpret_cast<const uint4*>(binid + threadIdx.x * 16);
         const uint4 a = pid[0], b = pid[1];
-        const unsigned w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-        for (int i = 0; i < 16; ++i) id[i] = (unsigned short)((w[i >> 1] >> (16 * (i & 1))) & 0xFFFFu);
+        id.w[0] = a.x; id.w[1] = a.y; id.w[2] = a.z; id.w[3] = a.w; id.w[4] = b.x; id.w[5] = b.y; id.w[6] = b.z; id.w[7] = b.w;
     }
-    const unsigned prev_last = __shfl_up_sync(0xffffffffu, (unsigned)id[15], 1);
-    cont_in = lane > 0 && prev_last == id[0];
-    const unsigned next_first = __shfl_down_sync(0xffffffffu, (unsigned)id[0], 1);
-    cont_out = lane < 31 && next_first == id[15];
+    const unsigned prev_last = __shfl_up_sync(0xffffffffu, id.get(15), 1);
+    cont_in = lane > 0 && prev_last == id.get(0);
+    const unsigned next_first = __shfl_down_sync(0xffffffffu, id.get(0), 1);
+    cont_out = lane < 31 && next_first == id.get(15);
 }
 // Sums of the runs of equal keys in the key-ordered staging array: every thread adds up its own 16 consecutive slots
 // (128-bit loads, perfectly balanced); runs that span lanes are completed by a warp-wide segmented scan of the partial sums
 // still open at the end of each lane; emit(key, sum) is called once per run and warp (a run that crosses a warp boundary is
 // emitted in two parts).
 template <class Emit>
-__device__ __forceinline__ void bins_segmented_sum(const float* slots, const unsigned short (&id)[16], bool cont_in, bool cont_out, Emit&& emit) {
+__device__ __forceinline__ void bins_segmented_sum(const float* slots, const Packed16& id, bool cont_in, bool cont_out, Emit&& emit) {
     const int lane = threadIdx.x & 31;
     float x[16];
     const float4* pv = reinterpret_cast<const float4*>(slots);
@@ -2337,8 +2404,8 @@ __device__ __forceinline__ void bins_segmented_sum(const float* slots, const uns
     bool split = false;     // a run boundary inside these slots
 #pragma unroll
     for (int i = 1; i < 16; ++i) {
-        if (id[i] != id[i - 1]) {
-            if (!split) { head = acc; split = true; } else emit((unsigned)id[i - 1], acc);
+        if (id.get(i) != id.get(i - 1)) {
+            if (!split) { head = acc; split = true; } else emit(id.get(i - 1), acc);
             acc = x[i];
         } else {
             acc += x[i];
@@ -2353,8 +2420,8 @@ __device__ __forceinline__ void bins_segmented_sum(const float* slots, const uns
         if (lane >= off && !flag) { open += y; flag = fy; }
     }
     const float before = __shfl_up_sync(0xffffffffu, open, 1);   // sum of the run that reaches this lane's first slot
-    if (split) emit((unsigned)id[0], head + (cont_in ? before : 0.f));
-    if (!cont_out) emit((unsigned)id[15], open);
+    if (split) emit(id.get(0), head + (cont_in ? before : 0.f));
+    if (!cont_out) emit(id.get(15), open);
 }
 
 // =============================================================================================
@@ -2409,7 +2476,8 @@ rows_bins_kernel(RowsBins io, const float2* __restrict__ tw) {
     const int Ny = 1 << io.base.logNy;
     const int sy = io.base.shift_y ? Ny / 2 : 0, sx = io.base.shift_x ? Nx / 2 : 0;
     // ---- once per launch: bins of this thread's cells, counting sort of the CTA's cells by (slot, bin)
-    unsigned short key[E], pos[E], id[E];
+    unsigned short key[E];
+    Packed16 pos, id;
     bool cont_in, cont_out;
     {
         const int* lrow = io.lut + (long)((ky + sy) & (Ny - 1)) * Nx;
@@ -2433,26 +2501,42 @@ rows_bins_kernel(RowsBins io, const float2* __restrict__ tw) {
         act = tl < tiles_total && plane < io.nplanes;
         return plane * io.base.H + ky;
     };
-    cplx<T> raw[E];
-    {
-        bool act; const long sq = seq_of(tile, act);
+    // The row index ky of a thread is the same for every tile, so the completion factors W(ky), J(ky) of the column-line detrend
+    // are loaded once; the per-plane completion vector ag travels one tile ahead together with the row itself.
+    const bool fix = io.base.ag != nullptr;
+    cplx<T> Wk = mk<T>(0, 0), Jk = mk<T>(0, 0);
+    if (fix) { Wk = __ldg(io.base.wj + 2 * ky); Jk = __ldg(io.base.wj + 2 * ky + 1); }
+    cplx<T> raw[E], agr[E];
+    auto fetch_tile = [&](long tl) {
+        bool act; const long sq = seq_of(tl, act);
         io.base.template fetch<LOG2L, LOGE>(sq, act, u, raw);
-    }
-    for (; tile < tiles_total; tile += tstep) {
-        bool act; const long sq = seq_of(tile, act);
-        cplx<T> v[1][E];
-        io.base.template prologue<LOG2L, LOGE>(sq, act, u, raw, v[0]);
-        block_fft<T, LOG2L, LOGE, 1, 1>(v, u, sm, 0, tw);
-        {   // the next tile's rows travel while this one is binned
-            bool actn; const long sqn = seq_of(tile + tstep, actn);
-            io.base.template fetch<LOG2L, LOGE>(sqn, actn, u, raw);
+        if (fix) {
+            const long plane = per_slot ? tl * SEQ + s : tl;
+            const cplx<T>* pa = io.base.ag + (plane << LOG2L) + u;
+#pragma unroll
+            for (int q = 0; q < E; ++q) { agr[q] = mk<T>(0, 0); if (act) agr[q] = __ldg(pa + q * NT); }
         }
+    };
+    fetch_tile(tile);
+    for (; tile < tiles_total; tile += tstep) {
+        cplx<T> v[1][E];
+        if (fix) {
+#pragma unroll
+            for (int q = 0; q < E; ++q)
+                v[0][q] = mk<T>(raw[q].x + agr[q].x * Wk.x + agr[q].y * Jk.x, raw[q].y + agr[q].x * Wk.y + agr[q].y * Jk.y);
+        } else {
+#pragma unroll
+            for (int q = 0; q < E; ++q) v[0][q] = raw[q];
+        }
+        block_fft<T, LOG2L, LOGE, 1, 1>(v, u, sm, 0, tw);
         __syncthreads();   // every gather of the last exchange is done: the buffer becomes the staging array
 #pragma unroll
         for (int i = 0; i < E; ++i) {
             const cplx<T> f = v[0][i];
-            if (pos[i] != 0xFFFFu) stage[pos[i]] = (f.x * f.x + f.y * f.y) * mult;
+            const unsigned p = pos.get(i);
+            if (p != 0xFFFFu) stage[p] = (f.x * f.x + f.y * f.y) * mult;
         }
+        fetch_tile(tile + tstep);   // the next tile's rows and completion vector travel while this one is binned (v is dead here)
         __syncthreads();
         bins_segmented_sum(stage + threadIdx.x * E, id, cont_in, cont_out, [&](unsigned k, float val) {
             if (k == 0xFFFFu) return;
@@ -2509,7 +2593,8 @@ rowszx_bins_kernel(RowsZCrossBins io, const float2* __restrict__ tw) {
     const bool self = (ky == 0) || (2 * ky == Ny);
     // only tiles with a self-mirrored row have imaginary parts to add up (uniform per CTA)
     const bool has_im = per_slot ? (io.ky0 == 0 || 2 * io.ky0 == Ny) : (io.ky0 == 0 && g0 == 0) || (2 * (io.ky0 + g0 * ROWS) <= Ny && 2 * (io.ky0 + g0 * ROWS + ROWS - 1) >= Ny);
-    unsigned short key[16], pos[16], id[16];
+    unsigned short key[16];
+    Packed16 pos, id;
     bool cont_in, cont_out;
     {
         const int* lrow = io.lut + (long)((ky + sy) & (Ny - 1)) * Nx;
@@ -2536,7 +2621,7 @@ rowszx_bins_kernel(RowsZCrossBins io, const float2* __restrict__ tw) {
             const cplx<T>* pb = zf + ((bb << io.base.logNy) + ((Ny - ky) & (Ny - 1))) * (long)M + u;
             cplx<T> za[E], zb[E];
 #pragma unroll
-            for (int q = 0; q < E; ++q) { za[q] = act ? pa[q * NT] : mk<T>(0, 0); zb[q] = act ? pb[q * NT] : mk<T>(0, 0); }
+            for (int q = 0; q < E; ++q) { za[q] = act ? ld_once(pa + q * NT) : mk<T>(0, 0); zb[q] = act ? ld_once(pb + q * NT) : mk<T>(0, 0); }
 #pragma unroll
             for (int q = 0; q < E; ++q) {
                 v[0][q] = mk<T>(za[q].x + zb[q].x, za[q].y - zb[q].y);
@@ -2579,8 +2664,10 @@ rowszx_bins_kernel(RowsZCrossBins io, const float2* __restrict__ tw) {
         }
         __syncthreads();   // both fields' rows have been read: the buffers become the staging arrays
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-            if (pos[j] != 0xFFFFu) { stage_re[pos[j]] = cre[j]; if (has_im) stage_im[pos[j]] = cim[j]; }
+        for (int j = 0; j < 16; ++j) {
+            const unsigned p = pos.get(j);
+            if (p != 0xFFFFu) { stage_re[p] = cre[j]; if (has_im) stage_im[p] = cim[j]; }
+        }
         __syncthreads();
         auto target = [&](unsigned k) -> double* {
             const long plane = per_slot ? tile * ROWS + (long)(k / (unsigned)io.nbins) : tile;
