@@ -165,3 +165,35 @@ def test_fit_loglog():
     y = 3.0 * x ** -2.5
     _, a, b = xrft.fit_loglog(x, y)
     np.testing.assert_allclose([a, 2 ** b], [-2.5, 3.0])
+
+
+def test_calendar_coordinates_through_a_cftime_stand_in(monkeypatch):
+    """cftime is not installable in this image: a stand-in module with cftime's date2num signature drives the
+    calendar branch of the coordinate helpers (xrft/xrft.py:195-234, 269-274) -- spacing, lag and validity of a time axis
+    whose values carry a `calendar` attribute."""
+    import datetime as dt
+    import sys
+    import types
+    from xrft_b200 import api as A
+    from xrft_b200 import DataArray
+
+    class NoLeap(dt.datetime):
+        calendar = "noleap"
+
+    def date2num(dates, units, calendar):
+        assert units == "seconds since 1800-01-01 00:00:00" and calendar == "noleap"
+        ref = dt.datetime(1800, 1, 1)
+        f = lambda d: (d - ref).total_seconds()
+        return f(dates) if isinstance(dates, dt.datetime) else np.array([f(d) for d in np.asarray(dates).ravel()]).reshape(np.shape(dates))
+
+    monkeypatch.setitem(sys.modules, "cftime", types.SimpleNamespace(date2num=date2num))
+    t = np.array([NoLeap(2001, 1, 1) + dt.timedelta(hours=6 * i) for i in range(16)], dtype=object)
+    coord = DataArray(np.zeros(16), dims=["time"], coords={"time": t})["time"]
+    assert A._is_valid_fft_coord(coord)
+    assert np.allclose(A._diff_coord(coord), 6 * 3600.0)
+    assert A._get_coordinate_spacing(coord, 1e-3) == pytest.approx(6 * 3600.0)
+    assert A._lag_coord(coord) == pytest.approx(date2num(t[8], "seconds since 1800-01-01 00:00:00", "noleap"))
+    rev = DataArray(np.zeros(16), dims=["time"], coords={"time": t[::-1].copy()})["time"]
+    assert A._lag_coord(rev) == pytest.approx(date2num(t[8], "seconds since 1800-01-01 00:00:00", "noleap"))
+    bad = DataArray(np.zeros(3), dims=["time"], coords={"time": np.array(["a", "b", "c"], dtype=object)})["time"]
+    assert not A._is_valid_fft_coord(bad)
