@@ -13,9 +13,6 @@ VARIANTS = [
     ("separated half spectrum (no z mode)", {"XRFTB_ZPACK": "0"}),
     ("rows first + mirror pass", {"XRFTB_COLS_FIRST": "0"}),
 ]
-PREV = os.path.join(ROOT, "variants", "nosplit", "xrft_b200", "libxrftb200.so")   # an intermediate build kept for comparison
-if os.path.exists(PREV):
-    VARIANTS += [("intermediate build (variants/nosplit)", {"XRFTB_LIB": PREV})]
 if os.path.exists(BASE):
     VARIANTS += [("previous commit", {"XRFTB_LIB": BASE})]
 for name, env in VARIANTS:

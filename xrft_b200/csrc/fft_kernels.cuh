@@ -27,30 +27,6 @@ constexpr int ilog2c(int n) { return n <= 1 ? 0 : 1 + ilog2c(n / 2); }
 enum : int { EPI_COMPLEX = 0, EPI_POWER = 1, EPI_CROSS = 2, EPI_PHASE = 3, EPI_BINS_POWER = 4, EPI_BINS_CROSS = 5,
              EPI_CROSS_AND_PHASE = 6 /* internal: CROSS with the optional second output (desc.out2) */ };
 
-// read-once rows of pass 2 (packed column spectra): optionally loaded without allocating in L1, so that the tables every row
-// of an item re-reads (completion vector, twiddles) stay there
-#ifndef XRFTB_Z_LDNA
-#define XRFTB_Z_LDNA 0
-#endif
-__device__ __forceinline__ float2 ld_once(const float2* p) {
-#if XRFTB_Z_LDNA
-    float2 r;
-    asm volatile("ld.global.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
-    return r;
-#else
-    return *p;
-#endif
-}
-__device__ __forceinline__ double2 ld_once(const double2* p) {
-#if XRFTB_Z_LDNA
-    double2 r;
-    asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
-    return r;
-#else
-    return *p;
-#endif
-}
-
 __device__ __forceinline__ float xatan2(float y, float x) { return atan2f(y, x); }
 __device__ __forceinline__ double xatan2(double y, double x) { return atan2(y, x); }
 
@@ -795,7 +771,7 @@ rowsz_power_kernel(RowsZPower<T> io, const cplx<T>* __restrict__ tw, long nseq) 
             const cplx<T>* pb = io.z + ((b << io.logNy) + ((Ny - ky) & (Ny - 1))) * (long)M + u;
             cplx<T> za[E], zb[E];
 #pragma unroll
-            for (int q = 0; q < E; ++q) { za[q] = act ? ld_once(pa + q * NT) : mk<T>(0, 0); zb[q] = act ? ld_once(pb + q * NT) : mk<T>(0, 0); }
+            for (int q = 0; q < E; ++q) { za[q] = act ? pa[q * NT] : mk<T>(0, 0); zb[q] = act ? pb[q * NT] : mk<T>(0, 0); }
 #pragma unroll
             for (int q = 0; q < E; ++q) {
                 v[0][q] = mk<T>(za[q].x + zb[q].x, za[q].y - zb[q].y);
@@ -932,7 +908,7 @@ rowszx_kernel(RowsZCross<float> io, const float2* __restrict__ tw, long nseq) {
             const cplx<T>* pb = zf + ((b << io.logNy) + ((Ny - ky) & (Ny - 1))) * (long)M + u;
             cplx<T> za[E], zb[E];
 #pragma unroll
-            for (int q = 0; q < E; ++q) { za[q] = act ? ld_once(pa + q * NT) : mk<T>(0, 0); zb[q] = act ? ld_once(pb + q * NT) : mk<T>(0, 0); }
+            for (int q = 0; q < E; ++q) { za[q] = act ? pa[q * NT] : mk<T>(0, 0); zb[q] = act ? pb[q * NT] : mk<T>(0, 0); }
 #pragma unroll
             for (int q = 0; q < E; ++q) {
                 v[0][q] = mk<T>(za[q].x + zb[q].x, za[q].y - zb[q].y);
@@ -2621,7 +2597,7 @@ rowszx_bins_kernel(RowsZCrossBins io, const float2* __restrict__ tw) {
             const cplx<T>* pb = zf + ((bb << io.base.logNy) + ((Ny - ky) & (Ny - 1))) * (long)M + u;
             cplx<T> za[E], zb[E];
 #pragma unroll
-            for (int q = 0; q < E; ++q) { za[q] = act ? ld_once(pa + q * NT) : mk<T>(0, 0); zb[q] = act ? ld_once(pb + q * NT) : mk<T>(0, 0); }
+            for (int q = 0; q < E; ++q) { za[q] = act ? pa[q * NT] : mk<T>(0, 0); zb[q] = act ? pb[q * NT] : mk<T>(0, 0); }
 #pragma unroll
             for (int q = 0; q < E; ++q) {
                 v[0][q] = mk<T>(za[q].x + zb[q].x, za[q].y - zb[q].y);
