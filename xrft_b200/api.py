@@ -390,17 +390,26 @@ def _stream_host_chunks(arrs, ntrans, out_host, core):
     bufs = [[torch.empty((step,) + tuple(h.shape[1:]), dtype=h.dtype, device=dev) for h in host] for _ in range(2)]
     ev_in = [torch.cuda.Event() for _ in range(2)]
     ev_free = [torch.cuda.Event() for _ in range(2)]   # input buffer b consumed by the kernels
-    result = None
     keep = []
-    for i, lo in enumerate(range(0, lead, step)):
+    los = list(range(0, lead, step))
+
+    def upload(i):
+        # host -> device copy of chunk i into buffer i % 2 (free once the kernels of chunk i-2 have consumed it)
+        lo, b = los[i], i % 2
         hi = min(lead, lo + step)
-        b = i % 2
         with torch.cuda.stream(s_in):
             if i >= 2:
                 s_in.wait_event(ev_free[b])
             for h, d in zip(host, bufs[b]):
                 d[: hi - lo].copy_(h[lo:hi], non_blocking=True)
             ev_in[b].record(s_in)
+
+    upload(0)
+    for i, lo in enumerate(los):
+        hi = min(lead, lo + step)
+        b = i % 2
+        if i + 1 < len(los):
+            upload(i + 1)   # queued BEFORE this chunk's kernels are launched: the copy engine never waits for the host code below
         with torch.cuda.stream(s_cmp):
             s_cmp.wait_event(ev_in[b])
             xs = [d[: hi - lo] for d in bufs[b]]
@@ -470,9 +479,19 @@ def _run_forward(P, das, mode, detrend, window, scale, ramps=None, weight=None, 
         keep_half = real_dim is not None
         shifts = [P["shift"]] * ntrans if real_dim is None else [False] * ntrans
 
+        # the per-axis vectors go to the device ONCE: a pageable copy inside the chunk loop would block the host until the
+        # chunk's own upload has finished, and the copy engine would idle while the host catches up
+        dev = torch.device("cuda", torch.cuda.current_device())
+        f32 = das[0].data.dtype == np.float32
+        rdt, cdt = (torch.float32, torch.complex64) if f32 else (torch.float64, torch.complex128)
+        up = lambda v, dt: None if v is None else (v if _is_torch(v) else torch.from_numpy(np.ascontiguousarray(v))).to(device=dev, dtype=dt)
+        wins_d = None if wins is None else [up(w, rdt) for w in wins]
+        ramps_d = None if ramps is None else [up(r, cdt) for r in ramps]
+        weight_d = up(weight, rdt)
+
         def core(x1, x2):
-            return _spectral_core(x1, x2, ntrans, mode, detrend=detrend, windows=wins, keep_half=keep_half, shift=shifts,
-                                  ramps=ramps, weight=weight, scale=scale, lut=lut, nbins=nbins)
+            return _spectral_core(x1, x2, ntrans, mode, detrend=detrend, windows=wins_d, keep_half=keep_half, shift=shifts,
+                                  ramps=ramps_d, weight=weight_d, scale=scale, lut=lut, nbins=nbins)
 
         oh = None
         if out is not None:
