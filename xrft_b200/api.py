@@ -404,12 +404,12 @@ def _stream_host_chunks(arrs, ntrans, out_host, core):
                 d[: hi - lo].copy_(h[lo:hi], non_blocking=True)
             ev_in[b].record(s_in)
 
-    upload(0)
     for i, lo in enumerate(los):
         hi = min(lead, lo + step)
         b = i % 2
-        if i + 1 < len(los):
-            upload(i + 1)   # queued BEFORE this chunk's kernels are launched: the copy engine never waits for the host code below
+        # (queueing the upload of chunk i+1 ahead of chunk i's kernels was measured too: 0.52-0.82 of the link probe against
+        # 0.78-0.95 in this order on a two-GPU box, profiles/README.md)
+        upload(i)
         with torch.cuda.stream(s_cmp):
             s_cmp.wait_event(ev_in[b])
             xs = [d[: hi - lo] for d in bufs[b]]
