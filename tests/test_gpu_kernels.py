@@ -308,6 +308,31 @@ def test_smooth_real_transforms_2d(dt):
     assert relerr(back, x) < TOL[dt] * 10
 
 
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("n", [96, 100, 120, 360, 1000, 1440, 3600, 10000, 12600, 25200, 135, 1125])
+def test_real_transforms_smooth_lengths(dt, n):
+    """rfft / irfft along a smooth non-power-of-two axis: even lengths run the packed half-length mixed-radix transform with the
+    split / merge in its stores / loads (one pass); odd lengths and lengths beyond its capacity take the promoted complex path.
+    irfft ignores the imaginary parts of the DC and Nyquist terms like numpy."""
+    from xrft_b200 import backend as B
+    rng = np.random.default_rng(n)
+    rows = 37 if n < 2000 else 5
+    x = rng.standard_normal((rows, n)).astype(dt)
+    y = B.rfftn(torch.from_numpy(x).cuda(), axes=[1]).cpu().numpy()
+    ref = np.fft.rfft(x.astype(np.float64), axis=1)
+    assert y.shape == ref.shape
+    assert relerr(y, ref) < TOL[dt] * 10
+    if n % 2 == 0:
+        spec = ref.copy()
+        spec[:, 0] += 0.25j
+        spec[:, -1] -= 0.5j
+        back = B.irfftn(torch.from_numpy(spec.astype(y.dtype)).cuda(), axes=[1]).cpu().numpy()
+        assert relerr(back, np.fft.irfft(spec, n=n, axis=1)) < TOL[dt] * 10
+    x3 = rng.standard_normal((3, 90, n if n <= 1440 else 96)).astype(dt)     # two axes: strided smooth pass behind the real one
+    y3 = B.rfftn(torch.from_numpy(x3).cuda(), axes=[1, 2]).cpu().numpy()
+    assert relerr(y3, np.fft.rfftn(x3.astype(np.float64), axes=[1, 2])) < TOL[dt] * 10
+
+
 @pytest.mark.gpu
 def test_permute_flip_kernel():
     """xrftb_permute (axis permutation + reversal; the reference's da.transpose / flipped coordinates) equals numpy"""

@@ -1039,8 +1039,11 @@ static int fftn_impl(const void* in, void* out, void* work, size_t work_bytes, i
         } else if (N <= kSmallDft) {
             dft_small_kernel<T><<<small_grid, 128, 0, st>>>(in, dst, (int)N, nseq, 1, 2, (T)1);
             if (int rc = check_launch("dft_small_kernel")) return rc;
+        } else if (smooth_real_ok<T>(N)) {
+            // even smooth length: packed half-length mixed-radix transform, split in its stores (one pass, no promotion)
+            if (int rc = smooth_r2c<T>(reinterpret_cast<const T*>(in), dst, nseq, N, st)) return rc;
         } else {
-            // promote to complex, full-length complex pass (four-step / Bluestein), keep k <= N/2
+            // promote to complex, full-length complex pass (mixed radix / four-step / Bluestein), keep k <= N/2
             const size_t cb = (((size_t)nseq * N * sizeof(C)) + 256) & ~(size_t)255;
             if (wleft < cb) { set_error("rfftn: workspace too small (%zu < %zu)", wleft, cb); return XRFTB_EWORKSPACE; }
             C* full = reinterpret_cast<C*>(wbase);
@@ -1074,6 +1077,7 @@ static int fftn_impl(const void* in, void* out, void* work, size_t work_bytes, i
         dft_small_kernel<T><<<small_grid, 128, 0, st>>>(src, out, (int)N, nseq, 1, 3, inv_scale);
         return check_launch("dft_small_kernel");
     }
+    if (smooth_real_ok<T>(N)) return smooth_c2r<T>(src, reinterpret_cast<T*>(out), nseq, N, inv_scale * (T)2, st);   // 1 / (N/2)
     {
         const size_t cb = (((size_t)nseq * N * sizeof(C)) + 256) & ~(size_t)255;
         if (wleft < cb) { set_error("irfftn: workspace too small (%zu < %zu)", wleft, cb); return XRFTB_EWORKSPACE; }

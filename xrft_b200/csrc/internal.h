@@ -70,6 +70,11 @@ template <typename T> int cols_c2c(const cplx<T>* in, cplx<T>* out, int log2L, l
 // [A][n][B] view (in-place safe); smooth_len_ok = the length is covered (factors and shared-memory capacity)
 template <typename T> bool smooth_len_ok(long n);
 template <typename T> int smooth_c2c(const cplx<T>* src, cplx<T>* dst, long A, long n, long B, int inverse, T scale, cudaStream_t st);
+// real transforms of even length N (N / 2 covered by smooth_len_ok) along the contiguous axis: [nseq][N] real <-> [nseq][N/2+1]
+// complex in one pass (packed half-length transform + split in the stores / merge in the loads); c2r scales by `scale`
+template <typename T> bool smooth_real_ok(long N);
+template <typename T> int smooth_r2c(const T* in, cplx<T>* out, long nseq, long N, cudaStream_t st);
+template <typename T> int smooth_c2r(const cplx<T>* in, T* out, long nseq, long N, T scale, cudaStream_t st);
 // one explicit instantiation per (T, MODE), spread over several translation units
 template <typename T, int MODE> int cols_fused_mode(const cplx<T>* in1, const cplx<T>* in2, int log2L, long ntiles_total, int ntile,
                                                     const EpilogueDesc& d, const CUtensorMap* tmap, cudaStream_t st);

@@ -163,7 +163,7 @@ __device__ __forceinline__ void smooth_pass(const cplx<T>* __restrict__ src, cpl
 template <typename T>
 __global__ void __launch_bounds__(256, 2) smooth_c2c_kernel(const cplx<T>* __restrict__ in, cplx<T>* __restrict__ out, const cplx<T>* __restrict__ tw,
                                                          long A, int n, long B, int C, int contig, int inverse, T scale, const __grid_constant__ SmoothPlan plan,
-                                                         long ntiles, long tiles_per_item) {
+                                                         long ntiles, long tiles_per_item, int real_mode, const cplx<T>* __restrict__ twN) {
     extern __shared__ __align__(16) unsigned char smooth_smem[];
     __shared__ cplx<T> w9[9], w25[25];   // internal factors of the composite radices, from the length-n table (9 | n, 25 | n)
     if (n % 9 == 0 && threadIdx.x < 9) w9[threadIdx.x] = __ldg(tw + threadIdx.x * (n / 9));
@@ -179,12 +179,29 @@ __global__ void __launch_bounds__(256, 2) smooth_c2c_kernel(const cplx<T>* __res
         if (contig) {
             a0 = tile * C;
             nc = (int)(A - a0 < C ? A - a0 : C);
-            const cplx<T>* p = in + a0 * n;
-            for (int e = threadIdx.x; e < nc * n; e += blockDim.x) {
-                const int c = e / n, q = e - c * n;
-                cplx<T> x = p[e];
-                if (inverse) x.y = -x.y;
-                buf0[c * sc + q] = x;
+            if (real_mode == 2) {
+                // C2R of even length N = 2n: the half spectrum X[0..n] of a real row folds into the n-point spectrum Z = E + i O of
+                // the packed sequence z[m] = x[2m] + i x[2m+1]:  E = (X[k] + conj X[n-k]) / 2,  O = conj(w_N^k) (X[k] - conj X[n-k]) / 2
+                // (the imaginary parts of X[0] and X[n] are ignored, like numpy's irfft)
+                const cplx<T>* p = in + a0 * (long)(n + 1);
+                const float inv_n = 1.0f / (float)n;
+                for (int e = threadIdx.x; e < nc * n; e += blockDim.x) {
+                    const int c = fdiv(e, inv_n), k = e - c * n;
+                    cplx<T> xk = p[(long)c * (n + 1) + k], xm = p[(long)c * (n + 1) + (n - k)];
+                    if (k == 0) { xk.y = (T)0; xm.y = (T)0; }
+                    const cplx<T> ev = mk<T>((T)0.5 * (xk.x + xm.x), (T)0.5 * (xk.y - xm.y));
+                    const cplx<T> dv = mk<T>((T)0.5 * (xk.x - xm.x), (T)0.5 * (xk.y + xm.y));
+                    const cplx<T> od = cmulc(dv, __ldg(twN + k));
+                    buf0[c * sc + k] = mk<T>(ev.x - od.y, -(ev.y + od.x));   // conj(Z): the inverse runs as a conjugated forward transform
+                }
+            } else {
+                const cplx<T>* p = in + a0 * n;
+                for (int e = threadIdx.x; e < nc * n; e += blockDim.x) {
+                    const int c = e / n, q = e - c * n;
+                    cplx<T> x = p[e];
+                    if (inverse) x.y = -x.y;
+                    buf0[c * sc + q] = x;
+                }
             }
         } else {
             a0 = tile / tiles_per_item;
@@ -226,7 +243,21 @@ __global__ void __launch_bounds__(256, 2) smooth_c2c_kernel(const cplx<T>* __res
             Ns *= R;
         }
         // ---- store
-        if (contig) {
+        if (contig && real_mode == 1) {
+            // R2C of even length N = 2n: the real row was read as n packed points z[m] = x[2m] + i x[2m+1]; with Z its spectrum,
+            // X[k] = E + w_N^k O,  E = (Z[k] + conj Z[n-k]) / 2,  O = -i (Z[k] - conj Z[n-k]) / 2,  k = 0 .. n (Z[n] = Z[0])
+            cplx<T>* p = out + a0 * (long)(n + 1);
+            const float inv_h = 1.0f / (float)(n + 1);
+            for (int e = threadIdx.x; e < nc * (n + 1); e += blockDim.x) {
+                const int c = fdiv(e, inv_h), k = e - c * (n + 1);
+                const cplx<T> zk = src[c * sc + (k == n ? 0 : k)];
+                const cplx<T> zm = src[c * sc + ((k == 0 || k == n) ? 0 : n - k)];
+                const cplx<T> ev = mk<T>((T)0.5 * (zk.x + zm.x), (T)0.5 * (zk.y - zm.y));
+                const cplx<T> dv = mk<T>((T)0.5 * (zk.x - zm.x), (T)0.5 * (zk.y + zm.y));
+                const cplx<T> x = cadd(ev, cmul(mk<T>(dv.y, -dv.x), __ldg(twN + k)));
+                p[e] = cscale(x, scale);
+            }
+        } else if (contig) {
             cplx<T>* p = out + a0 * n;
             for (int e = threadIdx.x; e < nc * n; e += blockDim.x) {
                 const int c = e / n, q = e - c * n;
@@ -283,8 +314,28 @@ template <typename T> bool smooth_len_ok(long n) {
     return factorize(n, &p, sizeof(T) == 4);
 }
 
+namespace {
+template <typename T>
+int smooth_launch(const cplx<T>* src, cplx<T>* dst, long A, long n, long B, int inverse, T scale, cudaStream_t st, int real_mode);
+}
 template <typename T>
 int smooth_c2c(const cplx<T>* src, cplx<T>* dst, long A, long n, long B, int inverse, T scale, cudaStream_t st) {
+    return smooth_launch<T>(src, dst, A, n, B, inverse, scale, st, 0);
+}
+// real transforms of even length N along the contiguous axis through the packed half-length transform (N / 2 smooth):
+// one pass over the data, no promotion to complex
+template <typename T> bool smooth_real_ok(long N) { return N >= 4 && N % 2 == 0 && smooth_len_ok<T>(N / 2); }
+template <typename T> int smooth_r2c(const T* in, cplx<T>* out, long nseq, long N, cudaStream_t st) {
+    if (!smooth_real_ok<T>(N)) { set_error("smooth_r2c: length %ld is not covered", N); return XRFTB_EUNSUPPORTED; }
+    return smooth_launch<T>(reinterpret_cast<const cplx<T>*>(in), out, nseq, N / 2, 1, 0, (T)1, st, 1);
+}
+template <typename T> int smooth_c2r(const cplx<T>* in, T* out, long nseq, long N, T scale, cudaStream_t st) {
+    if (!smooth_real_ok<T>(N)) { set_error("smooth_c2r: length %ld is not covered", N); return XRFTB_EUNSUPPORTED; }
+    return smooth_launch<T>(in, reinterpret_cast<cplx<T>*>(out), nseq, N / 2, 1, 1, scale, st, 2);
+}
+namespace {
+template <typename T>
+int smooth_launch(const cplx<T>* src, cplx<T>* dst, long A, long n, long B, int inverse, T scale, cudaStream_t st, int real_mode) {
     SmoothPlan plan;
     if (!smooth_len_ok<T>(n) || !factorize(n, &plan, sizeof(T) == 4)) { set_error("smooth_c2c: length %ld is not covered", n); return XRFTB_EUNSUPPORTED; }
     if (A < 1 || B < 1) return 0;
@@ -309,6 +360,8 @@ int smooth_c2c(const cplx<T>* src, cplx<T>* dst, long A, long n, long B, int inv
     if (smem > (size_t)kSmoothMaxDynSmem) { set_error("smooth_c2c: tile of length %ld does not fit shared memory", n); return XRFTB_EUNSUPPORTED; }
     const cplx<T>* tw = smooth_table<T>(n);
     if (!tw) return XRFTB_ECUDA;
+    const cplx<T>* twN = real_mode ? smooth_table<T>(2 * n) : nullptr;   // exp(-2 pi i k / N) of the real-transform split
+    if (real_mode && !twN) return XRFTB_ECUDA;
     auto kern = smooth_c2c_kernel<T>;
     int dev = 0;
     cudaGetDevice(&dev);
@@ -323,13 +376,21 @@ int smooth_c2c(const cplx<T>* src, cplx<T>* dst, long A, long n, long B, int inv
     }
     long grid = (long)sm_count() * 4;
     if (grid > ntiles) grid = ntiles;
-    kern<<<(unsigned)grid, 256, smem, st>>>(src, dst, tw, A, (int)n, B, (int)C, contig ? 1 : 0, inverse ? 1 : 0, scale, plan, ntiles, tiles_per_item);
+    kern<<<(unsigned)grid, 256, smem, st>>>(src, dst, tw, A, (int)n, B, (int)C, contig ? 1 : 0, inverse ? 1 : 0, scale, plan, ntiles, tiles_per_item,
+                                            real_mode, twN);
     return check_launch("smooth_c2c_kernel");
 }
+}  // namespace
 
 template bool smooth_len_ok<float>(long);
 template bool smooth_len_ok<double>(long);
 template int smooth_c2c<float>(const cplx<float>*, cplx<float>*, long, long, long, int, float, cudaStream_t);
 template int smooth_c2c<double>(const cplx<double>*, cplx<double>*, long, long, long, int, double, cudaStream_t);
+template bool smooth_real_ok<float>(long);
+template bool smooth_real_ok<double>(long);
+template int smooth_r2c<float>(const float*, cplx<float>*, long, long, cudaStream_t);
+template int smooth_r2c<double>(const double*, cplx<double>*, long, long, cudaStream_t);
+template int smooth_c2r<float>(const cplx<float>*, float*, long, long, float, cudaStream_t);
+template int smooth_c2r<double>(const cplx<double>*, double*, long, long, double, cudaStream_t);
 
 }  // namespace xrftb
