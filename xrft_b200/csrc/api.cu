@@ -311,6 +311,30 @@ __global__ void __launch_bounds__(256) rowline_wj_out_kernel(const double2* __re
 }
 
 // ------------------------------------------------------------------------------------------------
+// Index of a grid-stride loop over a [batch][n0][n1][n2] array, decomposed ONCE per thread (four 64-bit divisions) and advanced
+// by the decomposed stride with carries: the elementwise kernels below spent most of their instructions on a 64-bit
+// division chain per element (1 TB/s on 4-byte elements; profiles/r02_pass1_source_profile.md).
+// ------------------------------------------------------------------------------------------------
+struct GridIndex {
+    long b; int i0, i1, i2;
+    long sb; int s0, s1, s2;
+    int n0, n1, n2;
+    __device__ __forceinline__ GridIndex(long start, long stride, long n0_, long n1_, long n2_) : n0((int)n0_), n1((int)n1_), n2((int)n2_) {
+        i2 = (int)(start % n2_); long r = start / n2_; i1 = (int)(r % n1_); r /= n1_; i0 = (int)(r % n0_); b = r / n0_;
+        s2 = (int)(stride % n2_); r = stride / n2_; s1 = (int)(r % n1_); r /= n1_; s0 = (int)(r % n0_); sb = r / n0_;
+    }
+    __device__ __forceinline__ void next() {
+        int c;
+        i2 += s2; c = i2 >= n2; i2 -= c ? n2 : 0;
+        i1 += s1 + c; c = i1 >= n1; i1 -= c ? n1 : 0;
+        i0 += s0 + c; c = i0 >= n0; i0 -= c ? n0 : 0;
+        b += sb + c;
+    }
+};
+// (o + add) mod n for 0 <= o, add < n
+__device__ __forceinline__ int wrap_add(int o, int add, int n) { const int x = o + add; return x >= n ? x - n : x; }
+
+// ------------------------------------------------------------------------------------------------
 // detrend + window (non-fused path and the public xrft.detrend)
 // ------------------------------------------------------------------------------------------------
 template <typename T>
@@ -318,28 +342,28 @@ __global__ void __launch_bounds__(256) detrend_window_kernel(const T* __restrict
                                                              const double* __restrict__ mom, int detrend, const T* w0,
                                                              const T* w1, const T* w2, long n0, long n1, long n2, long total) {
     const double npts = (double)n0 * (double)n1 * (double)n2;
-    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-        const long i2 = i % n2;
-        long r = i / n2;
-        const long i1 = r % n1;
-        r /= n1;
-        const long i0 = r % n0;
-        const long b = r / n0;
+    // plane = m0 / npts + sum_a m_a c_a (i_a - (n_a - 1) / 2): the reciprocals are per launch, the products per element
+    const double inv_npts = 1.0 / npts;
+    const double c0 = n0 > 1 ? 1.0 / (npts * ((double)n0 * n0 - 1.0) / 12.0) : 0.0;
+    const double c1 = n1 > 1 ? 1.0 / (npts * ((double)n1 * n1 - 1.0) / 12.0) : 0.0;
+    const double c2 = n2 > 1 ? 1.0 / (npts * ((double)n2 * n2 - 1.0) / 12.0) : 0.0;
+    const double h0 = 0.5 * (double)(n0 - 1), h1 = 0.5 * (double)(n1 - 1), h2 = 0.5 * (double)(n2 - 1);
+    const long stride = (long)gridDim.x * blockDim.x;
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    GridIndex g(i, stride, n0, n1, n2);
+    for (; i < total; i += stride, g.next()) {
         double x = (double)in[i];
         if (detrend) {
-            const double* m = mom + b * 4;
-            double p = m[0] / npts;
-            if (detrend == 2) {
-                if (n0 > 1) p += m[1] / (npts * ((double)n0 * n0 - 1.0) / 12.0) * ((double)i0 - 0.5 * (n0 - 1));
-                if (n1 > 1) p += m[2] / (npts * ((double)n1 * n1 - 1.0) / 12.0) * ((double)i1 - 0.5 * (n1 - 1));
-                if (n2 > 1) p += m[3] / (npts * ((double)n2 * n2 - 1.0) / 12.0) * ((double)i2 - 0.5 * (n2 - 1));
-            }
+            const double* m = mom + g.b * 4;
+            double p = m[0] * inv_npts;
+            if (detrend == 2) p += m[1] * c0 * ((double)g.i0 - h0) + m[2] * c1 * ((double)g.i1 - h1) + m[3] * c2 * ((double)g.i2 - h2);
             x -= p;
         }
         T y = (T)x;  // the reference rounds the detrended field to the input dtype (output_dtypes=[da.dtype])
-        if (w0) y *= w0[i0];
-        if (w1) y *= w1[i1];
-        if (w2) y *= w2[i2];
+        if (w0) y *= w0[g.i0];
+        if (w1) y *= w1[g.i1];
+        if (w2) y *= w2[g.i2];
         out[i] = y;
     }
 }
@@ -361,22 +385,24 @@ struct PostDesc {
 template <typename T>
 __global__ void __launch_bounds__(256) spectral_post_kernel(const cplx<T>* __restrict__ in1, const cplx<T>* __restrict__ in2,
                                                             void* __restrict__ out, PostDesc d, long total) {
-    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-        const long o2 = i % d.W;
-        long r = i / d.W;
-        const long o1 = r % d.k1;
-        r /= d.k1;
-        const long o0 = r % d.k0;
-        const long b = r / d.k0;
-        // o = (k + N/2) % N  <=>  k = (o + N - N/2) % N
-        // shift 1 (fftshift): o = (f + N/2) % N ; shift 2 (ifftshift): o = (f + N - N/2) % N
-        const long f0 = d.shift[0] == 1 ? (o0 + d.k0 - d.k0 / 2) % d.k0 : d.shift[0] == 2 ? (o0 + d.k0 / 2) % d.k0 : o0;
-        const long f1 = d.shift[1] == 1 ? (o1 + d.k1 - d.k1 / 2) % d.k1 : d.shift[1] == 2 ? (o1 + d.k1 / 2) % d.k1 : o1;
-        const long f2 = d.shift[2] == 1 ? (o2 + d.k2 - d.k2 / 2) % d.k2 : d.shift[2] == 2 ? (o2 + d.k2 / 2) % d.k2 : o2;
+    const long stride = (long)gridDim.x * blockDim.x;
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int k0 = (int)d.k0, k1 = (int)d.k1, k2 = (int)d.k2;
+    // o = (f + N/2) % N (fftshift) <=> f = (o + N - N/2) % N ; ifftshift: o = (f + N - N/2) % N <=> f = (o + N/2) % N
+    const int a0 = d.shift[0] == 1 ? k0 - k0 / 2 : d.shift[0] == 2 ? k0 / 2 : 0;
+    const int a1 = d.shift[1] == 1 ? k1 - k1 / 2 : d.shift[1] == 2 ? k1 / 2 : 0;
+    const int a2 = d.shift[2] == 1 ? k2 - k2 / 2 : d.shift[2] == 2 ? k2 / 2 : 0;
+    GridIndex gi(i, stride, d.k0, d.k1, d.W);
+    for (; i < total; i += stride, gi.next()) {
+        const int o0 = gi.i0, o1 = gi.i1, o2 = gi.i2;
+        const long b = gi.b;
+        const int f0 = wrap_add(o0, a0 == k0 ? 0 : a0, k0), f1 = wrap_add(o1, a1 == k1 ? 0 : a1, k1);
+        const int f2 = d.shift[2] ? wrap_add(o2, a2 == k2 ? 0 : a2, k2) : o2;   // (without a shift o2 runs over W <= k2 columns)
         long s0 = f0, s1 = f1, s2 = f2;
         bool cj = false;
-        if (d.hermitian && f2 > d.k2 / 2) {
-            s0 = (d.k0 - f0) % d.k0; s1 = (d.k1 - f1) % d.k1; s2 = d.k2 - f2; cj = true;
+        if (d.hermitian && f2 > k2 / 2) {
+            s0 = f0 ? k0 - f0 : 0; s1 = f1 ? k1 - f1 : 0; s2 = k2 - f2; cj = true;
         }
         const long src = ((b * d.k0 + s0) * d.k1 + s1) * d.k2in + s2;
         cplx<T> a = in1[src];
@@ -419,14 +445,13 @@ __global__ void __launch_bounds__(256) spectral_post_kernel(const cplx<T>* __res
 template <typename T>
 __global__ void __launch_bounds__(256) roll_scale_kernel(const T* __restrict__ in, T* __restrict__ out, long n0, long n1, long n2,
                                                          long s0, long s1, long s2, int width, T scale, long total) {
-    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-        const long i2 = i % n2;
-        long r = i / n2;
-        const long i1 = r % n1;
-        r /= n1;
-        const long i0 = r % n0;
-        const long b = r / n0;
-        const long o = ((b * n0 + (i0 + s0) % n0) * n1 + (i1 + s1) % n1) * n2 + (i2 + s2) % n2;
+    const long stride = (long)gridDim.x * blockDim.x;
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int r0 = (int)(s0 % n0), r1 = (int)(s1 % n1), r2 = (int)(s2 % n2);   // shifts reduced once: 0 <= r < n
+    GridIndex g(i, stride, n0, n1, n2);
+    for (; i < total; i += stride, g.next()) {
+        const long o = ((g.b * n0 + wrap_add(g.i0, r0, (int)n0)) * n1 + wrap_add(g.i1, r1, (int)n1)) * n2 + wrap_add(g.i2, r2, (int)n2);
         for (int w = 0; w < width; ++w) out[o * width + w] = in[i * width + w] * scale;
     }
 }
