@@ -337,7 +337,19 @@ __device__ __forceinline__ int wrap_add(int o, int add, int n) { const int x = o
 // ------------------------------------------------------------------------------------------------
 // detrend + window (non-fused path and the public xrft.detrend)
 // ------------------------------------------------------------------------------------------------
-template <typename T>
+// VEC consecutive elements of the last axis per thread and trip (VEC = 4 needs n2 % 4 == 0 and 16-byte aligned rows): four
+// independent loads in flight per thread -- with one 4-byte load per thread the kernel could not keep HBM busy -- and vector stores
+__device__ __forceinline__ void load_vec4(const float* p, float (&v)[4]) { const float4 q = *reinterpret_cast<const float4*>(p); v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
+__device__ __forceinline__ void load_vec4(const double* p, double (&v)[4]) {
+    const double2 a = *reinterpret_cast<const double2*>(p), b = *reinterpret_cast<const double2*>(p + 2);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+__device__ __forceinline__ void store_vec4(float* p, const float (&v)[4]) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+__device__ __forceinline__ void store_vec4(double* p, const double (&v)[4]) {
+    *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
+    *reinterpret_cast<double2*>(p + 2) = make_double2(v[2], v[3]);
+}
+template <typename T, int VEC>
 __global__ void __launch_bounds__(256) detrend_window_kernel(const T* __restrict__ in, T* __restrict__ out,
                                                              const double* __restrict__ mom, int detrend, const T* w0,
                                                              const T* w1, const T* w2, long n0, long n1, long n2, long total) {
@@ -349,22 +361,32 @@ __global__ void __launch_bounds__(256) detrend_window_kernel(const T* __restrict
     const double c2 = n2 > 1 ? 1.0 / (npts * ((double)n2 * n2 - 1.0) / 12.0) : 0.0;
     const double h0 = 0.5 * (double)(n0 - 1), h1 = 0.5 * (double)(n1 - 1), h2 = 0.5 * (double)(n2 - 1);
     const long stride = (long)gridDim.x * blockDim.x;
-    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    GridIndex g(i, stride, n0, n1, n2);
-    for (; i < total; i += stride, g.next()) {
-        double x = (double)in[i];
+    const long ngroups = total / VEC;
+    long iv = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (iv >= ngroups) return;
+    GridIndex g(iv, stride, n0, n1, n2 / VEC);
+    for (; iv < ngroups; iv += stride, g.next()) {
+        const long e = iv * VEC;
+        T v[VEC];
+        if constexpr (VEC == 4) load_vec4(in + e, v); else v[0] = in[e];
+        double prow = 0.0, pcol = 0.0;
         if (detrend) {
             const double* m = mom + g.b * 4;
-            double p = m[0] * inv_npts;
-            if (detrend == 2) p += m[1] * c0 * ((double)g.i0 - h0) + m[2] * c1 * ((double)g.i1 - h1) + m[3] * c2 * ((double)g.i2 - h2);
-            x -= p;
+            prow = m[0] * inv_npts;
+            if (detrend == 2) { prow += m[1] * c0 * ((double)g.i0 - h0) + m[2] * c1 * ((double)g.i1 - h1); pcol = m[3] * c2; }
         }
-        T y = (T)x;  // the reference rounds the detrended field to the input dtype (output_dtypes=[da.dtype])
-        if (w0) y *= w0[g.i0];
-        if (w1) y *= w1[g.i1];
-        if (w2) y *= w2[g.i2];
-        out[i] = y;
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+            const int i2 = g.i2 * VEC + k;
+            double x = (double)v[k];
+            if (detrend) x -= prow + pcol * ((double)i2 - h2);
+            T y = (T)x;  // the reference rounds the detrended field to the input dtype (output_dtypes=[da.dtype])
+            if (w0) y *= w0[g.i0];
+            if (w1) y *= w1[g.i1];
+            if (w2) y *= w2[i2];
+            v[k] = y;
+        }
+        if constexpr (VEC == 4) store_vec4(out + e, v); else out[e] = v[0];
     }
 }
 
@@ -382,59 +404,89 @@ struct PostDesc {
     long seg_n, seg_inner;   // seg_n > 0: mean over an axis of the batch (Welch segments): batch = [outer][seg_n][seg_inner]
 };
 
-template <typename T>
+// VEC = 4 (W % 4 == 0, aligned rows, no segment mean): four outputs of a row per thread and trip -- four independent source
+// loads in flight and one vector store
+template <typename T, int VEC>
 __global__ void __launch_bounds__(256) spectral_post_kernel(const cplx<T>* __restrict__ in1, const cplx<T>* __restrict__ in2,
                                                             void* __restrict__ out, PostDesc d, long total) {
     const long stride = (long)gridDim.x * blockDim.x;
-    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
-    if (i >= total) return;
+    const long ngroups = total / VEC;
+    long iv = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (iv >= ngroups) return;
     const int k0 = (int)d.k0, k1 = (int)d.k1, k2 = (int)d.k2;
     // o = (f + N/2) % N (fftshift) <=> f = (o + N - N/2) % N ; ifftshift: o = (f + N - N/2) % N <=> f = (o + N/2) % N
     const int a0 = d.shift[0] == 1 ? k0 - k0 / 2 : d.shift[0] == 2 ? k0 / 2 : 0;
     const int a1 = d.shift[1] == 1 ? k1 - k1 / 2 : d.shift[1] == 2 ? k1 / 2 : 0;
     const int a2 = d.shift[2] == 1 ? k2 - k2 / 2 : d.shift[2] == 2 ? k2 / 2 : 0;
-    GridIndex gi(i, stride, d.k0, d.k1, d.W);
-    for (; i < total; i += stride, gi.next()) {
-        const int o0 = gi.i0, o1 = gi.i1, o2 = gi.i2;
+    const bool two = !(d.mode == EPI_COMPLEX || d.mode == EPI_POWER);
+    GridIndex gi(iv, stride, d.k0, d.k1, d.W / VEC);
+    for (; iv < ngroups; iv += stride, gi.next()) {
+        const int o0 = gi.i0, o1 = gi.i1;
         const long b = gi.b;
         const int f0 = wrap_add(o0, a0 == k0 ? 0 : a0, k0), f1 = wrap_add(o1, a1 == k1 ? 0 : a1, k1);
-        const int f2 = d.shift[2] ? wrap_add(o2, a2 == k2 ? 0 : a2, k2) : o2;   // (without a shift o2 runs over W <= k2 columns)
-        long s0 = f0, s1 = f1, s2 = f2;
-        bool cj = false;
-        if (d.hermitian && f2 > k2 / 2) {
-            s0 = f0 ? k0 - f0 : 0; s1 = f1 ? k1 - f1 : 0; s2 = k2 - f2; cj = true;
+        const long rowd = (b * d.k0 + f0) * d.k1 + f1;                                // direct source row
+        const long rowm = (b * d.k0 + (f0 ? k0 - f0 : 0)) * d.k1 + (f1 ? k1 - f1 : 0);   // its Hermitian partner
+        int f2[VEC];
+        bool cj[VEC];
+        cplx<T> a[VEC], g[VEC];
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+            const int o2 = gi.i2 * VEC + k;
+            f2[k] = d.shift[2] ? wrap_add(o2, a2 == k2 ? 0 : a2, k2) : o2;   // (without a shift o2 runs over W <= k2 columns)
+            cj[k] = d.hermitian && f2[k] > k2 / 2;
+            const long src = cj[k] ? rowm * d.k2in + (k2 - f2[k]) : rowd * d.k2in + f2[k];
+            a[k] = in1[src];
+            if (two) g[k] = in2[src];
         }
-        const long src = ((b * d.k0 + s0) * d.k1 + s1) * d.k2in + s2;
-        cplx<T> a = in1[src];
-        if (cj) a.y = -a.y;
-        cplx<T> val;
-        if (d.mode == EPI_COMPLEX) val = a;
-        else if (d.mode == EPI_POWER) val = mk<T>(a.x * a.x + a.y * a.y, 0);
-        else {
-            cplx<T> g = in2[src];
-            if (cj) g.y = -g.y;
-            val = cmulc(a, g);
+        const long i = iv * VEC;
+        T re[VEC], im[VEC];
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+            cplx<T> x = a[k];
+            if (cj[k]) x.y = -x.y;
+            cplx<T> val;
+            if (d.mode == EPI_COMPLEX) val = x;
+            else if (d.mode == EPI_POWER) val = mk<T>(x.x * x.x + x.y * x.y, 0);
+            else {
+                cplx<T> y = g[k];
+                if (cj[k]) y.y = -y.y;
+                val = cmulc(x, y);
+            }
+            if (d.ramp[0]) val = cmul(val, reinterpret_cast<const cplx<T>*>(d.ramp[0])[f0]);
+            if (d.ramp[1]) val = cmul(val, reinterpret_cast<const cplx<T>*>(d.ramp[1])[f1]);
+            if (d.ramp[2]) val = cmul(val, reinterpret_cast<const cplx<T>*>(d.ramp[2])[f2[k]]);
+            T sc = (T)d.scale;
+            if (d.weight) sc *= reinterpret_cast<const T*>(d.weight)[f2[k]];
+            val = cscale(val, sc);
+            if constexpr (VEC == 1) {
+                if (d.seg_n > 0) {
+                    // segment mean as an epilogue reduction: the per-segment spectra are never written; every value is added
+                    // (already divided by the number of segments) to the cell of the reduced array
+                    const long span = d.seg_n * d.seg_inner;
+                    const long outer = b / span;
+                    const long ob = outer * d.seg_inner + (b - outer * span) % d.seg_inner;
+                    const long oi = ((ob * d.k0 + o0) * d.k1 + o1) * d.W + gi.i2;
+                    if (d.mode == EPI_POWER) atomicAdd(reinterpret_cast<T*>(out) + oi, val.x);
+                    else { atomicAdd(reinterpret_cast<T*>(out) + 2 * oi, val.x); atomicAdd(reinterpret_cast<T*>(out) + 2 * oi + 1, val.y); }
+                    continue;
+                }
+            }
+            re[k] = val.x; im[k] = val.y;
+            if (d.mode == EPI_PHASE) re[k] = xatan2(val.y, val.x);
         }
-        if (d.ramp[0]) val = cmul(val, reinterpret_cast<const cplx<T>*>(d.ramp[0])[f0]);
-        if (d.ramp[1]) val = cmul(val, reinterpret_cast<const cplx<T>*>(d.ramp[1])[f1]);
-        if (d.ramp[2]) val = cmul(val, reinterpret_cast<const cplx<T>*>(d.ramp[2])[f2]);
-        T sc = (T)d.scale;
-        if (d.weight) sc *= reinterpret_cast<const T*>(d.weight)[f2];
-        val = cscale(val, sc);
-        if (d.seg_n > 0) {
-            // segment mean as an epilogue reduction: the per-segment spectra are never written; every value is added (already
-            // divided by the number of segments) to the cell of the reduced array
-            const long span = d.seg_n * d.seg_inner;
-            const long outer = b / span;
-            const long ob = outer * d.seg_inner + (b - outer * span) % d.seg_inner;
-            const long oi = ((ob * d.k0 + o0) * d.k1 + o1) * d.W + o2;
-            if (d.mode == EPI_POWER) atomicAdd(reinterpret_cast<T*>(out) + oi, val.x);
-            else { atomicAdd(reinterpret_cast<T*>(out) + 2 * oi, val.x); atomicAdd(reinterpret_cast<T*>(out) + 2 * oi + 1, val.y); }
-            continue;
+        if constexpr (VEC == 1) {
+            if (d.seg_n > 0) continue;
+            if (d.mode == EPI_COMPLEX || d.mode == EPI_CROSS) reinterpret_cast<cplx<T>*>(out)[i] = mk<T>(re[0], im[0]);
+            else reinterpret_cast<T*>(out)[i] = re[0];
+        } else {
+            if (d.mode == EPI_COMPLEX || d.mode == EPI_CROSS) {
+                T lo[4] = {re[0], im[0], re[1], im[1]}, hi[4] = {re[2], im[2], re[3], im[3]};
+                store_vec4(reinterpret_cast<T*>(out) + 2 * i, lo);
+                store_vec4(reinterpret_cast<T*>(out) + 2 * i + 4, hi);
+            } else {
+                store_vec4(reinterpret_cast<T*>(out) + i, re);
+            }
         }
-        if (d.mode == EPI_COMPLEX || d.mode == EPI_CROSS) reinterpret_cast<cplx<T>*>(out)[i] = val;
-        else if (d.mode == EPI_POWER) reinterpret_cast<T*>(out)[i] = val.x;
-        else reinterpret_cast<T*>(out)[i] = xatan2(val.y, val.x);
     }
 }
 
@@ -1698,13 +1750,17 @@ int xrftb_detrend_window(const void* in, void* out, const double* moments, int d
     if (!in || !out || (detrend && !moments)) { set_error("detrend_window: bad arguments"); return XRFTB_EINVAL; }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const long total = batch * n0 * n1 * n2;
-    if (dtype == XRFTB_F32)
-        detrend_window_kernel<float><<<ew_grid(total), 256, 0, st>>>(reinterpret_cast<const float*>(in), reinterpret_cast<float*>(out), moments, detrend,
+    // four elements of the last axis per thread when its rows keep the 16-byte alignment of the vector accesses
+    const bool vec = n2 % 4 == 0 && ((uintptr_t)in % 16) == 0 && ((uintptr_t)out % 16) == 0;
+    if (dtype == XRFTB_F32) {
+        auto k = vec ? detrend_window_kernel<float, 4> : detrend_window_kernel<float, 1>;
+        k<<<ew_grid(vec ? total / 4 : total), 256, 0, st>>>(reinterpret_cast<const float*>(in), reinterpret_cast<float*>(out), moments, detrend,
             reinterpret_cast<const float*>(w0), reinterpret_cast<const float*>(w1), reinterpret_cast<const float*>(w2), n0, n1, n2, total);
-    else if (dtype == XRFTB_F64)
-        detrend_window_kernel<double><<<ew_grid(total), 256, 0, st>>>(reinterpret_cast<const double*>(in), reinterpret_cast<double*>(out), moments, detrend,
+    } else if (dtype == XRFTB_F64) {
+        auto k = vec ? detrend_window_kernel<double, 4> : detrend_window_kernel<double, 1>;
+        k<<<ew_grid(vec ? total / 4 : total), 256, 0, st>>>(reinterpret_cast<const double*>(in), reinterpret_cast<double*>(out), moments, detrend,
             reinterpret_cast<const double*>(w0), reinterpret_cast<const double*>(w1), reinterpret_cast<const double*>(w2), n0, n1, n2, total);
-    else { set_error("detrend_window: bad dtype"); return XRFTB_EINVAL; }
+    } else { set_error("detrend_window: bad dtype"); return XRFTB_EINVAL; }
     return check_launch("detrend_window_kernel");
 }
 
@@ -1731,10 +1787,14 @@ static int spectral_post_launch(const void* in1, const void* in2, void* out, int
         if (e != cudaSuccess) { set_error("memset: %s", cudaGetErrorString(e)); return XRFTB_ECUDA; }
     }
     const long total = batch * k0 * k1 * d.W;
-    if (dtype == XRFTB_F32)
-        spectral_post_kernel<float><<<ew_grid(total), 256, 0, st>>>(reinterpret_cast<const float2*>(in1), reinterpret_cast<const float2*>(in2), out, d, total);
-    else
-        spectral_post_kernel<double><<<ew_grid(total), 256, 0, st>>>(reinterpret_cast<const double2*>(in1), reinterpret_cast<const double2*>(in2), out, d, total);
+    const bool vec = d.W % 4 == 0 && d.seg_n == 0 && ((uintptr_t)out % 16) == 0;   // four outputs of a row per thread
+    if (dtype == XRFTB_F32) {
+        auto k = vec ? spectral_post_kernel<float, 4> : spectral_post_kernel<float, 1>;
+        k<<<ew_grid(vec ? total / 4 : total), 256, 0, st>>>(reinterpret_cast<const float2*>(in1), reinterpret_cast<const float2*>(in2), out, d, total);
+    } else {
+        auto k = vec ? spectral_post_kernel<double, 4> : spectral_post_kernel<double, 1>;
+        k<<<ew_grid(vec ? total / 4 : total), 256, 0, st>>>(reinterpret_cast<const double2*>(in1), reinterpret_cast<const double2*>(in2), out, d, total);
+    }
     return check_launch("spectral_post_kernel");
 }
 
