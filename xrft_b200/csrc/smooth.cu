@@ -151,7 +151,7 @@ __device__ __forceinline__ void smooth_pass(const cplx<T>* __restrict__ src, cpl
         if (Ns > 1) {
             const int ti = jm * step;
 #pragma unroll
-            for (int t = 1; t < R; ++t) v[t] = cmul(v[t], __ldg(tw + t * ti));
+            for (int t = 1; t < R; ++t) v[t] = cmul(v[t], tw[t * ti]);   // (tw: the CTA's shared-memory copy for short lengths, else global)
         }
         dft_any<T, R>(v, w9, w25);
         cplx<T>* pd = dst + c * sc + ((j - jm) * R + jm) * sp;
@@ -163,7 +163,7 @@ __device__ __forceinline__ void smooth_pass(const cplx<T>* __restrict__ src, cpl
 template <typename T>
 __global__ void __launch_bounds__(256, 2) smooth_c2c_kernel(const cplx<T>* __restrict__ in, cplx<T>* __restrict__ out, const cplx<T>* __restrict__ tw,
                                                          long A, int n, long B, int C, int contig, int inverse, T scale, const __grid_constant__ SmoothPlan plan,
-                                                         long ntiles, long tiles_per_item, int real_mode, const cplx<T>* __restrict__ twN) {
+                                                         long ntiles, long tiles_per_item, int real_mode, const cplx<T>* __restrict__ twN, int tw_smem) {
     extern __shared__ __align__(16) unsigned char smooth_smem[];
     __shared__ cplx<T> w9[9], w25[25];   // internal factors of the composite radices, from the length-n table (9 | n, 25 | n)
     if (n % 9 == 0 && threadIdx.x < 9) w9[threadIdx.x] = __ldg(tw + threadIdx.x * (n / 9));
@@ -172,6 +172,14 @@ __global__ void __launch_bounds__(256, 2) smooth_c2c_kernel(const cplx<T>* __res
     const int sp = contig ? 1 : C, sc = contig ? n + 1 : 1;
     const int tile_elems = contig ? C * (n + 1) : n * C;
     cplx<T>* buf1 = buf0 + tile_elems;
+    // short lengths: the butterflies read their twiddles from a copy of the table in shared memory (a global load per factor
+    // and butterfly is a full L2 round trip in a kernel with two butterflies per thread and pass)
+    const cplx<T>* twp = tw;
+    if (tw_smem) {
+        cplx<T>* tws = buf1 + tile_elems;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) tws[i] = __ldg(tw + i);
+        twp = tws;   // published by the barrier behind the first tile's loads
+    }
     for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         // ---- load (the inverse transform is the conjugate of the forward transform of the conjugate)
         long a0 = 0, b0 = 0;
@@ -224,17 +232,17 @@ __global__ void __launch_bounds__(256, 2) smooth_c2c_kernel(const cplx<T>* __res
         for (int f = 0; f < plan.nfac; ++f) {
             const int R = plan.radix[f];
             switch (R) {
-                case 2: smooth_pass<T, 2>(src, dst, tw, n, Ns, cc, contig, sp, sc, w9, w25); break;
-                case 3: smooth_pass<T, 3>(src, dst, tw, n, Ns, cc, contig, sp, sc, w9, w25); break;
-                case 4: smooth_pass<T, 4>(src, dst, tw, n, Ns, cc, contig, sp, sc, w9, w25); break;
-                case 5: smooth_pass<T, 5>(src, dst, tw, n, Ns, cc, contig, sp, sc, w9, w25); break;
-                case 7: smooth_pass<T, 7>(src, dst, tw, n, Ns, cc, contig, sp, sc, w9, w25); break;
-                case 8: smooth_pass<T, 8>(src, dst, tw, n, Ns, cc, contig, sp, sc, w9, w25); break;
-                case 9: smooth_pass<T, 9>(src, dst, tw, n, Ns, cc, contig, sp, sc, w9, w25); break;
+                case 2: smooth_pass<T, 2>(src, dst, twp, n, Ns, cc, contig, sp, sc, w9, w25); break;
+                case 3: smooth_pass<T, 3>(src, dst, twp, n, Ns, cc, contig, sp, sc, w9, w25); break;
+                case 4: smooth_pass<T, 4>(src, dst, twp, n, Ns, cc, contig, sp, sc, w9, w25); break;
+                case 5: smooth_pass<T, 5>(src, dst, twp, n, Ns, cc, contig, sp, sc, w9, w25); break;
+                case 7: smooth_pass<T, 7>(src, dst, twp, n, Ns, cc, contig, sp, sc, w9, w25); break;
+                case 8: smooth_pass<T, 8>(src, dst, twp, n, Ns, cc, contig, sp, sc, w9, w25); break;
+                case 9: smooth_pass<T, 9>(src, dst, twp, n, Ns, cc, contig, sp, sc, w9, w25); break;
                 default:
                     if constexpr (sizeof(T) == 4) {
-                        if (R == 16) smooth_pass<T, 16>(src, dst, tw, n, Ns, cc, contig, sp, sc, w9, w25);
-                        else smooth_pass<T, 25>(src, dst, tw, n, Ns, cc, contig, sp, sc, w9, w25);
+                        if (R == 16) smooth_pass<T, 16>(src, dst, twp, n, Ns, cc, contig, sp, sc, w9, w25);
+                        else smooth_pass<T, 25>(src, dst, twp, n, Ns, cc, contig, sp, sc, w9, w25);
                     }
                     break;
             }
@@ -356,7 +364,8 @@ int smooth_launch(const cplx<T>* src, cplx<T>* dst, long A, long n, long B, int 
     const long tiles_per_item = contig ? 1 : (B + C - 1) / C;
     const long ntiles = contig ? (A + C - 1) / C : A * tiles_per_item;
     const size_t tile_elems = contig ? (size_t)C * (n + 1) : (size_t)n * C;
-    const size_t smem = 2 * tile_elems * sizeof(cplx<T>);
+    const int tw_smem = (size_t)n * sizeof(cplx<T>) <= 16384 ? 1 : 0;   // table copy in shared memory for short lengths
+    const size_t smem = 2 * tile_elems * sizeof(cplx<T>) + (tw_smem ? (size_t)n * sizeof(cplx<T>) : 0);
     if (smem > (size_t)kSmoothMaxDynSmem) { set_error("smooth_c2c: tile of length %ld does not fit shared memory", n); return XRFTB_EUNSUPPORTED; }
     const cplx<T>* tw = smooth_table<T>(n);
     if (!tw) return XRFTB_ECUDA;
@@ -377,7 +386,7 @@ int smooth_launch(const cplx<T>* src, cplx<T>* dst, long A, long n, long B, int 
     long grid = (long)sm_count() * 4;
     if (grid > ntiles) grid = ntiles;
     kern<<<(unsigned)grid, 256, smem, st>>>(src, dst, tw, A, (int)n, B, (int)C, contig ? 1 : 0, inverse ? 1 : 0, scale, plan, ntiles, tiles_per_item,
-                                            real_mode, twN);
+                                            real_mode, twN, tw_smem);
     return check_launch("smooth_c2c_kernel");
 }
 }  // namespace
