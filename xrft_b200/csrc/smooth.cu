@@ -164,6 +164,7 @@ template <typename T>
 __global__ void __launch_bounds__(256, 2) smooth_c2c_kernel(const cplx<T>* __restrict__ in, cplx<T>* __restrict__ out, const cplx<T>* __restrict__ tw,
                                                          long A, int n, long B, int C, int contig, int inverse, T scale, const __grid_constant__ SmoothPlan plan,
                                                          long ntiles, long tiles_per_item, int real_mode, const cplx<T>* __restrict__ twN, int tw_smem) {
+    constexpr int kLoadAhead = 4;   // independent global loads per thread in the tile-load loops
     extern __shared__ __align__(16) unsigned char smooth_smem[];
     __shared__ cplx<T> w9[9], w25[25];   // internal factors of the composite radices, from the length-n table (9 | n, 25 | n)
     if (n % 9 == 0 && threadIdx.x < 9) w9[threadIdx.x] = __ldg(tw + threadIdx.x * (n / 9));
@@ -193,22 +194,50 @@ __global__ void __launch_bounds__(256, 2) smooth_c2c_kernel(const cplx<T>* __res
                 // (the imaginary parts of X[0] and X[n] are ignored, like numpy's irfft)
                 const cplx<T>* p = in + a0 * (long)(n + 1);
                 const float inv_n = 1.0f / (float)n;
-                for (int e = threadIdx.x; e < nc * n; e += blockDim.x) {
-                    const int c = fdiv(e, inv_n), k = e - c * n;
-                    cplx<T> xk = p[(long)c * (n + 1) + k], xm = p[(long)c * (n + 1) + (n - k)];
-                    if (k == 0) { xk.y = (T)0; xm.y = (T)0; }
-                    const cplx<T> ev = mk<T>((T)0.5 * (xk.x + xm.x), (T)0.5 * (xk.y - xm.y));
-                    const cplx<T> dv = mk<T>((T)0.5 * (xk.x - xm.x), (T)0.5 * (xk.y + xm.y));
-                    const cplx<T> od = cmulc(dv, __ldg(twN + k));
-                    buf0[c * sc + k] = mk<T>(ev.x - od.y, -(ev.y + od.x));   // conj(Z): the inverse runs as a conjugated forward transform
+                const int tot = nc * n;
+                for (int e0 = threadIdx.x; e0 < tot; e0 += blockDim.x * (kLoadAhead / 2)) {
+                    cplx<T> xa[kLoadAhead / 2], xb[kLoadAhead / 2], wv[kLoadAhead / 2];
+#pragma unroll
+                    for (int u = 0; u < kLoadAhead / 2; ++u) {
+                        const int e = e0 + u * blockDim.x;
+                        if (e < tot) {
+                            const int c = fdiv(e, inv_n), k = e - c * n;
+                            xa[u] = p[(long)c * (n + 1) + k]; xb[u] = p[(long)c * (n + 1) + (n - k)]; wv[u] = __ldg(twN + k);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < kLoadAhead / 2; ++u) {
+                        const int e = e0 + u * blockDim.x;
+                        if (e < tot) {
+                            const int c = fdiv(e, inv_n), k = e - c * n;
+                            cplx<T> xk = xa[u], xm = xb[u];
+                            if (k == 0) { xk.y = (T)0; xm.y = (T)0; }
+                            const cplx<T> ev = mk<T>((T)0.5 * (xk.x + xm.x), (T)0.5 * (xk.y - xm.y));
+                            const cplx<T> dv = mk<T>((T)0.5 * (xk.x - xm.x), (T)0.5 * (xk.y + xm.y));
+                            const cplx<T> od = cmulc(dv, wv[u]);
+                            buf0[c * sc + k] = mk<T>(ev.x - od.y, -(ev.y + od.x));   // conj(Z): the inverse runs as a conjugated forward transform
+                        }
+                    }
                 }
             } else {
+                // kLoadAhead independent loads in flight per thread (a load consumed right away costs one memory round trip per
+                // element: ncu showed 5.9 long-scoreboard stalls per issue and 1 TB/s before this)
                 const cplx<T>* p = in + a0 * n;
-                for (int e = threadIdx.x; e < nc * n; e += blockDim.x) {
-                    const int c = e / n, q = e - c * n;
-                    cplx<T> x = p[e];
-                    if (inverse) x.y = -x.y;
-                    buf0[c * sc + q] = x;
+                const int tot = nc * n;
+                const float inv_n = 1.0f / (float)n;
+                for (int e0 = threadIdx.x; e0 < tot; e0 += blockDim.x * kLoadAhead) {
+                    cplx<T> x[kLoadAhead];
+#pragma unroll
+                    for (int k = 0; k < kLoadAhead; ++k) { const int e = e0 + k * blockDim.x; if (e < tot) x[k] = p[e]; }
+#pragma unroll
+                    for (int k = 0; k < kLoadAhead; ++k) {
+                        const int e = e0 + k * blockDim.x;
+                        if (e < tot) {
+                            const int c = fdiv(e, inv_n), q = e - c * n;
+                            if (inverse) x[k].y = -x[k].y;
+                            buf0[c * sc + q] = x[k];
+                        }
+                    }
                 }
             }
         } else {
@@ -216,11 +245,21 @@ __global__ void __launch_bounds__(256, 2) smooth_c2c_kernel(const cplx<T>* __res
             b0 = (tile - a0 * tiles_per_item) * C;
             nc = (int)(B - b0 < C ? B - b0 : C);
             const cplx<T>* p = in + a0 * n * B + b0;
-            for (int e = threadIdx.x; e < n * C; e += blockDim.x) {
-                const int q = e / C, c = e - q * C;
-                cplx<T> x = mk<T>(0, 0);
-                if (c < nc) { x = p[q * B + c]; if (inverse) x.y = -x.y; }
-                buf0[e] = x;
+            const int tot = n * C;
+            const float inv_c = 1.0f / (float)C;
+            for (int e0 = threadIdx.x; e0 < tot; e0 += blockDim.x * kLoadAhead) {
+                cplx<T> x[kLoadAhead];
+#pragma unroll
+                for (int k = 0; k < kLoadAhead; ++k) {
+                    const int e = e0 + k * blockDim.x;
+                    x[k] = mk<T>(0, 0);
+                    if (e < tot) { const int q = fdiv(e, inv_c), c = e - q * C; if (c < nc) x[k] = p[(long)q * B + c]; }
+                }
+#pragma unroll
+                for (int k = 0; k < kLoadAhead; ++k) {
+                    const int e = e0 + k * blockDim.x;
+                    if (e < tot) { if (inverse) x[k].y = -x[k].y; buf0[e] = x[k]; }
+                }
             }
         }
         __syncthreads();
