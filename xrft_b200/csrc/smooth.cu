@@ -128,6 +128,18 @@ template <typename T, int R> __device__ __forceinline__ void dft_any(cplx<T>* v,
     else dft_r<T, R>(v);
 }
 
+// asynchronous global -> shared copy of one complex point (LDGSTS: no register staging, every copy of the tile in flight at once)
+__device__ __forceinline__ void cp_async_point(float2* dst, const float2* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_point(double2* dst, const double2* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 // floor(a / d) for 0 <= a < 2^20 through the float reciprocal inv = 1 / d: (a + 1/2) / d is at least 1 / (2 d) away from an
 // integer and the rounding error (a / d) 2^-23 stays below that for every quotient that occurs here (< 12800)
 __device__ __forceinline__ int fdiv(int a, float inv) { return __float2int_rd(((float)a + 0.5f) * inv); }
@@ -135,7 +147,7 @@ __device__ __forceinline__ int fdiv(int a, float inv) { return __float2int_rd(((
 // one Stockham pass of radix R over the whole tile: src -> dst (point stride sp, sequence stride sc)
 template <typename T, int R>
 __device__ __forceinline__ void smooth_pass(const cplx<T>* __restrict__ src, cplx<T>* __restrict__ dst, const cplx<T>* __restrict__ tw,
-                                            int n, int Ns, int C, bool contig, int sp, int sc, const cplx<T>* w9, const cplx<T>* w25) {
+                                            int n, int Ns, int C, bool contig, int sp, int sc, const cplx<T>* w9, const cplx<T>* w25, bool cj) {
     const int nb = n / R;              // butterflies per sequence
     const int step = nb / Ns;          // n / (Ns R): table stride of this pass
     const int work = nb * C;
@@ -148,6 +160,10 @@ __device__ __forceinline__ void smooth_pass(const cplx<T>* __restrict__ src, cpl
         cplx<T> v[R];
 #pragma unroll
         for (int t = 0; t < R; ++t) v[t] = ps[t * nb * sp];
+        if (cj) {   // first pass of an inverse transform whose tile was copied in unconjugated
+#pragma unroll
+            for (int t = 0; t < R; ++t) v[t].y = -v[t].y;
+        }
         if (Ns > 1) {
             const int ti = jm * step;
 #pragma unroll
@@ -164,7 +180,7 @@ template <typename T>
 __global__ void __launch_bounds__(256, 2) smooth_c2c_kernel(const cplx<T>* __restrict__ in, cplx<T>* __restrict__ out, const cplx<T>* __restrict__ tw,
                                                          long A, int n, long B, int C, int contig, int inverse, T scale, const __grid_constant__ SmoothPlan plan,
                                                          long ntiles, long tiles_per_item, int real_mode, const cplx<T>* __restrict__ twN, int tw_smem) {
-    constexpr int kLoadAhead = 4;   // independent global loads per thread in the tile-load loops
+    constexpr int kLoadAhead = sizeof(T) == 4 ? 8 : 4;   // C2R merge loop: kLoadAhead / 2 row pairs + twiddles in flight per thread
     extern __shared__ __align__(16) unsigned char smooth_smem[];
     __shared__ cplx<T> w9[9], w25[25];   // internal factors of the composite radices, from the length-n table (9 | n, 25 | n)
     if (n % 9 == 0 && threadIdx.x < 9) w9[threadIdx.x] = __ldg(tw + threadIdx.x * (n / 9));
@@ -220,25 +236,17 @@ __global__ void __launch_bounds__(256, 2) smooth_c2c_kernel(const cplx<T>* __res
                     }
                 }
             } else {
-                // kLoadAhead independent loads in flight per thread (a load consumed right away costs one memory round trip per
-                // element: ncu showed 5.9 long-scoreboard stalls per issue and 1 TB/s before this)
+                // asynchronous copies straight into the tile: every point of the tile in flight at once, no register staging (with one
+                // register load at a time ncu showed 52 % of the samples in long-scoreboard stalls of this loop and 1 TB/s); an
+                // inverse transform conjugates in its first pass instead
                 const cplx<T>* p = in + a0 * n;
                 const int tot = nc * n;
                 const float inv_n = 1.0f / (float)n;
-                for (int e0 = threadIdx.x; e0 < tot; e0 += blockDim.x * kLoadAhead) {
-                    cplx<T> x[kLoadAhead];
-#pragma unroll
-                    for (int k = 0; k < kLoadAhead; ++k) { const int e = e0 + k * blockDim.x; if (e < tot) x[k] = p[e]; }
-#pragma unroll
-                    for (int k = 0; k < kLoadAhead; ++k) {
-                        const int e = e0 + k * blockDim.x;
-                        if (e < tot) {
-                            const int c = fdiv(e, inv_n), q = e - c * n;
-                            if (inverse) x[k].y = -x[k].y;
-                            buf0[c * sc + q] = x[k];
-                        }
-                    }
+                for (int e = threadIdx.x; e < tot; e += blockDim.x) {
+                    const int c = fdiv(e, inv_n), q = e - c * n;
+                    cp_async_point(buf0 + c * sc + q, p + e);
                 }
+                cp_async_wait_all();
             }
         } else {
             a0 = tile / tiles_per_item;
@@ -247,23 +255,16 @@ __global__ void __launch_bounds__(256, 2) smooth_c2c_kernel(const cplx<T>* __res
             const cplx<T>* p = in + a0 * n * B + b0;
             const int tot = n * C;
             const float inv_c = 1.0f / (float)C;
-            for (int e0 = threadIdx.x; e0 < tot; e0 += blockDim.x * kLoadAhead) {
-                cplx<T> x[kLoadAhead];
-#pragma unroll
-                for (int k = 0; k < kLoadAhead; ++k) {
-                    const int e = e0 + k * blockDim.x;
-                    x[k] = mk<T>(0, 0);
-                    if (e < tot) { const int q = fdiv(e, inv_c), c = e - q * C; if (c < nc) x[k] = p[(long)q * B + c]; }
-                }
-#pragma unroll
-                for (int k = 0; k < kLoadAhead; ++k) {
-                    const int e = e0 + k * blockDim.x;
-                    if (e < tot) { if (inverse) x[k].y = -x[k].y; buf0[e] = x[k]; }
-                }
+            for (int e = threadIdx.x; e < tot; e += blockDim.x) {
+                const int q = fdiv(e, inv_c), c = e - q * C;
+                if (c < nc) cp_async_point(buf0 + e, p + (long)q * B + c);
+                else buf0[e] = mk<T>(0, 0);
             }
+            cp_async_wait_all();
         }
         __syncthreads();
         // ---- one pass per factor
+        const bool cj0 = inverse && real_mode != 2;   // (the C2R merge stores the conjugate itself)
         cplx<T>* src = buf0;
         cplx<T>* dst = buf1;
         int Ns = 1;
@@ -271,17 +272,17 @@ __global__ void __launch_bounds__(256, 2) smooth_c2c_kernel(const cplx<T>* __res
         for (int f = 0; f < plan.nfac; ++f) {
             const int R = plan.radix[f];
             switch (R) {
-                case 2: smooth_pass<T, 2>(src, dst, twp, n, Ns, cc, contig, sp, sc, w9, w25); break;
-                case 3: smooth_pass<T, 3>(src, dst, twp, n, Ns, cc, contig, sp, sc, w9, w25); break;
-                case 4: smooth_pass<T, 4>(src, dst, twp, n, Ns, cc, contig, sp, sc, w9, w25); break;
-                case 5: smooth_pass<T, 5>(src, dst, twp, n, Ns, cc, contig, sp, sc, w9, w25); break;
-                case 7: smooth_pass<T, 7>(src, dst, twp, n, Ns, cc, contig, sp, sc, w9, w25); break;
-                case 8: smooth_pass<T, 8>(src, dst, twp, n, Ns, cc, contig, sp, sc, w9, w25); break;
-                case 9: smooth_pass<T, 9>(src, dst, twp, n, Ns, cc, contig, sp, sc, w9, w25); break;
+                case 2: smooth_pass<T, 2>(src, dst, twp, n, Ns, cc, contig, sp, sc, w9, w25, cj0 && f == 0); break;
+                case 3: smooth_pass<T, 3>(src, dst, twp, n, Ns, cc, contig, sp, sc, w9, w25, cj0 && f == 0); break;
+                case 4: smooth_pass<T, 4>(src, dst, twp, n, Ns, cc, contig, sp, sc, w9, w25, cj0 && f == 0); break;
+                case 5: smooth_pass<T, 5>(src, dst, twp, n, Ns, cc, contig, sp, sc, w9, w25, cj0 && f == 0); break;
+                case 7: smooth_pass<T, 7>(src, dst, twp, n, Ns, cc, contig, sp, sc, w9, w25, cj0 && f == 0); break;
+                case 8: smooth_pass<T, 8>(src, dst, twp, n, Ns, cc, contig, sp, sc, w9, w25, cj0 && f == 0); break;
+                case 9: smooth_pass<T, 9>(src, dst, twp, n, Ns, cc, contig, sp, sc, w9, w25, cj0 && f == 0); break;
                 default:
                     if constexpr (sizeof(T) == 4) {
-                        if (R == 16) smooth_pass<T, 16>(src, dst, twp, n, Ns, cc, contig, sp, sc, w9, w25);
-                        else smooth_pass<T, 25>(src, dst, twp, n, Ns, cc, contig, sp, sc, w9, w25);
+                        if (R == 16) smooth_pass<T, 16>(src, dst, twp, n, Ns, cc, contig, sp, sc, w9, w25, cj0 && f == 0);
+                        else smooth_pass<T, 25>(src, dst, twp, n, Ns, cc, contig, sp, sc, w9, w25, cj0 && f == 0);
                     }
                     break;
             }
