@@ -618,15 +618,32 @@ __global__ void __launch_bounds__(256) binned_sum_kernel(const T* __restrict__ a
         for (int i = threadIdx.x; i < nbins * width; i += blockDim.x) hist[i] = 0.0;
         __syncthreads();
         const T* p = arr + b * ncell * width;
-        for (long i = c0 + threadIdx.x; i < c1; i += blockDim.x) {
-            const int bin = lut[i];
-            if (bin < 0) continue;
-            if (CPLX) {
-                atomicAdd(&hist[2 * bin], (double)p[2 * i]);
-                atomicAdd(&hist[2 * bin + 1], (double)p[2 * i + 1]);
-            } else {
-                atomicAdd(&hist[bin], (double)p[i]);
+        // Every thread takes RUN consecutive cells: their loads are independent (RUN in flight), neighbouring cells mostly share
+        // the radial bin, so a thread adds up runs of equal bins in registers and pays one shared-memory atomic per run
+        // (fp64 atomics on shared memory are compare-and-swap loops: one per cell was the cost of this kernel)
+        constexpr int RUN = 8;
+        for (long i0 = c0 + (long)threadIdx.x * RUN; i0 < c1; i0 += (long)blockDim.x * RUN) {
+            int bins_[RUN];
+            T re[RUN], im[RUN];
+#pragma unroll
+            for (int k = 0; k < RUN; ++k) {
+                const long i = i0 + k;
+                const bool ok = i < c1;
+                bins_[k] = ok ? lut[i] : -1;
+                re[k] = ok ? p[width * i] : (T)0;
+                im[k] = (CPLX && ok) ? p[width * i + 1] : (T)0;
             }
+            int cur = -1;
+            double ar = 0.0, ai = 0.0;
+#pragma unroll
+            for (int k = 0; k < RUN; ++k) {
+                if (bins_[k] != cur) {
+                    if (cur >= 0) { atomicAdd(&hist[width * cur], ar); if (CPLX) atomicAdd(&hist[2 * cur + 1], ai); }
+                    cur = bins_[k]; ar = 0.0; ai = 0.0;
+                }
+                ar += (double)re[k]; ai += (double)im[k];
+            }
+            if (cur >= 0) { atomicAdd(&hist[width * cur], ar); if (CPLX) atomicAdd(&hist[2 * cur + 1], ai); }
         }
         __syncthreads();
         for (int i = threadIdx.x; i < nbins * width; i += blockDim.x)
@@ -853,6 +870,35 @@ __global__ void __launch_bounds__(256) permute_kernel(const E* __restrict__ in, 
             if (a < d.ndim) { const long idx = r % d.out_n[a]; r /= d.out_n[a]; src += idx * d.in_stride[a]; }
         }
         out[i] = in[src];
+    }
+}
+
+// Permutations that collapse to a batched 2-D transpose out[b][q][p] = in[b][p][q] (the usual case: ONE block of axes moved
+// behind the others, e.g. dim="time" of a [time][y][x] array): 32 x 32 tiles through shared memory, reads along q and writes
+// along p both coalesced -- the generic gather above reads with a stride of Q elements.
+template <typename E>
+__global__ void __launch_bounds__(256) transpose_kernel(const E* __restrict__ in, E* __restrict__ out, long P, long Q, long tiles_p, long tiles_q, long ntiles) {
+    __shared__ E tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8 threads
+    for (long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const long tq = t % tiles_q, r = t / tiles_q;
+        const long tp = r % tiles_p, b = r / tiles_p;
+        const E* src = in + b * P * Q;
+        E* dst = out + b * P * Q;
+        const long q = tq * 32 + tx;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const long p_ = tp * 32 + ty + 8 * k;
+            if (p_ < P && q < Q) tile[ty + 8 * k][tx] = src[p_ * Q + q];
+        }
+        __syncthreads();
+        const long p2 = tp * 32 + tx;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const long q2 = tq * 32 + ty + 8 * k;
+            if (q2 < Q && p2 < P) dst[q2 * P + p2] = tile[tx][ty + 8 * k];
+        }
+        __syncthreads();
     }
 }
 
@@ -1890,6 +1936,29 @@ int xrftb_permute(const void* in, void* out, int elem_bytes, int ndim, const int
         if (flip && flip[p]) { d.in_off += (in_shape[p] - 1) * istride[p]; d.in_stride[a] = -istride[p]; }
     }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    {
+        // collapse output axes that are also adjacent in the input; [b][q][p] <- [b][p][q] without flips is a batched transpose
+        long on[6], is_[6];
+        int m = 0;
+        for (int a = 0; a < ndim; ++a) {
+            if (d.out_n[a] == 1) continue;
+            if (m > 0 && is_[m - 1] == d.in_stride[a] * d.out_n[a] && d.in_stride[a] > 0) { on[m - 1] *= d.out_n[a]; is_[m - 1] = d.in_stride[a]; }
+            else { on[m] = d.out_n[a]; is_[m] = d.in_stride[a]; ++m; }
+        }
+        long Bt = 1, Q = 0, P = 0;
+        bool tr = false;
+        if (d.in_off == 0 && m == 2 && is_[0] == 1 && is_[1] == on[0]) { Q = on[0]; P = on[1]; tr = true; }
+        else if (d.in_off == 0 && m == 3 && is_[1] == 1 && is_[2] == on[1] && is_[0] == on[1] * on[2]) { Bt = on[0]; Q = on[1]; P = on[2]; tr = true; }
+        if (tr && P >= 8 && Q >= 8) {
+            const long tp = (P + 31) / 32, tq = (Q + 31) / 32, nt = Bt * tp * tq;
+            const unsigned grid = (unsigned)(nt < (long)sm_count() * 32 ? nt : (long)sm_count() * 32);
+            if (elem_bytes == 4) transpose_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(in), reinterpret_cast<float*>(out), P, Q, tp, tq, nt);
+            else if (elem_bytes == 8) transpose_kernel<double><<<grid, 256, 0, st>>>(reinterpret_cast<const double*>(in), reinterpret_cast<double*>(out), P, Q, tp, tq, nt);
+            else if (elem_bytes == 16) transpose_kernel<double2><<<grid, 256, 0, st>>>(reinterpret_cast<const double2*>(in), reinterpret_cast<double2*>(out), P, Q, tp, tq, nt);
+            else { set_error("permute: element size %d unsupported (4, 8 or 16 bytes)", elem_bytes); return XRFTB_EINVAL; }
+            return check_launch("transpose_kernel");
+        }
+    }
     if (elem_bytes == 4) permute_kernel<float><<<ew_grid(total), 256, 0, st>>>(reinterpret_cast<const float*>(in), reinterpret_cast<float*>(out), d, total);
     else if (elem_bytes == 8) permute_kernel<double><<<ew_grid(total), 256, 0, st>>>(reinterpret_cast<const double*>(in), reinterpret_cast<double*>(out), d, total);
     else if (elem_bytes == 16) permute_kernel<double2><<<ew_grid(total), 256, 0, st>>>(reinterpret_cast<const double2*>(in), reinterpret_cast<double2*>(out), d, total);
