@@ -344,3 +344,16 @@ def test_permute_flip_kernel():
             got = B.permute_flip(torch.from_numpy(x).cuda(), perm, flips).cpu().numpy()
             ref = np.transpose(np.flip(x, axis=flips) if flips else x, perm)
             np.testing.assert_array_equal(got, ref)
+
+
+def test_permute_transpose_fast_path():
+    """permutations that collapse to a batched 2-D transpose (one block of axes moved behind the others: dim="time" of a
+    [time][y][x] array) take the tiled shared-memory kernel; sizes off the 32-multiples, all element sizes, with a batch axis"""
+    from xrft_b200 import backend as B
+    rng = np.random.default_rng(13)
+    for dt in (np.float32, np.float64, np.complex64, np.complex128):
+        for shape, perm in (((100, 37, 65), (1, 2, 0)), ((100, 37, 65), (2, 0, 1)), ((3, 70, 33, 45), (0, 2, 3, 1)), ((5, 129, 257), (0, 2, 1)),
+                            ((1024, 2048), (1, 0)), ((9, 16), (1, 0)), ((4, 3, 50), (0, 2, 1))):
+            x = rng.standard_normal(shape).astype(dt) if np.dtype(dt).kind != "c" else cplx(rng, shape, np.float32 if dt == np.complex64 else np.float64)
+            got = B.permute_flip(torch.from_numpy(x).cuda(), perm, ()).cpu().numpy()
+            np.testing.assert_array_equal(got, np.transpose(x, perm))
