@@ -87,7 +87,7 @@ int xrftb_spectrum2d_last_path(void);
  *                 the input's size when naxes > 1 (input is never modified).
  * Lengths: powers of two up to 2^14 (f32) / 2^13 (f64) on the contiguous axis (R2C/C2R: twice that) and
  * up to 8192 on strided axes run in one Stockham pass; longer powers of two (to 2^26) run the four-step
- * decomposition n = n1*n2 on the same kernels; any length <= 64 runs a direct DFT; lengths 2^a 3^b 5^c 7^d up to
+ * decomposition n = n1*n2 on the same kernels; non-smooth lengths <= 64 run a direct DFT; lengths 2^a 3^b 5^c 7^d up to
  * 12800 (f32) / 6400 (f64) run a mixed-radix shared-memory kernel (one pass); every other length runs Bluestein's
  * chirp-z on top of the power-of-two machinery.  `work` must hold xrftb_fftn_workspace(...) bytes
  * (0 for single-pass power-of-two C2C/R2C).  in == out is allowed for C2C. */

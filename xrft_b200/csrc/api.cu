@@ -670,12 +670,19 @@ __global__ void __launch_bounds__(256) binned_sum_global_kernel(const T* __restr
 
 // ------------------------------------------------------------------------------------------------
 // arbitrary lengths (the reference's tests use 10, 15, 19, 20, 30, 40, 100, 1000 ...)
-//   N <= kSmallDft : direct O(N^2) DFT, one thread per sequence, twiddles in shared memory
+//   N <= kSmallDft : direct O(N^2) DFT, one thread per sequence, twiddles in shared memory (non-smooth lengths, tiny strided axes)
 //   2^a 3^b 5^c 7^d: mixed-radix Stockham kernel in shared memory (smooth.cu), up to 12800 (float32) / 6400 (float64) points
 //   otherwise      : Bluestein chirp-z on top of the power-of-two passes (no cuFFT, no CPU fallback)
 // All operate on a [A][N][B] row-major view (FFT along the middle axis), in-place safe.
 // ------------------------------------------------------------------------------------------------
 constexpr int kSmallDft = 64;
+// Short smooth lengths run the mixed-radix kernel too, except on a strided axis with a handful of points or columns (its tiles
+// would be nearly empty there).  Measured (tools/probe_small.py): 400000 x 40 complex64 1.38 -> 0.11 ms, 200000 x 60 2.65 -> 0.10,
+// 100000 x 48 complex128 0.84 -> 0.07, rfft of 400000 x 40 float32 0.70 -> 0.08; 65536 x 12 x 20 (strided 12 x 11 columns) stays direct.
+template <typename T> static inline bool small_direct(long n, long B) {
+    return n <= kSmallDft && !(n >= 6 && smooth_len_ok<T>(n) && (B == 1 || (n >= 16 && B >= 16)));
+}
+template <typename T> static inline bool small_direct_real(long N) { return N <= kSmallDft && !(N >= 12 && smooth_real_ok<T>(N)); }
 
 // mode: 0 C2C forward, 1 C2C inverse (x scale), 2 R2C (real in, k <= N/2 out), 3 C2R (half in, real out, x scale)
 template <typename T>
@@ -1011,7 +1018,7 @@ static int c2c_pass(const cplx<T>* src, cplx<T>* dst, long A, long n, long B, in
         if (B == 1) return rows_c2c<T>(src, dst, l2, A, n, n, inverse, scale, st);
         return cols_c2c<T>(src, dst, l2, A, B, inverse, scale, st, hooks);
     }
-    if (n <= kSmallDft) {
+    if (small_direct<T>(n, B)) {
         const long nseq = A * B;
         dft_small_kernel<T><<<(unsigned)((nseq + 127) / 128 > 4096 ? 4096 : (nseq + 127) / 128), 128, 0, st>>>(src, dst, (int)n, A, B, inverse ? 1 : 0, scale);
         return check_launch("dft_small_kernel");
@@ -1159,7 +1166,7 @@ static int fftn_impl(const void* in, void* out, void* work, size_t work_bytes, i
             io.in = reinterpret_cast<const T*>(in); io.in_row_stride = N; io.logNy = 0; io.detrend = 0; io.moments = nullptr;
             io.wy = nullptr; io.wx = nullptr; io.out = dst; io.logC = -1; io.out_seq_stride = H;
             if (int rc = rows_r2c<T>(io, l2 - 1, nseq, st)) return rc;
-        } else if (N <= kSmallDft) {
+        } else if (small_direct_real<T>(N)) {
             dft_small_kernel<T><<<small_grid, 128, 0, st>>>(in, dst, (int)N, nseq, 1, 2, (T)1);
             if (int rc = check_launch("dft_small_kernel")) return rc;
         } else if (smooth_real_ok<T>(N)) {
@@ -1196,7 +1203,7 @@ static int fftn_impl(const void* in, void* out, void* work, size_t work_bytes, i
         }
     }
     if (fast_real) return rows_c2r<T>(src, H, reinterpret_cast<T*>(out), N, l2 - 1, nseq, inv_scale * (T)2, st);  // half-length inverse: 1/M = 2/N
-    if (N <= kSmallDft) {
+    if (small_direct_real<T>(N)) {
         dft_small_kernel<T><<<small_grid, 128, 0, st>>>(src, out, (int)N, nseq, 1, 3, inv_scale);
         return check_launch("dft_small_kernel");
     }
