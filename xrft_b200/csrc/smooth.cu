@@ -7,8 +7,12 @@
 //
 // One CTA transforms a tile of C sequences of the [A][n][B] view in shared memory, ping-ponging between two buffers: one
 // pass per factor r in {16, 8, 4, 2, 9, 3, 25, 5, 7}, one thread per radix-r butterfly (Stockham auto-sort: no bit reversal,
-// natural order out; 9 and 25 are 3 x 3 and 5 x 5 butterflies in registers).  Strided sequences (B > 1): the tile is C adjacent columns, stored [n][C] so that global and shared accesses run along
-// the columns.  Contiguous sequences (B == 1): the tile is C consecutive sequences, stored [C][n + 1].
+// natural order out; 9 and 25 are 3 x 3 and 5 x 5 butterflies in registers).  Strided sequences (B > 1): the tile is C adjacent
+// columns, stored [n][C] so that global and shared accesses run along the columns.  Contiguous sequences (B == 1): the tile is
+// C consecutive sequences, stored [C][n + 1].  Tiles arrive by asynchronous global -> shared copies (cp.async); an inverse
+// transform is the conjugate of the forward transform of the conjugate (conjugation in the first pass and in the stores).
+// Real transforms of even length N along the contiguous axis run as the packed transform of length N / 2 with the split of the
+// half spectrum in the stores (R2C) or its merge in the loads (C2R).  Lengths from 6 up to 12800 (float32) / 6400 (float64).
 #include <math.h>
 #include <map>
 #include <mutex>
